@@ -1,0 +1,129 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own importable modules.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python oracle/make_golden.py
+
+It imports, by path, the three leaf modules of the reference hot path
+  /root/reference/scalerl/algorithms/impala/vtrace.py
+  /root/reference/scalerl/algorithms/impala/loss_fn.py
+  /root/reference/scalerl/algorithms/utils/atari_model.py
+(the trainer module impala_atari.py itself cannot be imported: wrong import roots + gymnasium missing,
+SURVEY.md §0) and drives them with the statements of ImpalaTrainer.learn (impala_atari.py:288-346).
+Inputs are NOT stored: they are regenerated from seeds by oracle.impala_oracle.{init_params,
+synthetic_batch} (numpy RNG), so the fixtures stay a few KB.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import impala_oracle as O  # noqa: E402
+
+REF = '/root/reference/scalerl/algorithms'
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main():
+    torch.set_num_threads(8)
+    vtrace = _load('ref_vtrace', f'{REF}/impala/vtrace.py')
+    loss_fn = _load('ref_loss_fn', f'{REF}/impala/loss_fn.py')
+    atari_model = _load('ref_atari_model', f'{REF}/utils/atari_model.py')
+    out_dir = os.path.join(ROOT, 'tests', 'golden')
+    os.makedirs(out_dir, exist_ok=True)
+
+    # ---------------- V-trace known-answer vectors (vtrace.py:78-172) ----------------
+    vt = {}
+    cases = [(5, 3, 1.0, 1.0, 0), (20, 32, 1.0, 1.0, 1), (20, 7, None, None, 2), (33, 5, 2.0, 0.5, 3),
+             (100, 4, 1.0, 1.0, 4), (1, 1, 1.0, 1.0, 5), (64, 2, 1.0, None, 6)]
+    for i, (T, B, cr, cp, seed) in enumerate(cases):
+        rng = np.random.RandomState(seed)
+        log_rhos = (rng.randn(T, B) * 0.7).astype(np.float32)
+        discounts = ((rng.rand(T, B) > 0.1) * 0.99).astype(np.float32)
+        rewards = rng.randn(T, B).astype(np.float32)
+        values = rng.randn(T, B).astype(np.float32)
+        boot = rng.randn(B).astype(np.float32)
+        r = vtrace.from_importance_weights(torch.from_numpy(log_rhos), torch.from_numpy(discounts),
+                                           torch.from_numpy(rewards), torch.from_numpy(values),
+                                           torch.from_numpy(boot), clip_rho_threshold=cr, clip_pg_rho_threshold=cp)
+        vt[f'c{i}_meta'] = np.array([T, B, -1 if cr is None else cr, -1 if cp is None else cp, seed], dtype=np.float64)
+        for k, v in dict(log_rhos=log_rhos, discounts=discounts, rewards=rewards, values=values, boot=boot,
+                         vs=r.vs.numpy(), pg=r.pg_advantages.numpy()).items():
+            vt[f'c{i}_{k}'] = v
+    np.savez_compressed(os.path.join(out_dir, 'vtrace_cases.npz'), **vt)
+
+    # ---------------- whole learn() step through the reference modules ----------------
+    step_cases = [dict(name='t5b4a6', T=5, B=4, A=6, seed=0, reward_clipping='abs_one', steps=2),
+                  dict(name='t3b5a4', T=3, B=5, A=4, seed=1, reward_clipping='none', steps=1)]
+    for c in step_cases:
+        T, B, A = c['T'], c['B'], c['A']
+        hp = dict(O.DEFAULT_HP, reward_clipping=c['reward_clipping'])
+        params = O.init_params(A, seed=c['seed'])
+        model = atari_model.AtariNet((4, 84, 84), A, use_lstm=False)
+        model.load_state_dict(params)
+        model.train()
+        opt = torch.optim.RMSprop(model.parameters(), lr=hp['learning_rate'], momentum=hp['momentum'],
+                                  eps=hp['epsilon'], alpha=hp['alpha'])            # impala_atari.py:99-105
+        g = {}
+        for step in range(c['steps']):
+            batch = O.synthetic_batch(T, B, A, seed=c['seed'] * 10 + step)
+            torch.manual_seed(0)
+            learner_outputs, _ = model(batch, ())                                  # :289
+            bootstrap_value = learner_outputs['baseline'][-1]                      # :293
+            b1 = {k: t[1:] for k, t in batch.items()}                              # :296
+            lo = {k: t[:-1] for k, t in learner_outputs.items()}                   # :297-300
+            rewards = b1['reward']
+            clipped = torch.clamp(rewards, -1, 1) if hp['reward_clipping'] == 'abs_one' else rewards
+            discounts = (~b1['done']).float() * hp['discounting']                  # :308
+            vr = vtrace.from_logits(behavior_policy_logits=b1['policy_logits'],
+                                    target_policy_logits=lo['policy_logits'], actions=b1['action'],
+                                    discounts=discounts, rewards=clipped, values=lo['baseline'],
+                                    bootstrap_value=bootstrap_value)               # :310-318
+            pg_loss = loss_fn.compute_policy_gradient_loss(lo['policy_logits'], b1['action'], vr.pg_advantages)
+            baseline_loss = hp['baseline_cost'] * loss_fn.compute_baseline_loss(vr.vs - lo['baseline'])
+            entropy_loss = hp['entropy_cost'] * loss_fn.compute_entropy_loss(lo['policy_logits'])
+            total_loss = pg_loss + baseline_loss + entropy_loss                    # :330
+            opt.zero_grad()
+            total_loss.backward()                                                  # :343
+            grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+            gn = torch.nn.utils.clip_grad_norm_(model.parameters(), hp['max_grad_norm'])  # :344
+            opt.step()                                                             # :346
+            s = f's{step}_'
+            g[s + 'policy_logits'] = learner_outputs['policy_logits'].detach().numpy()
+            g[s + 'baseline'] = learner_outputs['baseline'].detach().numpy()
+            g[s + 'vs'] = vr.vs.numpy()
+            g[s + 'pg_advantages'] = vr.pg_advantages.numpy()
+            g[s + 'log_rhos'] = vr.log_rhos.detach().numpy()
+            g[s + 'losses'] = np.array([pg_loss.item(), baseline_loss.item(), entropy_loss.item(), total_loss.item()])
+            g[s + 'grad_norm'] = np.array([float(gn)])
+            for k, v in grads.items():
+                flat = v.reshape(-1).double()
+                g[s + 'gradnorm_' + k] = np.array([float(flat.norm())])
+                g[s + 'gradsum_' + k] = np.array([float(flat.sum())])
+                g[s + 'gradhead_' + k] = v.reshape(-1)[:64].numpy().copy()
+                # a strided sample across the whole tensor
+                idx = torch.linspace(0, flat.numel() - 1, steps=min(257, flat.numel())).long()
+                g[s + 'gradsamp_' + k] = v.reshape(-1)[idx].numpy().copy()
+            for k, p in model.named_parameters():
+                flat = p.detach().reshape(-1)
+                idx = torch.linspace(0, flat.numel() - 1, steps=min(257, flat.numel())).long()
+                g[s + 'param_' + k] = flat[idx].numpy().copy()
+                g[s + 'paramsum_' + k] = np.array([float(flat.double().sum())])
+        g['meta'] = np.array([T, B, A, c['seed'], c['steps'], 1 if c['reward_clipping'] == 'abs_one' else 0])
+        np.savez_compressed(os.path.join(out_dir, f"learn_{c['name']}.npz"), **g)
+        print('wrote', c['name'], 'total_loss', float(total_loss))
+
+
+if __name__ == '__main__':
+    main()
