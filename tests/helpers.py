@@ -27,3 +27,14 @@ def assert_close(a, b, tol, name=''):
 def strided_sample(flat, n=257):
     idx = torch.linspace(0, flat.numel() - 1, steps=min(n, flat.numel())).long()
     return flat[idx]
+
+
+def rel_l2(a, b):
+    """||a-b||_2 / ||b||_2 -- robust to isolated ReLU-mask flips (bf16 vs fp32 comparisons)."""
+    if isinstance(a, torch.Tensor):
+        a = a.detach().float().cpu().numpy()
+    if isinstance(b, torch.Tensor):
+        b = b.detach().float().cpu().numpy()
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))

@@ -8,7 +8,7 @@ import torch
 
 from oracle import impala_oracle as O
 from tests.conftest import GOLDEN
-from tests.helpers import assert_close, strided_sample
+from tests.helpers import assert_close, rel_l2, strided_sample
 
 
 def _vt_cases():
@@ -96,7 +96,7 @@ def test_bf16_emulation_is_close_to_fp32():
     e = O.learn_step(dict(params), None, batch, update=False, emulate_bf16=True)
     assert_close(e['policy_logits'], a['policy_logits'], 2e-2, 'logits bf16')
     for k in O.PARAM_ORDER:
-        assert_close(e['grads'][k], a['grads'][k], 1e-1, k)
+        assert rel_l2(e['grads'][k], a['grads'][k]) < 5e-2, k
 
 
 def test_adam_step_matches_torch():
