@@ -1,0 +1,137 @@
+/* scalerl_b200 -- C ABI of the B200-native IMPALA learner hot path.
+ *
+ * The reference (jianzhnie/ScaleRL) is 100 % Python and has no FFI; the interface these entry points
+ * replace is the Python one of scalerl/algorithms/impala (file:line given per function).  A host
+ * binds them with ctypes (see INTEGRATION.md and scalerl_b200/_lib.py).  Plain pointers and sizes
+ * only -- no torch types.  Every pointer is a DEVICE pointer unless the name ends in `_host`.
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Return value: 0 on
+ * success, otherwise a cudaError_t (>0) or a negative SRL_E* argument error; srl_last_error()
+ * returns a message for the calling thread.  Nothing here synchronises the stream.
+ */
+#ifndef SCALERL_B200_H_
+#define SCALERL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRL_EINVAL (-1)   /* bad argument (shape / alignment / NULL) */
+#define SRL_ESTATE (-2)   /* call order violated */
+
+const char* srl_last_error(void);
+int srl_version(void);
+
+/* ---- V-trace -------------------------------------------------------------------------------------------
+ * replaces vtrace.from_importance_weights (scalerl/algorithms/impala/vtrace.py:78-172).
+ * log_rhos, discounts, rewards, values: f32 [T,B] row-major; bootstrap_value f32 [B]; outputs f32 [T,B].
+ * clip thresholds < 0 mean None (no clipping), as the Python API's clip_*=None.
+ * variant: 0 = column-sequential (float4 over B when B%4==0), 1 = warp-shuffle affine scan over T. */
+int srl_vtrace_from_importance_weights(const float* log_rhos, const float* discounts, const float* rewards,
+                                       const float* values, const float* bootstrap_value, int T, int B,
+                                       float clip_rho_threshold, float clip_pg_rho_threshold,
+                                       float* vs, float* pg_advantages, int variant, void* stream);
+
+/* replaces vtrace.from_logits (vtrace.py:43-75): logits f32 [T,B,A], actions i64 [T,B].
+ * Outputs (any may be NULL except vs/pg): vs, pg_advantages, log_rhos, behavior_alp, target_alp, all f32 [T,B]. */
+int srl_vtrace_from_logits(const float* behavior_policy_logits, const float* target_policy_logits,
+                           const int64_t* actions, const float* discounts, const float* rewards,
+                           const float* values, const float* bootstrap_value, int T, int B, int A,
+                           float clip_rho_threshold, float clip_pg_rho_threshold,
+                           float* vs, float* pg_advantages, float* log_rhos, float* behavior_action_log_probs,
+                           float* target_action_log_probs, void* stream);
+
+/* ---- fused learner tail: learn() pre-processing + V-trace + the three losses + head gradients ----------
+ * replaces impala_atari.py:293-330 + loss_fn.py:5-23 + the autograd step from total_loss to
+ * (policy_logits, baseline).  Inputs are the [T+1,B] batch rows as they lie in the trajectory batch
+ * (impala_atari.py:122-151): the kernel applies the [1:] / [:-1] shifts itself.
+ *   behavior_logits f32 [T+1,B,A] (batch['policy_logits']), target_logits f32 [T+1,B,A] and baseline f32 [T+1,B]
+ *   (learner outputs), action i64 [T+1,B], reward f32 [T+1,B], done u8/bool [T+1,B].
+ * Outputs: vs, pg_advantages f32 [T,B]; dlogits f32 [T,B,A]; dbaseline f32 [T,B];
+ *   losses f32 [4] = {pg_loss, baseline_loss (x baseline_cost), entropy_loss (x entropy_cost), total}.
+ * scratch: f32 [3*ceil(B/128)+4] workspace (block partials + ticket). */
+int srl_impala_loss_and_head_grads(const float* behavior_logits, const float* target_logits, const float* baseline,
+                                   const int64_t* action, const float* reward, const uint8_t* done,
+                                   int T, int B, int A, float discounting, int reward_clip_abs_one,
+                                   float clip_rho_threshold, float clip_pg_rho_threshold,
+                                   float baseline_cost, float entropy_cost,
+                                   float* vs, float* pg_advantages, float* dlogits, float* dbaseline,
+                                   float* losses, float* scratch, void* stream);
+
+/* ---- learner context: encoder fwd/bwd on tcgen05 + heads + optimizer ------------------------------------
+ * replaces AtariNet.forward (scalerl/algorithms/utils/atari_model.py:77-143, use_lstm=False) and
+ * ImpalaTrainer.learn (impala_atari.py:270-349) for one GPU's shard of the batch.                         */
+typedef struct srl_learner srl_learner_t;
+
+typedef struct srl_config {
+  int32_t T;                 /* rollout_length                                   */
+  int32_t B;                 /* batch columns processed by THIS GPU              */
+  int32_t A;                 /* num_actions (<= 32)                              */
+  int32_t optimizer;         /* 0 = RMSprop (reference, impala_atari.py:99-105), 1 = Adam */
+  int32_t reward_clip_abs_one;
+  int32_t simt_mainloop;     /* debug only: CUDA-core inner product instead of tcgen05 */
+  float discounting, baseline_cost, entropy_cost;
+  float clip_rho_threshold, clip_pg_rho_threshold;   /* < 0: None */
+  float max_grad_norm;       /* clip_grad_norm_ threshold (rl_args.py:108)       */
+  float learning_rate, alpha, epsilon;               /* RMSprop (rl_args.py:112-117) */
+  float adam_beta1, adam_beta2, adam_eps;
+} srl_config_t;
+
+/* Number of fp32 elements of the flat parameter buffer for A actions, and the element offset / count of
+ * each of the 12 AtariNet tensors in state_dict order (conv1.weight, conv1.bias, ..., baseline.bias),
+ * PyTorch layouts.  Segments are padded to multiples of 4 floats. offsets/counts: int64[12]. */
+int64_t srl_param_layout(int A, int64_t* offsets, int64_t* counts);
+
+/* params / grads / opt_state0 / opt_state1: flat f32 device buffers of srl_param_layout() elements, owned
+ * by the caller (so torch can expose state_dict views and NCCL can all-reduce `grads` in place).
+ * opt_state1 is only used by Adam (may be NULL for RMSprop). */
+int srl_learner_create(const srl_config_t* cfg, float* params, float* grads, float* opt_state0, float* opt_state1,
+                       srl_learner_t** out);
+int srl_learner_destroy(srl_learner_t* L);
+/* bytes of device workspace held by the context */
+int64_t srl_learner_workspace_bytes(const srl_learner_t* L);
+/* update a hyper-parameter that does not change buffer sizes (lr, costs, clip...) */
+int srl_learner_set_config(srl_learner_t* L, const srl_config_t* cfg);
+
+/* re-derive the packed bf16 operand copies from the fp32 master parameters (call after the caller wrote params) */
+int srl_learner_pack_weights(srl_learner_t* L, void* stream);
+
+/* AtariNet.forward for n_rows*B frames: obs u8 [rows,B,4,84,84], reward f32 [rows,B], action i64 [rows,B]
+ * -> policy_logits f32 [rows,B,A], baseline f32 [rows,B].  rows <= T+1. */
+int srl_learner_forward(srl_learner_t* L, const uint8_t* obs, const float* reward, const int64_t* action, int rows,
+                        float* policy_logits, float* baseline, void* stream);
+
+/* forward + V-trace + losses + full backward.  Leaves SUM-reduced gradients (loss_fn.py sums) in `grads`
+ * and {pg, baseline, entropy, total} in losses[4]; vs/pg_advantages (f32 [T,B]) may be NULL. */
+int srl_learner_forward_backward(srl_learner_t* L, const uint8_t* obs, const float* reward, const uint8_t* done,
+                                 const int64_t* action, const float* behavior_logits,
+                                 float* losses, float* vs, float* pg_advantages, void* stream);
+
+/* clip_grad_norm_(max_grad_norm) over `grads` (after the caller's all-reduce, if any) + optimizer step +
+ * weight re-pack.  grad_norm_out: f32 [2] = {total L2 norm, clip coefficient} (may be NULL). */
+int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_out, void* stream);
+
+/* borrow internal activations / operand copies for tests: name in {"a1","a2","a3","h","logits","baseline",
+ * "dlogits","dbaseline","dh","da3","da2","da1","wpack"}; returns device pointer + element count. */
+int srl_learner_debug_buffer(srl_learner_t* L, const char* name, void** ptr, int64_t* count);
+
+/* ---- stand-alone optimizer ops (flat f32 buffers of n elements) ------------------------------------------
+ * srl_grad_norm_clip_coef: coef[0] = ||g||_2, coef[1] = min(1, max_norm/(||g||+1e-6)); scratch f32[>=1028]. */
+int srl_grad_norm_clip_coef(const float* grads, int64_t n, float max_norm, float* coef, float* scratch, void* stream);
+int srl_rmsprop_step(float* params, const float* grads, float* square_avg, int64_t n, const float* coef,
+                     float lr, float alpha, float eps, void* stream);
+int srl_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* coef,
+                  float lr, float beta1, float beta2, float eps, int step, void* stream);
+
+/* ---- unit-test GEMMs for the tcgen05 mainloop (bf16 in, f32 out) -------------------------------------------
+ * kmajor : D[M,N] = A[M,K] . B[N,K]^T   (K%64==0, N%64==0)
+ * mnmajor: D[M,N] = At[K,M]^T . Bt[K,N] (M%128==0, N%64==0) */
+int srl_test_gemm_kmajor(const void* A, const void* B, float* D, int M, int N, int K, int simt, void* stream);
+int srl_test_gemm_mnmajor(const void* At, const void* Bt, float* D, int M, int N, int K, int simt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCALERL_B200_H_ */

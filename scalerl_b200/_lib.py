@@ -1,0 +1,83 @@
+"""ctypes binding of libscalerl_b200.so (the C ABI declared in include/scalerl_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing this module raises at import
+of the first op (build it with ``python -m scalerl_b200.build`` or ``__graft_entry__.build()``).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libscalerl_b200.so')
+
+_lib = None
+
+
+class SrlConfig(C.Structure):
+    """mirror of srl_config_t"""
+    _fields_ = [('T', C.c_int32), ('B', C.c_int32), ('A', C.c_int32), ('optimizer', C.c_int32),
+                ('reward_clip_abs_one', C.c_int32), ('simt_mainloop', C.c_int32),
+                ('discounting', C.c_float), ('baseline_cost', C.c_float), ('entropy_cost', C.c_float),
+                ('clip_rho_threshold', C.c_float), ('clip_pg_rho_threshold', C.c_float),
+                ('max_grad_norm', C.c_float), ('learning_rate', C.c_float), ('alpha', C.c_float), ('epsilon', C.c_float),
+                ('adam_beta1', C.c_float), ('adam_beta2', C.c_float), ('adam_eps', C.c_float)]
+
+
+_P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+# name -> argtypes; every function returns int except where noted
+_SIGS = {
+    'srl_vtrace_from_importance_weights': [_P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _I, _P],
+    'srl_vtrace_from_logits': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
+    'srl_impala_loss_and_head_grads': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P],
+    'srl_learner_create': [C.POINTER(SrlConfig), _P, _P, _P, _P, C.POINTER(_P)],
+    'srl_learner_destroy': [_P],
+    'srl_learner_set_config': [_P, C.POINTER(SrlConfig)],
+    'srl_learner_pack_weights': [_P, _P],
+    'srl_learner_forward': [_P, _P, _P, _P, _I, _P, _P, _P],
+    'srl_learner_forward_backward': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    'srl_learner_apply_gradients': [_P, _P, _P],
+    'srl_learner_debug_buffer': [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_L)],
+    'srl_grad_norm_clip_coef': [_P, _L, _F, _P, _P, _P],
+    'srl_rmsprop_step': [_P, _P, _P, _L, _P, _F, _F, _F, _P],
+    'srl_adam_step': [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _I, _P],
+    'srl_test_gemm_kmajor': [_P, _P, _P, _I, _I, _I, _I, _P],
+    'srl_test_gemm_mnmajor': [_P, _P, _P, _I, _I, _I, _I, _P],
+    'srl_version': [],
+}
+EXPORTS = sorted(list(_SIGS) + ['srl_last_error', 'srl_param_layout', 'srl_learner_workspace_bytes'])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} is missing: the CUDA library must be built (python -m scalerl_b200.build); '
+                               'scalerl_b200 has no CPU fallback')
+        L = C.CDLL(LIB_PATH)
+        for name, args in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        L.srl_last_error.restype = C.c_char_p
+        L.srl_last_error.argtypes = []
+        L.srl_param_layout.restype = C.c_int64
+        L.srl_param_layout.argtypes = [_I, C.POINTER(_L), C.POINTER(_L)]
+        L.srl_learner_workspace_bytes.restype = C.c_int64
+        L.srl_learner_workspace_bytes.argtypes = [_P]
+        _lib = L
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().srl_last_error().decode()
+        if rc == -1:
+            raise ValueError(f'{what}: {msg}')
+        raise RuntimeError(f'{what}: rc={rc}: {msg}')
+
+
+def param_layout(A):
+    off = (_L * 12)()
+    cnt = (_L * 12)()
+    total = lib().srl_param_layout(int(A), off, cnt)
+    return int(total), [int(x) for x in off], [int(x) for x in cnt]

@@ -1,0 +1,303 @@
+// extern "C" entry points (include/scalerl_b200.h).  Argument checking + the learner context that owns
+// the activation workspaces and sequences the kernels of one learner step on the caller's stream.
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include <new>
+
+#include "../../include/scalerl_b200.h"
+#include "kernels.h"
+
+using namespace srl;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return (int)e;
+}
+#define CU(x, what) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_, what); } while (0)
+#define REQ(c, ...) do { if (!(c)) return fail(SRL_EINVAL, __VA_ARGS__); } while (0)
+
+extern "C" const char* srl_last_error(void) { return g_err; }
+extern "C" int srl_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone ops
+// ------------------------------------------------------------------------------------------------
+extern "C" int srl_vtrace_from_importance_weights(const float* log_rhos, const float* discounts, const float* rewards,
+                                                  const float* values, const float* bootstrap_value, int T, int B,
+                                                  float clip_rho, float clip_pg, float* vs, float* pg, int variant, void* stream) {
+  REQ(T >= 0 && B >= 0, "vtrace: negative shape T=%d B=%d", T, B);
+  if (T == 0 || B == 0) return 0;
+  REQ(log_rhos && discounts && rewards && values && bootstrap_value && vs && pg, "vtrace: NULL pointer");
+  CU(launch_vtrace_iw(log_rhos, discounts, rewards, values, bootstrap_value, T, B, clip_rho, clip_pg, vs, pg, variant,
+                      (cudaStream_t)stream), "vtrace_from_importance_weights");
+  return 0;
+}
+
+extern "C" int srl_vtrace_from_logits(const float* bl, const float* tl, const int64_t* actions, const float* discounts,
+                                      const float* rewards, const float* values, const float* bootstrap_value, int T, int B, int A,
+                                      float clip_rho, float clip_pg, float* vs, float* pg, float* log_rhos, float* balp, float* talp,
+                                      void* stream) {
+  REQ(T >= 0 && B >= 0 && A >= 1, "vtrace_from_logits: bad shape T=%d B=%d A=%d", T, B, A);
+  if (T == 0 || B == 0) return 0;
+  REQ(bl && tl && actions && discounts && rewards && values && bootstrap_value && vs && pg, "vtrace_from_logits: NULL pointer");
+  CU(launch_vtrace_logits(bl, tl, actions, discounts, rewards, values, bootstrap_value, T, B, A, clip_rho, clip_pg, vs, pg, log_rhos,
+                          balp, talp, (cudaStream_t)stream), "vtrace_from_logits");
+  return 0;
+}
+
+extern "C" int srl_impala_loss_and_head_grads(const float* bl, const float* tl, const float* baseline, const int64_t* action,
+                                              const float* reward, const uint8_t* done, int T, int B, int A, float discounting,
+                                              int reward_clip_abs_one, float clip_rho, float clip_pg, float baseline_cost,
+                                              float entropy_cost, float* vs, float* pg, float* dlogits, float* dbaseline, float* losses,
+                                              float* scratch, void* stream) {
+  REQ(T >= 1 && B >= 1 && A >= 1, "impala_loss: bad shape T=%d B=%d A=%d", T, B, A);
+  REQ(bl && tl && baseline && action && reward && done && dlogits && dbaseline && losses && scratch, "impala_loss: NULL pointer");
+  CU(launch_impala_tail(bl, tl, baseline, action, reward, done, T, B, A, discounting, reward_clip_abs_one, clip_rho, clip_pg,
+                        baseline_cost, entropy_cost, vs, pg, dlogits, dbaseline, losses, scratch, (cudaStream_t)stream), "impala_tail");
+  return 0;
+}
+
+extern "C" int srl_grad_norm_clip_coef(const float* grads, int64_t n, float max_norm, float* coef, float* scratch, void* stream) {
+  REQ(grads && coef && scratch && n >= 0, "grad_norm: bad argument");
+  REQ((reinterpret_cast<uintptr_t>(grads) & 15) == 0, "grad_norm: grads must be 16-byte aligned");
+  CU(launch_grad_norm(grads, n, max_norm, coef, scratch, (cudaStream_t)stream), "grad_norm");
+  return 0;
+}
+extern "C" int srl_rmsprop_step(float* params, const float* grads, float* square_avg, int64_t n, const float* coef, float lr, float alpha,
+                                float eps, void* stream) {
+  REQ(params && grads && square_avg && n >= 0, "rmsprop: bad argument");
+  REQ(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(square_avg)) & 15) == 0,
+      "rmsprop: buffers must be 16-byte aligned");
+  CU(launch_rmsprop(params, grads, square_avg, n, coef, lr, alpha, eps, (cudaStream_t)stream), "rmsprop");
+  return 0;
+}
+extern "C" int srl_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* coef, float lr,
+                             float beta1, float beta2, float eps, int step, void* stream) {
+  REQ(params && grads && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "adam: bad argument");
+  CU(launch_adam(params, grads, exp_avg, exp_avg_sq, n, coef, lr, beta1, beta2, eps, step, (cudaStream_t)stream), "adam");
+  return 0;
+}
+
+extern "C" int srl_test_gemm_kmajor(const void* A, const void* B, float* D, int M, int N, int K, int simt, void* stream) {
+  REQ(A && B && D && M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 64 == 0, "test_gemm_kmajor: need K%%64==0, N%%64==0");
+  CU(test_gemm(A, B, D, M, N, K, false, simt != 0, (cudaStream_t)stream), "test_gemm_kmajor");
+  return 0;
+}
+extern "C" int srl_test_gemm_mnmajor(const void* At, const void* Bt, float* D, int M, int N, int K, int simt, void* stream) {
+  REQ(At && Bt && D && M > 0 && N > 0 && K > 0 && M % 128 == 0 && N % 64 == 0, "test_gemm_mnmajor: need M%%128==0, N%%64==0");
+  CU(test_gemm(At, Bt, D, M, N, K, true, simt != 0, (cudaStream_t)stream), "test_gemm_mnmajor");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameter layout
+// ------------------------------------------------------------------------------------------------
+static int64_t layout(int A, int64_t* off, int64_t* cnt) {
+  const int64_t core = 513 + A;
+  const int64_t counts[12] = {32 * 256, 32, 64 * 512, 64, 64 * 576, 64, 512 * 3136, 512, A * core, A, core, 1};
+  int64_t o = 0;
+  for (int i = 0; i < 12; ++i) {
+    if (off) off[i] = o;
+    if (cnt) cnt[i] = counts[i];
+    o += (counts[i] + 3) & ~int64_t(3);
+  }
+  return o;
+}
+extern "C" int64_t srl_param_layout(int A, int64_t* offsets, int64_t* counts) { return layout(A, offsets, counts); }
+
+static ParamPtrs make_ptrs(float* base, int A) {
+  int64_t off[12];
+  layout(A, off, nullptr);
+  ParamPtrs p;
+  p.w1 = base + off[0]; p.b1 = base + off[1]; p.w2 = base + off[2]; p.b2 = base + off[3]; p.w3 = base + off[4]; p.b3 = base + off[5];
+  p.wf = base + off[6]; p.bf = base + off[7]; p.wp = base + off[8]; p.bp = base + off[9]; p.wb = base + off[10]; p.bb = base + off[11];
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// learner context
+// ------------------------------------------------------------------------------------------------
+struct srl_learner {
+  srl_config_t cfg;
+  float *params, *grads, *opt0, *opt1;
+  int64_t nparams;
+  ParamPtrs P, G;
+  EncoderBuffers buf;
+  float *logits, *baseline;       // [NF][A], [NF]
+  float *dlogits, *dbaseline;     // [NB][A], [NB]
+  float *scratch;                 // reductions (tail + grad norm)
+  float *coef;                    // {norm, clip coef}
+  char* arena;
+  int64_t arena_bytes;
+  int step;                       // optimizer step count (Adam bias correction)
+  bool have_fwd;
+};
+
+static int check_cfg(const srl_config_t* c) {
+  REQ(c, "config is NULL");
+  REQ(c->T >= 1 && c->B >= 1, "config: T=%d B=%d must be >= 1", c->T, c->B);
+  REQ(c->A >= 1 && c->A <= 32, "config: A=%d must be in [1,32]", c->A);
+  REQ((int64_t)(c->T + 1) * c->B <= 65536, "config: (T+1)*B=%lld frames per GPU exceeds 65536", (long long)(c->T + 1) * c->B);
+  REQ(c->optimizer == 0 || c->optimizer == 1, "config: optimizer must be 0 (rmsprop) or 1 (adam)");
+  return 0;
+}
+
+extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float* grads, float* opt0, float* opt1, srl_learner_t** out) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  REQ(params && grads && opt0 && out, "learner_create: NULL buffer");
+  REQ(cfg->optimizer == 0 || opt1, "learner_create: Adam needs opt_state1");
+  REQ(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(opt0) |
+        reinterpret_cast<uintptr_t>(opt1)) & 15) == 0, "learner_create: flat buffers must be 16-byte aligned");
+  srl_learner* L = new (std::nothrow) srl_learner();
+  REQ(L, "out of host memory");
+  L->cfg = *cfg; L->params = params; L->grads = grads; L->opt0 = opt0; L->opt1 = opt1;
+  L->nparams = layout(cfg->A, nullptr, nullptr);
+  L->P = make_ptrs(params, cfg->A);
+  L->G = make_ptrs(grads, cfg->A);
+  L->step = 0; L->have_fwd = false;
+  const int64_t NF = (int64_t)(cfg->T + 1) * cfg->B, NB = (int64_t)cfg->T * cfg->B, A = cfg->A;
+  // carve one arena (256-byte aligned pieces)
+  int64_t sizes[16]; int k = 0;
+  auto al = [](int64_t b) { return (b + 255) & ~int64_t(255); };
+  sizes[k++] = al(NF * 400 * 32 * 2);   // a1
+  sizes[k++] = al(NF * 81 * 64 * 2);    // a2
+  sizes[k++] = al(NF * 49 * 64 * 2);    // a3
+  sizes[k++] = al(NF * 512 * 4);        // h
+  sizes[k++] = al(NB * 512 * 2);        // dh
+  sizes[k++] = al(NB * 49 * 64 * 2);    // da3
+  sizes[k++] = al(NB * 81 * 64 * 2);    // da2
+  sizes[k++] = al(NB * 400 * 32 * 2);   // da1
+  sizes[k++] = al(WPack::TOTAL * 2);    // wpack
+  sizes[k++] = al(NF * A * 4);          // logits
+  sizes[k++] = al(NF * 4);              // baseline
+  sizes[k++] = al(NB * A * 4);          // dlogits
+  sizes[k++] = al(NB * 4);              // dbaseline
+  sizes[k++] = al(4096 * 4);            // scratch
+  sizes[k++] = al(16);                  // coef
+  int64_t total = 0;
+  for (int i = 0; i < k; ++i) total += sizes[i];
+  cudaError_t e = cudaMalloc(&L->arena, total);
+  if (e != cudaSuccess) { delete L; return cuda_fail(e, "learner_create: cudaMalloc workspace"); }
+  e = cudaMemset(L->arena, 0, total);
+  if (e != cudaSuccess) { cudaFree(L->arena); delete L; return cuda_fail(e, "learner_create: cudaMemset"); }
+  L->arena_bytes = total;
+  char* q = L->arena; int i = 0;
+  L->buf.a1 = (__nv_bfloat16*)q; q += sizes[i++];
+  L->buf.a2 = (__nv_bfloat16*)q; q += sizes[i++];
+  L->buf.a3 = (__nv_bfloat16*)q; q += sizes[i++];
+  L->buf.h = (float*)q; q += sizes[i++];
+  L->buf.dh = (__nv_bfloat16*)q; q += sizes[i++];
+  L->buf.da3 = (__nv_bfloat16*)q; q += sizes[i++];
+  L->buf.da2 = (__nv_bfloat16*)q; q += sizes[i++];
+  L->buf.da1 = (__nv_bfloat16*)q; q += sizes[i++];
+  L->buf.wpack = (__nv_bfloat16*)q; q += sizes[i++];
+  L->logits = (float*)q; q += sizes[i++];
+  L->baseline = (float*)q; q += sizes[i++];
+  L->dlogits = (float*)q; q += sizes[i++];
+  L->dbaseline = (float*)q; q += sizes[i++];
+  L->scratch = (float*)q; q += sizes[i++];
+  L->coef = (float*)q; q += sizes[i++];
+  *out = L;
+  return 0;
+}
+
+extern "C" int srl_learner_destroy(srl_learner_t* L) {
+  if (!L) return 0;
+  cudaFree(L->arena);
+  delete L;
+  return 0;
+}
+extern "C" int64_t srl_learner_workspace_bytes(const srl_learner_t* L) { return L ? L->arena_bytes : 0; }
+
+extern "C" int srl_learner_set_config(srl_learner_t* L, const srl_config_t* cfg) {
+  REQ(L, "learner is NULL");
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  REQ(cfg->T == L->cfg.T && cfg->B == L->cfg.B && cfg->A == L->cfg.A && cfg->optimizer == L->cfg.optimizer,
+      "set_config: T/B/A/optimizer are fixed at creation");
+  L->cfg = *cfg;
+  return 0;
+}
+
+extern "C" int srl_learner_pack_weights(srl_learner_t* L, void* stream) {
+  REQ(L, "learner is NULL");
+  CU(launch_pack_weights(L->P, L->buf.wpack, (cudaStream_t)stream), "pack_weights");
+  return 0;
+}
+
+static int forward_impl(srl_learner* L, const uint8_t* obs, const float* reward, const int64_t* action, int frames, float* logits,
+                        float* baseline, cudaStream_t st) {
+  CU(encoder_forward(obs, frames, L->P, L->buf, L->cfg.simt_mainloop != 0, st), "encoder_forward");
+  CU(launch_head_fwd(L->buf.h, reward, action, L->P.wp, L->P.bp, L->P.wb, L->P.bb, frames, L->cfg.A, logits, baseline, st), "head_fwd");
+  return 0;
+}
+
+extern "C" int srl_learner_forward(srl_learner_t* L, const uint8_t* obs, const float* reward, const int64_t* action, int rows,
+                                   float* policy_logits, float* baseline, void* stream) {
+  REQ(L && obs && reward && action && policy_logits && baseline, "learner_forward: NULL pointer");
+  REQ(rows >= 1 && rows <= L->cfg.T + 1, "learner_forward: rows=%d must be in [1, T+1=%d]", rows, L->cfg.T + 1);
+  REQ((reinterpret_cast<uintptr_t>(obs) & 3) == 0, "learner_forward: obs must be 4-byte aligned");
+  return forward_impl(L, obs, reward, action, rows * L->cfg.B, policy_logits, baseline, (cudaStream_t)stream);
+}
+
+extern "C" int srl_learner_forward_backward(srl_learner_t* L, const uint8_t* obs, const float* reward, const uint8_t* done,
+                                            const int64_t* action, const float* behavior_logits, float* losses, float* vs,
+                                            float* pg_advantages, void* stream) {
+  REQ(L && obs && reward && done && action && behavior_logits && losses, "learner_forward_backward: NULL pointer");
+  REQ((reinterpret_cast<uintptr_t>(obs) & 3) == 0, "learner_forward_backward: obs must be 4-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const srl_config_t& c = L->cfg;
+  const int NF = (c.T + 1) * c.B, NB = c.T * c.B;
+  int rc = forward_impl(L, obs, reward, action, NF, L->logits, L->baseline, st);
+  if (rc) return rc;
+  CU(launch_impala_tail(behavior_logits, L->logits, L->baseline, action, reward, done, c.T, c.B, c.A, c.discounting,
+                        c.reward_clip_abs_one, c.clip_rho_threshold, c.clip_pg_rho_threshold, c.baseline_cost, c.entropy_cost, vs,
+                        pg_advantages, L->dlogits, L->dbaseline, losses, L->scratch, st), "impala_tail");
+  CU(cudaMemsetAsync(L->grads, 0, L->nparams * sizeof(float), st), "zero grads");
+  CU(launch_head_bwd(L->dlogits, L->dbaseline, L->buf.h, reward, action, L->P.wp, L->P.wb, NB, c.A, L->buf.dh, L->G.wp, L->G.bp, L->G.wb,
+                     L->G.bb, st), "head_bwd");
+  CU(encoder_backward(obs, NB, L->buf, L->G, c.simt_mainloop != 0, st), "encoder_backward");
+  L->have_fwd = true;
+  return 0;
+}
+
+extern "C" int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_out, void* stream) {
+  REQ(L, "learner is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const srl_config_t& c = L->cfg;
+  CU(launch_grad_norm(L->grads, L->nparams, c.max_grad_norm, L->coef, L->scratch + 2048, st), "grad_norm");
+  L->step += 1;
+  if (c.optimizer == 0) {
+    CU(launch_rmsprop(L->params, L->grads, L->opt0, L->nparams, L->coef, c.learning_rate, c.alpha, c.epsilon, st), "rmsprop");
+  } else {
+    CU(launch_adam(L->params, L->grads, L->opt0, L->opt1, L->nparams, L->coef, c.learning_rate, c.adam_beta1, c.adam_beta2, c.adam_eps,
+                   L->step, st), "adam");
+  }
+  CU(launch_pack_weights(L->P, L->buf.wpack, st), "pack_weights");
+  if (grad_norm_out) CU(cudaMemcpyAsync(grad_norm_out, L->coef, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy coef");
+  return 0;
+}
+
+extern "C" int srl_learner_debug_buffer(srl_learner_t* L, const char* name, void** ptr, int64_t* count) {
+  REQ(L && name && ptr && count, "debug_buffer: NULL argument");
+  const int64_t NF = (int64_t)(L->cfg.T + 1) * L->cfg.B, NB = (int64_t)L->cfg.T * L->cfg.B, A = L->cfg.A;
+  struct { const char* n; void* p; int64_t c; } tab[] = {
+      {"a1", L->buf.a1, NF * 400 * 32}, {"a2", L->buf.a2, NF * 81 * 64}, {"a3", L->buf.a3, NF * 49 * 64}, {"h", L->buf.h, NF * 512},
+      {"logits", L->logits, NF * A}, {"baseline", L->baseline, NF}, {"dlogits", L->dlogits, NB * A}, {"dbaseline", L->dbaseline, NB},
+      {"dh", L->buf.dh, NB * 512}, {"da3", L->buf.da3, NB * 49 * 64}, {"da2", L->buf.da2, NB * 81 * 64},
+      {"da1", L->buf.da1, NB * 400 * 32}, {"wpack", L->buf.wpack, WPack::TOTAL}};
+  for (auto& t : tab)
+    if (strcmp(t.n, name) == 0) { *ptr = t.p; *count = t.c; return 0; }
+  return fail(SRL_EINVAL, "debug_buffer: unknown buffer '%s'", name);
+}

@@ -1,0 +1,107 @@
+// Encoder forward / backward drivers: weight packing + the sequence of tcgen05 implicit-GEMM launches.
+#include "encoder_problems.cuh"
+#include "kernels.h"
+
+namespace srl {
+
+// fp32 master parameters (PyTorch layouts) -> bf16 operand copies in the layouts the GEMMs consume.
+__global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < WPack::TOTAL; i += (int64_t)gridDim.x * blockDim.x) {
+    float v;
+    if (i < WPack::W2K) {                       // w1k[co][k] = W1[co][c][kh][kw] flat
+      v = p.w1[i - WPack::W1K];
+    } else if (i < WPack::W3K) {                // w2k[co][(kh*4+kw)*32 + c]
+      const int e = (int)(i - WPack::W2K), co = e >> 9, k = e & 511, tap = k >> 5, c = k & 31;
+      v = p.w2[((co * 32 + c) << 4) + tap];
+    } else if (i < WPack::WFK) {                // w3k[co][(kh*3+kw)*64 + c]
+      const int e = (int)(i - WPack::W3K), co = e / 576, k = e - co * 576, tap = k >> 6, c = k & 63;
+      v = p.w3[(co * 64 + c) * 9 + tap];
+    } else if (i < WPack::WFD) {                // wfk[j][hw*64 + c] = Wfc[j][c*49 + hw]
+      const int e = (int)(i - WPack::WFK), j = e / 3136, k = e - j * 3136, hw = k >> 6, c = k & 63;
+      v = p.wf[(size_t)j * 3136 + c * 49 + hw];
+    } else if (i < WPack::W3D) {                // wfd[hw*64 + c][j]
+      const int e = (int)(i - WPack::WFD), row = e >> 9, j = e & 511, hw = row >> 6, c = row & 63;
+      v = p.wf[(size_t)j * 3136 + c * 49 + hw];
+    } else if (i < WPack::W2D) {                // w3d[c][(kh*3+kw)*64 + co]
+      const int e = (int)(i - WPack::W3D), c = e / 576, k = e - c * 576, tap = k >> 6, co = k & 63;
+      v = p.w3[(co * 64 + c) * 9 + tap];
+    } else {                                    // w2d[cls][c][(kh'*2+kw')*64 + co], kh = ph + 2kh', kw = pw + 2kw'
+      const int e = (int)(i - WPack::W2D), cls = e >> 13, r = e & 8191, c = r >> 8, k = r & 255, t = k >> 6, co = k & 63;
+      const int kh = (cls >> 1) + 2 * (t >> 1), kw = (cls & 1) + 2 * (t & 1);
+      v = p.w2[((co * 32 + c) << 4) + kh * 4 + kw];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+cudaError_t launch_pack_weights(const ParamPtrs& p, bf16* wpack, cudaStream_t st) {
+  pack_weights_kernel<<<1184, 256, 0, st>>>(p, wpack);
+  return cudaGetLastError();
+}
+
+#define SRL_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, bool simt, cudaStream_t st) {
+  if (frames <= 0) return cudaSuccess;
+  { Conv1Fwd::Params q{obs, buf.wpack + WPack::W1K, p.b1, buf.a1, frames * 400};
+    SRL_TRY(igemm_launch<Conv1Fwd>(q, dim3(cdiv(q.M, 128), 1), st, simt)); }
+  { Conv2Fwd::Params q{buf.a1, buf.wpack + WPack::W2K, p.b2, buf.a2, frames * 81};
+    SRL_TRY(igemm_launch<Conv2Fwd>(q, dim3(cdiv(q.M, 128), 1), st, simt)); }
+  { Conv3Fwd::Params q{buf.a2, buf.wpack + WPack::W3K, p.b3, buf.a3, frames * 49};
+    SRL_TRY(igemm_launch<Conv3Fwd>(q, dim3(cdiv(q.M, 128), 1), st, simt)); }
+  { FcFwd::Params q{buf.a3, buf.wpack + WPack::WFK, p.bf, buf.h, frames};
+    SRL_TRY(igemm_launch<FcFwd>(q, dim3(cdiv(q.M, 128), 8), st, simt)); }
+  return cudaSuccess;
+}
+
+// split the contraction range P into ~target CTAs' worth of 64-aligned pieces
+static inline void split_k(int P, int target, int* pps, int* nsplit) {
+  int per = cdiv(cdiv(P, 64), target) * 64;
+  if (per < 64) per = 64;
+  *pps = per;
+  *nsplit = cdiv(P, per);
+}
+
+cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, bool simt, cudaStream_t st) {
+  if (frames <= 0) return cudaSuccess;
+  int pps, ns;
+  // ---- fc: bias, wgrad, dgrad
+  SRL_TRY(launch_colsum_bf16(buf.dh, frames, 512, g.bf, st));
+  { FcWgrad::Params q{buf.dh, buf.a3, g.wf, frames};
+    SRL_TRY(igemm_launch<FcWgrad>(q, dim3(1, 4 * 49), st, simt)); }
+  { FcDgrad::Params q{buf.dh, buf.wpack + WPack::WFD, buf.a3, buf.da3, frames};
+    SRL_TRY(igemm_launch<FcDgrad>(q, dim3(cdiv(frames, 128), 49), st, simt)); }
+  // ---- conv3
+  SRL_TRY(launch_colsum_bf16(buf.da3, frames * 49, 64, g.b3, st));
+  { split_k(frames * 49, 29, &pps, &ns);
+    Conv3Wgrad::Params q{buf.a2, buf.da3, g.w3, frames * 49, pps};
+    SRL_TRY(igemm_launch<Conv3Wgrad>(q, dim3(ns, 5), st, simt)); }
+  { Conv3Dgrad::Params q{buf.da3, buf.wpack + WPack::W3D, buf.a2, buf.da2, frames * 81};
+    SRL_TRY(igemm_launch<Conv3Dgrad>(q, dim3(cdiv(q.M, 128), 1), st, simt)); }
+  // ---- conv2
+  SRL_TRY(launch_colsum_bf16(buf.da2, frames * 81, 64, g.b2, st));
+  { split_k(frames * 81, 37, &pps, &ns);
+    Conv2Wgrad::Params q{buf.a1, buf.da2, g.w2, frames * 81, pps};
+    SRL_TRY(igemm_launch<Conv2Wgrad>(q, dim3(ns, 4), st, simt)); }
+  { Conv2Dgrad::Params q{buf.da2, buf.wpack + WPack::W2D, buf.a1, buf.da1, frames * 100};
+    SRL_TRY(igemm_launch<Conv2Dgrad>(q, dim3(cdiv(q.M, 128), 4), st, simt)); }
+  // ---- conv1 (no dgrad: the frame is the network input)
+  SRL_TRY(launch_colsum_bf16(buf.da1, frames * 400, 32, g.b1, st));
+  { split_k(frames * 400, 74, &pps, &ns);
+    Conv1Wgrad::Params q{obs, buf.da1, g.w1, frames * 400, pps};
+    SRL_TRY(igemm_launch<Conv1Wgrad>(q, dim3(ns, 2), st, simt)); }
+  return cudaSuccess;
+}
+
+cudaError_t test_gemm(const void* A, const void* B, float* D, int M, int N, int K, bool mn_major, bool simt, cudaStream_t st) {
+  if (mn_major) {
+    TestGemmMN::Params q{(const bf16*)A, (const bf16*)B, D, M, N, K};
+    return igemm_launch<TestGemmMN>(q, dim3(M / 128, N / 64), st, simt);
+  }
+  TestGemmK::Params q{(const bf16*)A, (const bf16*)B, D, M, N, K};
+  return igemm_launch<TestGemmK>(q, dim3(cdiv(M, 128), N / 64), st, simt);
+}
+
+}  // namespace srl

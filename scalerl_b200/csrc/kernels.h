@@ -1,0 +1,62 @@
+// Internal launch prototypes shared by the .cu translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace srl {
+
+// ---- vtrace.cu
+cudaError_t launch_vtrace_iw(const float* log_rhos, const float* discounts, const float* rewards, const float* values,
+                             const float* bootstrap, int T, int B, float clip_rho, float clip_pg, float* vs, float* pg, int variant,
+                             cudaStream_t st);
+cudaError_t launch_vtrace_logits(const float* bl, const float* tl, const int64_t* actions, const float* discounts, const float* rewards,
+                                 const float* values, const float* bootstrap, int T, int B, int A, float clip_rho, float clip_pg,
+                                 float* vs, float* pg, float* lr, float* balp, float* talp, cudaStream_t st);
+cudaError_t launch_impala_tail(const float* bl, const float* tl, const float* baseline, const int64_t* action, const float* reward,
+                               const uint8_t* done, int T, int B, int A, float discounting, int clip_reward, float clip_rho,
+                               float clip_pg, float baseline_cost, float entropy_cost, float* vs, float* pg, float* dlogits,
+                               float* dbaseline, float* losses, float* scratch, cudaStream_t st);
+
+// ---- heads_optim.cu
+cudaError_t launch_head_fwd(const float* h, const float* reward, const int64_t* action, const float* Wp, const float* bp, const float* Wb,
+                            const float* bb, int N, int A, float* logits, float* baseline, cudaStream_t st);
+cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const float* h, const float* reward, const int64_t* action,
+                            const float* Wp, const float* Wb, int N, int A, __nv_bfloat16* dh, float* gWp, float* gbp, float* gWb,
+                            float* gbb, cudaStream_t st);
+cudaError_t launch_colsum_bf16(const __nv_bfloat16* dy, int M, int C, float* db, cudaStream_t st);
+cudaError_t launch_grad_norm(const float* g, int64_t n, float max_norm, float* coef, float* scratch, cudaStream_t st);
+cudaError_t launch_rmsprop(float* p, const float* g, float* v, int64_t n, const float* coef, float lr, float alpha, float eps,
+                           cudaStream_t st);
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* coef, float lr, float b1, float b2, float eps,
+                        int step, cudaStream_t st);
+
+// ---- encoder.cu
+// packed bf16 operand copies of the conv/fc weights (element offsets into one buffer)
+struct WPack {
+  static constexpr int64_t W1K = 0;                       // [32][256]            k = (c,kh,kw)  (PyTorch order)
+  static constexpr int64_t W2K = W1K + 32 * 256;          // [64][512]            k = (kh,kw,c)
+  static constexpr int64_t W3K = W2K + 64 * 512;          // [64][576]            k = (kh,kw,c)
+  static constexpr int64_t WFK = W3K + 64 * 576;          // [512][3136]          k = (hw,c)
+  static constexpr int64_t WFD = WFK + 512 * 3136;        // [3136][512]          row = (hw,c), k = j
+  static constexpr int64_t W3D = WFD + 3136 * 512;        // [64 c][576]          k = (kh,kw,co)
+  static constexpr int64_t W2D = W3D + 64 * 576;          // [4 cls][32 c][256]   k = (kh',kw',co)
+  static constexpr int64_t TOTAL = W2D + 4 * 32 * 256;
+};
+// pointers to the fp32 master tensors inside the flat parameter (or gradient) buffer
+struct ParamPtrs {
+  float *w1, *b1, *w2, *b2, *w3, *b3, *wf, *bf, *wp, *bp, *wb, *bb;
+};
+struct EncoderBuffers {
+  __nv_bfloat16 *a1, *a2, *a3;          // NHWC activations for NF frames
+  float* h;                             // [NF][512] fc output (post-ReLU), fp32
+  __nv_bfloat16 *dh, *da3, *da2, *da1;  // gradients w.r.t. (post-ReLU-masked) pre-activations, NB frames
+  __nv_bfloat16* wpack;
+};
+cudaError_t launch_pack_weights(const ParamPtrs& p, __nv_bfloat16* wpack, cudaStream_t st);
+cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, bool simt, cudaStream_t st);
+// backward for the first `frames` frames given buf.dh; accumulates into the (pre-zeroed) gradient tensors in `g`
+cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, bool simt, cudaStream_t st);
+cudaError_t test_gemm(const void* A, const void* B, float* D, int M, int N, int K, bool mn_major, bool simt, cudaStream_t st);
+
+}  // namespace srl

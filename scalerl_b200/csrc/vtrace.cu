@@ -1,0 +1,303 @@
+// V-trace kernels (reference: scalerl/algorithms/impala/vtrace.py) and the fused learner tail
+// (impala_atari.py:293-330 + loss_fn.py:5-23 + head gradients).  All fp32, HBM/latency bound.
+//
+//   vtrace_iw_seq_kernel<VEC>  column-sequential reverse recursion, lanes along B (coalesced; float4 when VEC=4)
+//   vtrace_iw_scan_kernel      [T x 32] tile staged through shared memory, lane = t, Kogge-Stone scan of the
+//                              affine maps x -> delta_t + (gamma_t c_t) x with warp shuffles, 32-step chunks + carry
+//   vtrace_logits_kernel       from_logits (log-softmax gather for both policies, then the recursion)
+//   impala_tail_kernel         one pass over the [T+1,B] batch rows: shifts, reward clip, discounts, V-trace,
+//                              pg/baseline/entropy losses (deterministic two-level reduction), dlogits, dbaseline
+#include "common.cuh"
+#include "kernels.h"
+
+namespace srl {
+
+struct F4 { float v[4]; };
+template <int VEC> struct VecT;
+template <> struct VecT<1> { typedef float type; };
+template <> struct VecT<4> { typedef float4 type; };
+
+template <int VEC>
+SRL_DEVINL void ldv(const float* p, float (&o)[VEC]) {
+  if (VEC == 4) { float4 t = __ldg(reinterpret_cast<const float4*>(p)); o[0] = t.x; o[1 % VEC] = t.y; o[2 % VEC] = t.z; o[3 % VEC] = t.w; }
+  else o[0] = __ldg(p);
+}
+template <int VEC>
+SRL_DEVINL void stv(float* p, const float (&o)[VEC]) {
+  if (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+  else *p = o[0];
+}
+
+// vtrace.py:135-169.  Each thread owns VEC adjacent columns; the reverse loop carries acc and vs_{t+1}.
+template <int VEC>
+__global__ void __launch_bounds__(128) vtrace_iw_seq_kernel(const float* __restrict__ log_rhos, const float* __restrict__ discounts,
+                                                            const float* __restrict__ rewards, const float* __restrict__ values,
+                                                            const float* __restrict__ bootstrap, int T, int B, float clip_rho,
+                                                            float clip_pg, float* __restrict__ vs, float* __restrict__ pg) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (b >= B) return;
+  float acc[VEC], vnext[VEC], vsnext[VEC];
+  ldv<VEC>(bootstrap + b, vnext);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { acc[i] = 0.f; vsnext[i] = vnext[i]; }
+#pragma unroll 4
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t o = (size_t)t * B + b;
+    float lr[VEC], g[VEC], r[VEC], v[VEC], ovs[VEC], opg[VEC];
+    ldv<VEC>(log_rhos + o, lr); ldv<VEC>(discounts + o, g); ldv<VEC>(rewards + o, r); ldv<VEC>(values + o, v);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float rho = expf(lr[i]);
+      const float crho = clip_rho >= 0.f ? fminf(rho, clip_rho) : rho;
+      const float c = fminf(rho, 1.0f);
+      const float delta = crho * (r[i] + g[i] * vnext[i] - v[i]);
+      acc[i] = delta + g[i] * c * acc[i];
+      const float prho = clip_pg >= 0.f ? fminf(rho, clip_pg) : rho;
+      opg[i] = prho * (r[i] + g[i] * vsnext[i] - v[i]);
+      ovs[i] = acc[i] + v[i];
+      vsnext[i] = ovs[i];
+      vnext[i] = v[i];
+    }
+    stv<VEC>(vs + o, ovs);
+    stv<VEC>(pg + o, opg);
+  }
+}
+
+// Warp-shuffle segmented scan variant.  Block = 32 columns x 8 warps (4 columns per warp).
+constexpr int SCAN_MAX_T = 128;
+__global__ void __launch_bounds__(256) vtrace_iw_scan_kernel(const float* __restrict__ log_rhos, const float* __restrict__ discounts,
+                                                             const float* __restrict__ rewards, const float* __restrict__ values,
+                                                             const float* __restrict__ bootstrap, int T, int B, float clip_rho,
+                                                             float clip_pg, float* __restrict__ vs, float* __restrict__ pg) {
+  extern __shared__ float sm[];   // 4 arrays [T][33]
+  float* s_lr = sm;
+  float* s_g = sm + (size_t)T * 33;
+  float* s_r = sm + (size_t)2 * T * 33;
+  float* s_v = sm + (size_t)3 * T * 33;
+  const int b0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // coalesced tile load: lanes along B
+  for (int t = warp; t < T; t += 8) {
+    const int b = b0 + lane;
+    const size_t o = (size_t)t * B + b;
+    const bool ok = b < B;
+    s_lr[t * 33 + lane] = ok ? __ldg(log_rhos + o) : 0.f;
+    s_g[t * 33 + lane] = ok ? __ldg(discounts + o) : 0.f;
+    s_r[t * 33 + lane] = ok ? __ldg(rewards + o) : 0.f;
+    s_v[t * 33 + lane] = ok ? __ldg(values + o) : 0.f;
+  }
+  __syncthreads();
+  const int nchunk = (T + 31) / 32;
+  for (int cc = 0; cc < 4; ++cc) {
+    const int c = warp * 4 + cc;
+    const int b = b0 + c;
+    const float boot = b < B ? __ldg(bootstrap + b) : 0.f;
+    float carry_acc = 0.f;        // acc_{t_end} entering the chunk from the future
+    float carry_v = boot;         // V_{t_end}
+    float carry_vs = boot;        // vs_{t_end}
+    for (int ch = nchunk - 1; ch >= 0; --ch) {
+      const int t = ch * 32 + lane;
+      const bool ok = t < T;
+      const float lr = ok ? s_lr[t * 33 + c] : 0.f;
+      const float g = ok ? s_g[t * 33 + c] : 0.f;
+      const float r = ok ? s_r[t * 33 + c] : 0.f;
+      const float v = ok ? s_v[t * 33 + c] : 0.f;
+      float vn = __shfl_down_sync(0xffffffffu, v, 1);
+      if (lane == 31 || t + 1 >= T) vn = carry_v;
+      const float rho = expf(lr);
+      const float crho = clip_rho >= 0.f ? fminf(rho, clip_rho) : rho;
+      // affine map of this step: x -> bb + aa * x ; identity for padding lanes
+      float aa = ok ? g * fminf(rho, 1.0f) : 1.f;
+      float bb = ok ? crho * (r + g * vn - v) : 0.f;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {   // suffix composition F_t = f_t o F_{t+d}
+        const float a2 = __shfl_down_sync(0xffffffffu, aa, d);
+        const float b2 = __shfl_down_sync(0xffffffffu, bb, d);
+        if (lane + d < 32) { bb = fmaf(aa, b2, bb); aa = aa * a2; }
+      }
+      const float acc = fmaf(aa, carry_acc, bb);
+      const float myvs = acc + v;
+      float vsn = __shfl_down_sync(0xffffffffu, myvs, 1);
+      if (lane == 31 || t + 1 >= T) vsn = carry_vs;
+      const float prho = clip_pg >= 0.f ? fminf(rho, clip_pg) : rho;
+      const float mypg = prho * (r + g * vsn - v);
+      if (ok) { s_lr[t * 33 + c] = myvs; s_g[t * 33 + c] = mypg; }   // reuse the tiles for the outputs
+      carry_acc = __shfl_sync(0xffffffffu, acc, 0);
+      carry_v = __shfl_sync(0xffffffffu, v, 0);
+      carry_vs = __shfl_sync(0xffffffffu, myvs, 0);
+    }
+  }
+  __syncthreads();
+  for (int t = warp; t < T; t += 8) {
+    const int b = b0 + lane;
+    if (b < B) {
+      const size_t o = (size_t)t * B + b;
+      vs[o] = s_lr[t * 33 + lane];
+      pg[o] = s_g[t * 33 + lane];
+    }
+  }
+}
+
+// log_softmax(logits)[action] for one row of A logits (vtrace.py:31-40)
+SRL_DEVINL float action_logp(const float* __restrict__ row, int A, int act) {
+  float mx = -INFINITY;
+  for (int a = 0; a < A; ++a) mx = fmaxf(mx, __ldg(row + a));
+  float se = 0.f;
+  for (int a = 0; a < A; ++a) se += expf(__ldg(row + a) - mx);
+  return (__ldg(row + act) - mx) - logf(se);
+}
+
+__global__ void __launch_bounds__(128) vtrace_logits_kernel(const float* __restrict__ bl, const float* __restrict__ tl,
+                                                            const int64_t* __restrict__ actions, const float* __restrict__ discounts,
+                                                            const float* __restrict__ rewards, const float* __restrict__ values,
+                                                            const float* __restrict__ bootstrap, int T, int B, int A, float clip_rho,
+                                                            float clip_pg, float* __restrict__ vs, float* __restrict__ pg,
+                                                            float* __restrict__ o_lr, float* __restrict__ o_balp, float* __restrict__ o_talp) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float acc = 0.f, vnext = __ldg(bootstrap + b), vsnext = vnext;
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t o = (size_t)t * B + b;
+    const int act = (int)__ldg(actions + o);
+    const float talp = action_logp(tl + o * A, A, act);
+    const float balp = action_logp(bl + o * A, A, act);
+    const float lr = talp - balp;
+    const float g = __ldg(discounts + o), r = __ldg(rewards + o), v = __ldg(values + o);
+    const float rho = expf(lr);
+    const float crho = clip_rho >= 0.f ? fminf(rho, clip_rho) : rho;
+    acc = crho * (r + g * vnext - v) + g * fminf(rho, 1.0f) * acc;
+    const float prho = clip_pg >= 0.f ? fminf(rho, clip_pg) : rho;
+    pg[o] = prho * (r + g * vsnext - v);
+    vsnext = acc + v;
+    vs[o] = vsnext;
+    vnext = v;
+    if (o_lr) o_lr[o] = lr;
+    if (o_balp) o_balp[o] = balp;
+    if (o_talp) o_talp[o] = talp;
+  }
+}
+
+// Fused learner tail.  One thread per batch column; rows follow the reference's shifts:
+//   model outputs (target logits, values) use row t, trajectory fields (behaviour logits, action, reward, done)
+//   use row t+1 (impala_atari.py:296-300), bootstrap = baseline[T] (:293).
+__global__ void __launch_bounds__(128) impala_tail_kernel(const float* __restrict__ bl, const float* __restrict__ tl,
+                                                          const float* __restrict__ baseline, const int64_t* __restrict__ action,
+                                                          const float* __restrict__ reward, const uint8_t* __restrict__ done, int T, int B,
+                                                          int A, float discounting, int clip_reward, float clip_rho, float clip_pg,
+                                                          float baseline_cost, float entropy_cost, float* __restrict__ vs,
+                                                          float* __restrict__ pg, float* __restrict__ dlogits, float* __restrict__ dbaseline,
+                                                          float* __restrict__ losses, float* __restrict__ scratch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  float l_pg = 0.f, l_bl = 0.f, l_ent = 0.f;
+  if (b < B) {
+    float acc = 0.f;
+    float vnext = __ldg(baseline + (size_t)T * B + b);
+    float vsnext = vnext;
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t o = (size_t)t * B + b;        // model row t
+      const size_t o1 = o + B;                   // trajectory row t+1
+      const int act = (int)__ldg(action + o1);
+      const float* trow = tl + o * A;
+      float mx = -INFINITY;
+      for (int a = 0; a < A; ++a) mx = fmaxf(mx, __ldg(trow + a));
+      float se = 0.f;
+      for (int a = 0; a < A; ++a) se += expf(__ldg(trow + a) - mx);
+      const float lse = logf(se);
+      float ent = 0.f;                           // sum_a p log p
+      for (int a = 0; a < A; ++a) { const float lp = (__ldg(trow + a) - mx) - lse; ent += expf(lp) * lp; }
+      const float talp = (__ldg(trow + act) - mx) - lse;
+      const float balp = action_logp(bl + o1 * A, A, act);
+      const float rho = expf(talp - balp);
+      float r = __ldg(reward + o1);
+      if (clip_reward) r = fminf(fmaxf(r, -1.f), 1.f);
+      const float g = done[o1] ? 0.f : discounting;
+      const float v = __ldg(baseline + o);
+      const float crho = clip_rho >= 0.f ? fminf(rho, clip_rho) : rho;
+      acc = crho * (r + g * vnext - v) + g * fminf(rho, 1.0f) * acc;
+      const float prho = clip_pg >= 0.f ? fminf(rho, clip_pg) : rho;
+      const float adv = prho * (r + g * vsnext - v);
+      const float myvs = acc + v;
+      if (vs) vs[o] = myvs;
+      if (pg) pg[o] = adv;
+      l_pg += -talp * adv;                                   // loss_fn.py:16-23
+      l_bl += 0.5f * (myvs - v) * (myvs - v);                // loss_fn.py:5-6
+      l_ent += ent;                                          // loss_fn.py:9-13
+      dbaseline[o] = -baseline_cost * (myvs - v);
+      float* drow = dlogits + o * A;
+      for (int a = 0; a < A; ++a) {
+        const float lp = (__ldg(trow + a) - mx) - lse;
+        const float p = expf(lp);
+        drow[a] = adv * (p - (a == act ? 1.f : 0.f)) + entropy_cost * p * (lp - ent);
+      }
+      vsnext = myvs;
+      vnext = v;
+    }
+  }
+  // deterministic reduction: warp -> block -> per-block partial; the last block sums partials in order
+  __shared__ float red[3][4];
+  __shared__ bool is_last;
+  l_pg = warp_sum(l_pg); l_bl = warp_sum(l_bl); l_ent = warp_sum(l_ent);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = l_pg; red[1][warp] = l_bl; red[2][warp] = l_ent; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) scratch[4 + blockIdx.x * 3 + i] = (red[i][0] + red[i][1]) + (red[i][2] + red[i][3]);
+    __threadfence();
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(scratch), 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    double s[3] = {0, 0, 0};
+    for (unsigned k = 0; k < gridDim.x; ++k)
+      for (int i = 0; i < 3; ++i) s[i] += (double)reinterpret_cast<volatile float*>(scratch)[4 + k * 3 + i];
+    const float a = (float)s[0], c = baseline_cost * (float)s[1], e = entropy_cost * (float)s[2];
+    losses[0] = a; losses[1] = c; losses[2] = e; losses[3] = a + c + e;
+    *reinterpret_cast<unsigned*>(scratch) = 0u;   // re-arm the ticket
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_vtrace_iw(const float* log_rhos, const float* discounts, const float* rewards, const float* values,
+                             const float* bootstrap, int T, int B, float clip_rho, float clip_pg, float* vs, float* pg, int variant,
+                             cudaStream_t st) {
+  if (T <= 0 || B <= 0) return cudaSuccess;
+  if (variant == 1 && T <= SCAN_MAX_T) {
+    const size_t smem = (size_t)4 * T * 33 * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(vtrace_iw_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    vtrace_iw_scan_kernel<<<(B + 31) / 32, 256, smem, st>>>(log_rhos, discounts, rewards, values, bootstrap, T, B, clip_rho, clip_pg, vs, pg);
+    return cudaGetLastError();
+  }
+  const bool al = ((reinterpret_cast<uintptr_t>(log_rhos) | reinterpret_cast<uintptr_t>(discounts) | reinterpret_cast<uintptr_t>(rewards) |
+                    reinterpret_cast<uintptr_t>(values) | reinterpret_cast<uintptr_t>(bootstrap) | reinterpret_cast<uintptr_t>(vs) |
+                    reinterpret_cast<uintptr_t>(pg)) & 15) == 0;
+  if (B % 4 == 0 && al && B >= 4 * 128 * 148) {   // enough columns to fill the chip with 4-wide threads
+    const int threads = B / 4;
+    vtrace_iw_seq_kernel<4><<<(threads + 127) / 128, 128, 0, st>>>(log_rhos, discounts, rewards, values, bootstrap, T, B, clip_rho, clip_pg, vs, pg);
+  } else {
+    vtrace_iw_seq_kernel<1><<<(B + 127) / 128, 128, 0, st>>>(log_rhos, discounts, rewards, values, bootstrap, T, B, clip_rho, clip_pg, vs, pg);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vtrace_logits(const float* bl, const float* tl, const int64_t* actions, const float* discounts, const float* rewards,
+                                 const float* values, const float* bootstrap, int T, int B, int A, float clip_rho, float clip_pg,
+                                 float* vs, float* pg, float* lr, float* balp, float* talp, cudaStream_t st) {
+  if (T <= 0 || B <= 0) return cudaSuccess;
+  vtrace_logits_kernel<<<(B + 127) / 128, 128, 0, st>>>(bl, tl, actions, discounts, rewards, values, bootstrap, T, B, A, clip_rho, clip_pg,
+                                                         vs, pg, lr, balp, talp);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_impala_tail(const float* bl, const float* tl, const float* baseline, const int64_t* action, const float* reward,
+                               const uint8_t* done, int T, int B, int A, float discounting, int clip_reward, float clip_rho,
+                               float clip_pg, float baseline_cost, float entropy_cost, float* vs, float* pg, float* dlogits,
+                               float* dbaseline, float* losses, float* scratch, cudaStream_t st) {
+  impala_tail_kernel<<<(B + 127) / 128, 128, 0, st>>>(bl, tl, baseline, action, reward, done, T, B, A, discounting, clip_reward, clip_rho,
+                                                       clip_pg, baseline_cost, entropy_cost, vs, pg, dlogits, dbaseline, losses, scratch);
+  return cudaGetLastError();
+}
+
+}  // namespace srl

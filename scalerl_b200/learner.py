@@ -1,0 +1,289 @@
+"""B200ImpalaLearner -- the learner side of ImpalaTrainer.learn behind ScaleRL's agent API.
+
+Replaces, for one GPU's shard of the batch, the arithmetic of
+``ImpalaTrainer.learn`` (/root/reference scalerl/algorithms/impala/impala_atari.py:270-349) and of
+``AtariNet.forward`` (scalerl/algorithms/utils/atari_model.py:77-143, use_lstm=False); implements the
+``BaseAgent`` surface (scalerl/algorithms/base.py:68-116): learn / predict / get_weights / set_weights /
+save_checkpoint / load_checkpoint.  All math runs in libscalerl_b200.so (C ABI); torch supplies device
+memory, streams and (for world_size > 1) the NCCL all-reduce of the flat gradient buffer.
+
+Data parallelism: each rank processes B_local columns; gradients are SUM-reduced because
+the reference losses are sums over T*B (loss_fn.py:6,13,23); the 40.0 clip applies to the global gradient.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from dataclasses import dataclass, asdict
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+PARAM_NAMES = ('conv1.weight', 'conv1.bias', 'conv2.weight', 'conv2.bias', 'conv3.weight', 'conv3.bias',
+               'fc.weight', 'fc.bias', 'policy.weight', 'policy.bias', 'baseline.weight', 'baseline.bias')
+
+
+def param_shapes(num_actions: int):
+    core = 513 + num_actions
+    return OrderedDict([
+        ('conv1.weight', (32, 4, 8, 8)), ('conv1.bias', (32,)), ('conv2.weight', (64, 32, 4, 4)), ('conv2.bias', (64,)),
+        ('conv3.weight', (64, 64, 3, 3)), ('conv3.bias', (64,)), ('fc.weight', (512, 3136)), ('fc.bias', (512,)),
+        ('policy.weight', (num_actions, core)), ('policy.bias', (num_actions,)),
+        ('baseline.weight', (1, core)), ('baseline.bias', (1,))])
+
+
+@dataclass
+class ImpalaHParams:
+    """Hyper-parameters read by ImpalaTrainer (impala_atari.py:56,72-77,302-328,344) -- the fields the
+    reference's RLArguments forgot are added with upstream torchbeast defaults."""
+    rollout_length: int = 20
+    batch_size: int = 32                 # columns handled by THIS rank
+    num_actions: int = 6
+    discounting: float = 0.99
+    baseline_cost: float = 0.5
+    entropy_cost: float = 0.0006
+    reward_clipping: str = 'abs_one'
+    clip_rho_threshold: Optional[float] = 1.0
+    clip_pg_rho_threshold: Optional[float] = 1.0
+    max_grad_norm: float = 40.0          # rl_args.py:108
+    learning_rate: float = 1e-4          # rl_args.py:112
+    alpha: float = 0.99                  # rl_args.py:114
+    momentum: float = 0.0                # rl_args.py:116 (only 0 is supported, as the reference uses)
+    epsilon: float = 1e-5                # rl_args.py:117
+    optimizer: str = 'rmsprop'           # 'rmsprop' (reference) | 'adam' (north_star)
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    adam_eps: float = 1e-8
+    simt_mainloop: bool = False          # debug: CUDA-core inner product instead of tcgen05
+
+    def to_c(self) -> _lib.SrlConfig:
+        if self.reward_clipping not in ('abs_one', 'none'):
+            raise ValueError("reward_clipping must be 'abs_one' or 'none'")
+        if self.optimizer not in ('rmsprop', 'adam'):
+            raise ValueError("optimizer must be 'rmsprop' or 'adam'")
+        if self.momentum != 0.0:
+            raise ValueError('only momentum=0 is supported (the reference default)')
+        c = _lib.SrlConfig()
+        c.T, c.B, c.A = self.rollout_length, self.batch_size, self.num_actions
+        c.optimizer = 0 if self.optimizer == 'rmsprop' else 1
+        c.reward_clip_abs_one = 1 if self.reward_clipping == 'abs_one' else 0
+        c.simt_mainloop = 1 if self.simt_mainloop else 0
+        c.discounting, c.baseline_cost, c.entropy_cost = self.discounting, self.baseline_cost, self.entropy_cost
+        c.clip_rho_threshold = -1.0 if self.clip_rho_threshold is None else self.clip_rho_threshold
+        c.clip_pg_rho_threshold = -1.0 if self.clip_pg_rho_threshold is None else self.clip_pg_rho_threshold
+        c.max_grad_norm = self.max_grad_norm
+        c.learning_rate, c.alpha, c.epsilon = self.learning_rate, self.alpha, self.epsilon
+        c.adam_beta1, c.adam_beta2, c.adam_eps = self.adam_beta1, self.adam_beta2, self.adam_eps
+        return c
+
+
+class B200ImpalaLearner:
+    """One learner process per GPU.  ``learn(batch)`` consumes the reference's batch dict
+    (keys of create_buffers, impala_atari.py:122-151; tensors [T+1, B_local, ...]) and returns the
+    reference's stats dict (impala_atari.py:333-340)."""
+
+    def __init__(self, hp: ImpalaHParams, device: Optional[torch.device] = None, process_group=None,
+                 init_state_dict: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError('B200ImpalaLearner needs a CUDA device: scalerl_b200 has no CPU fallback')
+        self.hp = hp
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        # process_group: None -> default group when torch.distributed is initialised; False -> never all-reduce
+        self.pg = process_group
+        dist = torch.distributed
+        self._dist = (process_group is not False and dist.is_available() and dist.is_initialized()
+                      and dist.get_world_size(process_group or None) > 1)
+        self._L = _lib.lib()
+        with torch.cuda.device(self.device):
+            total, self._off, self._cnt = _lib.param_layout(hp.num_actions)
+            self.numel = total
+            z = lambda: torch.zeros(total, dtype=torch.float32, device=self.device)
+            self.flat_params, self.flat_grads, self.opt_state0 = z(), z(), z()
+            self.opt_state1 = z() if hp.optimizer == 'adam' else None
+            self.shapes = param_shapes(hp.num_actions)
+            self.params = OrderedDict((n, self._view(self.flat_params, i)) for i, n in enumerate(PARAM_NAMES))
+            self.grads = OrderedDict((n, self._view(self.flat_grads, i)) for i, n in enumerate(PARAM_NAMES))
+            if init_state_dict is None:
+                init_state_dict = self._default_init(seed)
+            self._cfg = hp.to_c()
+            h = C.c_void_p()
+            _lib.check(self._L.srl_learner_create(
+                C.byref(self._cfg), self.flat_params.data_ptr(), self.flat_grads.data_ptr(), self.opt_state0.data_ptr(),
+                self.opt_state1.data_ptr() if self.opt_state1 is not None else None, C.byref(h)), 'srl_learner_create')
+            self._h = h
+            self.load_state_dict(init_state_dict)
+            T, B, A = hp.rollout_length, hp.batch_size, hp.num_actions
+            self._losses = torch.zeros(4, device=self.device)
+            self._coef = torch.zeros(2, device=self.device)
+            self._vs = torch.empty(T, B, device=self.device)
+            self._pg_adv = torch.empty(T, B, device=self.device)
+            self._stats_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.global_step = 0
+
+    # ------------------------------------------------------------------ parameters
+    def _view(self, flat, i):
+        n = PARAM_NAMES[i]
+        return flat[self._off[i]:self._off[i] + self._cnt[i]].view(self.shapes[n])
+
+    def _default_init(self, seed):
+        """torch's default Conv2d/Linear init distribution (U(+-1/sqrt(fan_in))), as AtariNet() would draw."""
+        g = torch.Generator().manual_seed(seed)
+        sd, fan = OrderedDict(), 1
+        for n, shp in self.shapes.items():
+            if n.endswith('.weight'):
+                fan = 1
+                for d in shp[1:]:
+                    fan *= d
+            bound = 1.0 / fan ** 0.5
+            sd[n] = (torch.rand(shp, generator=g) * 2 - 1) * bound
+        return sd
+
+    def state_dict(self) -> 'OrderedDict[str, torch.Tensor]':
+        """AtariNet-compatible state_dict (names/layouts of atari_model.py:30-59)."""
+        return OrderedDict((n, p.detach().clone()) for n, p in self.params.items())
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        for n in PARAM_NAMES:
+            if n not in sd:
+                raise KeyError(f'missing key {n} in state_dict')
+            if tuple(sd[n].shape) != tuple(self.shapes[n]):
+                raise ValueError(f'{n}: shape {tuple(sd[n].shape)} != {tuple(self.shapes[n])}')
+            self.params[n].copy_(sd[n].to(self.device, torch.float32))
+        _lib.check(self._L.srl_learner_pack_weights(self._h, self._stream()), 'pack_weights')
+
+    def get_weights(self):            # BaseAgent.get_weights (algorithms/base.py:86-92)
+        return {k: v.cpu() for k, v in self.state_dict().items()}
+
+    def set_weights(self, weights):   # BaseAgent.set_weights (algorithms/base.py:94-100)
+        self.load_state_dict(weights)
+
+    def optimizer_state_dict(self):
+        names = ('square_avg',) if self.hp.optimizer == 'rmsprop' else ('exp_avg', 'exp_avg_sq')
+        flats = (self.opt_state0,) if self.hp.optimizer == 'rmsprop' else (self.opt_state0, self.opt_state1)
+        return {'step': self.global_opt_step, 'state': {nm: OrderedDict((n, self._view(f, i).detach().clone())
+                                                                     for i, n in enumerate(PARAM_NAMES)) for nm, f in zip(names, flats)}}
+
+    @property
+    def global_opt_step(self):
+        return getattr(self, '_opt_steps', 0)
+
+    def save_checkpoint(self, path: str) -> None:
+        """same dict keys as ImpalaTrainer.save_checkpoint (impala_atari.py:506-511)"""
+        torch.save({'model_state_dict': {k: v.cpu() for k, v in self.state_dict().items()},
+                    'optimizer_state_dict': self.optimizer_state_dict(), 'hparam': asdict(self.hp)}, path)
+
+    def load_checkpoint(self, path: str) -> None:
+        ck = torch.load(path, map_location='cpu', weights_only=False)
+        self.load_state_dict(ck['model_state_dict'])
+        st = ck.get('optimizer_state_dict', {}).get('state', {})
+        for nm, flat in (('square_avg', self.opt_state0), ('exp_avg', self.opt_state0), ('exp_avg_sq', self.opt_state1)):
+            if nm in st and flat is not None:
+                for i, n in enumerate(PARAM_NAMES):
+                    self._view(flat, i).copy_(st[nm][n])
+
+    # ------------------------------------------------------------------ compute
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _check_batch(self, batch, rows):
+        hp = self.hp
+        B, A = hp.batch_size, hp.num_actions
+        exp = {'obs': ((rows, B, 4, 84, 84), torch.uint8), 'reward': ((rows, B), torch.float32), 'action': ((rows, B), torch.int64)}
+        for k, (shp, dt) in exp.items():
+            if k not in batch:
+                raise KeyError(f"batch is missing key '{k}'")
+            t = batch[k]
+            if tuple(t.shape) != shp or t.dtype != dt:
+                raise ValueError(f"batch['{k}']: expected {shp} {dt}, got {tuple(t.shape)} {t.dtype}")
+            if not t.is_cuda or not t.is_contiguous():
+                raise ValueError(f"batch['{k}'] must be a contiguous CUDA tensor")
+
+    @torch.no_grad()
+    def forward(self, batch: Dict[str, torch.Tensor]):
+        """AtariNet.forward (learner path: no action sampling) -> dict(policy_logits [R,B,A], baseline [R,B])."""
+        rows = batch['obs'].shape[0]
+        self._check_batch(batch, rows)
+        hp = self.hp
+        logits = torch.empty(rows, hp.batch_size, hp.num_actions, device=self.device)
+        baseline = torch.empty(rows, hp.batch_size, device=self.device)
+        _lib.check(self._L.srl_learner_forward(self._h, batch['obs'].data_ptr(), batch['reward'].data_ptr(), batch['action'].data_ptr(),
+                                               rows, logits.data_ptr(), baseline.data_ptr(), self._stream()), 'srl_learner_forward')
+        return dict(policy_logits=logits, baseline=baseline)
+
+    predict = forward
+
+    @torch.no_grad()
+    def forward_backward(self, batch):
+        """enqueue forward + V-trace/loss + backward; gradients (SUM over this rank's columns) land in flat_grads."""
+        hp = self.hp
+        self._check_batch(batch, hp.rollout_length + 1)
+        done = batch['done']
+        done_u8 = done.view(torch.uint8) if done.dtype == torch.bool else done
+        bl = batch['policy_logits']
+        if tuple(bl.shape) != (hp.rollout_length + 1, hp.batch_size, hp.num_actions) or bl.dtype != torch.float32:
+            raise ValueError("batch['policy_logits'] must be float32 [T+1, B, A]")
+        _lib.check(self._L.srl_learner_forward_backward(
+            self._h, batch['obs'].data_ptr(), batch['reward'].data_ptr(), done_u8.data_ptr(), batch['action'].data_ptr(),
+            bl.data_ptr(), self._losses.data_ptr(), self._vs.data_ptr(), self._pg_adv.data_ptr(), self._stream()),
+            'srl_learner_forward_backward')
+
+    def all_reduce_gradients(self):
+        """SUM (not mean) all-reduce of the flat gradient + loss scalars over NCCL."""
+        dist = torch.distributed
+        dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM, group=self.pg or None)
+        dist.all_reduce(self._losses, op=dist.ReduceOp.SUM, group=self.pg or None)
+
+    @torch.no_grad()
+    def apply_gradients(self):
+        _lib.check(self._L.srl_learner_apply_gradients(self._h, self._coef.data_ptr(), self._stream()), 'srl_learner_apply_gradients')
+        self._opt_steps = self.global_opt_step + 1
+
+    @torch.no_grad()
+    def learn(self, batch: Dict[str, torch.Tensor], initial_rnn_state=(), sync_stats: bool = True) -> Dict[str, object]:
+        """One learner step (impala_atari.py:288-346).  Returns the reference's stats dict when sync_stats
+        (one D2H read of 6 floats), else {} with everything left enqueued on the stream."""
+        self.forward_backward(batch)
+        if self._dist:
+            self.all_reduce_gradients()
+        self.apply_gradients()
+        self.global_step += self.hp.rollout_length * self.hp.batch_size
+        if not sync_stats:
+            return {}
+        host = self._stats_host
+        host[:4].copy_(self._losses, non_blocking=True)
+        host[4:6].copy_(self._coef, non_blocking=True)
+        done = batch['done'][1:]
+        ep = batch['episode_return'][1:][done] if 'episode_return' in batch else torch.empty(0, device=self.device)
+        ep_host = ep.cpu()                                  # synchronises the stream (the reference does 6 .item() syncs)
+        torch.cuda.current_stream(self.device).synchronize()
+        return {'episode_returns': tuple(ep_host.numpy()),
+                'mean_episode_return': float(ep_host.mean()) if ep_host.numel() else float('nan'),
+                'total_loss': float(host[3]), 'pg_loss': float(host[0]), 'baseline_loss': float(host[1]),
+                'entropy_loss': float(host[2]), 'grad_norm': float(host[4])}
+
+    def debug_buffer(self, name: str, dtype=None):
+        """copy of an internal activation buffer (tests only)"""
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(self._L.srl_learner_debug_buffer(self._h, name.encode(), C.byref(p), C.byref(n)), 'debug_buffer')
+        fp32 = name in ('h', 'logits', 'baseline', 'dlogits', 'dbaseline')
+        dt = torch.float32 if fp32 else torch.bfloat16
+        nbytes = n.value * (4 if fp32 else 2)
+        out = torch.empty(n.value, dtype=dt, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), p.value, nbytes, 3)   # cudaMemcpyDeviceToDevice
+        if int(rc) != 0:
+            raise RuntimeError(f'cudaMemcpy failed: {rc}')
+        return out
+
+    def close(self):
+        if getattr(self, '_h', None) is not None:
+            self._L.srl_learner_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

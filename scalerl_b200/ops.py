@@ -1,0 +1,128 @@
+"""Torch-tensor front end of the C ABI (device memory + streams are torch's; the math is ours).
+
+Mirrors the reference's operator surface for the hot path:
+  from_importance_weights / from_logits  <->  scalerl/algorithms/impala/vtrace.py:43-172
+  impala_loss_and_head_grads            <->  scalerl/algorithms/impala/loss_fn.py:5-23 + impala_atari.py:293-330
+Errors follow the reference's Python behaviour: ValueError for bad arguments, RuntimeError for CUDA failures.
+"""
+import collections
+
+import torch
+
+from . import _lib
+
+VTraceFromLogitsReturns = collections.namedtuple(
+    'VTraceFromLogitsReturns',
+    ['vs', 'pg_advantages', 'log_rhos', 'behavior_action_log_probs', 'target_action_log_probs'])
+VTraceReturns = collections.namedtuple('VTraceReturns', 'vs pg_advantages')
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t, name):
+    if not t.is_cuda:
+        raise ValueError(f'{name} must be a CUDA tensor (scalerl_b200 has no CPU path)')
+    if t.dtype != torch.float32:
+        raise ValueError(f'{name} must be float32, got {t.dtype}')
+    return t.contiguous()
+
+
+def _clip(v):
+    return -1.0 if v is None else float(v)
+
+
+@torch.no_grad()
+def from_importance_weights(log_rhos, discounts, rewards, values, bootstrap_value,
+                            clip_rho_threshold=1.0, clip_pg_rho_threshold=1.0, variant=0):
+    """vtrace.from_importance_weights (vtrace.py:78-172) for [T,B] inputs -> VTraceReturns(vs, pg_advantages)."""
+    log_rhos, discounts, rewards, values = [_f32(t, n) for t, n in
+                                            ((log_rhos, 'log_rhos'), (discounts, 'discounts'), (rewards, 'rewards'), (values, 'values'))]
+    bootstrap_value = _f32(bootstrap_value, 'bootstrap_value')
+    if log_rhos.dim() != 2:
+        raise ValueError('log_rhos must be [T, B]')
+    T, B = log_rhos.shape
+    for t, n in ((discounts, 'discounts'), (rewards, 'rewards'), (values, 'values')):
+        if tuple(t.shape) != (T, B):
+            raise ValueError(f'{n} has shape {tuple(t.shape)}, expected {(T, B)}')
+    if tuple(bootstrap_value.shape) != (B,):
+        raise ValueError(f'bootstrap_value has shape {tuple(bootstrap_value.shape)}, expected {(B,)}')
+    vs = torch.empty_like(log_rhos)
+    pg = torch.empty_like(log_rhos)
+    _lib.check(_lib.lib().srl_vtrace_from_importance_weights(
+        log_rhos.data_ptr(), discounts.data_ptr(), rewards.data_ptr(), values.data_ptr(), bootstrap_value.data_ptr(),
+        T, B, _clip(clip_rho_threshold), _clip(clip_pg_rho_threshold), vs.data_ptr(), pg.data_ptr(), int(variant), _stream()),
+        'vtrace_from_importance_weights')
+    return VTraceReturns(vs=vs, pg_advantages=pg)
+
+
+@torch.no_grad()
+def from_logits(behavior_policy_logits, target_policy_logits, actions, discounts, rewards, values, bootstrap_value,
+                clip_rho_threshold=1.0, clip_pg_rho_threshold=1.0):
+    """vtrace.from_logits (vtrace.py:43-75): logits [T,B,A], actions int64 [T,B]."""
+    bl = _f32(behavior_policy_logits, 'behavior_policy_logits')
+    tl = _f32(target_policy_logits, 'target_policy_logits')
+    discounts, rewards, values = _f32(discounts, 'discounts'), _f32(rewards, 'rewards'), _f32(values, 'values')
+    bootstrap_value = _f32(bootstrap_value, 'bootstrap_value')
+    if actions.dtype != torch.int64:
+        raise ValueError('actions must be int64')
+    actions = actions.contiguous()
+    if tl.dim() != 3 or bl.shape != tl.shape:
+        raise ValueError('policy logits must both be [T, B, A]')
+    T, B, A = tl.shape
+    outs = [torch.empty(T, B, device=tl.device, dtype=torch.float32) for _ in range(5)]
+    _lib.check(_lib.lib().srl_vtrace_from_logits(
+        bl.data_ptr(), tl.data_ptr(), actions.data_ptr(), discounts.data_ptr(), rewards.data_ptr(), values.data_ptr(),
+        bootstrap_value.data_ptr(), T, B, A, _clip(clip_rho_threshold), _clip(clip_pg_rho_threshold),
+        *[o.data_ptr() for o in outs], _stream()), 'vtrace_from_logits')
+    return VTraceFromLogitsReturns(vs=outs[0], pg_advantages=outs[1], log_rhos=outs[2],
+                                   behavior_action_log_probs=outs[3], target_action_log_probs=outs[4])
+
+
+@torch.no_grad()
+def impala_loss_and_head_grads(behavior_logits, target_logits, baseline, action, reward, done, discounting=0.99,
+                               reward_clipping='abs_one', clip_rho_threshold=1.0, clip_pg_rho_threshold=1.0,
+                               baseline_cost=0.5, entropy_cost=0.0006):
+    """Fused learner tail on [T+1,B] batch rows -> dict(vs, pg_advantages, dlogits, dbaseline, losses[4])."""
+    bl, tl, baseline, reward = [_f32(t, n) for t, n in ((behavior_logits, 'behavior_logits'), (target_logits, 'target_logits'),
+                                                         (baseline, 'baseline'), (reward, 'reward'))]
+    T1, B, A = tl.shape
+    T = T1 - 1
+    if T < 1:
+        raise ValueError('need at least 2 rows (T >= 1)')
+    if reward_clipping not in ('abs_one', 'none'):
+        raise ValueError("reward_clipping must be 'abs_one' or 'none'")
+    action = action.contiguous()
+    done_u8 = done.contiguous().view(torch.uint8) if done.dtype == torch.bool else done.contiguous()
+    dev = tl.device
+    vs = torch.empty(T, B, device=dev)
+    pg = torch.empty(T, B, device=dev)
+    dlogits = torch.empty(T, B, A, device=dev)
+    dbaseline = torch.empty(T, B, device=dev)
+    losses = torch.empty(4, device=dev)
+    scratch = torch.zeros(3 * ((B + 127) // 128) + 8, device=dev)
+    _lib.check(_lib.lib().srl_impala_loss_and_head_grads(
+        bl.data_ptr(), tl.data_ptr(), baseline.data_ptr(), action.data_ptr(), reward.data_ptr(), done_u8.data_ptr(), T, B, A,
+        float(discounting), 1 if reward_clipping == 'abs_one' else 0, _clip(clip_rho_threshold), _clip(clip_pg_rho_threshold),
+        float(baseline_cost), float(entropy_cost), vs.data_ptr(), pg.data_ptr(), dlogits.data_ptr(), dbaseline.data_ptr(),
+        losses.data_ptr(), scratch.data_ptr(), _stream()), 'impala_loss_and_head_grads')
+    return dict(vs=vs, pg_advantages=pg, dlogits=dlogits, dbaseline=dbaseline, losses=losses)
+
+
+@torch.no_grad()
+def test_gemm(a, b, mn_major=False, simt=False):
+    """unit-test hook for the tcgen05 mainloop. kmajor: a [M,K], b [N,K]; mnmajor: a [K,M], b [K,N]. bf16 in, f32 out."""
+    a = a.contiguous()
+    b = b.contiguous()
+    if mn_major:
+        K, M = a.shape
+        N = b.shape[1]
+        fn = _lib.lib().srl_test_gemm_mnmajor
+    else:
+        M, K = a.shape
+        N = b.shape[0]
+        fn = _lib.lib().srl_test_gemm_kmajor
+    d = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    _lib.check(fn(a.data_ptr(), b.data_ptr(), d.data_ptr(), M, N, K, 1 if simt else 0, _stream()), 'test_gemm')
+    return d

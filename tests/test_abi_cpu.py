@@ -1,0 +1,65 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/scalerl_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from scalerl_b200 import _lib, build as srl_build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    srl_build.build()
+    return ctypes.CDLL(_lib.LIB_PATH)
+
+
+def _declared():
+    src = open(os.path.join(ROOT, 'include', 'scalerl_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(srl_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_header_symbols_exported(lib):
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in include/scalerl_b200.h but not exported'
+    assert sorted(_lib.EXPORTS) == names, 'ctypes binding table and header disagree'
+
+
+def test_param_layout_matches_atarinet():
+    total, off, cnt = _lib.param_layout(6)
+    assert sum(cnt) == 1687768        # AtariNet((4,84,84), 6) parameter count
+    assert all(o % 4 == 0 for o in off) and total >= sum(cnt)
+    total4, _, cnt4 = _lib.param_layout(4)
+    assert sum(cnt4) == 1686718
+
+
+def test_config_struct_size():
+    assert ctypes.sizeof(_lib.SrlConfig) == 18 * 4
+
+
+def test_argument_errors_without_gpu(lib):
+    L = _lib.lib()
+    # NULL pointers / bad shapes are rejected before any CUDA call
+    assert L.srl_vtrace_from_importance_weights(None, None, None, None, None, 4, 4, 1.0, 1.0, None, None, 0, None) == -1
+    assert b'NULL' in L.srl_last_error()
+    assert L.srl_vtrace_from_importance_weights(None, None, None, None, None, 0, 4, 1.0, 1.0, None, None, 0, None) == 0  # empty
+    cfg = _lib.SrlConfig()
+    cfg.T, cfg.B, cfg.A = 20, 32, 99
+    h = ctypes.c_void_p()
+    assert L.srl_learner_create(ctypes.byref(cfg), None, None, None, None, ctypes.byref(h)) == -1
+    assert b'A=99' in L.srl_last_error()
+
+
+def test_product_path_has_no_oracle_import():
+    """the shipped package must never import the oracle or fall back to CPU"""
+    pkg = os.path.join(ROOT, 'scalerl_b200')
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith('.py'):
+                s = open(os.path.join(dp, f)).read()
+                assert 'import oracle' not in s and 'from oracle' not in s, f
