@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- IMPALA learner frames/s on synthetic 84x84x4 uint8 trajectories (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one full learner step (ImpalaTrainer.learn, impala_atari.py:288-346): encoder forward over
+(T+1)*B frames, fused V-trace + losses + head gradients, full backward over T*B frames, [NCCL SUM all-reduce],
+clip_grad_norm_ + RMSprop, weight re-pack.  The metric counts T*B frames per step (impala_atari.py:391).
+Workload: BASELINE.json configs[1] (T=20, B=32 columns per GPU, A=6 Pong) -- weak scaling: every rank keeps 32
+columns, global batch = 32*N.
+
+Printed JSON (one line, rank 0):
+  value     device-resident whole-job frames/s (inputs already in HBM), CUDA events, max over ranks
+  e2e       same metric through the public host-batch API (HostBatchFeeder + B200ImpalaLearner.learn): pinned-host
+            H2D of every step's batch and D2H of the step's losses inside the timed region
+  roofline  dominant kernel of the step: algorithmic FLOPs per launch / per-launch duration (CUDA events recorded
+            around every launch, srl_learner_set_profiling) vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference learner step timed on this box's host cores (rank 0, N=1)
+`--impl reference` times that CPU learner alone (the reference is pure Python + torch-CPU; its own trainer cannot
+be imported -- SURVEY.md §0 -- so the arm runs oracle/impala_oracle.py, the restatement pinned to the reference's
+modules by tests/golden).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T_DEFAULT, B_DEFAULT, A_DEFAULT = 20, 32, 6
+POOL = 8   # distinct batches cycled through: 8 x 19.5 MB = 156 MB > 126 MB L2, so a step's inputs are never L2-resident
+
+# algorithmic MACs per frame: conv1, conv2, conv3, fc
+MACS = {'conv1': 3276800, 'conv2': 2654208, 'conv3': 1806336, 'fc': 1605632}
+SLOT_FLOPS = {  # slot -> (MACs per frame, frames = 'fwd' (T+1)*B or 'bwd' T*B)
+    'conv1_fwd': ('conv1', 'fwd'), 'conv2_fwd': ('conv2', 'fwd'), 'conv3_fwd': ('conv3', 'fwd'), 'fc_fwd': ('fc', 'fwd'),
+    'fc_wgrad': ('fc', 'bwd'), 'fc_dgrad': ('fc', 'bwd'), 'conv3_wgrad': ('conv3', 'bwd'), 'conv3_dgrad': ('conv3', 'bwd'),
+    'conv2_wgrad': ('conv2', 'bwd'), 'conv2_dgrad': ('conv2', 'bwd'), 'conv1_wgrad': ('conv1', 'bwd')}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d['hbm_gbs'], bf16_tflops=d['bf16_tflops'], bf16_sustained=d.get('bf16_tflops_sustained'), source='measured')
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {'sm_mhz': med, 'sm_max_mhz': mx, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def make_host_pool(T, B, A, n, seed):
+    """n distinct synthetic [T+1,B] batches in pinned host memory (distributions of SURVEY.md §8d)."""
+    import numpy as np
+    import torch
+    from scalerl_b200.data.feeder import pinned_batch
+    pool = []
+    for i in range(n):
+        rng = np.random.RandomState(seed * 1000 + i)
+        hb = pinned_batch(T, B, A)
+        hb['obs'].copy_(torch.from_numpy(rng.randint(0, 256, size=(T + 1, B, 4, 84, 84), dtype=np.uint8)))
+        hb['reward'].copy_(torch.from_numpy(rng.randn(T + 1, B).astype(np.float32)))
+        hb['done'].copy_(torch.from_numpy(rng.rand(T + 1, B) < 0.02))
+        hb['action'].copy_(torch.from_numpy(rng.randint(0, A, size=(T + 1, B)).astype(np.int64)))
+        hb['policy_logits'].copy_(torch.from_numpy(rng.randn(T + 1, B, A).astype(np.float32)))
+        hb['episode_return'].copy_(torch.from_numpy(rng.randn(T + 1, B).astype(np.float32)))
+        pool.append(hb)
+    return pool
+
+
+def cpu_learner_fps(T, B, A, budget_s, warmup=2, max_steps=50, min_steps=3):
+    """oracle port of ImpalaTrainer.learn (fp32, autograd, RMSprop) on the host cores."""
+    import torch
+    from oracle import impala_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = O.init_params(A, seed=0)
+    opt = O.new_opt_state(params)
+    batch = O.synthetic_batch(T, B, A, seed=0)
+    for _ in range(warmup):
+        O.learn_step(params, opt, batch, use_autograd=True)
+    n, t0 = 0, time.perf_counter()
+    while n < max_steps and (n < min_steps or time.perf_counter() - t0 < budget_s):
+        O.learn_step(params, opt, batch, use_autograd=True)
+        n += 1
+    dt = time.perf_counter() - t0
+    return n * T * B / dt, n, dt / n, cores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    T, B, A = args.T, args.B, args.A
+    import torch
+    from oracle import impala_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = O.init_params(A, seed=0)
+    opt = O.new_opt_state(params)
+    batch = O.synthetic_batch(T, B, A, seed=0)
+    for _ in range(args.warmup):
+        O.learn_step(params, opt, batch, use_autograd=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.learn_step(params, opt, batch, use_autograd=True)
+    dt = time.perf_counter() - t0
+    fps = args.steps * T * B / dt
+    sample = f'{args.steps} learner steps of T={T}, B={B} columns (one GPU-rank shard of the global batch {B * world}), fp32 torch-CPU'
+    out = {'impl': 'reference', 'metric': 'learner_frames_per_sec', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
+           'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
+           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': f'IMPALA Pong 84x84x4 uint8, T={T}, B={B}/GPU, A={A}, synthetic trajectories', 'rollout_length': T,
+                      'columns_per_gpu': B, 'global_batch': B * world, 'num_actions': A, 'optimizer': 'rmsprop'},
+           'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+           'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--T', type=int, default=T_DEFAULT)
+    ap.add_argument('--B', type=int, default=B_DEFAULT, help='columns per GPU')
+    ap.add_argument('--A', type=int, default=A_DEFAULT)
+    ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU-baseline work (rank 0, N=1)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('launch with torch.distributed.run --nproc-per-node N for --gpus N > 1')
+
+    import torch
+    import torch.distributed as dist
+    from scalerl_b200.learner import B200ImpalaLearner, ImpalaHParams
+    from scalerl_b200.data.feeder import HostBatchFeeder, H2D_KEYS
+    from scalerl_b200 import _lib
+    import ctypes as C
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    T, B, A, K, W = args.T, args.B, args.A, args.steps, args.warmup
+    hp = ImpalaHParams(rollout_length=T, batch_size=B, num_actions=A)
+    learner = B200ImpalaLearner(hp, device=dev, seed=0)
+    host_pool = make_host_pool(T, B, A, POOL, seed=rank)
+    dev_pool = [{k: v.to(dev, non_blocking=True) for k, v in hb.items()} for hb in host_pool]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput ----------------
+    for i in range(W):
+        learner.learn(dev_pool[i % POOL], sync_stats=False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        learner.learn(dev_pool[(W + i) % POOL], sync_stats=False)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    frames = K * T * B * world
+    value = frames / (ms_total * 1e-3)
+    losses_finite = bool(torch.isfinite(learner._losses).all().item())
+
+    # ---------------- end to end through the host-batch API ----------------
+    feeder = HostBatchFeeder(learner, depth=2)
+    def e2e_loop(n, off):
+        last = None
+        feeder.submit(host_pool[off % POOL])
+        for i in range(n):
+            if i + 1 < n:
+                feeder.submit(host_pool[(off + i + 1) % POOL])
+            s = feeder.learn()
+            if last is not None:
+                feeder.result(last)             # D2H read of the previous step's losses (one step behind)
+            last = s
+        return feeder.result(last)
+    e2e_loop(W, 0)
+    barrier()
+    t0 = time.perf_counter()
+    stats = e2e_loop(K, W)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+    e2e_s = max_over_ranks(dt)
+    e2e_value = frames / e2e_s
+
+    # ---------------- per-kernel durations (events around every launch) ----------------
+    L = _lib.lib()
+    _lib.check(L.srl_learner_set_profiling(learner._h, 1))
+    nslot = L.srl_profile_slot_count()
+    names = [L.srl_profile_slot_name(i).decode() for i in range(nslot)]
+    acc = [0.0] * nslot
+    buf = (C.c_float * nslot)()
+    nprof = min(K, 20)
+    for i in range(nprof):
+        learner.learn(dev_pool[i % POOL], sync_stats=False)
+        torch.cuda.synchronize()
+        _lib.check(L.srl_learner_profile_collect(learner._h, buf))
+        for j in range(nslot):
+            acc[j] += max(0.0, buf[j])
+    _lib.check(L.srl_learner_set_profiling(learner._h, 0))
+    per_kernel_ms = {names[j]: acc[j] / nprof for j in range(nslot)}
+    pk = peaks()
+    NF, NBk = (T + 1) * B, T * B
+    gemm = {}
+    for slot, (layer, which) in SLOT_FLOPS.items():
+        fl = 2.0 * MACS[layer] * (NF if which == 'fwd' else NBk)
+        ms = per_kernel_ms[slot]
+        gemm[slot] = {'ms': ms, 'gflop': fl / 1e9, 'tflops': fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
+    dom = max(gemm, key=lambda s: gemm[s]['ms'])
+    step_flops = NF * 18.693e6 + NBk * 30.833e6
+    sum_kernel_ms = sum(per_kernel_ms.values())
+    roofline = {'bound': 'tensor', 'kernel': dom, 'achieved': gemm[dom]['tflops'], 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s',
+                'frac': gemm[dom]['tflops'] / pk['bf16_tflops'], 'traffic': None, 'peak_source': pk['source'] + ' burst bf16 (MEASURED_PEAKS.json)',
+                'flops_per_launch': gemm[dom]['gflop'] * 1e9, 'ms_per_launch': gemm[dom]['ms'],
+                'how': f'CUDA events around each launch on the launch stream, mean of {nprof} steps after the timed region',
+                'step': {'gflop': step_flops / 1e9, 'tflops_device_resident': step_flops / (ms_total / K * 1e-3) / 1e12,
+                         'frac_of_peak': step_flops / (ms_total / K * 1e-3) / 1e12 / pk['bf16_tflops'], 'sum_kernel_ms': sum_kernel_ms},
+                'per_kernel_ms': {k: round(v, 5) for k, v in per_kernel_ms.items()},
+                'per_gemm_tflops': {k: round(v['tflops'], 2) for k, v in gemm.items()}}
+
+    # ---------------- CPU baseline (rank 0, N=1) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fps, n, s_per, cores = cpu_learner_fps(T, B, A, args.cpu_budget)
+        cpu = {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+               'sample': f'{n} full learner steps of the same workload (T={T}, B={B}, fp32 torch-CPU autograd + RMSprop), {s_per * 1e3:.1f} ms/step'}
+
+    if rank == 0:
+        out = {'metric': 'learner_frames_per_sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+               'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+               'data': 'synthetic',
+               'config': {'workload': f'IMPALA Pong 84x84x4 uint8, T={T}, B={B}/GPU, A={A}, synthetic trajectories (BASELINE.json configs[1] per GPU)',
+                          'rollout_length': T, 'columns_per_gpu': B, 'global_batch': B * world, 'num_actions': A, 'optimizer': 'rmsprop',
+                          'parallelism': f'dp{world}' if world > 1 else 'single', 'grad_allreduce': 'nccl sum' if world > 1 else 'none',
+                          'l2': f'inputs cycle through {POOL} distinct batches ({POOL * feeder.h2d_bytes / 1e6:.0f} MB > 126 MB L2)',
+                          'operands': 'bf16 tensor-core operands, fp32 accumulate, fp32 master weights / V-trace / optimizer'},
+               'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': feeder.h2d_bytes, 'd2h_bytes_per_step': feeder.d2h_bytes,
+                       'ms_per_step': e2e_s / K * 1e3, 'api': 'HostBatchFeeder.submit/learn/result + B200ImpalaLearner.learn (pinned host batches)',
+                       'last_total_loss': stats['total_loss']},
+               'gpu_launches': 22 * K, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'losses_finite': losses_finite}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -117,6 +117,18 @@ int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_out, void* st
  * "dlogits","dbaseline","dh","da3","da2","da1","wpack"}; returns device pointer + element count. */
 int srl_learner_debug_buffer(srl_learner_t* L, const char* name, void** ptr, int64_t* count);
 
+/* per-kernel timing of one learner step: when enabled every kernel launch of forward_backward /
+ * apply_gradients is bracketed by cudaEventRecord on the caller's stream; profile_collect() synchronises
+ * on those events and writes milliseconds per slot (-1 for slots not executed) to a HOST array of
+ * srl_profile_slot_count() floats. */
+int srl_learner_set_profiling(srl_learner_t* L, int enable);
+int srl_profile_slot_count(void);
+const char* srl_profile_slot_name(int slot);
+int srl_learner_profile_collect(srl_learner_t* L, float* ms_out_host);
+
+/* asynchronous device-to-device copy on `stream` (used by tests to read the borrowed buffers) */
+int srl_memcpy_d2d(void* dst, const void* src, int64_t bytes, void* stream);
+
 /* ---- stand-alone optimizer ops (flat f32 buffers of n elements) ------------------------------------------
  * srl_grad_norm_clip_coef: coef[0] = ||g||_2, coef[1] = min(1, max_norm/(||g||+1e-6)); scratch f32[>=1028]. */
 int srl_grad_norm_clip_coef(const float* grads, int64_t n, float max_norm, float* coef, float* scratch, void* stream);

@@ -42,9 +42,13 @@ _SIGS = {
     'srl_adam_step': [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _I, _P],
     'srl_test_gemm_kmajor': [_P, _P, _P, _I, _I, _I, _I, _P],
     'srl_test_gemm_mnmajor': [_P, _P, _P, _I, _I, _I, _I, _P],
+    'srl_memcpy_d2d': [_P, _P, _L, _P],
+    'srl_learner_set_profiling': [_P, _I],
+    'srl_profile_slot_count': [],
+    'srl_learner_profile_collect': [_P, _P],
     'srl_version': [],
 }
-EXPORTS = sorted(list(_SIGS) + ['srl_last_error', 'srl_param_layout', 'srl_learner_workspace_bytes'])
+EXPORTS = sorted(list(_SIGS) + ['srl_last_error', 'srl_param_layout', 'srl_learner_workspace_bytes', 'srl_profile_slot_name'])
 
 
 def lib():
@@ -62,6 +66,8 @@ def lib():
         L.srl_last_error.argtypes = []
         L.srl_param_layout.restype = C.c_int64
         L.srl_param_layout.argtypes = [_I, C.POINTER(_L), C.POINTER(_L)]
+        L.srl_profile_slot_name.restype = C.c_char_p
+        L.srl_profile_slot_name.argtypes = [_I]
         L.srl_learner_workspace_bytes.restype = C.c_int64
         L.srl_learner_workspace_bytes.argtypes = [_P]
         _lib = L

@@ -141,7 +141,15 @@ struct srl_learner {
   int64_t arena_bytes;
   int step;                       // optimizer step count (Adam bias correction)
   bool have_fwd;
+  Profiler pf;                    // per-kernel event bracketing (off by default)
+  cudaEvent_t events[2 * PS_COUNT];
+  bool slot_used[PS_COUNT];
 };
+
+static const char* kSlotNames[PS_COUNT] = {"conv1_fwd", "conv2_fwd", "conv3_fwd", "fc_fwd", "head_fwd", "vtrace_loss_tail", "zero_grads",
+                                           "head_bwd", "fc_bias_grad", "fc_wgrad", "fc_dgrad", "conv3_bias_grad", "conv3_wgrad",
+                                           "conv3_dgrad", "conv2_bias_grad", "conv2_wgrad", "conv2_dgrad", "conv1_bias_grad",
+                                           "conv1_wgrad", "grad_norm", "optimizer", "pack_weights"};
 
 static int check_cfg(const srl_config_t* c) {
   REQ(c, "config is NULL");
@@ -166,6 +174,8 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   L->P = make_ptrs(params, cfg->A);
   L->G = make_ptrs(grads, cfg->A);
   L->step = 0; L->have_fwd = false;
+  for (int i = 0; i < 2 * PS_COUNT; ++i) L->events[i] = nullptr;
+  for (int i = 0; i < PS_COUNT; ++i) L->slot_used[i] = false;
   const int64_t NF = (int64_t)(cfg->T + 1) * cfg->B, NB = (int64_t)cfg->T * cfg->B, A = cfg->A;
   // carve one arena (256-byte aligned pieces)
   int64_t sizes[16]; int k = 0;
@@ -214,6 +224,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
 
 extern "C" int srl_learner_destroy(srl_learner_t* L) {
   if (!L) return 0;
+  for (int i = 0; i < 2 * PS_COUNT; ++i) if (L->events[i]) cudaEventDestroy(L->events[i]);
   cudaFree(L->arena);
   delete L;
   return 0;
@@ -238,8 +249,11 @@ extern "C" int srl_learner_pack_weights(srl_learner_t* L, void* stream) {
 
 static int forward_impl(srl_learner* L, const uint8_t* obs, const float* reward, const int64_t* action, int frames, float* logits,
                         float* baseline, cudaStream_t st) {
-  CU(encoder_forward(obs, frames, L->P, L->buf, L->cfg.simt_mainloop != 0, st), "encoder_forward");
+  L->pf.st = st;
+  CU(encoder_forward(obs, frames, L->P, L->buf, L->cfg.simt_mainloop != 0, st, L->pf), "encoder_forward");
+  L->pf.b(PS_HEAD_FWD);
   CU(launch_head_fwd(L->buf.h, reward, action, L->P.wp, L->P.bp, L->P.wb, L->P.bb, frames, L->cfg.A, logits, baseline, st), "head_fwd");
+  L->pf.e(PS_HEAD_FWD);
   return 0;
 }
 
@@ -261,13 +275,19 @@ extern "C" int srl_learner_forward_backward(srl_learner_t* L, const uint8_t* obs
   const int NF = (c.T + 1) * c.B, NB = c.T * c.B;
   int rc = forward_impl(L, obs, reward, action, NF, L->logits, L->baseline, st);
   if (rc) return rc;
+  L->pf.b(PS_TAIL);
   CU(launch_impala_tail(behavior_logits, L->logits, L->baseline, action, reward, done, c.T, c.B, c.A, c.discounting,
                         c.reward_clip_abs_one, c.clip_rho_threshold, c.clip_pg_rho_threshold, c.baseline_cost, c.entropy_cost, vs,
                         pg_advantages, L->dlogits, L->dbaseline, losses, L->scratch, st), "impala_tail");
+  L->pf.e(PS_TAIL);
+  L->pf.b(PS_ZERO_GRADS);
   CU(cudaMemsetAsync(L->grads, 0, L->nparams * sizeof(float), st), "zero grads");
+  L->pf.e(PS_ZERO_GRADS);
+  L->pf.b(PS_HEAD_BWD);
   CU(launch_head_bwd(L->dlogits, L->dbaseline, L->buf.h, reward, action, L->P.wp, L->P.wb, NB, c.A, L->buf.dh, L->G.wp, L->G.bp, L->G.wb,
                      L->G.bb, st), "head_bwd");
-  CU(encoder_backward(obs, NB, L->buf, L->G, c.simt_mainloop != 0, st), "encoder_backward");
+  L->pf.e(PS_HEAD_BWD);
+  CU(encoder_backward(obs, NB, L->buf, L->G, c.simt_mainloop != 0, st, L->pf), "encoder_backward");
   L->have_fwd = true;
   return 0;
 }
@@ -276,16 +296,52 @@ extern "C" int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_ou
   REQ(L, "learner is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   const srl_config_t& c = L->cfg;
+  L->pf.st = st;
+  L->pf.b(PS_GRAD_NORM);
   CU(launch_grad_norm(L->grads, L->nparams, c.max_grad_norm, L->coef, L->scratch + 2048, st), "grad_norm");
+  L->pf.e(PS_GRAD_NORM);
   L->step += 1;
+  L->pf.b(PS_OPTIMIZER);
   if (c.optimizer == 0) {
     CU(launch_rmsprop(L->params, L->grads, L->opt0, L->nparams, L->coef, c.learning_rate, c.alpha, c.epsilon, st), "rmsprop");
   } else {
     CU(launch_adam(L->params, L->grads, L->opt0, L->opt1, L->nparams, L->coef, c.learning_rate, c.adam_beta1, c.adam_beta2, c.adam_eps,
                    L->step, st), "adam");
   }
+  L->pf.e(PS_OPTIMIZER);
+  L->pf.b(PS_PACK);
   CU(launch_pack_weights(L->P, L->buf.wpack, st), "pack_weights");
+  L->pf.e(PS_PACK);
   if (grad_norm_out) CU(cudaMemcpyAsync(grad_norm_out, L->coef, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy coef");
+  return 0;
+}
+
+extern "C" int srl_learner_set_profiling(srl_learner_t* L, int enable) {
+  REQ(L, "learner is NULL");
+  if (enable && !L->events[0])
+    for (int i = 0; i < 2 * PS_COUNT; ++i) CU(cudaEventCreate(&L->events[i]), "cudaEventCreate");
+  L->pf.on = enable != 0;
+  L->pf.ev = L->events;
+  return 0;
+}
+extern "C" int srl_profile_slot_count(void) { return PS_COUNT; }
+extern "C" const char* srl_profile_slot_name(int slot) { return (slot >= 0 && slot < PS_COUNT) ? kSlotNames[slot] : ""; }
+extern "C" int srl_learner_profile_collect(srl_learner_t* L, float* ms_out_host) {
+  REQ(L && ms_out_host, "profile_collect: NULL argument");
+  REQ(L->pf.on, "profile_collect: profiling is off");
+  for (int i = 0; i < PS_COUNT; ++i) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(L->events[2 * i + 1]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, L->events[2 * i], L->events[2 * i + 1]);
+    if (e != cudaSuccess) { cudaGetLastError(); ms = -1.f; }   // slot not recorded in the last step
+    ms_out_host[i] = ms;
+  }
+  return 0;
+}
+
+extern "C" int srl_memcpy_d2d(void* dst, const void* src, int64_t bytes, void* stream) {
+  REQ(dst && src && bytes >= 0, "memcpy_d2d: bad argument");
+  CU(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "memcpy_d2d");
   return 0;
 }
 

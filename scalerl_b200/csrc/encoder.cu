@@ -43,16 +43,17 @@ cudaError_t launch_pack_weights(const ParamPtrs& p, bf16* wpack, cudaStream_t st
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, bool simt, cudaStream_t st) {
+cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, bool simt, cudaStream_t st,
+                            const Profiler& pf) {
   if (frames <= 0) return cudaSuccess;
   { Conv1Fwd::Params q{obs, buf.wpack + WPack::W1K, p.b1, buf.a1, frames * 400};
-    SRL_TRY(igemm_launch<Conv1Fwd>(q, dim3(cdiv(q.M, 128), 1), st, simt)); }
+    pf.b(PS_CONV1_FWD); SRL_TRY(igemm_launch<Conv1Fwd>(q, dim3(cdiv(q.M, 128), 1), st, simt)); pf.e(PS_CONV1_FWD); }
   { Conv2Fwd::Params q{buf.a1, buf.wpack + WPack::W2K, p.b2, buf.a2, frames * 81};
-    SRL_TRY(igemm_launch<Conv2Fwd>(q, dim3(cdiv(q.M, 128), 1), st, simt)); }
+    pf.b(PS_CONV2_FWD); SRL_TRY(igemm_launch<Conv2Fwd>(q, dim3(cdiv(q.M, 128), 1), st, simt)); pf.e(PS_CONV2_FWD); }
   { Conv3Fwd::Params q{buf.a2, buf.wpack + WPack::W3K, p.b3, buf.a3, frames * 49};
-    SRL_TRY(igemm_launch<Conv3Fwd>(q, dim3(cdiv(q.M, 128), 1), st, simt)); }
+    pf.b(PS_CONV3_FWD); SRL_TRY(igemm_launch<Conv3Fwd>(q, dim3(cdiv(q.M, 128), 1), st, simt)); pf.e(PS_CONV3_FWD); }
   { FcFwd::Params q{buf.a3, buf.wpack + WPack::WFK, p.bf, buf.h, frames};
-    SRL_TRY(igemm_launch<FcFwd>(q, dim3(cdiv(q.M, 128), 8), st, simt)); }
+    pf.b(PS_FC_FWD); SRL_TRY(igemm_launch<FcFwd>(q, dim3(cdiv(q.M, 128), 8), st, simt)); pf.e(PS_FC_FWD); }
   return cudaSuccess;
 }
 
@@ -64,34 +65,35 @@ static inline void split_k(int P, int target, int* pps, int* nsplit) {
   *nsplit = cdiv(P, per);
 }
 
-cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, bool simt, cudaStream_t st) {
+cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, bool simt, cudaStream_t st,
+                             const Profiler& pf) {
   if (frames <= 0) return cudaSuccess;
   int pps, ns;
   // ---- fc: bias, wgrad, dgrad
-  SRL_TRY(launch_colsum_bf16(buf.dh, frames, 512, g.bf, st));
+  pf.b(PS_FC_BIAS); SRL_TRY(launch_colsum_bf16(buf.dh, frames, 512, g.bf, st)); pf.e(PS_FC_BIAS);
   { FcWgrad::Params q{buf.dh, buf.a3, g.wf, frames};
-    SRL_TRY(igemm_launch<FcWgrad>(q, dim3(1, 4 * 49), st, simt)); }
+    pf.b(PS_FC_WGRAD); SRL_TRY(igemm_launch<FcWgrad>(q, dim3(1, 4 * 49), st, simt)); pf.e(PS_FC_WGRAD); }
   { FcDgrad::Params q{buf.dh, buf.wpack + WPack::WFD, buf.a3, buf.da3, frames};
-    SRL_TRY(igemm_launch<FcDgrad>(q, dim3(cdiv(frames, 128), 49), st, simt)); }
+    pf.b(PS_FC_DGRAD); SRL_TRY(igemm_launch<FcDgrad>(q, dim3(cdiv(frames, 128), 49), st, simt)); pf.e(PS_FC_DGRAD); }
   // ---- conv3
-  SRL_TRY(launch_colsum_bf16(buf.da3, frames * 49, 64, g.b3, st));
+  pf.b(PS_CONV3_BIAS); SRL_TRY(launch_colsum_bf16(buf.da3, frames * 49, 64, g.b3, st)); pf.e(PS_CONV3_BIAS);
   { split_k(frames * 49, 29, &pps, &ns);
     Conv3Wgrad::Params q{buf.a2, buf.da3, g.w3, frames * 49, pps};
-    SRL_TRY(igemm_launch<Conv3Wgrad>(q, dim3(ns, 5), st, simt)); }
+    pf.b(PS_CONV3_WGRAD); SRL_TRY(igemm_launch<Conv3Wgrad>(q, dim3(ns, 5), st, simt)); pf.e(PS_CONV3_WGRAD); }
   { Conv3Dgrad::Params q{buf.da3, buf.wpack + WPack::W3D, buf.a2, buf.da2, frames * 81};
-    SRL_TRY(igemm_launch<Conv3Dgrad>(q, dim3(cdiv(q.M, 128), 1), st, simt)); }
+    pf.b(PS_CONV3_DGRAD); SRL_TRY(igemm_launch<Conv3Dgrad>(q, dim3(cdiv(q.M, 128), 1), st, simt)); pf.e(PS_CONV3_DGRAD); }
   // ---- conv2
-  SRL_TRY(launch_colsum_bf16(buf.da2, frames * 81, 64, g.b2, st));
+  pf.b(PS_CONV2_BIAS); SRL_TRY(launch_colsum_bf16(buf.da2, frames * 81, 64, g.b2, st)); pf.e(PS_CONV2_BIAS);
   { split_k(frames * 81, 37, &pps, &ns);
     Conv2Wgrad::Params q{buf.a1, buf.da2, g.w2, frames * 81, pps};
-    SRL_TRY(igemm_launch<Conv2Wgrad>(q, dim3(ns, 4), st, simt)); }
+    pf.b(PS_CONV2_WGRAD); SRL_TRY(igemm_launch<Conv2Wgrad>(q, dim3(ns, 4), st, simt)); pf.e(PS_CONV2_WGRAD); }
   { Conv2Dgrad::Params q{buf.da2, buf.wpack + WPack::W2D, buf.a1, buf.da1, frames * 100};
-    SRL_TRY(igemm_launch<Conv2Dgrad>(q, dim3(cdiv(q.M, 128), 4), st, simt)); }
+    pf.b(PS_CONV2_DGRAD); SRL_TRY(igemm_launch<Conv2Dgrad>(q, dim3(cdiv(q.M, 128), 4), st, simt)); pf.e(PS_CONV2_DGRAD); }
   // ---- conv1 (no dgrad: the frame is the network input)
-  SRL_TRY(launch_colsum_bf16(buf.da1, frames * 400, 32, g.b1, st));
+  pf.b(PS_CONV1_BIAS); SRL_TRY(launch_colsum_bf16(buf.da1, frames * 400, 32, g.b1, st)); pf.e(PS_CONV1_BIAS);
   { split_k(frames * 400, 74, &pps, &ns);
     Conv1Wgrad::Params q{obs, buf.da1, g.w1, frames * 400, pps};
-    SRL_TRY(igemm_launch<Conv1Wgrad>(q, dim3(ns, 2), st, simt)); }
+    pf.b(PS_CONV1_WGRAD); SRL_TRY(igemm_launch<Conv1Wgrad>(q, dim3(ns, 2), st, simt)); pf.e(PS_CONV1_WGRAD); }
   return cudaSuccess;
 }
 

@@ -6,6 +6,18 @@
 
 namespace srl {
 
+// per-kernel CUDA-event bracketing (bench.py's roofline numbers): slots of one learner step
+enum ProfSlot { PS_CONV1_FWD = 0, PS_CONV2_FWD, PS_CONV3_FWD, PS_FC_FWD, PS_HEAD_FWD, PS_TAIL, PS_ZERO_GRADS, PS_HEAD_BWD,
+                PS_FC_BIAS, PS_FC_WGRAD, PS_FC_DGRAD, PS_CONV3_BIAS, PS_CONV3_WGRAD, PS_CONV3_DGRAD, PS_CONV2_BIAS, PS_CONV2_WGRAD,
+                PS_CONV2_DGRAD, PS_CONV1_BIAS, PS_CONV1_WGRAD, PS_GRAD_NORM, PS_OPTIMIZER, PS_PACK, PS_COUNT };
+struct Profiler {
+  bool on = false;
+  cudaEvent_t* ev = nullptr;   // 2 * PS_COUNT events
+  cudaStream_t st = nullptr;
+  void b(int slot) const { if (on) cudaEventRecord(ev[2 * slot], st); }
+  void e(int slot) const { if (on) cudaEventRecord(ev[2 * slot + 1], st); }
+};
+
 // ---- vtrace.cu
 cudaError_t launch_vtrace_iw(const float* log_rhos, const float* discounts, const float* rewards, const float* values,
                              const float* bootstrap, int T, int B, float clip_rho, float clip_pg, float* vs, float* pg, int variant,
@@ -54,9 +66,11 @@ struct EncoderBuffers {
   __nv_bfloat16* wpack;
 };
 cudaError_t launch_pack_weights(const ParamPtrs& p, __nv_bfloat16* wpack, cudaStream_t st);
-cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, bool simt, cudaStream_t st);
+cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, bool simt, cudaStream_t st,
+                            const Profiler& pf);
 // backward for the first `frames` frames given buf.dh; accumulates into the (pre-zeroed) gradient tensors in `g`
-cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, bool simt, cudaStream_t st);
+cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, bool simt, cudaStream_t st,
+                             const Profiler& pf);
 cudaError_t test_gemm(const void* A, const void* B, float* D, int M, int N, int K, bool mn_major, bool simt, cudaStream_t st);
 
 }  // namespace srl

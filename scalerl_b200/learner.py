@@ -271,10 +271,8 @@ class B200ImpalaLearner:
         dt = torch.float32 if fp32 else torch.bfloat16
         nbytes = n.value * (4 if fp32 else 2)
         out = torch.empty(n.value, dtype=dt, device=self.device)
+        _lib.check(self._L.srl_memcpy_d2d(out.data_ptr(), p.value, nbytes, self._stream()), 'memcpy_d2d')
         torch.cuda.current_stream(self.device).synchronize()
-        rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), p.value, nbytes, 3)   # cudaMemcpyDeviceToDevice
-        if int(rc) != 0:
-            raise RuntimeError(f'cudaMemcpy failed: {rc}')
         return out
 
     def close(self):
