@@ -51,7 +51,7 @@ int srl_vtrace_from_logits(const float* behavior_policy_logits, const float* tar
  *   (learner outputs), action i64 [T+1,B], reward f32 [T+1,B], done u8/bool [T+1,B].
  * Outputs: vs, pg_advantages f32 [T,B]; dlogits f32 [T,B,A]; dbaseline f32 [T,B];
  *   losses f32 [4] = {pg_loss, baseline_loss (x baseline_cost), entropy_loss (x entropy_cost), total}.
- * scratch: f32 [3*ceil(B/128)+4] workspace (block partials + ticket). */
+ * scratch: zero-initialised f32 [3*ceil(B/4)+4] workspace (block partials + ticket; re-armed by the kernel). */
 int srl_impala_loss_and_head_grads(const float* behavior_logits, const float* target_logits, const float* baseline,
                                    const int64_t* action, const float* reward, const uint8_t* done,
                                    int T, int B, int A, float discounting, int reward_clip_abs_one,

@@ -146,10 +146,9 @@ struct srl_learner {
   bool slot_used[PS_COUNT];
 };
 
-static const char* kSlotNames[PS_COUNT] = {"conv1_fwd", "conv2_fwd", "conv3_fwd", "fc_fwd", "head_fwd", "vtrace_loss_tail", "zero_grads",
-                                           "head_bwd", "fc_bias_grad", "fc_wgrad", "fc_dgrad", "conv3_bias_grad", "conv3_wgrad",
-                                           "conv3_dgrad", "conv2_bias_grad", "conv2_wgrad", "conv2_dgrad", "conv1_bias_grad",
-                                           "conv1_wgrad", "grad_norm", "optimizer", "pack_weights"};
+static const char* kSlotNames[PS_COUNT] = {"obs_s2d", "conv1_fwd", "conv2_fwd", "conv3_fwd", "fc_fwd", "head_fwd", "vtrace_loss_tail",
+                                           "zero_grads", "head_bwd", "fc_wgrad", "fc_dgrad", "conv3_wgrad", "conv3_dgrad", "conv2_wgrad",
+                                           "conv2_dgrad", "conv1_wgrad", "grad_norm", "optimizer", "pack_weights"};
 
 static int check_cfg(const srl_config_t* c) {
   REQ(c, "config is NULL");
@@ -178,8 +177,10 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   for (int i = 0; i < PS_COUNT; ++i) L->slot_used[i] = false;
   const int64_t NF = (int64_t)(cfg->T + 1) * cfg->B, NB = (int64_t)cfg->T * cfg->B, A = cfg->A;
   // carve one arena (256-byte aligned pieces)
-  int64_t sizes[16]; int k = 0;
+  int64_t sizes[20]; int k = 0;
   auto al = [](int64_t b) { return (b + 255) & ~int64_t(255); };
+  sizes[k++] = al(NF * 441 * 64 * 2);   // xs
+  sizes[k++] = al((int64_t)FC_SPLITS * NF * 512 * 4);   // hpart
   sizes[k++] = al(NF * 400 * 32 * 2);   // a1
   sizes[k++] = al(NF * 81 * 64 * 2);    // a2
   sizes[k++] = al(NF * 49 * 64 * 2);    // a3
@@ -203,6 +204,8 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   if (e != cudaSuccess) { cudaFree(L->arena); delete L; return cuda_fail(e, "learner_create: cudaMemset"); }
   L->arena_bytes = total;
   char* q = L->arena; int i = 0;
+  L->buf.xs = (__nv_bfloat16*)q; q += sizes[i++];
+  L->buf.hpart = (float*)q; q += sizes[i++];
   L->buf.a1 = (__nv_bfloat16*)q; q += sizes[i++];
   L->buf.a2 = (__nv_bfloat16*)q; q += sizes[i++];
   L->buf.a3 = (__nv_bfloat16*)q; q += sizes[i++];
@@ -252,7 +255,8 @@ static int forward_impl(srl_learner* L, const uint8_t* obs, const float* reward,
   L->pf.st = st;
   CU(encoder_forward(obs, frames, L->P, L->buf, L->cfg.simt_mainloop != 0, st, L->pf), "encoder_forward");
   L->pf.b(PS_HEAD_FWD);
-  CU(launch_head_fwd(L->buf.h, reward, action, L->P.wp, L->P.bp, L->P.wb, L->P.bb, frames, L->cfg.A, logits, baseline, st), "head_fwd");
+  CU(launch_head_fwd(L->buf.hpart, FC_SPLITS, L->P.bf, L->buf.h, reward, action, L->P.wp, L->P.bp, L->P.wb, L->P.bb, frames, L->cfg.A,
+                     logits, baseline, st), "head_fwd");
   L->pf.e(PS_HEAD_FWD);
   return 0;
 }
@@ -349,7 +353,7 @@ extern "C" int srl_learner_debug_buffer(srl_learner_t* L, const char* name, void
   REQ(L && name && ptr && count, "debug_buffer: NULL argument");
   const int64_t NF = (int64_t)(L->cfg.T + 1) * L->cfg.B, NB = (int64_t)L->cfg.T * L->cfg.B, A = L->cfg.A;
   struct { const char* n; void* p; int64_t c; } tab[] = {
-      {"a1", L->buf.a1, NF * 400 * 32}, {"a2", L->buf.a2, NF * 81 * 64}, {"a3", L->buf.a3, NF * 49 * 64}, {"h", L->buf.h, NF * 512},
+      {"xs", L->buf.xs, NF * 441 * 64}, {"a1", L->buf.a1, NF * 400 * 32}, {"a2", L->buf.a2, NF * 81 * 64}, {"a3", L->buf.a3, NF * 49 * 64}, {"h", L->buf.h, NF * 512},
       {"logits", L->logits, NF * A}, {"baseline", L->baseline, NF}, {"dlogits", L->dlogits, NB * A}, {"dbaseline", L->dbaseline, NB},
       {"dh", L->buf.dh, NB * 512}, {"da3", L->buf.da3, NB * 49 * 64}, {"da2", L->buf.da2, NB * 81 * 64},
       {"da1", L->buf.da1, NB * 400 * 32}, {"wpack", L->buf.wpack, WPack::TOTAL}};

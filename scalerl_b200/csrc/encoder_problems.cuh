@@ -51,42 +51,16 @@ SRL_DEVINL void relu_mask16(const bf16* mask, float (&v)[16]) {
 // ============================================================================================
 // forward
 // ============================================================================================
-struct Conv1Fwd {   // atari_model.py:30-35,94,97 : x/255 -> conv 8x8 s4 (4->32) -> ReLU
-  static constexpr int BN = 32, STAGES = 4;
+// conv1 (8x8 s4 over the u8 frame == 2x2 s1 over the space-to-depth bf16 frame xs[N,21,21,64], 64 = (c,dy,dx)),
+// conv2 (4x4 s2, 32->64) and conv3 (3x3 s1, 64->64): K ordered (kh, kw, c); one K-block = 64 contiguous bf16.
+// SCALE255: conv1 multiplies the fp32 accumulator by 1/255 (the reference normalises its input, atari_model.py:94).
+template <int IH, int OH, int CIN, int COUT, int KH, int KW, int STRIDE, bool SCALE255>
+struct ConvFwd {   // atari_model.py:30-43,97-99
+  static constexpr int BN = COUT, STAGES = COUT <= 32 ? 4 : 3;
   static constexpr bool A_MN = false, B_MN = false;
-  struct Params { const uint8_t* obs; const bf16* w; const float* bias; bf16* out; int M; };
-  typedef int RowA;           // byte offset of (n, 4*oh, 4*ow) in channel 0, or -1
-  typedef const bf16* RowB;
-  SRL_DEVINL static int num_kblocks(const Params&, int, int) { return 4; }     // one per input channel
-  SRL_DEVINL static RowA make_rowA(const Params& p, int tm, int, int srow) {
-    const int m = tm * 128 + srow;
-    if (m >= p.M) return -1;
-    const int n = m / 400, r = m - n * 400, oh = r / 20, ow = r - oh * 20;
-    return n * 28224 + oh * 336 + ow * 4;
-  }
-  SRL_DEVINL static RowB make_rowB(const Params& p, int, int, int srow) { return p.w + srow * 256; }
-  SRL_DEVINL static uint4 load_A(const Params& p, RowA base, int kb, int chunk) {   // kb = c, chunk = kh, 8 x kw
-    if (base < 0) return zero16();
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(p.obs + base + kb * 7056 + chunk * 84);
-    return u8x8_to_bf16x8(__ldg(q), __ldg(q + 1));
-  }
-  SRL_DEVINL static uint4 load_B(const Params&, RowB w, int kb, int chunk) { return ldg16(w + kb * 64 + chunk * 8); }
-  SRL_DEVINL static void epilogue16(const Params& p, int tm, int, int row, int c0, float (&v)[16]) {
-    const int m = tm * 128 + row;
-    if (m >= p.M) return;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(fmaf(v[j], 1.0f / 255.0f, __ldg(p.bias + c0 + j)), 0.f);
-    store_bf16x16(p.out + (size_t)m * 32 + c0, v);
-  }
-};
-
-// conv2 (4x4 s2, 32->64) and conv3 (3x3 s1, 64->64): K ordered (kh, kw, c); one K-block = 64 contiguous bf16
-template <int IH, int OH, int CIN, int KH, int KW, int STRIDE>
-struct ConvFwd {   // atari_model.py:36-43,98-99
-  static constexpr int BN = 64, STAGES = 3;
-  static constexpr bool A_MN = false, B_MN = false;
+  static constexpr int BIAS = 0, BIAS_N = 0;
   static constexpr int KTOT = KH * KW * CIN;
-  static constexpr int TAPS_PER_KB = 64 / CIN;       // conv2: 2 kw taps per K-block; conv3: 1
+  static constexpr int TAPS_PER_KB = 64 / CIN;       // conv2: 2 kw taps per K-block; conv1/conv3: 1
   static constexpr int KB_PER_KH = KW / TAPS_PER_KB;
   struct Params { const bf16* in; const bf16* w; const float* bias; bf16* out; int M; };
   typedef int RowA;
@@ -109,25 +83,31 @@ struct ConvFwd {   // atari_model.py:36-43,98-99
     const int m = tm * 128 + row;
     if (m >= p.M) return;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + __ldg(p.bias + c0 + j), 0.f);
-    store_bf16x16(p.out + (size_t)m * 64 + c0, v);
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(fmaf(v[j], SCALE255 ? 1.0f / 255.0f : 1.0f, __ldg(p.bias + c0 + j)), 0.f);
+    store_bf16x16(p.out + (size_t)m * COUT + c0, v);
   }
 };
-typedef ConvFwd<20, 9, 32, 4, 4, 2> Conv2Fwd;
-typedef ConvFwd<9, 7, 64, 3, 3, 1> Conv3Fwd;
+typedef ConvFwd<21, 20, 64, 32, 2, 2, 1, true> Conv1Fwd;
+typedef ConvFwd<20, 9, 32, 64, 4, 4, 2, false> Conv2Fwd;
+typedef ConvFwd<9, 7, 64, 64, 3, 3, 1, false> Conv3Fwd;
 
-struct FcFwd {   // atari_model.py:46,100-101 : h = relu(a3_flat @ Wfc^T + b), fp32 out; grid.y = 512/64
-  static constexpr int BN = 64, STAGES = 3;
+struct FcFwd {   // atari_model.py:46,100 : split-K partials hpart[split][m][512] = a3_flat @ Wfc^T (bias + ReLU are applied by
+                  // head_fwd_kernel, which reduces the FC_SPLITS partials);  grid.y = (512/64) * FC_SPLITS,  ty = nt*FC_SPLITS + split
+  static constexpr int BN = 64, STAGES = 3, FC_SPLITS = 4;
   static constexpr bool A_MN = false, B_MN = false;
-  struct Params { const bf16* in; const bf16* w; const float* bias; float* out; int M; };
+  static constexpr int BIAS = 0, BIAS_N = 0;
+  struct Params { const bf16* in; const bf16* w; float* out; int M; };
   typedef int RowA;
   typedef const bf16* RowB;
-  SRL_DEVINL static int num_kblocks(const Params&, int, int) { return 49; }
-  SRL_DEVINL static RowA make_rowA(const Params& p, int tm, int, int srow) {
+  SRL_DEVINL static int kb_begin(int split) { return (49 * split) / FC_SPLITS; }
+  SRL_DEVINL static int num_kblocks(const Params&, int, int ty) { const int sp = ty % FC_SPLITS; return kb_begin(sp + 1) - kb_begin(sp); }
+  SRL_DEVINL static RowA make_rowA(const Params& p, int tm, int ty, int srow) {
     const int m = tm * 128 + srow;
-    return m < p.M ? m * 3136 : -1;
+    return m < p.M ? m * 3136 + kb_begin(ty % FC_SPLITS) * 64 : -1;
   }
-  SRL_DEVINL static RowB make_rowB(const Params& p, int, int ty, int srow) { return p.w + (size_t)(ty * 64 + srow) * 3136; }
+  SRL_DEVINL static RowB make_rowB(const Params& p, int, int ty, int srow) {
+    return p.w + (size_t)((ty / FC_SPLITS) * 64 + srow) * 3136 + kb_begin(ty % FC_SPLITS) * 64;
+  }
   SRL_DEVINL static uint4 load_A(const Params& p, RowA base, int kb, int chunk) {
     return base < 0 ? zero16() : ldg16(p.in + base + kb * 64 + chunk * 8);
   }
@@ -135,10 +115,7 @@ struct FcFwd {   // atari_model.py:46,100-101 : h = relu(a3_flat @ Wfc^T + b), f
   SRL_DEVINL static void epilogue16(const Params& p, int tm, int ty, int row, int c0, float (&v)[16]) {
     const int m = tm * 128 + row;
     if (m >= p.M) return;
-    const int n0 = ty * 64 + c0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + __ldg(p.bias + n0 + j), 0.f);
-    float4* o = reinterpret_cast<float4*>(p.out + (size_t)m * 512 + n0);
+    float4* o = reinterpret_cast<float4*>(p.out + ((size_t)(ty % FC_SPLITS) * p.M + m) * 512 + (ty / FC_SPLITS) * 64 + c0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
@@ -150,6 +127,7 @@ struct FcFwd {   // atari_model.py:46,100-101 : h = relu(a3_flat @ Wfc^T + b), f
 struct FcDgrad {   // da3[m][i] = (sum_j dh[m][j] * Wfc[j][i]) * (a3 > 0);  grid.y = 3136/64
   static constexpr int BN = 64, STAGES = 3;
   static constexpr bool A_MN = false, B_MN = false;
+  static constexpr int BIAS = 0, BIAS_N = 0;
   struct Params { const bf16* dh; const bf16* wd; const bf16* a3; bf16* da3; int M; };
   typedef int RowA;
   typedef const bf16* RowB;
@@ -175,6 +153,7 @@ struct FcDgrad {   // da3[m][i] = (sum_j dh[m][j] * Wfc[j][i]) * (a3 > 0);  grid
 struct Conv3Dgrad {   // da2[n,ih,iw,c] = sum_{kh,kw,co} da3[n,ih-kh,iw-kw,co] W3[co][c][kh][kw], masked by a2>0
   static constexpr int BN = 64, STAGES = 3;
   static constexpr bool A_MN = false, B_MN = false;
+  static constexpr int BIAS = 0, BIAS_N = 0;
   struct Params { const bf16* dy; const bf16* wd; const bf16* act; bf16* dx; int M; };   // M = frames*81
   typedef int RowA;   // (n*7*7) << 8 | ih << 4 | iw, or -1
   typedef const bf16* RowB;
@@ -206,6 +185,7 @@ struct Conv3Dgrad {   // da2[n,ih,iw,c] = sum_{kh,kw,co} da3[n,ih-kh,iw-kw,co] W
 struct Conv2Dgrad {   // stride-2 transposed conv split in 4 parity classes (grid.y = ph*2+pw); K = (kh',kw',co) = 256
   static constexpr int BN = 32, STAGES = 4;
   static constexpr bool A_MN = false, B_MN = false;
+  static constexpr int BIAS = 0, BIAS_N = 0;
   struct Params { const bf16* dy; const bf16* wd; const bf16* act; bf16* dx; int M; };   // M = frames*100 per class
   typedef int RowA;   // (n*81) << 8 | i' << 4 | j'
   typedef const bf16* RowB;
@@ -240,10 +220,12 @@ struct Conv2Dgrad {   // stride-2 transposed conv split in 4 parity classes (gri
 //   CTA (blockIdx.x = split s of the contraction range, blockIdx.y = which 128-row slice of dW)
 //   conv wgrads accumulate with fp32 atomics into the (pre-zeroed) PyTorch-layout gradient.
 // ============================================================================================
-struct Conv3Wgrad {   // dW3[co][c][kh][kw] = sum_p da3[p][co] * a2[n,oh+kh,ow+kw,c];  grid.y = 5 tap pairs
+struct Conv3Wgrad {   // dW3[co][c][kh][kw] = sum_p da3[p][co] * a2[n,oh+kh,ow+kw,c];  grid.y = 5 tap pairs; db3 = colsum(da3)
   static constexpr int BN = 64, STAGES = 3;
   static constexpr bool A_MN = true, B_MN = true;
-  struct Params { const bf16* act; const bf16* dy; float* dw; int P; int pps; };   // P = frames*49, pps % 64 == 0
+  static constexpr int BIAS = 2, BIAS_N = 64;
+  struct Params { const bf16* act; const bf16* dy; float* dw; float* db; int P; int pps; };   // P = frames*49, pps % 64 == 0
+  SRL_DEVINL static float* bias_dst(const Params& p, int, int ty) { return ty == 0 ? p.db : nullptr; }
   struct RowA { int krow; int tapoff; };   // tapoff = (kh*9+kw)*64 or -1 (tap 9 does not exist)
   typedef int RowB;
   SRL_DEVINL static int num_kblocks(const Params& p, int tm, int) {
@@ -274,10 +256,12 @@ struct Conv3Wgrad {   // dW3[co][c][kh][kw] = sum_p da3[p][co] * a2[n,oh+kh,ow+k
   }
 };
 
-struct Conv2Wgrad {   // dW2[co][c][kh][kw] = sum_p da2[p][co] * a1[n,2oh+kh,2ow+kw,c];  grid.y = kh, rows = (kw, c)
+struct Conv2Wgrad {   // dW2[co][c][kh][kw] = sum_p da2[p][co] * a1[n,2oh+kh,2ow+kw,c];  grid.y = kh, rows = (kw, c); db2 = colsum(da2)
   static constexpr int BN = 64, STAGES = 3;
   static constexpr bool A_MN = true, B_MN = true;
-  struct Params { const bf16* act; const bf16* dy; float* dw; int P; int pps; };   // P = frames*81
+  static constexpr int BIAS = 2, BIAS_N = 64;
+  struct Params { const bf16* act; const bf16* dy; float* dw; float* db; int P; int pps; };   // P = frames*81
+  SRL_DEVINL static float* bias_dst(const Params& p, int, int ty) { return ty == 0 ? p.db : nullptr; }
   struct RowA { int krow; int off; };    // off = kh*20*32 + block*64
   typedef int RowB;
   SRL_DEVINL static int num_kblocks(const Params& p, int tm, int) {
@@ -306,27 +290,28 @@ struct Conv2Wgrad {   // dW2[co][c][kh][kw] = sum_p da2[p][co] * a1[n,2oh+kh,2ow
   }
 };
 
-struct Conv1Wgrad {   // dW1[co][c][kh][kw] = (1/255) sum_p da1[p][co] * x[n,c,4oh+kh,4ow+kw]; grid.y = 2 (channel pairs)
+struct Conv1Wgrad {   // dW1[co][c][4kh2+dy][4kw2+dx] = (1/255) sum_p da1[p][co] * xs[n,oh+kh2,ow+kw2,(c,dy,dx)];  grid.y = kh2
   static constexpr int BN = 64, STAGES = 3;   // N padded 32 -> 64 (upper half zero) to keep the 128 B row form
   static constexpr bool A_MN = true, B_MN = true;
-  struct Params { const uint8_t* obs; const bf16* dy; float* dw; int P; int pps; };   // P = frames*400
-  struct RowA { int krow; int coff; };   // coff = c*7056
+  static constexpr int BIAS = 2, BIAS_N = 32;   // db1 = colsum(da1)
+  struct Params { const bf16* xs; const bf16* dy; float* dw; float* db; int P; int pps; };   // P = frames*400
+  struct RowA { int krow; int tapoff; };   // tapoff = (kh2*21 + kw2)*64
   typedef int RowB;
+  SRL_DEVINL static float* bias_dst(const Params& p, int, int ty) { return ty == 0 ? p.db : nullptr; }
   SRL_DEVINL static int num_kblocks(const Params& p, int tm, int) {
     const int lo = tm * p.pps, hi = min(p.P, lo + p.pps);
     return hi > lo ? (hi - lo + 63) >> 6 : 0;
   }
   SRL_DEVINL static RowA make_rowA(const Params&, int, int ty, int srow) {
-    RowA r; r.krow = srow & 63; r.coff = (2 * ty + (srow >> 6)) * 7056;
+    RowA r; r.krow = srow & 63; r.tapoff = (ty * 21 + (srow >> 6)) * 64;
     return r;
   }
   SRL_DEVINL static RowB make_rowB(const Params&, int, int, int srow) { return srow; }
-  SRL_DEVINL static uint4 load_A(const Params& p, const RowA& r, int kb, int chunk) {   // chunk = kh
+  SRL_DEVINL static uint4 load_A(const Params& p, const RowA& r, int kb, int chunk) {
     const int q = blockIdx.x * p.pps + kb * 64 + r.krow;
     if (q >= p.P) return zero16();
     const int n = q / 400, s = q - n * 400, oh = s / 20, ow = s - oh * 20;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(p.obs + (size_t)n * 28224 + r.coff + (4 * oh + chunk) * 84 + 4 * ow);
-    return u8x8_to_bf16x8(__ldg(w), __ldg(w + 1));
+    return ldg16(p.xs + (size_t)((n * 21 + oh) * 21 + ow) * 64 + r.tapoff + chunk * 8);
   }
   SRL_DEVINL static uint4 load_B(const Params& p, RowB krow, int kb, int chunk) {
     const int q = blockIdx.x * p.pps + kb * 64 + krow;
@@ -334,15 +319,19 @@ struct Conv1Wgrad {   // dW1[co][c][kh][kw] = (1/255) sum_p da1[p][co] * x[n,c,4
   }
   SRL_DEVINL static void epilogue16(const Params& p, int, int ty, int row, int c0, float (&v)[16]) {
     if (c0 >= 32) return;
+    const int kw2 = row >> 6, q = row & 63, c = q >> 4, dy = (q >> 2) & 3, dx = q & 3;
+    const int k = c * 64 + (4 * ty + dy) * 8 + 4 * kw2 + dx;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) atomicAdd(p.dw + (c0 + j) * 256 + ty * 128 + row, v[j] * (1.0f / 255.0f));
+    for (int j = 0; j < 16; ++j) atomicAdd(p.dw + (c0 + j) * 256 + k, v[j] * (1.0f / 255.0f));
   }
 };
 
-struct FcWgrad {   // dWfc[j][c*49+hw] = sum_m dh[m][j] * a3[m][hw*64+c];  grid = (1, 4*49): ty = hw*4 + jt
+struct FcWgrad {   // dWfc[j][c*49+hw] = sum_m dh[m][j] * a3[m][hw*64+c];  grid = (1, 4*49): ty = hw*4 + jt; dbfc = colsum(dh)
   static constexpr int BN = 64, STAGES = 3;
   static constexpr bool A_MN = true, B_MN = true;
-  struct Params { const bf16* dh; const bf16* a3; float* dw; int M; };
+  static constexpr int BIAS = 1, BIAS_N = 128;
+  struct Params { const bf16* dh; const bf16* a3; float* dw; float* db; int M; };
+  SRL_DEVINL static float* bias_dst(const Params& p, int, int ty) { return (ty >> 2) == 0 ? p.db + (ty & 3) * 128 : nullptr; }
   struct RowA { int krow; int joff; };
   typedef int RowB;
   SRL_DEVINL static int num_kblocks(const Params& p, int, int) { return (p.M + 63) >> 6; }
@@ -372,6 +361,7 @@ struct FcWgrad {   // dWfc[j][c*49+hw] = sum_m dh[m][j] * a3[m][hw*64+c];  grid 
 struct TestGemmK {    // D[M][N] = A[M][K] * B[N][K]^T, K % 64 == 0, N % 64 == 0; grid = (ceil(M/128), N/64)
   static constexpr int BN = 64, STAGES = 3;
   static constexpr bool A_MN = false, B_MN = false;
+  static constexpr int BIAS = 0, BIAS_N = 0;
   struct Params { const bf16* A; const bf16* B; float* D; int M, N, K; };
   typedef int RowA;
   typedef int RowB;
@@ -392,6 +382,7 @@ struct TestGemmK {    // D[M][N] = A[M][K] * B[N][K]^T, K % 64 == 0, N % 64 == 0
 struct TestGemmMN {   // D[M][N] = At[K][M]^T * Bt[K][N], M % 128 == 0, N % 64 == 0, any K; grid = (M/128, N/64)
   static constexpr int BN = 64, STAGES = 3;
   static constexpr bool A_MN = true, B_MN = true;
+  static constexpr int BIAS = 0, BIAS_N = 0;
   struct Params { const bf16* At; const bf16* Bt; float* D; int M, N, K; };
   typedef int RowA;
   typedef int RowB;

@@ -10,7 +10,8 @@ namespace srl {
 // ------------------------------------------------------------------------------------------------
 // heads forward: one warp per frame.  core = [h(512), clamp(reward,-1,1), one_hot(action)(A)]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ h, const float* __restrict__ reward,
+__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ hpart, int nsplit, const float* __restrict__ bfc,
+                                                       float* __restrict__ h, const float* __restrict__ reward,
                                                        const int64_t* __restrict__ action, const float* __restrict__ Wp,
                                                        const float* __restrict__ bp, const float* __restrict__ Wb,
                                                        const float* __restrict__ bb, int N, int A, float* __restrict__ logits,
@@ -21,7 +22,13 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
   const int CORE = 513 + A;
   float x[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = __ldg(h + (size_t)n * 512 + i * 32 + lane);
+  for (int i = 0; i < 16; ++i) {     // fc epilogue: reduce the split-K partials in fixed order, + bias, ReLU (atari_model.py:100-101)
+    const int j = i * 32 + lane;
+    float s = __ldg(hpart + (size_t)n * 512 + j);
+    for (int k = 1; k < nsplit; ++k) s += __ldg(hpart + ((size_t)k * N + n) * 512 + j);
+    x[i] = fmaxf(s + __ldg(bfc + j), 0.f);
+    h[(size_t)n * 512 + j] = x[i];
+  }
   const float r = fminf(fmaxf(__ldg(reward + n), -1.f), 1.f);
   const int act = (int)__ldg(action + n);
   for (int a = 0; a <= A; ++a) {
@@ -84,26 +91,6 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict
       if (j < CORE) atomicAdd(gWp + (size_t)a * CORE + j, acc[a]); else atomicAdd(gbp + a, acc[a]);
     }
   if (j < CORE) atomicAdd(gWb + j, acc[HEAD_MAX_A]); else atomicAdd(gbb, acc[HEAD_MAX_A]);
-}
-
-// db[c] += sum_r dY[r][c] for bf16 dY [M x C]  (C in {32, 64, 512})
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, int M, int C, int rows_per_block,
-                                                          float* __restrict__ db) {
-  __shared__ float red[256];
-  const int Cw = C < 256 ? C : 256;
-  const int c = threadIdx.x % Cw, rsub = threadIdx.x / Cw, rstep = 256 / Cw;
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
-  for (int cc = c; cc < C; cc += 256) {
-    float s = 0.f;
-    for (int r = r0 + rsub; r < r1; r += rstep) s += __bfloat162float(dy[(size_t)r * C + cc]);
-    red[threadIdx.x] = s;
-    __syncthreads();
-    if (rsub == 0) {
-      for (int k = 1; k < rstep; ++k) s += red[k * Cw + c];
-      atomicAdd(db + cc, s);
-    }
-    __syncthreads();
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -186,10 +173,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-cudaError_t launch_head_fwd(const float* h, const float* reward, const int64_t* action, const float* Wp, const float* bp, const float* Wb,
-                            const float* bb, int N, int A, float* logits, float* baseline, cudaStream_t st) {
+cudaError_t launch_head_fwd(const float* hpart, int nsplit, const float* bfc, float* h, const float* reward, const int64_t* action,
+                            const float* Wp, const float* bp, const float* Wb, const float* bb, int N, int A, float* logits,
+                            float* baseline, cudaStream_t st) {
   if (N <= 0) return cudaSuccess;
-  head_fwd_kernel<<<(N + 7) / 8, 256, 0, st>>>(h, reward, action, Wp, bp, Wb, bb, N, A, logits, baseline);
+  head_fwd_kernel<<<(N + 7) / 8, 256, 0, st>>>(hpart, nsplit, bfc, h, reward, action, Wp, bp, Wb, bb, N, A, logits, baseline);
   return cudaGetLastError();
 }
 cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const float* h, const float* reward, const int64_t* action,
@@ -200,15 +188,6 @@ cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const 
   const int CORE = 513 + A;
   const int slabs = 32, rps = (N + slabs - 1) / slabs;
   head_wgrad_kernel<<<dim3((CORE + 1 + 127) / 128, slabs), 128, 0, st>>>(dlogits, dbaseline, h, reward, action, N, A, rps, gWp, gbp, gWb, gbb);
-  return cudaGetLastError();
-}
-cudaError_t launch_colsum_bf16(const __nv_bfloat16* dy, int M, int C, float* db, cudaStream_t st) {
-  if (M <= 0) return cudaSuccess;
-  int blocks = 296;
-  int rpb = (M + blocks - 1) / blocks;
-  if (rpb < 8) rpb = 8;
-  blocks = (M + rpb - 1) / rpb;
-  colsum_bf16_kernel<<<blocks, 256, 0, st>>>(dy, M, C, rpb, db);
   return cudaGetLastError();
 }
 cudaError_t launch_grad_norm(const float* g, int64_t n, float max_norm, float* coef, float* scratch, cudaStream_t st) {

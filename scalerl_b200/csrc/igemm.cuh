@@ -23,6 +23,9 @@
 //   load_A(p, rowctx, kb, chunk) -> uint4             8 bf16 for 16-byte chunk `chunk` of that row
 //   load_B(p, rowctx, kb, chunk) -> uint4
 //   epilogue16(p, tm, ty, row, col0, const float (&v)[16])   row = 0..127 of the tile
+//   BIAS                    0: none.  1 / 2: the producers also accumulate fp32 column sums of the A / B operand
+//                           rows they gather (MN-major wgrad problems: rows are dY pixels, so this is the bias
+//                           gradient) and add them atomically to bias_dst(p, tm, ty) (nullptr: this CTA skips it)
 //
 // A second kernel, igemm_simt_kernel<P>, runs the SAME producers and epilogue around a plain
 // CUDA-core inner product.  It exists only to triage (gather/epilogue bug vs descriptor/pipeline
@@ -41,7 +44,7 @@ struct IgemmCfg {
   static constexpr int B_ROWS = P::B_MN ? 64 * ((P::BN + 63) / 64) : P::BN;  // smem rows of the B tile
   static constexpr int B_BYTES = B_ROWS * 128;
   static constexpr int STAGE_BYTES = IG_A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = P::STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = P::STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias sums*/;
   static constexpr int TMEM_COLS = P::BN <= 32 ? 32 : (P::BN <= 64 ? 64 : (P::BN <= 128 ? 128 : 256));
   static constexpr int A_PER_THREAD = 8;                 // 1024 chunks / 128 threads
   static constexpr int B_PER_THREAD = B_ROWS / 16;       // B_ROWS*8 chunks / 128 threads
@@ -49,10 +52,15 @@ struct IgemmCfg {
   static_assert(B_ROWS % 16 == 0, "B rows");
 };
 
+SRL_DEVINL void acc_bf16x8(const uint4& v, float* s) {
+  s[0] += bf16_lo(v.x); s[1] += bf16_hi(v.x); s[2] += bf16_lo(v.y); s[3] += bf16_hi(v.y);
+  s[4] += bf16_lo(v.z); s[5] += bf16_hi(v.z); s[6] += bf16_lo(v.w); s[7] += bf16_hi(v.w);
+}
+
 template <class P>
 SRL_DEVINL void ig_produce(const typename P::Params& p, const typename P::RowA (&ra)[8],
                            const typename P::RowB (&rb)[IgemmCfg<P>::B_PER_THREAD], int kb, uint8_t* sA, uint8_t* sB,
-                           int tid) {
+                           int tid, float* bsum = nullptr) {
   using C = IgemmCfg<P>;
   const int chunk = tid & 7;
   const int r0 = tid >> 3;
@@ -66,6 +74,14 @@ SRL_DEVINL void ig_produce(const typename P::Params& p, const typename P::RowA (
   for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(sA + swz128(i * 16 + r0, chunk)) = va[i];
 #pragma unroll
   for (int i = 0; i < C::B_PER_THREAD; ++i) *reinterpret_cast<uint4*>(sB + swz128(i * 16 + r0, chunk)) = vb[i];
+  if (P::BIAS == 1 && bsum) {       // A rows: smem rows 0..63 are M-block 0, 64..127 M-block 1
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc_bf16x8(va[i], bsum + (i >= 4 ? 8 : 0));
+  }
+  if (P::BIAS == 2 && bsum) {
+#pragma unroll
+    for (int i = 0; i < C::B_PER_THREAD; ++i) acc_bf16x8(vb[i], bsum);
+  }
 }
 
 template <class P>
@@ -78,6 +94,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_tc_kernel(const typename P::
   uint64_t* empty = bars + P::STAGES;
   uint64_t* done = bars + 2 * P::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P::STAGES + 1);
+  float* sbias = reinterpret_cast<float*>(bars + 2 * P::STAGES + 2);   // 128 floats (BIAS problems only)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -107,14 +124,33 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_tc_kernel(const typename P::
     for (int i = 0; i < 8; ++i) ra[i] = P::make_rowA(p, tm, ty, i * 16 + r0);
 #pragma unroll
     for (int i = 0; i < C::B_PER_THREAD; ++i) rb[i] = P::make_rowB(p, tm, ty, i * 16 + r0);
+    float bsum[16];
+    float* bias_dst = nullptr;
+    if constexpr (P::BIAS != 0) {
+      bias_dst = P::bias_dst(p, tm, ty);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) bsum[i] = 0.f;
+      sbias[tid] = 0.f;
+    }
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % P::STAGES;
       const uint32_t ph = (kb / P::STAGES) & 1;
       mbar_wait(&empty[s], ph ^ 1);
       uint8_t* sA = smem + s * C::STAGE_BYTES;
-      ig_produce<P>(p, ra, rb, kb, sA, sA + IG_A_BYTES, tid);
+      ig_produce<P>(p, ra, rb, kb, sA, sA + IG_A_BYTES, tid, (P::BIAS != 0 && bias_dst) ? bsum : nullptr);
       fence_proxy_async_smem();
       mbar_arrive(&full[s]);
+    }
+    if (P::BIAS != 0 && bias_dst) {   // block-uniform branch: 16 threads share each 8-channel chunk
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int chunk = tid & 7;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&sbias[chunk * 8 + e], bsum[e]);
+        if (P::BIAS == 1) atomicAdd(&sbias[64 + chunk * 8 + e], bsum[8 + e]);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid < P::BIAS_N) atomicAdd(bias_dst + tid, sbias[tid]);
     }
     // ---------------- epilogue ----------------
     mbar_wait(done, 0);
@@ -184,9 +220,18 @@ __global__ void __launch_bounds__(IG_PRODUCER_THREADS) igemm_simt_kernel(const t
 #pragma unroll
   for (int n = 0; n < P::BN; ++n) acc[n] = 0.f;
   const int m = tid;
+  __shared__ float sbias[128];
+  float bsum[16];
+  float* bias_dst = nullptr;
+  if constexpr (P::BIAS != 0) {
+    bias_dst = P::bias_dst(p, tm, ty);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bsum[i] = 0.f;
+    sbias[tid] = 0.f;
+  }
   for (int kb = 0; kb < nkb; ++kb) {
     __syncthreads();
-    ig_produce<P>(p, ra, rb, kb, sA, sB, tid);
+    ig_produce<P>(p, ra, rb, kb, sA, sB, tid, (P::BIAS != 0 && bias_dst) ? bsum : nullptr);
     __syncthreads();
     for (int k = 0; k < 64; ++k) {
       uint32_t aoff = P::A_MN ? swz128((m >> 6) * 64 + k, (m & 63) >> 3) + (m & 7) * 2 : swz128(m, k >> 3) + (k & 7) * 2;
@@ -197,6 +242,17 @@ __global__ void __launch_bounds__(IG_PRODUCER_THREADS) igemm_simt_kernel(const t
         acc[n] = fmaf(a, __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sB + boff)), acc[n]);
       }
     }
+  }
+  if (P::BIAS != 0 && bias_dst) {
+    __syncthreads();
+    const int chunk = tid & 7;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&sbias[chunk * 8 + e], bsum[e]);
+      if (P::BIAS == 1) atomicAdd(&sbias[64 + chunk * 8 + e], bsum[8 + e]);
+    }
+    __syncthreads();
+    if (tid < P::BIAS_N) atomicAdd(bias_dst + tid, sbias[tid]);
   }
 #pragma unroll
   for (int c0 = 0; c0 < P::BN; c0 += 16) {

@@ -7,9 +7,9 @@
 namespace srl {
 
 // per-kernel CUDA-event bracketing (bench.py's roofline numbers): slots of one learner step
-enum ProfSlot { PS_CONV1_FWD = 0, PS_CONV2_FWD, PS_CONV3_FWD, PS_FC_FWD, PS_HEAD_FWD, PS_TAIL, PS_ZERO_GRADS, PS_HEAD_BWD,
-                PS_FC_BIAS, PS_FC_WGRAD, PS_FC_DGRAD, PS_CONV3_BIAS, PS_CONV3_WGRAD, PS_CONV3_DGRAD, PS_CONV2_BIAS, PS_CONV2_WGRAD,
-                PS_CONV2_DGRAD, PS_CONV1_BIAS, PS_CONV1_WGRAD, PS_GRAD_NORM, PS_OPTIMIZER, PS_PACK, PS_COUNT };
+enum ProfSlot { PS_S2D = 0, PS_CONV1_FWD, PS_CONV2_FWD, PS_CONV3_FWD, PS_FC_FWD, PS_HEAD_FWD, PS_TAIL, PS_ZERO_GRADS, PS_HEAD_BWD,
+                PS_FC_WGRAD, PS_FC_DGRAD, PS_CONV3_WGRAD, PS_CONV3_DGRAD, PS_CONV2_WGRAD, PS_CONV2_DGRAD, PS_CONV1_WGRAD,
+                PS_GRAD_NORM, PS_OPTIMIZER, PS_PACK, PS_COUNT };
 struct Profiler {
   bool on = false;
   cudaEvent_t* ev = nullptr;   // 2 * PS_COUNT events
@@ -31,12 +31,13 @@ cudaError_t launch_impala_tail(const float* bl, const float* tl, const float* ba
                                float* dbaseline, float* losses, float* scratch, cudaStream_t st);
 
 // ---- heads_optim.cu
-cudaError_t launch_head_fwd(const float* h, const float* reward, const int64_t* action, const float* Wp, const float* bp, const float* Wb,
-                            const float* bb, int N, int A, float* logits, float* baseline, cudaStream_t st);
+// hpart: FC_SPLITS split-K partials [s][N][512] of the fc layer; writes h = relu(sum_s hpart + bfc) and the head outputs
+cudaError_t launch_head_fwd(const float* hpart, int nsplit, const float* bfc, float* h, const float* reward, const int64_t* action,
+                            const float* Wp, const float* bp, const float* Wb, const float* bb, int N, int A, float* logits,
+                            float* baseline, cudaStream_t st);
 cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const float* h, const float* reward, const int64_t* action,
                             const float* Wp, const float* Wb, int N, int A, __nv_bfloat16* dh, float* gWp, float* gbp, float* gWb,
                             float* gbb, cudaStream_t st);
-cudaError_t launch_colsum_bf16(const __nv_bfloat16* dy, int M, int C, float* db, cudaStream_t st);
 cudaError_t launch_grad_norm(const float* g, int64_t n, float max_norm, float* coef, float* scratch, cudaStream_t st);
 cudaError_t launch_rmsprop(float* p, const float* g, float* v, int64_t n, const float* coef, float lr, float alpha, float eps,
                            cudaStream_t st);
@@ -46,7 +47,7 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n,
 // ---- encoder.cu
 // packed bf16 operand copies of the conv/fc weights (element offsets into one buffer)
 struct WPack {
-  static constexpr int64_t W1K = 0;                       // [32][256]            k = (c,kh,kw)  (PyTorch order)
+  static constexpr int64_t W1K = 0;                       // [32][256]            k = (kh2,kw2,c,dy,dx), kh=4kh2+dy, kw=4kw2+dx
   static constexpr int64_t W2K = W1K + 32 * 256;          // [64][512]            k = (kh,kw,c)
   static constexpr int64_t W3K = W2K + 64 * 512;          // [64][576]            k = (kh,kw,c)
   static constexpr int64_t WFK = W3K + 64 * 576;          // [512][3136]          k = (hw,c)
@@ -59,8 +60,11 @@ struct WPack {
 struct ParamPtrs {
   float *w1, *b1, *w2, *b2, *w3, *b3, *wf, *bf, *wp, *bp, *wb, *bb;
 };
+constexpr int FC_SPLITS = 4;
 struct EncoderBuffers {
+  __nv_bfloat16* xs;                    // space-to-depth bf16 copy of the u8 frames [NF][21][21][64], 64 = (c,dy,dx)
   __nv_bfloat16 *a1, *a2, *a3;          // NHWC activations for NF frames
+  float* hpart;                         // [FC_SPLITS][NF][512] split-K partials of the fc layer
   float* h;                             // [NF][512] fc output (post-ReLU), fp32
   __nv_bfloat16 *dh, *da3, *da2, *da1;  // gradients w.r.t. (post-ReLU-masked) pre-activations, NB frames
   __nv_bfloat16* wpack;

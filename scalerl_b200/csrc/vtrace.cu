@@ -258,6 +258,104 @@ __global__ void __launch_bounds__(128) impala_tail_kernel(const float* __restric
   }
 }
 
+
+// Warp-per-column variant of the fused tail for small B (latency-bound regime): lane = t, the T-step
+// recursion becomes a Kogge-Stone scan of affine maps with warp shuffles (32-step chunks + carry), and the
+// softmax / log-prob work of all T steps of a column runs in parallel.  Block = 4 warps = 4 columns.
+__global__ void __launch_bounds__(128) impala_tail_warp_kernel(const float* __restrict__ bl, const float* __restrict__ tl,
+                                                               const float* __restrict__ baseline, const int64_t* __restrict__ action,
+                                                               const float* __restrict__ reward, const uint8_t* __restrict__ done, int T,
+                                                               int B, int A, float discounting, int clip_reward, float clip_rho,
+                                                               float clip_pg, float baseline_cost, float entropy_cost,
+                                                               float* __restrict__ vs, float* __restrict__ pg, float* __restrict__ dlogits,
+                                                               float* __restrict__ dbaseline, float* __restrict__ losses,
+                                                               float* __restrict__ scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * 4 + warp;
+  float l_pg = 0.f, l_bl = 0.f, l_ent = 0.f;
+  if (b < B) {
+    const float boot = __ldg(baseline + (size_t)T * B + b);
+    float carry_acc = 0.f, carry_vs = boot;
+    const int nchunk = (T + 31) >> 5;
+    for (int ch = nchunk - 1; ch >= 0; --ch) {
+      const int t = ch * 32 + lane;
+      const bool ok = t < T;
+      const size_t o = (size_t)(ok ? t : 0) * B + b, o1 = o + B;
+      const int act = (int)__ldg(action + o1);
+      const float* trow = tl + o * A;
+      float mx = -INFINITY;
+      for (int a = 0; a < A; ++a) mx = fmaxf(mx, __ldg(trow + a));
+      float se = 0.f;
+      for (int a = 0; a < A; ++a) se += expf(__ldg(trow + a) - mx);
+      const float lse = logf(se);
+      float ent = 0.f;
+      for (int a = 0; a < A; ++a) { const float lp = (__ldg(trow + a) - mx) - lse; ent += expf(lp) * lp; }
+      const float talp = (__ldg(trow + act) - mx) - lse;
+      const float balp = action_logp(bl + o1 * A, A, act);
+      const float rho = expf(talp - balp);
+      float r = __ldg(reward + o1);
+      if (clip_reward) r = fminf(fmaxf(r, -1.f), 1.f);
+      const float g = done[o1] ? 0.f : discounting;
+      const float v = __ldg(baseline + o);
+      const float vn = __ldg(baseline + o1);               // V_{t+1}; row T is the bootstrap value
+      const float crho = clip_rho >= 0.f ? fminf(rho, clip_rho) : rho;
+      float aa = ok ? g * fminf(rho, 1.0f) : 1.f;          // x -> bb + aa x ; identity on padding lanes
+      float bb = ok ? crho * (r + g * vn - v) : 0.f;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float a2 = __shfl_down_sync(0xffffffffu, aa, d);
+        const float b2 = __shfl_down_sync(0xffffffffu, bb, d);
+        if (lane + d < 32) { bb = fmaf(aa, b2, bb); aa = aa * a2; }
+      }
+      const float acc = fmaf(aa, carry_acc, bb);
+      const float myvs = acc + v;
+      float vsn = __shfl_down_sync(0xffffffffu, myvs, 1);
+      if (lane == 31 || t + 1 >= T) vsn = carry_vs;
+      const float prho = clip_pg >= 0.f ? fminf(rho, clip_pg) : rho;
+      const float adv = prho * (r + g * vsn - v);
+      if (ok) {
+        if (vs) vs[o] = myvs;
+        if (pg) pg[o] = adv;
+        l_pg += -talp * adv;
+        l_bl += 0.5f * (myvs - v) * (myvs - v);
+        l_ent += ent;
+        dbaseline[o] = -baseline_cost * (myvs - v);
+        float* drow = dlogits + o * A;
+        for (int a = 0; a < A; ++a) {
+          const float lp = (__ldg(trow + a) - mx) - lse;
+          const float p = expf(lp);
+          drow[a] = adv * (p - (a == act ? 1.f : 0.f)) + entropy_cost * p * (lp - ent);
+        }
+      }
+      carry_acc = __shfl_sync(0xffffffffu, acc, 0);
+      carry_vs = __shfl_sync(0xffffffffu, myvs, 0);
+    }
+  }
+  __shared__ float red[3][4];
+  __shared__ bool is_last;
+  l_pg = warp_sum(l_pg); l_bl = warp_sum(l_bl); l_ent = warp_sum(l_ent);
+  if (lane == 0) { red[0][warp] = l_pg; red[1][warp] = l_bl; red[2][warp] = l_ent; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) scratch[4 + blockIdx.x * 3 + i] = (red[i][0] + red[i][1]) + (red[i][2] + red[i][3]);
+    __threadfence();
+    is_last = atomicAdd(reinterpret_cast<unsigned*>(scratch), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last && warp == 0) {   // fixed-order parallel sum of the block partials: deterministic
+    __threadfence();
+    float s[3] = {0.f, 0.f, 0.f};
+    for (unsigned k = lane; k < gridDim.x; k += 32)
+      for (int i = 0; i < 3; ++i) s[i] += reinterpret_cast<volatile float*>(scratch)[4 + k * 3 + i];
+    for (int i = 0; i < 3; ++i) s[i] = warp_sum(s[i]);
+    if (lane == 0) {
+      const float a = s[0], c = baseline_cost * s[1], e = entropy_cost * s[2];
+      losses[0] = a; losses[1] = c; losses[2] = e; losses[3] = a + c + e;
+      *reinterpret_cast<unsigned*>(scratch) = 0u;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_vtrace_iw(const float* log_rhos, const float* discounts, const float* rewards, const float* values,
                              const float* bootstrap, int T, int B, float clip_rho, float clip_pg, float* vs, float* pg, int variant,
@@ -295,8 +393,14 @@ cudaError_t launch_impala_tail(const float* bl, const float* tl, const float* ba
                                const uint8_t* done, int T, int B, int A, float discounting, int clip_reward, float clip_rho,
                                float clip_pg, float baseline_cost, float entropy_cost, float* vs, float* pg, float* dlogits,
                                float* dbaseline, float* losses, float* scratch, cudaStream_t st) {
-  impala_tail_kernel<<<(B + 127) / 128, 128, 0, st>>>(bl, tl, baseline, action, reward, done, T, B, A, discounting, clip_reward, clip_rho,
-                                                       clip_pg, baseline_cost, entropy_cost, vs, pg, dlogits, dbaseline, losses, scratch);
+  if (B <= 2048) {   // latency-bound sizes: one warp per column, shuffle scan over T (block partials: 3*ceil(B/4) <= 1536 floats)
+    impala_tail_warp_kernel<<<(B + 3) / 4, 128, 0, st>>>(bl, tl, baseline, action, reward, done, T, B, A, discounting, clip_reward,
+                                                          clip_rho, clip_pg, baseline_cost, entropy_cost, vs, pg, dlogits, dbaseline, losses,
+                                                          scratch);
+  } else {
+    impala_tail_kernel<<<(B + 127) / 128, 128, 0, st>>>(bl, tl, baseline, action, reward, done, T, B, A, discounting, clip_reward, clip_rho,
+                                                         clip_pg, baseline_cost, entropy_cost, vs, pg, dlogits, dbaseline, losses, scratch);
+  }
   return cudaGetLastError();
 }
 

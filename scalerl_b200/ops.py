@@ -101,7 +101,7 @@ def impala_loss_and_head_grads(behavior_logits, target_logits, baseline, action,
     dlogits = torch.empty(T, B, A, device=dev)
     dbaseline = torch.empty(T, B, device=dev)
     losses = torch.empty(4, device=dev)
-    scratch = torch.zeros(3 * ((B + 127) // 128) + 8, device=dev)
+    scratch = torch.zeros(3 * ((B + 3) // 4) + 8, device=dev)
     _lib.check(_lib.lib().srl_impala_loss_and_head_grads(
         bl.data_ptr(), tl.data_ptr(), baseline.data_ptr(), action.data_ptr(), reward.data_ptr(), done_u8.data_ptr(), T, B, A,
         float(discounting), 1 if reward_clipping == 'abs_one' else 0, _clip(clip_rho_threshold), _clip(clip_pg_rho_threshold),
