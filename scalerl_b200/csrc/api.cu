@@ -141,6 +141,7 @@ struct srl_learner {
   int64_t arena_bytes;
   int step;                       // optimizer step count (Adam bias correction)
   bool have_fwd;
+  TmaMaps maps;                   // tensor maps of the TMA mainloop
   Profiler pf;                    // per-kernel event bracketing (off by default)
   cudaEvent_t events[2 * PS_COUNT];
   bool slot_used[PS_COUNT];
@@ -188,7 +189,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   sizes[k++] = al(NB * 512 * 2);        // dh
   sizes[k++] = al(NB * 49 * 64 * 2);    // da3
   sizes[k++] = al(NB * 81 * 64 * 2);    // da2
-  sizes[k++] = al(NB * 400 * 32 * 2);   // da1
+  sizes[k++] = al(NB * 400 * 64 * 2);   // da1 (64-channel pitch, upper half zero)
   sizes[k++] = al(WPack::TOTAL * 2);    // wpack
   sizes[k++] = al(NF * A * 4);          // logits
   sizes[k++] = al(NF * 4);              // baseline
@@ -221,6 +222,14 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   L->dbaseline = (float*)q; q += sizes[i++];
   L->scratch = (float*)q; q += sizes[i++];
   L->coef = (float*)q; q += sizes[i++];
+  if (cfg->simt_mainloop == 0) {
+    const char* why = nullptr;
+    if (build_tma_maps(L->buf, (int)NF, (int)NB, &L->maps, &why) != cudaSuccess) {
+      cudaFree(L->arena);
+      delete L;
+      return fail(SRL_ESTATE, "learner_create: building TMA tensor map '%s' failed (driver without cuTensorMapEncodeTiled?)", why ? why : "?");
+    }
+  }
   *out = L;
   return 0;
 }
@@ -238,8 +247,8 @@ extern "C" int srl_learner_set_config(srl_learner_t* L, const srl_config_t* cfg)
   REQ(L, "learner is NULL");
   int rc = check_cfg(cfg);
   if (rc) return rc;
-  REQ(cfg->T == L->cfg.T && cfg->B == L->cfg.B && cfg->A == L->cfg.A && cfg->optimizer == L->cfg.optimizer,
-      "set_config: T/B/A/optimizer are fixed at creation");
+  REQ(cfg->T == L->cfg.T && cfg->B == L->cfg.B && cfg->A == L->cfg.A && cfg->optimizer == L->cfg.optimizer &&
+      cfg->simt_mainloop == L->cfg.simt_mainloop, "set_config: T/B/A/optimizer/mainloop are fixed at creation");
   L->cfg = *cfg;
   return 0;
 }
@@ -253,7 +262,7 @@ extern "C" int srl_learner_pack_weights(srl_learner_t* L, void* stream) {
 static int forward_impl(srl_learner* L, const uint8_t* obs, const float* reward, const int64_t* action, int frames, float* logits,
                         float* baseline, cudaStream_t st) {
   L->pf.st = st;
-  CU(encoder_forward(obs, frames, L->P, L->buf, L->cfg.simt_mainloop != 0, st, L->pf), "encoder_forward");
+  CU(encoder_forward(obs, frames, L->P, L->buf, L->maps, L->cfg.simt_mainloop, st, L->pf), "encoder_forward");
   L->pf.b(PS_HEAD_FWD);
   CU(launch_head_fwd(L->buf.hpart, FC_SPLITS, L->P.bf, L->buf.h, reward, action, L->P.wp, L->P.bp, L->P.wb, L->P.bb, frames, L->cfg.A,
                      logits, baseline, st), "head_fwd");
@@ -291,7 +300,7 @@ extern "C" int srl_learner_forward_backward(srl_learner_t* L, const uint8_t* obs
   CU(launch_head_bwd(L->dlogits, L->dbaseline, L->buf.h, reward, action, L->P.wp, L->P.wb, NB, c.A, L->buf.dh, L->G.wp, L->G.bp, L->G.wb,
                      L->G.bb, st), "head_bwd");
   L->pf.e(PS_HEAD_BWD);
-  CU(encoder_backward(obs, NB, L->buf, L->G, c.simt_mainloop != 0, st, L->pf), "encoder_backward");
+  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.simt_mainloop, st, L->pf), "encoder_backward");
   L->have_fwd = true;
   return 0;
 }
@@ -356,7 +365,7 @@ extern "C" int srl_learner_debug_buffer(srl_learner_t* L, const char* name, void
       {"xs", L->buf.xs, NF * 441 * 64}, {"a1", L->buf.a1, NF * 400 * 32}, {"a2", L->buf.a2, NF * 81 * 64}, {"a3", L->buf.a3, NF * 49 * 64}, {"h", L->buf.h, NF * 512},
       {"logits", L->logits, NF * A}, {"baseline", L->baseline, NF}, {"dlogits", L->dlogits, NB * A}, {"dbaseline", L->dbaseline, NB},
       {"dh", L->buf.dh, NB * 512}, {"da3", L->buf.da3, NB * 49 * 64}, {"da2", L->buf.da2, NB * 81 * 64},
-      {"da1", L->buf.da1, NB * 400 * 32}, {"wpack", L->buf.wpack, WPack::TOTAL}};
+      {"da1", L->buf.da1, NB * 400 * 64}, {"wpack", L->buf.wpack, WPack::TOTAL}};
   for (auto& t : tab)
     if (strcmp(t.n, name) == 0) { *ptr = t.p; *count = t.c; return 0; }
   return fail(SRL_EINVAL, "debug_buffer: unknown buffer '%s'", name);

@@ -1,6 +1,8 @@
 // Encoder forward / backward drivers: weight packing + the sequence of tcgen05 implicit-GEMM launches.
 #include "encoder_problems.cuh"
+#include "tma_problems.cuh"
 #include "kernels.h"
+#include <initializer_list>
 
 namespace srl {
 
@@ -65,12 +67,103 @@ cudaError_t launch_pack_weights(const ParamPtrs& p, bf16* wpack, cudaStream_t st
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, bool simt, cudaStream_t st,
-                            const Profiler& pf) {
+// ------------------------------------------------------------------------------------------------
+// tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+// bf16 tensor, dims innermost-first, strides in ELEMENTS for dims 1..rank-1, SWIZZLE_128B, zero OOB fill
+static bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_elems[i] * 2;
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t build_tma_maps(const EncoderBuffers& b, int NF, int NB, TmaMaps* M, const char** why) {
+  const uint64_t nf = NF, nb = NB;
+  bool ok = true;
+#define MAP(field, base, rank, ...) do { const uint64_t d_[] = __VA_ARGS__; ok = ok && make_map(&M->field, base, rank, d_, d_ + rank, reinterpret_cast<const uint32_t*>(0)); } while (0)
+#undef MAP
+  auto mk = [&](CUtensorMap* m, const void* base, int rank, std::initializer_list<uint64_t> dims, std::initializer_list<uint64_t> strides,
+                std::initializer_list<uint32_t> box, const char* name) {
+    if (!ok) return;
+    uint64_t d[5], s[4]; uint32_t bx[5];
+    int i = 0; for (auto v : dims) d[i++] = v;
+    i = 0; for (auto v : strides) s[i++] = v;
+    i = 0; for (auto v : box) bx[i++] = v;
+    if (!make_map(m, base, rank, d, s, bx)) { ok = false; if (why) *why = name; }
+  };
+  mk(&M->xs3, b.xs, 3, {64, 21, nf * 21}, {64, 64 * 21}, {64, 20, 6}, "xs3");
+  mk(&M->xs4, b.xs, 4, {64, 21, 21, nf}, {64, 64 * 21, 64 * 441}, {64, 20, 4, 1}, "xs4");
+  mk(&M->a1v, b.a1, 5, {64, 10, 2, 10, nf}, {64, 640, 1280, 12800}, {64, 9, 1, 9, 1}, "a1v");
+  mk(&M->a2v2, b.a2, 4, {64, 9, 9, nf}, {64, 576, 5184}, {64, 7, 7, 2}, "a2v2");
+  mk(&M->a2v1, b.a2, 4, {64, 9, 9, nf}, {64, 576, 5184}, {64, 7, 7, 1}, "a2v1");
+  mk(&M->a3m128, b.a3, 2, {3136, nf}, {3136}, {64, 128}, "a3m128");
+  mk(&M->a3m64, b.a3, 2, {3136, nf}, {3136}, {64, 64}, "a3m64");
+  mk(&M->dhm128, b.dh, 2, {512, nb}, {512}, {64, 128}, "dhm128");
+  mk(&M->dhm64, b.dh, 2, {512, nb}, {512}, {64, 64}, "dhm64");
+  mk(&M->da3v, b.da3, 4, {64, 7, 7, nb}, {64, 448, 3136}, {64, 9, 9, 1}, "da3v");
+  mk(&M->da3m, b.da3, 2, {64, nb * 49}, {64}, {64, 49}, "da3m");
+  mk(&M->da2v, b.da2, 4, {64, 9, 9, nb}, {64, 576, 5184}, {64, 10, 10, 1}, "da2v");
+  mk(&M->da2m, b.da2, 2, {64, nb * 81}, {64}, {64, 81}, "da2m");
+  mk(&M->da1m, b.da1, 2, {64, nb * 400}, {64}, {64, 80}, "da1m");
+  const bf16* w = b.wpack;
+  mk(&M->w1k, w + WPack::W1K, 2, {256, 32}, {256}, {64, 32}, "w1k");
+  mk(&M->w2k, w + WPack::W2K, 2, {512, 64}, {512}, {64, 64}, "w2k");
+  mk(&M->w3k, w + WPack::W3K, 2, {576, 64}, {576}, {64, 64}, "w3k");
+  mk(&M->wfk, w + WPack::WFK, 2, {3136, 512}, {3136}, {64, 64}, "wfk");
+  mk(&M->wfd, w + WPack::WFD, 2, {512, 3136}, {512}, {64, 64}, "wfd");
+  mk(&M->w3d, w + WPack::W3D, 2, {576, 64}, {576}, {64, 64}, "w3d");
+  mk(&M->w2d, w + WPack::W2D, 2, {256, 128}, {256}, {64, 32}, "w2d");
+  M->valid = ok;
+  if (!ok && why && !*why) *why = "cuTensorMapEncodeTiled unavailable";
+  return ok ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+static cudaError_t launch_s2d(const uint8_t* obs, int frames, bf16* xs, cudaStream_t st) {
+  const int64_t total = (int64_t)frames * 441 * 16;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  obs_s2d_kernel<<<blocks, 256, 0, st>>>(obs, xs, total);
+  return cudaGetLastError();
+}
+
+cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, const TmaMaps& maps, int mode,
+                            cudaStream_t st, const Profiler& pf) {
   if (frames <= 0) return cudaSuccess;
-  { const int64_t total = (int64_t)frames * 441 * 16;
-    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-    pf.b(PS_S2D); obs_s2d_kernel<<<blocks, 256, 0, st>>>(obs, buf.xs, total); SRL_TRY(cudaGetLastError()); pf.e(PS_S2D); }
+  pf.b(PS_S2D); SRL_TRY(launch_s2d(obs, frames, buf.xs, st)); pf.e(PS_S2D);
+  if (mode == 0) {
+    if (!maps.valid) return cudaErrorInvalidValue;
+    { TConv1Fwd::Params q{maps.xs3, maps.w1k, p.b1, buf.a1, frames};
+      pf.b(PS_CONV1_FWD); SRL_TRY(igemm_tma_launch<TConv1Fwd>(q, dim3(cdiv(frames * 21, 6), 1), st)); pf.e(PS_CONV1_FWD); }
+    { TConv2Fwd::Params q{maps.a1v, maps.w2k, p.b2, buf.a2, frames};
+      pf.b(PS_CONV2_FWD); SRL_TRY(igemm_tma_launch<TConv2Fwd>(q, dim3(frames, 1), st)); pf.e(PS_CONV2_FWD); }
+    { TConv3Fwd::Params q{maps.a2v2, maps.w3k, p.b3, buf.a3, frames};
+      pf.b(PS_CONV3_FWD); SRL_TRY(igemm_tma_launch<TConv3Fwd>(q, dim3(cdiv(frames, 2), 1), st)); pf.e(PS_CONV3_FWD); }
+    { TFcFwd::Params q{maps.a3m128, maps.wfk, buf.hpart, frames};
+      static_assert(TFcFwd::SPLITS == FC_SPLITS, "split count");
+      pf.b(PS_FC_FWD); SRL_TRY(igemm_tma_launch<TFcFwd>(q, dim3(cdiv(frames, 128), 8 * FC_SPLITS), st)); pf.e(PS_FC_FWD); }
+    return cudaSuccess;
+  }
+  const bool simt = mode == 1;
   { Conv1Fwd::Params q{buf.xs, buf.wpack + WPack::W1K, p.b1, buf.a1, frames * 400};
     pf.b(PS_CONV1_FWD); SRL_TRY(igemm_launch<Conv1Fwd>(q, dim3(cdiv(q.M, 128), 1), st, simt)); pf.e(PS_CONV1_FWD); }
   { Conv2Fwd::Params q{buf.a1, buf.wpack + WPack::W2K, p.b2, buf.a2, frames * 81};
@@ -91,28 +184,46 @@ static inline void split_k(int P, int target, int* pps, int* nsplit) {
   *nsplit = cdiv(P, per);
 }
 
-cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, bool simt, cudaStream_t st,
-                             const Profiler& pf) {
+cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
+                             cudaStream_t st, const Profiler& pf) {
   if (frames <= 0) return cudaSuccess;
+  if (mode == 0) {
+    if (!maps.valid) return cudaErrorInvalidValue;
+    { TFcWgrad::Params q{maps.dhm64, maps.a3m64, g.wf, g.bf, frames};
+      pf.b(PS_FC_WGRAD); SRL_TRY(igemm_tma_launch<TFcWgrad>(q, dim3(1, 4 * 50), st)); pf.e(PS_FC_WGRAD); }
+    { TFcDgrad::Params q{maps.dhm128, maps.wfd, buf.a3, buf.da3, frames};
+      pf.b(PS_FC_DGRAD); SRL_TRY(igemm_tma_launch<TFcDgrad>(q, dim3(cdiv(frames, 128), 49), st)); pf.e(PS_FC_DGRAD); }
+    { const int fps = cdiv(frames, 30);
+      TConv3Wgrad::Params q{maps.a2v1, maps.da3m, g.w3, g.b3, frames, fps};
+      pf.b(PS_CONV3_WGRAD); SRL_TRY(igemm_tma_launch<TConv3Wgrad>(q, dim3(cdiv(frames, fps), 5), st)); pf.e(PS_CONV3_WGRAD); }
+    { TConv3Dgrad::Params q{maps.da3v, maps.w3d, buf.a2, buf.da2, frames};
+      pf.b(PS_CONV3_DGRAD); SRL_TRY(igemm_tma_launch<TConv3Dgrad>(q, dim3(frames, 1), st)); pf.e(PS_CONV3_DGRAD); }
+    { const int fps = cdiv(frames, 30);
+      TConv2Wgrad::Params q{maps.a1v, maps.da2m, g.w2, g.b2, frames, fps};
+      pf.b(PS_CONV2_WGRAD); SRL_TRY(igemm_tma_launch<TConv2Wgrad>(q, dim3(cdiv(frames, fps), 5), st)); pf.e(PS_CONV2_WGRAD); }
+    { TConv2Dgrad::Params q{maps.da2v, maps.w2d, buf.a1, buf.da1, frames};
+      pf.b(PS_CONV2_DGRAD); SRL_TRY(igemm_tma_launch<TConv2Dgrad>(q, dim3(frames, 4), st)); pf.e(PS_CONV2_DGRAD); }
+    { const int fps = cdiv(frames, 49);
+      TConv1Wgrad::Params q{maps.xs4, maps.da1m, g.w1, g.b1, frames, fps};
+      pf.b(PS_CONV1_WGRAD); SRL_TRY(igemm_tma_launch<TConv1Wgrad>(q, dim3(cdiv(frames, fps), 3), st)); pf.e(PS_CONV1_WGRAD); }
+    return cudaSuccess;
+  }
+  const bool simt = mode == 1;
   int pps, ns;
-  // ---- fc: bias, wgrad, dgrad
   { FcWgrad::Params q{buf.dh, buf.a3, g.wf, g.bf, frames};
     pf.b(PS_FC_WGRAD); SRL_TRY(igemm_launch<FcWgrad>(q, dim3(1, 4 * 49), st, simt)); pf.e(PS_FC_WGRAD); }
   { FcDgrad::Params q{buf.dh, buf.wpack + WPack::WFD, buf.a3, buf.da3, frames};
     pf.b(PS_FC_DGRAD); SRL_TRY(igemm_launch<FcDgrad>(q, dim3(cdiv(frames, 128), 49), st, simt)); pf.e(PS_FC_DGRAD); }
-  // ---- conv3
   { split_k(frames * 49, 29, &pps, &ns);
     Conv3Wgrad::Params q{buf.a2, buf.da3, g.w3, g.b3, frames * 49, pps};
     pf.b(PS_CONV3_WGRAD); SRL_TRY(igemm_launch<Conv3Wgrad>(q, dim3(ns, 5), st, simt)); pf.e(PS_CONV3_WGRAD); }
   { Conv3Dgrad::Params q{buf.da3, buf.wpack + WPack::W3D, buf.a2, buf.da2, frames * 81};
     pf.b(PS_CONV3_DGRAD); SRL_TRY(igemm_launch<Conv3Dgrad>(q, dim3(cdiv(q.M, 128), 1), st, simt)); pf.e(PS_CONV3_DGRAD); }
-  // ---- conv2
   { split_k(frames * 81, 37, &pps, &ns);
     Conv2Wgrad::Params q{buf.a1, buf.da2, g.w2, g.b2, frames * 81, pps};
     pf.b(PS_CONV2_WGRAD); SRL_TRY(igemm_launch<Conv2Wgrad>(q, dim3(ns, 4), st, simt)); pf.e(PS_CONV2_WGRAD); }
   { Conv2Dgrad::Params q{buf.da2, buf.wpack + WPack::W2D, buf.a1, buf.da1, frames * 100};
     pf.b(PS_CONV2_DGRAD); SRL_TRY(igemm_launch<Conv2Dgrad>(q, dim3(cdiv(q.M, 128), 4), st, simt)); pf.e(PS_CONV2_DGRAD); }
-  // ---- conv1 (no dgrad: the frame is the network input)
   { split_k(frames * 400, 74, &pps, &ns);
     Conv1Wgrad::Params q{buf.xs, buf.da1, g.w1, g.b1, frames * 400, pps};
     pf.b(PS_CONV1_WGRAD); SRL_TRY(igemm_launch<Conv1Wgrad>(q, dim3(ns, 2), st, simt)); pf.e(PS_CONV1_WGRAD); }

@@ -209,9 +209,9 @@ struct Conv2Dgrad {   // stride-2 transposed conv split in 4 parity classes (gri
     if (m >= p.M) return;
     const int n = m / 100, r = m - n * 100, i = r / 10, j = r - i * 10;
     const int ih = 2 * i + (ty >> 1), iw = 2 * j + (ty & 1);
-    const size_t idx = (size_t)((n * 20 + ih) * 20 + iw) * 32 + c0;
-    relu_mask16(p.act + idx, v);
-    store_bf16x16(p.dx + idx, v);
+    const size_t pix = (size_t)(n * 20 + ih) * 20 + iw;
+    relu_mask16(p.act + pix * 32 + c0, v);
+    store_bf16x16(p.dx + pix * 64 + c0, v);      // da1 has a 64-channel pitch (channels 32..63 stay zero)
   }
 };
 
@@ -315,7 +315,7 @@ struct Conv1Wgrad {   // dW1[co][c][4kh2+dy][4kw2+dx] = (1/255) sum_p da1[p][co]
   }
   SRL_DEVINL static uint4 load_B(const Params& p, RowB krow, int kb, int chunk) {
     const int q = blockIdx.x * p.pps + kb * 64 + krow;
-    return (q < p.P && chunk < 4) ? ldg16(p.dy + (size_t)q * 32 + chunk * 8) : zero16();
+    return (q < p.P && chunk < 4) ? ldg16(p.dy + (size_t)q * 64 + chunk * 8) : zero16();
   }
   SRL_DEVINL static void epilogue16(const Params& p, int, int ty, int row, int c0, float (&v)[16]) {
     if (c0 >= 32) return;

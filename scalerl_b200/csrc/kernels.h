@@ -1,5 +1,6 @@
 // Internal launch prototypes shared by the .cu translation units (not part of the C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -69,12 +70,21 @@ struct EncoderBuffers {
   __nv_bfloat16 *dh, *da3, *da2, *da1;  // gradients w.r.t. (post-ReLU-masked) pre-activations, NB frames
   __nv_bfloat16* wpack;
 };
+// tensor maps of the TMA mainloop (built once per learner context: every operand buffer is fixed)
+struct TmaMaps {
+  alignas(64) CUtensorMap xs3, xs4, a1v, a2v2, a2v1, a3m128, a3m64, dhm128, dhm64, da3v, da3m, da2v, da2m, da1m;
+  alignas(64) CUtensorMap w1k, w2k, w3k, wfk, wfd, w3d, w2d;
+  bool valid = false;
+};
+// returns cudaSuccess or an error; `why` gets a message on failure
+cudaError_t build_tma_maps(const EncoderBuffers& buf, int NF, int NB, TmaMaps* maps, const char** why);
+// mode: 0 = TMA-fed tcgen05 (product path), 1 = CUDA-core triage (register gather), 2 = register-gather tcgen05
 cudaError_t launch_pack_weights(const ParamPtrs& p, __nv_bfloat16* wpack, cudaStream_t st);
-cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, bool simt, cudaStream_t st,
-                            const Profiler& pf);
+cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, const TmaMaps& maps, int mode,
+                            cudaStream_t st, const Profiler& pf);
 // backward for the first `frames` frames given buf.dh; accumulates into the (pre-zeroed) gradient tensors in `g`
-cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, bool simt, cudaStream_t st,
-                             const Profiler& pf);
+cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
+                             cudaStream_t st, const Profiler& pf);
 cudaError_t test_gemm(const void* A, const void* B, float* D, int M, int N, int K, bool mn_major, bool simt, cudaStream_t st);
 
 }  // namespace srl

@@ -56,7 +56,7 @@ class ImpalaHParams:
     adam_beta1: float = 0.9
     adam_beta2: float = 0.999
     adam_eps: float = 1e-8
-    simt_mainloop: bool = False          # debug: CUDA-core inner product instead of tcgen05
+    simt_mainloop: int = 0               # 0: TMA-fed tcgen05 (product path); debug: 1 CUDA-core triage, 2 register-gather tcgen05
 
     def to_c(self) -> _lib.SrlConfig:
         if self.reward_clipping not in ('abs_one', 'none'):
@@ -69,7 +69,7 @@ class ImpalaHParams:
         c.T, c.B, c.A = self.rollout_length, self.batch_size, self.num_actions
         c.optimizer = 0 if self.optimizer == 'rmsprop' else 1
         c.reward_clip_abs_one = 1 if self.reward_clipping == 'abs_one' else 0
-        c.simt_mainloop = 1 if self.simt_mainloop else 0
+        c.simt_mainloop = int(self.simt_mainloop)
         c.discounting, c.baseline_cost, c.entropy_cost = self.discounting, self.baseline_cost, self.entropy_cost
         c.clip_rho_threshold = -1.0 if self.clip_rho_threshold is None else self.clip_rho_threshold
         c.clip_pg_rho_threshold = -1.0 if self.clip_pg_rho_threshold is None else self.clip_pg_rho_threshold
