@@ -253,7 +253,7 @@ def main():
         return float(t.item())
 
     # ---------------- device-resident throughput ----------------
-    for i in range(W):
+    for i in range(max(W, 2 * POOL)):          # every pool batch is seen twice: eager warm-up, then graph capture
         learner.learn(dev_pool[i % POOL], sync_stats=False)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -285,7 +285,7 @@ def main():
                 feeder.result(last)             # D2H read of the previous step's losses (one step behind)
             last = s
         return feeder.result(last)
-    e2e_loop(W, 0)
+    e2e_loop(max(W, 6), 0)
     barrier()
     t0 = time.perf_counter()
     stats = e2e_loop(K, W)
@@ -305,7 +305,7 @@ def main():
     buf = (C.c_float * nslot)()
     nprof = min(K, 20)
     for i in range(nprof):
-        learner.learn(dev_pool[i % POOL], sync_stats=False)
+        learner.learn(dev_pool[i % POOL], sync_stats=False, use_graph=False)
         torch.cuda.synchronize()
         _lib.check(L.srl_learner_profile_collect(learner._h, buf))
         for j in range(nslot):
@@ -346,7 +346,9 @@ def main():
                           'rollout_length': T, 'columns_per_gpu': B, 'global_batch': B * world, 'num_actions': A, 'optimizer': 'rmsprop',
                           'parallelism': f'dp{world}' if world > 1 else 'single', 'grad_allreduce': 'nccl sum' if world > 1 else 'none',
                           'l2': f'inputs cycle through {POOL} distinct batches ({POOL * feeder.h2d_bytes / 1e6:.0f} MB > 126 MB L2)',
-                          'operands': 'bf16 tensor-core operands, fp32 accumulate, fp32 master weights / V-trace / optimizer'},
+                          'operands': 'bf16 tensor-core operands, fp32 accumulate, fp32 master weights / V-trace / optimizer',
+                          'launch': 'one CUDA graph per step (wgrad GEMMs on a parallel branch)' if world == 1 else
+                                    'CUDA graphs (forward_backward | apply) around an eager NCCL all-reduce'},
                'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': feeder.h2d_bytes, 'd2h_bytes_per_step': feeder.d2h_bytes,
                        'ms_per_step': e2e_s / K * 1e3, 'api': 'HostBatchFeeder.submit/learn/result + B200ImpalaLearner.learn (pinned host batches)',
                        'last_total_loss': stats['total_loss']},

@@ -84,7 +84,7 @@ extern "C" int srl_rmsprop_step(float* params, const float* grads, float* square
 extern "C" int srl_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* coef, float lr,
                              float beta1, float beta2, float eps, int step, void* stream) {
   REQ(params && grads && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "adam: bad argument");
-  CU(launch_adam(params, grads, exp_avg, exp_avg_sq, n, coef, lr, beta1, beta2, eps, step, (cudaStream_t)stream), "adam");
+  CU(launch_adam(params, grads, exp_avg, exp_avg_sq, n, coef, lr, beta1, beta2, eps, step, nullptr, (cudaStream_t)stream), "adam");
   return 0;
 }
 
@@ -142,6 +142,8 @@ struct srl_learner {
   int step;                       // optimizer step count (Adam bias correction)
   bool have_fwd;
   TmaMaps maps;                   // tensor maps of the TMA mainloop
+  SideStream ss;                  // wgrad side stream + fork/join events
+  int* dstep;                     // device-side optimizer step count (graph-replay safe Adam bias correction)
   Profiler pf;                    // per-kernel event bracketing (off by default)
   cudaEvent_t events[2 * PS_COUNT];
   bool slot_used[PS_COUNT];
@@ -197,6 +199,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   sizes[k++] = al(NB * 4);              // dbaseline
   sizes[k++] = al(4096 * 4);            // scratch
   sizes[k++] = al(16);                  // coef
+  sizes[k++] = al(16);                  // dstep
   int64_t total = 0;
   for (int i = 0; i < k; ++i) total += sizes[i];
   cudaError_t e = cudaMalloc(&L->arena, total);
@@ -222,6 +225,11 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   L->dbaseline = (float*)q; q += sizes[i++];
   L->scratch = (float*)q; q += sizes[i++];
   L->coef = (float*)q; q += sizes[i++];
+  L->dstep = (int*)q; q += sizes[i++];
+  if (cudaStreamCreateWithFlags(&L->ss.side, cudaStreamNonBlocking) != cudaSuccess) L->ss.side = nullptr;
+  for (int e2 = 0; e2 < 6 && L->ss.side; ++e2)
+    if (cudaEventCreateWithFlags(&L->ss.ev[e2], cudaEventDisableTiming) != cudaSuccess) { L->ss.side = nullptr; }
+  cudaGetLastError();
   if (cfg->simt_mainloop == 0) {
     const char* why = nullptr;
     if (build_tma_maps(L->buf, (int)NF, (int)NB, &L->maps, &why) != cudaSuccess) {
@@ -237,6 +245,8 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
 extern "C" int srl_learner_destroy(srl_learner_t* L) {
   if (!L) return 0;
   for (int i = 0; i < 2 * PS_COUNT; ++i) if (L->events[i]) cudaEventDestroy(L->events[i]);
+  for (int i = 0; i < 6; ++i) if (L->ss.ev[i]) cudaEventDestroy(L->ss.ev[i]);
+  if (L->ss.side) cudaStreamDestroy(L->ss.side);
   cudaFree(L->arena);
   delete L;
   return 0;
@@ -294,13 +304,18 @@ extern "C" int srl_learner_forward_backward(srl_learner_t* L, const uint8_t* obs
                         pg_advantages, L->dlogits, L->dbaseline, losses, L->scratch, st), "impala_tail");
   L->pf.e(PS_TAIL);
   L->pf.b(PS_ZERO_GRADS);
-  CU(cudaMemsetAsync(L->grads, 0, L->nparams * sizeof(float), st), "zero grads");
+  {  // fc.weight (95 % of the buffer) is stored whole by the fc wgrad GEMM; only the atomically accumulated segments are cleared
+    int64_t off[12], cnt[12];
+    layout(c.A, off, cnt);
+    CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), st), "zero conv grads");
+    CU(cudaMemsetAsync(L->grads + off[7], 0, (L->nparams - off[7]) * sizeof(float), st), "zero fc.bias/head grads");
+  }
   L->pf.e(PS_ZERO_GRADS);
   L->pf.b(PS_HEAD_BWD);
   CU(launch_head_bwd(L->dlogits, L->dbaseline, L->buf.h, reward, action, L->P.wp, L->P.wb, NB, c.A, L->buf.dh, L->G.wp, L->G.bp, L->G.wb,
                      L->G.bb, st), "head_bwd");
   L->pf.e(PS_HEAD_BWD);
-  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.simt_mainloop, st, L->pf), "encoder_backward");
+  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.simt_mainloop, st, L->pf, L->ss), "encoder_backward");
   L->have_fwd = true;
   return 0;
 }
@@ -319,7 +334,7 @@ extern "C" int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_ou
     CU(launch_rmsprop(L->params, L->grads, L->opt0, L->nparams, L->coef, c.learning_rate, c.alpha, c.epsilon, st), "rmsprop");
   } else {
     CU(launch_adam(L->params, L->grads, L->opt0, L->opt1, L->nparams, L->coef, c.learning_rate, c.adam_beta1, c.adam_beta2, c.adam_eps,
-                   L->step, st), "adam");
+                   L->step, L->dstep, st), "adam");
   }
   L->pf.e(PS_OPTIMIZER);
   L->pf.b(PS_PACK);

@@ -39,22 +39,25 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __
 }
 
 // u8 NCHW frames -> space-to-depth bf16 NHWC: xs[n][Y][X][c*16+dy*4+dx] = obs[n][c][4Y+dy][4X+dx]  (exact: u8 fits bf16).
-// One thread moves one u32 (4 x dx) -> 4 bf16 (8 B); consecutive threads write consecutive 8 B.
-__global__ void __launch_bounds__(256) obs_s2d_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ xs, int64_t total) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i & 15);               // (c, dy)
-    const int64_t pix = i >> 4;                // (n, Y, X)
-    const int X = (int)(pix % 21);
-    const int64_t t = pix / 21;
-    const int Y = (int)(t % 21);
-    const int64_t n = t / 21;
-    const int c = g >> 2, dy = g & 3;
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(obs + n * 28224 + c * 7056 + (4 * Y + dy) * 84 + 4 * X));
+// One block per (frame, Y): the 16 source rows (c,dy) are read coalesced (21 u32 each) into shared memory, then each
+// thread converts one u32 (4 x dx) to 4 bf16 and the block writes the 21 x 128 B output row contiguously.
+__global__ void __launch_bounds__(352) obs_s2d_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ xs) {
+  __shared__ uint32_t tile[16][21];
+  const int n = blockIdx.x / 21, Y = blockIdx.x - n * 21;
+  const int t = threadIdx.x;
+  if (t < 336) {
+    const int g = t / 21, X = t - g * 21;      // g = (c, dy)
+    tile[g][X] = __ldg(reinterpret_cast<const uint32_t*>(obs + (size_t)n * 28224 + (g >> 2) * 7056 + (4 * Y + (g & 3)) * 84) + X);
+  }
+  __syncthreads();
+  if (t < 336) {
+    const int X = t >> 4, g = t & 15;
+    const uint32_t w = tile[g][X];
     const float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - 8388608.f;
     const float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - 8388608.f;
     const float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388608.f;
     const float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388608.f;
-    *reinterpret_cast<uint2*>(xs + i * 4) = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3));
+    *reinterpret_cast<uint2*>(xs + ((size_t)blockIdx.x * 21 + X) * 64 + g * 4) = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3));
   }
 }
 
@@ -139,10 +142,7 @@ cudaError_t build_tma_maps(const EncoderBuffers& b, int NF, int NB, TmaMaps* M, 
 }
 
 static cudaError_t launch_s2d(const uint8_t* obs, int frames, bf16* xs, cudaStream_t st) {
-  const int64_t total = (int64_t)frames * 441 * 16;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  obs_s2d_kernel<<<blocks, 256, 0, st>>>(obs, xs, total);
+  obs_s2d_kernel<<<frames * 21, 352, 0, st>>>(obs, xs);
   return cudaGetLastError();
 }
 
@@ -185,27 +185,36 @@ static inline void split_k(int P, int target, int* pps, int* nsplit) {
 }
 
 cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
-                             cudaStream_t st, const Profiler& pf) {
+                             cudaStream_t st, const Profiler& pf, const SideStream& ss) {
   if (frames <= 0) return cudaSuccess;
   if (mode == 0) {
     if (!maps.valid) return cudaErrorInvalidValue;
+    // The wgrad GEMMs only feed the optimizer, so they run on a side stream beside the dgrad chain
+    // (dh -> da3 -> da2 -> da1).  With per-kernel profiling on everything stays on `st` so durations are clean.
+    const bool fork = ss.side != nullptr && !pf.on;
+    cudaStream_t sw = fork ? ss.side : st;
+    Profiler pw = pf; pw.st = sw;
+    if (fork) { SRL_TRY(cudaEventRecord(ss.ev[0], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[0], 0)); }
     { TFcWgrad::Params q{maps.dhm64, maps.a3m64, g.wf, g.bf, frames};
-      pf.b(PS_FC_WGRAD); SRL_TRY(igemm_tma_launch<TFcWgrad>(q, dim3(1, 4 * 50), st)); pf.e(PS_FC_WGRAD); }
+      pw.b(PS_FC_WGRAD); SRL_TRY(igemm_tma_launch<TFcWgrad>(q, dim3(1, 4 * 50), sw)); pw.e(PS_FC_WGRAD); }
     { TFcDgrad::Params q{maps.dhm128, maps.wfd, buf.a3, buf.da3, frames};
       pf.b(PS_FC_DGRAD); SRL_TRY(igemm_tma_launch<TFcDgrad>(q, dim3(cdiv(frames, 128), 49), st)); pf.e(PS_FC_DGRAD); }
+    if (fork) { SRL_TRY(cudaEventRecord(ss.ev[1], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[1], 0)); }
     { const int fps = cdiv(frames, 30);
       TConv3Wgrad::Params q{maps.a2v1, maps.da3m, g.w3, g.b3, frames, fps};
-      pf.b(PS_CONV3_WGRAD); SRL_TRY(igemm_tma_launch<TConv3Wgrad>(q, dim3(cdiv(frames, fps), 5), st)); pf.e(PS_CONV3_WGRAD); }
+      pw.b(PS_CONV3_WGRAD); SRL_TRY(igemm_tma_launch<TConv3Wgrad>(q, dim3(cdiv(frames, fps), 5), sw)); pw.e(PS_CONV3_WGRAD); }
     { TConv3Dgrad::Params q{maps.da3v, maps.w3d, buf.a2, buf.da2, frames};
       pf.b(PS_CONV3_DGRAD); SRL_TRY(igemm_tma_launch<TConv3Dgrad>(q, dim3(frames, 1), st)); pf.e(PS_CONV3_DGRAD); }
+    if (fork) { SRL_TRY(cudaEventRecord(ss.ev[2], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[2], 0)); }
     { const int fps = cdiv(frames, 30);
       TConv2Wgrad::Params q{maps.a1v, maps.da2m, g.w2, g.b2, frames, fps};
-      pf.b(PS_CONV2_WGRAD); SRL_TRY(igemm_tma_launch<TConv2Wgrad>(q, dim3(cdiv(frames, fps), 5), st)); pf.e(PS_CONV2_WGRAD); }
+      pw.b(PS_CONV2_WGRAD); SRL_TRY(igemm_tma_launch<TConv2Wgrad>(q, dim3(cdiv(frames, fps), 5), sw)); pw.e(PS_CONV2_WGRAD); }
     { TConv2Dgrad::Params q{maps.da2v, maps.w2d, buf.a1, buf.da1, frames};
       pf.b(PS_CONV2_DGRAD); SRL_TRY(igemm_tma_launch<TConv2Dgrad>(q, dim3(frames, 4), st)); pf.e(PS_CONV2_DGRAD); }
     { const int fps = cdiv(frames, 49);
       TConv1Wgrad::Params q{maps.xs4, maps.da1m, g.w1, g.b1, frames, fps};
       pf.b(PS_CONV1_WGRAD); SRL_TRY(igemm_tma_launch<TConv1Wgrad>(q, dim3(cdiv(frames, fps), 3), st)); pf.e(PS_CONV1_WGRAD); }
+    if (fork) { SRL_TRY(cudaEventRecord(ss.ev[3], sw)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[3], 0)); }
     return cudaSuccess;
   }
   const bool simt = mode == 1;

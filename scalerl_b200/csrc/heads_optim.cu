@@ -10,7 +10,7 @@ namespace srl {
 // ------------------------------------------------------------------------------------------------
 // heads forward: one warp per frame.  core = [h(512), clamp(reward,-1,1), one_hot(action)(A)]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ hpart, int nsplit, const float* __restrict__ bfc,
+__global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__ hpart, int nsplit, const float* __restrict__ bfc,
                                                        float* __restrict__ h, const float* __restrict__ reward,
                                                        const int64_t* __restrict__ action, const float* __restrict__ Wp,
                                                        const float* __restrict__ bp, const float* __restrict__ Wb,
@@ -121,14 +121,18 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict
     is_last = atomicAdd(reinterpret_cast<unsigned*>(scratch), 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  if (is_last && threadIdx.x < 32) {   // fixed-order parallel sum of the block partials (deterministic)
     __threadfence();
     double t = 0.0;
-    for (unsigned k = 0; k < gridDim.x; ++k) t += (double)reinterpret_cast<volatile float*>(scratch)[4 + k];
-    const float norm = (float)sqrt(t);
-    coef[0] = norm;
-    coef[1] = max_norm >= 0.f ? fminf(max_norm / (norm + 1e-6f), 1.0f) : 1.0f;
-    *reinterpret_cast<unsigned*>(scratch) = 0u;
+    for (unsigned k = threadIdx.x; k < gridDim.x; k += 32) t += (double)reinterpret_cast<volatile float*>(scratch)[4 + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) {
+      const float norm = (float)sqrt(t);
+      coef[0] = norm;
+      coef[1] = max_norm >= 0.f ? fminf(max_norm / (norm + 1e-6f), 1.0f) : 1.0f;
+      *reinterpret_cast<unsigned*>(scratch) = 0u;
+    }
   }
 }
 
@@ -159,10 +163,16 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, con
 }
 
 // torch.optim.Adam: m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= (lr/bc1) m / (sqrt(v)/sqrt(bc2) + eps)
+// The 1-based step count is read from device memory (dstep, incremented by adam_step_inc_kernel) so that a captured
+// CUDA graph replays with the right bias correction; dstep == nullptr uses the host-provided `step`.
+__global__ void adam_step_inc_kernel(int* dstep) { *dstep += 1; }
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, const float* __restrict__ coef, float lr, float b1,
-                                                   float b2, float eps, float inv_bc1, float inv_sqrt_bc2) {
+                                                   float b2, float eps, int step, const int* __restrict__ dstep) {
   const float c = coef ? __ldg(coef + 1) : 1.0f;
+  const int t = dstep ? *dstep : step;
+  const float inv_bc1 = 1.0f / (float)(1.0 - pow((double)b1, (double)t));
+  const float inv_sqrt_bc2 = 1.0f / sqrtf((float)(1.0 - pow((double)b2, (double)t)));
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gk = g[i] * c;
     const float mk = b1 * m[i] + (1.f - b1) * gk;
@@ -177,7 +187,7 @@ cudaError_t launch_head_fwd(const float* hpart, int nsplit, const float* bfc, fl
                             const float* Wp, const float* bp, const float* Wb, const float* bb, int N, int A, float* logits,
                             float* baseline, cudaStream_t st) {
   if (N <= 0) return cudaSuccess;
-  head_fwd_kernel<<<(N + 7) / 8, 256, 0, st>>>(hpart, nsplit, bfc, h, reward, action, Wp, bp, Wb, bb, N, A, logits, baseline);
+  head_fwd_kernel<<<(N + 3) / 4, 128, 0, st>>>(hpart, nsplit, bfc, h, reward, action, Wp, bp, Wb, bb, N, A, logits, baseline);
   return cudaGetLastError();
 }
 cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const float* h, const float* reward, const int64_t* action,
@@ -204,9 +214,9 @@ cudaError_t launch_rmsprop(float* p, const float* g, float* v, int64_t n, const 
   return cudaGetLastError();
 }
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* coef, float lr, float b1, float b2, float eps,
-                        int step, cudaStream_t st) {
-  const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
-  adam_kernel<<<ew_blocks(n * 4), 256, 0, st>>>(p, g, m, v, n, coef, lr, b1, b2, eps, (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)));
+                        int step, int* dstep, cudaStream_t st) {
+  if (dstep) adam_step_inc_kernel<<<1, 1, 0, st>>>(dstep);
+  adam_kernel<<<ew_blocks(n * 4), 256, 0, st>>>(p, g, m, v, n, coef, lr, b1, b2, eps, step, dstep);
   return cudaGetLastError();
 }
 

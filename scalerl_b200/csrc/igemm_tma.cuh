@@ -164,8 +164,12 @@ template <class P>
 cudaError_t igemm_tma_launch(const typename P::Params& p, dim3 grid, cudaStream_t stream) {
   using C = TmaCfg<P>;
   if (grid.x == 0 || grid.y == 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(igemm_tma_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
+  static bool attr_set = false;   // set once (outside any stream capture: the first step always runs eagerly)
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_tma_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
   igemm_tma_kernel<P><<<grid, IGT_THREADS, C::SMEM_BYTES, stream>>>(p);
   return cudaGetLastError();
 }

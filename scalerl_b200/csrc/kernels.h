@@ -18,6 +18,11 @@ struct Profiler {
   void b(int slot) const { if (on) cudaEventRecord(ev[2 * slot], st); }
   void e(int slot) const { if (on) cudaEventRecord(ev[2 * slot + 1], st); }
 };
+// second stream + fork/join events: the wgrad GEMMs run beside the dgrad chain (also under stream capture)
+struct SideStream {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
 
 // ---- vtrace.cu
 cudaError_t launch_vtrace_iw(const float* log_rhos, const float* discounts, const float* rewards, const float* values,
@@ -43,7 +48,7 @@ cudaError_t launch_grad_norm(const float* g, int64_t n, float max_norm, float* c
 cudaError_t launch_rmsprop(float* p, const float* g, float* v, int64_t n, const float* coef, float lr, float alpha, float eps,
                            cudaStream_t st);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* coef, float lr, float b1, float b2, float eps,
-                        int step, cudaStream_t st);
+                        int step, int* dstep, cudaStream_t st);
 
 // ---- encoder.cu
 // packed bf16 operand copies of the conv/fc weights (element offsets into one buffer)
@@ -84,7 +89,7 @@ cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, 
                             cudaStream_t st, const Profiler& pf);
 // backward for the first `frames` frames given buf.dh; accumulates into the (pre-zeroed) gradient tensors in `g`
 cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
-                             cudaStream_t st, const Profiler& pf);
+                             cudaStream_t st, const Profiler& pf, const SideStream& ss);
 cudaError_t test_gemm(const void* A, const void* B, float* D, int M, int N, int K, bool mn_major, bool simt, cudaStream_t st);
 
 }  // namespace srl

@@ -85,7 +85,7 @@ class B200ImpalaLearner:
     reference's stats dict (impala_atari.py:333-340)."""
 
     def __init__(self, hp: ImpalaHParams, device: Optional[torch.device] = None, process_group=None,
-                 init_state_dict: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0):
+                 init_state_dict: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0, use_graph: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError('B200ImpalaLearner needs a CUDA device: scalerl_b200 has no CPU fallback')
         self.hp = hp
@@ -121,6 +121,9 @@ class B200ImpalaLearner:
             self._pg_adv = torch.empty(T, B, device=self.device)
             self._stats_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self.global_step = 0
+        self.use_graph = use_graph
+        self._graphs = {}       # batch buffer addresses -> captured CUDA graph(s) of the step
+        self._seen = set()
 
     # ------------------------------------------------------------------ parameters
     def _view(self, flat, i):
@@ -240,14 +243,59 @@ class B200ImpalaLearner:
         _lib.check(self._L.srl_learner_apply_gradients(self._h, self._coef.data_ptr(), self._stream()), 'srl_learner_apply_gradients')
         self._opt_steps = self.global_opt_step + 1
 
-    @torch.no_grad()
-    def learn(self, batch: Dict[str, torch.Tensor], initial_rnn_state=(), sync_stats: bool = True) -> Dict[str, object]:
-        """One learner step (impala_atari.py:288-346).  Returns the reference's stats dict when sync_stats
-        (one D2H read of 6 floats), else {} with everything left enqueued on the stream."""
+    def _enqueue_step(self, batch):
+        """forward_backward -> [NCCL SUM all-reduce] -> apply_gradients on the current stream"""
         self.forward_backward(batch)
         if self._dist:
             self.all_reduce_gradients()
         self.apply_gradients()
+
+    def _graph_step(self, batch):
+        """Replay the step as CUDA graph(s) keyed by the batch buffers' addresses.  First sight of a buffer set runs
+        eagerly (warm-up: sets kernel attributes, allocator state), the second captures, later calls replay.
+        With world_size > 1 the NCCL all-reduce stays outside: graph(forward_backward) -> all_reduce -> graph(apply)."""
+        key = tuple(batch[k].data_ptr() for k in ('obs', 'reward', 'done', 'action', 'policy_logits'))
+        g = self._graphs.get(key)
+        if g is None:
+            if key not in self._seen:
+                self._seen.add(key)
+                self._enqueue_step(batch)
+                return
+            hp = self.hp
+            self._check_batch(batch, hp.rollout_length + 1)
+            cur = torch.cuda.current_stream(self.device)
+            cur.synchronize()
+            if self._dist:
+                g_fb, g_ap = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_fb):
+                    self.forward_backward(batch)
+                with torch.cuda.graph(g_ap):
+                    self.apply_gradients()
+                g = (g_fb, g_ap)
+            else:
+                g_all = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_all):
+                    self.forward_backward(batch)
+                    self.apply_gradients()
+                g = (g_all,)
+            self._graphs[key] = g
+        if len(g) == 2:
+            g[0].replay()
+            self.all_reduce_gradients()
+            g[1].replay()
+        else:
+            g[0].replay()
+        self._opt_steps = self.global_opt_step + 1
+
+    @torch.no_grad()
+    def learn(self, batch: Dict[str, torch.Tensor], initial_rnn_state=(), sync_stats: bool = True,
+              use_graph: Optional[bool] = None) -> Dict[str, object]:
+        """One learner step (impala_atari.py:288-346).  Returns the reference's stats dict when sync_stats
+        (one D2H read of 6 floats), else {} with everything left enqueued on the stream."""
+        if self.use_graph if use_graph is None else use_graph:
+            self._graph_step(batch)
+        else:
+            self._enqueue_step(batch)
         self.global_step += self.hp.rollout_length * self.hp.batch_size
         if not sync_stats:
             return {}

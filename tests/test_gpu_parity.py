@@ -337,3 +337,18 @@ def test_optimizer_ops_vs_oracle():
         _lib.check(L.srl_adam_step(P2.data_ptr(), G.data_ptr(), M.data_ptr(), V2.data_ptr(), n, None, 1e-3, 0.9, 0.999, 1e-8, step, None))
         O.adam_step(pa, {'x': gr}, ma, va, step, 1e-3)
     assert_close(P2, pa['x'], 1e-6, 'adam p')
+
+
+def test_graph_replay_equals_eager():
+    """the CUDA-graph path (wgrads on a parallel branch) gives the same update as eager single-stream launches"""
+    T, B, A = 5, 6, 6
+    La, params = _learner(T, B, A, 7)
+    Lb, _ = _learner(T, B, A, 7)
+    La.use_graph, Lb.use_graph = True, False
+    batch = {k: dev(v) for k, v in O.synthetic_batch(T, B, A, seed=3, done_p=0.1).items()}
+    for step in range(4):          # eager warm-up, capture, replay, replay
+        sa = La.learn(batch)
+        sb = Lb.learn(batch)
+        assert abs(sa['total_loss'] - sb['total_loss']) <= 1e-5 * max(1.0, abs(sb['total_loss'])), step
+        assert rel_l2(La.flat_params.cpu(), Lb.flat_params.cpu()) < 1e-6, step
+    assert len(La._graphs) == 1 and len(Lb._graphs) == 0
