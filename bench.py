@@ -295,6 +295,22 @@ def main():
         dist.barrier(device_ids=[local_rank])
     e2e_s = max_over_ranks(dt)
     e2e_value = frames / e2e_s
+    # diagnostics: the H2D copies alone, and the same loop with eager launches instead of CUDA graphs
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        s_ = feeder.submit(host_pool[i % POOL])
+        feeder.ready[s_].synchronize()
+        feeder._learned += 1          # slot handed back without a learner step
+    h2d_only_ms = (time.perf_counter() - t0) / K * 1e3
+    learner.use_graph = False
+    e2e_loop(3, 0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_loop(K, W)
+    torch.cuda.synchronize()
+    e2e_eager_ms = (time.perf_counter() - t0) / K * 1e3
+    learner.use_graph = True
 
     # ---------------- per-kernel durations (events around every launch) ----------------
     L = _lib.lib()
@@ -331,6 +347,33 @@ def main():
                 'per_kernel_ms': {k: round(v, 5) for k, v in per_kernel_ms.items()},
                 'per_gemm_tflops': {k: round(v['tflops'], 2) for k, v in gemm.items()}}
 
+    # ---------------- stand-alone V-trace kernel: GB/s vs measured HBM peak (BASELINE.json metric, second half) ----------------
+    vtrace = None
+    if rank == 0:
+        from scalerl_b200 import ops
+        vtrace = {}
+        for (vt, vb, variant) in ((20, 512, 1), (20, 512, 0), (20, 1 << 20, 0), (20, 1 << 22, 0)):
+            g = torch.Generator(device=dev).manual_seed(1)
+            nrot = 1 if vb < (1 << 18) else max(2, int(200e6 // (24 * vt * vb)) + 1)   # rotate > L2 worth of inputs at the large sizes
+            sets = [[torch.randn(vt, vb, device=dev, generator=g) * 0.5, (torch.rand(vt, vb, device=dev, generator=g) > 0.02).float() * 0.99,
+                     torch.randn(vt, vb, device=dev, generator=g), torch.randn(vt, vb, device=dev, generator=g),
+                     torch.randn(vb, device=dev, generator=g)] for _ in range(nrot)]
+            for i in range(3):
+                ops.from_importance_weights(*sets[i % nrot], variant=variant)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            a.record()
+            for i in range(reps):
+                ops.from_importance_weights(*sets[i % nrot], variant=variant)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / reps
+            nbytes = 24 * vt * vb + 4 * vb
+            vtrace[f'T{vt}_B{vb}_{"scan" if variant else "seq"}'] = {
+                'us': ms * 1e3, 'algorithmic_bytes': nbytes, 'GBps': nbytes / (ms * 1e-3) / 1e9,
+                'frac_of_hbm_peak': nbytes / (ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'includes': 'torch.empty of 2 outputs + launch (host-timed ops wrapper)'}
+
     # ---------------- CPU baseline (rank 0, N=1) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -351,8 +394,9 @@ def main():
                                     'CUDA graphs (forward_backward | apply) around an eager NCCL all-reduce'},
                'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': feeder.h2d_bytes, 'd2h_bytes_per_step': feeder.d2h_bytes,
                        'ms_per_step': e2e_s / K * 1e3, 'api': 'HostBatchFeeder.submit/learn/result + B200ImpalaLearner.learn (pinned host batches)',
-                       'last_total_loss': stats['total_loss']},
-               'gpu_launches': 19 * K, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'losses_finite': losses_finite}
+                       'last_total_loss': stats['total_loss'], 'h2d_only_ms_per_step': h2d_only_ms, 'eager_launch_ms_per_step': e2e_eager_ms},
+               'gpu_launches': 19 * K, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'losses_finite': losses_finite,
+               'vtrace_standalone': vtrace}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

