@@ -168,7 +168,7 @@ def cpu_learner_fps(T, B, A, budget_s, warmup=1, max_steps=50, min_steps=3):
     return n * T * B / dt, n, dt / n, cores
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, real_stdout):
     if rank != 0:
         return
     T, B, A = args.T, args.B, args.A
@@ -194,10 +194,24 @@ def run_reference(args, rank, world):
                       'columns_per_gpu': B, 'global_batch': B * world, 'num_actions': A, 'optimizer': 'rmsprop'},
            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
            'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
-    print(json.dumps(out), flush=True)
+    emit(real_stdout, out)
 
 
 def main():
+    # keep stdout clean for the single JSON line: anything libraries print (NCCL banner, warnings) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main(real_stdout)
+    finally:
+        os.dup2(real_stdout, 1)
+
+
+def emit(real_stdout, obj):
+    os.write(real_stdout, (json.dumps(obj) + '\n').encode())
+
+
+def _main(real_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
@@ -215,7 +229,7 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, real_stdout)
         return
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
@@ -391,13 +405,13 @@ def main():
                           'l2': f'inputs cycle through {POOL} distinct batches ({POOL * feeder.h2d_bytes / 1e6:.0f} MB > 126 MB L2)',
                           'operands': 'bf16 tensor-core operands, fp32 accumulate, fp32 master weights / V-trace / optimizer',
                           'launch': 'one CUDA graph per step (wgrad GEMMs on a parallel branch)' if world == 1 else
-                                    'CUDA graphs (forward_backward | apply) around an eager NCCL all-reduce'},
+                                    'CUDA graphs begin|finish|apply; NCCL all-reduce of fc.weight overlaps the conv backward'},
                'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': feeder.h2d_bytes, 'd2h_bytes_per_step': feeder.d2h_bytes,
                        'ms_per_step': e2e_s / K * 1e3, 'api': 'HostBatchFeeder.submit/learn/result + B200ImpalaLearner.learn (pinned host batches)',
                        'last_total_loss': stats['total_loss'], 'h2d_only_ms_per_step': h2d_only_ms, 'eager_launch_ms_per_step': e2e_eager_ms},
                'gpu_launches': 19 * K, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'losses_finite': losses_finite,
                'vtrace_standalone': vtrace}
-        print(json.dumps(out), flush=True)
+        emit(real_stdout, out)
     if world > 1:
         dist.destroy_process_group()
 

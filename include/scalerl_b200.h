@@ -81,7 +81,9 @@ typedef struct srl_config {
 
 /* Number of fp32 elements of the flat parameter buffer for A actions, and the element offset / count of
  * each of the 12 AtariNet tensors in state_dict order (conv1.weight, conv1.bias, ..., baseline.bias),
- * PyTorch layouts.  Segments are padded to multiples of 4 floats. offsets/counts: int64[12]. */
+ * PyTorch layouts.  Segments are padded to multiples of 4 floats. offsets/counts: int64[12], indexed in state_dict order;
+ * in memory the small tensors come first and fc.weight last (offsets[6] is the largest), so [0, offsets[6]) is the
+ * "small" gradient block and [offsets[6], total) is fc.weight. */
 int64_t srl_param_layout(int A, int64_t* offsets, int64_t* counts);
 
 /* params / grads / opt_state0 / opt_state1: flat f32 device buffers of srl_param_layout() elements, owned
@@ -108,6 +110,16 @@ int srl_learner_forward(srl_learner_t* L, const uint8_t* obs, const float* rewar
 int srl_learner_forward_backward(srl_learner_t* L, const uint8_t* obs, const float* reward, const uint8_t* done,
                                  const int64_t* action, const float* behavior_logits,
                                  float* losses, float* vs, float* pg_advantages, void* stream);
+
+/* The same step in two halves, for overlapping the gradient all-reduce with the backward pass:
+ *   _begin : forward + V-trace/loss + head backward + the fc layer's backward.  On return (in stream order) the
+ *            fc.weight / fc.bias segments of `grads` (95 % of the bytes) are final -> start their all-reduce.
+ *   _finish: conv3 / conv2 / conv1 backward; afterwards the remaining segments are final.
+ * srl_learner_forward_backward == _begin followed by _finish. */
+int srl_learner_forward_backward_begin(srl_learner_t* L, const uint8_t* obs, const float* reward, const uint8_t* done,
+                                       const int64_t* action, const float* behavior_logits,
+                                       float* losses, float* vs, float* pg_advantages, void* stream);
+int srl_learner_backward_finish(srl_learner_t* L, const uint8_t* obs, void* stream);
 
 /* clip_grad_norm_(max_grad_norm) over `grads` (after the caller's all-reduce, if any) + optimizer step +
  * weight re-pack.  grad_norm_out: f32 [2] = {total L2 norm, clip coefficient} (may be NULL). */

@@ -35,6 +35,8 @@ _SIGS = {
     'srl_learner_pack_weights': [_P, _P],
     'srl_learner_forward': [_P, _P, _P, _P, _I, _P, _P, _P],
     'srl_learner_forward_backward': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    'srl_learner_forward_backward_begin': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    'srl_learner_backward_finish': [_P, _P, _P],
     'srl_learner_apply_gradients': [_P, _P, _P],
     'srl_learner_debug_buffer': [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_L)],
     'srl_grad_norm_clip_coef': [_P, _L, _F, _P, _P, _P],

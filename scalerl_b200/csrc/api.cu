@@ -102,11 +102,16 @@ extern "C" int srl_test_gemm_mnmajor(const void* At, const void* Bt, float* D, i
 // ------------------------------------------------------------------------------------------------
 // parameter layout
 // ------------------------------------------------------------------------------------------------
+// Flat buffer order: every small tensor first (conv1..3, fc.bias, heads), fc.weight LAST.  The small block is one
+// contiguous range (one memset, one late all-reduce); fc.weight (95 % of the bytes) is final early in the backward pass
+// and can be all-reduced while the conv layers are still back-propagating.  off/cnt are indexed in state_dict order.
 static int64_t layout(int A, int64_t* off, int64_t* cnt) {
   const int64_t core = 513 + A;
   const int64_t counts[12] = {32 * 256, 32, 64 * 512, 64, 64 * 576, 64, 512 * 3136, 512, A * core, A, core, 1};
+  const int order[12] = {0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 6};
   int64_t o = 0;
-  for (int i = 0; i < 12; ++i) {
+  for (int k = 0; k < 12; ++k) {
+    const int i = order[k];
     if (off) off[i] = o;
     if (cnt) cnt[i] = counts[i];
     o += (counts[i] + 3) & ~int64_t(3);
@@ -288,12 +293,8 @@ extern "C" int srl_learner_forward(srl_learner_t* L, const uint8_t* obs, const f
   return forward_impl(L, obs, reward, action, rows * L->cfg.B, policy_logits, baseline, (cudaStream_t)stream);
 }
 
-extern "C" int srl_learner_forward_backward(srl_learner_t* L, const uint8_t* obs, const float* reward, const uint8_t* done,
-                                            const int64_t* action, const float* behavior_logits, float* losses, float* vs,
-                                            float* pg_advantages, void* stream) {
-  REQ(L && obs && reward && done && action && behavior_logits && losses, "learner_forward_backward: NULL pointer");
-  REQ((reinterpret_cast<uintptr_t>(obs) & 3) == 0, "learner_forward_backward: obs must be 4-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
+static int fb_begin(srl_learner* L, const uint8_t* obs, const float* reward, const uint8_t* done, const int64_t* action,
+                    const float* behavior_logits, float* losses, float* vs, float* pg_advantages, cudaStream_t st, int phase) {
   const srl_config_t& c = L->cfg;
   const int NF = (c.T + 1) * c.B, NB = c.T * c.B;
   int rc = forward_impl(L, obs, reward, action, NF, L->logits, L->baseline, st);
@@ -307,16 +308,40 @@ extern "C" int srl_learner_forward_backward(srl_learner_t* L, const uint8_t* obs
   {  // fc.weight (95 % of the buffer) is stored whole by the fc wgrad GEMM; only the atomically accumulated segments are cleared
     int64_t off[12], cnt[12];
     layout(c.A, off, cnt);
-    CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), st), "zero conv grads");
-    CU(cudaMemsetAsync(L->grads + off[7], 0, (L->nparams - off[7]) * sizeof(float), st), "zero fc.bias/head grads");
+    CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), st), "zero small grads");   // everything before fc.weight
   }
   L->pf.e(PS_ZERO_GRADS);
   L->pf.b(PS_HEAD_BWD);
   CU(launch_head_bwd(L->dlogits, L->dbaseline, L->buf.h, reward, action, L->P.wp, L->P.wb, NB, c.A, L->buf.dh, L->G.wp, L->G.bp, L->G.wb,
                      L->G.bb, st), "head_bwd");
   L->pf.e(PS_HEAD_BWD);
-  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.simt_mainloop, st, L->pf, L->ss), "encoder_backward");
+  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.simt_mainloop, st, L->pf, L->ss, phase), "encoder_backward");
   L->have_fwd = true;
+  return 0;
+}
+
+extern "C" int srl_learner_forward_backward(srl_learner_t* L, const uint8_t* obs, const float* reward, const uint8_t* done,
+                                            const int64_t* action, const float* behavior_logits, float* losses, float* vs,
+                                            float* pg_advantages, void* stream) {
+  REQ(L && obs && reward && done && action && behavior_logits && losses, "learner_forward_backward: NULL pointer");
+  REQ((reinterpret_cast<uintptr_t>(obs) & 3) == 0, "learner_forward_backward: obs must be 4-byte aligned");
+  return fb_begin(L, obs, reward, done, action, behavior_logits, losses, vs, pg_advantages, (cudaStream_t)stream, 2);
+}
+
+extern "C" int srl_learner_forward_backward_begin(srl_learner_t* L, const uint8_t* obs, const float* reward, const uint8_t* done,
+                                                  const int64_t* action, const float* behavior_logits, float* losses, float* vs,
+                                                  float* pg_advantages, void* stream) {
+  REQ(L && obs && reward && done && action && behavior_logits && losses, "learner_forward_backward_begin: NULL pointer");
+  REQ((reinterpret_cast<uintptr_t>(obs) & 3) == 0, "learner_forward_backward_begin: obs must be 4-byte aligned");
+  return fb_begin(L, obs, reward, done, action, behavior_logits, losses, vs, pg_advantages, (cudaStream_t)stream, 0);
+}
+
+extern "C" int srl_learner_backward_finish(srl_learner_t* L, const uint8_t* obs, void* stream) {
+  REQ(L && obs, "learner_backward_finish: NULL pointer");
+  REQ(L->have_fwd, "learner_backward_finish: call srl_learner_forward_backward_begin first");
+  const srl_config_t& c = L->cfg;
+  L->pf.st = (cudaStream_t)stream;
+  CU(encoder_backward(obs, c.T * c.B, L->buf, L->G, L->maps, c.simt_mainloop, (cudaStream_t)stream, L->pf, L->ss, 1), "encoder_backward");
   return 0;
 }
 

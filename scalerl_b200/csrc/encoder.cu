@@ -185,8 +185,9 @@ static inline void split_k(int P, int target, int* pps, int* nsplit) {
 }
 
 cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
-                             cudaStream_t st, const Profiler& pf, const SideStream& ss) {
+                             cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase) {
   if (frames <= 0) return cudaSuccess;
+  const bool do_fc = phase != 1, do_conv = phase != 0;
   if (mode == 0) {
     if (!maps.valid) return cudaErrorInvalidValue;
     // The wgrad GEMMs only feed the optimizer, so they run on a side stream beside the dgrad chain
@@ -194,11 +195,15 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
     const bool fork = ss.side != nullptr && !pf.on;
     cudaStream_t sw = fork ? ss.side : st;
     Profiler pw = pf; pw.st = sw;
-    if (fork) { SRL_TRY(cudaEventRecord(ss.ev[0], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[0], 0)); }
-    { TFcWgrad::Params q{maps.dhm64, maps.a3m64, g.wf, g.bf, frames};
-      pw.b(PS_FC_WGRAD); SRL_TRY(igemm_tma_launch<TFcWgrad>(q, dim3(1, 4 * 50), sw)); pw.e(PS_FC_WGRAD); }
-    { TFcDgrad::Params q{maps.dhm128, maps.wfd, buf.a3, buf.da3, frames};
-      pf.b(PS_FC_DGRAD); SRL_TRY(igemm_tma_launch<TFcDgrad>(q, dim3(cdiv(frames, 128), 49), st)); pf.e(PS_FC_DGRAD); }
+    if (do_fc) {
+      if (fork) { SRL_TRY(cudaEventRecord(ss.ev[0], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[0], 0)); }
+      { TFcWgrad::Params q{maps.dhm64, maps.a3m64, g.wf, g.bf, frames};
+        pw.b(PS_FC_WGRAD); SRL_TRY(igemm_tma_launch<TFcWgrad>(q, dim3(1, 4 * 50), sw)); pw.e(PS_FC_WGRAD); }
+      { TFcDgrad::Params q{maps.dhm128, maps.wfd, buf.a3, buf.da3, frames};
+        pf.b(PS_FC_DGRAD); SRL_TRY(igemm_tma_launch<TFcDgrad>(q, dim3(cdiv(frames, 128), 49), st)); pf.e(PS_FC_DGRAD); }
+      if (fork && !do_conv) { SRL_TRY(cudaEventRecord(ss.ev[4], sw)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[4], 0)); }
+    }
+    if (!do_conv) return cudaSuccess;
     if (fork) { SRL_TRY(cudaEventRecord(ss.ev[1], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[1], 0)); }
     { const int fps = cdiv(frames, 30);
       TConv3Wgrad::Params q{maps.a2v1, maps.da3m, g.w3, g.b3, frames, fps};
@@ -219,10 +224,13 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
   }
   const bool simt = mode == 1;
   int pps, ns;
-  { FcWgrad::Params q{buf.dh, buf.a3, g.wf, g.bf, frames};
-    pf.b(PS_FC_WGRAD); SRL_TRY(igemm_launch<FcWgrad>(q, dim3(1, 4 * 49), st, simt)); pf.e(PS_FC_WGRAD); }
-  { FcDgrad::Params q{buf.dh, buf.wpack + WPack::WFD, buf.a3, buf.da3, frames};
-    pf.b(PS_FC_DGRAD); SRL_TRY(igemm_launch<FcDgrad>(q, dim3(cdiv(frames, 128), 49), st, simt)); pf.e(PS_FC_DGRAD); }
+  if (do_fc) {
+    { FcWgrad::Params q{buf.dh, buf.a3, g.wf, g.bf, frames};
+      pf.b(PS_FC_WGRAD); SRL_TRY(igemm_launch<FcWgrad>(q, dim3(1, 4 * 49), st, simt)); pf.e(PS_FC_WGRAD); }
+    { FcDgrad::Params q{buf.dh, buf.wpack + WPack::WFD, buf.a3, buf.da3, frames};
+      pf.b(PS_FC_DGRAD); SRL_TRY(igemm_launch<FcDgrad>(q, dim3(cdiv(frames, 128), 49), st, simt)); pf.e(PS_FC_DGRAD); }
+  }
+  if (!do_conv) return cudaSuccess;
   { split_k(frames * 49, 29, &pps, &ns);
     Conv3Wgrad::Params q{buf.a2, buf.da3, g.w3, g.b3, frames * 49, pps};
     pf.b(PS_CONV3_WGRAD); SRL_TRY(igemm_launch<Conv3Wgrad>(q, dim3(ns, 5), st, simt)); pf.e(PS_CONV3_WGRAD); }

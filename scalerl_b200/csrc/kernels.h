@@ -88,8 +88,10 @@ cudaError_t launch_pack_weights(const ParamPtrs& p, __nv_bfloat16* wpack, cudaSt
 cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, const TmaMaps& maps, int mode,
                             cudaStream_t st, const Profiler& pf);
 // backward for the first `frames` frames given buf.dh; accumulates into the (pre-zeroed) gradient tensors in `g`
+// phase: 0 = fc layer only (fc.weight / fc.bias gradients complete and joined to `st` on return: 95 % of the gradient
+//        bytes, ready for an early all-reduce), 1 = conv layers only, 2 = both
 cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
-                             cudaStream_t st, const Profiler& pf, const SideStream& ss);
+                             cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase);
 cudaError_t test_gemm(const void* A, const void* B, float* D, int M, int N, int K, bool mn_major, bool simt, cudaStream_t st);
 
 }  // namespace srl

@@ -233,10 +233,25 @@ class B200ImpalaLearner:
             'srl_learner_forward_backward')
 
     def all_reduce_gradients(self):
-        """SUM (not mean) all-reduce of the flat gradient + loss scalars over NCCL."""
+        """SUM (not mean) all-reduce of the whole flat gradient over NCCL."""
         dist = torch.distributed
         dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM, group=self.pg or None)
-        dist.all_reduce(self._losses, op=dist.ReduceOp.SUM, group=self.pg or None)
+
+    @torch.no_grad()
+    def forward_backward_begin(self, batch):
+        """first half of forward_backward: on return (stream order) the fc.weight gradient (95 % of the bytes) is final"""
+        hp = self.hp
+        self._check_batch(batch, hp.rollout_length + 1)
+        done = batch['done']
+        done_u8 = done.view(torch.uint8) if done.dtype == torch.bool else done
+        _lib.check(self._L.srl_learner_forward_backward_begin(
+            self._h, batch['obs'].data_ptr(), batch['reward'].data_ptr(), done_u8.data_ptr(), batch['action'].data_ptr(),
+            batch['policy_logits'].data_ptr(), self._losses.data_ptr(), self._vs.data_ptr(), self._pg_adv.data_ptr(), self._stream()),
+            'srl_learner_forward_backward_begin')
+
+    @torch.no_grad()
+    def backward_finish(self, batch):
+        _lib.check(self._L.srl_learner_backward_finish(self._h, batch['obs'].data_ptr(), self._stream()), 'srl_learner_backward_finish')
 
     @torch.no_grad()
     def apply_gradients(self):
@@ -244,16 +259,30 @@ class B200ImpalaLearner:
         self._opt_steps = self.global_opt_step + 1
 
     def _enqueue_step(self, batch):
-        """forward_backward -> [NCCL SUM all-reduce] -> apply_gradients on the current stream"""
-        self.forward_backward(batch)
-        if self._dist:
-            self.all_reduce_gradients()
-        self.apply_gradients()
+        """forward_backward -> apply_gradients on the current stream; with world_size > 1 the fc.weight gradient is
+        all-reduced (async, NCCL stream) while the conv layers back-propagate, the small block afterwards."""
+        if not self._dist:
+            self.forward_backward(batch)
+            self.apply_gradients()
+            return
+        self._dp_step(batch, lambda: self.forward_backward_begin(batch), lambda: self.backward_finish(batch), self.apply_gradients)
+
+    def _dp_step(self, batch, begin, finish, apply):
+        dist = torch.distributed
+        fcw = self.flat_grads[self._off[6]:]
+        small = self.flat_grads[:self._off[6]]
+        begin()
+        work = dist.all_reduce(fcw, op=dist.ReduceOp.SUM, group=self.pg or None, async_op=True)
+        finish()
+        dist.all_reduce(small, op=dist.ReduceOp.SUM, group=self.pg or None)
+        work.wait()
+        apply()
 
     def _graph_step(self, batch):
         """Replay the step as CUDA graph(s) keyed by the batch buffers' addresses.  First sight of a buffer set runs
         eagerly (warm-up: sets kernel attributes, allocator state), the second captures, later calls replay.
-        With world_size > 1 the NCCL all-reduce stays outside: graph(forward_backward) -> all_reduce -> graph(apply)."""
+        With world_size > 1 the NCCL all-reduces stay outside: graph(begin) -> allreduce(fc.weight, async) ->
+        graph(finish) -> allreduce(small) -> graph(apply)."""
         key = tuple(batch[k].data_ptr() for k in ('obs', 'reward', 'done', 'action', 'policy_logits'))
         g = self._graphs.get(key)
         if g is None:
@@ -263,26 +292,23 @@ class B200ImpalaLearner:
                 return
             hp = self.hp
             self._check_batch(batch, hp.rollout_length + 1)
-            cur = torch.cuda.current_stream(self.device)
-            cur.synchronize()
+            torch.cuda.current_stream(self.device).synchronize()
             if self._dist:
-                g_fb, g_ap = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_fb):
-                    self.forward_backward(batch)
-                with torch.cuda.graph(g_ap):
+                g = tuple(torch.cuda.CUDAGraph() for _ in range(3))
+                with torch.cuda.graph(g[0]):
+                    self.forward_backward_begin(batch)
+                with torch.cuda.graph(g[1]):
+                    self.backward_finish(batch)
+                with torch.cuda.graph(g[2]):
                     self.apply_gradients()
-                g = (g_fb, g_ap)
             else:
-                g_all = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_all):
+                g = (torch.cuda.CUDAGraph(),)
+                with torch.cuda.graph(g[0]):
                     self.forward_backward(batch)
                     self.apply_gradients()
-                g = (g_all,)
             self._graphs[key] = g
-        if len(g) == 2:
-            g[0].replay()
-            self.all_reduce_gradients()
-            g[1].replay()
+        if len(g) == 3:
+            self._dp_step(batch, g[0].replay, g[1].replay, g[2].replay)
         else:
             g[0].replay()
         self._opt_steps = self.global_opt_step + 1
@@ -300,6 +326,8 @@ class B200ImpalaLearner:
         if not sync_stats:
             return {}
         host = self._stats_host
+        if self._dist:      # loss scalars are SUMs over the global batch in the reference; reduced only when somebody reads them
+            torch.distributed.all_reduce(self._losses, op=torch.distributed.ReduceOp.SUM, group=self.pg or None)
         host[:4].copy_(self._losses, non_blocking=True)
         host[4:6].copy_(self._coef, non_blocking=True)
         done = batch['done'][1:]
