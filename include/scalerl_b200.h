@@ -154,6 +154,10 @@ int srl_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  * mnmajor: D[M,N] = At[K,M]^T . Bt[K,N] (M%128==0, N%64==0) */
 int srl_test_gemm_kmajor(const void* A, const void* B, float* D, int M, int N, int K, int simt, void* stream);
 int srl_test_gemm_mnmajor(const void* At, const void* Bt, float* D, int M, int N, int K, int simt, void* stream);
+/* descriptor experiment: operand windows that start at an arbitrary 128-byte row of a SWIZZLE_128B tile.
+ * kmajor (mn_major=0): A bf16 [160,64], B bf16 [64,64]  -> D[128,64] = A[shift:shift+128] . B^T
+ * mnmajor (=1)       : A bf16 [96,128], B bf16 [96,64]  -> D[128,64] = A[shift:shift+64]^T . B[shift:shift+64]   (shift <= 32) */
+int srl_test_shifted_operand(const void* A, const void* B, float* D, int shift, int mn_major, int base_offset_mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -93,6 +93,11 @@ extern "C" int srl_test_gemm_kmajor(const void* A, const void* B, float* D, int 
   CU(test_gemm(A, B, D, M, N, K, false, simt != 0, (cudaStream_t)stream), "test_gemm_kmajor");
   return 0;
 }
+extern "C" int srl_test_shifted_operand(const void* A, const void* B, float* D, int shift, int mn_major, int base_offset_mode, void* stream) {
+  REQ(A && B && D && shift >= 0 && shift <= 32, "test_shifted_operand: bad argument");
+  CU(test_shift(A, B, D, shift, mn_major, base_offset_mode, (cudaStream_t)stream), "test_shifted_operand");
+  return 0;
+}
 extern "C" int srl_test_gemm_mnmajor(const void* At, const void* Bt, float* D, int M, int N, int K, int simt, void* stream) {
   REQ(At && Bt && D && M > 0 && N > 0 && K > 0 && M % 128 == 0 && N % 64 == 0, "test_gemm_mnmajor: need M%%128==0, N%%64==0");
   CU(test_gemm(At, Bt, D, M, N, K, true, simt != 0, (cudaStream_t)stream), "test_gemm_mnmajor");

@@ -39,25 +39,31 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __
 }
 
 // u8 NCHW frames -> space-to-depth bf16 NHWC: xs[n][Y][X][c*16+dy*4+dx] = obs[n][c][4Y+dy][4X+dx]  (exact: u8 fits bf16).
-// One block per (frame, Y): the 16 source rows (c,dy) are read coalesced (21 u32 each) into shared memory, then each
-// thread converts one u32 (4 x dx) to 4 bf16 and the block writes the 21 x 128 B output row contiguously.
+// One block per (frame, 3 consecutive Y): the 48 source rows (c,dy) are read coalesced (21 u32 each) into shared memory, then
+// each thread converts u32 (4 x dx) -> 4 bf16 and the block writes 3 x 21 x 128 B contiguously.
+constexpr int S2D_Y = 3;
 __global__ void __launch_bounds__(352) obs_s2d_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ xs) {
-  __shared__ uint32_t tile[16][21];
-  const int n = blockIdx.x / 21, Y = blockIdx.x - n * 21;
+  __shared__ uint32_t tile[S2D_Y][16][21];
+  const int n = blockIdx.x / (21 / S2D_Y), Y0 = (blockIdx.x - n * (21 / S2D_Y)) * S2D_Y;
   const int t = threadIdx.x;
   if (t < 336) {
     const int g = t / 21, X = t - g * 21;      // g = (c, dy)
-    tile[g][X] = __ldg(reinterpret_cast<const uint32_t*>(obs + (size_t)n * 28224 + (g >> 2) * 7056 + (4 * Y + (g & 3)) * 84) + X);
+    const uint8_t* src = obs + (size_t)n * 28224 + (g >> 2) * 7056 + (g & 3) * 84;
+#pragma unroll
+    for (int y = 0; y < S2D_Y; ++y) tile[y][g][X] = __ldg(reinterpret_cast<const uint32_t*>(src + (Y0 + y) * 336) + X);
   }
   __syncthreads();
   if (t < 336) {
     const int X = t >> 4, g = t & 15;
-    const uint32_t w = tile[g][X];
-    const float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - 8388608.f;
-    const float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - 8388608.f;
-    const float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388608.f;
-    const float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388608.f;
-    *reinterpret_cast<uint2*>(xs + ((size_t)blockIdx.x * 21 + X) * 64 + g * 4) = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3));
+#pragma unroll
+    for (int y = 0; y < S2D_Y; ++y) {
+      const uint32_t w = tile[y][g][X];
+      const float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - 8388608.f;
+      const float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - 8388608.f;
+      const float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388608.f;
+      const float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388608.f;
+      *reinterpret_cast<uint2*>(xs + (((size_t)n * 21 + Y0 + y) * 21 + X) * 64 + g * 4) = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3));
+    }
   }
 }
 
@@ -135,14 +141,14 @@ cudaError_t build_tma_maps(const EncoderBuffers& b, int NF, int NB, TmaMaps* M, 
   mk(&M->wfk, w + WPack::WFK, 2, {3136, 512}, {3136}, {64, 64}, "wfk");
   mk(&M->wfd, w + WPack::WFD, 2, {512, 3136}, {512}, {64, 64}, "wfd");
   mk(&M->w3d, w + WPack::W3D, 2, {576, 64}, {576}, {64, 64}, "w3d");
-  mk(&M->w2d, w + WPack::W2D, 2, {256, 128}, {256}, {64, 32}, "w2d");
+  mk(&M->w2d, w + WPack::W2D, 2, {256, 128}, {256}, {64, 128}, "w2d");
   M->valid = ok;
   if (!ok && why && !*why) *why = "cuTensorMapEncodeTiled unavailable";
   return ok ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 static cudaError_t launch_s2d(const uint8_t* obs, int frames, bf16* xs, cudaStream_t st) {
-  obs_s2d_kernel<<<frames * 21, 352, 0, st>>>(obs, xs);
+  obs_s2d_kernel<<<frames * (21 / S2D_Y), 352, 0, st>>>(obs, xs);
   return cudaGetLastError();
 }
 
@@ -215,7 +221,7 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
       TConv2Wgrad::Params q{maps.a1v, maps.da2m, g.w2, g.b2, frames, fps};
       pw.b(PS_CONV2_WGRAD); SRL_TRY(igemm_tma_launch<TConv2Wgrad>(q, dim3(cdiv(frames, fps), 5), sw)); pw.e(PS_CONV2_WGRAD); }
     { TConv2Dgrad::Params q{maps.da2v, maps.w2d, buf.a1, buf.da1, frames};
-      pf.b(PS_CONV2_DGRAD); SRL_TRY(igemm_tma_launch<TConv2Dgrad>(q, dim3(frames, 4), st)); pf.e(PS_CONV2_DGRAD); }
+      pf.b(PS_CONV2_DGRAD); SRL_TRY(igemm_tma_launch<TConv2Dgrad>(q, dim3(frames, 1), st)); pf.e(PS_CONV2_DGRAD); }
     { const int fps = cdiv(frames, 49);
       TConv1Wgrad::Params q{maps.xs4, maps.da1m, g.w1, g.b1, frames, fps};
       pf.b(PS_CONV1_WGRAD); SRL_TRY(igemm_tma_launch<TConv1Wgrad>(q, dim3(cdiv(frames, fps), 3), st)); pf.e(PS_CONV1_WGRAD); }

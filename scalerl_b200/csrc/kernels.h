@@ -92,6 +92,7 @@ cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, 
 //        bytes, ready for an early all-reduce), 1 = conv layers only, 2 = both
 cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
                              cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase);
+cudaError_t test_shift(const void* A, const void* B, float* D, int shift, int mn_major, int bo_mode, cudaStream_t st);
 cudaError_t test_gemm(const void* A, const void* B, float* D, int M, int N, int K, bool mn_major, bool simt, cudaStream_t st);
 
 }  // namespace srl

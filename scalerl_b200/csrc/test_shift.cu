@@ -1,0 +1,93 @@
+// Experiment / unit test: can a UMMA operand descriptor start at an arbitrary 128-byte ROW of a SWIZZLE_128B tile
+// (i.e. not at a 1024-byte swizzle-atom boundary)?  If yes, every filter tap of a convolution can read a shifted
+// window of ONE shared-memory copy of the input instead of a re-loaded im2col tile.
+//   kmajor : D[128 x 64] = A[shift : shift+128, 0:64] * B[64 x 64]^T         (rows = M index)
+//   mnmajor: D[128 x 64] = At[shift : shift+64, 0:128]^T * Bt[shift : shift+64, 0:64]   (rows = K index)
+// base_offset_mode: 0 -> descriptor base_offset field 0; 1 -> base_offset = (start_address >> 7) & 7
+#include "common.cuh"
+#include "kernels.h"
+
+namespace srl {
+
+__global__ void __launch_bounds__(160) shift_test_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
+                                                         float* __restrict__ D, int shift, int mn_major, int bo_mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // K-major : sA = 160 rows x 128 B ; sB = 64 rows x 128 B
+  // MN-major: sA = 2 blocks x 96 rows x 128 B ; sB = 96 rows x 128 B     (rows = contraction index, 64 + up to 32 shift)
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 32768;
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 49152);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid < 128) {
+    if (!mn_major) {
+      for (int i = tid; i < 160 * 8; i += 128) {          // A is [160][64] in global
+        const int r = i >> 3, c = i & 7;
+        *reinterpret_cast<uint4*>(sA + swz128(r, c)) = *reinterpret_cast<const uint4*>(A + r * 64 + c * 8);
+      }
+      for (int i = tid; i < 64 * 8; i += 128) {
+        const int r = i >> 3, c = i & 7;
+        *reinterpret_cast<uint4*>(sB + swz128(r, c)) = *reinterpret_cast<const uint4*>(B + r * 64 + c * 8);
+      }
+    } else {
+      for (int i = tid; i < 2 * 96 * 8; i += 128) {       // At is [96][128] in global; block b holds columns 64b..64b+63
+        const int b = i / (96 * 8), r = (i >> 3) % 96, c = i & 7;
+        *reinterpret_cast<uint4*>(sA + swz128(b * 96 + r, c)) = *reinterpret_cast<const uint4*>(A + r * 128 + b * 64 + c * 8);
+      }
+      for (int i = tid; i < 96 * 8; i += 128) {           // Bt is [96][64]
+        const int r = i >> 3, c = i & 7;
+        *reinterpret_cast<uint4*>(sB + swz128(r, c)) = *reinterpret_cast<const uint4*>(B + r * 64 + c * 8);
+      }
+    }
+    fence_proxy_async_smem();
+  }
+  if (warp == 4) {
+    if ((tid & 31) == 0) { mbar_init(done, 1); mbar_fence_init(); }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 64);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tid == 128) {
+    const uint32_t idesc = make_idesc_bf16(128, 64, mn_major, mn_major);
+    const uint32_t a0 = smem_u32(sA) + shift * 128, b0 = smem_u32(sB) + (mn_major ? shift * 128 : 0);
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t aa = a0 + (mn_major ? k * 2048 : k * 32), bb = b0 + (mn_major ? k * 2048 : k * 32);
+      uint64_t ad = mn_major ? make_smem_desc(aa, 96 * 128, 1024) : make_smem_desc(aa, 16, 1024);
+      uint64_t bd = mn_major ? make_smem_desc(bb, 96 * 128, 1024) : make_smem_desc(bb, 16, 1024);
+      if (bo_mode) {
+        ad |= (uint64_t)((aa >> 7) & 7) << 49;
+        bd |= (uint64_t)((bb >> 7) & 7) << 49;
+      }
+      umma_bf16(tmem_base, ad, bd, idesc, k != 0);
+    }
+    umma_commit(done);
+  }
+  if (tid < 128) {
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(lane_base + c0, r);
+      tmem_ld_wait();
+      for (int j = 0; j < 16; ++j) D[tid * 64 + c0 + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+}
+
+cudaError_t test_shift(const void* A, const void* B, float* D, int shift, int mn_major, int bo_mode, cudaStream_t st) {
+  const int smem = 49152 + 1024 + 256;
+  cudaError_t e = cudaFuncSetAttribute(shift_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  shift_test_kernel<<<1, 160, smem, st>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, shift, mn_major, bo_mode);
+  return cudaGetLastError();
+}
+
+}  // namespace srl

@@ -150,24 +150,26 @@ struct TConv3Dgrad {   // tile = one frame's 9x9 input grid (81 rows); tap (kh,k
   }
 };
 
-struct TConv2Dgrad {   // grid = (frames, 4 parity classes); tile = the 10x10 input pixels of one class; kb = (kh', kw')
-  static constexpr int BN = 32, STAGES = 4;
+struct TConv2Dgrad {   // grid = (frames, 1); rows = the 10x10 positions (i',j'); the four stride-parity classes share the same
+                        // A operand (da2 at (i'-kh', j'-kw')) and differ only in the weights, so they are ONE GEMM with
+                        // N = 4 classes x 32 channels = 128; column block cls goes to input pixel (2i'+ph, 2j'+pw).  kb = (kh', kw')
+  static constexpr int BN = 128, STAGES = 3;
   static constexpr bool A_MN = false, B_MN = false, ZERO_INIT = false;
   static constexpr int KROWS = 64;
   struct Params { SRL_TMAP dyv; SRL_TMAP w; const bf16* act; bf16* dx; int NB; };
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.dyv); tma_prefetch_desc(&p.w); }
   SRL_DEVINL static int num_kblocks(const Params&, int, int) { return 4; }
-  SRL_DEVINL static void issue(const Params& p, int tm, int ty, int kb, uint8_t* sA, uint8_t* sB, uint64_t* bar) {
-    mbar_arrive_expect_tx(bar, 100 * 128 + 32 * 128);
+  SRL_DEVINL static void issue(const Params& p, int tm, int, int kb, uint8_t* sA, uint8_t* sB, uint64_t* bar) {
+    mbar_arrive_expect_tx(bar, 100 * 128 + 128 * 128);
     tma_load_4d(sA, &p.dyv, bar, 0, -(kb & 1), -(kb >> 1), tm);
-    tma_load_2d(sB, &p.w, bar, kb * 64, ty * 32);
+    tma_load_2d(sB, &p.w, bar, kb * 64, 0);
   }
-  SRL_DEVINL static void epilogue16(const Params& p, int tm, int ty, int row, int c0, float (&v)[16]) {
+  SRL_DEVINL static void epilogue16(const Params& p, int tm, int, int row, int c0, float (&v)[16]) {
     if (row >= 100) return;
-    const int i = row / 10, j = row - i * 10;
-    const size_t pix = (size_t)(tm * 20 + 2 * i + (ty >> 1)) * 20 + 2 * j + (ty & 1);
-    relu_mask16(p.act + pix * 32 + c0, v);
-    store_bf16x16(p.dx + pix * 64 + c0, v);     // da1 has a 64-channel pitch (upper half stays zero)
+    const int i = row / 10, j = row - i * 10, cls = c0 >> 5, c = c0 & 31;
+    const size_t pix = (size_t)(tm * 20 + 2 * i + (cls >> 1)) * 20 + 2 * j + (cls & 1);
+    relu_mask16(p.act + pix * 32 + c, v);
+    store_bf16x16(p.dx + pix * 64 + c, v);     // da1 has a 64-channel pitch (upper half stays zero)
   }
 };
 
