@@ -13,6 +13,7 @@ the reference losses are sums over T*B (loss_fn.py:6,13,23); the 40.0 clip appli
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import OrderedDict
 from dataclasses import dataclass, asdict
 from typing import Dict, Optional
@@ -121,7 +122,7 @@ class B200ImpalaLearner:
             self._pg_adv = torch.empty(T, B, device=self.device)
             self._stats_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self.global_step = 0
-        self.use_graph = use_graph
+        self.use_graph = use_graph and not os.environ.get('SRL_NO_GRAPH')   # SRL_NO_GRAPH=1: eager launches (for ncu)
         self._graphs = {}       # batch buffer addresses -> captured CUDA graph(s) of the step
         self._seen = set()
 
