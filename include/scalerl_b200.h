@@ -71,7 +71,7 @@ typedef struct srl_config {
   int32_t A;                 /* num_actions (<= 32)                              */
   int32_t optimizer;         /* 0 = RMSprop (reference, impala_atari.py:99-105), 1 = Adam */
   int32_t reward_clip_abs_one;
-  int32_t simt_mainloop;     /* mainloop: 0 = TMA-fed tcgen05 (product path); debug: 1 = CUDA-core triage, 2 = register-gather tcgen05 */
+  int32_t simt_mainloop;     /* reserved, must be 0 (TMA-fed tcgen05 mainloop) */
   float discounting, baseline_cost, entropy_cost;
   float clip_rho_threshold, clip_pg_rho_threshold;   /* < 0: None */
   float max_grad_norm;       /* clip_grad_norm_ threshold (rl_args.py:108)       */

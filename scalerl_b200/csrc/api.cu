@@ -169,6 +169,7 @@ static int check_cfg(const srl_config_t* c) {
   REQ(c->A >= 1 && c->A <= 32, "config: A=%d must be in [1,32]", c->A);
   REQ((int64_t)(c->T + 1) * c->B <= 65536, "config: (T+1)*B=%lld frames per GPU exceeds 65536", (long long)(c->T + 1) * c->B);
   REQ(c->optimizer == 0 || c->optimizer == 1, "config: optimizer must be 0 (rmsprop) or 1 (adam)");
+  REQ(c->simt_mainloop == 0, "config: only mainloop 0 (TMA-fed tcgen05) exists; the register-gather triage modes were retired with the grid layouts");
   return 0;
 }
 
@@ -199,9 +200,9 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   sizes[k++] = al(NF * 49 * 64 * 2);    // a3
   sizes[k++] = al(NF * 512 * 4);        // h
   sizes[k++] = al(NB * 512 * 2);        // dh
-  sizes[k++] = al(NB * 49 * 64 * 2);    // da3
-  sizes[k++] = al(NB * 81 * 64 * 2);    // da2
-  sizes[k++] = al(NB * 400 * 64 * 2);   // da1 (64-channel pitch, upper half zero)
+  sizes[k++] = al(NB * 81 * 64 * 2);    // da3g (9x9 grid)
+  sizes[k++] = al(NB * 100 * 64 * 2);   // da2g (10x10 grid)
+  sizes[k++] = al(NB * 441 * 64 * 2);   // da1g (21x21 grid, 64-channel pitch, upper half zero)
   sizes[k++] = al(WPack::TOTAL * 2);    // wpack
   sizes[k++] = al(NF * A * 4);          // logits
   sizes[k++] = al(NF * 4);              // baseline
@@ -229,6 +230,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   L->buf.da2 = (__nv_bfloat16*)q; q += sizes[i++];
   L->buf.da1 = (__nv_bfloat16*)q; q += sizes[i++];
   L->buf.wpack = (__nv_bfloat16*)q; q += sizes[i++];
+  L->buf.NF = (int)NF;
   L->logits = (float*)q; q += sizes[i++];
   L->baseline = (float*)q; q += sizes[i++];
   L->dlogits = (float*)q; q += sizes[i++];
@@ -240,7 +242,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   for (int e2 = 0; e2 < 6 && L->ss.side; ++e2)
     if (cudaEventCreateWithFlags(&L->ss.ev[e2], cudaEventDisableTiming) != cudaSuccess) { L->ss.side = nullptr; }
   cudaGetLastError();
-  if (cfg->simt_mainloop == 0) {
+  {
     const char* why = nullptr;
     if (build_tma_maps(L->buf, (int)NF, (int)NB, &L->maps, &why) != cudaSuccess) {
       cudaFree(L->arena);
@@ -409,8 +411,8 @@ extern "C" int srl_learner_debug_buffer(srl_learner_t* L, const char* name, void
   struct { const char* n; void* p; int64_t c; } tab[] = {
       {"xs", L->buf.xs, NF * 441 * 64}, {"a1", L->buf.a1, NF * 400 * 32}, {"a2", L->buf.a2, NF * 81 * 64}, {"a3", L->buf.a3, NF * 49 * 64}, {"h", L->buf.h, NF * 512},
       {"logits", L->logits, NF * A}, {"baseline", L->baseline, NF}, {"dlogits", L->dlogits, NB * A}, {"dbaseline", L->dbaseline, NB},
-      {"dh", L->buf.dh, NB * 512}, {"da3", L->buf.da3, NB * 49 * 64}, {"da2", L->buf.da2, NB * 81 * 64},
-      {"da1", L->buf.da1, NB * 400 * 64}, {"wpack", L->buf.wpack, WPack::TOTAL}};
+      {"dh", L->buf.dh, NB * 512}, {"da3", L->buf.da3, NB * 81 * 64}, {"da2", L->buf.da2, NB * 100 * 64},
+      {"da1", L->buf.da1, NB * 441 * 64}, {"wpack", L->buf.wpack, WPack::TOTAL}};
   for (auto& t : tab)
     if (strcmp(t.n, name) == 0) { *ptr = t.p; *count = t.c; return 0; }
   return fail(SRL_EINVAL, "debug_buffer: unknown buffer '%s'", name);

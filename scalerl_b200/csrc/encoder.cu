@@ -1,6 +1,7 @@
 // Encoder forward / backward drivers: weight packing + the sequence of tcgen05 implicit-GEMM launches.
 #include "encoder_problems.cuh"
 #include "tma_problems.cuh"
+#include "res_problems.cuh"
 #include "kernels.h"
 #include <initializer_list>
 
@@ -109,8 +110,6 @@ static bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t*
 cudaError_t build_tma_maps(const EncoderBuffers& b, int NF, int NB, TmaMaps* M, const char** why) {
   const uint64_t nf = NF, nb = NB;
   bool ok = true;
-#define MAP(field, base, rank, ...) do { const uint64_t d_[] = __VA_ARGS__; ok = ok && make_map(&M->field, base, rank, d_, d_ + rank, reinterpret_cast<const uint32_t*>(0)); } while (0)
-#undef MAP
   auto mk = [&](CUtensorMap* m, const void* base, int rank, std::initializer_list<uint64_t> dims, std::initializer_list<uint64_t> strides,
                 std::initializer_list<uint32_t> box, const char* name) {
     if (!ok) return;
@@ -120,20 +119,24 @@ cudaError_t build_tma_maps(const EncoderBuffers& b, int NF, int NB, TmaMaps* M, 
     i = 0; for (auto v : box) bx[i++] = v;
     if (!make_map(m, base, rank, d, s, bx)) { ok = false; if (why) *why = name; }
   };
-  mk(&M->xs3, b.xs, 3, {64, 21, nf * 21}, {64, 64 * 21}, {64, 20, 6}, "xs3");
-  mk(&M->xs4, b.xs, 4, {64, 21, 21, nf}, {64, 64 * 21, 64 * 441}, {64, 20, 4, 1}, "xs4");
-  mk(&M->a1v, b.a1, 5, {64, 10, 2, 10, nf}, {64, 640, 1280, 12800}, {64, 9, 1, 9, 1}, "a1v");
-  mk(&M->a2v2, b.a2, 4, {64, 9, 9, nf}, {64, 576, 5184}, {64, 7, 7, 2}, "a2v2");
-  mk(&M->a2v1, b.a2, 4, {64, 9, 9, nf}, {64, 576, 5184}, {64, 7, 7, 1}, "a2v1");
+  auto rows = [&](CUtensorMap* m, const void* base, uint64_t nrows, uint32_t boxrows, const char* name) {
+    mk(m, base, 2, {64, nrows}, {64}, {64, boxrows}, name);
+  };
+  rows(&M->xs_w, b.xs, nf * 441, RConv1Fwd::WROWS, "xs_w");
+  rows(&M->a1p0_w, b.a1, nf * 100, RConv2Fwd::WROWS, "a1p0_w");
+  rows(&M->a1p1_w, b.a1 + (size_t)nf * 100 * 64, nf * 100, RConv2Fwd::WROWS, "a1p1_w");
+  rows(&M->a2_w, b.a2, nf * 81, RConv3Fwd::WROWS, "a2_w");
+  rows(&M->da3g_w, b.da3, nb * 81, RConv3Dgrad::WROWS, "da3g_w");
+  rows(&M->da3g_b, b.da3, nb * 81, 128, "da3g_b");
+  rows(&M->da2g_w, b.da2, nb * 100, RConv2Dgrad::WROWS, "da2g_w");
+  rows(&M->da2g_b, b.da2, nb * 100, 128, "da2g_b");
+  rows(&M->da1g_b, b.da1, nb * 441, 128, "da1g_b");
+  static_assert(RConv1Wgrad::WROWS == RConv1Fwd::WROWS && RConv2Wgrad::WROWS == RConv2Fwd::WROWS && RConv3Wgrad::WROWS == RConv3Fwd::WROWS,
+                "forward and wgrad share the window maps");
   mk(&M->a3m128, b.a3, 2, {3136, nf}, {3136}, {64, 128}, "a3m128");
   mk(&M->a3m64, b.a3, 2, {3136, nf}, {3136}, {64, 64}, "a3m64");
   mk(&M->dhm128, b.dh, 2, {512, nb}, {512}, {64, 128}, "dhm128");
   mk(&M->dhm64, b.dh, 2, {512, nb}, {512}, {64, 64}, "dhm64");
-  mk(&M->da3v, b.da3, 4, {64, 7, 7, nb}, {64, 448, 3136}, {64, 9, 9, 1}, "da3v");
-  mk(&M->da3m, b.da3, 2, {64, nb * 49}, {64}, {64, 49}, "da3m");
-  mk(&M->da2v, b.da2, 4, {64, 9, 9, nb}, {64, 576, 5184}, {64, 10, 10, 1}, "da2v");
-  mk(&M->da2m, b.da2, 2, {64, nb * 81}, {64}, {64, 81}, "da2m");
-  mk(&M->da1m, b.da1, 2, {64, nb * 400}, {64}, {64, 80}, "da1m");
   const bf16* w = b.wpack;
   mk(&M->w1k, w + WPack::W1K, 2, {256, 32}, {256}, {64, 32}, "w1k");
   mk(&M->w2k, w + WPack::W2K, 2, {512, 64}, {512}, {64, 64}, "w2k");
@@ -152,104 +155,58 @@ static cudaError_t launch_s2d(const uint8_t* obs, int frames, bf16* xs, cudaStre
   return cudaGetLastError();
 }
 
+constexpr int kPersistentCtas = 148;   // one persistent CTA per SM for the resident-window kernels
+
 cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, const TmaMaps& maps, int mode,
                             cudaStream_t st, const Profiler& pf) {
   if (frames <= 0) return cudaSuccess;
+  if (mode != 0 || !maps.valid) return cudaErrorInvalidValue;
   pf.b(PS_S2D); SRL_TRY(launch_s2d(obs, frames, buf.xs, st)); pf.e(PS_S2D);
-  if (mode == 0) {
-    if (!maps.valid) return cudaErrorInvalidValue;
-    { TConv1Fwd::Params q{maps.xs3, maps.w1k, p.b1, buf.a1, frames};
-      pf.b(PS_CONV1_FWD); SRL_TRY(igemm_tma_launch<TConv1Fwd>(q, dim3(cdiv(frames * 21, 6), 1), st)); pf.e(PS_CONV1_FWD); }
-    { TConv2Fwd::Params q{maps.a1v, maps.w2k, p.b2, buf.a2, frames};
-      pf.b(PS_CONV2_FWD); SRL_TRY(igemm_tma_launch<TConv2Fwd>(q, dim3(frames, 1), st)); pf.e(PS_CONV2_FWD); }
-    { TConv3Fwd::Params q{maps.a2v2, maps.w3k, p.b3, buf.a3, frames};
-      pf.b(PS_CONV3_FWD); SRL_TRY(igemm_tma_launch<TConv3Fwd>(q, dim3(cdiv(frames, 2), 1), st)); pf.e(PS_CONV3_FWD); }
-    { TFcFwd::Params q{maps.a3m128, maps.wfk, buf.hpart, frames};
-      static_assert(TFcFwd::SPLITS == FC_SPLITS, "split count");
-      pf.b(PS_FC_FWD); SRL_TRY(igemm_tma_launch<TFcFwd>(q, dim3(cdiv(frames, 128), 8 * FC_SPLITS), st)); pf.e(PS_FC_FWD); }
-    return cudaSuccess;
-  }
-  const bool simt = mode == 1;
-  { Conv1Fwd::Params q{buf.xs, buf.wpack + WPack::W1K, p.b1, buf.a1, frames * 400};
-    pf.b(PS_CONV1_FWD); SRL_TRY(igemm_launch<Conv1Fwd>(q, dim3(cdiv(q.M, 128), 1), st, simt)); pf.e(PS_CONV1_FWD); }
-  { Conv2Fwd::Params q{buf.a1, buf.wpack + WPack::W2K, p.b2, buf.a2, frames * 81};
-    pf.b(PS_CONV2_FWD); SRL_TRY(igemm_launch<Conv2Fwd>(q, dim3(cdiv(q.M, 128), 1), st, simt)); pf.e(PS_CONV2_FWD); }
-  { Conv3Fwd::Params q{buf.a2, buf.wpack + WPack::W3K, p.b3, buf.a3, frames * 49};
-    pf.b(PS_CONV3_FWD); SRL_TRY(igemm_launch<Conv3Fwd>(q, dim3(cdiv(q.M, 128), 1), st, simt)); pf.e(PS_CONV3_FWD); }
-  { FcFwd::Params q{buf.a3, buf.wpack + WPack::WFK, buf.hpart, frames};
-    static_assert(FcFwd::FC_SPLITS == FC_SPLITS, "split count");
-    pf.b(PS_FC_FWD); SRL_TRY(igemm_launch<FcFwd>(q, dim3(cdiv(q.M, 128), 8 * FC_SPLITS), st, simt)); pf.e(PS_FC_FWD); }
+  { RConv1Fwd::Params q{maps.xs_w, maps.w1k, p.b1, buf.a1, frames};
+    pf.b(PS_CONV1_FWD); SRL_TRY(res_fwd_launch<RConv1Fwd>(q, cdiv(frames * 441, 128), 2 * kPersistentCtas, st)); pf.e(PS_CONV1_FWD); }
+  { RConv2Fwd::Params q{maps.a1p0_w, maps.a1p1_w, maps.w2k, p.b2, buf.a2, frames};
+    pf.b(PS_CONV2_FWD); SRL_TRY(res_fwd_launch<RConv2Fwd>(q, cdiv(frames * 100, 128), kPersistentCtas, st)); pf.e(PS_CONV2_FWD); }
+  { RConv3Fwd::Params q{maps.a2_w, maps.w3k, p.b3, buf.a3, frames};
+    pf.b(PS_CONV3_FWD); SRL_TRY(res_fwd_launch<RConv3Fwd>(q, cdiv(frames * 81, 128), kPersistentCtas, st)); pf.e(PS_CONV3_FWD); }
+  { TFcFwd::Params q{maps.a3m128, maps.wfk, buf.hpart, frames};
+    static_assert(TFcFwd::SPLITS == FC_SPLITS, "split count");
+    pf.b(PS_FC_FWD); SRL_TRY(igemm_tma_launch<TFcFwd>(q, dim3(cdiv(frames, 128), 8 * FC_SPLITS), st)); pf.e(PS_FC_FWD); }
   return cudaSuccess;
-}
-
-// split the contraction range P into ~target CTAs' worth of 64-aligned pieces
-static inline void split_k(int P, int target, int* pps, int* nsplit) {
-  int per = cdiv(cdiv(P, 64), target) * 64;
-  if (per < 64) per = 64;
-  *pps = per;
-  *nsplit = cdiv(P, per);
 }
 
 cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
                              cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase) {
+  (void)obs;
   if (frames <= 0) return cudaSuccess;
+  if (mode != 0 || !maps.valid) return cudaErrorInvalidValue;
   const bool do_fc = phase != 1, do_conv = phase != 0;
-  if (mode == 0) {
-    if (!maps.valid) return cudaErrorInvalidValue;
-    // The wgrad GEMMs only feed the optimizer, so they run on a side stream beside the dgrad chain
-    // (dh -> da3 -> da2 -> da1).  With per-kernel profiling on everything stays on `st` so durations are clean.
-    const bool fork = ss.side != nullptr && !pf.on;
-    cudaStream_t sw = fork ? ss.side : st;
-    Profiler pw = pf; pw.st = sw;
-    if (do_fc) {
-      if (fork) { SRL_TRY(cudaEventRecord(ss.ev[0], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[0], 0)); }
-      { TFcWgrad::Params q{maps.dhm64, maps.a3m64, g.wf, g.bf, frames};
-        pw.b(PS_FC_WGRAD); SRL_TRY(igemm_tma_launch<TFcWgrad>(q, dim3(1, 4 * 50), sw)); pw.e(PS_FC_WGRAD); }
-      { TFcDgrad::Params q{maps.dhm128, maps.wfd, buf.a3, buf.da3, frames};
-        pf.b(PS_FC_DGRAD); SRL_TRY(igemm_tma_launch<TFcDgrad>(q, dim3(cdiv(frames, 128), 49), st)); pf.e(PS_FC_DGRAD); }
-      if (fork && !do_conv) { SRL_TRY(cudaEventRecord(ss.ev[4], sw)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[4], 0)); }
-    }
-    if (!do_conv) return cudaSuccess;
-    if (fork) { SRL_TRY(cudaEventRecord(ss.ev[1], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[1], 0)); }
-    { const int fps = cdiv(frames, 30);
-      TConv3Wgrad::Params q{maps.a2v1, maps.da3m, g.w3, g.b3, frames, fps};
-      pw.b(PS_CONV3_WGRAD); SRL_TRY(igemm_tma_launch<TConv3Wgrad>(q, dim3(cdiv(frames, fps), 5), sw)); pw.e(PS_CONV3_WGRAD); }
-    { TConv3Dgrad::Params q{maps.da3v, maps.w3d, buf.a2, buf.da2, frames};
-      pf.b(PS_CONV3_DGRAD); SRL_TRY(igemm_tma_launch<TConv3Dgrad>(q, dim3(frames, 1), st)); pf.e(PS_CONV3_DGRAD); }
-    if (fork) { SRL_TRY(cudaEventRecord(ss.ev[2], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[2], 0)); }
-    { const int fps = cdiv(frames, 30);
-      TConv2Wgrad::Params q{maps.a1v, maps.da2m, g.w2, g.b2, frames, fps};
-      pw.b(PS_CONV2_WGRAD); SRL_TRY(igemm_tma_launch<TConv2Wgrad>(q, dim3(cdiv(frames, fps), 5), sw)); pw.e(PS_CONV2_WGRAD); }
-    { TConv2Dgrad::Params q{maps.da2v, maps.w2d, buf.a1, buf.da1, frames};
-      pf.b(PS_CONV2_DGRAD); SRL_TRY(igemm_tma_launch<TConv2Dgrad>(q, dim3(frames, 1), st)); pf.e(PS_CONV2_DGRAD); }
-    { const int fps = cdiv(frames, 49);
-      TConv1Wgrad::Params q{maps.xs4, maps.da1m, g.w1, g.b1, frames, fps};
-      pf.b(PS_CONV1_WGRAD); SRL_TRY(igemm_tma_launch<TConv1Wgrad>(q, dim3(cdiv(frames, fps), 3), st)); pf.e(PS_CONV1_WGRAD); }
-    if (fork) { SRL_TRY(cudaEventRecord(ss.ev[3], sw)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[3], 0)); }
-    return cudaSuccess;
-  }
-  const bool simt = mode == 1;
-  int pps, ns;
+  // The wgrad GEMMs only feed the optimizer, so they run on a side stream beside the dgrad chain
+  // (dh -> da3 -> da2 -> da1).  With per-kernel profiling on everything stays on `st` so durations are clean.
+  const bool fork = ss.side != nullptr && !pf.on;
+  cudaStream_t sw = fork ? ss.side : st;
+  Profiler pw = pf; pw.st = sw;
   if (do_fc) {
-    { FcWgrad::Params q{buf.dh, buf.a3, g.wf, g.bf, frames};
-      pf.b(PS_FC_WGRAD); SRL_TRY(igemm_launch<FcWgrad>(q, dim3(1, 4 * 49), st, simt)); pf.e(PS_FC_WGRAD); }
-    { FcDgrad::Params q{buf.dh, buf.wpack + WPack::WFD, buf.a3, buf.da3, frames};
-      pf.b(PS_FC_DGRAD); SRL_TRY(igemm_launch<FcDgrad>(q, dim3(cdiv(frames, 128), 49), st, simt)); pf.e(PS_FC_DGRAD); }
+    if (fork) { SRL_TRY(cudaEventRecord(ss.ev[0], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[0], 0)); }
+    { TFcWgrad::Params q{maps.dhm64, maps.a3m64, g.wf, g.bf, frames};
+      pw.b(PS_FC_WGRAD); SRL_TRY(igemm_tma_launch<TFcWgrad>(q, dim3(1, 4 * 50), sw)); pw.e(PS_FC_WGRAD); }
+    { TFcDgrad::Params q{maps.dhm128, maps.wfd, buf.a3, buf.da3, frames};
+      pf.b(PS_FC_DGRAD); SRL_TRY(igemm_tma_launch<TFcDgrad>(q, dim3(cdiv(frames, 128), 49), st)); pf.e(PS_FC_DGRAD); }
+    if (fork && !do_conv) { SRL_TRY(cudaEventRecord(ss.ev[4], sw)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[4], 0)); }
   }
   if (!do_conv) return cudaSuccess;
-  { split_k(frames * 49, 29, &pps, &ns);
-    Conv3Wgrad::Params q{buf.a2, buf.da3, g.w3, g.b3, frames * 49, pps};
-    pf.b(PS_CONV3_WGRAD); SRL_TRY(igemm_launch<Conv3Wgrad>(q, dim3(ns, 5), st, simt)); pf.e(PS_CONV3_WGRAD); }
-  { Conv3Dgrad::Params q{buf.da3, buf.wpack + WPack::W3D, buf.a2, buf.da2, frames * 81};
-    pf.b(PS_CONV3_DGRAD); SRL_TRY(igemm_launch<Conv3Dgrad>(q, dim3(cdiv(q.M, 128), 1), st, simt)); pf.e(PS_CONV3_DGRAD); }
-  { split_k(frames * 81, 37, &pps, &ns);
-    Conv2Wgrad::Params q{buf.a1, buf.da2, g.w2, g.b2, frames * 81, pps};
-    pf.b(PS_CONV2_WGRAD); SRL_TRY(igemm_launch<Conv2Wgrad>(q, dim3(ns, 4), st, simt)); pf.e(PS_CONV2_WGRAD); }
-  { Conv2Dgrad::Params q{buf.da2, buf.wpack + WPack::W2D, buf.a1, buf.da1, frames * 100};
-    pf.b(PS_CONV2_DGRAD); SRL_TRY(igemm_launch<Conv2Dgrad>(q, dim3(cdiv(q.M, 128), 4), st, simt)); pf.e(PS_CONV2_DGRAD); }
-  { split_k(frames * 400, 74, &pps, &ns);
-    Conv1Wgrad::Params q{buf.xs, buf.da1, g.w1, g.b1, frames * 400, pps};
-    pf.b(PS_CONV1_WGRAD); SRL_TRY(igemm_launch<Conv1Wgrad>(q, dim3(ns, 2), st, simt)); pf.e(PS_CONV1_WGRAD); }
+  if (fork) { SRL_TRY(cudaEventRecord(ss.ev[1], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[1], 0)); }
+  { RConv3Wgrad::Params q{maps.a2_w, maps.da3g_b, g.w3, g.b3, frames * 81, 0};
+    pw.b(PS_CONV3_WGRAD); SRL_TRY(res_wgrad_launch<RConv3Wgrad>(q, kPersistentCtas, sw)); pw.e(PS_CONV3_WGRAD); }
+  { RConv3Dgrad::Params q{maps.da3g_w, maps.w3d, buf.a2, buf.da2, frames};
+    pf.b(PS_CONV3_DGRAD); SRL_TRY(res_fwd_launch<RConv3Dgrad>(q, cdiv(frames * 81, 128), kPersistentCtas, st)); pf.e(PS_CONV3_DGRAD); }
+  if (fork) { SRL_TRY(cudaEventRecord(ss.ev[2], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[2], 0)); }
+  { RConv2Wgrad::Params q{maps.a1p0_w, maps.a1p1_w, maps.da2g_b, g.w2, g.b2, frames * 100, 0};
+    pw.b(PS_CONV2_WGRAD); SRL_TRY(res_wgrad_launch<RConv2Wgrad>(q, kPersistentCtas, sw)); pw.e(PS_CONV2_WGRAD); }
+  { RConv2Dgrad::Params q{maps.da2g_w, maps.w2d, buf.a1, buf.da1, frames, buf.NF};
+    pf.b(PS_CONV2_DGRAD); SRL_TRY(res_fwd_launch<RConv2Dgrad>(q, cdiv(frames * 100, 128), kPersistentCtas, st)); pf.e(PS_CONV2_DGRAD); }
+  { RConv1Wgrad::Params q{maps.xs_w, maps.da1g_b, g.w1, g.b1, frames * 441, 0};
+    pf.b(PS_CONV1_WGRAD); SRL_TRY(res_wgrad_launch<RConv1Wgrad>(q, kPersistentCtas, st)); pf.e(PS_CONV1_WGRAD); }
+  if (fork) { SRL_TRY(cudaEventRecord(ss.ev[3], sw)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[3], 0)); }
   return cudaSuccess;
 }
 

@@ -1,0 +1,293 @@
+// "Resident window" convolution kernels on tcgen05 (sm_100a).
+//
+// Every activation tensor is stored as rows of 64 bf16 channels (128 B) on the spatial grid of the conv INPUT it
+// belongs to (frames concatenated: row = n * GRID + y * PITCH + x).  A filter tap is then a CONSTANT ROW SHIFT of the
+// whole batch, so one shared-memory window of the input (loaded once with one 2-D TMA box) serves every tap: the UMMA
+// operand descriptor of tap j simply starts  shift_j * 128 B  further into the window.  (UMMA applies SWIZZLE_128B to
+// absolute shared-memory address bits, so a descriptor may start at any 128-byte row -- verified by
+// tests/exp_shifted_operand.py / srl_test_shifted_operand.)  Compared with one im2col box per tap this divides the
+// L2->SM operand traffic by the number of taps (4 / 8 / 9) and keeps the weights stationary in shared memory.
+// Output positions are enumerated on the same grid; positions outside the valid output range are computed and
+// discarded (conv1 9 %, conv2 19 %, conv3 40 % of the MMA rows -- the MMA is not the limiter of these layers).
+//
+//   res_fwd_kernel<P>   K-major, persistent: forward convs and dgrads (dgrad = negative shifts over dY stored on the
+//                       grid of the conv input with zeros outside the valid outputs, which doubles as padding).
+//                       warp 4 = TMA producer (weights once, then one window per 128-position tile, S-deep ring),
+//                       warp 5 = MMA issuer (NT taps x 4 MMAs into one of two TMEM accumulators),
+//                       warps 0-3 = epilogue of the previous tile while the next one is being multiplied.
+//   res_wgrad_kernel<P> MN-major: dW[tap] = sum over positions X[pos + shift_tap]^T dY[pos].  One CTA owns a contiguous
+//                       range of positions, streams (window, dY) chunks of 128 positions through a ring and keeps ALL
+//                       taps' accumulators in TMEM (tap pairs form M = 128; an all-ones block yields the bias gradient).
+#pragma once
+#include "igemm_tma.cuh"
+
+namespace srl {
+
+constexpr int RES_THREADS = 192;
+constexpr int RES_MAX_TAPS = 10;
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward / dgrad
+//   P: BN, NT (taps), NWIN (input windows per tile: 1, or 2 for conv2's two row-parity planes), WROWS (rows per window,
+//      128 + max shift - min shift), SHIFT_MIN, STAGES, Params{ in[NWIN] maps, w map, ... },
+//      tap_win(j), tap_shift(j) (relative to SHIFT_MIN, i.e. >= 0), num_tiles(p), epilogue16(p, tile, row, c0, v)
+// ------------------------------------------------------------------------------------------------------------------
+template <class P>
+struct ResFwdCfg {
+  static constexpr int WIN_BYTES = ((P::WROWS * 128 + 1023) / 1024) * 1024;
+  static constexpr int IN_BYTES = P::NWIN * WIN_BYTES;
+  static constexpr int W_BYTES = P::NT * P::BN * 128;
+  static constexpr int SMEM_BYTES = W_BYTES + P::STAGES * IN_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 2 * P::BN <= 32 ? 32 : (2 * P::BN <= 64 ? 64 : (2 * P::BN <= 128 ? 128 : 256));
+  static_assert(W_BYTES % 1024 == 0, "weight block alignment");
+  static_assert(2 * P::BN <= 256, "two accumulators must fit");
+};
+
+template <class P>
+__global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_constant__ typename P::Params p) {
+  using C = ResFwdCfg<P>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;
+  uint8_t* sIn = smem + C::W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + P::STAGES * C::IN_BYTES);
+  uint64_t* in_full = bars;
+  uint64_t* in_empty = bars + P::STAGES;
+  uint64_t* acc_full = bars + 2 * P::STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* w_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int ntiles = P::num_tiles(p);
+
+  if (warp == 4) {
+    if ((tid & 31) == 0) {
+      for (int s = 0; s < P::STAGES; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+      mbar_init(w_full, 1);
+      mbar_fence_init();
+      P::prefetch(p);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if ((tid & 31) == 0) {
+      mbar_arrive_expect_tx(w_full, C::W_BYTES);
+      for (int j = 0; j < P::NT; ++j) tma_load_2d(sW + j * P::BN * 128, &p.w, w_full, j * 64, 0);
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = it % P::STAGES;
+        mbar_wait(&in_empty[s], ((it / P::STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&in_full[s], P::NWIN * P::WROWS * 128);
+        P::load_windows(p, t, sIn + s * C::IN_BYTES, C::WIN_BYTES, &in_full[s]);
+      }
+    }
+  } else if (warp == 5) {
+    if ((tid & 31) == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, P::BN, 0, 0);
+      mbar_wait(w_full, 0);
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = it % P::STAGES, b = it & 1;
+        mbar_wait(&acc_empty[b], ((it >> 1) & 1) ^ 1);       // epilogue drained this accumulator (two tiles ago)
+        mbar_wait(&in_full[s], (it / P::STAGES) & 1);
+        tc_fence_after();
+        const uint32_t in0 = smem_u32(sIn + s * C::IN_BYTES), w0 = smem_u32(sW);
+        const uint32_t acc = tmem_base + b * P::BN;
+#pragma unroll
+        for (int j = 0; j < P::NT; ++j) {
+          const uint32_t a0 = in0 + P::tap_win(j) * C::WIN_BYTES + P::tap_shift(j) * 128;
+          const uint32_t b0 = w0 + j * P::BN * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(acc, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc, (j | k) != 0);
+        }
+        umma_commit(&in_empty[s]);
+        umma_commit(&acc_full[b]);
+      }
+    }
+  } else {
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int b = it & 1;
+      mbar_wait(&acc_full[b], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16) + b * P::BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < P::BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(lane_base + c0, r);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        P::epilogue16(p, t, tid, c0, v);
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[b]);
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <class P>
+cudaError_t res_fwd_launch(const typename P::Params& p, int ntiles, int max_ctas, cudaStream_t stream) {
+  using C = ResFwdCfg<P>;
+  if (ntiles <= 0) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(res_fwd_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid = ntiles < max_ctas ? ntiles : max_ctas;
+  res_fwd_kernel<P><<<grid, RES_THREADS, C::SMEM_BYTES, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// wgrad
+//   P: NACC accumulators (each M = 128 = two 64-row blocks, N = 64), NWIN, WROWS (= 128 + max shift), STAGES,
+//      acc_win(a), acc_shift0(a), acc_shift1(a) (block 1 = -1 -> the all-ones block: bias gradient),
+//      Params{ in[NWIN] maps, dy map, P (positions), chunks_per_cta }, epilogue16(p, acc, row, c0, v)
+// ------------------------------------------------------------------------------------------------------------------
+template <class P>
+struct ResWgradCfg {
+  static constexpr int WIN_BYTES = ((P::WROWS * 128 + 1023) / 1024) * 1024;
+  static constexpr int DY_BYTES = 128 * 128;
+  static constexpr int STAGE_BYTES = P::NWIN * WIN_BYTES + DY_BYTES;
+  static constexpr int ONES_BYTES = 128 * 128;
+  static constexpr int SMEM_BYTES = ONES_BYTES + P::STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = P::NACC * 64 <= 64 ? 64 : (P::NACC * 64 <= 128 ? 128 : (P::NACC * 64 <= 256 ? 256 : 512));
+  static_assert(P::NACC * 64 <= 512, "accumulators must fit TMEM");
+};
+
+template <class P>
+__global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_constant__ typename P::Params p) {
+  using C = ResWgradCfg<P>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sSt = smem;
+  uint8_t* sOnes = smem + P::STAGES * C::STAGE_BYTES;     // after the stages: block-1 - block-0 distances stay positive
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + C::ONES_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + P::STAGES;
+  uint64_t* done = bars + 2 * P::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int nchunks_total = (p.P + 127) >> 7;
+  const int c_begin = blockIdx.x * p.chunks_per_cta;
+  const int c_end = min(nchunks_total, c_begin + p.chunks_per_cta);
+  const int nch = max(0, c_end - c_begin);
+
+  {  // all-ones block (bf16 1.0) for the bias-gradient accumulator
+    uint4* q = reinterpret_cast<uint4*>(sOnes);
+    for (int i = tid; i < C::ONES_BYTES / 16; i += RES_THREADS) q[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
+  if (warp == 4) {
+    if ((tid & 31) == 0) {
+      for (int s = 0; s < P::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      mbar_init(done, 1);
+      mbar_fence_init();
+      P::prefetch(p);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if ((tid & 31) == 0) {
+      for (int i = 0; i < nch; ++i) {
+        const int s = i % P::STAGES;
+        mbar_wait(&empty[s], ((i / P::STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], P::NWIN * P::WROWS * 128 + C::DY_BYTES);
+        uint8_t* st = sSt + s * C::STAGE_BYTES;
+        P::load_windows(p, c_begin + i, st, C::WIN_BYTES, &full[s]);
+        tma_load_2d(st + P::NWIN * C::WIN_BYTES, &p.dy, &full[s], 0, (c_begin + i) * 128);
+      }
+    }
+  } else if (warp == 5) {
+    if ((tid & 31) == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t ones = smem_u32(sOnes);
+      for (int i = 0; i < nch; ++i) {
+        const int s = i % P::STAGES;
+        mbar_wait(&full[s], (i / P::STAGES) & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(sSt + s * C::STAGE_BYTES);
+        const uint32_t dy0 = st + P::NWIN * C::WIN_BYTES;
+#pragma unroll
+        for (int a = 0; a < P::NACC; ++a) {
+          const uint32_t blk0 = st + P::acc_win(a) * C::WIN_BYTES + P::acc_shift0(a) * 128;
+          const uint32_t blk1 = P::acc_shift1(a) >= 0 ? st + P::acc_win1(a) * C::WIN_BYTES + P::acc_shift1(a) * 128 : ones;
+          const uint32_t lbo = blk1 - blk0;      // byte distance between the two 64-row M blocks (any multiple of 16)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)            // 128 positions = 8 x (K = 16)
+            umma_bf16(tmem_base + a * 64, make_smem_desc(blk0 + k * 2048, lbo, 1024), make_smem_desc(dy0 + k * 2048, 8192, 1024), idesc,
+                      (i | k) != 0);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(done);
+    }
+  } else {
+    if (nch > 0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int a = 0; a < P::NACC; ++a) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(lane_base + a * 64 + c0, r);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          P::epilogue16(p, a, tid, c0, v);
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <class P>
+cudaError_t res_wgrad_launch(typename P::Params p, int target_ctas, cudaStream_t stream) {
+  using C = ResWgradCfg<P>;
+  const int nchunks = (p.P + 127) >> 7;
+  if (nchunks <= 0) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(res_wgrad_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  p.chunks_per_cta = (nchunks + target_ctas - 1) / target_ctas;
+  const int grid = (nchunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
+  res_wgrad_kernel<P><<<grid, RES_THREADS, C::SMEM_BYTES, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace srl

@@ -67,23 +67,25 @@ struct ParamPtrs {
   float *w1, *b1, *w2, *b2, *w3, *b3, *wf, *bf, *wp, *bp, *wb, *bb;
 };
 constexpr int FC_SPLITS = 4;
-struct EncoderBuffers {
-  __nv_bfloat16* xs;                    // space-to-depth bf16 copy of the u8 frames [NF][21][21][64], 64 = (c,dy,dx)
-  __nv_bfloat16 *a1, *a2, *a3;          // NHWC activations for NF frames
+struct EncoderBuffers {   // row layouts: see res_problems.cuh
+  __nv_bfloat16* xs;                    // space-to-depth bf16 copy of the u8 frames [NF*441][64], 64 = (c,dy,dx)
+  __nv_bfloat16 *a1, *a2, *a3;          // a1 [2 planes][NF*100][64], a2 [NF*81][64], a3 [NF*49][64]
   float* hpart;                         // [FC_SPLITS][NF][512] split-K partials of the fc layer
   float* h;                             // [NF][512] fc output (post-ReLU), fp32
-  __nv_bfloat16 *dh, *da3, *da2, *da1;  // gradients w.r.t. (post-ReLU-masked) pre-activations, NB frames
+  __nv_bfloat16 *dh, *da3, *da2, *da1;  // dh [NB][512]; da3g [NB*81][64], da2g [NB*100][64], da1g [NB*441][64] (grid layouts, zero-padded)
   __nv_bfloat16* wpack;
+  int NF;                               // frames the forward buffers were sized for (plane stride of a1)
 };
-// tensor maps of the TMA mainloop (built once per learner context: every operand buffer is fixed)
+// tensor maps of the TMA kernels (built once per learner context: every operand buffer is fixed).
+// Activations are [rows][64] bf16; "w" = window box (128 + max tap shift rows), "b" = 128-row box.
 struct TmaMaps {
-  alignas(64) CUtensorMap xs3, xs4, a1v, a2v2, a2v1, a3m128, a3m64, dhm128, dhm64, da3v, da3m, da2v, da2m, da1m;
+  alignas(64) CUtensorMap xs_w, a1p0_w, a1p1_w, a2_w, da3g_w, da3g_b, da2g_w, da2g_b, da1g_b;      // conv layers (res_problems.cuh)
+  alignas(64) CUtensorMap a3m128, a3m64, dhm128, dhm64;                                            // fc layer (tma_problems.cuh)
   alignas(64) CUtensorMap w1k, w2k, w3k, wfk, wfd, w3d, w2d;
   bool valid = false;
 };
 // returns cudaSuccess or an error; `why` gets a message on failure
 cudaError_t build_tma_maps(const EncoderBuffers& buf, int NF, int NB, TmaMaps* maps, const char** why);
-// mode: 0 = TMA-fed tcgen05 (product path), 1 = CUDA-core triage (register gather), 2 = register-gather tcgen05
 cudaError_t launch_pack_weights(const ParamPtrs& p, __nv_bfloat16* wpack, cudaStream_t st);
 cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, const TmaMaps& maps, int mode,
                             cudaStream_t st, const Profiler& pf);

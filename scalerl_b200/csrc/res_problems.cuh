@@ -1,0 +1,178 @@
+// Resident-window problem definitions (see igemm_res.cuh) for conv1 / conv2 / conv3: forward, dgrad, wgrad.
+//
+// Row layouts (all bf16, 64 channels = 128 B per row, frames concatenated; "grid" = spatial grid of the conv input):
+//   xs   [NF*441]   21x21 grid of conv1 (space-to-depth frame)            channel = (c,dy,dx)
+//   a1   [2][NF*100] two row-parity planes of conv1's output, 10x10 grid of conv2: plane hp, row n*100 + (h>>1)*10 + (w>>1),
+//                   channel = (w&1)*32 + c          (a stride-2 tap of conv2 = a unit row shift inside one plane)
+//   a2   [NF*81]    9x9 grid of conv3
+//   a3   [NF*49]    dense (the fc input)
+//   da3g [NB*81]    d(conv3 out) on conv3's 9x9 grid, zeros outside the 7x7 valid outputs (those zeros ARE the padding of dgrad)
+//   da2g [NB*100]   d(conv2 out) on conv2's 10x10 grid, zeros outside 9x9
+//   da1g [NB*441]   d(conv1 out) on conv1's 21x21 grid, zeros outside 20x20, channels 32..63 zero
+#pragma once
+#include "igemm_res.cuh"
+#include "encoder_problems.cuh"
+
+namespace srl {
+
+// ================================================================================================ forward
+struct RConv1Fwd {   // 2x2 s1 over xs (== 8x8 s4 over the frame): taps (kh2,kw2) -> shifts {0, 1, 21, 22}
+  static constexpr int BN = 32, NT = 4, NWIN = 1, WROWS = 128 + 22, STAGES = 4;
+  struct Params { SRL_TMAP in0; SRL_TMAP w; const float* bias; bf16* out; int NF; };
+  SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.w); }
+  SRL_DEVINL static int num_tiles(const Params& p) { return (p.NF * 441 + 127) >> 7; }
+  SRL_DEVINL static constexpr int tap_win(int) { return 0; }
+  SRL_DEVINL static constexpr int tap_shift(int j) { return (j >> 1) * 21 + (j & 1); }
+  SRL_DEVINL static void load_windows(const Params& p, int t, uint8_t* dst, int, uint64_t* bar) { tma_load_2d(dst, &p.in0, bar, 0, t * 128); }
+  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16]) {
+    const int Q = t * 128 + row, n = Q / 441, r = Q - n * 441, oh = r / 21, ow = r - oh * 21;
+    if (n >= p.NF || oh >= 20 || ow >= 20) return;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(fmaf(v[j], 1.0f / 255.0f, __ldg(p.bias + c0 + j)), 0.f);
+    const size_t prow = (size_t)(oh & 1) * p.NF * 100 + (size_t)n * 100 + (oh >> 1) * 10 + (ow >> 1);
+    store_bf16x16(p.out + prow * 64 + (ow & 1) * 32 + c0, v);
+  }
+};
+
+struct RConv2Fwd {   // 4x4 s2 over a1: tap j = (kh, kww): plane kh&1, shift (kh>>1)*10 + kww, K-block = (kh, kw in {2kww, 2kww+1}, c)
+  static constexpr int BN = 64, NT = 8, NWIN = 2, WROWS = 128 + 11, STAGES = 3;
+  struct Params { SRL_TMAP in0; SRL_TMAP in1; SRL_TMAP w; const float* bias; bf16* out; int NF; };
+  SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.in1); tma_prefetch_desc(&p.w); }
+  SRL_DEVINL static int num_tiles(const Params& p) { return (p.NF * 100 + 127) >> 7; }
+  SRL_DEVINL static constexpr int tap_win(int j) { return (j >> 1) & 1; }
+  SRL_DEVINL static constexpr int tap_shift(int j) { return (j >> 2) * 10 + (j & 1); }
+  SRL_DEVINL static void load_windows(const Params& p, int t, uint8_t* dst, int win_bytes, uint64_t* bar) {
+    tma_load_2d(dst, &p.in0, bar, 0, t * 128);
+    tma_load_2d(dst + win_bytes, &p.in1, bar, 0, t * 128);
+  }
+  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16]) {
+    const int Q = t * 128 + row, n = Q / 100, r = Q - n * 100, oh = r / 10, ow = r - oh * 10;
+    if (n >= p.NF || oh >= 9 || ow >= 9) return;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + __ldg(p.bias + c0 + j), 0.f);
+    store_bf16x16(p.out + ((size_t)n * 81 + oh * 9 + ow) * 64 + c0, v);
+  }
+};
+
+struct RConv3Fwd {   // 3x3 s1 over a2: tap (kh,kw) -> shift kh*9 + kw
+  static constexpr int BN = 64, NT = 9, NWIN = 1, WROWS = 128 + 20, STAGES = 4;
+  struct Params { SRL_TMAP in0; SRL_TMAP w; const float* bias; bf16* out; int NF; };
+  SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.w); }
+  SRL_DEVINL static int num_tiles(const Params& p) { return (p.NF * 81 + 127) >> 7; }
+  SRL_DEVINL static constexpr int tap_win(int) { return 0; }
+  SRL_DEVINL static constexpr int tap_shift(int j) { return (j / 3) * 9 + j % 3; }
+  SRL_DEVINL static void load_windows(const Params& p, int t, uint8_t* dst, int, uint64_t* bar) { tma_load_2d(dst, &p.in0, bar, 0, t * 128); }
+  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16]) {
+    const int Q = t * 128 + row, n = Q / 81, r = Q - n * 81, oh = r / 9, ow = r - oh * 9;
+    if (n >= p.NF || oh >= 7 || ow >= 7) return;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + __ldg(p.bias + c0 + j), 0.f);
+    store_bf16x16(p.out + ((size_t)n * 49 + oh * 7 + ow) * 64 + c0, v);
+  }
+};
+
+// ================================================================================================ dgrad
+struct RConv3Dgrad {   // da2[ih,iw] = sum_{kh,kw} da3g[(ih-kh),(iw-kw)] W3[:, :, kh, kw]: shifts -(kh*9+kw); window starts 20 rows early
+  static constexpr int BN = 64, NT = 9, NWIN = 1, WROWS = 128 + 20, STAGES = 4;
+  struct Params { SRL_TMAP in0; SRL_TMAP w; const bf16* act; bf16* dx; int NB; };
+  SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.w); }
+  SRL_DEVINL static int num_tiles(const Params& p) { return (p.NB * 81 + 127) >> 7; }
+  SRL_DEVINL static constexpr int tap_win(int) { return 0; }
+  SRL_DEVINL static constexpr int tap_shift(int j) { return 20 - ((j / 3) * 9 + j % 3); }
+  SRL_DEVINL static void load_windows(const Params& p, int t, uint8_t* dst, int, uint64_t* bar) { tma_load_2d(dst, &p.in0, bar, 0, t * 128 - 20); }
+  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16]) {
+    const int Q = t * 128 + row, n = Q / 81, r = Q - n * 81, ih = r / 9, iw = r - ih * 9;
+    if (n >= p.NB) return;
+    relu_mask16(p.act + (size_t)Q * 64 + c0, v);                                   // a2 lives on the same 9x9 grid
+    store_bf16x16(p.dx + ((size_t)n * 100 + ih * 10 + iw) * 64 + c0, v);           // da2g: conv2's 10x10 grid
+  }
+};
+
+struct RConv2Dgrad {   // the 4 stride-parity classes share A (da2g at (i'-kh', j'-kw')): one N = 4 x 32 GEMM; shifts -(kh'*10 + kw')
+  static constexpr int BN = 128, NT = 4, NWIN = 1, WROWS = 128 + 11, STAGES = 3;
+  struct Params { SRL_TMAP in0; SRL_TMAP w; const bf16* act; bf16* dx; int NB; int NF; };
+  SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.w); }
+  SRL_DEVINL static int num_tiles(const Params& p) { return (p.NB * 100 + 127) >> 7; }
+  SRL_DEVINL static constexpr int tap_win(int) { return 0; }
+  SRL_DEVINL static constexpr int tap_shift(int j) { return 11 - ((j >> 1) * 10 + (j & 1)); }
+  SRL_DEVINL static void load_windows(const Params& p, int t, uint8_t* dst, int, uint64_t* bar) { tma_load_2d(dst, &p.in0, bar, 0, t * 128 - 11); }
+  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16]) {
+    const int Q = t * 128 + row, n = Q / 100, r = Q - n * 100, i = r / 10, j = r - i * 10;
+    if (n >= p.NB) return;
+    const int cls = c0 >> 5, c = c0 & 31, ph = cls >> 1, pw = cls & 1;
+    relu_mask16(p.act + ((size_t)ph * p.NF * 100 + Q) * 64 + pw * 32 + c, v);     // a1 plane ph, same row Q
+    store_bf16x16(p.dx + ((size_t)n * 441 + (2 * i + ph) * 21 + 2 * j + pw) * 64 + c, v);   // da1g: conv1's 21x21 grid
+  }
+};
+
+// ================================================================================================ wgrad
+struct RConv3Wgrad {   // acc a = taps (2a, 2a+1); acc 4 = (tap 8, ones -> db3)
+  static constexpr int NACC = 5, NWIN = 1, WROWS = 128 + 20, STAGES = 3;
+  struct Params { SRL_TMAP in0; SRL_TMAP dy; float* dw; float* db; int P; int chunks_per_cta; };
+  SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.dy); }
+  SRL_DEVINL static constexpr int sh(int tap) { return (tap / 3) * 9 + tap % 3; }
+  SRL_DEVINL static constexpr int acc_win(int) { return 0; }
+  SRL_DEVINL static constexpr int acc_win1(int) { return 0; }
+  SRL_DEVINL static constexpr int acc_shift0(int a) { return sh(2 * a); }
+  SRL_DEVINL static constexpr int acc_shift1(int a) { return a < 4 ? sh(2 * a + 1) : -1; }
+  SRL_DEVINL static void load_windows(const Params& p, int chunk, uint8_t* dst, int, uint64_t* bar) { tma_load_2d(dst, &p.in0, bar, 0, chunk * 128); }
+  SRL_DEVINL static void epilogue16(const Params& p, int a, int row, int c0, float (&v)[16]) {
+    const int tap = 2 * a + (row >> 6), c = row & 63;
+    if (tap < 9) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) atomicAdd(p.dw + ((c0 + j) * 64 + c) * 9 + tap, v[j]);
+    } else if (c == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) atomicAdd(p.db + c0 + j, v[j]);
+    }
+  }
+};
+
+struct RConv2Wgrad {   // acc a = kh (blocks kww = 0,1: rows = (kw = 2kww + wp, c)); acc 4 = (ones, ones) -> db2
+  static constexpr int NACC = 5, NWIN = 2, WROWS = 128 + 11, STAGES = 3;
+  struct Params { SRL_TMAP in0; SRL_TMAP in1; SRL_TMAP dy; float* dw; float* db; int P; int chunks_per_cta; };
+  SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.in1); tma_prefetch_desc(&p.dy); }
+  SRL_DEVINL static constexpr int acc_win(int a) { return a & 1; }
+  SRL_DEVINL static constexpr int acc_win1(int a) { return a & 1; }
+  SRL_DEVINL static constexpr int acc_shift0(int a) { return a < 4 ? (a >> 1) * 10 : 0; }
+  SRL_DEVINL static constexpr int acc_shift1(int a) { return a < 4 ? (a >> 1) * 10 + 1 : -1; }
+  SRL_DEVINL static void load_windows(const Params& p, int chunk, uint8_t* dst, int win_bytes, uint64_t* bar) {
+    tma_load_2d(dst, &p.in0, bar, 0, chunk * 128);
+    tma_load_2d(dst + win_bytes, &p.in1, bar, 0, chunk * 128);
+  }
+  SRL_DEVINL static void epilogue16(const Params& p, int a, int row, int c0, float (&v)[16]) {
+    if (a < 4) {
+      const int kw = row >> 5, c = row & 31;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) atomicAdd(p.dw + (((c0 + j) * 32 + c) * 4 + a) * 4 + kw, v[j]);
+    } else if (row == 64) {          // block 1 of the last accumulator is the all-ones block
+#pragma unroll
+      for (int j = 0; j < 16; ++j) atomicAdd(p.db + c0 + j, v[j]);
+    }
+  }
+};
+
+struct RConv1Wgrad {   // acc a = kh2 (blocks kw2 = 0,1: rows = (kw2, c, dy, dx)); acc 2 = (tap 0, ones) -> db1 (block 0 unused)
+  static constexpr int NACC = 3, NWIN = 1, WROWS = 128 + 22, STAGES = 3;
+  struct Params { SRL_TMAP in0; SRL_TMAP dy; float* dw; float* db; int P; int chunks_per_cta; };
+  SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.dy); }
+  SRL_DEVINL static constexpr int acc_win(int) { return 0; }
+  SRL_DEVINL static constexpr int acc_win1(int) { return 0; }
+  SRL_DEVINL static constexpr int acc_shift0(int a) { return a < 2 ? a * 21 : 0; }
+  SRL_DEVINL static constexpr int acc_shift1(int a) { return a < 2 ? a * 21 + 1 : -1; }
+  SRL_DEVINL static void load_windows(const Params& p, int chunk, uint8_t* dst, int, uint64_t* bar) { tma_load_2d(dst, &p.in0, bar, 0, chunk * 128); }
+  SRL_DEVINL static void epilogue16(const Params& p, int a, int row, int c0, float (&v)[16]) {
+    if (c0 >= 32) return;                    // da1g channels 32..63 are zero
+    if (a < 2) {
+      const int kw2 = row >> 6, q = row & 63, c = q >> 4, dy = (q >> 2) & 3, dx = q & 3;
+      const int k = c * 64 + (4 * a + dy) * 8 + 4 * kw2 + dx;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) atomicAdd(p.dw + (c0 + j) * 256 + k, v[j] * (1.0f / 255.0f));
+    } else if (row == 64) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) atomicAdd(p.db + c0 + j, v[j]);
+    }
+  }
+};
+
+}  // namespace srl

@@ -57,7 +57,7 @@ class ImpalaHParams:
     adam_beta1: float = 0.9
     adam_beta2: float = 0.999
     adam_eps: float = 1e-8
-    simt_mainloop: int = 0               # 0: TMA-fed tcgen05 (product path); debug: 1 CUDA-core triage, 2 register-gather tcgen05
+    simt_mainloop: int = 0               # reserved (must be 0: TMA-fed tcgen05 mainloop)
 
     def to_c(self) -> _lib.SrlConfig:
         if self.reward_clipping not in ('abs_one', 'none'):
