@@ -161,7 +161,7 @@ struct srl_learner {
 
 static const char* kSlotNames[PS_COUNT] = {"obs_s2d", "conv1_fwd", "conv2_fwd", "conv3_fwd", "fc_fwd", "head_fwd", "vtrace_loss_tail",
                                            "zero_grads", "head_bwd", "fc_wgrad", "fc_dgrad", "conv3_wgrad", "conv3_dgrad", "conv2_wgrad",
-                                           "conv2_dgrad", "conv1_wgrad", "grad_norm", "optimizer", "pack_weights"};
+                                           "conv2_dgrad", "conv1_wgrad", "conv_wgrad_finalize", "grad_norm", "optimizer", "pack_weights"};
 
 static int check_cfg(const srl_config_t* c) {
   REQ(c, "config is NULL");
@@ -211,6 +211,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   sizes[k++] = al(4096 * 4);            // scratch
   sizes[k++] = al(16);                  // coef
   sizes[k++] = al(16);                  // dstep
+  sizes[k++] = al(81920 * 4);           // conv wgrad workspace (res_problems.cuh WS_TOTAL = 81920 floats)
   int64_t total = 0;
   for (int i = 0; i < k; ++i) total += sizes[i];
   cudaError_t e = cudaMalloc(&L->arena, total);
@@ -238,6 +239,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   L->scratch = (float*)q; q += sizes[i++];
   L->coef = (float*)q; q += sizes[i++];
   L->dstep = (int*)q; q += sizes[i++];
+  L->buf.wgrad_ws = (float*)q; q += sizes[i++];
   if (cudaStreamCreateWithFlags(&L->ss.side, cudaStreamNonBlocking) != cudaSuccess) L->ss.side = nullptr;
   for (int e2 = 0; e2 < 6 && L->ss.side; ++e2)
     if (cudaEventCreateWithFlags(&L->ss.ev[e2], cudaEventDisableTiming) != cudaSuccess) { L->ss.side = nullptr; }
@@ -316,6 +318,7 @@ static int fb_begin(srl_learner* L, const uint8_t* obs, const float* reward, con
     int64_t off[12], cnt[12];
     layout(c.A, off, cnt);
     CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), st), "zero small grads");   // everything before fc.weight
+    CU(cudaMemsetAsync(L->buf.wgrad_ws, 0, 81920 * sizeof(float), st), "zero conv wgrad workspace");
   }
   L->pf.e(PS_ZERO_GRADS);
   L->pf.b(PS_HEAD_BWD);

@@ -129,6 +129,15 @@ SRL_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
 SRL_DEVINL float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 SRL_DEVINL float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
+// 16-byte vector reduction: 4 fp32 adds in one L2 atomic transaction (sm_90+)
+SRL_DEVINL void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+SRL_DEVINL void red_add_16(float* dst, const float (&v)[16], float scale = 1.0f) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) red_add_v4(dst + j, v[j] * scale, v[j + 1] * scale, v[j + 2] * scale, v[j + 3] * scale);
+}
+
 SRL_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

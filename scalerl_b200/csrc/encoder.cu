@@ -157,6 +157,22 @@ static cudaError_t launch_s2d(const uint8_t* obs, int frames, bf16* xs, cudaStre
 
 constexpr int kPersistentCtas = 148;   // one persistent CTA per SM for the resident-window kernels
 
+// workspace [tap-block][row][co] -> PyTorch-layout conv weight gradients (plain stores: these segments need no zeroing)
+__global__ void __launch_bounds__(256) conv_wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ g1, float* __restrict__ g2,
+                                                                  float* __restrict__ g3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 36864) {                       // dW3[co][c][tap] = ws3[tap>>1][(tap&1)*64 + c][co]
+    const int co = i / 576, r = i - co * 576, c = r / 9, tap = r - c * 9;
+    g3[i] = ws[WS_W3 + ((tap >> 1) * 128 + (tap & 1) * 64 + c) * 64 + co];
+  } else if (i < 36864 + 32768) {        // dW2[co][c][kh][kw] = ws2[kh][kw*32 + c][co]
+    const int e = i - 36864, co = e >> 9, r = e & 511, c = r >> 4, kh = (r >> 2) & 3, kw = r & 3;
+    g2[e] = ws[WS_W2 + (kh * 128 + kw * 32 + c) * 64 + co];
+  } else if (i < 36864 + 32768 + 8192) { // dW1[co][c][kh][kw] = ws1[kh>>2][(kw>>2)*64 + c*16 + (kh&3)*4 + (kw&3)][co] / 255
+    const int e = i - 36864 - 32768, co = e >> 8, k = e & 255, c = k >> 6, kh = (k >> 3) & 7, kw = k & 7;
+    g1[e] = ws[WS_W1 + ((kh >> 2) * 128 + (kw >> 2) * 64 + c * 16 + (kh & 3) * 4 + (kw & 3)) * 32 + co] * (1.0f / 255.0f);
+  }
+}
+
 cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, const TmaMaps& maps, int mode,
                             cudaStream_t st, const Profiler& pf) {
   if (frames <= 0) return cudaSuccess;
@@ -195,18 +211,22 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
   }
   if (!do_conv) return cudaSuccess;
   if (fork) { SRL_TRY(cudaEventRecord(ss.ev[1], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[1], 0)); }
-  { RConv3Wgrad::Params q{maps.a2_w, maps.da3g_b, g.w3, g.b3, frames * 81, 0};
-    pw.b(PS_CONV3_WGRAD); SRL_TRY(res_wgrad_launch<RConv3Wgrad>(q, kPersistentCtas, sw)); pw.e(PS_CONV3_WGRAD); }
+  { RConv3Wgrad::Params q{maps.a2_w, maps.da3g_b, buf.wgrad_ws + WS_W3, g.b3, frames * 81, 0};
+    pw.b(PS_CONV3_WGRAD); SRL_TRY(res_wgrad_launch<RConv3Wgrad>(q, 64, sw)); pw.e(PS_CONV3_WGRAD); }
   { RConv3Dgrad::Params q{maps.da3g_w, maps.w3d, buf.a2, buf.da2, frames};
     pf.b(PS_CONV3_DGRAD); SRL_TRY(res_fwd_launch<RConv3Dgrad>(q, cdiv(frames * 81, 128), kPersistentCtas, st)); pf.e(PS_CONV3_DGRAD); }
   if (fork) { SRL_TRY(cudaEventRecord(ss.ev[2], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[2], 0)); }
-  { RConv2Wgrad::Params q{maps.a1p0_w, maps.a1p1_w, maps.da2g_b, g.w2, g.b2, frames * 100, 0};
-    pw.b(PS_CONV2_WGRAD); SRL_TRY(res_wgrad_launch<RConv2Wgrad>(q, kPersistentCtas, sw)); pw.e(PS_CONV2_WGRAD); }
+  { RConv2Wgrad::Params q{maps.a1p0_w, maps.a1p1_w, maps.da2g_b, buf.wgrad_ws + WS_W2, g.b2, frames * 100, 0};
+    pw.b(PS_CONV2_WGRAD); SRL_TRY(res_wgrad_launch<RConv2Wgrad>(q, 64, sw)); pw.e(PS_CONV2_WGRAD); }
   { RConv2Dgrad::Params q{maps.da2g_w, maps.w2d, buf.a1, buf.da1, frames, buf.NF};
     pf.b(PS_CONV2_DGRAD); SRL_TRY(res_fwd_launch<RConv2Dgrad>(q, cdiv(frames * 100, 128), kPersistentCtas, st)); pf.e(PS_CONV2_DGRAD); }
-  { RConv1Wgrad::Params q{maps.xs_w, maps.da1g_b, g.w1, g.b1, frames * 441, 0};
+  { RConv1Wgrad::Params q{maps.xs_w, maps.da1g_b, buf.wgrad_ws + WS_W1, g.b1, frames * 441, 0};
     pf.b(PS_CONV1_WGRAD); SRL_TRY(res_wgrad_launch<RConv1Wgrad>(q, kPersistentCtas, st)); pf.e(PS_CONV1_WGRAD); }
   if (fork) { SRL_TRY(cudaEventRecord(ss.ev[3], sw)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[3], 0)); }
+  pf.b(PS_WGRAD_FINALIZE);
+  conv_wgrad_finalize_kernel<<<(36864 + 32768 + 8192 + 255) / 256, 256, 0, st>>>(buf.wgrad_ws, g.w1, g.w2, g.w3);
+  SRL_TRY(cudaGetLastError());
+  pf.e(PS_WGRAD_FINALIZE);
   return cudaSuccess;
 }
 

@@ -10,7 +10,7 @@ namespace srl {
 // per-kernel CUDA-event bracketing (bench.py's roofline numbers): slots of one learner step
 enum ProfSlot { PS_S2D = 0, PS_CONV1_FWD, PS_CONV2_FWD, PS_CONV3_FWD, PS_FC_FWD, PS_HEAD_FWD, PS_TAIL, PS_ZERO_GRADS, PS_HEAD_BWD,
                 PS_FC_WGRAD, PS_FC_DGRAD, PS_CONV3_WGRAD, PS_CONV3_DGRAD, PS_CONV2_WGRAD, PS_CONV2_DGRAD, PS_CONV1_WGRAD,
-                PS_GRAD_NORM, PS_OPTIMIZER, PS_PACK, PS_COUNT };
+                PS_WGRAD_FINALIZE, PS_GRAD_NORM, PS_OPTIMIZER, PS_PACK, PS_COUNT };
 struct Profiler {
   bool on = false;
   cudaEvent_t* ev = nullptr;   // 2 * PS_COUNT events
@@ -74,6 +74,7 @@ struct EncoderBuffers {   // row layouts: see res_problems.cuh
   float* h;                             // [NF][512] fc output (post-ReLU), fp32
   __nv_bfloat16 *dh, *da3, *da2, *da1;  // dh [NB][512]; da3g [NB*81][64], da2g [NB*100][64], da1g [NB*441][64] (grid layouts, zero-padded)
   __nv_bfloat16* wpack;
+  float* wgrad_ws;                      // conv weight-gradient accumulation workspace (res_problems.cuh: WS_TOTAL floats)
   int NF;                               // frames the forward buffers were sized for (plane stride of a1)
 };
 // tensor maps of the TMA kernels (built once per learner context: every operand buffer is fixed).

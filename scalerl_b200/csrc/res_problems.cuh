@@ -106,9 +106,16 @@ struct RConv2Dgrad {   // the 4 stride-parity classes share A (da2g at (i'-kh', 
 };
 
 // ================================================================================================ wgrad
-struct RConv3Wgrad {   // acc a = taps (2a, 2a+1); acc 4 = (tap 8, ones -> db3)
+// The weight-gradient accumulators are added (16-byte vector reductions) into a zeroed fp32 workspace in the
+// kernels' native [tap-block][row][co] order; conv_wgrad_finalize_kernel (encoder.cu) then writes the PyTorch-layout
+// gradient tensors.  Workspace offsets (floats):
+constexpr int WS_W3 = 0;                       // [5 acc][128 rows][64 co]   (tap 9 half unused)
+constexpr int WS_W2 = WS_W3 + 5 * 128 * 64;    // [4 kh][128 rows][64 co]
+constexpr int WS_W1 = WS_W2 + 4 * 128 * 64;    // [2 kh2][128 rows][32 co]
+constexpr int WS_TOTAL = WS_W1 + 2 * 128 * 32;
+struct RConv3Wgrad {   // acc a = taps (2a, 2a+1); acc 4 = (tap 8, ones -> db3).  ws: [10 taps][64 c][64 co] fp32 (co contiguous)
   static constexpr int NACC = 5, NWIN = 1, WROWS = 128 + 20, STAGES = 3;
-  struct Params { SRL_TMAP in0; SRL_TMAP dy; float* dw; float* db; int P; int chunks_per_cta; };
+  struct Params { SRL_TMAP in0; SRL_TMAP dy; float* ws; float* db; int P; int chunks_per_cta; };
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.dy); }
   SRL_DEVINL static constexpr int sh(int tap) { return (tap / 3) * 9 + tap % 3; }
   SRL_DEVINL static constexpr int acc_win(int) { return 0; }
@@ -119,8 +126,7 @@ struct RConv3Wgrad {   // acc a = taps (2a, 2a+1); acc 4 = (tap 8, ones -> db3)
   SRL_DEVINL static void epilogue16(const Params& p, int a, int row, int c0, float (&v)[16]) {
     const int tap = 2 * a + (row >> 6), c = row & 63;
     if (tap < 9) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) atomicAdd(p.dw + ((c0 + j) * 64 + c) * 9 + tap, v[j]);
+      red_add_16(p.ws + ((size_t)(a * 128 + row)) * 64 + c0, v);
     } else if (c == 0) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) atomicAdd(p.db + c0 + j, v[j]);
@@ -130,7 +136,7 @@ struct RConv3Wgrad {   // acc a = taps (2a, 2a+1); acc 4 = (tap 8, ones -> db3)
 
 struct RConv2Wgrad {   // acc a = kh (blocks kww = 0,1: rows = (kw = 2kww + wp, c)); acc 4 = (ones, ones) -> db2
   static constexpr int NACC = 5, NWIN = 2, WROWS = 128 + 11, STAGES = 3;
-  struct Params { SRL_TMAP in0; SRL_TMAP in1; SRL_TMAP dy; float* dw; float* db; int P; int chunks_per_cta; };
+  struct Params { SRL_TMAP in0; SRL_TMAP in1; SRL_TMAP dy; float* ws; float* db; int P; int chunks_per_cta; };   // ws: [4 kh][128 (kw,c)][64 co]
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.in1); tma_prefetch_desc(&p.dy); }
   SRL_DEVINL static constexpr int acc_win(int a) { return a & 1; }
   SRL_DEVINL static constexpr int acc_win1(int a) { return a & 1; }
@@ -142,9 +148,7 @@ struct RConv2Wgrad {   // acc a = kh (blocks kww = 0,1: rows = (kw = 2kww + wp, 
   }
   SRL_DEVINL static void epilogue16(const Params& p, int a, int row, int c0, float (&v)[16]) {
     if (a < 4) {
-      const int kw = row >> 5, c = row & 31;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) atomicAdd(p.dw + (((c0 + j) * 32 + c) * 4 + a) * 4 + kw, v[j]);
+      red_add_16(p.ws + ((size_t)(a * 128 + row)) * 64 + c0, v);
     } else if (row == 64) {          // block 1 of the last accumulator is the all-ones block
 #pragma unroll
       for (int j = 0; j < 16; ++j) atomicAdd(p.db + c0 + j, v[j]);
@@ -154,7 +158,7 @@ struct RConv2Wgrad {   // acc a = kh (blocks kww = 0,1: rows = (kw = 2kww + wp, 
 
 struct RConv1Wgrad {   // acc a = kh2 (blocks kw2 = 0,1: rows = (kw2, c, dy, dx)); acc 2 = (tap 0, ones) -> db1 (block 0 unused)
   static constexpr int NACC = 3, NWIN = 1, WROWS = 128 + 22, STAGES = 3;
-  struct Params { SRL_TMAP in0; SRL_TMAP dy; float* dw; float* db; int P; int chunks_per_cta; };
+  struct Params { SRL_TMAP in0; SRL_TMAP dy; float* ws; float* db; int P; int chunks_per_cta; };   // ws: [2 kh2][128 (kw2,c,dy,dx)][32 co]
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.dy); }
   SRL_DEVINL static constexpr int acc_win(int) { return 0; }
   SRL_DEVINL static constexpr int acc_win1(int) { return 0; }
@@ -164,10 +168,7 @@ struct RConv1Wgrad {   // acc a = kh2 (blocks kw2 = 0,1: rows = (kw2, c, dy, dx)
   SRL_DEVINL static void epilogue16(const Params& p, int a, int row, int c0, float (&v)[16]) {
     if (c0 >= 32) return;                    // da1g channels 32..63 are zero
     if (a < 2) {
-      const int kw2 = row >> 6, q = row & 63, c = q >> 4, dy = (q >> 2) & 3, dx = q & 3;
-      const int k = c * 64 + (4 * a + dy) * 8 + 4 * kw2 + dx;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) atomicAdd(p.dw + (c0 + j) * 256 + k, v[j] * (1.0f / 255.0f));
+      red_add_16(p.ws + ((size_t)(a * 128 + row)) * 32 + c0, v);
     } else if (row == 64) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) atomicAdd(p.db + c0 + j, v[j]);
