@@ -97,7 +97,7 @@ int64_t srl_learner_workspace_bytes(const srl_learner_t* L);
 /* update a hyper-parameter that does not change buffer sizes (lr, costs, clip...) */
 int srl_learner_set_config(srl_learner_t* L, const srl_config_t* cfg);
 
-/* re-derive the packed bf16 operand copies from the fp32 master parameters (call after the caller wrote params) */
+/* re-derive the packed bf16 operand copies from the fp32 master parameters now (optional: every forward does it) */
 int srl_learner_pack_weights(srl_learner_t* L, void* stream);
 
 /* AtariNet.forward for n_rows*B frames: obs u8 [rows,B,4,84,84], reward f32 [rows,B], action i64 [rows,B]
@@ -121,8 +121,9 @@ int srl_learner_forward_backward_begin(srl_learner_t* L, const uint8_t* obs, con
                                        float* losses, float* vs, float* pg_advantages, void* stream);
 int srl_learner_backward_finish(srl_learner_t* L, const uint8_t* obs, void* stream);
 
-/* clip_grad_norm_(max_grad_norm) over `grads` (after the caller's all-reduce, if any) + optimizer step +
- * weight re-pack.  grad_norm_out: f32 [2] = {total L2 norm, clip coefficient} (may be NULL). */
+/* clip_grad_norm_(max_grad_norm) over `grads` (after the caller's all-reduce, if any) + optimizer step.
+ * grad_norm_out: f32 [2] = {total L2 norm, clip coefficient} (may be NULL).  The bf16 operand copies of the weights
+ * are re-derived at the start of the next srl_learner_forward* call. */
 int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_out, void* stream);
 
 /* borrow internal activations / operand copies for tests: name in {"a1","a2","a3","h","logits","baseline",

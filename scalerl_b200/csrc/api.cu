@@ -241,7 +241,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   L->dstep = (int*)q; q += sizes[i++];
   L->buf.wgrad_ws = (float*)q; q += sizes[i++];
   if (cudaStreamCreateWithFlags(&L->ss.side, cudaStreamNonBlocking) != cudaSuccess) L->ss.side = nullptr;
-  for (int e2 = 0; e2 < 6 && L->ss.side; ++e2)
+  for (int e2 = 0; e2 < 8 && L->ss.side; ++e2)
     if (cudaEventCreateWithFlags(&L->ss.ev[e2], cudaEventDisableTiming) != cudaSuccess) { L->ss.side = nullptr; }
   cudaGetLastError();
   {
@@ -259,7 +259,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
 extern "C" int srl_learner_destroy(srl_learner_t* L) {
   if (!L) return 0;
   for (int i = 0; i < 2 * PS_COUNT; ++i) if (L->events[i]) cudaEventDestroy(L->events[i]);
-  for (int i = 0; i < 6; ++i) if (L->ss.ev[i]) cudaEventDestroy(L->ss.ev[i]);
+  for (int i = 0; i < 8; ++i) if (L->ss.ev[i]) cudaEventDestroy(L->ss.ev[i]);
   if (L->ss.side) cudaStreamDestroy(L->ss.side);
   cudaFree(L->arena);
   delete L;
@@ -286,7 +286,21 @@ extern "C" int srl_learner_pack_weights(srl_learner_t* L, void* stream) {
 static int forward_impl(srl_learner* L, const uint8_t* obs, const float* reward, const int64_t* action, int frames, float* logits,
                         float* baseline, cudaStream_t st) {
   L->pf.st = st;
-  CU(encoder_forward(obs, frames, L->P, L->buf, L->maps, L->cfg.simt_mainloop, st, L->pf), "encoder_forward");
+  // The bf16 operand copies are re-derived from the fp32 master weights at the START of every forward (not at the end
+  // of the optimizer step): the pack kernel runs on the side stream underneath the frame conversion.
+  cudaEvent_t packed = nullptr;
+  if (L->ss.side && !L->pf.on) {
+    CU(cudaEventRecord(L->ss.ev[5], st), "fork pack");
+    CU(cudaStreamWaitEvent(L->ss.side, L->ss.ev[5], 0), "fork pack");
+    CU(launch_pack_weights(L->P, L->buf.wpack, L->ss.side), "pack_weights");
+    CU(cudaEventRecord(L->ss.ev[6], L->ss.side), "join pack");
+    packed = L->ss.ev[6];
+  } else {
+    L->pf.b(PS_PACK);
+    CU(launch_pack_weights(L->P, L->buf.wpack, st), "pack_weights");
+    L->pf.e(PS_PACK);
+  }
+  CU(encoder_forward(obs, frames, L->P, L->buf, L->maps, L->cfg.simt_mainloop, st, L->pf, packed), "encoder_forward");
   L->pf.b(PS_HEAD_FWD);
   CU(launch_head_fwd(L->buf.hpart, FC_SPLITS, L->P.bf, L->buf.h, reward, action, L->P.wp, L->P.bp, L->P.wb, L->P.bb, frames, L->cfg.A,
                      logits, baseline, st), "head_fwd");
@@ -318,7 +332,6 @@ static int fb_begin(srl_learner* L, const uint8_t* obs, const float* reward, con
     int64_t off[12], cnt[12];
     layout(c.A, off, cnt);
     CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), st), "zero small grads");   // everything before fc.weight
-    CU(cudaMemsetAsync(L->buf.wgrad_ws, 0, 81920 * sizeof(float), st), "zero conv wgrad workspace");
   }
   L->pf.e(PS_ZERO_GRADS);
   L->pf.b(PS_HEAD_BWD);
@@ -372,9 +385,6 @@ extern "C" int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_ou
                    L->step, L->dstep, st), "adam");
   }
   L->pf.e(PS_OPTIMIZER);
-  L->pf.b(PS_PACK);
-  CU(launch_pack_weights(L->P, L->buf.wpack, st), "pack_weights");
-  L->pf.e(PS_PACK);
   if (grad_norm_out) CU(cudaMemcpyAsync(grad_norm_out, L->coef, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy coef");
   return 0;
 }

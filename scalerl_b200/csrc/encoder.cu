@@ -157,27 +157,31 @@ static cudaError_t launch_s2d(const uint8_t* obs, int frames, bf16* xs, cudaStre
 
 constexpr int kPersistentCtas = 148;   // one persistent CTA per SM for the resident-window kernels
 
-// workspace [tap-block][row][co] -> PyTorch-layout conv weight gradients (plain stores: these segments need no zeroing)
-__global__ void __launch_bounds__(256) conv_wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ g1, float* __restrict__ g2,
+// workspace [tap-block][row][co] -> PyTorch-layout conv weight gradients (plain stores), and re-zero what was read
+__global__ void __launch_bounds__(256) conv_wgrad_finalize_kernel(float* __restrict__ ws, float* __restrict__ g1, float* __restrict__ g2,
                                                                   float* __restrict__ g3) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 36864) {                       // dW3[co][c][tap] = ws3[tap>>1][(tap&1)*64 + c][co]
     const int co = i / 576, r = i - co * 576, c = r / 9, tap = r - c * 9;
-    g3[i] = ws[WS_W3 + ((tap >> 1) * 128 + (tap & 1) * 64 + c) * 64 + co];
+    float* q = ws + WS_W3 + ((tap >> 1) * 128 + (tap & 1) * 64 + c) * 64 + co;
+    g3[i] = *q; *q = 0.f;        // self-cleaning: the workspace is zero again for the next step
   } else if (i < 36864 + 32768) {        // dW2[co][c][kh][kw] = ws2[kh][kw*32 + c][co]
     const int e = i - 36864, co = e >> 9, r = e & 511, c = r >> 4, kh = (r >> 2) & 3, kw = r & 3;
-    g2[e] = ws[WS_W2 + (kh * 128 + kw * 32 + c) * 64 + co];
+    float* q = ws + WS_W2 + (kh * 128 + kw * 32 + c) * 64 + co;
+    g2[e] = *q; *q = 0.f;
   } else if (i < 36864 + 32768 + 8192) { // dW1[co][c][kh][kw] = ws1[kh>>2][(kw>>2)*64 + c*16 + (kh&3)*4 + (kw&3)][co] / 255
     const int e = i - 36864 - 32768, co = e >> 8, k = e & 255, c = k >> 6, kh = (k >> 3) & 7, kw = k & 7;
-    g1[e] = ws[WS_W1 + ((kh >> 2) * 128 + (kw >> 2) * 64 + c * 16 + (kh & 3) * 4 + (kw & 3)) * 32 + co] * (1.0f / 255.0f);
+    float* q = ws + WS_W1 + ((kh >> 2) * 128 + (kw >> 2) * 64 + c * 16 + (kh & 3) * 4 + (kw & 3)) * 32 + co;
+    g1[e] = *q * (1.0f / 255.0f); *q = 0.f;
   }
 }
 
 cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, const TmaMaps& maps, int mode,
-                            cudaStream_t st, const Profiler& pf) {
+                            cudaStream_t st, const Profiler& pf, cudaEvent_t wait_before_conv1) {
   if (frames <= 0) return cudaSuccess;
   if (mode != 0 || !maps.valid) return cudaErrorInvalidValue;
   pf.b(PS_S2D); SRL_TRY(launch_s2d(obs, frames, buf.xs, st)); pf.e(PS_S2D);
+  if (wait_before_conv1) SRL_TRY(cudaStreamWaitEvent(st, wait_before_conv1, 0));
   { RConv1Fwd::Params q{maps.xs_w, maps.w1k, p.b1, buf.a1, frames};
     pf.b(PS_CONV1_FWD); SRL_TRY(res_fwd_launch<RConv1Fwd>(q, cdiv(frames * 441, 128), 2 * kPersistentCtas, st)); pf.e(PS_CONV1_FWD); }
   { RConv2Fwd::Params q{maps.a1p0_w, maps.a1p1_w, maps.w2k, p.b2, buf.a2, frames};

@@ -7,40 +7,49 @@
 
 namespace srl {
 
+constexpr int HEAD_MAX_A = 32;
+
 // ------------------------------------------------------------------------------------------------
 // heads forward: one warp per frame.  core = [h(512), clamp(reward,-1,1), one_hot(action)(A)]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__ hpart, int nsplit, const float* __restrict__ bfc,
+// Block = 256 threads = 2 frames x 4 warps; warp w of a frame owns features [128w, 128w+128), 4 per lane (float4 loads).
+__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ hpart, int nsplit, const float* __restrict__ bfc,
                                                        float* __restrict__ h, const float* __restrict__ reward,
                                                        const int64_t* __restrict__ action, const float* __restrict__ Wp,
                                                        const float* __restrict__ bp, const float* __restrict__ Wb,
                                                        const float* __restrict__ bb, int N, int A, float* __restrict__ logits,
                                                        float* __restrict__ baseline) {
-  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (n >= N) return;
+  __shared__ float part[2][4][HEAD_MAX_A + 1];
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3, f = threadIdx.x >> 7;
+  const int n = blockIdx.x * 2 + f;
   const int CORE = 513 + A;
-  float x[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {     // fc epilogue: reduce the split-K partials in fixed order, + bias, ReLU (atari_model.py:100-101)
-    const int j = i * 32 + lane;
-    float s = __ldg(hpart + (size_t)n * 512 + j);
-    for (int k = 1; k < nsplit; ++k) s += __ldg(hpart + ((size_t)k * N + n) * 512 + j);
-    x[i] = fmaxf(s + __ldg(bfc + j), 0.f);
-    h[(size_t)n * 512 + j] = x[i];
-  }
-  const float r = fminf(fmaxf(__ldg(reward + n), -1.f), 1.f);
-  const int act = (int)__ldg(action + n);
-  for (int a = 0; a <= A; ++a) {
-    const float* w = a < A ? Wp + (size_t)a * CORE : Wb;
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) s = fmaf(x[i], __ldg(w + i * 32 + lane), s);
-    s = warp_sum(s);
-    if (lane == 0) {
-      s += __ldg(w + 512) * r + __ldg(w + 513 + act) + (a < A ? __ldg(bp + a) : __ldg(bb));
-      if (a < A) logits[(size_t)n * A + a] = s; else baseline[n] = s;
+  const int j = warp * 128 + lane * 4;
+  if (n < N) {
+    // fc epilogue: reduce the split-K partials in fixed order, + bias, ReLU (atari_model.py:100-101)
+    float4 x = __ldg(reinterpret_cast<const float4*>(hpart + (size_t)n * 512 + j));
+    for (int k = 1; k < nsplit; ++k) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(hpart + ((size_t)k * N + n) * 512 + j));
+      x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
     }
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bfc + j));
+    x.x = fmaxf(x.x + b4.x, 0.f); x.y = fmaxf(x.y + b4.y, 0.f); x.z = fmaxf(x.z + b4.z, 0.f); x.w = fmaxf(x.w + b4.w, 0.f);
+    *reinterpret_cast<float4*>(h + (size_t)n * 512 + j) = x;
+    for (int a = 0; a <= A; ++a) {
+      const float* w = (a < A ? Wp + (size_t)a * CORE : Wb) + j;     // rows are not 16-byte aligned (CORE is odd): scalar loads
+      float s = x.x * __ldg(w) + x.y * __ldg(w + 1) + x.z * __ldg(w + 2) + x.w * __ldg(w + 3);
+      s = warp_sum(s);
+      if (lane == 0) part[f][warp][a] = s;
+    }
+  }
+  __syncthreads();
+  if (n < N && warp == 0 && lane <= A) {
+    const int a = lane;
+    const float* w = a < A ? Wp + (size_t)a * CORE : Wb;
+    const float r = fminf(fmaxf(__ldg(reward + n), -1.f), 1.f);
+    const int act = (int)__ldg(action + n);
+    float s = (part[f][0][a] + part[f][1][a]) + (part[f][2][a] + part[f][3][a]);
+    s += __ldg(w + 512) * r + __ldg(w + 513 + act) + (a < A ? __ldg(bp + a) : __ldg(bb));
+    if (a < A) logits[(size_t)n * A + a] = s; else baseline[n] = s;
   }
 }
 
@@ -59,38 +68,47 @@ __global__ void __launch_bounds__(128) head_bwd_dh_kernel(const float* __restric
 
 // head weight/bias gradients: thread = one column j of `core` (j == CORE is the bias "ones" column),
 // blockIdx.y = slab of frames; accumulates A+1 outputs and adds them atomically into the pre-zeroed gradient.
-constexpr int HEAD_MAX_A = 32;
+constexpr int HEAD_SLAB = 16;   // frames per block
 __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ dbaseline,
                                                          const float* __restrict__ h, const float* __restrict__ reward,
                                                          const int64_t* __restrict__ action, int N, int A, int rows_per_slab,
                                                          float* __restrict__ gWp, float* __restrict__ gbp, float* __restrict__ gWb,
                                                          float* __restrict__ gbb) {
+  __shared__ float sd[HEAD_SLAB][HEAD_MAX_A + 1];
+  __shared__ float sr[HEAD_SLAB];
+  __shared__ int sa[HEAD_SLAB];
   const int j = blockIdx.x * 128 + threadIdx.x;
   const int CORE = 513 + A;
-  if (j > CORE) return;
-  const int n0 = blockIdx.y * rows_per_slab, n1 = min(N, n0 + rows_per_slab);
-  float acc[HEAD_MAX_A + 1];
-#pragma unroll
-  for (int a = 0; a <= HEAD_MAX_A; ++a) acc[a] = 0.f;
-  for (int n = n0; n < n1; ++n) {
-    float c;
-    if (j < 512) c = __ldg(h + (size_t)n * 512 + j);
-    else if (j == 512) c = fminf(fmaxf(__ldg(reward + n), -1.f), 1.f);
-    else if (j < CORE) c = ((int)__ldg(action + n) == j - 513) ? 1.f : 0.f;
-    else c = 1.f;
-    if (c != 0.f) {
-#pragma unroll
-      for (int a = 0; a < HEAD_MAX_A; ++a)
-        if (a < A) acc[a] = fmaf(__ldg(dlogits + (size_t)n * A + a), c, acc[a]);
-      acc[HEAD_MAX_A] = fmaf(__ldg(dbaseline + n), c, acc[HEAD_MAX_A]);
-    }
+  const int n0 = blockIdx.y * HEAD_SLAB, cnt = min(HEAD_SLAB, N - n0);
+  for (int i = threadIdx.x; i < cnt * (A + 1); i += 128) {
+    const int r = i / (A + 1), a = i - r * (A + 1);
+    sd[r][a] = a < A ? __ldg(dlogits + (size_t)(n0 + r) * A + a) : __ldg(dbaseline + n0 + r);
   }
+  if (threadIdx.x < cnt) {
+    sr[threadIdx.x] = fminf(fmaxf(__ldg(reward + n0 + threadIdx.x), -1.f), 1.f);
+    sa[threadIdx.x] = (int)__ldg(action + n0 + threadIdx.x);
+  }
+  __syncthreads();
+  if (j > CORE) return;
+  float c[HEAD_SLAB];
 #pragma unroll
-  for (int a = 0; a < HEAD_MAX_A; ++a)
-    if (a < A) {
-      if (j < CORE) atomicAdd(gWp + (size_t)a * CORE + j, acc[a]); else atomicAdd(gbp + a, acc[a]);
+  for (int r = 0; r < HEAD_SLAB; ++r) {       // all loads of the slab are independent: HEAD_SLAB requests in flight
+    float v = 0.f;
+    if (r < cnt) {
+      if (j < 512) v = __ldg(h + (size_t)(n0 + r) * 512 + j);
+      else if (j == 512) v = sr[r];
+      else if (j < CORE) v = (sa[r] == j - 513) ? 1.f : 0.f;
+      else v = 1.f;
     }
-  if (j < CORE) atomicAdd(gWb + j, acc[HEAD_MAX_A]); else atomicAdd(gbb, acc[HEAD_MAX_A]);
+    c[r] = v;
+  }
+  for (int a = 0; a <= A; ++a) {
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < HEAD_SLAB; ++r) acc = fmaf(sd[r][a], c[r], acc);
+    if (a < A) { if (j < CORE) atomicAdd(gWp + (size_t)a * CORE + j, acc); else atomicAdd(gbp + a, acc); }
+    else       { if (j < CORE) atomicAdd(gWb + j, acc); else atomicAdd(gbb, acc); }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -187,7 +205,7 @@ cudaError_t launch_head_fwd(const float* hpart, int nsplit, const float* bfc, fl
                             const float* Wp, const float* bp, const float* Wb, const float* bb, int N, int A, float* logits,
                             float* baseline, cudaStream_t st) {
   if (N <= 0) return cudaSuccess;
-  head_fwd_kernel<<<(N + 3) / 4, 128, 0, st>>>(hpart, nsplit, bfc, h, reward, action, Wp, bp, Wb, bb, N, A, logits, baseline);
+  head_fwd_kernel<<<(N + 1) / 2, 256, 0, st>>>(hpart, nsplit, bfc, h, reward, action, Wp, bp, Wb, bb, N, A, logits, baseline);
   return cudaGetLastError();
 }
 cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const float* h, const float* reward, const int64_t* action,
@@ -196,8 +214,8 @@ cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const 
   if (N <= 0) return cudaSuccess;
   head_bwd_dh_kernel<<<dim3(N, 4), 128, 0, st>>>(dlogits, dbaseline, h, Wp, Wb, N, A, dh);
   const int CORE = 513 + A;
-  const int slabs = 32, rps = (N + slabs - 1) / slabs;
-  head_wgrad_kernel<<<dim3((CORE + 1 + 127) / 128, slabs), 128, 0, st>>>(dlogits, dbaseline, h, reward, action, N, A, rps, gWp, gbp, gWb, gbb);
+  head_wgrad_kernel<<<dim3((CORE + 1 + 127) / 128, (N + HEAD_SLAB - 1) / HEAD_SLAB), 128, 0, st>>>(dlogits, dbaseline, h, reward, action, N, A,
+                                                                                                       HEAD_SLAB, gWp, gbp, gWb, gbb);
   return cudaGetLastError();
 }
 cudaError_t launch_grad_norm(const float* g, int64_t n, float max_norm, float* coef, float* scratch, cudaStream_t st) {

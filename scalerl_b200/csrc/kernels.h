@@ -21,7 +21,7 @@ struct Profiler {
 // second stream + fork/join events: the wgrad GEMMs run beside the dgrad chain (also under stream capture)
 struct SideStream {
   cudaStream_t side = nullptr;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // ---- vtrace.cu
@@ -88,8 +88,9 @@ struct TmaMaps {
 // returns cudaSuccess or an error; `why` gets a message on failure
 cudaError_t build_tma_maps(const EncoderBuffers& buf, int NF, int NB, TmaMaps* maps, const char** why);
 cudaError_t launch_pack_weights(const ParamPtrs& p, __nv_bfloat16* wpack, cudaStream_t st);
+// wait_before_conv1: optional event (weight re-pack running on the side stream) that conv1 must wait for
 cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, const TmaMaps& maps, int mode,
-                            cudaStream_t st, const Profiler& pf);
+                            cudaStream_t st, const Profiler& pf, cudaEvent_t wait_before_conv1);
 // backward for the first `frames` frames given buf.dh; accumulates into the (pre-zeroed) gradient tensors in `g`
 // phase: 0 = fc layer only (fc.weight / fc.bias gradients complete and joined to `st` on return: 95 % of the gradient
 //        bytes, ready for an early all-reduce), 1 = conv layers only, 2 = both
