@@ -295,13 +295,27 @@ class B200ImpalaLearner:
             self._check_batch(batch, hp.rollout_length + 1)
             torch.cuda.current_stream(self.device).synchronize()
             if self._dist:
-                g = tuple(torch.cuda.CUDAGraph() for _ in range(3))
-                with torch.cuda.graph(g[0]):
-                    self.forward_backward_begin(batch)
-                with torch.cuda.graph(g[1]):
-                    self.backward_finish(batch)
-                with torch.cuda.graph(g[2]):
-                    self.apply_gradients()
+                g = None
+                if not os.environ.get('SRL_DP_SPLIT_GRAPHS'):
+                    try:        # preferred: ONE graph with the two NCCL all-reduces captured inside it
+                        g1 = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g1):
+                            self._dp_step(batch, lambda: self.forward_backward_begin(batch), lambda: self.backward_finish(batch),
+                                          self.apply_gradients)
+                        g = (g1,)
+                    except Exception as e:     # e.g. an NCCL build that cannot be stream-captured
+                        import warnings
+                        warnings.warn(f'capturing NCCL inside the step graph failed ({e!r}); falling back to split graphs')
+                        torch.cuda.synchronize()
+                        g = None
+                if g is None:
+                    g = tuple(torch.cuda.CUDAGraph() for _ in range(3))
+                    with torch.cuda.graph(g[0]):
+                        self.forward_backward_begin(batch)
+                    with torch.cuda.graph(g[1]):
+                        self.backward_finish(batch)
+                    with torch.cuda.graph(g[2]):
+                        self.apply_gradients()
             else:
                 g = (torch.cuda.CUDAGraph(),)
                 with torch.cuda.graph(g[0]):

@@ -1,0 +1,49 @@
+"""Multi-GPU data-parallel check (run with torchrun on >= 2 GPUs; not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/dp_check.py
+
+Every rank learns on its column shard (NCCL SUM all-reduce inside the step, captured in the CUDA graph); rank 0 also runs
+a single-GPU learner on the FULL batch.  After 4 steps (eager warm-up, capture, 2 replays) the sharded weights must equal
+the full-batch weights (up to fp32 summation order) -- the property SURVEY.md §8e asks for."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import impala_oracle as O                       # noqa: E402  (checker/input generator only)
+from scalerl_b200.learner import B200ImpalaLearner, ImpalaHParams   # noqa: E402
+from scalerl_b200 import parallel as par                    # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    T, A, B = 6, 6, 4 * world
+    params = O.init_params(A, seed=11)
+    shard = B200ImpalaLearner(ImpalaHParams(rollout_length=T, batch_size=B // world, num_actions=A), init_state_dict=params)
+    full = B200ImpalaLearner(ImpalaHParams(rollout_length=T, batch_size=B, num_actions=A), init_state_dict=params, process_group=False) \
+        if rank == 0 else None
+    batch = {k: v.cuda() for k, v in O.synthetic_batch(T, B, A, seed=5, done_p=0.1).items()}
+    mine = {k: v.contiguous() for k, v in par.shard_columns(batch, rank, world).items()}
+    worst = 0.0
+    for step in range(4):
+        s = shard.learn(mine)
+        if rank == 0:
+            f = full.learn(batch)
+            rel = float((shard.flat_params - full.flat_params).norm() / full.flat_params.norm())
+            gl = float((shard.flat_grads - full.flat_grads).norm() / full.flat_grads.norm())
+            worst = max(worst, rel)
+            print(f'step {step}: total_loss shard-sum {s["total_loss"]:.5f} full {f["total_loss"]:.5f} | grad rel-L2 {gl:.2e} | '
+                  f'param rel-L2 {rel:.2e} | graphs {len(shard._graphs)} (nodes per step: {[len(g) for g in shard._graphs.values()]})', flush=True)
+    if rank == 0:
+        assert worst < 1e-4, worst
+        print('DP CHECK OK', flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
