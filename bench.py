@@ -412,8 +412,14 @@ def _main(real_stdout):
                'gpu_launches': 20 * K, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'losses_finite': losses_finite,
                'vtrace_standalone': vtrace}
         emit(real_stdout, out)
+    learner.release_graphs()
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        dist.barrier(device_ids=[local_rank])
+        # no destroy_process_group(): tearing NCCL down at interpreter exit has been seen to hang; the JSON line is out,
+        # so leave immediately (os._exit skips atexit handlers of the NCCL watchdog)
+        os.dup2(real_stdout, 1)
+        os._exit(0)
 
 
 if __name__ == '__main__':

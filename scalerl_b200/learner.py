@@ -272,12 +272,20 @@ class B200ImpalaLearner:
         dist = torch.distributed
         fcw = self.flat_grads[self._off[6]:]
         small = self.flat_grads[:self._off[6]]
+        skip = bool(os.environ.get('SRL_DP_SKIP_ALLREDUCE'))      # diagnostics only: measures the cost of the split itself
         begin()
-        work = dist.all_reduce(fcw, op=dist.ReduceOp.SUM, group=self.pg or None, async_op=True)
+        work = None if skip else dist.all_reduce(fcw, op=dist.ReduceOp.SUM, group=self.pg or None, async_op=True)
         finish()
-        dist.all_reduce(small, op=dist.ReduceOp.SUM, group=self.pg or None)
-        work.wait()
+        if not skip:
+            dist.all_reduce(small, op=dist.ReduceOp.SUM, group=self.pg or None)
+            work.wait()
         apply()
+
+    def release_graphs(self):
+        """drop the captured CUDA graphs (call before torch.distributed.destroy_process_group)"""
+        torch.cuda.synchronize(self.device)
+        self._graphs.clear()
+        self._seen.clear()
 
     def _graph_step(self, batch):
         """Replay the step as CUDA graph(s) keyed by the batch buffers' addresses.  First sight of a buffer set runs
@@ -296,8 +304,9 @@ class B200ImpalaLearner:
             torch.cuda.current_stream(self.device).synchronize()
             if self._dist:
                 g = None
-                if not os.environ.get('SRL_DP_SPLIT_GRAPHS'):
-                    try:        # preferred: ONE graph with the two NCCL all-reduces captured inside it
+                if os.environ.get('SRL_DP_SINGLE_GRAPH'):
+                    try:        # opt-in: ONE graph with the two NCCL all-reduces captured inside it (measured: no faster than split
+                                # graphs, and process-group teardown can hang while such graphs are alive -- call release_graphs() first)
                         g1 = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g1):
                             self._dp_step(batch, lambda: self.forward_backward_begin(batch), lambda: self.backward_finish(batch),

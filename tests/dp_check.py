@@ -42,7 +42,9 @@ def main():
     if rank == 0:
         assert worst < 1e-4, worst
         print('DP CHECK OK', flush=True)
-    dist.destroy_process_group()
+    shard.release_graphs()
+    dist.barrier(device_ids=[local])
+    os._exit(0)
 
 
 if __name__ == '__main__':
