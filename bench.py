@@ -350,10 +350,19 @@ def _main(real_stdout):
         ms = per_kernel_ms[slot]
         gemm[slot] = {'ms': ms, 'gflop': fl / 1e9, 'tflops': fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
     dom = max(gemm, key=lambda s: gemm[s]['ms'])
+    traffic, traffic_src, tensor_pct = None, None, None
+    tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tp) and (T, B) == (T_DEFAULT, B_DEFAULT):      # the ncu capture was taken at the default workload
+        tj = json.load(open(tp))
+        if dom in tj['kernels']:
+            traffic = tj['kernels'][dom]['dram_bytes_per_launch']
+            tensor_pct = tj['kernels'][dom]['tensor_pipe_active_pct']
+            traffic_src = tj['source']
     step_flops = NF * 18.693e6 + NBk * 30.833e6
     sum_kernel_ms = sum(per_kernel_ms.values())
     roofline = {'bound': 'tensor', 'kernel': dom, 'achieved': gemm[dom]['tflops'], 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s',
-                'frac': gemm[dom]['tflops'] / pk['bf16_tflops'], 'traffic': None, 'peak_source': pk['source'] + ' burst bf16 (MEASURED_PEAKS.json)',
+                'frac': gemm[dom]['tflops'] / pk['bf16_tflops'], 'traffic': traffic, 'traffic_unit': 'bytes (dram read+write per launch)',
+                'traffic_source': traffic_src, 'ncu_tensor_pipe_active_pct': tensor_pct, 'peak_source': pk['source'] + ' burst bf16 (MEASURED_PEAKS.json)',
                 'flops_per_launch': gemm[dom]['gflop'] * 1e9, 'ms_per_launch': gemm[dom]['ms'],
                 'how': f'CUDA events around each launch on the launch stream, mean of {nprof} steps after the timed region',
                 'step': {'gflop': step_flops / 1e9, 'tflops_device_resident': step_flops / (ms_total / K * 1e-3) / 1e12,
