@@ -359,3 +359,58 @@ def test_graph_replay_equals_eager():
         assert rel_l2(La.flat_grads.cpu(), Lb.flat_grads.cpu()) < 1e-4, step      # fp32 atomics order differs
         assert rel_l2(La.flat_params.cpu(), Lb.flat_params.cpu()) < 1e-4, step    # RMSprop normalises: near-zero grads may flip sign
     assert len(La._graphs) == 1 and len(Lb._graphs) == 0
+
+
+@pytest.mark.parametrize('mn_major', [0, 1])
+def test_shifted_operand_descriptors(mn_major):
+    """Hardware property the resident-window kernels rely on: a UMMA operand descriptor may start at ANY 128-byte row
+    of a SWIZZLE_128B tile with base_offset = 0 (the swizzle is applied to absolute shared-memory address bits)."""
+    from scalerl_b200 import _lib
+    Lb = _lib.lib()
+    g = torch.Generator().manual_seed(mn_major)
+    if mn_major == 0:
+        A = torch.randn(160, 64, generator=g).bfloat16().cuda()
+        Bm = torch.randn(64, 64, generator=g).bfloat16().cuda()
+    else:
+        A = torch.randn(96, 128, generator=g).bfloat16().cuda()
+        Bm = torch.randn(96, 64, generator=g).bfloat16().cuda()
+    for shift in range(0, 25):
+        D = torch.zeros(128, 64, device='cuda')
+        _lib.check(Lb.srl_test_shifted_operand(A.data_ptr(), Bm.data_ptr(), D.data_ptr(), shift, mn_major, 0, None))
+        torch.cuda.synchronize()
+        ref = (A[shift:shift + 128].float() @ Bm.float().t()) if mn_major == 0 else (A[shift:shift + 64].float().t() @ Bm[shift:shift + 64].float())
+        assert_close(D, ref, 1e-5, f'shift {shift}')
+
+
+def test_graft_smoke():
+    import __graft_entry__ as ge
+    ge.smoke()
+
+
+def test_full_size_cfg3_sharding_property():
+    """BASELINE.json configs[2]: T=20, B=512 sharded 8 x 64 columns.  The full-batch gradient on one GPU equals the SUM of
+    the eight shard gradients (what the NCCL SUM all-reduce computes); exercises the B=512 buffers / tensor maps."""
+    T, A, B, shards = 20, 4, 512, 8
+    full, params = _learner(T, B, A, 2)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    batch = {
+        'obs': torch.randint(0, 256, (T + 1, B, 4, 84, 84), dtype=torch.uint8, device='cuda', generator=g),
+        'reward': torch.randn(T + 1, B, device='cuda', generator=g),
+        'done': torch.rand(T + 1, B, device='cuda', generator=g) < 0.02,
+        'action': torch.randint(0, A, (T + 1, B), device='cuda', generator=g),
+        'policy_logits': torch.randn(T + 1, B, A, device='cuda', generator=g),
+        'episode_return': torch.randn(T + 1, B, device='cuda', generator=g)}
+    full.forward_backward(batch)
+    g_full = full.flat_grads.clone()
+    loss_full = full._losses.clone()
+    part, _ = _learner(T, B // shards, A, 2)
+    acc = torch.zeros_like(g_full)
+    loss_acc = torch.zeros_like(loss_full)
+    for s in range(shards):
+        sl = slice(s * 64, (s + 1) * 64)
+        part.forward_backward({k: v[:, sl].contiguous() for k, v in batch.items()})
+        acc += part.flat_grads
+        loss_acc += part._losses
+    assert rel_l2(acc.cpu(), g_full.cpu()) < 2e-4
+    assert torch.allclose(loss_acc.cpu(), loss_full.cpu(), rtol=1e-4, atol=1e-2)
+    assert torch.isfinite(g_full).all()
