@@ -142,6 +142,15 @@ int srl_learner_profile_collect(srl_learner_t* L, float* ms_out_host);
 /* asynchronous device-to-device copy on `stream` (used by tests to read the borrowed buffers) */
 int srl_memcpy_d2d(void* dst, const void* src, int64_t bytes, void* stream);
 
+/* ---- trajectory ring -> time-major batch (the stacking step of ImpalaTrainer.get_batch, impala_atari.py:248-251) -----------
+ * staging: B trajectory slots on the DEVICE, each one contiguous record of slot_bytes holding every key of create_buffers
+ * (impala_atari.py:135-147) for T+1 steps; offsets6_host (HOST array) = byte offsets of {obs u8[T+1,4,84,84], reward f32[T+1],
+ * done u8[T+1], action i64[T+1], policy_logits f32[T+1,A], episode_return f32[T+1]} inside a slot.
+ * Outputs: the time-major batch tensors [T+1,B,...] (episode_return may be NULL). */
+int srl_unpack_slots(const uint8_t* staging, int64_t slot_bytes, const int64_t* offsets6_host, int T, int B, int A,
+                     uint8_t* obs, float* reward, uint8_t* done, int64_t* action, float* policy_logits, float* episode_return,
+                     void* stream);
+
 /* ---- stand-alone optimizer ops (flat f32 buffers of n elements) ------------------------------------------
  * srl_grad_norm_clip_coef: coef[0] = ||g||_2, coef[1] = min(1, max_norm/(||g||+1e-6)); scratch f32[>=1028]. */
 int srl_grad_norm_clip_coef(const float* grads, int64_t n, float max_norm, float* coef, float* scratch, void* stream);

@@ -39,6 +39,7 @@ _SIGS = {
     'srl_learner_backward_finish': [_P, _P, _P],
     'srl_learner_apply_gradients': [_P, _P, _P],
     'srl_learner_debug_buffer': [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_L)],
+    'srl_unpack_slots': [_P, _L, C.POINTER(_L), _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     'srl_grad_norm_clip_coef': [_P, _L, _F, _P, _P, _P],
     'srl_rmsprop_step': [_P, _P, _P, _L, _P, _F, _F, _F, _P],
     'srl_adam_step': [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _I, _P],

@@ -203,6 +203,11 @@ class ImpalaTrainer:
             self._dev_batches = [{k: torch.empty(specs[k][0], dtype=specs[k][1], device=dev) for k in H2D_KEYS} for _ in range(2)]
             self._consumed = [None, None]
             self._slot = 0
+            # slot-level staging: one H2D copy per trajectory slot (all keys), then one unpack kernel
+            self._staging = [torch.empty(hp.batch_size, self.ring.slot_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+            import ctypes
+            lay = self.ring.layout
+            self._slot_off = (ctypes.c_int64 * 6)(*[lay[k][0] for k in ('obs', 'reward', 'done', 'action', 'policy_logits', 'episode_return')])
             self._publish_host = {n: torch.empty(self.learner.shapes[n], dtype=torch.float32).pin_memory() for n in PARAM_NAMES}
 
     def get_batch(self, free_queue, full_queue, buffers=None, rnn_state_buffers=None, timings=None, lock=None):
@@ -219,12 +224,24 @@ class ImpalaTrainer:
         s = self._slot
         self._slot ^= 1
         dst = self._dev_batches[s]
+        from ... import _lib
+        sb = self.ring.slot_bytes
+        hp = self.learner.hp
         with torch.cuda.stream(self._copy_stream):
             if self._consumed[s] is not None:
                 self._copy_stream.wait_event(self._consumed[s])
-            for b, m in enumerate(indices):
-                for k in H2D_KEYS:
-                    dst[k][:, b].copy_(buffers[k][m], non_blocking=True)
+            if buffers is self.buffers:       # ring slots: ONE pinned H2D copy per slot, then scatter on the device
+                stg = self._staging[s]
+                for b, m in enumerate(indices):
+                    stg[b].copy_(self.ring.block[m * sb:(m + 1) * sb], non_blocking=True)
+                _lib.check(_lib.lib().srl_unpack_slots(
+                    stg.data_ptr(), sb, self._slot_off, hp.rollout_length, hp.batch_size, hp.num_actions, dst['obs'].data_ptr(),
+                    dst['reward'].data_ptr(), dst['done'].data_ptr(), dst['action'].data_ptr(), dst['policy_logits'].data_ptr(),
+                    dst['episode_return'].data_ptr(), self._copy_stream.cuda_stream), 'srl_unpack_slots')
+            else:                             # foreign buffer dict (reference-style lists of tensors): per-key column copies
+                for b, m in enumerate(indices):
+                    for k in H2D_KEYS:
+                        dst[k][:, b].copy_(buffers[k][m], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         ev.synchronize()                           # slots are owned until their copy finished

@@ -67,6 +67,17 @@ extern "C" int srl_impala_loss_and_head_grads(const float* bl, const float* tl, 
   return 0;
 }
 
+extern "C" int srl_unpack_slots(const uint8_t* staging, int64_t slot_bytes, const int64_t* offsets6_host, int T, int B, int A, uint8_t* obs,
+                                float* reward, uint8_t* done, int64_t* action, float* policy_logits, float* episode_return, void* stream) {
+  REQ(staging && offsets6_host && obs && reward && done && action && policy_logits, "unpack_slots: NULL pointer");
+  REQ(T >= 1 && B >= 1 && A >= 1 && A <= 32 && slot_bytes > 0, "unpack_slots: bad shape");
+  REQ((slot_bytes & 15) == 0 && (offsets6_host[0] & 15) == 0 && (reinterpret_cast<uintptr_t>(staging) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(obs) & 15) == 0, "unpack_slots: obs record and buffers must be 16-byte aligned");
+  CU(launch_unpack_slots(staging, slot_bytes, offsets6_host, T, B, A, obs, reward, done, action, policy_logits, episode_return,
+                         (cudaStream_t)stream), "unpack_slots");
+  return 0;
+}
+
 extern "C" int srl_grad_norm_clip_coef(const float* grads, int64_t n, float max_norm, float* coef, float* scratch, void* stream) {
   REQ(grads && coef && scratch && n >= 0, "grad_norm: bad argument");
   REQ((reinterpret_cast<uintptr_t>(grads) & 15) == 0, "grad_norm: grads must be 16-byte aligned");

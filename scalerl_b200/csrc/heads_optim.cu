@@ -201,6 +201,38 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// trajectory-slot unpack: B slots (one contiguous record per actor rollout, all keys of create_buffers,
+// impala_atari.py:135-147) copied host->device as they lie, then scattered into the time-major [T+1, B, ...] batch.
+// grid = (T+1, B): one block moves one 28,224-byte frame with 16-byte vectors; thread 0 moves the scalars.
+// ------------------------------------------------------------------------------------------------
+struct SlotOffsets { int64_t obs, reward, done, action, policy_logits, episode_return; };
+__global__ void __launch_bounds__(256) unpack_slots_kernel(const uint8_t* __restrict__ staging, int64_t slot_bytes, SlotOffsets o, int B, int A,
+                                                           uint8_t* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
+                                                           int64_t* __restrict__ action, float* __restrict__ logits,
+                                                           float* __restrict__ episode_return) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  const uint8_t* slot = staging + (size_t)b * slot_bytes;
+  const uint4* src = reinterpret_cast<const uint4*>(slot + o.obs + (size_t)t * 28224);
+  uint4* dst = reinterpret_cast<uint4*>(obs + ((size_t)t * B + b) * 28224);
+  for (int i = threadIdx.x; i < 1764; i += 256) dst[i] = __ldg(src + i);
+  const size_t n = (size_t)t * B + b;
+  if (threadIdx.x == 0) {
+    reward[n] = reinterpret_cast<const float*>(slot + o.reward)[t];
+    done[n] = (slot + o.done)[t];
+    action[n] = reinterpret_cast<const int64_t*>(slot + o.action)[t];
+    if (episode_return) episode_return[n] = reinterpret_cast<const float*>(slot + o.episode_return)[t];
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + A) logits[n * A + threadIdx.x - 32] = reinterpret_cast<const float*>(slot + o.policy_logits)[t * A + threadIdx.x - 32];
+}
+
+cudaError_t launch_unpack_slots(const uint8_t* staging, int64_t slot_bytes, const int64_t* off6, int T, int B, int A, uint8_t* obs, float* reward,
+                                uint8_t* done, int64_t* action, float* logits, float* episode_return, cudaStream_t st) {
+  SlotOffsets o{off6[0], off6[1], off6[2], off6[3], off6[4], off6[5]};
+  unpack_slots_kernel<<<dim3(T + 1, B), 256, 0, st>>>(staging, slot_bytes, o, B, A, obs, reward, done, action, logits, episode_return);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 cudaError_t launch_head_fwd(const float* hpart, int nsplit, const float* bfc, float* h, const float* reward, const int64_t* action,
                             const float* Wp, const float* bp, const float* Wb, const float* bb, int N, int A, float* logits,
                             float* baseline, cudaStream_t st) {

@@ -56,3 +56,30 @@ def test_train_short_run_on_gpu(tmp_path):
     assert set(ck) == {'model_state_dict', 'optimizer_state_dict', 'hparam'}   # impala_atari.py:506-511
     assert set(ck['model_state_dict']) == {'conv1.weight', 'conv1.bias', 'conv2.weight', 'conv2.bias', 'conv3.weight', 'conv3.bias',
                                            'fc.weight', 'fc.bias', 'policy.weight', 'policy.bias', 'baseline.weight', 'baseline.bias'}
+
+
+@pytest.mark.gpu
+def test_get_batch_slot_unpack_matches_stack(tmp_path):
+    """get_batch (one H2D copy per slot + srl_unpack_slots) == the reference's torch.stack(dim=1) of the slot tensors"""
+    a = ImpalaArguments(num_actors=1, batch_size=3, rollout_length=4, num_buffers=5, output_dir=str(tmp_path), num_actions=6)
+    t = ImpalaTrainer(a)
+    g = torch.Generator().manual_seed(0)
+    for m in range(a.num_buffers):
+        t.buffers['obs'][m].copy_(torch.randint(0, 256, t.buffers['obs'][m].shape, dtype=torch.uint8, generator=g))
+        t.buffers['reward'][m].copy_(torch.randn(t.buffers['reward'][m].shape, generator=g))
+        t.buffers['done'][m].copy_(torch.rand(t.buffers['done'][m].shape, generator=g) < 0.3)
+        t.buffers['action'][m].copy_(torch.randint(0, 6, t.buffers['action'][m].shape, generator=g))
+        t.buffers['policy_logits'][m].copy_(torch.randn(t.buffers['policy_logits'][m].shape, generator=g))
+        t.buffers['episode_return'][m].copy_(torch.randn(t.buffers['episode_return'][m].shape, generator=g))
+    ctx = torch.multiprocessing.get_context('fork')
+    free_q, full_q = ctx.SimpleQueue(), ctx.SimpleQueue()
+    order = [4, 0, 2]
+    for m in order:
+        full_q.put(m)
+    batch, state = t.get_batch(free_q, full_q)
+    torch.cuda.synchronize()
+    for k in ('obs', 'reward', 'done', 'action', 'policy_logits', 'episode_return'):
+        want = torch.stack([t.buffers[k][m] for m in order], dim=1)          # impala_atari.py:248-251
+        assert torch.equal(batch[k].cpu(), want), k
+    assert sorted(free_q.get() for _ in range(3)) == sorted(order)            # slots released after their copy
+    assert state == tuple()
