@@ -388,6 +388,93 @@ def learn_step(params: Dict[str, torch.Tensor], opt_state: Dict[str, Dict[str, t
         return out
 
 
+# --------------------------------------------------------------------------------------------
+# LSTM core (atari_model.py:52-55,61-75,109-120; use_lstm=True): 2-layer nn.LSTM(H, H), H = 513 + A,
+# stepped one time step at a time with the state multiplied by (1 - done_t) BEFORE each step.
+# --------------------------------------------------------------------------------------------
+LSTM_PARAM_ORDER = tuple(f'rnn_layer.{w}_l{l}' for l in (0, 1) for w in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh'))
+
+
+def init_lstm_params(num_actions: int, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """numpy init with nn.LSTM's default distribution U(-1/sqrt(H), 1/sqrt(H)); names = nn.LSTM state_dict keys"""
+    H = 513 + num_actions
+    rng = np.random.RandomState(7000 + seed)
+    k = 1.0 / math.sqrt(H)
+    out = {}
+    for name in LSTM_PARAM_ORDER:
+        shp = (4 * H, H) if 'weight' in name else (4 * H,)
+        out[name] = torch.from_numpy(rng.uniform(-k, k, size=shp).astype(np.float32))
+    return out
+
+
+def lstm_core_forward(lp: Dict[str, torch.Tensor], core: torch.Tensor, done: torch.Tensor, state):
+    """core [T1,B,H], done bool [T1,B], state = (h [2,B,H], c [2,B,H]) -> (out [T1,B,H], new state).
+    Gate order i,f,g,o (torch.nn.LSTM); atari_model.py:113-119 resets the state with notdone before every step."""
+    T1, B, H = core.shape
+    h = [state[0][0], state[0][1]]
+    c = [state[1][0], state[1][1]]
+    outs = []
+    notdone = (~done).float()
+    for t in range(T1):
+        m = notdone[t].view(B, 1)
+        x = core[t]
+        for l in range(2):
+            hp, cp = h[l] * m, c[l] * m
+            g = F.linear(x, lp[f'rnn_layer.weight_ih_l{l}'], lp[f'rnn_layer.bias_ih_l{l}']) + \
+                F.linear(hp, lp[f'rnn_layer.weight_hh_l{l}'], lp[f'rnn_layer.bias_hh_l{l}'])
+            i, f, gg, o = g.chunk(4, dim=1)
+            c[l] = torch.sigmoid(f) * cp + torch.sigmoid(i) * torch.tanh(gg)
+            h[l] = torch.sigmoid(o) * torch.tanh(c[l])
+            x = h[l]
+        outs.append(x)
+    return torch.stack(outs), (torch.stack(h), torch.stack(c))
+
+
+def atari_forward_lstm(params, lp, obs, reward, action, done, state):
+    """AtariNet.forward with use_lstm=True (fp32): conv encoder -> core -> 2-layer LSTM -> heads on the LSTM output"""
+    T1, B = obs.shape[:2]
+    N = T1 * B
+    x = obs.reshape(N, *obs.shape[2:]).float() / 255.0
+    a1 = F.relu(F.conv2d(x, params['conv1.weight'], params['conv1.bias'], stride=4))
+    a2 = F.relu(F.conv2d(a1, params['conv2.weight'], params['conv2.bias'], stride=2))
+    a3 = F.relu(F.conv2d(a2, params['conv3.weight'], params['conv3.bias'], stride=1))
+    hfc = F.relu(F.linear(a3.reshape(N, -1), params['fc.weight'], params['fc.bias']))
+    A = params['policy.weight'].shape[0]
+    core = torch.cat([hfc, torch.clamp(reward, -1, 1).reshape(N, 1), F.one_hot(action.reshape(N), A).float()], dim=-1)
+    out, new_state = lstm_core_forward(lp, core.view(T1, B, -1), done, state)
+    flat = out.reshape(N, -1)
+    logits = F.linear(flat, params['policy.weight'], params['policy.bias'])
+    baseline = F.linear(flat, params['baseline.weight'], params['baseline.bias'])
+    return logits.view(T1, B, A), baseline.view(T1, B), new_state
+
+
+def learn_step_lstm(params, lp, batch, state, hp: Optional[dict] = None):
+    """impala_atari.py:288-346 with use_lstm=True, fp32 autograd; returns losses, logits, vs and the gradients of BOTH
+    parameter dicts (no optimizer update -- the update rule is layout-agnostic and tested separately)."""
+    h = dict(DEFAULT_HP)
+    if hp:
+        h.update(hp)
+    ps = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    ls = {k: v.detach().clone().requires_grad_(True) for k, v in lp.items()}
+    logits, baseline, _ = atari_forward_lstm(ps, ls, batch['obs'], batch['reward'], batch['action'], batch['done'], state)
+    bootstrap_value = baseline[-1].detach()
+    tl, tv = logits[:-1], baseline[:-1]
+    rewards = batch['reward'][1:]
+    if h['reward_clipping'] == 'abs_one':
+        rewards = torch.clamp(rewards, -1, 1)
+    discounts = (~batch['done'][1:]).float() * h['discounting']
+    actions = batch['action'][1:]
+    with torch.no_grad():
+        vs, pg_adv, *_ = vtrace_from_logits(batch['policy_logits'][1:], tl.detach(), actions, discounts, rewards, tv.detach(),
+                                            bootstrap_value, h['clip_rho_threshold'], h['clip_pg_rho_threshold'])
+    pg_loss, baseline_loss, entropy_loss = impala_losses(tl, actions, tv, vs, pg_adv, h['baseline_cost'], h['entropy_cost'])
+    total = pg_loss + baseline_loss + entropy_loss
+    total.backward()
+    return dict(policy_logits=logits.detach(), baseline=baseline.detach(), vs=vs, pg_advantages=pg_adv,
+                pg_loss=float(pg_loss), baseline_loss=float(baseline_loss), entropy_loss=float(entropy_loss), total_loss=float(total),
+                grads={k: v.grad.detach().clone() for k, v in ps.items()}, lstm_grads={k: v.grad.detach().clone() for k, v in ls.items()})
+
+
 def new_opt_state(params, optimizer='rmsprop'):
     z = lambda: {k: torch.zeros_like(v) for k, v in params.items()}
     if optimizer == 'rmsprop':

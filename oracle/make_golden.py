@@ -124,6 +124,39 @@ def main():
         np.savez_compressed(os.path.join(out_dir, f"learn_{c['name']}.npz"), **g)
         print('wrote', c['name'], 'total_loss', float(total_loss))
 
+    # ---------------- LSTM core through the reference AtariNet(use_lstm=True) (atari_model.py:52-55,109-120) ----------------
+    T, B, A = 4, 3, 6
+    params = O.init_params(A, seed=2)
+    lp = O.init_lstm_params(A, seed=2)
+    model = atari_model.AtariNet((4, 84, 84), A, use_lstm=True)
+    model.load_state_dict({**params, **lp})
+    model.train()
+    batch = O.synthetic_batch(T, B, A, seed=42, done_p=0.25)
+    rng = np.random.RandomState(5)
+    state = (torch.from_numpy(rng.randn(2, B, 513 + A).astype(np.float32) * 0.3), torch.from_numpy(rng.randn(2, B, 513 + A).astype(np.float32) * 0.3))
+    torch.manual_seed(0)
+    out, new_state = model(batch, state)
+    baseline = out['baseline']
+    tl, tv = out['policy_logits'][:-1], baseline[:-1]
+    b1 = {k: t[1:] for k, t in batch.items()}
+    discounts = (~b1['done']).float() * 0.99
+    vr = vtrace.from_logits(behavior_policy_logits=b1['policy_logits'], target_policy_logits=tl, actions=b1['action'], discounts=discounts,
+                            rewards=torch.clamp(b1['reward'], -1, 1), values=tv, bootstrap_value=baseline[-1])
+    total = (loss_fn.compute_policy_gradient_loss(tl, b1['action'], vr.pg_advantages) + 0.5 * loss_fn.compute_baseline_loss(vr.vs - tv) +
+             0.0006 * loss_fn.compute_entropy_loss(tl))
+    model.zero_grad()
+    total.backward()
+    g = {'policy_logits': out['policy_logits'].detach().numpy(), 'baseline': baseline.detach().numpy(), 'vs': vr.vs.numpy(),
+         'h_out': new_state[0].detach().numpy(), 'c_out': new_state[1].detach().numpy(), 'total_loss': np.array([total.item()]),
+         'state_h': state[0].numpy(), 'state_c': state[1].numpy(), 'meta': np.array([T, B, A, 2, 42])}
+    for k, p_ in model.named_parameters():
+        flat = p_.grad.detach().reshape(-1)
+        idx = torch.linspace(0, flat.numel() - 1, steps=min(257, flat.numel())).long()
+        g['gradsamp_' + k] = flat[idx].numpy().copy()
+        g['gradnorm_' + k] = np.array([float(flat.double().norm())])
+    np.savez_compressed(os.path.join(out_dir, 'lstm_t4b3a6.npz'), **g)
+    print('wrote lstm_t4b3a6 total_loss', total.item())
+
 
 if __name__ == '__main__':
     main()

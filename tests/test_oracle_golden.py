@@ -114,3 +114,25 @@ def test_adam_step_matches_torch():
         O.adam_step(params, grads, st['exp_avg'], st['exp_avg_sq'], st['step'], 1e-3)
     for k in params:
         assert_close(params[k], tp[k].detach(), 1e-6, k)
+
+
+def test_lstm_oracle_matches_reference_goldens():
+    """use_lstm=True branch (atari_model.py:109-120): the oracle's step-wise LSTM with done-resets vs the reference AtariNet"""
+    g = np.load(os.path.join(GOLDEN, 'lstm_t4b3a6.npz'))
+    T, B, A, seed, bseed = [int(v) for v in g['meta']]
+    params, lp = O.init_params(A, seed=seed), O.init_lstm_params(A, seed=seed)
+    batch = O.synthetic_batch(T, B, A, seed=bseed, done_p=0.25)
+    state = (torch.from_numpy(g['state_h']), torch.from_numpy(g['state_c']))
+    with torch.no_grad():
+        lg, bs, ns = O.atari_forward_lstm(params, lp, batch['obs'], batch['reward'], batch['action'], batch['done'], state)
+    assert_close(lg, g['policy_logits'], 5e-6, 'logits')
+    assert_close(bs, g['baseline'], 5e-6, 'baseline')
+    assert_close(ns[0], g['h_out'], 5e-6, 'h')
+    assert_close(ns[1], g['c_out'], 5e-6, 'c')
+    out = O.learn_step_lstm(params, lp, batch, state)
+    assert abs(out['total_loss'] - g['total_loss'][0]) <= 1e-4 * abs(g['total_loss'][0])
+    assert_close(out['vs'], g['vs'], 1e-5, 'vs')
+    for k, v in {**out['grads'], **out['lstm_grads']}.items():
+        samp = strided_sample(v.reshape(-1)).numpy()
+        scale = max(np.abs(g['gradsamp_' + k]).max(), float(g['gradnorm_' + k][0]) / np.sqrt(v.numel()))
+        assert np.abs(samp - g['gradsamp_' + k]).max() <= 3e-4 * scale, k
