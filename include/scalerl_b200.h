@@ -142,6 +142,20 @@ int srl_learner_profile_collect(srl_learner_t* L, float* ms_out_host);
 /* asynchronous device-to-device copy on `stream` (used by tests to read the borrowed buffers) */
 int srl_memcpy_d2d(void* dst, const void* src, int64_t bytes, void* stream);
 
+/* ---- LSTM core (AtariNet use_lstm=True; atari_model.py:52-55,109-120) -------------------------------
+ * 2-layer LSTM(H, H), H = 513 + A, stepped with the state multiplied by (1 - done_t) before every step.
+ * weights8 / grads8: 8 device pointers in nn.LSTM state_dict order {weight_ih_l0 [4H,H], weight_hh_l0 [4H,H], bias_ih_l0 [4H],
+ * bias_hh_l0 [4H], *_l1 ...} (fp32, caller-owned); gradients are ACCUMULATED into grads8 (zero them before the step).
+ * forward : core f32 [T1,B,H], done u8 [T1,B], h0/c0 f32 [2,B,H] -> out f32 [T1,B,H], hT/cT f32 [2,B,H] (may be NULL)
+ * backward: dout f32 [T1-1,B,H] (steps 0..T-1; the bootstrap row T carries no gradient) -> dcore f32 [T1-1,B,H] */
+typedef struct srl_lstm srl_lstm_t;
+int srl_lstm_create(int T1, int B, int H, const float* const* weights8, float* const* grads8, srl_lstm_t** out);
+int srl_lstm_destroy(srl_lstm_t* L);
+int srl_lstm_forward(srl_lstm_t* L, const float* core, const uint8_t* done, const float* h0, const float* c0, float* out,
+                     float* hT, float* cT, void* stream);
+int srl_lstm_backward(srl_lstm_t* L, const float* dout, const uint8_t* done, float* dcore, void* stream);
+const char* srl_lstm_last_error(void);
+
 /* ---- trajectory ring -> time-major batch (the stacking step of ImpalaTrainer.get_batch, impala_atari.py:248-251) -----------
  * staging: B trajectory slots on the DEVICE, each one contiguous record of slot_bytes holding every key of create_buffers
  * (impala_atari.py:135-147) for T+1 steps; offsets6_host (HOST array) = byte offsets of {obs u8[T+1,4,84,84], reward f32[T+1],

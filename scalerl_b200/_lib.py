@@ -39,6 +39,10 @@ _SIGS = {
     'srl_learner_backward_finish': [_P, _P, _P],
     'srl_learner_apply_gradients': [_P, _P, _P],
     'srl_learner_debug_buffer': [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_L)],
+    'srl_lstm_create': [_I, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)],
+    'srl_lstm_destroy': [_P],
+    'srl_lstm_forward': [_P, _P, _P, _P, _P, _P, _P, _P, _P],
+    'srl_lstm_backward': [_P, _P, _P, _P, _P],
     'srl_unpack_slots': [_P, _L, C.POINTER(_L), _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     'srl_grad_norm_clip_coef': [_P, _L, _F, _P, _P, _P],
     'srl_rmsprop_step': [_P, _P, _P, _L, _P, _F, _F, _F, _P],
@@ -52,7 +56,7 @@ _SIGS = {
     'srl_learner_profile_collect': [_P, _P],
     'srl_version': [],
 }
-EXPORTS = sorted(list(_SIGS) + ['srl_last_error', 'srl_param_layout', 'srl_learner_workspace_bytes', 'srl_profile_slot_name'])
+EXPORTS = sorted(list(_SIGS) + ['srl_last_error', 'srl_param_layout', 'srl_learner_workspace_bytes', 'srl_profile_slot_name', 'srl_lstm_last_error'])
 
 
 def lib():
@@ -70,6 +74,8 @@ def lib():
         L.srl_last_error.argtypes = []
         L.srl_param_layout.restype = C.c_int64
         L.srl_param_layout.argtypes = [_I, C.POINTER(_L), C.POINTER(_L)]
+        L.srl_lstm_last_error.restype = C.c_char_p
+        L.srl_lstm_last_error.argtypes = []
         L.srl_profile_slot_name.restype = C.c_char_p
         L.srl_profile_slot_name.argtypes = [_I]
         L.srl_learner_workspace_bytes.restype = C.c_int64

@@ -87,6 +87,8 @@ struct TmaMaps {
   alignas(64) CUtensorMap w1k, w2k, w3k, wfk, wfd, w3d, w2d;
   bool valid = false;
 };
+// bf16 tensor map, dims innermost-first, strides in ELEMENTS for dims 1..rank-1, SWIZZLE_128B, zero OOB fill (encoder.cu)
+bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box);
 // returns cudaSuccess or an error; `why` gets a message on failure
 cudaError_t build_tma_maps(const EncoderBuffers& buf, int NF, int NB, TmaMaps* maps, const char** why);
 cudaError_t launch_pack_weights(const ParamPtrs& p, __nv_bfloat16* wpack, cudaStream_t st);

@@ -1,0 +1,59 @@
+"""GPU parity of the LSTM core against the oracle restatement of AtariNet's use_lstm branch
+(oracle.lstm_core_forward, pinned to the reference model by tests/golden/lstm_t4b3a6.npz).
+Tolerances: bf16 GEMM operands with fp32 accumulation and fp32 cell state -> rel-L2 <= 1e-2 on outputs/states,
+<= 3e-2 on gradients (errors compound over the recurrence)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import impala_oracle as O
+from tests.helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(T1, B, A, seed, done_p):
+    H = 513 + A
+    lp = O.init_lstm_params(A, seed=seed)
+    rng = np.random.RandomState(seed)
+    core = torch.from_numpy(rng.randn(T1, B, H).astype(np.float32) * 0.5)
+    done = torch.from_numpy(rng.rand(T1, B) < done_p)
+    state = (torch.from_numpy(rng.randn(2, B, H).astype(np.float32) * 0.3), torch.from_numpy(rng.randn(2, B, H).astype(np.float32) * 0.3))
+    return H, lp, core, done, state
+
+
+@pytest.mark.parametrize('T1,B,A,done_p', [(5, 3, 6, 0.25), (21, 32, 6, 0.05), (9, 130, 4, 0.1), (3, 1, 6, 0.0)])
+def test_lstm_forward_backward_vs_oracle(T1, B, A, done_p):
+    from scalerl_b200.lstm import B200LstmCore
+    H, lp, core, done, state = _case(T1, B, A, 3, done_p)
+    net = B200LstmCore(T1, B, H, state_dict=lp)
+    out, (hT, cT) = net.forward(core.cuda(), done.cuda(), (state[0].cuda(), state[1].cuda()))
+    # oracle with autograd
+    ls = {k: v.clone().requires_grad_(True) for k, v in lp.items()}
+    cr = core.clone().requires_grad_(True)
+    ref, (rh, rc) = O.lstm_core_forward(ls, cr, done, state)
+    assert rel_l2(out.cpu(), ref.detach()) < 1e-2
+    assert rel_l2(hT.cpu(), rh.detach()) < 1e-2 and rel_l2(cT.cpu(), rc.detach()) < 1e-2
+    rng = np.random.RandomState(9)
+    dout = torch.from_numpy(rng.randn(T1 - 1, B, H).astype(np.float32))
+    (ref[:-1] * dout).sum().backward()
+    net.zero_grad()
+    dcore = net.backward(dout.cuda())
+    assert rel_l2(dcore.cpu(), cr.grad[:-1]) < 3e-2
+    for k in lp:
+        assert rel_l2(net.grads[k].cpu(), ls[k].grad) < 3e-2, k
+    # a second backward accumulates (the C ABI contract)
+    net.backward(dout.cuda())
+    assert rel_l2(net.grads['rnn_layer.weight_hh_l1'].cpu(), 2 * ls['rnn_layer.weight_hh_l1'].grad) < 3e-2
+
+
+def test_lstm_done_resets_state():
+    """all-done input: the carried state must not matter (atari_model.py:116-117)"""
+    from scalerl_b200.lstm import B200LstmCore
+    T1, B, A = 4, 5, 6
+    H, lp, core, done, state = _case(T1, B, A, 1, 1.1)
+    assert bool(done.all())
+    net = B200LstmCore(T1, B, H, state_dict=lp)
+    a, _ = net.forward(core.cuda(), done.cuda(), (state[0].cuda(), state[1].cuda()))
+    b, _ = net.forward(core.cuda(), done.cuda(), (torch.zeros_like(state[0]).cuda(), torch.zeros_like(state[1]).cuda()))
+    assert torch.equal(a, b)
