@@ -77,6 +77,7 @@ typedef struct srl_config {
   float max_grad_norm;       /* clip_grad_norm_ threshold (rl_args.py:108)       */
   float learning_rate, alpha, epsilon;               /* RMSprop (rl_args.py:112-117) */
   float adam_beta1, adam_beta2, adam_eps;
+  int32_t use_lstm;          /* 1: AtariNet(use_lstm=True): 2-layer LSTM core between the encoder and the heads (config 5) */
 } srl_config_t;
 
 /* Number of fp32 elements of the flat parameter buffer for A actions, and the element offset / count of
@@ -86,7 +87,11 @@ typedef struct srl_config {
  * "small" gradient block and [offsets[6], total) is fc.weight. */
 int64_t srl_param_layout(int A, int64_t* offsets, int64_t* counts);
 
-/* params / grads / opt_state0 / opt_state1: flat f32 device buffers of srl_param_layout() elements, owned
+/* Same with the 8 LSTM tensors (nn.LSTM state_dict order: weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, *_l1) appended
+ * after fc.weight when use_lstm != 0: offsets/counts are int64[20] (entries 12..19 = LSTM; unused when use_lstm == 0). */
+int64_t srl_param_layout_ex(int A, int use_lstm, int64_t* offsets20, int64_t* counts20);
+
+/* params / grads / opt_state0 / opt_state1: flat f32 device buffers of srl_param_layout() (srl_param_layout_ex() with use_lstm) elements, owned
  * by the caller (so torch can expose state_dict views and NCCL can all-reduce `grads` in place).
  * opt_state1 is only used by Adam (may be NULL for RMSprop). */
 int srl_learner_create(const srl_config_t* cfg, float* params, float* grads, float* opt_state0, float* opt_state1,
@@ -110,6 +115,14 @@ int srl_learner_forward(srl_learner_t* L, const uint8_t* obs, const float* rewar
 int srl_learner_forward_backward(srl_learner_t* L, const uint8_t* obs, const float* reward, const uint8_t* done,
                                  const int64_t* action, const float* behavior_logits,
                                  float* losses, float* vs, float* pg_advantages, void* stream);
+
+/* use_lstm variants.  h0/c0: initial LSTM state f32 [2,B,513+A] (create_rnn_state_buffers,
+ * impala_atari.py:108-120); rows of the forward must be T+1.  hT/cT (may be NULL) receive the state after the last row. */
+int srl_learner_forward_lstm(srl_learner_t* L, const uint8_t* obs, const float* reward, const uint8_t* done, const int64_t* action,
+                             const float* h0, const float* c0, float* policy_logits, float* baseline, float* hT, float* cT, void* stream);
+int srl_learner_forward_backward_lstm(srl_learner_t* L, const uint8_t* obs, const float* reward, const uint8_t* done,
+                                      const int64_t* action, const float* behavior_logits, const float* h0, const float* c0,
+                                      float* losses, float* vs, float* pg_advantages, void* stream);
 
 /* The same step in two halves, for overlapping the gradient all-reduce with the backward pass:
  *   _begin : forward + V-trace/loss + head backward + the fc layer's backward.  On return (in stream order) the

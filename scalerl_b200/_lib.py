@@ -19,7 +19,7 @@ class SrlConfig(C.Structure):
                 ('discounting', C.c_float), ('baseline_cost', C.c_float), ('entropy_cost', C.c_float),
                 ('clip_rho_threshold', C.c_float), ('clip_pg_rho_threshold', C.c_float),
                 ('max_grad_norm', C.c_float), ('learning_rate', C.c_float), ('alpha', C.c_float), ('epsilon', C.c_float),
-                ('adam_beta1', C.c_float), ('adam_beta2', C.c_float), ('adam_eps', C.c_float)]
+                ('adam_beta1', C.c_float), ('adam_beta2', C.c_float), ('adam_eps', C.c_float), ('use_lstm', C.c_int32)]
 
 
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -37,6 +37,8 @@ _SIGS = {
     'srl_learner_forward_backward': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     'srl_learner_forward_backward_begin': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     'srl_learner_backward_finish': [_P, _P, _P],
+    'srl_learner_forward_lstm': [_P] * 12,
+    'srl_learner_forward_backward_lstm': [_P] * 12,
     'srl_learner_apply_gradients': [_P, _P, _P],
     'srl_learner_debug_buffer': [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_L)],
     'srl_lstm_create': [_I, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)],
@@ -56,7 +58,7 @@ _SIGS = {
     'srl_learner_profile_collect': [_P, _P],
     'srl_version': [],
 }
-EXPORTS = sorted(list(_SIGS) + ['srl_last_error', 'srl_param_layout', 'srl_learner_workspace_bytes', 'srl_profile_slot_name', 'srl_lstm_last_error'])
+EXPORTS = sorted(list(_SIGS) + ['srl_last_error', 'srl_param_layout', 'srl_param_layout_ex', 'srl_learner_workspace_bytes', 'srl_profile_slot_name', 'srl_lstm_last_error'])
 
 
 def lib():
@@ -74,6 +76,8 @@ def lib():
         L.srl_last_error.argtypes = []
         L.srl_param_layout.restype = C.c_int64
         L.srl_param_layout.argtypes = [_I, C.POINTER(_L), C.POINTER(_L)]
+        L.srl_param_layout_ex.restype = C.c_int64
+        L.srl_param_layout_ex.argtypes = [_I, _I, C.POINTER(_L), C.POINTER(_L)]
         L.srl_lstm_last_error.restype = C.c_char_p
         L.srl_lstm_last_error.argtypes = []
         L.srl_profile_slot_name.restype = C.c_char_p
@@ -92,8 +96,10 @@ def check(rc, what=''):
         raise RuntimeError(f'{what}: rc={rc}: {msg}')
 
 
-def param_layout(A):
-    off = (_L * 12)()
-    cnt = (_L * 12)()
-    total = lib().srl_param_layout(int(A), off, cnt)
-    return int(total), [int(x) for x in off], [int(x) for x in cnt]
+def param_layout(A, use_lstm=False):
+    """(total floats, offsets, counts) of the flat parameter buffer; 12 AtariNet tensors (+ 8 nn.LSTM tensors with use_lstm)"""
+    off = (_L * 20)()
+    cnt = (_L * 20)()
+    total = lib().srl_param_layout_ex(int(A), 1 if use_lstm else 0, off, cnt)
+    n = 20 if use_lstm else 12
+    return int(total), [int(x) for x in off][:n], [int(x) for x in cnt][:n]

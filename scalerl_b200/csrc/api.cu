@@ -121,20 +121,30 @@ extern "C" int srl_test_gemm_mnmajor(const void* At, const void* Bt, float* D, i
 // Flat buffer order: every small tensor first (conv1..3, fc.bias, heads), fc.weight LAST.  The small block is one
 // contiguous range (one memset, one late all-reduce); fc.weight (95 % of the bytes) is final early in the backward pass
 // and can be all-reduced while the conv layers are still back-propagating.  off/cnt are indexed in state_dict order.
-static int64_t layout(int A, int64_t* off, int64_t* cnt) {
+static int64_t layout_ex(int A, int use_lstm, int64_t* off, int64_t* cnt) {
   const int64_t core = 513 + A;
-  const int64_t counts[12] = {32 * 256, 32, 64 * 512, 64, 64 * 576, 64, 512 * 3136, 512, A * core, A, core, 1};
-  const int order[12] = {0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 6};
+  const int64_t counts[20] = {32 * 256, 32, 64 * 512, 64, 64 * 576, 64, 512 * 3136, 512, A * core, A, core, 1,
+                              4 * core * core, 4 * core * core, 4 * core, 4 * core, 4 * core * core, 4 * core * core, 4 * core, 4 * core};
+  const int order[20] = {0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 6, 12, 13, 14, 15, 16, 17, 18, 19};
   int64_t o = 0;
-  for (int k = 0; k < 12; ++k) {
+  const int n = use_lstm ? 20 : 12;
+  for (int k = 0; k < 20; ++k) {
     const int i = order[k];
+    if (k >= n) { if (off) off[i] = o; if (cnt) cnt[i] = 0; continue; }
     if (off) off[i] = o;
     if (cnt) cnt[i] = counts[i];
     o += (counts[i] + 3) & ~int64_t(3);
   }
   return o;
 }
+static int64_t layout(int A, int64_t* off, int64_t* cnt) {
+  int64_t o20[20], c20[20];
+  const int64_t total = layout_ex(A, 0, o20, c20);
+  for (int i = 0; i < 12; ++i) { if (off) off[i] = o20[i]; if (cnt) cnt[i] = c20[i]; }
+  return total;
+}
 extern "C" int64_t srl_param_layout(int A, int64_t* offsets, int64_t* counts) { return layout(A, offsets, counts); }
+extern "C" int64_t srl_param_layout_ex(int A, int use_lstm, int64_t* offsets20, int64_t* counts20) { return layout_ex(A, use_lstm, offsets20, counts20); }
 
 static ParamPtrs make_ptrs(float* base, int A) {
   int64_t off[12];
@@ -165,6 +175,10 @@ struct srl_learner {
   TmaMaps maps;                   // tensor maps of the TMA mainloop
   SideStream ss;                  // wgrad side stream + fork/join events
   int* dstep;                     // device-side optimizer step count (graph-replay safe Adam bias correction)
+  srl_lstm_t* lstm;               // use_lstm: the 2-layer LSTM core (csrc/lstm.cu) working on views of params/grads
+  float *core, *lstm_out, *dout, *dcore;   // [NF][H], [NF][H], [NB][H], [NB][H]
+  char* lstm_arena;
+  int64_t lstm_off0, lstm_len;    // LSTM gradient range inside the flat buffer
   Profiler pf;                    // per-kernel event bracketing (off by default)
   cudaEvent_t events[2 * PS_COUNT];
   bool slot_used[PS_COUNT];
@@ -180,6 +194,7 @@ static int check_cfg(const srl_config_t* c) {
   REQ(c->A >= 1 && c->A <= 32, "config: A=%d must be in [1,32]", c->A);
   REQ((int64_t)(c->T + 1) * c->B <= 65536, "config: (T+1)*B=%lld frames per GPU exceeds 65536", (long long)(c->T + 1) * c->B);
   REQ(c->optimizer == 0 || c->optimizer == 1, "config: optimizer must be 0 (rmsprop) or 1 (adam)");
+  REQ(c->use_lstm == 0 || c->use_lstm == 1, "config: use_lstm must be 0 or 1");
   REQ(c->simt_mainloop == 0, "config: only mainloop 0 (TMA-fed tcgen05) exists; the register-gather triage modes were retired with the grid layouts");
   return 0;
 }
@@ -194,7 +209,8 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   srl_learner* L = new (std::nothrow) srl_learner();
   REQ(L, "out of host memory");
   L->cfg = *cfg; L->params = params; L->grads = grads; L->opt0 = opt0; L->opt1 = opt1;
-  L->nparams = layout(cfg->A, nullptr, nullptr);
+  L->nparams = layout_ex(cfg->A, cfg->use_lstm, nullptr, nullptr);
+  L->lstm = nullptr; L->lstm_arena = nullptr; L->core = L->lstm_out = L->dout = L->dcore = nullptr; L->lstm_off0 = L->lstm_len = 0;
   L->P = make_ptrs(params, cfg->A);
   L->G = make_ptrs(grads, cfg->A);
   L->step = 0; L->have_fwd = false;
@@ -263,6 +279,27 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
       return fail(SRL_ESTATE, "learner_create: building TMA tensor map '%s' failed (driver without cuTensorMapEncodeTiled?)", why ? why : "?");
     }
   }
+  if (cfg->use_lstm) {
+    int64_t off[20], cnt[20];
+    const int64_t total_p = layout_ex(cfg->A, 1, off, cnt);
+    const int H = 513 + cfg->A;
+    const float* wp[8]; float* gp[8];
+    for (int i = 0; i < 8; ++i) { wp[i] = params + off[12 + i]; gp[i] = grads + off[12 + i]; }
+    L->lstm_off0 = off[12]; L->lstm_len = total_p - off[12];
+    const int64_t bytes = ((NF + NF + NB + NB) * (int64_t)H * 4 + 1024);
+    bool ok = cudaMalloc(&L->lstm_arena, bytes) == cudaSuccess && cudaMemset(L->lstm_arena, 0, bytes) == cudaSuccess;
+    if (ok) {
+      float* q2 = (float*)L->lstm_arena;
+      L->core = q2; q2 += NF * H; L->lstm_out = q2; q2 += NF * H; L->dout = q2; q2 += NB * H; L->dcore = q2;
+      ok = srl_lstm_create(cfg->T + 1, cfg->B, H, wp, gp, &L->lstm) == 0;
+    }
+    if (!ok) {
+      if (L->lstm_arena) cudaFree(L->lstm_arena);
+      cudaFree(L->arena);
+      delete L;
+      return fail(SRL_ESTATE, "learner_create: LSTM core allocation failed: %s", srl_lstm_last_error());
+    }
+  }
   *out = L;
   return 0;
 }
@@ -272,6 +309,8 @@ extern "C" int srl_learner_destroy(srl_learner_t* L) {
   for (int i = 0; i < 2 * PS_COUNT; ++i) if (L->events[i]) cudaEventDestroy(L->events[i]);
   for (int i = 0; i < 8; ++i) if (L->ss.ev[i]) cudaEventDestroy(L->ss.ev[i]);
   if (L->ss.side) cudaStreamDestroy(L->ss.side);
+  if (L->lstm) srl_lstm_destroy(L->lstm);
+  if (L->lstm_arena) cudaFree(L->lstm_arena);
   cudaFree(L->arena);
   delete L;
   return 0;
@@ -283,7 +322,7 @@ extern "C" int srl_learner_set_config(srl_learner_t* L, const srl_config_t* cfg)
   int rc = check_cfg(cfg);
   if (rc) return rc;
   REQ(cfg->T == L->cfg.T && cfg->B == L->cfg.B && cfg->A == L->cfg.A && cfg->optimizer == L->cfg.optimizer &&
-      cfg->simt_mainloop == L->cfg.simt_mainloop, "set_config: T/B/A/optimizer/mainloop are fixed at creation");
+      cfg->simt_mainloop == L->cfg.simt_mainloop && cfg->use_lstm == L->cfg.use_lstm, "set_config: T/B/A/optimizer/mainloop/use_lstm are fixed at creation");
   L->cfg = *cfg;
   return 0;
 }
@@ -294,8 +333,7 @@ extern "C" int srl_learner_pack_weights(srl_learner_t* L, void* stream) {
   return 0;
 }
 
-static int forward_impl(srl_learner* L, const uint8_t* obs, const float* reward, const int64_t* action, int frames, float* logits,
-                        float* baseline, cudaStream_t st) {
+static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStream_t st) {
   L->pf.st = st;
   // The bf16 operand copies are re-derived from the fp32 master weights at the START of every forward (not at the end
   // of the optimizer step): the pack kernel runs on the side stream underneath the frame conversion.
@@ -312,6 +350,14 @@ static int forward_impl(srl_learner* L, const uint8_t* obs, const float* reward,
     L->pf.e(PS_PACK);
   }
   CU(encoder_forward(obs, frames, L->P, L->buf, L->maps, L->cfg.simt_mainloop, st, L->pf, packed), "encoder_forward");
+  return 0;
+}
+
+static int forward_impl(srl_learner* L, const uint8_t* obs, const float* reward, const int64_t* action, int frames, float* logits,
+                        float* baseline, cudaStream_t st) {
+  REQ(!L->cfg.use_lstm, "this learner was created with use_lstm=1: call the *_lstm entry points");
+  int rc = encode_impl(L, obs, frames, st);
+  if (rc) return rc;
   L->pf.b(PS_HEAD_FWD);
   CU(launch_head_fwd(L->buf.hpart, FC_SPLITS, L->P.bf, L->buf.h, reward, action, L->P.wp, L->P.bp, L->P.wb, L->P.bb, frames, L->cfg.A,
                      logits, baseline, st), "head_fwd");
@@ -376,6 +422,55 @@ extern "C" int srl_learner_backward_finish(srl_learner_t* L, const uint8_t* obs,
   const srl_config_t& c = L->cfg;
   L->pf.st = (cudaStream_t)stream;
   CU(encoder_backward(obs, c.T * c.B, L->buf, L->G, L->maps, c.simt_mainloop, (cudaStream_t)stream, L->pf, L->ss, 1), "encoder_backward");
+  return 0;
+}
+
+static int forward_lstm_impl(srl_learner* L, const uint8_t* obs, const float* reward, const uint8_t* done, const int64_t* action,
+                             const float* h0, const float* c0, float* logits, float* baseline, float* hT, float* cT, cudaStream_t st) {
+  REQ(L->cfg.use_lstm && L->lstm, "this learner was created with use_lstm=0");
+  const srl_config_t& c = L->cfg;
+  const int NF = (c.T + 1) * c.B;
+  int rc = encode_impl(L, obs, NF, st);
+  if (rc) return rc;
+  CU(launch_core_build(L->buf.hpart, FC_SPLITS, L->P.bf, reward, action, NF, c.A, L->buf.h, L->core, st), "core_build");
+  rc = srl_lstm_forward(L->lstm, L->core, done, h0, c0, L->lstm_out, hT, cT, st);
+  if (rc) return fail(rc, "lstm_forward: %s", srl_lstm_last_error());
+  CU(launch_head_dense_fwd(L->lstm_out, L->P.wp, L->P.bp, L->P.wb, L->P.bb, NF, c.A, logits, baseline, st), "head_dense_fwd");
+  return 0;
+}
+
+extern "C" int srl_learner_forward_lstm(srl_learner_t* L, const uint8_t* obs, const float* reward, const uint8_t* done, const int64_t* action,
+                                        const float* h0, const float* c0, float* policy_logits, float* baseline, float* hT, float* cT,
+                                        void* stream) {
+  REQ(L && obs && reward && done && action && h0 && c0 && policy_logits && baseline, "learner_forward_lstm: NULL pointer");
+  return forward_lstm_impl(L, obs, reward, done, action, h0, c0, policy_logits, baseline, hT, cT, (cudaStream_t)stream);
+}
+
+extern "C" int srl_learner_forward_backward_lstm(srl_learner_t* L, const uint8_t* obs, const float* reward, const uint8_t* done,
+                                                 const int64_t* action, const float* behavior_logits, const float* h0, const float* c0,
+                                                 float* losses, float* vs, float* pg_advantages, void* stream) {
+  REQ(L && obs && reward && done && action && behavior_logits && h0 && c0 && losses, "learner_forward_backward_lstm: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const srl_config_t& c = L->cfg;
+  const int NB = c.T * c.B;
+  int rc = forward_lstm_impl(L, obs, reward, done, action, h0, c0, L->logits, L->baseline, nullptr, nullptr, st);
+  if (rc) return rc;
+  CU(launch_impala_tail(behavior_logits, L->logits, L->baseline, action, reward, done, c.T, c.B, c.A, c.discounting, c.reward_clip_abs_one,
+                        c.clip_rho_threshold, c.clip_pg_rho_threshold, c.baseline_cost, c.entropy_cost, vs, pg_advantages, L->dlogits,
+                        L->dbaseline, losses, L->scratch, st), "impala_tail");
+  {
+    int64_t off[12], cnt[12];
+    layout(c.A, off, cnt);
+    CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), st), "zero small grads");
+    CU(cudaMemsetAsync(L->grads + L->lstm_off0, 0, L->lstm_len * sizeof(float), st), "zero lstm grads");
+  }
+  CU(launch_head_dense_bwd(L->lstm_out, L->dlogits, L->dbaseline, L->P.wp, L->P.wb, NB, c.A, L->dout, L->G.wp, L->G.bp, L->G.wb, L->G.bb, st),
+     "head_dense_bwd");
+  rc = srl_lstm_backward(L->lstm, L->dout, done, L->dcore, st);
+  if (rc) return fail(rc, "lstm_backward: %s", srl_lstm_last_error());
+  CU(launch_dcore_to_dh(L->dcore, L->buf.h, NB, c.A, L->buf.dh, st), "dcore_to_dh");
+  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.simt_mainloop, st, L->pf, L->ss, 2), "encoder_backward");
+  L->have_fwd = true;
   return 0;
 }
 

@@ -201,6 +201,107 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// LSTM path (use_lstm): the heads read the LSTM output X [N][H] (H = 513 + A) instead of [h, reward, one-hot]
+// ------------------------------------------------------------------------------------------------
+// core[n] = [relu(sum_s hpart + bfc) (512), clamp(reward,-1,1), one_hot(action) (A)]  (atari_model.py:100-107); also stores h
+__global__ void __launch_bounds__(128) core_build_kernel(const float* __restrict__ hpart, int nsplit, const float* __restrict__ bfc,
+                                                         const float* __restrict__ reward, const int64_t* __restrict__ action, int N, int A,
+                                                         float* __restrict__ h, float* __restrict__ core) {
+  const int n = blockIdx.x, H = 513 + A;
+  for (int j = threadIdx.x; j < H; j += 128) {
+    float v;
+    if (j < 512) {
+      v = __ldg(hpart + (size_t)n * 512 + j);
+      for (int k = 1; k < nsplit; ++k) v += __ldg(hpart + ((size_t)k * N + n) * 512 + j);
+      v = fmaxf(v + __ldg(bfc + j), 0.f);
+      h[(size_t)n * 512 + j] = v;
+    } else if (j == 512) {
+      v = fminf(fmaxf(__ldg(reward + n), -1.f), 1.f);
+    } else {
+      v = ((int)__ldg(action + n) == j - 513) ? 1.f : 0.f;
+    }
+    core[(size_t)n * H + j] = v;
+  }
+}
+// logits[n][a] = X[n] . Wp[a] + bp[a];  baseline[n] = X[n] . Wb + bb      (one warp per frame)
+__global__ void __launch_bounds__(256) head_dense_fwd_kernel(const float* __restrict__ X, const float* __restrict__ Wp, const float* __restrict__ bp,
+                                                             const float* __restrict__ Wb, const float* __restrict__ bb, int N, int A,
+                                                             float* __restrict__ logits, float* __restrict__ baseline) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const int H = 513 + A;
+  for (int a = 0; a <= A; ++a) {
+    const float* w = a < A ? Wp + (size_t)a * H : Wb;
+    float s = 0.f;
+    for (int j = lane; j < H; j += 32) s = fmaf(__ldg(X + (size_t)n * H + j), __ldg(w + j), s);
+    s = warp_sum(s);
+    if (lane == 0) { if (a < A) logits[(size_t)n * A + a] = s + __ldg(bp + a); else baseline[n] = s + __ldg(bb); }
+  }
+}
+// dX[n][j] = sum_a dlogits[n][a] Wp[a][j] + dV[n] Wb[j];  head weight/bias gradients accumulated atomically (slabs of 16 frames)
+__global__ void __launch_bounds__(128) head_dense_bwd_kernel(const float* __restrict__ X, const float* __restrict__ dlogits,
+                                                             const float* __restrict__ dbaseline, const float* __restrict__ Wp,
+                                                             const float* __restrict__ Wb, int N, int A, float* __restrict__ dX,
+                                                             float* __restrict__ gWp, float* __restrict__ gbp, float* __restrict__ gWb,
+                                                             float* __restrict__ gbb) {
+  __shared__ float sd[16][HEAD_MAX_A + 1];
+  const int H = 513 + A, j = blockIdx.x * 128 + threadIdx.x;
+  const int n0 = blockIdx.y * 16, cnt = min(16, N - n0);
+  for (int i = threadIdx.x; i < cnt * (A + 1); i += 128) {
+    const int r = i / (A + 1), a = i - r * (A + 1);
+    sd[r][a] = a < A ? __ldg(dlogits + (size_t)(n0 + r) * A + a) : __ldg(dbaseline + n0 + r);
+  }
+  __syncthreads();
+  if (j > H) return;
+  float acc[HEAD_MAX_A + 1];
+#pragma unroll
+  for (int a = 0; a <= HEAD_MAX_A; ++a) acc[a] = 0.f;
+  for (int r = 0; r < cnt; ++r) {
+    const float x = j < H ? __ldg(X + (size_t)(n0 + r) * H + j) : 1.f;     // j == H: the bias "ones" column
+    float dx = 0.f;
+#pragma unroll
+    for (int a = 0; a < HEAD_MAX_A; ++a)
+      if (a < A) { acc[a] = fmaf(sd[r][a], x, acc[a]); if (j < H) dx = fmaf(sd[r][a], __ldg(Wp + (size_t)a * H + j), dx); }
+    acc[HEAD_MAX_A] = fmaf(sd[r][A], x, acc[HEAD_MAX_A]);
+    if (j < H) dX[(size_t)(n0 + r) * H + j] = dx + sd[r][A] * __ldg(Wb + j);
+  }
+#pragma unroll
+  for (int a = 0; a < HEAD_MAX_A; ++a)
+    if (a < A) { if (j < H) atomicAdd(gWp + (size_t)a * H + j, acc[a]); else atomicAdd(gbp + a, acc[a]); }
+  if (j < H) atomicAdd(gWb + j, acc[HEAD_MAX_A]); else atomicAdd(gbb, acc[HEAD_MAX_A]);
+}
+// dh[n][j] = bf16(dcore[n][j] * (h[n][j] > 0)), j < 512 (the reward / one-hot columns of core have no parameters below them)
+__global__ void __launch_bounds__(128) dcore_to_dh_kernel(const float* __restrict__ dcore, const float* __restrict__ h, int A,
+                                                          __nv_bfloat16* __restrict__ dh) {
+  const int n = blockIdx.x, H = 513 + A;
+  for (int j = threadIdx.x; j < 512; j += 128) {
+    const float v = __ldg(h + (size_t)n * 512 + j) > 0.f ? __ldg(dcore + (size_t)n * H + j) : 0.f;
+    dh[(size_t)n * 512 + j] = __float2bfloat16_rn(v);
+  }
+}
+
+cudaError_t launch_core_build(const float* hpart, int nsplit, const float* bfc, const float* reward, const int64_t* action, int N, int A, float* h,
+                              float* core, cudaStream_t st) {
+  core_build_kernel<<<N, 128, 0, st>>>(hpart, nsplit, bfc, reward, action, N, A, h, core);
+  return cudaGetLastError();
+}
+cudaError_t launch_head_dense_fwd(const float* X, const float* Wp, const float* bp, const float* Wb, const float* bb, int N, int A, float* logits,
+                                  float* baseline, cudaStream_t st) {
+  head_dense_fwd_kernel<<<(N + 7) / 8, 256, 0, st>>>(X, Wp, bp, Wb, bb, N, A, logits, baseline);
+  return cudaGetLastError();
+}
+cudaError_t launch_head_dense_bwd(const float* X, const float* dlogits, const float* dbaseline, const float* Wp, const float* Wb, int N, int A,
+                                  float* dX, float* gWp, float* gbp, float* gWb, float* gbb, cudaStream_t st) {
+  const int H = 513 + A;
+  head_dense_bwd_kernel<<<dim3((H + 1 + 127) / 128, (N + 15) / 16), 128, 0, st>>>(X, dlogits, dbaseline, Wp, Wb, N, A, dX, gWp, gbp, gWb, gbb);
+  return cudaGetLastError();
+}
+cudaError_t launch_dcore_to_dh(const float* dcore, const float* h, int N, int A, __nv_bfloat16* dh, cudaStream_t st) {
+  dcore_to_dh_kernel<<<N, 128, 0, st>>>(dcore, h, A, dh);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // trajectory-slot unpack: B slots (one contiguous record per actor rollout, all keys of create_buffers,
 // impala_atari.py:135-147) copied host->device as they lie, then scattered into the time-major [T+1, B, ...] batch.
 // grid = (T+1, B): one block moves one 28,224-byte frame with 16-byte vectors; thread 0 moves the scalars.

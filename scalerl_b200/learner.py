@@ -24,9 +24,19 @@ from . import _lib
 
 PARAM_NAMES = ('conv1.weight', 'conv1.bias', 'conv2.weight', 'conv2.bias', 'conv3.weight', 'conv3.bias',
                'fc.weight', 'fc.bias', 'policy.weight', 'policy.bias', 'baseline.weight', 'baseline.bias')
+LSTM_PARAM_NAMES = tuple(f'rnn_layer.{w}_l{l}' for l in (0, 1) for w in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh'))
 
 
-def param_shapes(num_actions: int):
+def param_shapes(num_actions: int, use_lstm: bool = False):
+    core = 513 + num_actions
+    d = _base_shapes(num_actions)
+    if use_lstm:
+        for n in LSTM_PARAM_NAMES:
+            d[n] = (4 * core, core) if 'weight' in n else (4 * core,)
+    return d
+
+
+def _base_shapes(num_actions: int):
     core = 513 + num_actions
     return OrderedDict([
         ('conv1.weight', (32, 4, 8, 8)), ('conv1.bias', (32,)), ('conv2.weight', (64, 32, 4, 4)), ('conv2.bias', (64,)),
@@ -58,6 +68,7 @@ class ImpalaHParams:
     adam_beta2: float = 0.999
     adam_eps: float = 1e-8
     simt_mainloop: int = 0               # reserved (must be 0: TMA-fed tcgen05 mainloop)
+    use_lstm: bool = False               # AtariNet(use_lstm=True): 2-layer LSTM core (impala_atari.py:56; config 5)
 
     def to_c(self) -> _lib.SrlConfig:
         if self.reward_clipping not in ('abs_one', 'none'):
@@ -77,6 +88,7 @@ class ImpalaHParams:
         c.max_grad_norm = self.max_grad_norm
         c.learning_rate, c.alpha, c.epsilon = self.learning_rate, self.alpha, self.epsilon
         c.adam_beta1, c.adam_beta2, c.adam_eps = self.adam_beta1, self.adam_beta2, self.adam_eps
+        c.use_lstm = 1 if self.use_lstm else 0
         return c
 
 
@@ -98,14 +110,15 @@ class B200ImpalaLearner:
                       and dist.get_world_size(process_group or None) > 1)
         self._L = _lib.lib()
         with torch.cuda.device(self.device):
-            total, self._off, self._cnt = _lib.param_layout(hp.num_actions)
+            self.names = PARAM_NAMES + (LSTM_PARAM_NAMES if hp.use_lstm else ())
+            total, self._off, self._cnt = _lib.param_layout(hp.num_actions, hp.use_lstm)
             self.numel = total
             z = lambda: torch.zeros(total, dtype=torch.float32, device=self.device)
             self.flat_params, self.flat_grads, self.opt_state0 = z(), z(), z()
             self.opt_state1 = z() if hp.optimizer == 'adam' else None
-            self.shapes = param_shapes(hp.num_actions)
-            self.params = OrderedDict((n, self._view(self.flat_params, i)) for i, n in enumerate(PARAM_NAMES))
-            self.grads = OrderedDict((n, self._view(self.flat_grads, i)) for i, n in enumerate(PARAM_NAMES))
+            self.shapes = param_shapes(hp.num_actions, hp.use_lstm)
+            self.params = OrderedDict((n, self._view(self.flat_params, i)) for i, n in enumerate(self.names))
+            self.grads = OrderedDict((n, self._view(self.flat_grads, i)) for i, n in enumerate(self.names))
             if init_state_dict is None:
                 init_state_dict = self._default_init(seed)
             self._cfg = hp.to_c()
@@ -116,6 +129,9 @@ class B200ImpalaLearner:
             self._h = h
             self.load_state_dict(init_state_dict)
             T, B, A = hp.rollout_length, hp.batch_size, hp.num_actions
+            if hp.use_lstm:     # static copies of the initial LSTM state (graph-replay safe addresses)
+                self._h0 = torch.zeros(2, B, 513 + A, device=self.device)
+                self._c0 = torch.zeros(2, B, 513 + A, device=self.device)
             self._losses = torch.zeros(4, device=self.device)
             self._coef = torch.zeros(2, device=self.device)
             self._vs = torch.empty(T, B, device=self.device)
@@ -128,15 +144,18 @@ class B200ImpalaLearner:
 
     # ------------------------------------------------------------------ parameters
     def _view(self, flat, i):
-        n = PARAM_NAMES[i]
+        n = self.names[i]
         return flat[self._off[i]:self._off[i] + self._cnt[i]].view(self.shapes[n])
 
     def _default_init(self, seed):
         """torch's default Conv2d/Linear init distribution (U(+-1/sqrt(fan_in))), as AtariNet() would draw."""
         g = torch.Generator().manual_seed(seed)
         sd, fan = OrderedDict(), 1
+        H = 513 + self.hp.num_actions
         for n, shp in self.shapes.items():
-            if n.endswith('.weight'):
+            if n.startswith('rnn_layer.'):
+                fan = H                     # nn.LSTM: U(+-1/sqrt(hidden_size)) for every tensor
+            elif n.endswith('.weight'):
                 fan = 1
                 for d in shp[1:]:
                     fan *= d
@@ -149,7 +168,7 @@ class B200ImpalaLearner:
         return OrderedDict((n, p.detach().clone()) for n, p in self.params.items())
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
-        for n in PARAM_NAMES:
+        for n in self.names:
             if n not in sd:
                 raise KeyError(f'missing key {n} in state_dict')
             if tuple(sd[n].shape) != tuple(self.shapes[n]):
@@ -167,7 +186,7 @@ class B200ImpalaLearner:
         names = ('square_avg',) if self.hp.optimizer == 'rmsprop' else ('exp_avg', 'exp_avg_sq')
         flats = (self.opt_state0,) if self.hp.optimizer == 'rmsprop' else (self.opt_state0, self.opt_state1)
         return {'step': self.global_opt_step, 'state': {nm: OrderedDict((n, self._view(f, i).detach().clone())
-                                                                     for i, n in enumerate(PARAM_NAMES)) for nm, f in zip(names, flats)}}
+                                                                     for i, n in enumerate(self.names)) for nm, f in zip(names, flats)}}
 
     @property
     def global_opt_step(self):
@@ -184,7 +203,7 @@ class B200ImpalaLearner:
         st = ck.get('optimizer_state_dict', {}).get('state', {})
         for nm, flat in (('square_avg', self.opt_state0), ('exp_avg', self.opt_state0), ('exp_avg_sq', self.opt_state1)):
             if nm in st and flat is not None:
-                for i, n in enumerate(PARAM_NAMES):
+                for i, n in enumerate(self.names):
                     self._view(flat, i).copy_(st[nm][n])
 
     # ------------------------------------------------------------------ compute
@@ -204,14 +223,34 @@ class B200ImpalaLearner:
             if not t.is_cuda or not t.is_contiguous():
                 raise ValueError(f"batch['{k}'] must be a contiguous CUDA tensor")
 
+    def _done_u8(self, batch):
+        d = batch['done']
+        return d.view(torch.uint8) if d.dtype == torch.bool else d
+
+    def _set_rnn_state(self, state):
+        if state is None or len(state) == 0:
+            self._h0.zero_(); self._c0.zero_()
+        else:
+            self._h0.copy_(state[0]); self._c0.copy_(state[1])
+
     @torch.no_grad()
-    def forward(self, batch: Dict[str, torch.Tensor]):
+    def forward(self, batch: Dict[str, torch.Tensor], initial_rnn_state=()):
         """AtariNet.forward (learner path: no action sampling) -> dict(policy_logits [R,B,A], baseline [R,B])."""
         rows = batch['obs'].shape[0]
         self._check_batch(batch, rows)
         hp = self.hp
         logits = torch.empty(rows, hp.batch_size, hp.num_actions, device=self.device)
         baseline = torch.empty(rows, hp.batch_size, device=self.device)
+        if hp.use_lstm:
+            if rows != hp.rollout_length + 1:
+                raise ValueError('the LSTM learner forward needs T+1 rows')
+            self._set_rnn_state(initial_rnn_state)
+            hT, cT = torch.empty_like(self._h0), torch.empty_like(self._c0)
+            _lib.check(self._L.srl_learner_forward_lstm(
+                self._h, batch['obs'].data_ptr(), batch['reward'].data_ptr(), self._done_u8(batch).data_ptr(), batch['action'].data_ptr(),
+                self._h0.data_ptr(), self._c0.data_ptr(), logits.data_ptr(), baseline.data_ptr(), hT.data_ptr(), cT.data_ptr(), self._stream()),
+                'srl_learner_forward_lstm')
+            return dict(policy_logits=logits, baseline=baseline), (hT, cT)
         _lib.check(self._L.srl_learner_forward(self._h, batch['obs'].data_ptr(), batch['reward'].data_ptr(), batch['action'].data_ptr(),
                                                rows, logits.data_ptr(), baseline.data_ptr(), self._stream()), 'srl_learner_forward')
         return dict(policy_logits=logits, baseline=baseline)
@@ -228,6 +267,12 @@ class B200ImpalaLearner:
         bl = batch['policy_logits']
         if tuple(bl.shape) != (hp.rollout_length + 1, hp.batch_size, hp.num_actions) or bl.dtype != torch.float32:
             raise ValueError("batch['policy_logits'] must be float32 [T+1, B, A]")
+        if hp.use_lstm:
+            _lib.check(self._L.srl_learner_forward_backward_lstm(
+                self._h, batch['obs'].data_ptr(), batch['reward'].data_ptr(), done_u8.data_ptr(), batch['action'].data_ptr(), bl.data_ptr(),
+                self._h0.data_ptr(), self._c0.data_ptr(), self._losses.data_ptr(), self._vs.data_ptr(), self._pg_adv.data_ptr(), self._stream()),
+                'srl_learner_forward_backward_lstm')
+            return
         _lib.check(self._L.srl_learner_forward_backward(
             self._h, batch['obs'].data_ptr(), batch['reward'].data_ptr(), done_u8.data_ptr(), batch['action'].data_ptr(),
             bl.data_ptr(), self._losses.data_ptr(), self._vs.data_ptr(), self._pg_adv.data_ptr(), self._stream()),
@@ -262,8 +307,10 @@ class B200ImpalaLearner:
     def _enqueue_step(self, batch):
         """forward_backward -> apply_gradients on the current stream; with world_size > 1 the fc.weight gradient is
         all-reduced (async, NCCL stream) while the conv layers back-propagate, the small block afterwards."""
-        if not self._dist:
+        if not self._dist or self.hp.use_lstm:
             self.forward_backward(batch)
+            if self._dist:          # LSTM path: one all-reduce of the whole flat gradient after BPTT
+                self.all_reduce_gradients()
             self.apply_gradients()
             return
         self._dp_step(batch, lambda: self.forward_backward_begin(batch), lambda: self.backward_finish(batch), self.apply_gradients)
@@ -302,7 +349,13 @@ class B200ImpalaLearner:
             hp = self.hp
             self._check_batch(batch, hp.rollout_length + 1)
             torch.cuda.current_stream(self.device).synchronize()
-            if self._dist:
+            if self._dist and self.hp.use_lstm:
+                g = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph())
+                with torch.cuda.graph(g[0]):
+                    self.forward_backward(batch)
+                with torch.cuda.graph(g[1]):
+                    self.apply_gradients()
+            elif self._dist:
                 g = None
                 if os.environ.get('SRL_DP_SINGLE_GRAPH'):
                     try:        # opt-in: ONE graph with the two NCCL all-reduces captured inside it (measured: no faster than split
@@ -333,6 +386,10 @@ class B200ImpalaLearner:
             self._graphs[key] = g
         if len(g) == 3:
             self._dp_step(batch, g[0].replay, g[1].replay, g[2].replay)
+        elif len(g) == 2:
+            g[0].replay()
+            self.all_reduce_gradients()
+            g[1].replay()
         else:
             g[0].replay()
         self._opt_steps = self.global_opt_step + 1
@@ -342,6 +399,8 @@ class B200ImpalaLearner:
               use_graph: Optional[bool] = None) -> Dict[str, object]:
         """One learner step (impala_atari.py:288-346).  Returns the reference's stats dict when sync_stats
         (one D2H read of 6 floats), else {} with everything left enqueued on the stream."""
+        if self.hp.use_lstm:
+            self._set_rnn_state(initial_rnn_state)
         if self.use_graph if use_graph is None else use_graph:
             self._graph_step(batch)
         else:

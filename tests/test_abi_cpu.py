@@ -39,7 +39,7 @@ def test_param_layout_matches_atarinet():
 
 
 def test_config_struct_size():
-    assert ctypes.sizeof(_lib.SrlConfig) == 18 * 4
+    assert ctypes.sizeof(_lib.SrlConfig) == 19 * 4
 
 
 def test_argument_errors_without_gpu(lib):
