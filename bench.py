@@ -222,6 +222,7 @@ def _main(real_stdout):
     ap.add_argument('--A', type=int, default=A_DEFAULT)
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU-baseline work (rank 0, N=1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--use-lstm', action='store_true', help='AtariNet(use_lstm=True) learner (BASELINE.json configs[4]: use with --T 100)')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -248,7 +249,7 @@ def _main(real_stdout):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
     T, B, A, K, W = args.T, args.B, args.A, args.steps, args.warmup
-    hp = ImpalaHParams(rollout_length=T, batch_size=B, num_actions=A)
+    hp = ImpalaHParams(rollout_length=T, batch_size=B, num_actions=A, use_lstm=args.use_lstm)
     learner = B200ImpalaLearner(hp, device=dev, seed=0)
     host_pool = make_host_pool(T, B, A, POOL, seed=rank)
     dev_pool = [{k: v.to(dev, non_blocking=True) for k, v in hb.items()} for hb in host_pool]
@@ -334,12 +335,15 @@ def _main(real_stdout):
     acc = [0.0] * nslot
     buf = (C.c_float * nslot)()
     nprof = min(K, 20)
+    if args.use_lstm:
+        nprof = 0          # the per-slot event bracketing covers the non-LSTM step only
     for i in range(nprof):
         learner.learn(dev_pool[i % POOL], sync_stats=False, use_graph=False)
         torch.cuda.synchronize()
         _lib.check(L.srl_learner_profile_collect(learner._h, buf))
         for j in range(nslot):
             acc[j] += max(0.0, buf[j])
+    nprof = max(nprof, 1)
     _lib.check(L.srl_learner_set_profiling(learner._h, 0))
     per_kernel_ms = {names[j]: acc[j] / nprof for j in range(nslot)}
     pk = peaks()
@@ -359,6 +363,9 @@ def _main(real_stdout):
             tensor_pct = tj['kernels'][dom]['tensor_pipe_active_pct']
             traffic_src = tj['source']
     step_flops = NF * 18.693e6 + NBk * 30.833e6
+    if args.use_lstm:     # 2 layers x (Wih + Whh) x 4H x H MACs per frame forward; backward = dX/dh + dW (2x)
+        Hh = 513 + A
+        step_flops += NF * 2 * (2 * 2 * 4 * Hh * Hh) + NBk * 2 * 2 * (2 * 2 * 4 * Hh * Hh)
     sum_kernel_ms = sum(per_kernel_ms.values())
     roofline = {'bound': 'tensor', 'kernel': dom, 'achieved': gemm[dom]['tflops'], 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s',
                 'frac': gemm[dom]['tflops'] / pk['bf16_tflops'], 'traffic': traffic, 'traffic_unit': 'bytes (dram read+write per launch)',
@@ -409,7 +416,7 @@ def _main(real_stdout):
                'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
                'data': 'synthetic',
                'config': {'workload': f'IMPALA Pong 84x84x4 uint8, T={T}, B={B}/GPU, A={A}, synthetic trajectories (BASELINE.json configs[1] per GPU)',
-                          'rollout_length': T, 'columns_per_gpu': B, 'global_batch': B * world, 'num_actions': A, 'optimizer': 'rmsprop',
+                          'rollout_length': T, 'columns_per_gpu': B, 'global_batch': B * world, 'num_actions': A, 'optimizer': 'rmsprop', 'use_lstm': bool(args.use_lstm),
                           'parallelism': f'dp{world}' if world > 1 else 'single', 'grad_allreduce': 'nccl sum' if world > 1 else 'none',
                           'l2': f'inputs cycle through {POOL} distinct batches ({POOL * feeder.h2d_bytes / 1e6:.0f} MB > 126 MB L2)',
                           'operands': 'bf16 tensor-core operands, fp32 accumulate, fp32 master weights / V-trace / optimizer',
