@@ -169,6 +169,22 @@ int srl_lstm_forward(srl_lstm_t* L, const float* core, const uint8_t* done, cons
 int srl_lstm_backward(srl_lstm_t* L, const float* dout, const uint8_t* done, float* dcore, void* stream);
 const char* srl_lstm_last_error(void);
 
+/* ---- prioritized-replay sampler (BASELINE.json configs[3]) ---------------------------------------------------
+ * Device-resident float64 sum/min segment trees; replaces PrioritizedReplayBuffer's tree arithmetic
+ * (scalerl/data/replay_buffer.py:305-381 over scalerl/data/segment_tree.py:7-196).  Index results are identical to the
+ * reference's Python-float trees given identical leaf values.  The transition storage itself stays with the caller. */
+typedef struct srl_per srl_per_t;
+int srl_per_create(int64_t memory_size, double alpha, srl_per_t** out);
+int srl_per_destroy(srl_per_t* P);
+int64_t srl_per_size(const srl_per_t* P);
+int64_t srl_per_capacity(const srl_per_t* P);
+int srl_per_add(srl_per_t* P, int64_t n, void* stream);                                  /* _add x n  (replay_buffer.py:318-322) */
+int srl_per_update_priorities(srl_per_t* P, const int64_t* idxs, const double* priorities, int64_t n, void* stream);   /* :346-351 */
+int srl_per_sample(srl_per_t* P, const double* uniforms, int batch, double beta, int64_t* idxs, double* weights64,
+                   float* weights32, void* stream);                                      /* :353-381, uniforms f64 [batch] in [0,1) */
+int srl_per_debug_trees(srl_per_t* P, double* sum_out, double* min_out, double* max_priority_out, void* stream);
+const char* srl_per_last_error(void);
+
 /* ---- trajectory ring -> time-major batch (the stacking step of ImpalaTrainer.get_batch, impala_atari.py:248-251) -----------
  * staging: B trajectory slots on the DEVICE, each one contiguous record of slot_bytes holding every key of create_buffers
  * (impala_atari.py:135-147) for T+1 steps; offsets6_host (HOST array) = byte offsets of {obs u8[T+1,4,84,84], reward f32[T+1],

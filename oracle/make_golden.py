@@ -157,6 +157,51 @@ def main():
     np.savez_compressed(os.path.join(out_dir, 'lstm_t4b3a6.npz'), **g)
     print('wrote lstm_t4b3a6 total_loss', total.item())
 
+    # ---------------- prioritized replay: the reference's own tree classes driven by the statements of
+    # PrioritizedReplayBuffer._add / update_priorities / _sample_proprtional / _calculate_weight (replay_buffer.py:318-381);
+    # `retrieve` (missing upstream) -> find_prefixsum_idx ----------------
+    seg = _load('ref_segment_tree', '/root/reference/scalerl/data/segment_tree.py')
+    per = {}
+    for ci, (mem, alpha, beta, nadd, batch, seed) in enumerate([(100, 0.6, 0.4, 100, 32, 0), (1000, 0.7, 0.5, 700, 64, 1), (64, 0.6, 1.0, 200, 16, 2)]):
+        cap = 1
+        while cap < mem:
+            cap *= 2
+        st, mt = seg.SumSegmentTree(cap), seg.MinSegmentTree(cap)
+        rng = np.random.RandomState(seed)
+        max_p, ptr, size = 1.0, 0, 0
+        for _ in range(nadd):
+            st[ptr] = max_p ** alpha
+            mt[ptr] = max_p ** alpha
+            ptr = (ptr + 1) % mem
+            size = min(size + 1, mem)
+        upd_idx = rng.randint(0, size, size=3 * batch)
+        upd_p = rng.rand(3 * batch) * 5 + 1e-3
+        for i, pr in zip(upd_idx, upd_p):
+            st[int(i)] = float(pr) ** alpha
+            mt[int(i)] = float(pr) ** alpha
+            max_p = max(max_p, float(pr))
+        for _ in range(5):                                   # adds after updates use the new max priority
+            st[ptr] = max_p ** alpha
+            mt[ptr] = max_p ** alpha
+            ptr = (ptr + 1) % mem
+            size = min(size + 1, mem)
+        u = rng.rand(batch)
+        p_total = st.sum(0, size - 1)
+        segment = p_total / batch
+        idxs = []
+        for i in range(batch):
+            a, b = segment * i, segment * (i + 1)
+            idxs.append(st.find_prefixsum_idx(a + (b - a) * float(u[i])))
+        p_min = mt.min() / st.sum()
+        max_w = (p_min * size) ** (-beta)
+        w = [((st[i] / st.sum()) * size) ** (-beta) / max_w for i in idxs]
+        per[f'c{ci}_meta'] = np.array([mem, alpha, beta, nadd, batch, seed, size, max_p], dtype=np.float64)
+        per[f'c{ci}_upd_idx'], per[f'c{ci}_upd_p'], per[f'c{ci}_u'] = upd_idx.astype(np.int64), upd_p, u
+        per[f'c{ci}_idxs'], per[f'c{ci}_w'] = np.array(idxs, dtype=np.int64), np.array(w, dtype=np.float64)
+        per[f'c{ci}_sum_root'], per[f'c{ci}_min_root'] = np.array([st.sum()]), np.array([mt.min()])
+    np.savez_compressed(os.path.join(out_dir, 'per_cases.npz'), **per)
+    print('wrote per_cases')
+
 
 if __name__ == '__main__':
     main()

@@ -45,6 +45,12 @@ _SIGS = {
     'srl_lstm_destroy': [_P],
     'srl_lstm_forward': [_P, _P, _P, _P, _P, _P, _P, _P, _P],
     'srl_lstm_backward': [_P, _P, _P, _P, _P],
+    'srl_per_create': [_L, C.c_double, C.POINTER(_P)],
+    'srl_per_destroy': [_P],
+    'srl_per_add': [_P, _L, _P],
+    'srl_per_update_priorities': [_P, _P, _P, _L, _P],
+    'srl_per_sample': [_P, _P, _I, C.c_double, _P, _P, _P, _P],
+    'srl_per_debug_trees': [_P, _P, _P, _P, _P],
     'srl_unpack_slots': [_P, _L, C.POINTER(_L), _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     'srl_grad_norm_clip_coef': [_P, _L, _F, _P, _P, _P],
     'srl_rmsprop_step': [_P, _P, _P, _L, _P, _F, _F, _F, _P],
@@ -58,7 +64,7 @@ _SIGS = {
     'srl_learner_profile_collect': [_P, _P],
     'srl_version': [],
 }
-EXPORTS = sorted(list(_SIGS) + ['srl_last_error', 'srl_param_layout', 'srl_param_layout_ex', 'srl_learner_workspace_bytes', 'srl_profile_slot_name', 'srl_lstm_last_error'])
+EXPORTS = sorted(list(_SIGS) + ['srl_last_error', 'srl_param_layout', 'srl_param_layout_ex', 'srl_learner_workspace_bytes', 'srl_profile_slot_name', 'srl_lstm_last_error', 'srl_per_last_error', 'srl_per_size', 'srl_per_capacity'])
 
 
 def lib():
@@ -78,6 +84,11 @@ def lib():
         L.srl_param_layout.argtypes = [_I, C.POINTER(_L), C.POINTER(_L)]
         L.srl_param_layout_ex.restype = C.c_int64
         L.srl_param_layout_ex.argtypes = [_I, _I, C.POINTER(_L), C.POINTER(_L)]
+        L.srl_per_last_error.restype = C.c_char_p
+        L.srl_per_last_error.argtypes = []
+        for nm in ('srl_per_size', 'srl_per_capacity'):
+            getattr(L, nm).restype = C.c_int64
+            getattr(L, nm).argtypes = [_P]
         L.srl_lstm_last_error.restype = C.c_char_p
         L.srl_lstm_last_error.argtypes = []
         L.srl_profile_slot_name.restype = C.c_char_p

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libscalerl_b200.so')
-SOURCES = ['api.cu', 'encoder.cu', 'vtrace.cu', 'heads_optim.cu', 'test_shift.cu', 'lstm.cu']
+SOURCES = ['api.cu', 'encoder.cu', 'vtrace.cu', 'heads_optim.cu', 'test_shift.cu', 'lstm.cu', 'per.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr']
 
