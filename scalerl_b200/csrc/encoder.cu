@@ -4,6 +4,7 @@
 #include "res_problems.cuh"
 #include "kernels.h"
 #include <initializer_list>
+#include <stdlib.h>
 
 namespace srl {
 
@@ -155,7 +156,18 @@ static cudaError_t launch_s2d(const uint8_t* obs, int frames, bf16* xs, cudaStre
   return cudaGetLastError();
 }
 
-constexpr int kPersistentCtas = 148;   // one persistent CTA per SM for the resident-window kernels
+// persistent CTAs of the resident-window kernels: one per SM by default; data-parallel runs leave a few SMs to the NCCL
+// all-reduce that overlaps the conv backward (SRL_PERSISTENT_CTAS, read once)
+static int persistent_ctas() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("SRL_PERSISTENT_CTAS");
+    v = e ? atoi(e) : 148;
+    if (v < 16 || v > 148) v = 148;
+  }
+  return v;
+}
+#define kPersistentCtas persistent_ctas()
 
 // workspace [tap-block][row][co] -> PyTorch-layout conv weight gradients (plain stores), and re-zero what was read
 __global__ void __launch_bounds__(256) conv_wgrad_finalize_kernel(float* __restrict__ ws, float* __restrict__ g1, float* __restrict__ g2,
