@@ -42,6 +42,17 @@ SRL_DEVINL void relu_mask16(const bf16* mask, float (&v)[16]) {
   }
 }
 
+// same with the 32 mask bytes already in registers (prefetched before the accumulator was waited for)
+SRL_DEVINL void relu_mask16_pre(const uint4 (&m)[2], float (&v)[16]) {
+  const uint32_t w[8] = {m[0].x, m[0].y, m[0].z, m[0].w, m[1].x, m[1].y, m[1].z, m[1].w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (!(bf16_lo(w[i]) > 0.f)) v[2 * i] = 0.f;
+    if (!(bf16_hi(w[i]) > 0.f)) v[2 * i + 1] = 0.f;
+  }
+}
+SRL_DEVINL void ld_mask16(const bf16* mask, uint4 (&m)[2]) { m[0] = ldg16(mask); m[1] = ldg16(mask + 8); }
+
 // ============================================================================================
 // plain GEMM problems used by the unit tests to validate descriptors / pipeline in isolation
 // ============================================================================================

@@ -116,18 +116,23 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int b = it & 1;
+      // global operands of the epilogue (ReLU masks of the dgrads) are requested BEFORE waiting for the accumulator, so
+      // their L2 latency overlaps the MMAs instead of being paid once per 16-column chunk
+      uint4 pre[P::BN / 16][2];
+#pragma unroll
+      for (int c = 0; c < P::BN / 16; ++c) P::prefetch16(p, t, tid, c * 16, pre[c]);
       mbar_wait(&acc_full[b], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16) + b * P::BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < P::BN; c0 += 16) {
+#pragma unroll
+      for (int c = 0; c < P::BN / 16; ++c) {
         uint32_t r[16];
-        tmem_ld16(lane_base + c0, r);
+        tmem_ld16(lane_base + c * 16, r);
         tmem_ld_wait();
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        P::epilogue16(p, t, tid, c0, v);
+        P::epilogue16(p, t, tid, c * 16, v, pre[c]);
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[b]);

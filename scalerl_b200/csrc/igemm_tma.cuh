@@ -130,12 +130,29 @@ __global__ void __launch_bounds__(IGT_THREADS) igemm_tma_kernel(const __grid_con
       umma_commit(done);
     }
   } else {
+    const int row = tid;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if constexpr (P::PREFETCH) {     // epilogue with global operands (ReLU mask): requested before the accumulator is waited for
+      uint4 pre[P::BN / 16][2];
+#pragma unroll
+      for (int c = 0; c < P::BN / 16; ++c) P::prefetch16(p, tm, ty, row, c * 16, pre[c]);
+      mbar_wait(done, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < P::BN / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(lane_base + c * 16, r);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        P::epilogue16(p, tm, ty, row, c * 16, v, pre[c]);
+      }
+    } else {
     if (nkb > 0) {
       mbar_wait(done, 0);
       tc_fence_after();
     }
-    const int row = tid;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int c0 = 0; c0 < P::BN; c0 += 16) {
       float v[16];
@@ -150,6 +167,7 @@ __global__ void __launch_bounds__(IGT_THREADS) igemm_tma_kernel(const __grid_con
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
       }
       P::epilogue16(p, tm, ty, row, c0, v);
+    }
     }
     tc_fence_before();
   }

@@ -19,7 +19,8 @@
 namespace srl {
 
 // ------------------------------------------------------------------------------------------------ generic GEMM problems
-struct LGemmK {      // C[c_row0 + m][n] = sum_k A[a_row0 + m][k] * B[n][k];  grid = (ceil(M/128), Npad/64)
+struct LGemmK {
+  static constexpr bool PREFETCH = false;      // C[c_row0 + m][n] = sum_k A[a_row0 + m][k] * B[n][k];  grid = (ceil(M/128), Npad/64)
   static constexpr int BN = 64, STAGES = 4, KROWS = 64;
   static constexpr bool A_MN = false, B_MN = false, ZERO_INIT = false;
   struct Params { SRL_TMAP a; SRL_TMAP b; float* C; int M, nkb, ldc, a_row0, c_row0; };
@@ -38,7 +39,8 @@ struct LGemmK {      // C[c_row0 + m][n] = sum_k A[a_row0 + m][k] * B[n][k];  gr
     for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
 };
-struct LGemmMN {     // C[i][j] = sum_r A[r][i] * B[r][j]  (rows r = samples, MN-major operands); grid = (Ipad/128, Jpad/64)
+struct LGemmMN {
+  static constexpr bool PREFETCH = false;     // C[i][j] = sum_r A[r][i] * B[r][j]  (rows r = samples, MN-major operands); grid = (Ipad/128, Jpad/64)
   static constexpr int BN = 64, STAGES = 4, KROWS = 64;
   static constexpr bool A_MN = true, B_MN = true, ZERO_INIT = false;
   struct Params { SRL_TMAP a; SRL_TMAP b; float* C; int R, ldc; };

@@ -24,7 +24,8 @@ struct RConv1Fwd {   // 2x2 s1 over xs (== 8x8 s4 over the frame): taps (kh2,kw2
   SRL_DEVINL static constexpr int tap_win(int) { return 0; }
   SRL_DEVINL static constexpr int tap_shift(int j) { return (j >> 1) * 21 + (j & 1); }
   SRL_DEVINL static void load_windows(const Params& p, int t, uint8_t* dst, int, uint64_t* bar) { tma_load_2d(dst, &p.in0, bar, 0, t * 128); }
-  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16]) {
+  SRL_DEVINL static void prefetch16(const Params&, int, int, int, uint4 (&)[2]) {}
+  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16], const uint4 (&)[2]) {
     const int Q = t * 128 + row, n = Q / 441, r = Q - n * 441, oh = r / 21, ow = r - oh * 21;
     if (n >= p.NF || oh >= 20 || ow >= 20) return;
 #pragma unroll
@@ -45,7 +46,8 @@ struct RConv2Fwd {   // 4x4 s2 over a1: tap j = (kh, kww): plane kh&1, shift (kh
     tma_load_2d(dst, &p.in0, bar, 0, t * 128);
     tma_load_2d(dst + win_bytes, &p.in1, bar, 0, t * 128);
   }
-  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16]) {
+  SRL_DEVINL static void prefetch16(const Params&, int, int, int, uint4 (&)[2]) {}
+  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16], const uint4 (&)[2]) {
     const int Q = t * 128 + row, n = Q / 100, r = Q - n * 100, oh = r / 10, ow = r - oh * 10;
     if (n >= p.NF || oh >= 9 || ow >= 9) return;
 #pragma unroll
@@ -62,7 +64,8 @@ struct RConv3Fwd {   // 3x3 s1 over a2: tap (kh,kw) -> shift kh*9 + kw
   SRL_DEVINL static constexpr int tap_win(int) { return 0; }
   SRL_DEVINL static constexpr int tap_shift(int j) { return (j / 3) * 9 + j % 3; }
   SRL_DEVINL static void load_windows(const Params& p, int t, uint8_t* dst, int, uint64_t* bar) { tma_load_2d(dst, &p.in0, bar, 0, t * 128); }
-  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16]) {
+  SRL_DEVINL static void prefetch16(const Params&, int, int, int, uint4 (&)[2]) {}
+  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16], const uint4 (&)[2]) {
     const int Q = t * 128 + row, n = Q / 81, r = Q - n * 81, oh = r / 9, ow = r - oh * 9;
     if (n >= p.NF || oh >= 7 || ow >= 7) return;
 #pragma unroll
@@ -80,10 +83,14 @@ struct RConv3Dgrad {   // da2[ih,iw] = sum_{kh,kw} da3g[(ih-kh),(iw-kw)] W3[:, :
   SRL_DEVINL static constexpr int tap_win(int) { return 0; }
   SRL_DEVINL static constexpr int tap_shift(int j) { return 20 - ((j / 3) * 9 + j % 3); }
   SRL_DEVINL static void load_windows(const Params& p, int t, uint8_t* dst, int, uint64_t* bar) { tma_load_2d(dst, &p.in0, bar, 0, t * 128 - 20); }
-  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16]) {
+  SRL_DEVINL static void prefetch16(const Params& p, int t, int row, int c0, uint4 (&m)[2]) {
+    const int Q = t * 128 + row;
+    if (Q < p.NB * 81) ld_mask16(p.act + (size_t)Q * 64 + c0, m);                  // a2 lives on the same 9x9 grid
+  }
+  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16], const uint4 (&m)[2]) {
     const int Q = t * 128 + row, n = Q / 81, r = Q - n * 81, ih = r / 9, iw = r - ih * 9;
     if (n >= p.NB) return;
-    relu_mask16(p.act + (size_t)Q * 64 + c0, v);                                   // a2 lives on the same 9x9 grid
+    relu_mask16_pre(m, v);
     store_bf16x16(p.dx + ((size_t)n * 100 + ih * 10 + iw) * 64 + c0, v);           // da2g: conv2's 10x10 grid
   }
 };
@@ -96,11 +103,15 @@ struct RConv2Dgrad {   // the 4 stride-parity classes share A (da2g at (i'-kh', 
   SRL_DEVINL static constexpr int tap_win(int) { return 0; }
   SRL_DEVINL static constexpr int tap_shift(int j) { return 11 - ((j >> 1) * 10 + (j & 1)); }
   SRL_DEVINL static void load_windows(const Params& p, int t, uint8_t* dst, int, uint64_t* bar) { tma_load_2d(dst, &p.in0, bar, 0, t * 128 - 11); }
-  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16]) {
+  SRL_DEVINL static void prefetch16(const Params& p, int t, int row, int c0, uint4 (&m)[2]) {
+    const int Q = t * 128 + row, cls = c0 >> 5, c = c0 & 31;
+    if (Q < p.NB * 100) ld_mask16(p.act + ((size_t)(cls >> 1) * p.NF * 100 + Q) * 64 + (cls & 1) * 32 + c, m);   // a1 plane ph, same row Q
+  }
+  SRL_DEVINL static void epilogue16(const Params& p, int t, int row, int c0, float (&v)[16], const uint4 (&m)[2]) {
     const int Q = t * 128 + row, n = Q / 100, r = Q - n * 100, i = r / 10, j = r - i * 10;
     if (n >= p.NB) return;
     const int cls = c0 >> 5, c = c0 & 31, ph = cls >> 1, pw = cls & 1;
-    relu_mask16(p.act + ((size_t)ph * p.NF * 100 + Q) * 64 + pw * 32 + c, v);     // a1 plane ph, same row Q
+    relu_mask16_pre(m, v);
     store_bf16x16(p.dx + ((size_t)n * 441 + (2 * i + ph) * 21 + 2 * j + pw) * 64 + c, v);   // da1g: conv1's 21x21 grid
   }
 };

@@ -9,7 +9,8 @@ namespace srl {
 #define SRL_TMAP alignas(64) CUtensorMap
 
 // ============================================================================================ fc
-struct TFcFwd {   // split-K partials; grid.y = 8 N-tiles x FC_SPLITS, ty = nt*FC_SPLITS + split
+struct TFcFwd {
+  static constexpr bool PREFETCH = false;   // split-K partials; grid.y = 8 N-tiles x FC_SPLITS, ty = nt*FC_SPLITS + split
   static constexpr int BN = 64, STAGES = 4, SPLITS = 4;
   static constexpr bool A_MN = false, B_MN = false, ZERO_INIT = false;
   static constexpr int KROWS = 64;
@@ -32,7 +33,8 @@ struct TFcFwd {   // split-K partials; grid.y = 8 N-tiles x FC_SPLITS, ty = nt*F
   }
 };
 
-struct TFcDgrad {   // da3[m][i] = (dh[m][:] . Wfc[:][i]) * (a3 > 0); grid = (ceil(M/128), 49)
+struct TFcDgrad {
+  static constexpr bool PREFETCH = true;   // da3[m][i] = (dh[m][:] . Wfc[:][i]) * (a3 > 0); grid = (ceil(M/128), 49)
   static constexpr int BN = 64, STAGES = 4;
   static constexpr bool A_MN = false, B_MN = false, ZERO_INIT = false;
   static constexpr int KROWS = 64;
@@ -44,10 +46,14 @@ struct TFcDgrad {   // da3[m][i] = (dh[m][:] . Wfc[:][i]) * (a3 > 0); grid = (ce
     tma_load_2d(sA, &p.dhm, bar, kb * 64, tm * 128);
     tma_load_2d(sB, &p.w, bar, kb * 64, ty * 64);
   }
-  SRL_DEVINL static void epilogue16(const Params& p, int tm, int ty, int row, int c0, float (&v)[16]) {
+  SRL_DEVINL static void prefetch16(const Params& p, int tm, int ty, int row, int c0, uint4 (&mk)[2]) {
+    const int m = tm * 128 + row;
+    if (m < p.M) ld_mask16(p.a3 + (size_t)m * 3136 + ty * 64 + c0, mk);
+  }
+  SRL_DEVINL static void epilogue16(const Params& p, int tm, int ty, int row, int c0, float (&v)[16], const uint4 (&mk)[2]) {
     const int m = tm * 128 + row;
     if (m >= p.M) return;
-    relu_mask16(p.a3 + (size_t)m * 3136 + ty * 64 + c0, v);
+    relu_mask16_pre(mk, v);
     // N-tile ty == one output pixel hw of conv3; da3g lives on conv3's 9x9 input grid (zeros outside the 7x7 outputs)
     store_bf16x16(p.da3 + ((size_t)m * 81 + (ty / 7) * 9 + ty % 7) * 64 + c0, v);
   }
@@ -58,7 +64,8 @@ SRL_DEVINL void fill_ones(uint8_t* dst, int bytes, int tid) {   // bf16 1.0 = 0x
   for (int i = tid; i < bytes / 16; i += IGT_THREADS) q[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
 }
 
-struct TFcWgrad {   // grid = (1, 4*50): ty = hw*4 + jt, hw == 49 is the ones slice (B = ones -> dbfc); stage = 64 frames
+struct TFcWgrad {
+  static constexpr bool PREFETCH = false;   // grid = (1, 4*50): ty = hw*4 + jt, hw == 49 is the ones slice (B = ones -> dbfc); stage = 64 frames
   static constexpr int BN = 64, STAGES = 4, KROWS = 64;
   static constexpr bool A_MN = true, B_MN = true, ZERO_INIT = true;
   struct Params { SRL_TMAP dhm; SRL_TMAP a3m; float* dw; float* db; int M; };
