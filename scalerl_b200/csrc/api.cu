@@ -267,8 +267,10 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   L->coef = (float*)q; q += sizes[i++];
   L->dstep = (int*)q; q += sizes[i++];
   L->buf.wgrad_ws = (float*)q; q += sizes[i++];
-  if (cudaStreamCreateWithFlags(&L->ss.side, cudaStreamNonBlocking) != cudaSuccess) L->ss.side = nullptr;
-  for (int e2 = 0; e2 < 8 && L->ss.side; ++e2)
+  if (cudaStreamCreateWithFlags(&L->ss.side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&L->ss.side2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&L->ss.side3, cudaStreamNonBlocking) != cudaSuccess) L->ss.side = nullptr;
+  for (int e2 = 0; e2 < 12 && L->ss.side; ++e2)
     if (cudaEventCreateWithFlags(&L->ss.ev[e2], cudaEventDisableTiming) != cudaSuccess) { L->ss.side = nullptr; }
   cudaGetLastError();
   {
@@ -307,8 +309,10 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
 extern "C" int srl_learner_destroy(srl_learner_t* L) {
   if (!L) return 0;
   for (int i = 0; i < 2 * PS_COUNT; ++i) if (L->events[i]) cudaEventDestroy(L->events[i]);
-  for (int i = 0; i < 8; ++i) if (L->ss.ev[i]) cudaEventDestroy(L->ss.ev[i]);
+  for (int i = 0; i < 12; ++i) if (L->ss.ev[i]) cudaEventDestroy(L->ss.ev[i]);
   if (L->ss.side) cudaStreamDestroy(L->ss.side);
+  if (L->ss.side2) cudaStreamDestroy(L->ss.side2);
+  if (L->ss.side3) cudaStreamDestroy(L->ss.side3);
   if (L->lstm) srl_lstm_destroy(L->lstm);
   if (L->lstm_arena) cudaFree(L->lstm_arena);
   cudaFree(L->arena);

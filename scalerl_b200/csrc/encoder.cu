@@ -212,33 +212,38 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
   if (frames <= 0) return cudaSuccess;
   if (mode != 0 || !maps.valid) return cudaErrorInvalidValue;
   const bool do_fc = phase != 1, do_conv = phase != 0;
-  // The wgrad GEMMs only feed the optimizer, so they run on a side stream beside the dgrad chain
-  // (dh -> da3 -> da2 -> da1).  With per-kernel profiling on everything stays on `st` so durations are clean.
+  // The wgrad GEMMs only feed the optimizer: each runs on its own side stream beside the dgrad chain
+  // (dh -> da3 -> da2 -> da1) and beside each other.  With per-kernel profiling on everything stays on `st`.
   const bool fork = ss.side != nullptr && !pf.on;
-  cudaStream_t sw = fork ? ss.side : st;
-  Profiler pw = pf; pw.st = sw;
+  cudaStream_t s1 = fork ? ss.side : st, s2 = fork ? ss.side2 : st, s3 = fork ? ss.side3 : st;
+  Profiler p1 = pf, p2 = pf, p3 = pf; p1.st = s1; p2.st = s2; p3.st = s3;
   if (do_fc) {
-    if (fork) { SRL_TRY(cudaEventRecord(ss.ev[0], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[0], 0)); }
+    if (fork) { SRL_TRY(cudaEventRecord(ss.ev[0], st)); SRL_TRY(cudaStreamWaitEvent(s1, ss.ev[0], 0)); }
     { TFcWgrad::Params q{maps.dhm64, maps.a3m64, g.wf, g.bf, frames};
-      pw.b(PS_FC_WGRAD); SRL_TRY(igemm_tma_launch<TFcWgrad>(q, dim3(1, 4 * 50), sw)); pw.e(PS_FC_WGRAD); }
+      p1.b(PS_FC_WGRAD); SRL_TRY(igemm_tma_launch<TFcWgrad>(q, dim3(1, 4 * 50), s1)); p1.e(PS_FC_WGRAD); }
     { TFcDgrad::Params q{maps.dhm128, maps.wfd, buf.a3, buf.da3, frames};
       pf.b(PS_FC_DGRAD); SRL_TRY(igemm_tma_launch<TFcDgrad>(q, dim3(cdiv(frames, 128), 49), st)); pf.e(PS_FC_DGRAD); }
-    if (fork && !do_conv) { SRL_TRY(cudaEventRecord(ss.ev[4], sw)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[4], 0)); }
+    if (fork) { SRL_TRY(cudaEventRecord(ss.ev[4], s1)); }
+    if (fork && !do_conv) { SRL_TRY(cudaStreamWaitEvent(st, ss.ev[4], 0)); }
   }
   if (!do_conv) return cudaSuccess;
-  if (fork) { SRL_TRY(cudaEventRecord(ss.ev[1], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[1], 0)); }
+  if (fork) { SRL_TRY(cudaEventRecord(ss.ev[1], st)); SRL_TRY(cudaStreamWaitEvent(s2, ss.ev[1], 0)); }
   { RConv3Wgrad::Params q{maps.a2_w, maps.da3g_b, buf.wgrad_ws + WS_W3, g.b3, frames * 81, 0};
-    pw.b(PS_CONV3_WGRAD); SRL_TRY(res_wgrad_launch<RConv3Wgrad>(q, 64, sw)); pw.e(PS_CONV3_WGRAD); }
+    p2.b(PS_CONV3_WGRAD); SRL_TRY(res_wgrad_launch<RConv3Wgrad>(q, 64, s2)); p2.e(PS_CONV3_WGRAD); }
   { RConv3Dgrad::Params q{maps.da3g_w, maps.w3d, buf.a2, buf.da2, frames};
     pf.b(PS_CONV3_DGRAD); SRL_TRY(res_fwd_launch<RConv3Dgrad>(q, cdiv(frames * 81, 128), kPersistentCtas, st)); pf.e(PS_CONV3_DGRAD); }
-  if (fork) { SRL_TRY(cudaEventRecord(ss.ev[2], st)); SRL_TRY(cudaStreamWaitEvent(sw, ss.ev[2], 0)); }
+  if (fork) { SRL_TRY(cudaEventRecord(ss.ev[2], st)); SRL_TRY(cudaStreamWaitEvent(s3, ss.ev[2], 0)); }
   { RConv2Wgrad::Params q{maps.a1p0_w, maps.a1p1_w, maps.da2g_b, buf.wgrad_ws + WS_W2, g.b2, frames * 100, 0};
-    pw.b(PS_CONV2_WGRAD); SRL_TRY(res_wgrad_launch<RConv2Wgrad>(q, 64, sw)); pw.e(PS_CONV2_WGRAD); }
+    p3.b(PS_CONV2_WGRAD); SRL_TRY(res_wgrad_launch<RConv2Wgrad>(q, 64, s3)); p3.e(PS_CONV2_WGRAD); }
   { RConv2Dgrad::Params q{maps.da2g_w, maps.w2d, buf.a1, buf.da1, frames, buf.NF};
     pf.b(PS_CONV2_DGRAD); SRL_TRY(res_fwd_launch<RConv2Dgrad>(q, cdiv(frames * 100, 128), kPersistentCtas, st)); pf.e(PS_CONV2_DGRAD); }
   { RConv1Wgrad::Params q{maps.xs_w, maps.da1g_b, buf.wgrad_ws + WS_W1, g.b1, frames * 441, 0};
     pf.b(PS_CONV1_WGRAD); SRL_TRY(res_wgrad_launch<RConv1Wgrad>(q, kPersistentCtas, st)); pf.e(PS_CONV1_WGRAD); }
-  if (fork) { SRL_TRY(cudaEventRecord(ss.ev[3], sw)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[3], 0)); }
+  if (fork) {      // join: fc wgrad (phase 2 only: phase 1 was joined by the caller of phase 0), conv3 wgrad, conv2 wgrad
+    if (do_fc) { SRL_TRY(cudaStreamWaitEvent(st, ss.ev[4], 0)); }
+    SRL_TRY(cudaEventRecord(ss.ev[3], s2)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[3], 0));
+    SRL_TRY(cudaEventRecord(ss.ev[7], s3)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[7], 0));
+  }
   pf.b(PS_WGRAD_FINALIZE);
   conv_wgrad_finalize_kernel<<<(36864 + 32768 + 8192 + 255) / 256, 256, 0, st>>>(buf.wgrad_ws, g.w1, g.w2, g.w3);
   SRL_TRY(cudaGetLastError());

@@ -20,8 +20,10 @@ struct Profiler {
 };
 // second stream + fork/join events: the wgrad GEMMs run beside the dgrad chain (also under stream capture)
 struct SideStream {
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t side = nullptr;      // fc wgrad, weight re-pack
+  cudaStream_t side2 = nullptr;     // conv3 wgrad
+  cudaStream_t side3 = nullptr;     // conv2 wgrad
+  cudaEvent_t ev[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // ---- vtrace.cu
