@@ -211,6 +211,8 @@ int srl_test_gemm_mnmajor(const void* At, const void* Bt, float* D, int M, int N
  * kmajor (mn_major=0): A bf16 [160,64], B bf16 [64,64]  -> D[128,64] = A[shift:shift+128] . B^T
  * mnmajor (=1)       : A bf16 [96,128], B bf16 [96,64]  -> D[128,64] = A[shift:shift+64]^T . B[shift:shift+64]   (shift <= 32) */
 int srl_test_shifted_operand(const void* A, const void* B, float* D, int shift, int mn_major, int base_offset_mode, void* stream);
+/* test utility: fills the shared memory of every SM with quiet-NaN bit patterns (kernels must never depend on stale smem) */
+int srl_test_poison_smem(void* stream);
 
 #ifdef __cplusplus
 }

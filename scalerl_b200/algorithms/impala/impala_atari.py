@@ -21,6 +21,7 @@ Actors stay ordinary Python processes running a CPU policy.  Inside ScaleRL they
 """
 from __future__ import annotations
 
+import math
 import os
 import time
 import timeit
@@ -218,9 +219,9 @@ class ImpalaTrainer:
         buffers = buffers or self.buffers
         if lock is not None:
             with lock:
-                indices = [full_queue.get() for _ in range(self.args.batch_size)]
+                indices = [self._dequeue(full_queue) for _ in range(self.args.batch_size)]
         else:
-            indices = [full_queue.get() for _ in range(self.args.batch_size)]
+            indices = [self._dequeue(full_queue) for _ in range(self.args.batch_size)]
         s = self._slot
         self._slot ^= 1
         dst = self._dev_batches[s]
@@ -251,10 +252,30 @@ class ImpalaTrainer:
         self._cur_slot = s
         return dst, tuple()
 
+    def _dequeue(self, full_queue):
+        """full_queue.get() that notices dead actors: the reference blocks forever when an actor process has died
+        (impala_atari.py:238-241); here a crashed actor surfaces as an error in the learner instead of a hang."""
+        actors = getattr(self, '_actors', None)
+        if not actors:
+            return full_queue.get()
+        while full_queue.empty():
+            dead = [p.name for p in actors if not p.is_alive()]
+            if dead:
+                raise RuntimeError(f'actor process(es) exited while the learner was waiting for trajectories: {dead}')
+            time.sleep(0.0005)
+        return full_queue.get()
+
     def learn(self, actor_model, learner_model, batch, initial_rnn_state=(), lock=None) -> Dict[str, Any]:
         """impala_atari.py:270-349.  ``learner_model`` is ignored (the learner state lives in B200ImpalaLearner)."""
         self._ensure_learner()
         stats = self.learner.learn(batch)
+        if not math.isfinite(stats['total_loss']):          # never publish poisoned weights to the actors
+            raise FloatingPointError(f'non-finite learner loss: {stats}')
+        if os.environ.get('SRL_CHECK_FINITE'):               # debugging aid: name the first poisoned tensors
+            bad_p = [n for n, v in self.learner.params.items() if not bool(torch.isfinite(v).all())]
+            bad_g = [n for n, v in self.learner.grads.items() if not bool(torch.isfinite(v).all())]
+            if bad_p or bad_g:
+                raise FloatingPointError(f'step {self.learner.global_step}: non-finite params {bad_p} grads {bad_g} stats {stats}')
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.learner.device))
         if getattr(self, '_cur_slot', None) is not None:
@@ -295,6 +316,7 @@ class ImpalaTrainer:
                                   args=(i, free_queue, full_queue, self.actor_model, self.buffers, self.rnn_state_buffers))
             p.start()
             actors.append(p)
+        self._actors = actors
         for m in range(self.args.num_buffers):
             free_queue.put(m)
         timer = timeit.default_timer
@@ -303,6 +325,7 @@ class ImpalaTrainer:
         try:
             self.learn_process(0, self.actor_model, None, free_queue, full_queue, self.buffers, self.rnn_state_buffers, None)
         finally:
+            self._actors = None
             for _ in range(self.args.num_actors):
                 free_queue.put(None)
             for p in actors:

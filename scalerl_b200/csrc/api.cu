@@ -109,6 +109,10 @@ extern "C" int srl_test_shifted_operand(const void* A, const void* B, float* D, 
   CU(test_shift(A, B, D, shift, mn_major, base_offset_mode, (cudaStream_t)stream), "test_shifted_operand");
   return 0;
 }
+extern "C" int srl_test_poison_smem(void* stream) {
+  CU(test_poison_smem((cudaStream_t)stream), "test_poison_smem");
+  return 0;
+}
 extern "C" int srl_test_gemm_mnmajor(const void* At, const void* Bt, float* D, int M, int N, int K, int simt, void* stream) {
   REQ(At && Bt && D && M > 0 && N > 0 && K > 0 && M % 128 == 0 && N % 64 == 0, "test_gemm_mnmajor: need M%%128==0, N%%64==0");
   CU(test_gemm(At, Bt, D, M, N, K, true, simt != 0, (cudaStream_t)stream), "test_gemm_mnmajor");
@@ -337,18 +341,36 @@ extern "C" int srl_learner_pack_weights(srl_learner_t* L, void* stream) {
   return 0;
 }
 
-static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStream_t st) {
+static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStream_t st, bool zero_small_grads = false) {
   L->pf.st = st;
   // The bf16 operand copies are re-derived from the fp32 master weights at the START of every forward (not at the end
   // of the optimizer step): the pack kernel runs on the side stream underneath the frame conversion.
   cudaEvent_t packed = nullptr;
+  if (zero_small_grads && (side_mode() & 4)) {
+    int64_t off[12], cnt[12];
+    layout(L->cfg.A, off, cnt);
+    CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), st), "zero small grads");
+    zero_small_grads = false;
+  }
   if (L->ss.side && !L->pf.on) {
     CU(cudaEventRecord(L->ss.ev[5], st), "fork pack");
     CU(cudaStreamWaitEvent(L->ss.side, L->ss.ev[5], 0), "fork pack");
+    if (zero_small_grads) {   // the accumulated gradient segments (everything before fc.weight) are cleared under the frame conversion
+      int64_t off[12], cnt[12];
+      layout(L->cfg.A, off, cnt);
+      CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), L->ss.side), "zero small grads");
+    }
     CU(launch_pack_weights(L->P, L->buf.wpack, L->ss.side), "pack_weights");
     CU(cudaEventRecord(L->ss.ev[6], L->ss.side), "join pack");
     packed = L->ss.ev[6];
   } else {
+    if (zero_small_grads) {
+      int64_t off[12], cnt[12];
+      layout(L->cfg.A, off, cnt);
+      L->pf.b(PS_ZERO_GRADS);
+      CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), st), "zero small grads");
+      L->pf.e(PS_ZERO_GRADS);
+    }
     L->pf.b(PS_PACK);
     CU(launch_pack_weights(L->P, L->buf.wpack, st), "pack_weights");
     L->pf.e(PS_PACK);
@@ -358,9 +380,9 @@ static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStrea
 }
 
 static int forward_impl(srl_learner* L, const uint8_t* obs, const float* reward, const int64_t* action, int frames, float* logits,
-                        float* baseline, cudaStream_t st) {
+                        float* baseline, cudaStream_t st, bool zero_small_grads = false) {
   REQ(!L->cfg.use_lstm, "this learner was created with use_lstm=1: call the *_lstm entry points");
-  int rc = encode_impl(L, obs, frames, st);
+  int rc = encode_impl(L, obs, frames, st, zero_small_grads);
   if (rc) return rc;
   L->pf.b(PS_HEAD_FWD);
   CU(launch_head_fwd(L->buf.hpart, FC_SPLITS, L->P.bf, L->buf.h, reward, action, L->P.wp, L->P.bp, L->P.wb, L->P.bb, frames, L->cfg.A,
@@ -381,23 +403,21 @@ static int fb_begin(srl_learner* L, const uint8_t* obs, const float* reward, con
                     const float* behavior_logits, float* losses, float* vs, float* pg_advantages, cudaStream_t st, int phase) {
   const srl_config_t& c = L->cfg;
   const int NF = (c.T + 1) * c.B, NB = c.T * c.B;
-  int rc = forward_impl(L, obs, reward, action, NF, L->logits, L->baseline, st);
+  int rc = forward_impl(L, obs, reward, action, NF, L->logits, L->baseline, st, true);
   if (rc) return rc;
   L->pf.b(PS_TAIL);
   CU(launch_impala_tail(behavior_logits, L->logits, L->baseline, action, reward, done, c.T, c.B, c.A, c.discounting,
                         c.reward_clip_abs_one, c.clip_rho_threshold, c.clip_pg_rho_threshold, c.baseline_cost, c.entropy_cost, vs,
                         pg_advantages, L->dlogits, L->dbaseline, losses, L->scratch, st), "impala_tail");
   L->pf.e(PS_TAIL);
-  L->pf.b(PS_ZERO_GRADS);
-  {  // fc.weight (95 % of the buffer) is stored whole by the fc wgrad GEMM; only the atomically accumulated segments are cleared
-    int64_t off[12], cnt[12];
-    layout(c.A, off, cnt);
-    CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), st), "zero small grads");   // everything before fc.weight
-  }
-  L->pf.e(PS_ZERO_GRADS);
   L->pf.b(PS_HEAD_BWD);
-  CU(launch_head_bwd(L->dlogits, L->dbaseline, L->buf.h, reward, action, L->P.wp, L->P.wb, NB, c.A, L->buf.dh, L->G.wp, L->G.bp, L->G.wb,
-                     L->G.bb, st), "head_bwd");
+  {
+    const bool fork = L->ss.side != nullptr && !L->pf.on && !(side_mode() & 2);
+    cudaStream_t sw = fork ? L->ss.side : st;
+    if (fork) { CU(cudaEventRecord(L->ss.ev[8], st), "fork head wgrad"); CU(cudaStreamWaitEvent(sw, L->ss.ev[8], 0), "fork head wgrad"); }
+    CU(launch_head_bwd(L->dlogits, L->dbaseline, L->buf.h, reward, action, L->P.wp, L->P.wb, NB, c.A, L->buf.dh, L->G.wp, L->G.bp, L->G.wb,
+                       L->G.bb, st, sw), "head_bwd");      // side stream `side` is joined by encoder_backward (after the fc wgrad)
+  }
   L->pf.e(PS_HEAD_BWD);
   CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.simt_mainloop, st, L->pf, L->ss, phase), "encoder_backward");
   L->have_fwd = true;

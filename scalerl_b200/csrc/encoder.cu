@@ -206,6 +206,11 @@ cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, 
   return cudaSuccess;
 }
 
+int side_mode() {
+  static const int m = [] { const char* e = getenv("SRL_SIDE_MODE"); return e ? atoi(e) : 0; }();
+  return m;
+}
+
 cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
                              cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase) {
   (void)obs;
@@ -215,7 +220,8 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
   // The wgrad GEMMs only feed the optimizer: each runs on its own side stream beside the dgrad chain
   // (dh -> da3 -> da2 -> da1) and beside each other.  With per-kernel profiling on everything stays on `st`.
   const bool fork = ss.side != nullptr && !pf.on;
-  cudaStream_t s1 = fork ? ss.side : st, s2 = fork ? ss.side2 : st, s3 = fork ? ss.side3 : st;
+  const bool one_side = (side_mode() & 1) != 0;      // diagnostic: all wgrads serial on one side stream
+  cudaStream_t s1 = fork ? ss.side : st, s2 = fork ? (one_side ? ss.side : ss.side2) : st, s3 = fork ? (one_side ? ss.side : ss.side3) : st;
   Profiler p1 = pf, p2 = pf, p3 = pf; p1.st = s1; p2.st = s2; p3.st = s3;
   if (do_fc) {
     if (fork) { SRL_TRY(cudaEventRecord(ss.ev[0], st)); SRL_TRY(cudaStreamWaitEvent(s1, ss.ev[0], 0)); }

@@ -80,9 +80,9 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict
   const int j = blockIdx.x * 128 + threadIdx.x;
   const int CORE = 513 + A;
   const int n0 = blockIdx.y * HEAD_SLAB, cnt = min(HEAD_SLAB, N - n0);
-  for (int i = threadIdx.x; i < cnt * (A + 1); i += 128) {
+  for (int i = threadIdx.x; i < HEAD_SLAB * (A + 1); i += 128) {   // rows past the ragged end are ZERO (0 * stale smem could be NaN)
     const int r = i / (A + 1), a = i - r * (A + 1);
-    sd[r][a] = a < A ? __ldg(dlogits + (size_t)(n0 + r) * A + a) : __ldg(dbaseline + n0 + r);
+    sd[r][a] = r < cnt ? (a < A ? __ldg(dlogits + (size_t)(n0 + r) * A + a) : __ldg(dbaseline + n0 + r)) : 0.f;
   }
   if (threadIdx.x < cnt) {
     sr[threadIdx.x] = fminf(fmaxf(__ldg(reward + n0 + threadIdx.x), -1.f), 1.f);
@@ -247,9 +247,9 @@ __global__ void __launch_bounds__(128) head_dense_bwd_kernel(const float* __rest
   __shared__ float sd[16][HEAD_MAX_A + 1];
   const int H = 513 + A, j = blockIdx.x * 128 + threadIdx.x;
   const int n0 = blockIdx.y * 16, cnt = min(16, N - n0);
-  for (int i = threadIdx.x; i < cnt * (A + 1); i += 128) {
+  for (int i = threadIdx.x; i < HEAD_SLAB * (A + 1); i += 128) {   // rows past the ragged end are ZERO (0 * stale smem could be NaN)
     const int r = i / (A + 1), a = i - r * (A + 1);
-    sd[r][a] = a < A ? __ldg(dlogits + (size_t)(n0 + r) * A + a) : __ldg(dbaseline + n0 + r);
+    sd[r][a] = r < cnt ? (a < A ? __ldg(dlogits + (size_t)(n0 + r) * A + a) : __ldg(dbaseline + n0 + r)) : 0.f;
   }
   __syncthreads();
   if (j > H) return;
@@ -343,12 +343,13 @@ cudaError_t launch_head_fwd(const float* hpart, int nsplit, const float* bfc, fl
 }
 cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const float* h, const float* reward, const int64_t* action,
                             const float* Wp, const float* Wb, int N, int A, __nv_bfloat16* dh, float* gWp, float* gbp, float* gWb,
-                            float* gbb, cudaStream_t st) {
+                            float* gbb, cudaStream_t st, cudaStream_t st_wgrad) {
   if (N <= 0) return cudaSuccess;
   head_bwd_dh_kernel<<<dim3(N, 4), 128, 0, st>>>(dlogits, dbaseline, h, Wp, Wb, N, A, dh);
   const int CORE = 513 + A;
-  head_wgrad_kernel<<<dim3((CORE + 1 + 127) / 128, (N + HEAD_SLAB - 1) / HEAD_SLAB), 128, 0, st>>>(dlogits, dbaseline, h, reward, action, N, A,
-                                                                                                       HEAD_SLAB, gWp, gbp, gWb, gbb);
+  // the head weight gradients only feed the optimizer: they may run on a side stream (st_wgrad) beside the fc backward
+  head_wgrad_kernel<<<dim3((CORE + 1 + 127) / 128, (N + HEAD_SLAB - 1) / HEAD_SLAB), 128, 0, st_wgrad>>>(dlogits, dbaseline, h, reward, action, N, A,
+                                                                                                             HEAD_SLAB, gWp, gbp, gWb, gbb);
   return cudaGetLastError();
 }
 cudaError_t launch_grad_norm(const float* g, int64_t n, float max_norm, float* coef, float* scratch, cudaStream_t st) {

@@ -19,6 +19,8 @@ struct Profiler {
   void e(int slot) const { if (on) cudaEventRecord(ev[2 * slot + 1], st); }
 };
 // second stream + fork/join events: the wgrad GEMMs run beside the dgrad chain (also under stream capture)
+int side_mode();   // SRL_SIDE_MODE diagnostic bitmask: 1 = one wgrad side stream, 2 = head wgrad on the main stream, 4 = grad memset on the main stream
+
 struct SideStream {
   cudaStream_t side = nullptr;      // fc wgrad, weight re-pack
   cudaStream_t side2 = nullptr;     // conv3 wgrad
@@ -45,7 +47,7 @@ cudaError_t launch_head_fwd(const float* hpart, int nsplit, const float* bfc, fl
                             float* baseline, cudaStream_t st);
 cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const float* h, const float* reward, const int64_t* action,
                             const float* Wp, const float* Wb, int N, int A, __nv_bfloat16* dh, float* gWp, float* gbp, float* gWb,
-                            float* gbb, cudaStream_t st);
+                            float* gbb, cudaStream_t st, cudaStream_t st_wgrad);
 cudaError_t launch_core_build(const float* hpart, int nsplit, const float* bfc, const float* reward, const int64_t* action, int N, int A, float* h,
                               float* core, cudaStream_t st);
 cudaError_t launch_head_dense_fwd(const float* X, const float* Wp, const float* bp, const float* Wb, const float* bb, int N, int A, float* logits,
@@ -110,6 +112,7 @@ cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, 
 cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
                              cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase);
 cudaError_t test_shift(const void* A, const void* B, float* D, int shift, int mn_major, int bo_mode, cudaStream_t st);
+cudaError_t test_poison_smem(cudaStream_t st);
 cudaError_t test_gemm(const void* A, const void* B, float* D, int M, int N, int K, bool mn_major, bool simt, cudaStream_t st);
 
 }  // namespace srl

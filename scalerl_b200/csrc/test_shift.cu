@@ -90,4 +90,20 @@ cudaError_t test_shift(const void* A, const void* B, float* D, int shift, int mn
   return cudaGetLastError();
 }
 
+// Test utility: leave NaN bit patterns in (almost) all shared memory of every SM, so that a kernel which multiplies
+// stale shared memory by zero (instead of never reading it) shows up as NaN in the parity tests.
+__global__ void poison_smem_kernel(uint32_t pattern) {
+  extern __shared__ uint32_t poison[];
+  for (int i = threadIdx.x; i < (200 * 1024) / 4; i += blockDim.x) poison[i] = pattern;
+  __syncthreads();
+  if (poison[(threadIdx.x * 37) % 1024] != pattern) __trap();    // keep the stores alive
+}
+cudaError_t test_poison_smem(cudaStream_t st) {
+  const int smem = 200 * 1024;
+  cudaError_t e = cudaFuncSetAttribute(poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  poison_smem_kernel<<<148 * 2, 256, smem, st>>>(0x7FC00000u);
+  return cudaGetLastError();
+}
+
 }  // namespace srl

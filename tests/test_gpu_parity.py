@@ -260,6 +260,28 @@ def test_learn_step_vs_emulating_oracle(T, B, optimizer):
                 opt[name][k].copy_(d[k].cpu())
 
 
+@pytest.mark.parametrize('T,B', [(5, 4), (3, 7), (1, 1)])
+def test_learn_step_ignores_stale_shared_memory(T, B):
+    """Ragged frame counts (T*B not a multiple of any tile/slab) after every SM's shared memory was filled with NaN
+    patterns: the gradients must be finite and equal those of a run on clean shared memory up to the summation
+    order of the atomics (regression: 0 * stale-smem in the head weight-gradient slab)."""
+    from scalerl_b200 import _lib
+    A = 6
+    batch = {k: dev(v) for k, v in O.synthetic_batch(T, B, A, seed=77, done_p=0.2).items()}
+    grads = []
+    for poison in (False, True):
+        L, _ = _learner(T, B, A, 4)
+        for _ in range(3):                      # eager, capture, replay
+            if poison:
+                _lib.check(_lib.lib().srl_test_poison_smem(None))
+                torch.cuda.synchronize()
+            L.learn(batch)
+        g = L.flat_grads.clone()
+        assert bool(torch.isfinite(g).all()) and bool(torch.isfinite(L.flat_params).all())
+        grads.append(g)
+    assert rel_l2(grads[1].cpu(), grads[0].cpu()) < 1e-5
+
+
 @pytest.mark.parametrize('name', ['t5b4a6', 't3b5a4'])
 def test_learn_step_vs_reference_goldens(name):
     g = np.load(os.path.join(GOLDEN, f'learn_{name}.npz'))
