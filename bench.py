@@ -38,6 +38,15 @@ POOL = 8   # distinct batches cycled through: 8 x 19.5 MB = 156 MB > 126 MB L2, 
 
 # algorithmic MACs per frame: conv1, conv2, conv3, fc
 MACS = {'conv1': 3276800, 'conv2': 2654208, 'conv3': 1806336, 'fc': 1605632}
+# Algorithmic HBM bytes per frame of each GEMM kernel: every operand read once and every result written once at the
+# storage precision (bf16 activations / gradients; xs = space-to-depth frame 21x21x64, a1 20x20x32, a2 9x9x64,
+# a3 7x7x64, h 512).  The dgrads also read the forward activation for the ReLU mask.  (fixed bytes: weights.)
+_XS, _A1, _A2, _A3, _H = 28224 * 2, 12800 * 2, 5184 * 2, 3136 * 2, 512 * 2
+SLOT_BYTES = {   # slot -> (bytes per frame, fixed bytes per launch)
+    'conv1_fwd': (_XS + _A1, 8192 * 2), 'conv2_fwd': (_A1 + _A2, 32768 * 2), 'conv3_fwd': (_A2 + _A3, 36864 * 2),
+    'fc_fwd': (_A3 + 512 * 4, 1605632 * 2), 'fc_dgrad': (_H + 2 * _A3, 1605632 * 2), 'fc_wgrad': (_H + _A3, 1605632 * 4),
+    'conv3_dgrad': (_A3 + 2 * _A2, 36864 * 2), 'conv3_wgrad': (_A2 + _A3, 36864 * 4),
+    'conv2_dgrad': (_A2 + 2 * _A1, 32768 * 2), 'conv2_wgrad': (_A1 + _A2, 32768 * 4), 'conv1_wgrad': (_XS + _A1, 8192 * 4)}
 SLOT_FLOPS = {  # slot -> (MACs per frame, frames = 'fwd' (T+1)*B or 'bwd' T*B)
     'conv1_fwd': ('conv1', 'fwd'), 'conv2_fwd': ('conv2', 'fwd'), 'conv3_fwd': ('conv3', 'fwd'), 'fc_fwd': ('fc', 'fwd'),
     'fc_wgrad': ('fc', 'bwd'), 'fc_dgrad': ('fc', 'bwd'), 'conv3_wgrad': ('conv3', 'bwd'), 'conv3_dgrad': ('conv3', 'bwd'),
@@ -349,10 +358,15 @@ def _main(real_stdout):
     pk = peaks()
     NF, NBk = (T + 1) * B, T * B
     gemm = {}
+    ridge = pk['bf16_tflops'] * 1e12 / (pk['hbm_gbs'] * 1e9)         # flop/byte above which a kernel can be tensor-bound
     for slot, (layer, which) in SLOT_FLOPS.items():
-        fl = 2.0 * MACS[layer] * (NF if which == 'fwd' else NBk)
+        nfr = NF if which == 'fwd' else NBk
+        fl = 2.0 * MACS[layer] * nfr
+        by = SLOT_BYTES[slot][0] * nfr + SLOT_BYTES[slot][1]
         ms = per_kernel_ms[slot]
-        gemm[slot] = {'ms': ms, 'gflop': fl / 1e9, 'tflops': fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
+        gemm[slot] = {'ms': ms, 'gflop': fl / 1e9, 'tflops': fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, 'bytes': by,
+                      'gbs': by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0, 'intensity': fl / by,
+                      'bound': 'tensor' if fl / by >= ridge else 'hbm'}
     dom = max(gemm, key=lambda s: gemm[s]['ms'])
     traffic, traffic_src, tensor_pct = None, None, None
     tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
@@ -367,15 +381,25 @@ def _main(real_stdout):
         Hh = 513 + A
         step_flops += NF * 2 * (2 * 2 * 4 * Hh * Hh) + NBk * 2 * 2 * (2 * 2 * 4 * Hh * Hh)
     sum_kernel_ms = sum(per_kernel_ms.values())
-    roofline = {'bound': 'tensor', 'kernel': dom, 'achieved': gemm[dom]['tflops'], 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s',
-                'frac': gemm[dom]['tflops'] / pk['bf16_tflops'], 'traffic': traffic, 'traffic_unit': 'bytes (dram read+write per launch)',
-                'traffic_source': traffic_src, 'ncu_tensor_pipe_active_pct': tensor_pct, 'peak_source': pk['source'] + ' burst bf16 (MEASURED_PEAKS.json)',
-                'flops_per_launch': gemm[dom]['gflop'] * 1e9, 'ms_per_launch': gemm[dom]['ms'],
+    d = gemm[dom]
+    hbm_bound = d['bound'] == 'hbm'
+    roofline = {'bound': d['bound'], 'kernel': dom,
+                'achieved': d['gbs'] if hbm_bound else d['tflops'], 'peak': pk['hbm_gbs'] if hbm_bound else pk['bf16_tflops'],
+                'unit': 'GB/s' if hbm_bound else 'TFLOP/s',
+                'frac': d['gbs'] / pk['hbm_gbs'] if hbm_bound else d['tflops'] / pk['bf16_tflops'],
+                'traffic': traffic, 'traffic_unit': 'bytes (dram read+write per launch)',
+                'traffic_source': traffic_src, 'ncu_tensor_pipe_active_pct': tensor_pct,
+                'peak_source': pk['source'] + (' HBM copy bandwidth' if hbm_bound else ' burst bf16') + ' (MEASURED_PEAKS.json)',
+                'bound_why': f"arithmetic intensity {d['intensity']:.0f} flop/B (algorithmic) vs ridge {ridge:.0f} flop/B "
+                             f"(measured bf16 peak / measured HBM peak)",
+                'algorithmic_bytes_per_launch': d['bytes'], 'flops_per_launch': d['gflop'] * 1e9, 'ms_per_launch': d['ms'],
+                'tensor_view': {'achieved_tflops': d['tflops'], 'frac_of_bf16_peak': d['tflops'] / pk['bf16_tflops']},
                 'how': f'CUDA events around each launch on the launch stream, mean of {nprof} steps after the timed region',
                 'step': {'gflop': step_flops / 1e9, 'tflops_device_resident': step_flops / (ms_total / K * 1e-3) / 1e12,
                          'frac_of_peak': step_flops / (ms_total / K * 1e-3) / 1e12 / pk['bf16_tflops'], 'sum_kernel_ms': sum_kernel_ms},
                 'per_kernel_ms': {k: round(v, 5) for k, v in per_kernel_ms.items()},
-                'per_gemm_tflops': {k: round(v['tflops'], 2) for k, v in gemm.items()}}
+                'per_gemm': {k: {'tflops': round(v['tflops'], 1), 'gbs': round(v['gbs'], 0), 'flop_per_byte': round(v['intensity'], 0),
+                                 'bound': v['bound']} for k, v in gemm.items()}}
 
     # ---------------- stand-alone V-trace kernel: GB/s vs measured HBM peak (BASELINE.json metric, second half) ----------------
     vtrace = None
@@ -425,7 +449,7 @@ def _main(real_stdout):
                'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': feeder.h2d_bytes, 'd2h_bytes_per_step': feeder.d2h_bytes,
                        'ms_per_step': e2e_s / K * 1e3, 'api': 'HostBatchFeeder.submit/learn/result + B200ImpalaLearner.learn (pinned host batches)',
                        'last_total_loss': stats['total_loss'], 'h2d_only_ms_per_step': h2d_only_ms, 'eager_launch_ms_per_step': e2e_eager_ms},
-               'gpu_launches': 20 * K, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'losses_finite': losses_finite,
+               'gpu_launches': 19 * K, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'losses_finite': losses_finite,
                'vtrace_standalone': vtrace}
         emit(real_stdout, out)
     learner.release_graphs()

@@ -213,6 +213,8 @@ int srl_test_gemm_mnmajor(const void* At, const void* Bt, float* D, int M, int N
 int srl_test_shifted_operand(const void* A, const void* B, float* D, int shift, int mn_major, int base_offset_mode, void* stream);
 /* test utility: fills the shared memory of every SM with quiet-NaN bit patterns (kernels must never depend on stale smem) */
 int srl_test_poison_smem(void* stream);
+/* test utility: programmatic-dependent-launch self test; every out[0..nblk) must read 1 (flag, out: device int buffers) */
+int srl_test_pdl(int* flag, int* out, int nblk, unsigned delay_ns, void* stream);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,7 @@ _SIGS = {
     'srl_test_gemm_mnmajor': [_P, _P, _P, _I, _I, _I, _I, _P],
     'srl_test_shifted_operand': [_P, _P, _P, _I, _I, _I, _P],
     'srl_test_poison_smem': [_P],
+    'srl_test_pdl': [_P, _P, _I, C.c_uint, _P],
     'srl_memcpy_d2d': [_P, _P, _L, _P],
     'srl_learner_set_profiling': [_P, _I],
     'srl_profile_slot_count': [],

@@ -9,7 +9,8 @@ CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libscalerl_b200.so')
 SOURCES = ['api.cu', 'encoder.cu', 'vtrace.cu', 'heads_optim.cu', 'test_shift.cu', 'lstm.cu', 'per.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr']
+              '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr'] + \
+             [f'-D{d}' for d in os.environ.get('SRL_DEFINES', '').split(',') if d]       # e.g. SRL_DEFINES=SRL_DEBUG_BIAS_REREAD (debug builds)
 
 
 def _nvcc():

@@ -109,6 +109,11 @@ extern "C" int srl_test_shifted_operand(const void* A, const void* B, float* D, 
   CU(test_shift(A, B, D, shift, mn_major, base_offset_mode, (cudaStream_t)stream), "test_shifted_operand");
   return 0;
 }
+extern "C" int srl_test_pdl(int* flag, int* out, int nblk, unsigned delay_ns, void* stream) {
+  REQ(flag && out && nblk > 0, "test_pdl: bad argument");
+  CU(test_pdl(flag, out, nblk, delay_ns, (cudaStream_t)stream), "test_pdl");
+  return 0;
+}
 extern "C" int srl_test_poison_smem(void* stream) {
   CU(test_poison_smem((cudaStream_t)stream), "test_poison_smem");
   return 0;
@@ -341,8 +346,22 @@ extern "C" int srl_learner_pack_weights(srl_learner_t* L, void* stream) {
   return 0;
 }
 
+namespace srl {
+static bool g_pdl_on = true;
+bool pdl_active() {
+  static const bool env_on = [] { const char* e = getenv("SRL_PDL"); return !e || atoi(e) != 0; }();
+  return env_on && g_pdl_on;
+}
+void pdl_set_active(bool on) { g_pdl_on = on; }
+int pdl_skip_mask() {
+  static const int m = [] { const char* e = getenv("SRL_PDL_MASK"); return e ? atoi(e) : 0; }();
+  return m;
+}
+}  // namespace srl
+
 static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStream_t st, bool zero_small_grads = false) {
   L->pf.st = st;
+  pdl_set_active(!L->pf.on);
   // The bf16 operand copies are re-derived from the fp32 master weights at the START of every forward (not at the end
   // of the optimizer step): the pack kernel runs on the side stream underneath the frame conversion.
   cudaEvent_t packed = nullptr;
@@ -503,16 +522,15 @@ extern "C" int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_ou
   cudaStream_t st = (cudaStream_t)stream;
   const srl_config_t& c = L->cfg;
   L->pf.st = st;
-  L->pf.b(PS_GRAD_NORM);
-  CU(launch_grad_norm(L->grads, L->nparams, c.max_grad_norm, L->coef, L->scratch + 2048, st), "grad_norm");
-  L->pf.e(PS_GRAD_NORM);
   L->step += 1;
+  // clip_grad_norm_ + optimizer in one cooperative kernel (profile slot: optimizer)
   L->pf.b(PS_OPTIMIZER);
   if (c.optimizer == 0) {
-    CU(launch_rmsprop(L->params, L->grads, L->opt0, L->nparams, L->coef, c.learning_rate, c.alpha, c.epsilon, st), "rmsprop");
+    CU(launch_clip_optim(0, L->params, L->grads, L->opt0, nullptr, L->nparams, c.max_grad_norm, L->coef, L->scratch + 2048, c.learning_rate,
+                         c.alpha, 0.f, c.epsilon, 0, nullptr, st), "clip+rmsprop");
   } else {
-    CU(launch_adam(L->params, L->grads, L->opt0, L->opt1, L->nparams, L->coef, c.learning_rate, c.adam_beta1, c.adam_beta2, c.adam_eps,
-                   L->step, L->dstep, st), "adam");
+    CU(launch_clip_optim(1, L->params, L->grads, L->opt0, L->opt1, L->nparams, c.max_grad_norm, L->coef, L->scratch + 2048, c.learning_rate,
+                         c.adam_beta1, c.adam_beta2, c.adam_eps, L->step, L->dstep, st), "clip+adam");
   }
   L->pf.e(PS_OPTIMIZER);
   if (grad_norm_out) CU(cudaMemcpyAsync(grad_norm_out, L->coef, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy coef");

@@ -49,6 +49,22 @@ SRL_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its stream predecessor is still running: everything before pdl_wait() (barrier init, TMEM allocation, descriptor
+// prefetch, loads of data that was complete long before the predecessor started) overlaps the predecessor's tail;
+// pdl_wait() returns once the predecessor grid has completed and its memory is visible.  pdl_launch() lets the NEXT
+// kernel in the stream begin its own prologue.  Both are no-ops for a kernel launched without the attribute.
+SRL_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+SRL_DEVINL void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// 16-byte shared-memory load through the shared pipe (LDS), never a generic LD: keeps it in order with mbarrier operations
+SRL_DEVINL uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+SRL_DEVINL void sts_volatile_f32(uint32_t saddr, float v) { asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
+
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)
 SRL_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

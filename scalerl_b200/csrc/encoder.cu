@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __
 // each thread converts u32 (4 x dx) -> 4 bf16 and the block writes 3 x 21 x 128 B contiguously.
 constexpr int S2D_Y = 3;
 __global__ void __launch_bounds__(352) obs_s2d_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ xs) {
+  pdl_wait();      // launched with programmatic stream serialization: see common.cuh
+  pdl_launch();
   __shared__ uint32_t tile[S2D_Y][16][21];
   const int n = blockIdx.x / (21 / S2D_Y), Y0 = (blockIdx.x - n * (21 / S2D_Y)) * S2D_Y;
   const int t = threadIdx.x;
@@ -152,7 +154,7 @@ cudaError_t build_tma_maps(const EncoderBuffers& b, int NF, int NB, TmaMaps* M, 
 }
 
 static cudaError_t launch_s2d(const uint8_t* obs, int frames, bf16* xs, cudaStream_t st) {
-  obs_s2d_kernel<<<frames * (21 / S2D_Y), 352, 0, st>>>(obs, xs);
+  SRL_TRY(launch_chain<PDL_SIMT>(obs_s2d_kernel, dim3(frames * (21 / S2D_Y)), dim3(352), 0, st, obs, xs));
   return cudaGetLastError();
 }
 
@@ -172,6 +174,8 @@ static int persistent_ctas() {
 // workspace [tap-block][row][co] -> PyTorch-layout conv weight gradients (plain stores), and re-zero what was read
 __global__ void __launch_bounds__(256) conv_wgrad_finalize_kernel(float* __restrict__ ws, float* __restrict__ g1, float* __restrict__ g2,
                                                                   float* __restrict__ g3) {
+  pdl_wait();      // launched with programmatic stream serialization: see common.cuh
+  pdl_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 36864) {                       // dW3[co][c][tap] = ws3[tap>>1][(tap&1)*64 + c][co]
     const int co = i / 576, r = i - co * 576, c = r / 9, tap = r - c * 9;
@@ -251,7 +255,7 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
     SRL_TRY(cudaEventRecord(ss.ev[7], s3)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[7], 0));
   }
   pf.b(PS_WGRAD_FINALIZE);
-  conv_wgrad_finalize_kernel<<<(36864 + 32768 + 8192 + 255) / 256, 256, 0, st>>>(buf.wgrad_ws, g.w1, g.w2, g.w3);
+  SRL_TRY(launch_chain<PDL_SIMT>(conv_wgrad_finalize_kernel, dim3((36864 + 32768 + 8192 + 255) / 256), dim3(256), 0, st, buf.wgrad_ws, g.w1, g.w2, g.w3));
   SRL_TRY(cudaGetLastError());
   pf.e(PS_WGRAD_FINALIZE);
   return cudaSuccess;

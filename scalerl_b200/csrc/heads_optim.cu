@@ -4,6 +4,11 @@
 //   * clip_grad_norm_ (impala_atari.py:344-345) + RMSprop (impala_atari.py:99-105,346) / Adam update
 #include "common.cuh"
 #include "kernels.h"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+#ifndef SRL_TRY
+#define SRL_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+#endif
 
 namespace srl {
 
@@ -19,6 +24,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ bp, const float* __restrict__ Wb,
                                                        const float* __restrict__ bb, int N, int A, float* __restrict__ logits,
                                                        float* __restrict__ baseline) {
+  pdl_wait();      // launched with programmatic stream serialization: see common.cuh
+  pdl_launch();
   __shared__ float part[2][4][HEAD_MAX_A + 1];
   const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3, f = threadIdx.x >> 7;
   const int n = blockIdx.x * 2 + f;
@@ -57,6 +64,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
 __global__ void __launch_bounds__(128) head_bwd_dh_kernel(const float* __restrict__ dlogits, const float* __restrict__ dbaseline,
                                                           const float* __restrict__ h, const float* __restrict__ Wp,
                                                           const float* __restrict__ Wb, int N, int A, __nv_bfloat16* __restrict__ dh) {
+  pdl_wait();      // launched with programmatic stream serialization: see common.cuh
+  pdl_launch();
   const int n = blockIdx.x;
   const int j = blockIdx.y * 128 + threadIdx.x;
   const int CORE = 513 + A;
@@ -338,14 +347,14 @@ cudaError_t launch_head_fwd(const float* hpart, int nsplit, const float* bfc, fl
                             const float* Wp, const float* bp, const float* Wb, const float* bb, int N, int A, float* logits,
                             float* baseline, cudaStream_t st) {
   if (N <= 0) return cudaSuccess;
-  head_fwd_kernel<<<(N + 1) / 2, 256, 0, st>>>(hpart, nsplit, bfc, h, reward, action, Wp, bp, Wb, bb, N, A, logits, baseline);
+  return launch_chain<PDL_SIMT>(head_fwd_kernel, dim3((N + 1) / 2), dim3(256), 0, st, hpart, nsplit, bfc, h, reward, action, Wp, bp, Wb, bb, N, A, logits, baseline);
   return cudaGetLastError();
 }
 cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const float* h, const float* reward, const int64_t* action,
                             const float* Wp, const float* Wb, int N, int A, __nv_bfloat16* dh, float* gWp, float* gbp, float* gWb,
                             float* gbb, cudaStream_t st, cudaStream_t st_wgrad) {
   if (N <= 0) return cudaSuccess;
-  head_bwd_dh_kernel<<<dim3(N, 4), 128, 0, st>>>(dlogits, dbaseline, h, Wp, Wb, N, A, dh);
+  SRL_TRY(launch_chain<PDL_SIMT>(head_bwd_dh_kernel, dim3(N, 4), dim3(128), 0, st, dlogits, dbaseline, h, Wp, Wb, N, A, dh));
   const int CORE = 513 + A;
   // the head weight gradients only feed the optimizer: they may run on a side stream (st_wgrad) beside the fc backward
   head_wgrad_kernel<<<dim3((CORE + 1 + 127) / 128, (N + HEAD_SLAB - 1) / HEAD_SLAB), 128, 0, st_wgrad>>>(dlogits, dbaseline, h, reward, action, N, A,
@@ -370,6 +379,110 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n,
   if (dstep) adam_step_inc_kernel<<<1, 1, 0, st>>>(dstep);
   adam_kernel<<<ew_blocks(n * 4), 256, 0, st>>>(p, g, m, v, n, coef, lr, b1, b2, eps, step, dstep);
   return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// clip_grad_norm_ + optimizer step as ONE cooperative kernel (impala_atari.py:344-346): phase 1 sums g^2 (block partials
+// in a fixed slot each), grid barrier, every block adds the partials in the same fixed order (deterministic, identical
+// in all blocks), phase 2 applies the clipped update (g is re-read from L2).  OPT 0 = RMSprop, 1 = Adam.
+// ------------------------------------------------------------------------------------------------
+template <int OPT>
+__global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s0,
+                                                         float* __restrict__ s1, int64_t n, float max_norm, float* __restrict__ coef,
+                                                         float* __restrict__ scratch, float lr, float a, float b, float eps, int step,
+                                                         int* __restrict__ dstep) {
+  cg::grid_group grid = cg::this_grid();
+  const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = OPT == 1 ? (dstep ? *dstep + 1 : step) : 0;
+  float s = 0.f;
+  for (int64_t i = i0; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = g[n4 * 4 + threadIdx.x]; s += v * v; }
+  __shared__ float red[16];
+  __shared__ float c_sh;
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.f;
+    for (int w = 0; w < 16; ++w) tsum += red[w];
+    scratch[4 + blockIdx.x] = tsum;
+  }
+  grid.sync();
+  if (threadIdx.x < 32) {
+    double tsum = 0.0;
+    for (unsigned k = threadIdx.x; k < gridDim.x; k += 32) tsum += (double)__ldcg(scratch + 4 + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+    if (threadIdx.x == 0) {
+      const float norm = (float)sqrt(tsum);
+      const float c = max_norm >= 0.f ? fminf(max_norm / (norm + 1e-6f), 1.0f) : 1.0f;
+      c_sh = c;
+      if (blockIdx.x == 0) {
+        coef[0] = norm; coef[1] = c;
+        if (OPT == 1 && dstep) *dstep = t;
+      }
+    }
+  }
+  __syncthreads();
+  const float c = c_sh;
+  if (OPT == 0) {
+    for (int64_t i = i0; i < n4; i += stride) {
+      float4 pp = reinterpret_cast<float4*>(p)[i], vv = reinterpret_cast<float4*>(s0)[i];
+      const float4 gg = reinterpret_cast<const float4*>(g)[i];
+      float* P = &pp.x; float* V = &vv.x; const float* G = &gg.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gk = G[k] * c;
+        V[k] = a * V[k] + (1.f - a) * gk * gk;
+        P[k] = P[k] - lr * (gk / (sqrtf(V[k]) + eps));
+      }
+      reinterpret_cast<float4*>(p)[i] = pp;
+      reinterpret_cast<float4*>(s0)[i] = vv;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+      const int64_t i = n4 * 4 + threadIdx.x;
+      const float gk = g[i] * c;
+      s0[i] = a * s0[i] + (1.f - a) * gk * gk;
+      p[i] = p[i] - lr * (gk / (sqrtf(s0[i]) + eps));
+    }
+  } else {
+    const float inv_bc1 = 1.0f / (float)(1.0 - pow((double)a, (double)t));
+    const float inv_sqrt_bc2 = 1.0f / sqrtf((float)(1.0 - pow((double)b, (double)t)));
+    for (int64_t i = i0; i < n; i += stride) {
+      const float gk = g[i] * c;
+      const float mk = a * s0[i] + (1.f - a) * gk;
+      const float vk = b * s1[i] + (1.f - b) * gk * gk;
+      s0[i] = mk; s1[i] = vk;
+      p[i] = p[i] - (lr * inv_bc1) * (mk / (sqrtf(vk) * inv_sqrt_bc2 + eps));
+    }
+  }
+}
+
+template <int OPT>
+static cudaError_t launch_clip_optim_t(float* p, const float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef, float* scratch,
+                                       float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st) {
+  static int per_sm = 0, sms = 0;
+  if (!per_sm) {
+    int dev = 0;
+    SRL_TRY(cudaGetDevice(&dev));
+    SRL_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SRL_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, clip_optim_kernel<OPT>, 512, 0));
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  }
+  int64_t need = (n / 4 + 511) / 512;
+  int blocks = (int)(need < 1 ? 1 : need);
+  int cap = per_sm * sms; if (cap > 592) cap = 592;          // scratch holds 592 partials
+  if (blocks > cap) blocks = cap;
+  void* args[] = {&p, &g, &s0, &s1, &n, &max_norm, &coef, &scratch, &lr, &a, &b, &eps, &step, &dstep};
+  return cudaLaunchCooperativeKernel((const void*)clip_optim_kernel<OPT>, dim3(blocks), dim3(512), args, 0, st);
+}
+cudaError_t launch_clip_optim(int optimizer, float* p, const float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
+                              float* scratch, float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st) {
+  return optimizer == 0 ? launch_clip_optim_t<0>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, st)
+                        : launch_clip_optim_t<1>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, st);
 }
 
 }  // namespace srl

@@ -75,11 +75,16 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid != 128) pdl_wait();
 
   if (warp == 4) {
     if ((tid & 31) == 0) {
+      // the packed weights were complete before the first kernel of the chain started: their load overlaps the previous
+      // kernel's tail; the activations are only touched after pdl_wait()
       mbar_arrive_expect_tx(w_full, C::W_BYTES);
       for (int j = 0; j < P::NT; ++j) tma_load_2d(sW + j * P::BN * 128, &p.w, w_full, j * 64, 0);
+      pdl_wait();
+      pdl_launch();
       int it = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int s = it % P::STAGES;
@@ -156,8 +161,7 @@ cudaError_t res_fwd_launch(const typename P::Params& p, int ntiles, int max_ctas
     attr_set = true;
   }
   const int grid = ntiles < max_ctas ? ntiles : max_ctas;
-  res_fwd_kernel<P><<<grid, RES_THREADS, C::SMEM_BYTES, stream>>>(p);
-  return cudaGetLastError();
+  return launch_chain<PDL_RESFWD>(res_fwd_kernel<P>, dim3(grid), dim3(RES_THREADS), C::SMEM_BYTES, stream, p);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -195,14 +199,16 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
   const int c_end = min(nchunks_total, c_begin + p.chunks_per_cta);
   const int nch = max(0, c_end - c_begin);
 
-  {  // all-ones block (bf16 1.0) for the bias-gradient accumulator
+  if constexpr (!P::SMEM_BIAS) {  // all-ones block (bf16 1.0) for the bias-gradient accumulator
     uint4* q = reinterpret_cast<uint4*>(sOnes);
     for (int i = tid; i < C::ONES_BYTES / 16; i += RES_THREADS) q[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
   }
   if (warp == 4) {
     if ((tid & 31) == 0) {
-      for (int s = 0; s < P::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      // SMEM_BIAS: the four epilogue warps also read every dy tile (bias-gradient column sums), so a stage is free
+      // only after the MMA commit AND their four arrivals
+      for (int s = 0; s < P::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], P::SMEM_BIAS ? 5 : 1); }
       mbar_init(done, 1);
       mbar_fence_init();
       P::prefetch(p);
@@ -214,6 +220,8 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  if (tid == 128) pdl_launch();
 
   if (warp == 4) {
     if ((tid & 31) == 0) {
@@ -251,6 +259,48 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
       umma_commit(done);
     }
   } else {
+    if constexpr (P::SMEM_BIAS) {
+      // bias gradient = column sums of dy, taken from the staged dy tiles while the MMAs run (no all-ones accumulator).
+      // dy tile: 128 position rows of 128 B (64 channels), SWIZZLE_128B.  thread -> 16-byte channel group g, rows q + 16k.
+      const int g = tid & 7, q = tid >> 3;
+      float bs[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bs[j] = 0.f;
+      // Releasing a stage lets the producer's TMA overwrite it.  mbarrier.arrive does NOT wait for this warp's loads that
+      // are still in flight (seen on sm_100a: generic LD.E.128 of the tile overtaken by the arrive -> rows of the NEXT
+      // chunk were summed).  So the tile is read with ld.shared (same pipe as the mbarrier op), and every lane stores a
+      // value that depends on all of its loads before the warp arrives: the store cannot issue until the loads returned,
+      // and the arrive (release) is ordered after the store.
+      const uint32_t dep_slot = smem_u32(sOnes) + 4096 + tid * 4;
+      for (int i = 0; i < nch; ++i) {
+        const int s = i % P::STAGES;
+        mbar_wait(&full[s], (i / P::STAGES) & 1);
+        const uint32_t dyt = smem_u32(sSt + s * C::STAGE_BYTES + P::NWIN * C::WIN_BYTES);
+        float dep = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint4 v = lds128(dyt + swz128(q + 16 * k, g));
+          bs[0] += bf16_lo(v.x); bs[1] += bf16_hi(v.x); bs[2] += bf16_lo(v.y); bs[3] += bf16_hi(v.y);
+          bs[4] += bf16_lo(v.z); bs[5] += bf16_hi(v.z); bs[6] += bf16_lo(v.w); bs[7] += bf16_hi(v.w);
+          dep += __uint_as_float(v.x ^ v.y ^ v.z ^ v.w);
+        }
+        sts_volatile_f32(dep_slot, dep);
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+      }
+      float* red = reinterpret_cast<float*>(sOnes);          // the all-ones block is not used by these problems
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        bs[j] += __shfl_xor_sync(0xffffffffu, bs[j], 8);
+        bs[j] += __shfl_xor_sync(0xffffffffu, bs[j], 16);
+      }
+      if ((tid & 31) < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp * 64 + g * 8 + j] = bs[j];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");        // epilogue warps only
+      if (tid < P::BIAS_CH && nch > 0) atomicAdd(p.db + tid, red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]);
+    }
     if (nch > 0) {
       mbar_wait(done, 0);
       tc_fence_after();
@@ -291,8 +341,7 @@ cudaError_t res_wgrad_launch(typename P::Params p, int target_ctas, cudaStream_t
   }
   p.chunks_per_cta = (nchunks + target_ctas - 1) / target_ctas;
   const int grid = (nchunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
-  res_wgrad_kernel<P><<<grid, RES_THREADS, C::SMEM_BYTES, stream>>>(p);
-  return cudaGetLastError();
+  return launch_chain<PDL_RESWGRAD>(res_wgrad_kernel<P>, dim3(grid), dim3(RES_THREADS), C::SMEM_BYTES, stream, p);
 }
 
 }  // namespace srl

@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
+#include "kernels.h"
 
 namespace srl {
 
@@ -100,6 +101,8 @@ __global__ void __launch_bounds__(IGT_THREADS) igemm_tma_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                         // prologue above overlaps the previous kernel's tail
+  if (tid == 128) pdl_launch();
 
   if (warp == 4) {
     if ((tid & 31) == 0) {
@@ -188,8 +191,7 @@ cudaError_t igemm_tma_launch(const typename P::Params& p, dim3 grid, cudaStream_
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  igemm_tma_kernel<P><<<grid, IGT_THREADS, C::SMEM_BYTES, stream>>>(p);
-  return cudaGetLastError();
+  return launch_chain<PDL_IGEMM>(igemm_tma_kernel<P>, grid, dim3(IGT_THREADS), C::SMEM_BYTES, stream, p);
 }
 
 }  // namespace srl

@@ -19,6 +19,24 @@ struct Profiler {
   void e(int slot) const { if (on) cudaEventRecord(ev[2 * slot + 1], st); }
 };
 // second stream + fork/join events: the wgrad GEMMs run beside the dgrad chain (also under stream capture)
+// ---- programmatic dependent launch (see common.cuh) ----------------------------------------------------------
+// pdl_active(): SRL_PDL != 0 (default on) and not switched off by the caller (per-kernel profiling records events between
+// the kernels, which would serialise them anyway).
+bool pdl_active();
+void pdl_set_active(bool on);
+int pdl_skip_mask();      // SRL_PDL_MASK diagnostic: bit t set = kernels of class t launch without the attribute
+enum { PDL_SIMT = 0, PDL_IGEMM = 1, PDL_RESFWD = 2, PDL_RESWGRAD = 3 };
+template <int TAG, class... KA, class... A>
+inline cudaError_t launch_chain(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (pdl_active() && !((pdl_skip_mask() >> TAG) & 1)) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 int side_mode();   // SRL_SIDE_MODE diagnostic bitmask: 1 = one wgrad side stream, 2 = head wgrad on the main stream, 4 = grad memset on the main stream
 
 struct SideStream {
@@ -57,6 +75,8 @@ cudaError_t launch_head_dense_bwd(const float* X, const float* dlogits, const fl
 cudaError_t launch_dcore_to_dh(const float* dcore, const float* h, int N, int A, __nv_bfloat16* dh, cudaStream_t st);
 cudaError_t launch_unpack_slots(const uint8_t* staging, int64_t slot_bytes, const int64_t* off6, int T, int B, int A, uint8_t* obs, float* reward,
                                 uint8_t* done, int64_t* action, float* logits, float* episode_return, cudaStream_t st);
+cudaError_t launch_clip_optim(int optimizer, float* p, const float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
+                              float* scratch, float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st);
 cudaError_t launch_grad_norm(const float* g, int64_t n, float max_norm, float* coef, float* scratch, cudaStream_t st);
 cudaError_t launch_rmsprop(float* p, const float* g, float* v, int64_t n, const float* coef, float lr, float alpha, float eps,
                            cudaStream_t st);
@@ -113,6 +133,7 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
                              cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase);
 cudaError_t test_shift(const void* A, const void* B, float* D, int shift, int mn_major, int bo_mode, cudaStream_t st);
 cudaError_t test_poison_smem(cudaStream_t st);
+cudaError_t test_pdl(int* flag, int* out, int nblk, unsigned delay_ns, cudaStream_t st);
 cudaError_t test_gemm(const void* A, const void* B, float* D, int M, int N, int K, bool mn_major, bool simt, cudaStream_t st);
 
 }  // namespace srl

@@ -126,6 +126,8 @@ constexpr int WS_W1 = WS_W2 + 4 * 128 * 64;    // [2 kh2][128 rows][32 co]
 constexpr int WS_TOTAL = WS_W1 + 2 * 128 * 32;
 struct RConv3Wgrad {   // acc a = taps (2a, 2a+1); acc 4 = (tap 8, ones -> db3).  ws: [10 taps][64 c][64 co] fp32 (co contiguous)
   static constexpr int NACC = 5, NWIN = 1, WROWS = 128 + 20, STAGES = 3;
+  static constexpr bool SMEM_BIAS = false;     // the ninth tap leaves half an accumulator free: the all-ones block rides along
+  static constexpr int BIAS_CH = 64;
   struct Params { SRL_TMAP in0; SRL_TMAP dy; float* ws; float* db; int P; int chunks_per_cta; };
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.dy); }
   SRL_DEVINL static constexpr int sh(int tap) { return (tap / 3) * 9 + tap % 3; }
@@ -145,45 +147,39 @@ struct RConv3Wgrad {   // acc a = taps (2a, 2a+1); acc 4 = (tap 8, ones -> db3).
   }
 };
 
-struct RConv2Wgrad {   // acc a = kh (blocks kww = 0,1: rows = (kw = 2kww + wp, c)); acc 4 = (ones, ones) -> db2
-  static constexpr int NACC = 5, NWIN = 2, WROWS = 128 + 11, STAGES = 3;
+struct RConv2Wgrad {   // acc a = kh (blocks kww = 0,1: rows = (kw = 2kww + wp, c)); db2 = column sums of the staged dy tiles
+  static constexpr int NACC = 4, NWIN = 2, WROWS = 128 + 11, STAGES = 3;
+  static constexpr bool SMEM_BIAS = true;
+  static constexpr int BIAS_CH = 64;
   struct Params { SRL_TMAP in0; SRL_TMAP in1; SRL_TMAP dy; float* ws; float* db; int P; int chunks_per_cta; };   // ws: [4 kh][128 (kw,c)][64 co]
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.in1); tma_prefetch_desc(&p.dy); }
   SRL_DEVINL static constexpr int acc_win(int a) { return a & 1; }
   SRL_DEVINL static constexpr int acc_win1(int a) { return a & 1; }
-  SRL_DEVINL static constexpr int acc_shift0(int a) { return a < 4 ? (a >> 1) * 10 : 0; }
-  SRL_DEVINL static constexpr int acc_shift1(int a) { return a < 4 ? (a >> 1) * 10 + 1 : -1; }
+  SRL_DEVINL static constexpr int acc_shift0(int a) { return (a >> 1) * 10; }
+  SRL_DEVINL static constexpr int acc_shift1(int a) { return (a >> 1) * 10 + 1; }
   SRL_DEVINL static void load_windows(const Params& p, int chunk, uint8_t* dst, int win_bytes, uint64_t* bar) {
     tma_load_2d(dst, &p.in0, bar, 0, chunk * 128);
     tma_load_2d(dst + win_bytes, &p.in1, bar, 0, chunk * 128);
   }
   SRL_DEVINL static void epilogue16(const Params& p, int a, int row, int c0, float (&v)[16]) {
-    if (a < 4) {
-      red_add_16(p.ws + ((size_t)(a * 128 + row)) * 64 + c0, v);
-    } else if (row == 64) {          // block 1 of the last accumulator is the all-ones block
-#pragma unroll
-      for (int j = 0; j < 16; ++j) atomicAdd(p.db + c0 + j, v[j]);
-    }
+    red_add_16(p.ws + ((size_t)(a * 128 + row)) * 64 + c0, v);
   }
 };
 
-struct RConv1Wgrad {   // acc a = kh2 (blocks kw2 = 0,1: rows = (kw2, c, dy, dx)); acc 2 = (tap 0, ones) -> db1 (block 0 unused)
-  static constexpr int NACC = 3, NWIN = 1, WROWS = 128 + 22, STAGES = 3;
+struct RConv1Wgrad {   // acc a = kh2 (blocks kw2 = 0,1: rows = (kw2, c, dy, dx)); db1 = column sums of the staged dy tiles
+  static constexpr int NACC = 2, NWIN = 1, WROWS = 128 + 22, STAGES = 3;
+  static constexpr bool SMEM_BIAS = true;
+  static constexpr int BIAS_CH = 32;           // da1g channels 32..63 are zero
   struct Params { SRL_TMAP in0; SRL_TMAP dy; float* ws; float* db; int P; int chunks_per_cta; };   // ws: [2 kh2][128 (kw2,c,dy,dx)][32 co]
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.dy); }
   SRL_DEVINL static constexpr int acc_win(int) { return 0; }
   SRL_DEVINL static constexpr int acc_win1(int) { return 0; }
-  SRL_DEVINL static constexpr int acc_shift0(int a) { return a < 2 ? a * 21 : 0; }
-  SRL_DEVINL static constexpr int acc_shift1(int a) { return a < 2 ? a * 21 + 1 : -1; }
+  SRL_DEVINL static constexpr int acc_shift0(int a) { return a * 21; }
+  SRL_DEVINL static constexpr int acc_shift1(int a) { return a * 21 + 1; }
   SRL_DEVINL static void load_windows(const Params& p, int chunk, uint8_t* dst, int, uint64_t* bar) { tma_load_2d(dst, &p.in0, bar, 0, chunk * 128); }
   SRL_DEVINL static void epilogue16(const Params& p, int a, int row, int c0, float (&v)[16]) {
     if (c0 >= 32) return;                    // da1g channels 32..63 are zero
-    if (a < 2) {
-      red_add_16(p.ws + ((size_t)(a * 128 + row)) * 32 + c0, v);
-    } else if (row == 64) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) atomicAdd(p.db + c0 + j, v[j]);
-    }
+    red_add_16(p.ws + ((size_t)(a * 128 + row)) * 32 + c0, v);
   }
 };
 

@@ -106,4 +106,31 @@ cudaError_t test_poison_smem(cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// PDL self-test: kernel A spins ~delay_ns then sets flag = 1; kernel B (launched with programmatic stream serialization)
+// executes griddepcontrol.wait and records the flag it sees.  out[0] must be 1 on every stream.
+__global__ void pdl_test_a(volatile int* flag, unsigned delay_ns) {
+  pdl_launch();
+  if (threadIdx.x == 0) {
+    const unsigned long long t0 = clock64();
+    while (clock64() - t0 < (unsigned long long)delay_ns * 2) { }
+    *flag = 1;
+  }
+}
+__global__ void pdl_test_b(volatile int* flag, int* out) {
+  pdl_wait();
+  if (threadIdx.x == 0) out[blockIdx.x] = *flag;
+}
+cudaError_t test_pdl(int* flag, int* out, int nblk, unsigned delay_ns, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  pdl_test_a<<<1, 32, 0, st>>>(flag, delay_ns);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(32); cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, pdl_test_b, (volatile int*)flag, out);
+}
+
 }  // namespace srl

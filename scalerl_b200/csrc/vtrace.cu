@@ -187,6 +187,8 @@ __global__ void __launch_bounds__(128) impala_tail_kernel(const float* __restric
                                                           float baseline_cost, float entropy_cost, float* __restrict__ vs,
                                                           float* __restrict__ pg, float* __restrict__ dlogits, float* __restrict__ dbaseline,
                                                           float* __restrict__ losses, float* __restrict__ scratch) {
+  pdl_wait();      // launched with programmatic stream serialization: see common.cuh
+  pdl_launch();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l_pg = 0.f, l_bl = 0.f, l_ent = 0.f;
   if (b < B) {
@@ -270,6 +272,8 @@ __global__ void __launch_bounds__(128) impala_tail_warp_kernel(const float* __re
                                                                float* __restrict__ vs, float* __restrict__ pg, float* __restrict__ dlogits,
                                                                float* __restrict__ dbaseline, float* __restrict__ losses,
                                                                float* __restrict__ scratch) {
+  pdl_wait();      // launched with programmatic stream serialization: see common.cuh
+  pdl_launch();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * 4 + warp;
   float l_pg = 0.f, l_bl = 0.f, l_ent = 0.f;
@@ -394,12 +398,11 @@ cudaError_t launch_impala_tail(const float* bl, const float* tl, const float* ba
                                float clip_pg, float baseline_cost, float entropy_cost, float* vs, float* pg, float* dlogits,
                                float* dbaseline, float* losses, float* scratch, cudaStream_t st) {
   if (B <= 2048) {   // latency-bound sizes: one warp per column, shuffle scan over T (block partials: 3*ceil(B/4) <= 1536 floats)
-    impala_tail_warp_kernel<<<(B + 3) / 4, 128, 0, st>>>(bl, tl, baseline, action, reward, done, T, B, A, discounting, clip_reward,
-                                                          clip_rho, clip_pg, baseline_cost, entropy_cost, vs, pg, dlogits, dbaseline, losses,
-                                                          scratch);
+    return launch_chain<PDL_SIMT>(impala_tail_warp_kernel, dim3((B + 3) / 4), dim3(128), 0, st, bl, tl, baseline, action, reward, done, T, B, A, discounting,
+                        clip_reward, clip_rho, clip_pg, baseline_cost, entropy_cost, vs, pg, dlogits, dbaseline, losses, scratch);
   } else {
-    impala_tail_kernel<<<(B + 127) / 128, 128, 0, st>>>(bl, tl, baseline, action, reward, done, T, B, A, discounting, clip_reward, clip_rho,
-                                                         clip_pg, baseline_cost, entropy_cost, vs, pg, dlogits, dbaseline, losses, scratch);
+    return launch_chain<PDL_SIMT>(impala_tail_kernel, dim3((B + 127) / 128), dim3(128), 0, st, bl, tl, baseline, action, reward, done, T, B, A, discounting,
+                        clip_reward, clip_rho, clip_pg, baseline_cost, entropy_cost, vs, pg, dlogits, dbaseline, losses, scratch);
   }
   return cudaGetLastError();
 }

@@ -260,7 +260,7 @@ def test_learn_step_vs_emulating_oracle(T, B, optimizer):
                 opt[name][k].copy_(d[k].cpu())
 
 
-@pytest.mark.parametrize('T,B', [(5, 4), (3, 7), (1, 1)])
+@pytest.mark.parametrize('T,B', [(5, 4), (3, 7), (1, 1), (7, 19), (12, 24)])
 def test_learn_step_ignores_stale_shared_memory(T, B):
     """Ragged frame counts (T*B not a multiple of any tile/slab) after every SM's shared memory was filled with NaN
     patterns: the gradients must be finite and equal those of a run on clean shared memory up to the summation
@@ -270,7 +270,7 @@ def test_learn_step_ignores_stale_shared_memory(T, B):
     batch = {k: dev(v) for k, v in O.synthetic_batch(T, B, A, seed=77, done_p=0.2).items()}
     grads = []
     for poison in (False, True):
-        L, _ = _learner(T, B, A, 4)
+        L, _ = _learner(T, B, A, 4, learning_rate=0.0)     # lr = 0: the three steps see identical weights
         for _ in range(3):                      # eager, capture, replay
             if poison:
                 _lib.check(_lib.lib().srl_test_poison_smem(None))
@@ -280,6 +280,31 @@ def test_learn_step_ignores_stale_shared_memory(T, B):
         assert bool(torch.isfinite(g).all()) and bool(torch.isfinite(L.flat_params).all())
         grads.append(g)
     assert rel_l2(grads[1].cpu(), grads[0].cpu()) < 1e-5
+
+
+@pytest.mark.parametrize('T,B', [(7, 19), (12, 24)])
+def test_conv_bias_gradients_equal_dy_column_sums_every_run(T, B):
+    """conv1/conv2 bias gradients are column sums of dy tiles staged in shared memory, read by the epilogue warps while the
+    MMAs run.  Regression for a release hazard (the stage was handed back to the TMA producer while the warp's loads were
+    still in flight -> rows of the NEXT chunk were summed, sporadically, only when kernels overlap via programmatic
+    dependent launch): 30 back-to-back runs on a non-default stream, each compared with sum(da1) / sum(da2) taken from
+    the debug buffers of the same run, and all gradients compared with the first run."""
+    A = 4
+    L, _ = _learner(T, B, A, 1)
+    batch = {k: dev(v) for k, v in O.synthetic_batch(T, B, A, seed=5).items()}
+    first = None
+    with torch.cuda.stream(torch.cuda.Stream()):
+        for it in range(30):
+            L.forward_backward(batch)
+            torch.cuda.current_stream().synchronize()
+            b1 = L.debug_buffer('da1').float().view(-1, 64).sum(0)[:32]
+            b2 = L.debug_buffer('da2').float().view(-1, 64).sum(0)
+            assert rel_l2(L.grads['conv1.bias'].cpu(), b1.cpu()) < 1e-4, it
+            assert rel_l2(L.grads['conv2.bias'].cpu(), b2.cpu()) < 1e-4, it
+            g = L.flat_grads.clone()
+            if first is None:
+                first = g
+            assert rel_l2(g.cpu(), first.cpu()) < 1e-5, it
 
 
 @pytest.mark.parametrize('name', ['t5b4a6', 't3b5a4'])
