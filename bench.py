@@ -449,7 +449,7 @@ def _main(real_stdout):
                'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': feeder.h2d_bytes, 'd2h_bytes_per_step': feeder.d2h_bytes,
                        'ms_per_step': e2e_s / K * 1e3, 'api': 'HostBatchFeeder.submit/learn/result + B200ImpalaLearner.learn (pinned host batches)',
                        'last_total_loss': stats['total_loss'], 'h2d_only_ms_per_step': h2d_only_ms, 'eager_launch_ms_per_step': e2e_eager_ms},
-               'gpu_launches': 19 * K, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'losses_finite': losses_finite,
+               'gpu_launches': 17 * K, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'losses_finite': losses_finite,
                'vtrace_standalone': vtrace}
         emit(real_stdout, out)
     learner.release_graphs()

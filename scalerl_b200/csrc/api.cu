@@ -422,20 +422,37 @@ static int fb_begin(srl_learner* L, const uint8_t* obs, const float* reward, con
                     const float* behavior_logits, float* losses, float* vs, float* pg_advantages, cudaStream_t st, int phase) {
   const srl_config_t& c = L->cfg;
   const int NF = (c.T + 1) * c.B, NB = c.T * c.B;
-  int rc = forward_impl(L, obs, reward, action, NF, L->logits, L->baseline, st, true);
-  if (rc) return rc;
-  L->pf.b(PS_TAIL);
-  CU(launch_impala_tail(behavior_logits, L->logits, L->baseline, action, reward, done, c.T, c.B, c.A, c.discounting,
-                        c.reward_clip_abs_one, c.clip_rho_threshold, c.clip_pg_rho_threshold, c.baseline_cost, c.entropy_cost, vs,
-                        pg_advantages, L->dlogits, L->dbaseline, losses, L->scratch, st), "impala_tail");
-  L->pf.e(PS_TAIL);
+  // heads + V-trace/losses + dh: one fused column kernel when its shared-memory footprint fits, else three kernels
+  const char* nf = getenv("SRL_NO_COLUMN_FUSION");          // read per call: the tests toggle it
+  const bool no_fuse = nf && atoi(nf) != 0;
+  const bool fused = !no_fuse && column_step_supported(c.T, c.B, c.A);
+  int rc;
+  if (fused) {
+    REQ(!L->cfg.use_lstm, "this learner was created with use_lstm=1: call the *_lstm entry points");
+    rc = encode_impl(L, obs, NF, st, true);
+    if (rc) return rc;
+    L->pf.b(PS_TAIL);
+    CU(launch_column_step(L->buf.hpart, FC_SPLITS, L->P.bf, L->buf.h, reward, action, done, behavior_logits, L->P.wp, L->P.bp, L->P.wb,
+                          L->P.bb, c.T, c.B, c.A, c.discounting, c.reward_clip_abs_one, c.clip_rho_threshold, c.clip_pg_rho_threshold,
+                          c.baseline_cost, c.entropy_cost, L->logits, L->baseline, vs, pg_advantages, L->dlogits, L->dbaseline, L->buf.dh,
+                          losses, L->scratch, st), "column_step");
+    L->pf.e(PS_TAIL);
+  } else {
+    rc = forward_impl(L, obs, reward, action, NF, L->logits, L->baseline, st, true);
+    if (rc) return rc;
+    L->pf.b(PS_TAIL);
+    CU(launch_impala_tail(behavior_logits, L->logits, L->baseline, action, reward, done, c.T, c.B, c.A, c.discounting,
+                          c.reward_clip_abs_one, c.clip_rho_threshold, c.clip_pg_rho_threshold, c.baseline_cost, c.entropy_cost, vs,
+                          pg_advantages, L->dlogits, L->dbaseline, losses, L->scratch, st), "impala_tail");
+    L->pf.e(PS_TAIL);
+  }
   L->pf.b(PS_HEAD_BWD);
   {
     const bool fork = L->ss.side != nullptr && !L->pf.on && !(side_mode() & 2);
     cudaStream_t sw = fork ? L->ss.side : st;
     if (fork) { CU(cudaEventRecord(L->ss.ev[8], st), "fork head wgrad"); CU(cudaStreamWaitEvent(sw, L->ss.ev[8], 0), "fork head wgrad"); }
     CU(launch_head_bwd(L->dlogits, L->dbaseline, L->buf.h, reward, action, L->P.wp, L->P.wb, NB, c.A, L->buf.dh, L->G.wp, L->G.bp, L->G.wb,
-                       L->G.bb, st, sw), "head_bwd");      // side stream `side` is joined by encoder_backward (after the fc wgrad)
+                       L->G.bb, st, sw, !fused), "head_bwd");      // side stream `side` is joined by encoder_backward (after the fc wgrad)
   }
   L->pf.e(PS_HEAD_BWD);
   CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.simt_mainloop, st, L->pf, L->ss, phase), "encoder_backward");

@@ -41,9 +41,10 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __
 }
 
 // u8 NCHW frames -> space-to-depth bf16 NHWC: xs[n][Y][X][c*16+dy*4+dx] = obs[n][c][4Y+dy][4X+dx]  (exact: u8 fits bf16).
-// One block per (frame, 3 consecutive Y): the 48 source rows (c,dy) are read coalesced (21 u32 each) into shared memory, then
-// each thread converts u32 (4 x dx) -> 4 bf16 and the block writes 3 x 21 x 128 B contiguously.
-constexpr int S2D_Y = 3;
+// One block per (frame, S2D_Y consecutive Y): the 16 S2D_Y source rows (c,dy) are read coalesced (21 u32 each, all loads of a
+// thread in flight together) into shared memory, then each thread converts u32 (4 x dx) -> 4 bf16 and the block writes
+// S2D_Y x 21 x 128 B contiguously.  S2D_Y = 21 (a whole frame per block, 84 B of loads in flight per thread) by default.
+template <int S2D_Y>
 __global__ void __launch_bounds__(352) obs_s2d_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ xs) {
   pdl_wait();      // launched with programmatic stream serialization: see common.cuh
   pdl_launch();
@@ -154,7 +155,10 @@ cudaError_t build_tma_maps(const EncoderBuffers& b, int NF, int NB, TmaMaps* M, 
 }
 
 static cudaError_t launch_s2d(const uint8_t* obs, int frames, bf16* xs, cudaStream_t st) {
-  SRL_TRY(launch_chain<PDL_SIMT>(obs_s2d_kernel, dim3(frames * (21 / S2D_Y)), dim3(352), 0, st, obs, xs));
+  static const int ygroup = [] { const char* e = getenv("SRL_S2D_Y"); const int v = e ? atoi(e) : 21; return (v == 3 || v == 7) ? v : 21; }();
+  if (ygroup == 3) SRL_TRY(launch_chain<PDL_SIMT>(obs_s2d_kernel<3>, dim3(frames * 7), dim3(352), 0, st, obs, xs));
+  else if (ygroup == 7) SRL_TRY(launch_chain<PDL_SIMT>(obs_s2d_kernel<7>, dim3(frames * 3), dim3(352), 0, st, obs, xs));
+  else SRL_TRY(launch_chain<PDL_SIMT>(obs_s2d_kernel<21>, dim3(frames), dim3(352), 0, st, obs, xs));
   return cudaGetLastError();
 }
 

@@ -352,9 +352,9 @@ cudaError_t launch_head_fwd(const float* hpart, int nsplit, const float* bfc, fl
 }
 cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const float* h, const float* reward, const int64_t* action,
                             const float* Wp, const float* Wb, int N, int A, __nv_bfloat16* dh, float* gWp, float* gbp, float* gWb,
-                            float* gbb, cudaStream_t st, cudaStream_t st_wgrad) {
+                            float* gbb, cudaStream_t st, cudaStream_t st_wgrad, bool do_dh) {
   if (N <= 0) return cudaSuccess;
-  SRL_TRY(launch_chain<PDL_SIMT>(head_bwd_dh_kernel, dim3(N, 4), dim3(128), 0, st, dlogits, dbaseline, h, Wp, Wb, N, A, dh));
+  if (do_dh) SRL_TRY(launch_chain<PDL_SIMT>(head_bwd_dh_kernel, dim3(N, 4), dim3(128), 0, st, dlogits, dbaseline, h, Wp, Wb, N, A, dh));
   const int CORE = 513 + A;
   // the head weight gradients only feed the optimizer: they may run on a side stream (st_wgrad) beside the fc backward
   head_wgrad_kernel<<<dim3((CORE + 1 + 127) / 128, (N + HEAD_SLAB - 1) / HEAD_SLAB), 128, 0, st_wgrad>>>(dlogits, dbaseline, h, reward, action, N, A,

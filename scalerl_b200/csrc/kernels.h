@@ -53,6 +53,12 @@ cudaError_t launch_vtrace_iw(const float* log_rhos, const float* discounts, cons
 cudaError_t launch_vtrace_logits(const float* bl, const float* tl, const int64_t* actions, const float* discounts, const float* rewards,
                                  const float* values, const float* bootstrap, int T, int B, int A, float clip_rho, float clip_pg,
                                  float* vs, float* pg, float* lr, float* balp, float* talp, cudaStream_t st);
+bool column_step_supported(int T, int B, int A);
+cudaError_t launch_column_step(const float* hpart, int nsplit, const float* bfc, float* h, const float* reward, const int64_t* action,
+                               const uint8_t* done, const float* bl, const float* Wp, const float* bp, const float* Wb, const float* bb,
+                               int T, int B, int A, float discounting, int clip_reward, float clip_rho, float clip_pg,
+                               float baseline_cost, float entropy_cost, float* logits, float* baseline, float* vs, float* pg,
+                               float* dlogits, float* dbaseline, __nv_bfloat16* dh, float* losses, float* scratch, cudaStream_t st);
 cudaError_t launch_impala_tail(const float* bl, const float* tl, const float* baseline, const int64_t* action, const float* reward,
                                const uint8_t* done, int T, int B, int A, float discounting, int clip_reward, float clip_rho,
                                float clip_pg, float baseline_cost, float entropy_cost, float* vs, float* pg, float* dlogits,
@@ -65,7 +71,7 @@ cudaError_t launch_head_fwd(const float* hpart, int nsplit, const float* bfc, fl
                             float* baseline, cudaStream_t st);
 cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const float* h, const float* reward, const int64_t* action,
                             const float* Wp, const float* Wb, int N, int A, __nv_bfloat16* dh, float* gWp, float* gbp, float* gWb,
-                            float* gbb, cudaStream_t st, cudaStream_t st_wgrad);
+                            float* gbb, cudaStream_t st, cudaStream_t st_wgrad, bool do_dh = true);
 cudaError_t launch_core_build(const float* hpart, int nsplit, const float* bfc, const float* reward, const int64_t* action, int N, int A, float* h,
                               float* core, cudaStream_t st);
 cudaError_t launch_head_dense_fwd(const float* X, const float* Wp, const float* bp, const float* Wb, const float* bb, int N, int A, float* logits,

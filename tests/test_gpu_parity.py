@@ -307,8 +307,30 @@ def test_conv_bias_gradients_equal_dy_column_sums_every_run(T, B):
             assert rel_l2(g.cpu(), first.cpu()) < 1e-5, it
 
 
+@pytest.mark.parametrize('T,B,A', [(5, 6, 6), (7, 19, 6), (33, 3, 6), (6, 5, 18), (4, 3, 1)])
+def test_column_kernel_equals_three_kernel_path(T, B, A, monkeypatch):
+    """heads + V-trace/losses + dh as ONE column kernel vs the head_fwd / impala_tail / head_bwd_dh kernels it replaces
+    (still used when (T+1) * 2 KB of shared memory does not fit): same losses, vs, advantages and gradients.
+    A = 18 exercises the 32-action instantiation, T = 33 the two-chunk scan."""
+    batch = {k: dev(v) for k, v in O.synthetic_batch(T, B, A, seed=31, done_p=0.15).items()}
+    outs = []
+    for no_fuse in ('0', '1'):
+        monkeypatch.setenv('SRL_NO_COLUMN_FUSION', no_fuse)
+        L, _ = _learner(T, B, A, 3, learning_rate=0.0)
+        st = L.learn(batch)
+        outs.append((st, L._vs.clone(), L._pg_adv.clone(), L.flat_grads.clone(), L.debug_buffer('logits'), L.debug_buffer('dh').float()))
+    (s0, vs0, pg0, g0, lg0, dh0), (s1, vs1, pg1, g1, lg1, dh1) = outs
+    for k in ('pg_loss', 'baseline_loss', 'entropy_loss', 'total_loss'):
+        assert abs(s0[k] - s1[k]) <= 1e-5 * max(1.0, abs(s1[k])), k
+    assert rel_l2(lg0.cpu(), lg1.cpu()) < 1e-6 and rel_l2(vs0.cpu(), vs1.cpu()) < 1e-5 and rel_l2(pg0.cpu(), pg1.cpu()) < 1e-4
+    assert rel_l2(dh0.cpu(), dh1.cpu()) < 2e-3                # bf16 rounding of values that differ in the last fp32 bits
+    assert rel_l2(g0.cpu(), g1.cpu()) < 2e-3
+
+
+@pytest.mark.parametrize('fusion', ['column_kernel', 'three_kernels'])
 @pytest.mark.parametrize('name', ['t5b4a6', 't3b5a4'])
-def test_learn_step_vs_reference_goldens(name):
+def test_learn_step_vs_reference_goldens(name, fusion, monkeypatch):
+    monkeypatch.setenv('SRL_NO_COLUMN_FUSION', '0' if fusion == 'column_kernel' else '1')   # heads+V-trace+dh fused or not
     g = np.load(os.path.join(GOLDEN, f'learn_{name}.npz'))
     T, B, A, seed, steps, clip = [int(v) for v in g['meta']]
     L, params = _learner(T, B, A, seed, reward_clipping='abs_one' if clip else 'none')
