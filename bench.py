@@ -441,10 +441,13 @@ def _main(real_stdout):
                'data': 'synthetic',
                'config': {'workload': f'IMPALA Pong 84x84x4 uint8, T={T}, B={B}/GPU, A={A}, synthetic trajectories (BASELINE.json configs[1] per GPU)',
                           'rollout_length': T, 'columns_per_gpu': B, 'global_batch': B * world, 'num_actions': A, 'optimizer': 'rmsprop', 'use_lstm': bool(args.use_lstm),
-                          'parallelism': f'dp{world}' if world > 1 else 'single', 'grad_allreduce': 'nccl sum' if world > 1 else 'none',
+                          'parallelism': f'dp{world}' if world > 1 else 'single',
+                          'grad_allreduce': 'none' if world == 1 else ('peer memory (NVLink loads) fused into the clip+optimizer kernel'
+                                                                     if getattr(learner, '_peers', None) is not None else 'nccl sum'),
                           'l2': f'inputs cycle through {POOL} distinct batches ({POOL * feeder.h2d_bytes / 1e6:.0f} MB > 126 MB L2)',
                           'operands': 'bf16 tensor-core operands, fp32 accumulate, fp32 master weights / V-trace / optimizer',
-                          'launch': 'one CUDA graph per step (wgrad GEMMs on a parallel branch)' if world == 1 else
+                          'launch': 'one CUDA graph per step (wgrad GEMMs on parallel branches, programmatic dependent launch)'
+                                    if (world == 1 or getattr(learner, '_peers', None) is not None) else
                                     'CUDA graphs begin|finish|apply; NCCL all-reduce of fc.weight overlaps the conv backward'},
                'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': feeder.h2d_bytes, 'd2h_bytes_per_step': feeder.d2h_bytes,
                        'ms_per_step': e2e_s / K * 1e3, 'api': 'HostBatchFeeder.submit/learn/result + B200ImpalaLearner.learn (pinned host batches)',

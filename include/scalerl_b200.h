@@ -139,6 +139,16 @@ int srl_learner_backward_finish(srl_learner_t* L, const uint8_t* obs, void* stre
  * are re-derived at the start of the next srl_learner_forward* call. */
 int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_out, void* stream);
 
+/* Data-parallel apply step over peer memory, replacing ncclAllReduce + srl_learner_apply_gradients (impala_atari.py:344-346
+ * on every rank): reduce-scatter of the flat gradient through NVLink loads, global-norm clip, optimizer and all-gather in ONE
+ * cooperative kernel (see heads_optim.cu).  grads[i] / exchange[i] / ctl[i] (i < world) are rank i's gradient buffer, its
+ * exchange buffer (4 * ceil(n/4 / world) + 4 floats: the reduced slice the peers pull) and its 1 KiB control block, all
+ * mapped into this process (symmetric memory / CUDA IPC); grads[rank] must be the buffer given to srl_learner_create; the
+ * control blocks start zeroed.  Every rank must call it once per step.  On return (stream order) the
+ * local gradient buffer holds the SUM over ranks, as after ncclAllReduce. */
+typedef struct { void* grads[8]; void* exchange[8]; void* ctl[8]; int rank; int world; } srl_dp_peers_t;
+int srl_learner_apply_gradients_dp(srl_learner_t* L, const srl_dp_peers_t* peers, float* grad_norm_and_coef_out, void* stream);
+
 /* borrow internal activations / operand copies for tests: name in {"a1","a2","a3","h","logits","baseline",
  * "dlogits","dbaseline","dh","da3","da2","da1","wpack"}; returns device pointer + element count. */
 int srl_learner_debug_buffer(srl_learner_t* L, const char* name, void** ptr, int64_t* count);

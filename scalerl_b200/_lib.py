@@ -12,6 +12,11 @@ LIB_PATH = os.path.join(_HERE, 'libscalerl_b200.so')
 _lib = None
 
 
+class SrlDpPeers(C.Structure):
+    """mirror of srl_dp_peers_t: peer-mapped gradient buffers and control blocks of a data-parallel group (<= 8 ranks)"""
+    _fields_ = [('grads', C.c_void_p * 8), ('exchange', C.c_void_p * 8), ('ctl', C.c_void_p * 8), ('rank', C.c_int32), ('world', C.c_int32)]
+
+
 class SrlConfig(C.Structure):
     """mirror of srl_config_t"""
     _fields_ = [('T', C.c_int32), ('B', C.c_int32), ('A', C.c_int32), ('optimizer', C.c_int32),
@@ -40,6 +45,7 @@ _SIGS = {
     'srl_learner_forward_lstm': [_P] * 12,
     'srl_learner_forward_backward_lstm': [_P] * 12,
     'srl_learner_apply_gradients': [_P, _P, _P],
+    'srl_learner_apply_gradients_dp': [_P, _P, _P, _P],
     'srl_learner_debug_buffer': [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_L)],
     'srl_lstm_create': [_I, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)],
     'srl_lstm_destroy': [_P],

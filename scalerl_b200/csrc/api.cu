@@ -554,6 +554,36 @@ extern "C" int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_ou
   return 0;
 }
 
+extern "C" int srl_learner_apply_gradients_dp(srl_learner_t* L, const srl_dp_peers_t* peers, float* grad_norm_out, void* stream) {
+  REQ(L && peers, "apply_gradients_dp: NULL argument");
+  REQ(peers->world >= 2 && peers->world <= 8 && peers->rank >= 0 && peers->rank < peers->world, "apply_gradients_dp: world=%d rank=%d",
+      peers->world, peers->rank);
+  REQ(peers->grads[peers->rank] == (void*)L->grads, "apply_gradients_dp: grads[rank] must be the learner's gradient buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const srl_config_t& c = L->cfg;
+  DpPeers P;
+  for (int i = 0; i < 8; ++i) {
+    P.g[i] = i < peers->world ? (float*)peers->grads[i] : nullptr;
+    P.ctl[i] = i < peers->world ? (unsigned*)peers->ctl[i] : nullptr;
+    P.rs[i] = i < peers->world ? (float*)peers->exchange[i] : nullptr;
+    REQ(i >= peers->world || (P.g[i] && P.ctl[i] && P.rs[i]), "apply_gradients_dp: NULL peer pointer %d", i);
+  }
+  P.rank = peers->rank; P.world = peers->world;
+  L->pf.st = st;
+  L->step += 1;
+  L->pf.b(PS_OPTIMIZER);
+  if (c.optimizer == 0) {
+    CU(launch_dp_clip_optim(0, L->params, L->grads, L->opt0, nullptr, L->nparams, c.max_grad_norm, L->coef, L->scratch + 2048,
+                            c.learning_rate, c.alpha, 0.f, c.epsilon, 0, nullptr, P, st), "dp clip+rmsprop");
+  } else {
+    CU(launch_dp_clip_optim(1, L->params, L->grads, L->opt0, L->opt1, L->nparams, c.max_grad_norm, L->coef, L->scratch + 2048,
+                            c.learning_rate, c.adam_beta1, c.adam_beta2, c.adam_eps, L->step, L->dstep, P, st), "dp clip+adam");
+  }
+  L->pf.e(PS_OPTIMIZER);
+  if (grad_norm_out) CU(cudaMemcpyAsync(grad_norm_out, L->coef, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy coef");
+  return 0;
+}
+
 extern "C" int srl_learner_set_profiling(srl_learner_t* L, int enable) {
   REQ(L, "learner is NULL");
   if (enable && !L->events[0])

@@ -2,6 +2,8 @@
 //   * policy / baseline heads forward + backward (atari_model.py:104-107,126-127 and their autograd)
 //   * bias-gradient column sums over bf16 dY
 //   * clip_grad_norm_ (impala_atari.py:344-345) + RMSprop (impala_atari.py:99-105,346) / Adam update
+#include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 #include <cooperative_groups.h>
@@ -483,6 +485,248 @@ cudaError_t launch_clip_optim(int optimizer, float* p, const float* g, float* s0
                               float* scratch, float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st) {
   return optimizer == 0 ? launch_clip_optim_t<0>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, st)
                         : launch_clip_optim_t<1>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Data-parallel apply step as ONE cooperative kernel over peer memory (NVLink / NVSwitch loads), no NCCL on the data path:
+//   barrier 1 (every rank finished its backward)
+//   phase 1   reduce-scatter: rank r sums slice r of the flat gradient over all ranks (NVLink loads from the peers' buffers,
+//             rank order) into its exchange buffer rs[r] (and in place), accumulating the slice's sum of squares
+//   barrier 2 (all slices reduced, per-slice sums of squares published to every rank)
+//   phase 2   all-gather by pull fused with clip_grad_norm_ + RMSprop/Adam: every rank reads each reduced slice from its
+//             owner's exchange buffer (so all replicas see the same bits), keeps a copy in its gradient buffer, and updates
+//             its own replica of the parameters
+// No closing barrier: the exchange buffers are separate from the gradient buffers, so the next backward may start while a
+// slow peer is still pulling; rs[r] is rewritten only after the next barrier 1, which that peer reaches after this kernel.
+// (Measured at N = 2: pulling beats pushing the reduced slice into every rank -- the system-scope fence after remote
+// stores waits 3-10 us for their acknowledgements.)
+// The gradient buffers and the control blocks are symmetric-memory allocations mapped into every rank
+// (torch.distributed._symmetric_memory); ctl[p] is rank p's control block: words [0,8) = barrier epochs written by each
+// source rank, [8,16) = per-slice sums of squares (float bits) written by each source rank, [32] = local epoch counter.
+// Cross-GPU waits are bounded (10 s of globaltimer, then trap): a lost peer becomes a CUDA error, not a hang.
+// ------------------------------------------------------------------------------------------------
+SRL_DEVINL float4 ld_sys_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+SRL_DEVINL float ld_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+SRL_DEVINL void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+SRL_DEVINL void st_relaxed_sys(unsigned* p, unsigned v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+SRL_DEVINL unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+SRL_DEVINL unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+SRL_DEVINL void st_sys_v4(float* p, const float4& v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// cross-GPU barrier, split in two: one block signals every rank, EVERY block waits on the local flags (thread q < world
+// waits for rank q).  Waits are bounded: 10 s of globaltimer, then trap.
+// fence = true when this block wrote remote memory that the flag publishes (the release store is cumulative over what the
+// thread observed through the block / grid barriers, but remote relaxed stores of another thread are fenced explicitly)
+SRL_DEVINL void dp_signal(const DpPeers& P, unsigned epoch, bool fence) {      // threads q < world of one block
+  if ((int)threadIdx.x < P.world) {
+    if (fence) __threadfence_system();
+    st_release_sys(P.ctl[threadIdx.x] + P.rank, epoch);
+  }
+}
+SRL_DEVINL void dp_wait(const DpPeers& P, unsigned epoch) {        // all threads of a block
+  if ((int)threadIdx.x < P.world) {
+    const unsigned* mine = P.ctl[P.rank] + threadIdx.x;
+    const unsigned long long t0 = global_ns();
+    unsigned spins = 0;
+    while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+      if ((++spins & 0x3FFu) == 0 && global_ns() - t0 > 10000000000ull) __trap();     // the timer is read every 1024 polls
+    }
+  }
+  __syncthreads();
+}
+
+template <int OPT>
+__global__ void __launch_bounds__(512) dp_clip_optim_kernel(float* __restrict__ p, float* g, float* __restrict__ s0, float* __restrict__ s1,
+                                                            int64_t n, float max_norm, float* coef, float* scratch, float lr, float a,
+                                                            float b, float eps, int step, int* dstep, const DpPeers P, int dbg) {
+  cg::grid_group grid = cg::this_grid();
+  const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = P.world, R = P.rank;
+  unsigned long long ts[8];
+  ts[0] = dbg ? global_ns() : 0;
+  const int64_t chunk = (n4 + W - 1) / W, lo = R * chunk, hi = min(n4, lo + chunk);
+  const int t = OPT == 1 ? (dstep ? *reinterpret_cast<volatile int*>(dstep) + 1 : step) : 0;
+  const unsigned e0 = reinterpret_cast<volatile unsigned*>(P.ctl[R])[32];     // epoch base (rewritten after the grid barrier)
+  // ---- barrier 1: every rank's backward is complete
+  if (blockIdx.x == 0) dp_signal(P, e0 + 1, false);      // the gradients were written by earlier kernels: already at L2
+  dp_wait(P, e0 + 1);
+  if (dbg) ts[1] = global_ns();
+  // ---- phase 1: reduce my slice over all ranks (rank order); the result goes to my exchange buffer rs (read by the peers
+  //      in phase 2) and, in place, to my gradient buffer
+  float s = 0.f;
+  float* rs_mine = P.rs[R];
+  for (int64_t i = lo + i0; i < hi; i += stride) {
+    float4 acc = ld_sys_v4(P.g[0] + 4 * i);
+    for (int q = 1; q < W; ++q) {
+      const float4 v = ld_sys_v4(P.g[q] + 4 * i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(rs_mine)[i - lo] = acc;
+    reinterpret_cast<float4*>(g)[i] = acc;
+    s += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+  }
+  if (R == W - 1 && blockIdx.x == 0 && (int64_t)threadIdx.x < (n & 3)) {     // the n % 4 tail belongs to the last slice
+    const int64_t i = n4 * 4 + threadIdx.x;
+    float acc = ld_sys_f32(P.g[0] + i);
+    for (int q = 1; q < W; ++q) acc += ld_sys_f32(P.g[q] + i);
+    rs_mine[4 * chunk + threadIdx.x] = acc;
+    g[i] = acc;
+    s += acc * acc;
+  }
+  __shared__ float red[16];
+  __shared__ float c_sh;
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.f;
+    for (int w = 0; w < 16; ++w) tsum += red[w];
+    scratch[4 + blockIdx.x] = tsum;
+    if (dbg) ts[2] = global_ns();
+    // the slice stores are local: the grid barrier makes them visible at L2, which is where the peers' NVLink loads land
+    if (dbg) ts[3] = global_ns();
+  }
+  grid.sync();
+  if (dbg) ts[4] = global_ns();
+  // ---- barrier 2: all slices pushed everywhere, per-slice sums of squares published
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < 32) {
+      double tsum = 0.0;
+      for (unsigned k = threadIdx.x; k < gridDim.x; k += 32) tsum += (double)__ldcg(scratch + 4 + k);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+      if (threadIdx.x == 0) {
+        for (int q = 0; q < W; ++q) st_relaxed_sys(P.ctl[q] + 8 + R, __float_as_uint((float)tsum));
+        reinterpret_cast<volatile unsigned*>(P.ctl[R])[32] = e0 + 2;          // every block has read e0 / dstep (grid barrier above)
+        if (OPT == 1 && dstep) *dstep = t;
+      }
+    }
+    __syncthreads();
+    dp_signal(P, e0 + 2, true);
+  }
+  dp_wait(P, e0 + 2);
+  if (dbg) ts[5] = global_ns();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int q = 0; q < W; ++q) tot += (double)__uint_as_float(reinterpret_cast<volatile unsigned*>(P.ctl[R])[8 + q]);
+    const float norm = (float)sqrt(tot);
+    const float c = max_norm >= 0.f ? fminf(max_norm / (norm + 1e-6f), 1.0f) : 1.0f;     // identical in every block of every rank
+    c_sh = c;
+    if (blockIdx.x == 0) { coef[0] = norm; coef[1] = c; }
+  }
+  __syncthreads();
+  const float c = c_sh;
+  // ---- phase 2: clip + optimizer on my replica; the gradient buffer is local and fully reduced now
+  float inv_bc1 = 0.f, inv_sqrt_bc2 = 0.f;
+  if (OPT == 1) {
+    inv_bc1 = 1.0f / (float)(1.0 - pow((double)a, (double)t));
+    inv_sqrt_bc2 = 1.0f / sqrtf((float)(1.0 - pow((double)b, (double)t)));
+  }
+  // the pulls of up to DP_PF iterations are issued before any of them is used: one NVLink round trip, not one per iteration
+  constexpr int DP_PF = 4;
+  for (int64_t ib = i0; ib < n4; ib += DP_PF * stride) {
+    float4 gpre[DP_PF];
+#pragma unroll
+    for (int u = 0; u < DP_PF; ++u) {
+      const int64_t i = ib + u * stride;
+      if (i < n4) {
+        const int owner = (int)min((int64_t)(W - 1), i / chunk);
+        gpre[u] = owner == R ? reinterpret_cast<const float4*>(g)[i] : ld_sys_v4(P.rs[owner] + 4 * (i - owner * chunk));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < DP_PF; ++u) {
+      const int64_t i = ib + u * stride;
+      if (i >= n4) break;
+      const float4 gg = gpre[u];
+      if ((int)min((int64_t)(W - 1), i / chunk) != R) reinterpret_cast<float4*>(g)[i] = gg;       // keep a copy: all-gather
+      float4 pp = reinterpret_cast<float4*>(p)[i], vv = reinterpret_cast<float4*>(s0)[i];
+      float* Pp = &pp.x; float* V = &vv.x; const float* G = &gg.x;
+      if (OPT == 0) {
+  #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float gk = G[k] * c;
+          V[k] = a * V[k] + (1.f - a) * gk * gk;
+          Pp[k] = Pp[k] - lr * (gk / (sqrtf(V[k]) + eps));
+        }
+      } else {
+        float4 ww = reinterpret_cast<float4*>(s1)[i];
+        float* Wv = &ww.x;
+  #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float gk = G[k] * c;
+          V[k] = a * V[k] + (1.f - a) * gk;                    // exp_avg
+          Wv[k] = b * Wv[k] + (1.f - b) * gk * gk;             // exp_avg_sq
+          Pp[k] = Pp[k] - (lr * inv_bc1) * (V[k] / (sqrtf(Wv[k]) * inv_sqrt_bc2 + eps));
+        }
+        reinterpret_cast<float4*>(s1)[i] = ww;
+      }
+      reinterpret_cast<float4*>(p)[i] = pp;
+      reinterpret_cast<float4*>(s0)[i] = vv;
+    }
+  }
+  if (blockIdx.x == 0 && (int64_t)threadIdx.x < (n & 3)) {
+    const int64_t i = n4 * 4 + threadIdx.x;
+    float gv;
+    if (R == W - 1) gv = g[i];
+    else { gv = ld_sys_f32(P.rs[W - 1] + 4 * chunk + threadIdx.x); g[i] = gv; }
+    const float gk = gv * c;
+    if (OPT == 0) {
+      s0[i] = a * s0[i] + (1.f - a) * gk * gk;
+      p[i] = p[i] - lr * (gk / (sqrtf(s0[i]) + eps));
+    } else {
+      const float mk = a * s0[i] + (1.f - a) * gk, vk = b * s1[i] + (1.f - b) * gk * gk;
+      s0[i] = mk; s1[i] = vk;
+      p[i] = p[i] - (lr * inv_bc1) * (mk / (sqrtf(vk) * inv_sqrt_bc2 + eps));
+    }
+  }
+  // no closing barrier: after barrier 2 no rank touches another rank's memory until the next step's barrier 1
+  if (dbg && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+    printf("dp_apply rank %d blk %d ns: wait1 %llu  phase1 %llu  fence %llu  gridsync %llu  sum+signal+wait2 %llu  phase2 %llu\n", R, blockIdx.x,
+           ts[1] - ts[0], ts[2] - ts[1], ts[3] - ts[2], ts[4] - ts[3], ts[5] - ts[4], global_ns() - ts[5]);
+}
+
+template <int OPT>
+static cudaError_t launch_dp_clip_optim_t(float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef, float* scratch,
+                                          float lr, float a, float b, float eps, int step, int* dstep, DpPeers P, cudaStream_t st) {
+  static int per_sm = 0, sms = 0;
+  if (!per_sm) {
+    int dev = 0;
+    SRL_TRY(cudaGetDevice(&dev));
+    SRL_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SRL_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_clip_optim_kernel<OPT>, 512, 0));
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  }
+  int64_t need = (n / 4 + 511) / 512;
+  int blocks = (int)(need < 1 ? 1 : need);
+  int cap = per_sm * sms; if (cap > 592) cap = 592;
+  if (blocks > cap) blocks = cap;
+  static int dbg = [] { const char* e = getenv("SRL_DP_DEBUG"); return e ? atoi(e) : 0; }();
+  void* args[] = {&p, &g, &s0, &s1, &n, &max_norm, &coef, &scratch, &lr, &a, &b, &eps, &step, &dstep, &P, &dbg};
+  return cudaLaunchCooperativeKernel((const void*)dp_clip_optim_kernel<OPT>, dim3(blocks), dim3(512), args, 0, st);
+}
+cudaError_t launch_dp_clip_optim(int optimizer, float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
+                                 float* scratch, float lr, float a, float b, float eps, int step, int* dstep, const DpPeers& P,
+                                 cudaStream_t st) {
+  return optimizer == 0 ? launch_dp_clip_optim_t<0>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, P, st)
+                        : launch_dp_clip_optim_t<1>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, P, st);
 }
 
 }  // namespace srl

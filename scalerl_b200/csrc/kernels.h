@@ -83,6 +83,10 @@ cudaError_t launch_unpack_slots(const uint8_t* staging, int64_t slot_bytes, cons
                                 uint8_t* done, int64_t* action, float* logits, float* episode_return, cudaStream_t st);
 cudaError_t launch_clip_optim(int optimizer, float* p, const float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
                               float* scratch, float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st);
+struct DpPeers { float* g[8]; float* rs[8]; unsigned* ctl[8]; int rank, world; };      // peer-mapped gradient buffers / control blocks
+cudaError_t launch_dp_clip_optim(int optimizer, float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
+                                 float* scratch, float lr, float a, float b, float eps, int step, int* dstep, const DpPeers& P,
+                                 cudaStream_t st);
 cudaError_t launch_grad_norm(const float* g, int64_t n, float max_norm, float* coef, float* scratch, cudaStream_t st);
 cudaError_t launch_rmsprop(float* p, const float* g, float* v, int64_t n, const float* coef, float lr, float alpha, float eps,
                            cudaStream_t st);

@@ -115,6 +115,9 @@ class B200ImpalaLearner:
             self.numel = total
             z = lambda: torch.zeros(total, dtype=torch.float32, device=self.device)
             self.flat_params, self.flat_grads, self.opt_state0 = z(), z(), z()
+            self._peers = None
+            if self._dist and os.environ.get('SRL_DP_FUSED', '1') != '0':
+                self._setup_peer_memory(total)       # replaces flat_grads by a symmetric-memory buffer when that works
             self.opt_state1 = z() if hp.optimizer == 'adam' else None
             self.shapes = param_shapes(hp.num_actions, hp.use_lstm)
             self.params = OrderedDict((n, self._view(self.flat_params, i)) for i, n in enumerate(self.names))
@@ -141,6 +144,45 @@ class B200ImpalaLearner:
         self.use_graph = use_graph and not os.environ.get('SRL_NO_GRAPH')   # SRL_NO_GRAPH=1: eager launches (for ncu)
         self._graphs = {}       # batch buffer addresses -> captured CUDA graph(s) of the step
         self._seen = set()
+
+    def _setup_peer_memory(self, total):
+        """Gradient buffer + 1 KiB control block in symmetric memory (every rank maps every rank's copy): the apply step
+        then reduces, clips, updates and gathers in one kernel over NVLink loads (srl_learner_apply_gradients_dp) and the
+        step needs no NCCL call.  Any failure (no P2P, > 8 ranks, API missing) leaves the NCCL path in place."""
+        dist = torch.distributed
+        ok = torch.ones(1, device=self.device)
+        peers = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.pg or dist.group.WORLD
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            if world > 8:
+                raise RuntimeError('more than 8 ranks')
+            grads = symm.empty(total, dtype=torch.float32, device=self.device)
+            ctl = symm.empty(256, dtype=torch.int32, device=self.device)
+            chunk4 = ((total // 4) + world - 1) // world             # float4s per reduced slice
+            exch = symm.empty(4 * chunk4 + 4, dtype=torch.float32, device=self.device)
+            hg, hc, hx = symm.rendezvous(grads, group), symm.rendezvous(ctl, group), symm.rendezvous(exch, group)
+            grads.zero_(); ctl.zero_(); exch.zero_()
+            torch.cuda.synchronize(self.device)
+            peers = _lib.SrlDpPeers()
+            for i in range(world):
+                peers.grads[i] = int(hg.buffer_ptrs[i]); peers.ctl[i] = int(hc.buffer_ptrs[i]); peers.exchange[i] = int(hx.buffer_ptrs[i])
+            peers.rank, peers.world = rank, world
+            if int(hg.buffer_ptrs[rank]) != grads.data_ptr():
+                raise RuntimeError('symmetric buffer is not at the tensor address')
+            self._symm_keep = (grads, ctl, hg, hc, exch, hx)
+        except Exception as e:         # noqa: BLE001 -- any failure means "use NCCL"
+            import warnings
+            warnings.warn(f'peer-memory gradient path unavailable ({e!r}); using NCCL all-reduce')
+            ok.zero_()
+            peers = None
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.pg or None)     # all ranks take the same path (and: a barrier)
+        if bool(ok.item()) and peers is not None:
+            self.flat_grads = self._symm_keep[0]
+            self._peers = peers
+        else:
+            self._peers = None
 
     # ------------------------------------------------------------------ parameters
     def _view(self, flat, i):
@@ -304,9 +346,20 @@ class B200ImpalaLearner:
         _lib.check(self._L.srl_learner_apply_gradients(self._h, self._coef.data_ptr(), self._stream()), 'srl_learner_apply_gradients')
         self._opt_steps = self.global_opt_step + 1
 
+    @torch.no_grad()
+    def apply_gradients_dp(self):
+        """all ranks: SUM-reduce the gradients over peer memory, clip, optimizer step -- one kernel, no NCCL"""
+        _lib.check(self._L.srl_learner_apply_gradients_dp(self._h, C.byref(self._peers), self._coef.data_ptr(), self._stream()),
+                   'srl_learner_apply_gradients_dp')
+        self._opt_steps = self.global_opt_step + 1
+
     def _enqueue_step(self, batch):
         """forward_backward -> apply_gradients on the current stream; with world_size > 1 the fc.weight gradient is
         all-reduced (async, NCCL stream) while the conv layers back-propagate, the small block afterwards."""
+        if self._dist and self._peers is not None:
+            self.forward_backward(batch)
+            self.apply_gradients_dp()
+            return
         if not self._dist or self.hp.use_lstm:
             self.forward_backward(batch)
             if self._dist:          # LSTM path: one all-reduce of the whole flat gradient after BPTT
@@ -349,7 +402,12 @@ class B200ImpalaLearner:
             hp = self.hp
             self._check_batch(batch, hp.rollout_length + 1)
             torch.cuda.current_stream(self.device).synchronize()
-            if self._dist and self.hp.use_lstm:
+            if self._dist and self._peers is not None:     # whole DP step in ONE graph: the reduction is inside the apply kernel
+                g = (torch.cuda.CUDAGraph(),)
+                with torch.cuda.graph(g[0]):
+                    self.forward_backward(batch)
+                    self.apply_gradients_dp()
+            elif self._dist and self.hp.use_lstm:
                 g = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph())
                 with torch.cuda.graph(g[0]):
                     self.forward_backward(batch)

@@ -24,25 +24,37 @@ def main():
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     T, A, B = 6, 6, 4 * world
     params = O.init_params(A, seed=11)
-    shard = B200ImpalaLearner(ImpalaHParams(rollout_length=T, batch_size=B // world, num_actions=A), init_state_dict=params)
-    full = B200ImpalaLearner(ImpalaHParams(rollout_length=T, batch_size=B, num_actions=A), init_state_dict=params, process_group=False) \
-        if rank == 0 else None
     batch = {k: v.cuda() for k, v in O.synthetic_batch(T, B, A, seed=5, done_p=0.1).items()}
     mine = {k: v.contiguous() for k, v in par.shard_columns(batch, rank, world).items()}
-    worst = 0.0
-    for step in range(4):
-        s = shard.learn(mine)
+    for optimizer in ('rmsprop', 'adam'):
+        shard = B200ImpalaLearner(ImpalaHParams(rollout_length=T, batch_size=B // world, num_actions=A, optimizer=optimizer),
+                                  init_state_dict=params)
+        full = B200ImpalaLearner(ImpalaHParams(rollout_length=T, batch_size=B, num_actions=A, optimizer=optimizer),
+                                 init_state_dict=params, process_group=False) if rank == 0 else None
+        path = 'peer memory (fused reduce+clip+optimizer kernel)' if shard._peers is not None else 'NCCL all-reduce'
+        worst = 0.0
+        for step in range(5):
+            s = shard.learn(mine)
+            if rank == 0:
+                f = full.learn(batch)
+                rel = float((shard.flat_params - full.flat_params).norm() / full.flat_params.norm())
+                gl = float((shard.flat_grads - full.flat_grads).norm() / full.flat_grads.norm())
+                worst = max(worst, rel)
+                print(f'{optimizer} step {step}: total_loss shard-sum {s["total_loss"]:.5f} full {f["total_loss"]:.5f} | grad rel-L2 {gl:.2e} | '
+                      f'param rel-L2 {rel:.2e} | grad_norm {s["grad_norm"]:.4f} vs {f["grad_norm"]:.4f} | graphs {len(shard._graphs)} '
+                      f'(nodes per step: {[len(g) for g in shard._graphs.values()]})', flush=True)
+                assert abs(s['grad_norm'] - f['grad_norm']) <= 1e-4 * f['grad_norm']
+        # replicas must stay bit-identical: compare an integer checksum of the weights over the ranks
+        chk = shard.flat_params.view(torch.int32).to(torch.int64).sum().reshape(1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
         if rank == 0:
-            f = full.learn(batch)
-            rel = float((shard.flat_params - full.flat_params).norm() / full.flat_params.norm())
-            gl = float((shard.flat_grads - full.flat_grads).norm() / full.flat_grads.norm())
-            worst = max(worst, rel)
-            print(f'step {step}: total_loss shard-sum {s["total_loss"]:.5f} full {f["total_loss"]:.5f} | grad rel-L2 {gl:.2e} | '
-                  f'param rel-L2 {rel:.2e} | graphs {len(shard._graphs)} (nodes per step: {[len(g) for g in shard._graphs.values()]})', flush=True)
+            assert all(int(c) == int(allc[0]) for c in allc), [int(c) for c in allc]
+            assert worst < 1e-4, worst
+            print(f'{optimizer}: gradient path = {path}; replicas bit-identical on {world} ranks', flush=True)
+        shard.release_graphs()
     if rank == 0:
-        assert worst < 1e-4, worst
         print('DP CHECK OK', flush=True)
-    shard.release_graphs()
     dist.barrier(device_ids=[local])
     os._exit(0)
 
