@@ -483,3 +483,21 @@ def test_full_size_cfg3_sharding_property():
     assert rel_l2(acc.cpu(), g_full.cpu()) < 2e-4
     assert torch.allclose(loss_acc.cpu(), loss_full.cpu(), rtol=1e-4, atol=1e-2)
     assert torch.isfinite(g_full).all()
+
+
+def test_programmatic_dependent_launch_waits_for_the_primary_grid():
+    """The step's kernels are chained with programmatic stream serialization; every kernel relies on
+    griddepcontrol.wait returning only after the previous grid completed and flushed.  Self-test: kernel A spins ~20 us
+    then sets a flag, kernel B (512 blocks, launched with the attribute) records the flag after its wait -- on the
+    legacy default stream and on a created stream."""
+    from scalerl_b200 import _lib
+    L = _lib.lib()
+    flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+    out = torch.zeros(512, dtype=torch.int32, device='cuda')
+    for st in (None, torch.cuda.Stream()):
+        for _ in range(20):
+            out.zero_()
+            torch.cuda.synchronize()
+            _lib.check(L.srl_test_pdl(flag.data_ptr(), out.data_ptr(), 512, 20000, st.cuda_stream if st else None))
+            torch.cuda.synchronize()
+            assert int((out != 1).sum()) == 0
