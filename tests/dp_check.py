@@ -2,9 +2,12 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/dp_check.py
 
-Every rank learns on its column shard (NCCL SUM all-reduce inside the step, captured in the CUDA graph); rank 0 also runs
-a single-GPU learner on the FULL batch.  After 4 steps (eager warm-up, capture, 2 replays) the sharded weights must equal
-the full-batch weights (up to fp32 summation order) -- the property SURVEY.md §8e asks for."""
+Every rank learns on its column shard (gradient SUM over the ranks inside the step -- peer-memory apply kernel, or NCCL --
+captured in the CUDA graph); rank 0 also runs a single-GPU learner on the FULL batch.  Every step (eager warm-up, capture,
+replays) the sharded gradients / weights must equal the full-batch ones up to fp32 summation order -- the property
+SURVEY.md §8e asks for.  After each comparison the full-batch learner is re-synchronised to the sharded state: one bf16
+rounding flip of a weight or a ReLU mask turns 1e-7 into 1e-4 a step later (seen at N = 8), which says nothing about the
+reduction."""
 import os
 import sys
 
@@ -43,7 +46,11 @@ def main():
                 print(f'{optimizer} step {step}: total_loss shard-sum {s["total_loss"]:.5f} full {f["total_loss"]:.5f} | grad rel-L2 {gl:.2e} | '
                       f'param rel-L2 {rel:.2e} | grad_norm {s["grad_norm"]:.4f} vs {f["grad_norm"]:.4f} | graphs {len(shard._graphs)} '
                       f'(nodes per step: {[len(g) for g in shard._graphs.values()]})', flush=True)
-                assert abs(s['grad_norm'] - f['grad_norm']) <= 1e-4 * f['grad_norm']
+                assert abs(s['grad_norm'] - f['grad_norm']) <= 1e-4 * f['grad_norm'] and gl < 1e-4 and rel < 1e-5
+                full.flat_params.copy_(shard.flat_params)                      # next step starts from identical state
+                full.opt_state0.copy_(shard.opt_state0)
+                if full.opt_state1 is not None:
+                    full.opt_state1.copy_(shard.opt_state1)
         # replicas must stay bit-identical: compare an integer checksum of the weights over the ranks
         chk = shard.flat_params.view(torch.int32).to(torch.int64).sum().reshape(1)
         allc = [torch.zeros_like(chk) for _ in range(world)]
