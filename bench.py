@@ -367,7 +367,9 @@ def _main(real_stdout):
         gemm[slot] = {'ms': ms, 'gflop': fl / 1e9, 'tflops': fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, 'bytes': by,
                       'gbs': by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0, 'intensity': fl / by,
                       'bound': 'tensor' if fl / by >= ridge else 'hbm'}
-    dom = max(gemm, key=lambda s: gemm[s]['ms'])
+    # dominant kernel = the longest GEMM on the step's critical chain (fc/conv3/conv2 wgrad run on side branches beside it)
+    CHAIN = ('conv1_fwd', 'conv2_fwd', 'conv3_fwd', 'fc_fwd', 'fc_dgrad', 'conv3_dgrad', 'conv2_dgrad', 'conv1_wgrad')
+    dom = max(CHAIN, key=lambda s: gemm[s]['ms'])
     traffic, traffic_src, tensor_pct = None, None, None
     tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if os.path.exists(tp) and (T, B) == (T_DEFAULT, B_DEFAULT):      # the ncu capture was taken at the default workload
@@ -390,6 +392,7 @@ def _main(real_stdout):
                 'traffic': traffic, 'traffic_unit': 'bytes (dram read+write per launch)',
                 'traffic_source': traffic_src, 'ncu_tensor_pipe_active_pct': tensor_pct,
                 'peak_source': pk['source'] + (' HBM copy bandwidth' if hbm_bound else ' burst bf16') + ' (MEASURED_PEAKS.json)',
+                'dominant_rule': 'longest GEMM launch on the critical chain of the step graph (side-branch wgrads overlap it; all kernels in per_gemm)',
                 'bound_why': f"arithmetic intensity {d['intensity']:.0f} flop/B (algorithmic) vs ridge {ridge:.0f} flop/B "
                              f"(measured bf16 peak / measured HBM peak)",
                 'algorithmic_bytes_per_launch': d['bytes'], 'flops_per_launch': d['gflop'] * 1e9, 'ms_per_launch': d['ms'],
