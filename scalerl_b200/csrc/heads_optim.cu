@@ -503,7 +503,7 @@ cudaError_t launch_clip_optim(int optimizer, float* p, const float* g, float* s0
 // The gradient buffers and the control blocks are symmetric-memory allocations mapped into every rank
 // (torch.distributed._symmetric_memory); ctl[p] is rank p's control block: words [0,8) = barrier epochs written by each
 // source rank, [8,16) = per-slice sums of squares (float bits) written by each source rank, [32] = local epoch counter.
-// Cross-GPU waits are bounded (10 s of globaltimer, then trap): a lost peer becomes a CUDA error, not a hang.
+// Cross-GPU waits are bounded (30 s of globaltimer, then trap): a lost peer becomes a CUDA error, not a hang.
 // ------------------------------------------------------------------------------------------------
 SRL_DEVINL float4 ld_sys_v4(const float* p) {
   float4 v;
@@ -531,7 +531,7 @@ SRL_DEVINL void st_sys_v4(float* p, const float4& v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 // cross-GPU barrier, split in two: one block signals every rank, EVERY block waits on the local flags (thread q < world
-// waits for rank q).  Waits are bounded: 10 s of globaltimer, then trap.
+// waits for rank q).  Waits are bounded: 30 s of globaltimer, then trap.
 // fence = true when this block wrote remote memory that the flag publishes (the release store is cumulative over what the
 // thread observed through the block / grid barriers, but remote relaxed stores of another thread are fenced explicitly)
 SRL_DEVINL void dp_signal(const DpPeers& P, unsigned epoch, bool fence) {      // threads q < world of one block
@@ -546,7 +546,7 @@ SRL_DEVINL void dp_wait(const DpPeers& P, unsigned epoch) {        // all thread
     const unsigned long long t0 = global_ns();
     unsigned spins = 0;
     while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-      if ((++spins & 0x3FFu) == 0 && global_ns() - t0 > 10000000000ull) __trap();     // the timer is read every 1024 polls
+      if ((++spins & 0x3FFu) == 0 && global_ns() - t0 > 30000000000ull) __trap();     // the timer is read every 1024 polls
     }
   }
   __syncthreads();

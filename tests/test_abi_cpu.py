@@ -42,6 +42,30 @@ def test_config_struct_size():
     assert ctypes.sizeof(_lib.SrlConfig) == 19 * 4
 
 
+def test_dp_peers_struct_and_argument_checks():
+    """srl_dp_peers_t: 3 x 8 pointers + rank + world; bad descriptors are rejected before any CUDA call"""
+    assert ctypes.sizeof(_lib.SrlDpPeers) == 3 * 8 * 8 + 8
+    L = _lib.lib()
+    assert L.srl_learner_apply_gradients_dp(None, None, None, None) == -1
+    assert b'NULL' in L.srl_last_error()
+
+
+def test_bench_roofline_tables_are_consistent():
+    """bench.py's algorithmic flops / bytes tables: same kernels, intensities in the range DESIGN.md quotes"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert set(b.SLOT_FLOPS) == set(b.SLOT_BYTES)
+    NF, NB = 21 * 32, 20 * 32
+    ai = {}
+    for slot, (layer, which) in b.SLOT_FLOPS.items():
+        n = NF if which == 'fwd' else NB
+        ai[slot] = 2.0 * b.MACS[layer] * n / (b.SLOT_BYTES[slot][0] * n + b.SLOT_BYTES[slot][1])
+    assert 75 < ai['conv1_wgrad'] < 85 and 75 < ai['conv1_fwd'] < 85 and 140 < ai['conv2_fwd'] < 155 and 205 < ai['conv3_fwd'] < 225
+    assert all(v < 600 for v in ai.values())
+
+
 def test_argument_errors_without_gpu(lib):
     L = _lib.lib()
     # NULL pointers / bad shapes are rejected before any CUDA call
