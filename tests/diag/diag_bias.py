@@ -1,6 +1,6 @@
 """diagnostic: conv bias gradients of the device step vs the bf16-emulating oracle at several sizes"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import impala_oracle as O
 from scalerl_b200.learner import B200ImpalaLearner, ImpalaHParams

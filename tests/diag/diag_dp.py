@@ -1,6 +1,6 @@
 """torchrun diagnostic: phase times of the fused peer-memory apply kernel (SRL_DP_DEBUG=1) at the bench workload"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, torch.distributed as dist
 from oracle import impala_oracle as O
 from scalerl_b200.learner import B200ImpalaLearner, ImpalaHParams

@@ -1,6 +1,6 @@
 """diagnostic: is forward_backward repeatable (per tensor) with / without shared-memory poisoning; conv1.bias vs sum(da1)"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import impala_oracle as O
 from scalerl_b200 import _lib
