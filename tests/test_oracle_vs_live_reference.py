@@ -91,3 +91,67 @@ def test_atarinet_forward_random_weights(ref, A, seed):
     lg, bs = O.atari_forward(params, batch['obs'], batch['reward'], batch['action'])
     assert torch.allclose(lg.view(T + 1, B, A), out['policy_logits'], rtol=1e-4, atol=1e-5)
     assert torch.allclose(bs.view(T + 1, B), out['baseline'], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_per_trees_random_against_reference_segment_trees(seed):
+    """scalerl/data/segment_tree.py driven by the statements of PrioritizedReplayBuffer (replay_buffer.py:318-381) vs the
+    PER oracle: random capacities (incl. wrap-around of the ring pointer), duplicate update indices, several rounds"""
+    from oracle.per_oracle import PerOracle
+    seg = _load('live_ref_segment_tree', '/root/reference/scalerl/data/segment_tree.py')
+    rng = np.random.RandomState(300 + seed)
+    mem = int(rng.choice([7, 64, 100, 333, 1024]))
+    alpha, beta = float(rng.choice([0.4, 0.6, 1.0])), float(rng.choice([0.4, 0.7, 1.0]))
+    cap = 1
+    while cap < mem:
+        cap *= 2
+    st, mt = seg.SumSegmentTree(cap), seg.MinSegmentTree(cap)
+    o = PerOracle(mem, alpha)
+    max_p, ptr, size = 1.0, 0, 0
+    for rnd in range(3):
+        nadd = int(rng.randint(1, 2 * mem))
+        for _ in range(nadd):
+            st[ptr] = max_p ** alpha
+            mt[ptr] = max_p ** alpha
+            ptr = (ptr + 1) % mem
+            size = min(size + 1, mem)
+        o.add(nadd)
+        k = int(rng.randint(1, 50))
+        idx = rng.randint(0, size, size=k)                       # duplicates on purpose: last write wins
+        pr = rng.rand(k) * 4 + 1e-3
+        for i, p in zip(idx, pr):
+            st[int(i)] = float(p) ** alpha
+            mt[int(i)] = float(p) ** alpha
+            max_p = max(max_p, float(p))
+        o.update_priorities(idx, pr)
+        batch = int(rng.randint(1, 40))
+        u = rng.rand(batch)
+        p_total = st.sum(0, size - 1)
+        segment = p_total / batch
+        want = [st.find_prefixsum_idx(segment * i + (segment * (i + 1) - segment * i) * float(u[i])) for i in range(batch)]
+        p_min = mt.min() / st.sum()
+        max_w = (p_min * size) ** (-beta)
+        want_w = [((st[i] / st.sum()) * size) ** (-beta) / max_w for i in want]
+        got, got_w = o.sample(u, beta)
+        assert np.array_equal(got, np.array(want, dtype=np.int64)), (seed, rnd)
+        assert np.array_equal(got_w, np.array(want_w, dtype=np.float64))
+        assert o.size == size and o.max_priority == max_p and o.sum_tree.operate() == st.sum() and o.min_tree.operate() == mt.min()
+
+
+@pytest.mark.parametrize('A,seed', [(6, 0), (3, 1)])
+def test_atarinet_lstm_forward_random(ref, A, seed):
+    """use_lstm=True (atari_model.py:52-55,109-120): the oracle's step-wise 2-layer LSTM with done-resets and a random
+    initial state vs the reference module holding the same weights"""
+    net = ref['atari_model'].AtariNet((4, 84, 84), A, use_lstm=True)
+    params, lp = O.init_params(A, seed=seed), O.init_lstm_params(A, seed=seed)
+    net.load_state_dict({**params, **lp})
+    T, B = 4, 3
+    batch = O.synthetic_batch(T, B, A, seed=seed + 7, done_p=0.3)
+    g = torch.Generator().manual_seed(seed)
+    state = (torch.randn(2, B, 513 + A, generator=g) * 0.1, torch.randn(2, B, 513 + A, generator=g) * 0.1)
+    with torch.no_grad():
+        out, ns = net(batch, state)
+        lg, bs, os_ = O.atari_forward_lstm(params, lp, batch['obs'], batch['reward'], batch['action'], batch['done'], state)
+    assert torch.allclose(lg.view(T + 1, B, A), out['policy_logits'], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(bs.view(T + 1, B), out['baseline'], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(os_[0], ns[0], rtol=1e-4, atol=1e-5) and torch.allclose(os_[1], ns[1], rtol=1e-4, atol=1e-5)
