@@ -60,6 +60,19 @@ int srl_impala_loss_and_head_grads(const float* behavior_logits, const float* ta
                                    float* vs, float* pg_advantages, float* dlogits, float* dbaseline,
                                    float* losses, float* scratch, void* stream);
 
+/* ---- row-wise policy ops: the pieces of loss_fn.py / vtrace.action_log_probs as stand-alone, differentiable operators ------
+ * (used by the autograd drop-ins scalerl_b200/algorithms/impala/{loss_fn,vtrace}.py; the learner step itself uses the fused tail)
+ * forward : logp[n] = log_softmax(logits[n])[actions[n]] (vtrace.py:31-40; loss_fn.py:16-23), ent[n] = sum_a p log p (loss_fn.py:9-13);
+ *           logits f32 [N,A], actions i64 [N]; either output may be NULL (actions may be NULL when logp is).
+ * backward: dlogits[n][a] = w_logp[n] * (1{a == actions[n]} - p[a]) + w_ent[n] * p[a] * (log p[a] - ent[n]) -- the gradient of
+ *           sum_n w_logp[n] logp[n] + w_ent[n] ent[n]; a NULL weight array means zeros.
+ * srl_reduce_sum: out[0] = scale * sum x[i] (square = 0) or scale * sum x[i]^2 (square = 1), fixed summation order
+ *           (loss_fn.py:5-6 compute_baseline_loss = 0.5 * sum(adv^2)). */
+int srl_policy_rows_forward(const float* logits, const int64_t* actions, int64_t N, int A, float* logp, float* ent, void* stream);
+int srl_policy_rows_backward(const float* logits, const int64_t* actions, const float* w_logp, const float* w_ent, int64_t N, int A,
+                             float* dlogits, void* stream);
+int srl_reduce_sum(const float* x, int64_t n, int square, float scale, float* out, void* stream);
+
 /* ---- learner context: encoder fwd/bwd on tcgen05 + heads + optimizer ------------------------------------
  * replaces AtariNet.forward (scalerl/algorithms/utils/atari_model.py:77-143, use_lstm=False) and
  * ImpalaTrainer.learn (impala_atari.py:270-349) for one GPU's shard of the batch.                         */
@@ -68,7 +81,7 @@ typedef struct srl_learner srl_learner_t;
 typedef struct srl_config {
   int32_t T;                 /* rollout_length                                   */
   int32_t B;                 /* batch columns processed by THIS GPU              */
-  int32_t A;                 /* num_actions (<= 32)                              */
+  int32_t A;                 /* num_actions (<= 31)                              */
   int32_t optimizer;         /* 0 = RMSprop (reference, impala_atari.py:99-105), 1 = Adam */
   int32_t reward_clip_abs_one;
   int32_t simt_mainloop;     /* reserved, must be 0 (TMA-fed tcgen05 mainloop) */
@@ -101,6 +114,15 @@ int srl_learner_destroy(srl_learner_t* L);
 int64_t srl_learner_workspace_bytes(const srl_learner_t* L);
 /* update a hyper-parameter that does not change buffer sizes (lr, costs, clip...) */
 int srl_learner_set_config(srl_learner_t* L, const srl_config_t* cfg);
+
+/* run-time switches of one learner context: "column_fusion" (default 1; 0 = three kernels head_fwd / impala_tail / head_bwd
+ * instead of the fused column kernel -- the environment variable SRL_NO_COLUMN_FUSION is read once, at creation) */
+int srl_learner_set_option(srl_learner_t* L, const char* name, int value);
+
+/* optimizer step count (Adam's bias-correction t; torch.optim state['step']): restore it when resuming from a checkpoint
+ * (host counter and the device-resident counter the captured graphs read).  Both synchronise `stream`. */
+int srl_learner_set_step(srl_learner_t* L, int64_t step, void* stream);
+int64_t srl_learner_get_step(srl_learner_t* L, void* stream);
 
 /* re-derive the packed bf16 operand copies from the fp32 master parameters now (optional: every forward does it) */
 int srl_learner_pack_weights(srl_learner_t* L, void* stream);
@@ -149,6 +171,12 @@ int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_out, void* st
 typedef struct { void* grads[8]; void* exchange[8]; void* ctl[8]; int rank; int world; } srl_dp_peers_t;
 int srl_learner_apply_gradients_dp(srl_learner_t* L, const srl_dp_peers_t* peers, float* grad_norm_and_coef_out, void* stream);
 
+/* Weight-publish snapshot (impala_atari.py:348, actor_model.load_state_dict(learner_model.state_dict())): copies the flat fp32
+ * parameters to `dst` (same layout, srl_param_layout elements) on `stream` -- unless losses[3] (the step's total loss, device
+ * f32[4]; may be NULL = unconditional) is NaN/Inf, in which case `dst` keeps the last good weights.  The caller then copies
+ * `dst` to the actors' host memory asynchronously while the next step already updates the live parameters. */
+int srl_learner_snapshot_params(srl_learner_t* L, float* dst, const float* losses, void* stream);
+
 /* borrow internal activations / operand copies for tests: name in {"a1","a2","a3","h","logits","baseline",
  * "dlogits","dbaseline","dh","da3","da2","da1","wpack"}; returns device pointer + element count. */
 int srl_learner_debug_buffer(srl_learner_t* L, const char* name, void** ptr, int64_t* count);
@@ -190,6 +218,9 @@ int64_t srl_per_size(const srl_per_t* P);
 int64_t srl_per_capacity(const srl_per_t* P);
 int srl_per_add(srl_per_t* P, int64_t n, void* stream);                                  /* _add x n  (replay_buffer.py:318-322) */
 int srl_per_update_priorities(srl_per_t* P, const int64_t* idxs, const double* priorities, int64_t n, void* stream);   /* :346-351 */
+/* pairs skipped so far by srl_per_update_priorities because idx was outside [0, size) or priority <= 0 (the reference asserts
+ * both, replay_buffer.py:346-351); synchronises `stream`; -1 on error */
+int64_t srl_per_invalid_updates(srl_per_t* P, void* stream);
 int srl_per_sample(srl_per_t* P, const double* uniforms, int batch, double beta, int64_t* idxs, double* weights64,
                    float* weights32, void* stream);                                      /* :353-381, uniforms f64 [batch] in [0,1) */
 int srl_per_debug_trees(srl_per_t* P, double* sum_out, double* min_out, double* max_priority_out, void* stream);
@@ -211,20 +242,6 @@ int srl_rmsprop_step(float* params, const float* grads, float* square_avg, int64
                      float lr, float alpha, float eps, void* stream);
 int srl_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* coef,
                   float lr, float beta1, float beta2, float eps, int step, void* stream);
-
-/* ---- unit-test GEMMs for the tcgen05 mainloop (bf16 in, f32 out) -------------------------------------------
- * kmajor : D[M,N] = A[M,K] . B[N,K]^T   (K%64==0, N%64==0)
- * mnmajor: D[M,N] = At[K,M]^T . Bt[K,N] (M%128==0, N%64==0) */
-int srl_test_gemm_kmajor(const void* A, const void* B, float* D, int M, int N, int K, int simt, void* stream);
-int srl_test_gemm_mnmajor(const void* At, const void* Bt, float* D, int M, int N, int K, int simt, void* stream);
-/* descriptor experiment: operand windows that start at an arbitrary 128-byte row of a SWIZZLE_128B tile.
- * kmajor (mn_major=0): A bf16 [160,64], B bf16 [64,64]  -> D[128,64] = A[shift:shift+128] . B^T
- * mnmajor (=1)       : A bf16 [96,128], B bf16 [96,64]  -> D[128,64] = A[shift:shift+64]^T . B[shift:shift+64]   (shift <= 32) */
-int srl_test_shifted_operand(const void* A, const void* B, float* D, int shift, int mn_major, int base_offset_mode, void* stream);
-/* test utility: fills the shared memory of every SM with quiet-NaN bit patterns (kernels must never depend on stale smem) */
-int srl_test_poison_smem(void* stream);
-/* test utility: programmatic-dependent-launch self test; every out[0..nblk) must read 1 (flag, out: device int buffers) */
-int srl_test_pdl(int* flag, int* out, int nblk, unsigned delay_ns, void* stream);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,9 @@ _SIGS = {
     'srl_vtrace_from_importance_weights': [_P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _I, _P],
     'srl_vtrace_from_logits': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
     'srl_impala_loss_and_head_grads': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P],
+    'srl_policy_rows_forward': [_P, _P, _L, _I, _P, _P, _P],
+    'srl_policy_rows_backward': [_P, _P, _P, _P, _L, _I, _P, _P],
+    'srl_reduce_sum': [_P, _L, _I, _F, _P, _P],
     'srl_learner_create': [C.POINTER(SrlConfig), _P, _P, _P, _P, C.POINTER(_P)],
     'srl_learner_destroy': [_P],
     'srl_learner_set_config': [_P, C.POINTER(SrlConfig)],
@@ -61,18 +64,52 @@ _SIGS = {
     'srl_grad_norm_clip_coef': [_P, _L, _F, _P, _P, _P],
     'srl_rmsprop_step': [_P, _P, _P, _L, _P, _F, _F, _F, _P],
     'srl_adam_step': [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _I, _P],
-    'srl_test_gemm_kmajor': [_P, _P, _P, _I, _I, _I, _I, _P],
-    'srl_test_gemm_mnmajor': [_P, _P, _P, _I, _I, _I, _I, _P],
-    'srl_test_shifted_operand': [_P, _P, _P, _I, _I, _I, _P],
-    'srl_test_poison_smem': [_P],
-    'srl_test_pdl': [_P, _P, _I, C.c_uint, _P],
+    'srl_learner_set_option': [_P, C.c_char_p, _I],
+    'srl_learner_snapshot_params': [_P, _P, _P, _P],
+    'srl_learner_set_step': [_P, _L, _P],
     'srl_memcpy_d2d': [_P, _P, _L, _P],
     'srl_learner_set_profiling': [_P, _I],
     'srl_profile_slot_count': [],
     'srl_learner_profile_collect': [_P, _P],
     'srl_version': [],
 }
-EXPORTS = sorted(list(_SIGS) + ['srl_last_error', 'srl_param_layout', 'srl_param_layout_ex', 'srl_learner_workspace_bytes', 'srl_profile_slot_name', 'srl_lstm_last_error', 'srl_per_last_error', 'srl_per_size', 'srl_per_capacity'])
+# libscalerl_b200_testhooks.so (include/scalerl_b200_testhooks.h): unit-test entry points, loaded by tests only
+_HOOK_SIGS = {
+    'srl_test_gemm_kmajor': [_P, _P, _P, _I, _I, _I, _I, _P],
+    'srl_test_gemm_mnmajor': [_P, _P, _P, _I, _I, _I, _I, _P],
+    'srl_test_shifted_operand': [_P, _P, _P, _I, _I, _I, _P],
+    'srl_test_poison_smem': [_P],
+    'srl_test_pdl': [_P, _P, _I, C.c_uint, _P],
+}
+HOOK_EXPORTS = sorted(list(_HOOK_SIGS) + ['srl_test_last_error'])
+HOOKS_PATH = os.path.join(_HERE, 'libscalerl_b200_testhooks.so')
+_hooks = None
+
+
+def hooks():
+    """the test-hook library (tests only; the product path never loads it)"""
+    global _hooks
+    if _hooks is None:
+        if not os.path.exists(HOOKS_PATH):
+            raise RuntimeError(f'{HOOKS_PATH} is missing: build it with python -m scalerl_b200.build')
+        H = C.CDLL(HOOKS_PATH)
+        for name, args in _HOOK_SIGS.items():
+            fn = getattr(H, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        H.srl_test_last_error.restype = C.c_char_p
+        H.srl_test_last_error.argtypes = []
+        _hooks = H
+    return _hooks
+
+
+def check_hook(rc, what=''):
+    if rc != 0:
+        msg = hooks().srl_test_last_error().decode()
+        raise (ValueError if rc == -1 else RuntimeError)(f'{what}: rc={rc}: {msg}')
+
+
+EXPORTS = sorted(list(_SIGS) + ['srl_last_error', 'srl_param_layout', 'srl_param_layout_ex', 'srl_learner_workspace_bytes', 'srl_profile_slot_name', 'srl_lstm_last_error', 'srl_per_last_error', 'srl_per_size', 'srl_per_capacity', 'srl_per_invalid_updates', 'srl_learner_get_step'])
 
 
 def lib():
@@ -97,6 +134,10 @@ def lib():
         for nm in ('srl_per_size', 'srl_per_capacity'):
             getattr(L, nm).restype = C.c_int64
             getattr(L, nm).argtypes = [_P]
+        L.srl_learner_get_step.restype = C.c_int64
+        L.srl_learner_get_step.argtypes = [_P, _P]
+        L.srl_per_invalid_updates.restype = C.c_int64
+        L.srl_per_invalid_updates.argtypes = [_P, _P]
         L.srl_lstm_last_error.restype = C.c_char_p
         L.srl_lstm_last_error.argtypes = []
         L.srl_profile_slot_name.restype = C.c_char_p

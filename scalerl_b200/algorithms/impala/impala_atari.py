@@ -1,38 +1,44 @@
 """ImpalaTrainer -- drop-in for scalerl/algorithms/impala/impala_atari.py with the learner on a B200.
 
-Same public surface as the reference class (``ImpalaTrainer(args)``, ``create_buffers``, ``get_action``,
-``get_batch``, ``learn``, ``learn_process``, ``train``, ``save_checkpoint``; impala_atari.py:40-515), same
-trajectory key schema (impala_atari.py:122-151), same stats keys (:333-340) and checkpoint keys (:506-511).
-What changes behind it:
+Same public surface as the reference class (``ImpalaTrainer(args)``, ``create_buffers``, ``create_rnn_state_buffers``,
+``get_action``, ``get_batch``, ``learn``, ``learn_process``, ``train``, ``save_checkpoint``; impala_atari.py:40-515), same
+trajectory key schema (:122-151), same actor calling convention ``actor_model(env_output, agent_state) -> (outputs, state)``
+(:177-197 -- the reference's own ``AtariNet`` can be passed as ``actor_model_fn``), same stats keys (:333-340) and
+checkpoint keys (:506-511).  What changes behind it:
 
-  * buffers live in ONE shared-memory block per slot (obs + the small fields), registered as pinned host
-    memory by the learner process, so ``get_batch`` issues asynchronous H2D copies on a copy stream instead of
-    ``torch.stack`` + a pageable ``.to(device)`` (impala_atari.py:248-265); a slot returns to ``free_queue`` only
-    after its copy event fired (ownership rule);
-  * ``learn`` runs the sm_100a kernels (B200ImpalaLearner) and publishes the new weights into the shared CPU
-    actor parameters (impala_atari.py:348);
+  * buffers live in ONE shared-memory block per slot (obs + the small fields), registered as pinned host memory by the
+    learner process: ``get_batch`` issues one asynchronous H2D copy per slot on a copy stream + one unpack kernel instead of
+    ``torch.stack`` + a pageable ``.to(device)`` (:248-265).  Nothing in it waits for the GPU: a slot returns to
+    ``free_queue`` when its copy event has fired (polled; ownership rule of SURVEY.md §8b), the learner stream waits for the
+    copy on the device, and two device batches alternate so the copy of batch k+1 overlaps the step on batch k;
+  * ``learn`` enqueues the sm_100a step (B200ImpalaLearner.learn_async), a device-side snapshot of the new weights and
+    their asynchronous D2H on a publish stream straight into the (pinned, shared-memory) actor parameters, followed by a
+    version counter (:348 + SURVEY.md §8f-4); stats are read one step behind (``stats_lag``; 0 = the reference's
+    synchronous behaviour);
   * CUDA is first touched inside the learner process (the reference forks after building models in the parent,
-    SURVEY.md §7 hard part 8); ``global_step`` is a shared counter (the reference's plain int never reaches the
-    parent).
+    SURVEY.md §7 hard part 8); ``global_step`` is a shared counter (the reference's plain int never reaches the parent).
 
-Actors stay ordinary Python processes running a CPU policy.  Inside ScaleRL they use the reference's own
-``AtariNet`` + ``TorchEnvWrapper``; ``env_fn`` / ``actor_model_fn`` default to the self-contained stand-ins of
+Actors stay ordinary Python processes running a CPU policy.  Inside ScaleRL they use the reference's own ``AtariNet`` +
+``TorchEnvWrapper``; ``env_fn`` / ``actor_model_fn`` default to the self-contained stand-ins of
 ``scalerl_b200.algorithms.utils`` because gymnasium / ale_py are not installed in this image.
 """
 from __future__ import annotations
 
+import collections
+import ctypes
 import math
 import os
 import time
 import timeit
 import traceback
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import torch
 from torch import multiprocessing as mp
 
-from ...learner import B200ImpalaLearner, ImpalaHParams, PARAM_NAMES
+from ...learner import B200ImpalaLearner, ImpalaHParams
+from ...utils.profile import Timings, nvtx_range
 from ..utils.atari_model import ActorNet, SyntheticAtariEnv
 
 
@@ -66,14 +72,13 @@ class ImpalaArguments:
     num_actions: int = 6
     obs_shape: Tuple[int, int, int] = (4, 84, 84)
     seed: int = 0
+    stats_lag: int = 1            # learn() returns the stats of step k - stats_lag (0: synchronous, as the reference)
+    publish_every: int = 1        # weight publish cadence in learner steps (the reference publishes every step, :348)
 
 
 def slot_layout(T: int, A: int, obs_shape=(4, 84, 84)):
     """byte layout of one trajectory slot: every key of create_buffers (impala_atari.py:135-147), 64-byte aligned"""
     n = T + 1
-    obs_elems = 1
-    for d in obs_shape:
-        obs_elems *= d
     specs = [('obs', (n, *obs_shape), torch.uint8), ('reward', (n,), torch.float32), ('done', (n,), torch.bool),
              ('last_action', (n,), torch.int64), ('action', (n,), torch.int64), ('episode_return', (n,), torch.float32),
              ('episode_step', (n,), torch.int32), ('policy_logits', (n, A), torch.float32), ('baseline', (n,), torch.float32)]
@@ -85,6 +90,12 @@ def slot_layout(T: int, A: int, obs_shape=(4, 84, 84)):
         out[k] = (off, shp, dt, nbytes)
         off = (off + nbytes + 63) & ~63
     return out, off
+
+
+def _host_register(t: torch.Tensor) -> None:
+    rc = int(torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0))
+    if rc not in (0, 712):               # 712 = cudaErrorHostMemoryAlreadyRegistered (e.g. two tensors on one page)
+        raise RuntimeError(f'cudaHostRegister failed: {rc}')
 
 
 class TrajectoryRing:
@@ -104,9 +115,7 @@ class TrajectoryRing:
 
     def pin(self):
         if not self._pinned:
-            rc = torch.cuda.cudart().cudaHostRegister(self.block.data_ptr(), self.block.numel(), 0)
-            if int(rc) != 0:
-                raise RuntimeError(f'cudaHostRegister failed: {rc}')
+            _host_register(self.block)
             self._pinned = True
 
     def unpin(self):
@@ -121,8 +130,6 @@ class ImpalaTrainer:
     def __init__(self, args: ImpalaArguments, env_fn: Optional[Callable[[], Any]] = None,
                  actor_model_fn: Optional[Callable[[], torch.nn.Module]] = None) -> None:
         self.args = args
-        if args.use_lstm:
-            raise NotImplementedError('use_lstm=True is the "next" row of SURVEY.md §8f; the B200 learner is the non-LSTM core')
         if args.num_buffers is None:                                   # impala_atari.py:72-73, applied BEFORE create_buffers
             args.num_buffers = max(2 * args.num_actors, args.batch_size)
         if args.num_actors >= args.num_buffers:                        # :74-75
@@ -130,16 +137,23 @@ class ImpalaTrainer:
         if args.num_buffers < args.batch_size:                         # :76-77
             raise ValueError('num_buffers should be larger than batch_size')
         self.env_fn = env_fn or (lambda: SyntheticAtariEnv(args.obs_shape, args.num_actions, seed=args.seed))
-        self.actor_model = (actor_model_fn or (lambda: ActorNet(args.obs_shape, args.num_actions)))()
+        # any module with the reference AtariNet's interface: __call__(env_output, agent_state) -> (dict, state),
+        # initial_hidden_state(batch_size), state_dict() / load_state_dict() with AtariNet's parameter names
+        self.actor_model = (actor_model_fn or (lambda: ActorNet(args.obs_shape, args.num_actions, use_lstm=args.use_lstm)))()
         self.actor_model.share_memory()                                # :58
         self.ring = self.create_buffers(args.obs_shape, args.num_actions)
         self.buffers = self.ring.buffers
-        self.rnn_state_buffers = [tuple() for _ in range(args.num_buffers)]
+        self.rnn_state_buffers = self.create_rnn_state_buffers()
         args.checkpoint_path = os.path.join(args.output_dir, args.project, args.algo_name)
         os.makedirs(args.checkpoint_path, exist_ok=True)
         self._ctx = mp.get_context('fork')
         self._global_step = self._ctx.Value('q', 0)
+        # version of the weights the actors currently read: written by the GPU's copy engine (D2H on the publish stream,
+        # after the parameter copies of that version), readable from every process
+        self.weights_version = torch.zeros(1, dtype=torch.int64).share_memory_()
         self.learner: Optional[B200ImpalaLearner] = None
+        self._pending_release = collections.deque()          # (copy event, slot indices, free_queue)
+        self._tickets = collections.deque()
 
     # -------------------------------------------------------------------------------------------------
     @property
@@ -151,11 +165,22 @@ class ImpalaTrainer:
         return ImpalaHParams(rollout_length=a.rollout_length, batch_size=a.batch_size, num_actions=a.num_actions,
                              discounting=a.discounting, baseline_cost=a.baseline_cost, entropy_cost=a.entropy_cost,
                              reward_clipping=a.reward_clipping, max_grad_norm=a.max_grad_norm, learning_rate=a.learning_rate,
-                             alpha=a.alpha, momentum=a.momentum, epsilon=a.epsilon, optimizer=a.optimizer)
+                             alpha=a.alpha, momentum=a.momentum, epsilon=a.epsilon, optimizer=a.optimizer, use_lstm=a.use_lstm)
 
     def create_buffers(self, obs_shape, num_actions) -> TrajectoryRing:
         """impala_atari.py:122-151 -- same keys/dtypes/shapes, slot-contiguous shared memory"""
         return TrajectoryRing(self.args.rollout_length, num_actions, self.args.num_buffers, obs_shape)
+
+    def create_rnn_state_buffers(self) -> List[Tuple[torch.Tensor, ...]]:
+        """impala_atari.py:108-120: one initial (h, c) per slot, shared memory; views of ONE block [slot][h|c][2][1][H] so a
+        batch's states are gathered with a single index_select before their H2D copy.  () per slot without LSTM."""
+        state0 = self.actor_model.initial_hidden_state(batch_size=1)
+        if len(state0) == 0:
+            self._rnn_block = None
+            return [tuple() for _ in range(self.args.num_buffers)]
+        shp = tuple(state0[0].shape)                                   # [num_layers, 1, hidden]
+        self._rnn_block = torch.zeros(self.args.num_buffers, len(state0), *shp).share_memory_()
+        return [tuple(self._rnn_block[m, i] for i in range(len(state0))) for m in range(self.args.num_buffers)]
 
     # ------------------------------------------------------------------------------------------------- actors
     def get_action(self, actor_index, free_queue, full_queue, actor_model, buffers, rnn_state_buffers) -> None:
@@ -163,9 +188,11 @@ class ImpalaTrainer:
         SURVEY.md §0.9) is kept as the reference behaves: the agent's action overwrites the env's."""
         try:
             torch.set_num_threads(1)
+            timings = Timings()
             env = self.env_fn()
             env_output = env.reset()
-            agent_output = actor_model(env_output)
+            agent_state = actor_model.initial_hidden_state(batch_size=1)
+            agent_output, unused_state = actor_model(env_output, agent_state)
             while True:
                 index = free_queue.get()
                 if index is None:
@@ -174,14 +201,20 @@ class ImpalaTrainer:
                     buffers[key][index][0, ...] = env_output[key]
                 for key in agent_output:
                     buffers[key][index][0, ...] = agent_output[key]
+                for i, tensor in enumerate(agent_state):
+                    rnn_state_buffers[index][i][...] = tensor
                 for t in range(self.args.rollout_length):
+                    timings.reset()
                     with torch.no_grad():
-                        agent_output = actor_model(env_output)
+                        agent_output, agent_state = actor_model(env_output, agent_state)
+                    timings.time('model')
                     env_output = env.step(agent_output['action'])
+                    timings.time('step')
                     for key in env_output:
                         buffers[key][index][t + 1, ...] = env_output[key]
                     for key in agent_output:
                         buffers[key][index][t + 1, ...] = agent_output[key]
+                    timings.time('write')
                 full_queue.put(index)
         except KeyboardInterrupt:
             pass
@@ -191,46 +224,81 @@ class ImpalaTrainer:
 
     # ------------------------------------------------------------------------------------------------- learner
     def _ensure_learner(self):
+        if self.learner is not None:
+            return
+        if not (self.args.use_cuda and torch.cuda.is_available()):
+            raise RuntimeError('the B200 ImpalaTrainer needs CUDA (no CPU learner path)')
+        sd = {k: v.detach().clone() for k, v in self.actor_model.state_dict().items()}
+        self.learner = B200ImpalaLearner(self.hparams(), init_state_dict=sd, process_group=None)
+        self.ring.pin()
+        from ...data.feeder import batch_specs, H2D_KEYS
+        hp = self.learner.hp
+        specs = batch_specs(hp.rollout_length, hp.batch_size, hp.num_actions)
+        dev = self.learner.device
+        self._copy_stream = torch.cuda.Stream(dev)
+        self._publish_stream = torch.cuda.Stream(dev)
+        self._dev_batches = [{k: torch.empty(specs[k][0], dtype=specs[k][1], device=dev) for k in H2D_KEYS} for _ in range(2)]
+        self._consumed = [None, None]
+        self._slot = 0
+        self._cur_slot = None
+        # slot-level staging: one H2D copy per trajectory slot (all keys), then one unpack kernel
+        self._staging = [torch.empty(hp.batch_size, self.ring.slot_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        lay = self.ring.layout
+        self._slot_off = (ctypes.c_int64 * 6)(*[lay[k][0] for k in ('obs', 'reward', 'done', 'action', 'policy_logits', 'episode_return')])
+        if self._rnn_block is not None:          # initial LSTM states of a batch: host gather -> pinned -> device [h|c][2][B][H]
+            n_state, (nl, _, hid) = self._rnn_block.shape[1], self._rnn_block.shape[2:]
+            self._rnn_host = [torch.zeros(n_state, nl, hp.batch_size, hid).pin_memory() for _ in range(2)]
+            self._rnn_dev = [torch.zeros(n_state, nl, hp.batch_size, hid, device=dev) for _ in range(2)]
+            self._rnn_copied = [None, None]
+        # weight publish: snapshot (device) -> D2H straight into the actors' shared-memory parameters
+        self._snapshot = self.learner.flat_params.clone()        # last good weights (the device-side finite guard keeps them)
+        self._pub_done = None
+        self._version_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        _host_register(self.weights_version)
+        self._registered_actor = None
+        self._steps_done = 0
+
+    def _poll_releases(self) -> None:
+        """hand slots whose H2D copy has finished back to the actors (never blocks)"""
+        while self._pending_release and self._pending_release[0][0].query():
+            _, indices, fq = self._pending_release.popleft()
+            for m in indices:
+                fq.put(m)
+
+    def flush(self) -> None:
+        """wait for everything in flight (copies, steps, weight publish) and release every slot"""
         if self.learner is None:
-            if not (self.args.use_cuda and torch.cuda.is_available()):
-                raise RuntimeError('the B200 ImpalaTrainer needs CUDA (no CPU learner path)')
-            self.learner = B200ImpalaLearner(self.hparams(), init_state_dict=self.actor_model.reference_state_dict(), process_group=None)
-            self.ring.pin()
-            from ...data.feeder import batch_specs, H2D_KEYS
-            hp = self.learner.hp
-            specs = batch_specs(hp.rollout_length, hp.batch_size, hp.num_actions)
-            dev = self.learner.device
-            self._copy_stream = torch.cuda.Stream(dev)
-            self._dev_batches = [{k: torch.empty(specs[k][0], dtype=specs[k][1], device=dev) for k in H2D_KEYS} for _ in range(2)]
-            self._consumed = [None, None]
-            self._slot = 0
-            # slot-level staging: one H2D copy per trajectory slot (all keys), then one unpack kernel
-            self._staging = [torch.empty(hp.batch_size, self.ring.slot_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
-            import ctypes
-            lay = self.ring.layout
-            self._slot_off = (ctypes.c_int64 * 6)(*[lay[k][0] for k in ('obs', 'reward', 'done', 'action', 'policy_logits', 'episode_return')])
-            self._publish_host = {n: torch.empty(self.learner.shapes[n], dtype=torch.float32).pin_memory() for n in PARAM_NAMES}
+            return
+        torch.cuda.synchronize(self.learner.device)
+        self._poll_releases()
 
     def get_batch(self, free_queue, full_queue, buffers=None, rnn_state_buffers=None, timings=None, lock=None):
         """impala_atari.py:222-268: dequeue B slot indices, copy them column-wise into a time-major device batch
-        (async, pinned, copy stream), release the slots once the copies have finished."""
+        (async, pinned, copy stream); the slots go back to ``free_queue`` once their copies have finished (polled here,
+        in ``learn`` and while waiting for trajectories -- the host never waits for the GPU)."""
         self._ensure_learner()
         from ...data.feeder import H2D_KEYS
+        from ... import _lib
         buffers = buffers or self.buffers
+        timings = timings or Timings()
+        self._poll_releases()
         if lock is not None:
             with lock:
+                timings.time('lock')
                 indices = [self._dequeue(full_queue) for _ in range(self.args.batch_size)]
         else:
+            timings.time('lock')
             indices = [self._dequeue(full_queue) for _ in range(self.args.batch_size)]
+        timings.time('dequeue')
         s = self._slot
         self._slot ^= 1
         dst = self._dev_batches[s]
-        from ... import _lib
         sb = self.ring.slot_bytes
         hp = self.learner.hp
-        with torch.cuda.stream(self._copy_stream):
+        state: Tuple[torch.Tensor, ...] = tuple()
+        with nvtx_range('get_batch'), torch.cuda.stream(self._copy_stream):
             if self._consumed[s] is not None:
-                self._copy_stream.wait_event(self._consumed[s])
+                self._copy_stream.wait_event(self._consumed[s])          # the step that read this device batch has finished
             if buffers is self.buffers:       # ring slots: ONE pinned H2D copy per slot, then scatter on the device
                 stg = self._staging[s]
                 for b, m in enumerate(indices):
@@ -243,63 +311,139 @@ class ImpalaTrainer:
                 for b, m in enumerate(indices):
                     for k in H2D_KEYS:
                         dst[k][:, b].copy_(buffers[k][m], non_blocking=True)
+            if self._rnn_block is not None:   # initial_rnn_state = cat over the batch on dim 1 (:252-253)
+                rsb = rnn_state_buffers if rnn_state_buffers is not None else self.rnn_state_buffers
+                host = self._rnn_host[s]
+                if self._rnn_copied[s] is not None:
+                    self._rnn_copied[s].synchronize()       # the H2D that last read this pinned buffer (two batches ago) is done
+                if rsb is self.rnn_state_buffers:
+                    g = self._rnn_block.index_select(0, torch.as_tensor(indices))           # [B][h|c][2][1][H]
+                    host.copy_(g.squeeze(3).permute(1, 2, 0, 3))
+                else:
+                    for i in range(host.shape[0]):
+                        host[i].copy_(torch.cat([rsb[m][i] for m in indices], dim=1))
+                self._rnn_dev[s].copy_(host, non_blocking=True)
+                self._rnn_copied[s] = torch.cuda.Event()
+                self._rnn_copied[s].record(self._copy_stream)
+                state = tuple(self._rnn_dev[s][i] for i in range(host.shape[0]))
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        ev.synchronize()                           # slots are owned until their copy finished
-        for m in indices:
-            free_queue.put(m)
-        torch.cuda.current_stream(self.learner.device).wait_event(ev)
+        timings.time('batch')
+        self._pending_release.append((ev, indices, free_queue))              # slots stay owned until their copy has finished
+        self._poll_releases()
+        timings.time('enqueue')
+        torch.cuda.current_stream(self.learner.device).wait_event(ev)        # device-side wait: the host moves on
         self._cur_slot = s
-        return dst, tuple()
+        timings.time('device')
+        return dst, state
 
     def _dequeue(self, full_queue):
-        """full_queue.get() that notices dead actors: the reference blocks forever when an actor process has died
+        """full_queue.get() that (a) keeps releasing slots whose copies finish meanwhile -- the actors may be waiting for
+        exactly those -- and (b) notices dead actors: the reference blocks forever when an actor process has died
         (impala_atari.py:238-241); here a crashed actor surfaces as an error in the learner instead of a hang."""
         actors = getattr(self, '_actors', None)
-        if not actors:
+        if not actors and not self._pending_release:
             return full_queue.get()
         while full_queue.empty():
-            dead = [p.name for p in actors if not p.is_alive()]
-            if dead:
-                raise RuntimeError(f'actor process(es) exited while the learner was waiting for trajectories: {dead}')
-            time.sleep(0.0005)
+            self._poll_releases()
+            if actors:
+                dead = [p.name for p in actors if not p.is_alive()]
+                if dead:
+                    raise RuntimeError(f'actor process(es) exited while the learner was waiting for trajectories: {dead}')
+            time.sleep(0.0002)
         return full_queue.get()
 
     def learn(self, actor_model, learner_model, batch, initial_rnn_state=(), lock=None) -> Dict[str, Any]:
-        """impala_atari.py:270-349.  ``learner_model`` is ignored (the learner state lives in B200ImpalaLearner)."""
+        """impala_atari.py:270-349.  ``learner_model`` is ignored (the learner state lives in B200ImpalaLearner).
+        Returns the stats of step k - ``args.stats_lag`` (the first call(s) return their own step's stats)."""
         self._ensure_learner()
-        stats = self.learner.learn(batch)
-        if not math.isfinite(stats['total_loss']):          # never publish poisoned weights to the actors
+        L = self.learner
+        with nvtx_range('learn'):
+            ticket = L.learn_async(batch, initial_rnn_state)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(L.device))
+            if self._cur_slot is not None:
+                self._consumed[self._cur_slot] = ev
+            self._steps_done += 1
+            if self._steps_done % max(1, self.args.publish_every) == 0:
+                self.publish_weights(actor_model, wait=False)
+        self._tickets.append(ticket)
+        self._poll_releases()
+        lag = max(0, int(self.args.stats_lag))
+        while len(self._tickets) > lag + 1:
+            self._tickets.popleft()
+        stats = L.result(self._tickets[0])
+        self._poll_releases()
+        if not math.isfinite(stats['total_loss']):          # the device-side guard already kept these weights from the actors
             raise FloatingPointError(f'non-finite learner loss: {stats}')
         if os.environ.get('SRL_CHECK_FINITE'):               # debugging aid: name the first poisoned tensors
-            bad_p = [n for n, v in self.learner.params.items() if not bool(torch.isfinite(v).all())]
-            bad_g = [n for n, v in self.learner.grads.items() if not bool(torch.isfinite(v).all())]
+            bad_p = [n for n, v in L.params.items() if not bool(torch.isfinite(v).all())]
+            bad_g = [n for n, v in L.grads.items() if not bool(torch.isfinite(v).all())]
             if bad_p or bad_g:
-                raise FloatingPointError(f'step {self.learner.global_step}: non-finite params {bad_p} grads {bad_g} stats {stats}')
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.learner.device))
-        if getattr(self, '_cur_slot', None) is not None:
-            self._consumed[self._cur_slot] = ev
-        self.publish_weights(actor_model)
+                raise FloatingPointError(f'step {L.global_step}: non-finite params {bad_p} grads {bad_g} stats {stats}')
         return stats
 
-    def publish_weights(self, actor_model) -> None:
-        """impala_atari.py:348: actor_model.load_state_dict(learner_model.state_dict()) -- D2H into pinned staging, then
-        into the shared-memory actor parameters that the actor processes read lock-free"""
-        for n in PARAM_NAMES:
-            self._publish_host[n].copy_(self.learner.params[n], non_blocking=True)
-        torch.cuda.current_stream(self.learner.device).synchronize()
-        actor_model.load_reference_state_dict(self._publish_host)
+    def _register_actor(self, actor_model):
+        """pin the actor's shared-memory parameters so the publish D2H writes them directly (no host-side copy)"""
+        if self._registered_actor is actor_model:
+            return
+        sd = actor_model.state_dict()
+        missing = [n for n in self.learner.names if n not in sd]
+        if missing:
+            raise KeyError(f'actor_model.state_dict() lacks {missing}')
+        self._actor_targets = []
+        for n in self.learner.names:
+            t = sd[n]
+            if tuple(t.shape) != tuple(self.learner.shapes[n]) or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f'actor parameter {n}: expected contiguous float32 {tuple(self.learner.shapes[n])}')
+            if not t.is_shared():
+                raise ValueError('actor_model must live in shared memory (actor_model.share_memory())')
+            _host_register(t)
+            self._actor_targets.append(t)
+        self._registered_actor = actor_model
+
+    def publish_weights(self, actor_model, wait: bool = True) -> int:
+        """impala_atari.py:348 ``actor_model.load_state_dict(learner_model.state_dict())`` as an asynchronous, versioned
+        pipeline: (learner stream) snapshot of the flat fp32 parameters, skipped on the device when the step's loss is not
+        finite -> (publish stream) D2H of every tensor into the actors' pinned shared-memory parameters, then the version
+        counter.  Actors read lock-free, as in the reference.  Returns the version being published."""
+        self._ensure_learner()
+        self._register_actor(actor_model)
+        L = self.learner
+        cur = torch.cuda.current_stream(L.device)
+        if self._pub_done is not None:
+            cur.wait_event(self._pub_done)                    # the previous publish has read the snapshot
+        L.snapshot_params(self._snapshot)
+        snap_ev = torch.cuda.Event()
+        snap_ev.record(cur)
+        version = int(getattr(self, '_version', 0)) + 1
+        self._version = version
+        with torch.cuda.stream(self._publish_stream):
+            self._publish_stream.wait_event(snap_ev)
+            for i, t in enumerate(self._actor_targets):
+                t.copy_(L._view(self._snapshot, i), non_blocking=True)
+            self._version_dev.fill_(version)
+            self.weights_version.copy_(self._version_dev, non_blocking=True)
+            self._pub_done = torch.cuda.Event()
+            self._pub_done.record(self._publish_stream)
+        if wait:
+            self._pub_done.synchronize()
+        return version
 
     def learn_process(self, threading_id, actor_model, learner_model, free_queue, full_queue, buffers, rnn_state_buffers, lock=None):
         """impala_atari.py:351-401"""
         try:
+            timings = Timings()
             while self.global_step < self.args.total_steps:
-                batch, state = self.get_batch(free_queue, full_queue, buffers, rnn_state_buffers, None, lock)
+                timings.reset()
+                batch, state = self.get_batch(free_queue, full_queue, buffers, rnn_state_buffers, timings, lock)
                 stats = self.learn(actor_model, learner_model, batch, state, lock)
+                timings.time('learn')
                 with self._global_step.get_lock():
                     self._global_step.value += self.args.rollout_length * self.args.batch_size   # :391
                 self.last_stats = stats
+            self.flush()
+            self.timings = timings
         except KeyboardInterrupt:
             return
         except Exception:
@@ -326,6 +470,7 @@ class ImpalaTrainer:
             self.learn_process(0, self.actor_model, None, free_queue, full_queue, self.buffers, self.rnn_state_buffers, None)
         finally:
             self._actors = None
+            self.flush()
             for _ in range(self.args.num_actors):
                 free_queue.put(None)
             for p in actors:
@@ -334,13 +479,18 @@ class ImpalaTrainer:
                     p.terminate()
         sps = (self.global_step - s0) / max(timer() - t0, 1e-9)
         self.save_checkpoint(checkpoint_path)
-        return dict(steps=self.global_step, sps=sps, **getattr(self, 'last_stats', {}))
+        return dict(steps=self.global_step, sps=sps, weights_version=int(self.weights_version[0]), **getattr(self, 'last_stats', {}))
 
     def save_checkpoint(self, checkpoint_path: str) -> None:
-        """impala_atari.py:496-515 (same dict keys)"""
+        """impala_atari.py:496-515 (same dict keys; the optimizer state is in torch.optim's own layout)"""
         if self.args.disable_checkpoint:
             return
         os.makedirs(os.path.dirname(checkpoint_path), exist_ok=True)
-        opt = self.learner.optimizer_state_dict() if self.learner is not None else {}
-        torch.save({'model_state_dict': self.actor_model.reference_state_dict(), 'optimizer_state_dict': opt,
+        if self.learner is not None:
+            model = {k: v.cpu() for k, v in self.learner.state_dict().items()}
+            opt = self.learner.optimizer_state_dict()
+        else:
+            model = {k: v.detach().clone() for k, v in self.actor_model.state_dict().items()}
+            opt = {}
+        torch.save({'model_state_dict': model, 'optimizer_state_dict': opt,
                     'hparam': {k: v for k, v in vars(self.args).items()}}, checkpoint_path)

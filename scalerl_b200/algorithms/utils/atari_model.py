@@ -1,9 +1,12 @@
 """CPU actor-side stand-ins used when ScaleRL's own AtariNet / gym env are not available.
 
 ``ActorNet`` evaluates the AtariNet architecture (conv 8s4 -> 4s2 -> 3s1 -> fc512 -> [h, clipped reward, one-hot
-last action] -> policy/baseline heads; reference: scalerl/algorithms/utils/atari_model.py:30-59,93-134) for ONE
-environment step on the CPU and samples an action; its parameters live in shared memory and are overwritten by the
-learner's weight publish.  Parameter names/layouts are the reference's state_dict (so checkpoints interchange).
+last action] -> [2-layer LSTM] -> policy/baseline heads; reference: scalerl/algorithms/utils/atari_model.py:30-59,
+93-134) for the actor's one-step calls on the CPU and samples an action.  It follows the reference model's CALLING
+CONVENTION -- ``actor_model(env_output, agent_state) -> (dict(policy_logits, baseline, action), agent_state)``,
+``initial_hidden_state(batch_size)``, ``state_dict()`` / ``load_state_dict()`` with the reference's parameter names and
+layouts -- so ImpalaTrainer treats it and the reference's own ``AtariNet`` identically (either can be passed as
+``actor_model_fn``); its parameters live in shared memory and are overwritten by the learner's weight publish.
 ``SyntheticAtariEnv`` emits the TorchEnvWrapper record schema (scalerl/envs/torch_envwrapper.py:43-50,77-84)
 with random frames; it exists so the actor/ring/learner plumbing can be exercised without gymnasium/ale_py.
 """
@@ -12,17 +15,25 @@ from collections import OrderedDict
 import torch
 import torch.nn.functional as F
 
-from ...learner import PARAM_NAMES, param_shapes
+from ...learner import LSTM_PARAM_NAMES, PARAM_NAMES, param_shapes, reference_param_order
 
 
 class ActorNet(torch.nn.Module):
-    def __init__(self, obs_shape=(4, 84, 84), num_actions=6, seed=0):
+    def __init__(self, obs_shape=(4, 84, 84), num_actions=6, use_lstm=False, seed=0):
         super().__init__()
-        self.num_actions = num_actions
+        self.observation_shape = tuple(obs_shape)
+        self.num_actions = int(num_actions)
+        self.use_lstm = bool(use_lstm)
+        self.core_size = 513 + self.num_actions
+        self.names = reference_param_order(self.use_lstm)
         g = torch.Generator().manual_seed(seed)
         fan = 1
-        for n, shp in param_shapes(num_actions).items():
-            if n.endswith('.weight'):
+        shapes = param_shapes(num_actions, self.use_lstm)
+        for n in self.names:
+            shp = shapes[n]
+            if n.startswith('rnn_layer.'):
+                fan = self.core_size                       # nn.LSTM: U(+-1/sqrt(hidden_size)) for every tensor
+            elif n.endswith('.weight'):
                 fan = 1
                 for d in shp[1:]:
                     fan *= d
@@ -33,13 +44,39 @@ class ActorNet(torch.nn.Module):
     def _p(self, n):
         return getattr(self, n.replace('.', '_'))
 
-    def reference_state_dict(self):
-        return OrderedDict((n, self._p(n).detach().clone()) for n in PARAM_NAMES)
+    # ---- the reference model's parameter interface (names of atari_model.py:30-59) -----------------------------------
+    def state_dict(self, *args, **kwargs):
+        return OrderedDict((n, self._p(n).detach()) for n in self.names)
 
-    def load_reference_state_dict(self, sd):
+    def load_state_dict(self, sd, strict=True):
+        missing = [n for n in self.names if n not in sd]
+        extra = [k for k in sd if k not in self.names]
+        if strict and (missing or extra):
+            raise RuntimeError(f'ActorNet.load_state_dict: missing keys {missing}, unexpected keys {extra}')
         with torch.no_grad():
-            for n in PARAM_NAMES:
-                self._p(n).copy_(sd[n])
+            for n in self.names:
+                if n in sd:
+                    self._p(n).copy_(sd[n])
+
+    def initial_hidden_state(self, batch_size: int):
+        """atari_model.py:61-75: () without LSTM, else (h0, c0) zeros [2, batch, 513 + A]"""
+        if not self.use_lstm:
+            return tuple()
+        return tuple(torch.zeros(2, batch_size, self.core_size) for _ in range(2))
+
+    def _lstm_step(self, x, state):
+        """one time step of the 2-layer nn.LSTM (gate order i, f, g, o); state = (h [2,B,H], c [2,B,H])"""
+        h_in, c_in = state
+        hs, cs = [], []
+        for layer in (0, 1):
+            gates = (F.linear(x, self._p(f'rnn_layer.weight_ih_l{layer}'), self._p(f'rnn_layer.bias_ih_l{layer}'))
+                     + F.linear(h_in[layer], self._p(f'rnn_layer.weight_hh_l{layer}'), self._p(f'rnn_layer.bias_hh_l{layer}')))
+            i, f, g, o = gates.chunk(4, dim=-1)
+            c = torch.sigmoid(f) * c_in[layer] + torch.sigmoid(i) * torch.tanh(g)
+            x = torch.sigmoid(o) * torch.tanh(c)
+            hs.append(x)
+            cs.append(c)
+        return x, (torch.stack(hs), torch.stack(cs))
 
     @torch.no_grad()
     def forward(self, inputs, rnn_state=()):
@@ -52,10 +89,25 @@ class ActorNet(torch.nn.Module):
         x = F.relu(F.linear(x.reshape(T * B, -1), self._p('fc.weight'), self._p('fc.bias')))
         one_hot = F.one_hot(inputs['action'].reshape(T * B), self.num_actions).float()
         core = torch.cat([x, torch.clamp(inputs['reward'], -1, 1).reshape(T * B, 1), one_hot], dim=-1)
+        if self.use_lstm:
+            core = core.view(T, B, -1)
+            notdone = (~inputs['done']).float()
+            outs = []
+            for t in range(T):
+                nd = notdone[t].view(1, B, 1)
+                rnn_state = tuple(nd * s for s in rnn_state)        # state reset at episode ends (atari_model.py:114-116)
+                y, rnn_state = self._lstm_step(core[t], rnn_state)
+                outs.append(y)
+            core = torch.cat(outs, 0)
+        else:
+            rnn_state = tuple()
         logits = F.linear(core, self._p('policy.weight'), self._p('policy.bias'))
         baseline = F.linear(core, self._p('baseline.weight'), self._p('baseline.bias'))
-        action = torch.multinomial(F.softmax(logits, dim=1), num_samples=1)
-        return dict(policy_logits=logits.view(T, B, -1), baseline=baseline.view(T, B), action=action.view(T, B))
+        if self.training:
+            action = torch.multinomial(F.softmax(logits, dim=1), num_samples=1)
+        else:
+            action = torch.argmax(logits, dim=1)
+        return dict(policy_logits=logits.view(T, B, -1), baseline=baseline.view(T, B), action=action.view(T, B)), rnn_state
 
 
 class SyntheticAtariEnv:

@@ -1,4 +1,6 @@
-"""Build libscalerl_b200.so (sm_100a) in-tree with nvcc.  Usage: python -m scalerl_b200.build [--force]"""
+"""Build libscalerl_b200.so (the product C-ABI library, sm_100a) and libscalerl_b200_testhooks.so (unit-test entry points
+for the tcgen05 building blocks; never loaded by the product path) in-tree with nvcc.
+Usage: python -m scalerl_b200.build [--force] [-v]"""
 import concurrent.futures as cf
 import os
 import subprocess
@@ -7,7 +9,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libscalerl_b200.so')
-SOURCES = ['api.cu', 'encoder.cu', 'vtrace.cu', 'heads_optim.cu', 'test_shift.cu', 'lstm.cu', 'per.cu']
+OUT_HOOKS = os.path.join(HERE, 'libscalerl_b200_testhooks.so')
+SOURCES = ['api.cu', 'encoder.cu', 'vtrace.cu', 'heads_optim.cu', 'lstm.cu', 'per.cu']
+HOOK_SOURCES = ['testhooks.cu', 'test_shift.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr'] + \
              [f'-D{d}' for d in os.environ.get('SRL_DEFINES', '').split(',') if d]       # e.g. SRL_DEFINES=SRL_DEBUG_BIAS_REREAD (debug builds)
@@ -25,9 +29,9 @@ def _deps():
 
 
 def needs_build():
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(OUT_HOOKS):
         return True
-    t = os.path.getmtime(OUT)
+    t = min(os.path.getmtime(OUT), os.path.getmtime(OUT_HOOKS))
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
@@ -44,8 +48,8 @@ def build(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
 
-    with cf.ThreadPoolExecutor(len(SOURCES)) as ex:
-        results = list(ex.map(cc, SOURCES))
+    with cf.ThreadPoolExecutor(len(SOURCES) + len(HOOK_SOURCES)) as ex:
+        results = list(ex.map(cc, SOURCES + HOOK_SOURCES))
     log = []
     for src, obj, r in results:
         log.append(f'== {src}\n{r.stdout}\n{r.stderr}')
@@ -53,10 +57,11 @@ def build(force=False, verbose=False):
             raise RuntimeError(f'nvcc failed on {src}:\n{r.stdout}\n{r.stderr}')
     with open(os.path.join(objdir, 'ptxas.log'), 'w') as f:
         f.write('\n'.join(log))
-    cmd = [nvcc, '-shared', '-o', OUT] + [o for _, o, _ in results] + ['-lcudart']
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
+    for out, srcs in ((OUT, SOURCES), (OUT_HOOKS, HOOK_SOURCES)):
+        cmd = [nvcc, '-shared', '-o', out] + [o for s_, o, _ in results if s_ in srcs] + ['-lcudart']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
     if verbose:
         print('\n'.join(log))
     return OUT

@@ -67,6 +67,27 @@ extern "C" int srl_impala_loss_and_head_grads(const float* bl, const float* tl, 
   return 0;
 }
 
+extern "C" int srl_policy_rows_forward(const float* logits, const int64_t* actions, int64_t N, int A, float* logp, float* ent, void* stream) {
+  REQ(N >= 0 && A >= 1, "policy_rows_forward: bad shape N=%lld A=%d", (long long)N, A);
+  if (N == 0) return 0;
+  REQ(logits && (logp || ent) && (!logp || actions), "policy_rows_forward: NULL pointer");
+  CU(launch_policy_rows_fwd(logits, actions, N, A, logp, ent, (cudaStream_t)stream), "policy_rows_forward");
+  return 0;
+}
+extern "C" int srl_policy_rows_backward(const float* logits, const int64_t* actions, const float* w_logp, const float* w_ent, int64_t N, int A,
+                                        float* dlogits, void* stream) {
+  REQ(N >= 0 && A >= 1, "policy_rows_backward: bad shape N=%lld A=%d", (long long)N, A);
+  if (N == 0) return 0;
+  REQ(logits && dlogits && (!w_logp || actions), "policy_rows_backward: NULL pointer");
+  CU(launch_policy_rows_bwd(logits, actions, w_logp, w_ent, N, A, dlogits, (cudaStream_t)stream), "policy_rows_backward");
+  return 0;
+}
+extern "C" int srl_reduce_sum(const float* x, int64_t n, int square, float scale, float* out, void* stream) {
+  REQ(n >= 0 && out && (x || n == 0), "reduce_sum: bad argument");
+  CU(launch_reduce_sum(x, n, square, scale, out, (cudaStream_t)stream), "reduce_sum");
+  return 0;
+}
+
 extern "C" int srl_unpack_slots(const uint8_t* staging, int64_t slot_bytes, const int64_t* offsets6_host, int T, int B, int A, uint8_t* obs,
                                 float* reward, uint8_t* done, int64_t* action, float* policy_logits, float* episode_return, void* stream) {
   REQ(staging && offsets6_host && obs && reward && done && action && policy_logits, "unpack_slots: NULL pointer");
@@ -96,31 +117,6 @@ extern "C" int srl_adam_step(float* params, const float* grads, float* exp_avg, 
                              float beta1, float beta2, float eps, int step, void* stream) {
   REQ(params && grads && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "adam: bad argument");
   CU(launch_adam(params, grads, exp_avg, exp_avg_sq, n, coef, lr, beta1, beta2, eps, step, nullptr, (cudaStream_t)stream), "adam");
-  return 0;
-}
-
-extern "C" int srl_test_gemm_kmajor(const void* A, const void* B, float* D, int M, int N, int K, int simt, void* stream) {
-  REQ(A && B && D && M > 0 && N > 0 && K > 0 && K % 64 == 0 && N % 64 == 0, "test_gemm_kmajor: need K%%64==0, N%%64==0");
-  CU(test_gemm(A, B, D, M, N, K, false, simt != 0, (cudaStream_t)stream), "test_gemm_kmajor");
-  return 0;
-}
-extern "C" int srl_test_shifted_operand(const void* A, const void* B, float* D, int shift, int mn_major, int base_offset_mode, void* stream) {
-  REQ(A && B && D && shift >= 0 && shift <= 32, "test_shifted_operand: bad argument");
-  CU(test_shift(A, B, D, shift, mn_major, base_offset_mode, (cudaStream_t)stream), "test_shifted_operand");
-  return 0;
-}
-extern "C" int srl_test_pdl(int* flag, int* out, int nblk, unsigned delay_ns, void* stream) {
-  REQ(flag && out && nblk > 0, "test_pdl: bad argument");
-  CU(test_pdl(flag, out, nblk, delay_ns, (cudaStream_t)stream), "test_pdl");
-  return 0;
-}
-extern "C" int srl_test_poison_smem(void* stream) {
-  CU(test_poison_smem((cudaStream_t)stream), "test_poison_smem");
-  return 0;
-}
-extern "C" int srl_test_gemm_mnmajor(const void* At, const void* Bt, float* D, int M, int N, int K, int simt, void* stream) {
-  REQ(At && Bt && D && M > 0 && N > 0 && K > 0 && M % 128 == 0 && N % 64 == 0, "test_gemm_mnmajor: need M%%128==0, N%%64==0");
-  CU(test_gemm(At, Bt, D, M, N, K, true, simt != 0, (cudaStream_t)stream), "test_gemm_mnmajor");
   return 0;
 }
 
@@ -188,6 +184,7 @@ struct srl_learner {
   float *core, *lstm_out, *dout, *dcore;   // [NF][H], [NF][H], [NB][H], [NB][H]
   char* lstm_arena;
   int64_t lstm_off0, lstm_len;    // LSTM gradient range inside the flat buffer
+  bool column_fusion;             // heads + V-trace/loss + dh in one column kernel (SRL_NO_COLUMN_FUSION / srl_learner_set_option)
   Profiler pf;                    // per-kernel event bracketing (off by default)
   cudaEvent_t events[2 * PS_COUNT];
   bool slot_used[PS_COUNT];
@@ -200,7 +197,7 @@ static const char* kSlotNames[PS_COUNT] = {"obs_s2d", "conv1_fwd", "conv2_fwd", 
 static int check_cfg(const srl_config_t* c) {
   REQ(c, "config is NULL");
   REQ(c->T >= 1 && c->B >= 1, "config: T=%d B=%d must be >= 1", c->T, c->B);
-  REQ(c->A >= 1 && c->A <= 32, "config: A=%d must be in [1,32]", c->A);
+  REQ(c->A >= 1 && c->A <= 31, "config: A=%d must be in [1,31] (one warp lane per action plus one for the baseline)", c->A);
   REQ((int64_t)(c->T + 1) * c->B <= 65536, "config: (T+1)*B=%lld frames per GPU exceeds 65536", (long long)(c->T + 1) * c->B);
   REQ(c->optimizer == 0 || c->optimizer == 1, "config: optimizer must be 0 (rmsprop) or 1 (adam)");
   REQ(c->use_lstm == 0 || c->use_lstm == 1, "config: use_lstm must be 0 or 1");
@@ -223,6 +220,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   L->P = make_ptrs(params, cfg->A);
   L->G = make_ptrs(grads, cfg->A);
   L->step = 0; L->have_fwd = false;
+  { const char* nf = getenv("SRL_NO_COLUMN_FUSION"); L->column_fusion = !(nf && atoi(nf) != 0); }   // read once, at creation
   for (int i = 0; i < 2 * PS_COUNT; ++i) L->events[i] = nullptr;
   for (int i = 0; i < PS_COUNT; ++i) L->slot_used[i] = false;
   const int64_t NF = (int64_t)(cfg->T + 1) * cfg->B, NB = (int64_t)cfg->T * cfg->B, A = cfg->A;
@@ -340,6 +338,28 @@ extern "C" int srl_learner_set_config(srl_learner_t* L, const srl_config_t* cfg)
   return 0;
 }
 
+extern "C" int srl_learner_set_option(srl_learner_t* L, const char* name, int value) {
+  REQ(L && name, "set_option: NULL argument");
+  if (strcmp(name, "column_fusion") == 0) { L->column_fusion = value != 0; return 0; }
+  return fail(SRL_EINVAL, "set_option: unknown option '%s'", name);
+}
+
+extern "C" int srl_learner_set_step(srl_learner_t* L, int64_t step, void* stream) {
+  REQ(L && step >= 0 && step < (int64_t(1) << 31), "set_step: bad argument");
+  L->step = (int)step;
+  const int v = (int)step;       // the device counter drives Adam's bias correction under graph replay
+  CU(cudaMemcpyAsync(L->dstep, &v, sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)stream), "set_step");
+  CU(cudaStreamSynchronize((cudaStream_t)stream), "set_step");      // `v` is a stack variable
+  return 0;
+}
+extern "C" int64_t srl_learner_get_step(srl_learner_t* L, void* stream) {
+  if (!L) return -1;
+  int v = 0;
+  if (cudaMemcpyAsync(&v, L->dstep, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -1;
+  return v;
+}
+
 extern "C" int srl_learner_pack_weights(srl_learner_t* L, void* stream) {
   REQ(L, "learner is NULL");
   CU(launch_pack_weights(L->P, L->buf.wpack, (cudaStream_t)stream), "pack_weights");
@@ -347,7 +367,7 @@ extern "C" int srl_learner_pack_weights(srl_learner_t* L, void* stream) {
 }
 
 namespace srl {
-static bool g_pdl_on = true;
+static thread_local bool g_pdl_on = true;      // per calling thread: two learners driven from two threads do not race on it
 bool pdl_active() {
   static const bool env_on = [] { const char* e = getenv("SRL_PDL"); return !e || atoi(e) != 0; }();
   return env_on && g_pdl_on;
@@ -423,9 +443,7 @@ static int fb_begin(srl_learner* L, const uint8_t* obs, const float* reward, con
   const srl_config_t& c = L->cfg;
   const int NF = (c.T + 1) * c.B, NB = c.T * c.B;
   // heads + V-trace/losses + dh: one fused column kernel when its shared-memory footprint fits, else three kernels
-  const char* nf = getenv("SRL_NO_COLUMN_FUSION");          // read per call: the tests toggle it
-  const bool no_fuse = nf && atoi(nf) != 0;
-  const bool fused = !no_fuse && column_step_supported(c.T, c.B, c.A);
+  const bool fused = L->column_fusion && column_step_supported(c.T, c.B, c.A);
   int rc;
   if (fused) {
     REQ(!L->cfg.use_lstm, "this learner was created with use_lstm=1: call the *_lstm entry points");
@@ -481,6 +499,7 @@ extern "C" int srl_learner_backward_finish(srl_learner_t* L, const uint8_t* obs,
   REQ(L->have_fwd, "learner_backward_finish: call srl_learner_forward_backward_begin first");
   const srl_config_t& c = L->cfg;
   L->pf.st = (cudaStream_t)stream;
+  pdl_set_active(!L->pf.on);
   CU(encoder_backward(obs, c.T * c.B, L->buf, L->G, L->maps, c.simt_mainloop, (cudaStream_t)stream, L->pf, L->ss, 1), "encoder_backward");
   return 0;
 }
@@ -544,7 +563,7 @@ extern "C" int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_ou
   L->pf.b(PS_OPTIMIZER);
   if (c.optimizer == 0) {
     CU(launch_clip_optim(0, L->params, L->grads, L->opt0, nullptr, L->nparams, c.max_grad_norm, L->coef, L->scratch + 2048, c.learning_rate,
-                         c.alpha, 0.f, c.epsilon, 0, nullptr, st), "clip+rmsprop");
+                         c.alpha, 0.f, c.epsilon, L->step, L->dstep, st), "clip+rmsprop");
   } else {
     CU(launch_clip_optim(1, L->params, L->grads, L->opt0, L->opt1, L->nparams, c.max_grad_norm, L->coef, L->scratch + 2048, c.learning_rate,
                          c.adam_beta1, c.adam_beta2, c.adam_eps, L->step, L->dstep, st), "clip+adam");
@@ -574,7 +593,7 @@ extern "C" int srl_learner_apply_gradients_dp(srl_learner_t* L, const srl_dp_pee
   L->pf.b(PS_OPTIMIZER);
   if (c.optimizer == 0) {
     CU(launch_dp_clip_optim(0, L->params, L->grads, L->opt0, nullptr, L->nparams, c.max_grad_norm, L->coef, L->scratch + 2048,
-                            c.learning_rate, c.alpha, 0.f, c.epsilon, 0, nullptr, P, st), "dp clip+rmsprop");
+                            c.learning_rate, c.alpha, 0.f, c.epsilon, L->step, L->dstep, P, st), "dp clip+rmsprop");
   } else {
     CU(launch_dp_clip_optim(1, L->params, L->grads, L->opt0, L->opt1, L->nparams, c.max_grad_norm, L->coef, L->scratch + 2048,
                             c.learning_rate, c.adam_beta1, c.adam_beta2, c.adam_eps, L->step, L->dstep, P, st), "dp clip+adam");
@@ -604,6 +623,13 @@ extern "C" int srl_learner_profile_collect(srl_learner_t* L, float* ms_out_host)
     if (e != cudaSuccess) { cudaGetLastError(); ms = -1.f; }   // slot not recorded in the last step
     ms_out_host[i] = ms;
   }
+  return 0;
+}
+
+extern "C" int srl_learner_snapshot_params(srl_learner_t* L, float* dst, const float* losses, void* stream) {
+  REQ(L && dst, "snapshot_params: NULL argument");
+  REQ((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "snapshot_params: dst must be 16-byte aligned");
+  CU(launch_snapshot_if_finite(dst, L->params, L->nparams, losses, (cudaStream_t)stream), "snapshot_params");
   return 0;
 }
 

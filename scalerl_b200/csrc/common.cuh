@@ -154,6 +154,14 @@ SRL_DEVINL void red_add_16(float* dst, const float (&v)[16], float scale = 1.0f)
   for (int j = 0; j < 16; j += 4) red_add_v4(dst + j, v[j] * scale, v[j + 1] * scale, v[j + 2] * scale, v[j + 3] * scale);
 }
 
+// Action index of a trajectory element, clamped to [0, A-1]: the reference's F.one_hot / gather raise on an out-of-range
+// action (atari_model.py:104, vtrace.py:35-40); a kernel cannot raise, so it must at least never index out of bounds
+// (the host side offers the raising check: B200ImpalaLearner(validate_inputs=True)).
+SRL_DEVINL int ld_action(const int64_t* p, int A) {
+  const long long a = __ldg(reinterpret_cast<const long long*>(p));
+  return a < 0 ? 0 : (a >= A ? A - 1 : (int)a);
+}
+
 SRL_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -265,13 +265,4 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
   return cudaSuccess;
 }
 
-cudaError_t test_gemm(const void* A, const void* B, float* D, int M, int N, int K, bool mn_major, bool simt, cudaStream_t st) {
-  if (mn_major) {
-    TestGemmMN::Params q{(const bf16*)A, (const bf16*)B, D, M, N, K};
-    return igemm_launch<TestGemmMN>(q, dim3(M / 128, N / 64), st, simt);
-  }
-  TestGemmK::Params q{(const bf16*)A, (const bf16*)B, D, M, N, K};
-  return igemm_launch<TestGemmK>(q, dim3(cdiv(M, 128), N / 64), st, simt);
-}
-
 }  // namespace srl

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
     const int a = lane;
     const float* w = a < A ? Wp + (size_t)a * CORE : Wb;
     const float r = fminf(fmaxf(__ldg(reward + n), -1.f), 1.f);
-    const int act = (int)__ldg(action + n);
+    const int act = ld_action(action + n, A);
     float s = (part[f][0][a] + part[f][1][a]) + (part[f][2][a] + part[f][3][a]);
     s += __ldg(w + 512) * r + __ldg(w + 513 + act) + (a < A ? __ldg(bp + a) : __ldg(bb));
     if (a < A) logits[(size_t)n * A + a] = s; else baseline[n] = s;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict
   }
   if (threadIdx.x < cnt) {
     sr[threadIdx.x] = fminf(fmaxf(__ldg(reward + n0 + threadIdx.x), -1.f), 1.f);
-    sa[threadIdx.x] = (int)__ldg(action + n0 + threadIdx.x);
+    sa[threadIdx.x] = ld_action(action + n0 + threadIdx.x, A);
   }
   __syncthreads();
   if (j > CORE) return;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(128) core_build_kernel(const float* __restrict
     } else if (j == 512) {
       v = fminf(fmaxf(__ldg(reward + n), -1.f), 1.f);
     } else {
-      v = ((int)__ldg(action + n) == j - 513) ? 1.f : 0.f;
+      v = (ld_action(action + n, A) == j - 513) ? 1.f : 0.f;
     }
     core[(size_t)n * H + j] = v;
   }
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, 
                                                          int* __restrict__ dstep) {
   cg::grid_group grid = cg::this_grid();
   const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = OPT == 1 ? (dstep ? *dstep + 1 : step) : 0;
+  const int t = dstep ? *dstep + 1 : step;          // 1-based step count: Adam bias correction; counted for RMSprop too (checkpoints)
   float s = 0.f;
   for (int64_t i = i0; i < n4; i += stride) {
     const float4 v = reinterpret_cast<const float4*>(g)[i];
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, 
       c_sh = c;
       if (blockIdx.x == 0) {
         coef[0] = norm; coef[1] = c;
-        if (OPT == 1 && dstep) *dstep = t;
+        if (dstep) *dstep = t;
       }
     }
   }
@@ -466,14 +466,18 @@ __global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, 
 template <int OPT>
 static cudaError_t launch_clip_optim_t(float* p, const float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef, float* scratch,
                                        float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st) {
-  static int per_sm = 0, sms = 0;
-  if (!per_sm) {
-    int dev = 0;
-    SRL_TRY(cudaGetDevice(&dev));
-    SRL_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SRL_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, clip_optim_kernel<OPT>, 512, 0));
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  static int per_sm_dev[64] = {}, sms_dev[64] = {};      // per device: one process may drive several GPUs
+  int dev = 0;
+  SRL_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!per_sm_dev[dev]) {
+    int sm_count = 0, occ = 0;
+    SRL_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    SRL_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clip_optim_kernel<OPT>, 512, 0));
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    sms_dev[dev] = sm_count; per_sm_dev[dev] = occ;
   }
+  const int per_sm = per_sm_dev[dev], sms = sms_dev[dev];
   int64_t need = (n / 4 + 511) / 512;
   int blocks = (int)(need < 1 ? 1 : need);
   int cap = per_sm * sms; if (cap > 592) cap = 592;          // scratch holds 592 partials
@@ -562,7 +566,7 @@ __global__ void __launch_bounds__(512) dp_clip_optim_kernel(float* __restrict__ 
   unsigned long long ts[8];
   ts[0] = dbg ? global_ns() : 0;
   const int64_t chunk = (n4 + W - 1) / W, lo = R * chunk, hi = min(n4, lo + chunk);
-  const int t = OPT == 1 ? (dstep ? *reinterpret_cast<volatile int*>(dstep) + 1 : step) : 0;
+  const int t = dstep ? *reinterpret_cast<volatile int*>(dstep) + 1 : step;
   const unsigned e0 = reinterpret_cast<volatile unsigned*>(P.ctl[R])[32];     // epoch base (rewritten after the grid barrier)
   // ---- barrier 1: every rank's backward is complete
   if (blockIdx.x == 0) dp_signal(P, e0 + 1, false);      // the gradients were written by earlier kernels: already at L2
@@ -615,7 +619,7 @@ __global__ void __launch_bounds__(512) dp_clip_optim_kernel(float* __restrict__ 
       if (threadIdx.x == 0) {
         for (int q = 0; q < W; ++q) st_relaxed_sys(P.ctl[q] + 8 + R, __float_as_uint((float)tsum));
         reinterpret_cast<volatile unsigned*>(P.ctl[R])[32] = e0 + 2;          // every block has read e0 / dstep (grid barrier above)
-        if (OPT == 1 && dstep) *dstep = t;
+        if (dstep) *dstep = t;
       }
     }
     __syncthreads();
@@ -706,14 +710,18 @@ __global__ void __launch_bounds__(512) dp_clip_optim_kernel(float* __restrict__ 
 template <int OPT>
 static cudaError_t launch_dp_clip_optim_t(float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef, float* scratch,
                                           float lr, float a, float b, float eps, int step, int* dstep, DpPeers P, cudaStream_t st) {
-  static int per_sm = 0, sms = 0;
-  if (!per_sm) {
-    int dev = 0;
-    SRL_TRY(cudaGetDevice(&dev));
-    SRL_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    SRL_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_clip_optim_kernel<OPT>, 512, 0));
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  static int per_sm_dev[64] = {}, sms_dev[64] = {};      // per device: one process may drive several GPUs
+  int dev = 0;
+  SRL_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!per_sm_dev[dev]) {
+    int sm_count = 0, occ = 0;
+    SRL_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    SRL_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dp_clip_optim_kernel<OPT>, 512, 0));
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    sms_dev[dev] = sm_count; per_sm_dev[dev] = occ;
   }
+  const int per_sm = per_sm_dev[dev], sms = sms_dev[dev];
   int64_t need = (n / 4 + 511) / 512;
   int blocks = (int)(need < 1 ? 1 : need);
   int cap = per_sm * sms; if (cap > 592) cap = 592;
@@ -722,6 +730,25 @@ static cudaError_t launch_dp_clip_optim_t(float* p, float* g, float* s0, float* 
   void* args[] = {&p, &g, &s0, &s1, &n, &max_norm, &coef, &scratch, &lr, &a, &b, &eps, &step, &dstep, &P, &dbg};
   return cudaLaunchCooperativeKernel((const void*)dp_clip_optim_kernel<OPT>, dim3(blocks), dim3(512), args, 0, st);
 }
+// Weight-publish snapshot (impala_atari.py:348): dst = src when the step's total loss is finite, else dst keeps the last good
+// weights -- so the asynchronous D2H that follows never hands poisoned parameters to the actors.
+__global__ void __launch_bounds__(256) snapshot_if_finite_kernel(float4* __restrict__ dst, const float4* __restrict__ src, int64_t n4,
+                                                                 const float* __restrict__ losses) {
+  if (losses) {
+    const float t = losses[3];
+    if (!(fabsf(t) <= 3.0e38f)) return;          // NaN or Inf: keep the previous snapshot
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) dst[i] = __ldg(src + i);
+}
+cudaError_t launch_snapshot_if_finite(float* dst, const float* src, int64_t n, const float* losses, cudaStream_t st) {
+  const int64_t n4 = n >> 2;        // flat parameter buffers are padded to multiples of 4 floats
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  snapshot_if_finite_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), n4, losses);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_dp_clip_optim(int optimizer, float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
                                  float* scratch, float lr, float a, float b, float eps, int step, int* dstep, const DpPeers& P,
                                  cudaStream_t st) {

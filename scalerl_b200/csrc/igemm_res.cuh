@@ -154,12 +154,8 @@ template <class P>
 cudaError_t res_fwd_launch(const typename P::Params& p, int ntiles, int max_ctas, cudaStream_t stream) {
   using C = ResFwdCfg<P>;
   if (ntiles <= 0) return cudaSuccess;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(res_fwd_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  { cudaError_t e = ensure_max_dynamic_smem(once, res_fwd_kernel<P>, C::SMEM_BYTES); if (e != cudaSuccess) return e; }
   const int grid = ntiles < max_ctas ? ntiles : max_ctas;
   return launch_chain<PDL_RESFWD>(res_fwd_kernel<P>, dim3(grid), dim3(RES_THREADS), C::SMEM_BYTES, stream, p);
 }
@@ -333,12 +329,8 @@ cudaError_t res_wgrad_launch(typename P::Params p, int target_ctas, cudaStream_t
   using C = ResWgradCfg<P>;
   const int nchunks = (p.P + 127) >> 7;
   if (nchunks <= 0) return cudaSuccess;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(res_wgrad_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  { cudaError_t e = ensure_max_dynamic_smem(once, res_wgrad_kernel<P>, C::SMEM_BYTES); if (e != cudaSuccess) return e; }
   p.chunks_per_cta = (nchunks + target_ctas - 1) / target_ctas;
   const int grid = (nchunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
   return launch_chain<PDL_RESWGRAD>(res_wgrad_kernel<P>, dim3(grid), dim3(RES_THREADS), C::SMEM_BYTES, stream, p);

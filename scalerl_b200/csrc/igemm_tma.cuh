@@ -185,12 +185,8 @@ template <class P>
 cudaError_t igemm_tma_launch(const typename P::Params& p, dim3 grid, cudaStream_t stream) {
   using C = TmaCfg<P>;
   if (grid.x == 0 || grid.y == 0) return cudaSuccess;
-  static bool attr_set = false;   // set once (outside any stream capture: the first step always runs eagerly)
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tma_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static PerDeviceOnce once;      // set once per device (outside any stream capture: the first step always runs eagerly)
+  { cudaError_t e = ensure_max_dynamic_smem(once, igemm_tma_kernel<P>, C::SMEM_BYTES); if (e != cudaSuccess) return e; }
   return launch_chain<PDL_IGEMM>(igemm_tma_kernel<P>, grid, dim3(IGT_THREADS), C::SMEM_BYTES, stream, p);
 }
 

@@ -23,7 +23,7 @@ struct Profiler {
 // pdl_active(): SRL_PDL != 0 (default on) and not switched off by the caller (per-kernel profiling records events between
 // the kernels, which would serialise them anyway).
 bool pdl_active();
-void pdl_set_active(bool on);
+void pdl_set_active(bool on);      // per calling thread: every C-ABI entry point sets it for the launches it makes
 int pdl_skip_mask();      // SRL_PDL_MASK diagnostic: bit t set = kernels of class t launch without the attribute
 enum { PDL_SIMT = 0, PDL_IGEMM = 1, PDL_RESFWD = 2, PDL_RESWGRAD = 3 };
 template <int TAG, class... KA, class... A>
@@ -35,6 +35,28 @@ inline cudaError_t launch_chain(void (*kernel)(KA...), dim3 grid, dim3 block, si
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = (pdl_active() && !((pdl_skip_mask() >> TAG) & 1)) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// Per-DEVICE once flags (a process may drive several GPUs: function attributes and occupancy are per device).
+struct PerDeviceOnce {
+  bool done[64] = {};
+  // returns the current device ordinal, or -1 on error; *first = true when this device has not been marked yet
+  int device(bool* first) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { *first = true; return -1; }
+    *first = !done[dev];
+    return dev;
+  }
+  void mark(int dev) { if (dev >= 0 && dev < 64) done[dev] = true; }
+};
+template <class K>
+inline cudaError_t ensure_max_dynamic_smem(PerDeviceOnce& once, K kernel, int bytes) {
+  bool first;
+  const int dev = once.device(&first);
+  if (!first) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) once.mark(dev);
+  return e;
 }
 
 int side_mode();   // SRL_SIDE_MODE diagnostic bitmask: 1 = one wgrad side stream, 2 = head wgrad on the main stream, 4 = grad memset on the main stream
@@ -53,6 +75,10 @@ cudaError_t launch_vtrace_iw(const float* log_rhos, const float* discounts, cons
 cudaError_t launch_vtrace_logits(const float* bl, const float* tl, const int64_t* actions, const float* discounts, const float* rewards,
                                  const float* values, const float* bootstrap, int T, int B, int A, float clip_rho, float clip_pg,
                                  float* vs, float* pg, float* lr, float* balp, float* talp, cudaStream_t st);
+cudaError_t launch_policy_rows_fwd(const float* logits, const int64_t* actions, int64_t N, int A, float* logp, float* ent, cudaStream_t st);
+cudaError_t launch_policy_rows_bwd(const float* logits, const int64_t* actions, const float* w_logp, const float* w_ent, int64_t N, int A,
+                                   float* dlogits, cudaStream_t st);
+cudaError_t launch_reduce_sum(const float* x, int64_t n, int square, float scale, float* out, cudaStream_t st);
 bool column_step_supported(int T, int B, int A);
 cudaError_t launch_column_step(const float* hpart, int nsplit, const float* bfc, float* h, const float* reward, const int64_t* action,
                                const uint8_t* done, const float* bl, const float* Wp, const float* bp, const float* Wb, const float* bb,
@@ -87,6 +113,7 @@ struct DpPeers { float* g[8]; float* rs[8]; unsigned* ctl[8]; int rank, world; }
 cudaError_t launch_dp_clip_optim(int optimizer, float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
                                  float* scratch, float lr, float a, float b, float eps, int step, int* dstep, const DpPeers& P,
                                  cudaStream_t st);
+cudaError_t launch_snapshot_if_finite(float* dst, const float* src, int64_t n, const float* losses, cudaStream_t st);
 cudaError_t launch_grad_norm(const float* g, int64_t n, float max_norm, float* coef, float* scratch, cudaStream_t st);
 cudaError_t launch_rmsprop(float* p, const float* g, float* v, int64_t n, const float* coef, float lr, float alpha, float eps,
                            cudaStream_t st);

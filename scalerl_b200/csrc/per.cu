@@ -22,19 +22,24 @@ __global__ void __launch_bounds__(1024) per_update_kernel(double* __restrict__ s
   const int t = threadIdx.x;
   int64_t leaf = -1;
   double v = 0.0, pr = 0.0;
+  bool valid = t < n;
   if (t < n) {
-    if (mode == 0) { leaf = idxs[t]; pr = prios[t]; v = pow(pr, alpha); }
-    else { leaf = (ptr + t) % memory_size; v = pow(scal[0], alpha); }
+    if (mode == 0) {
+      leaf = idxs[t]; pr = prios[t]; v = pow(pr, alpha);
+      // the reference asserts priority > 0 and 0 <= idx < len(self) (replay_buffer.py:346-351): an invalid entry is
+      // skipped here (never an out-of-bounds write) and counted in scal[1]; the Python wrapper raises on it
+      if (!(leaf >= 0 && leaf < memory_size) || !(pr > 0.0)) { valid = false; leaf = -1; atomicAdd(reinterpret_cast<unsigned long long*>(scal + 1), 1ull); }
+    } else { leaf = (ptr + t) % memory_size; v = pow(scal[0], alpha); }
   }
   sidx[t] = leaf;
   __syncthreads();
-  bool winner = t < n;
+  bool winner = valid;
   if (winner && mode == 0)
     for (int u = t + 1; u < n; ++u)
       if (sidx[u] == leaf) { winner = false; break; }
   if (winner) { sum[cap + leaf] = v; mn[cap + leaf] = v; }
   if (mode == 0) {       // max_priority = max(max_priority, priorities...)
-    double m = t < n ? pr : 0.0;
+    double m = valid ? pr : 0.0;
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((t & 31) == 0) smax[t >> 5] = m;
     __syncthreads();
@@ -42,7 +47,7 @@ __global__ void __launch_bounds__(1024) per_update_kernel(double* __restrict__ s
   }
   __syncthreads();
   for (int d = 1; d <= levels; ++d) {
-    if (t < n) {
+    if (valid) {
       const int64_t node = (cap + leaf) >> d;
       sum[node] = sum[2 * node] + sum[2 * node + 1];
       mn[node] = fmin(mn[2 * node], mn[2 * node + 1]);
@@ -96,7 +101,7 @@ __global__ void per_sample_kernel(const double* __restrict__ sum, const double* 
 __global__ void per_fill_kernel(double* __restrict__ sum, double* __restrict__ mn, int64_t n2, double* scal) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n2) { sum[i] = 0.0; mn[i] = INFINITY; }
-  if (i == 0) scal[0] = 1.0;                                     // max_priority (replay_buffer.py:308)
+  if (i == 0) { scal[0] = 1.0; scal[1] = 0.0; }                  // max_priority (replay_buffer.py:308); [1] = invalid-update counter (u64 bits)
 }
 
 }  // namespace srl
@@ -154,10 +159,19 @@ extern "C" int srl_per_update_priorities(srl_per_t* P, const int64_t* idxs, cons
   for (int64_t o = 0; o < n; o += 1024) {
     const int c = (int)(n - o < 1024 ? n - o : 1024);
     per_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(P->sum, P->mn, P->capacity, P->levels, idxs + o, priorities + o, c, P->alpha, P->scal, 0,
-                                                            0, P->memory_size);
+                                                            0, P->size);        // mode 0: the last argument bounds the valid indices (idx < len(self))
   }
   PCU(cudaGetLastError(), "per_update_priorities");
   return 0;
+}
+// number of (idx, priority) pairs skipped so far because idx was outside [0, size) or priority <= 0 (the reference asserts,
+// replay_buffer.py:346-351); synchronises `stream`
+extern "C" int64_t srl_per_invalid_updates(srl_per_t* P, void* stream) {
+  if (!P) return -1;
+  unsigned long long c = 0;
+  if (cudaMemcpyAsync(&c, P->scal + 1, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -1;
+  return (int64_t)c;
 }
 // uniforms f64 [batch] in [0,1) (device) -> idxs i64 [batch], IS weights (f64 and/or f32, either may be NULL)
 extern "C" int srl_per_sample(srl_per_t* P, const double* uniforms, int batch, double beta, int64_t* idxs, double* weights64, float* weights32,

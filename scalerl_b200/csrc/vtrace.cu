@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128) vtrace_logits_kernel(const float* __restr
   float acc = 0.f, vnext = __ldg(bootstrap + b), vsnext = vnext;
   for (int t = T - 1; t >= 0; --t) {
     const size_t o = (size_t)t * B + b;
-    const int act = (int)__ldg(actions + o);
+    const int act = ld_action(actions + o, A);
     const float talp = action_logp(tl + o * A, A, act);
     const float balp = action_logp(bl + o * A, A, act);
     const float lr = talp - balp;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(128) impala_tail_kernel(const float* __restric
     for (int t = T - 1; t >= 0; --t) {
       const size_t o = (size_t)t * B + b;        // model row t
       const size_t o1 = o + B;                   // trajectory row t+1
-      const int act = (int)__ldg(action + o1);
+      const int act = ld_action(action + o1, A);
       const float* trow = tl + o * A;
       float mx = -INFINITY;
       for (int a = 0; a < A; ++a) mx = fmaxf(mx, __ldg(trow + a));
@@ -283,7 +283,7 @@ SRL_DEVINL void tail_column_warp(const float* __restrict__ bl, const float* trow
     const bool ok = t < T;
     const int tt = ok ? t : 0;
     const size_t o = (size_t)tt * B + b, o1 = o + B;
-    const int act = (int)__ldg(action + o1);
+    const int act = ld_action(action + o1, A);
     const float* trow = trow0 + (size_t)tt * tstride;
     float mx = -INFINITY;
     for (int a = 0; a < A; ++a) mx = fmaxf(mx, ldf<NC>(trow + a));
@@ -384,6 +384,83 @@ __global__ void __launch_bounds__(128) impala_tail_warp_kernel(const float* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Row-wise policy ops behind the differentiable drop-ins of loss_fn.py / vtrace.action_log_probs (host side:
+// scalerl_b200/algorithms/impala/{loss_fn,vtrace}.py).  One thread per row of A logits.
+//   forward : logp[n] = log_softmax(logits[n])[action[n]]   (vtrace.py:31-40; loss_fn.py:16-23 uses its negation)
+//             ent[n]  = sum_a p log p                       (loss_fn.py:9-13)
+//   backward: dlogits[n][a] = w_logp[n] * (onehot(a == action[n]) - p[a]) + w_ent[n] * p[a] * (log p[a] - ent[n])
+//             (the autograd of  sum_n w_logp[n] * logp[n] + w_ent[n] * ent[n];  NULL weight array = zeros)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) policy_rows_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ actions, int64_t N,
+                                                              int A, float* __restrict__ logp, float* __restrict__ ent) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* row = logits + n * A;
+  float mx = -INFINITY;
+  for (int a = 0; a < A; ++a) mx = fmaxf(mx, __ldg(row + a));
+  float se = 0.f;
+  for (int a = 0; a < A; ++a) se += expf(__ldg(row + a) - mx);
+  const float lse = logf(se);
+  if (logp) logp[n] = (__ldg(row + ld_action(actions + n, A)) - mx) - lse;
+  if (ent) {
+    float e = 0.f;
+    for (int a = 0; a < A; ++a) { const float lp = (__ldg(row + a) - mx) - lse; e += expf(lp) * lp; }
+    ent[n] = e;
+  }
+}
+__global__ void __launch_bounds__(128) policy_rows_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ actions,
+                                                              const float* __restrict__ w_logp, const float* __restrict__ w_ent, int64_t N,
+                                                              int A, float* __restrict__ dlogits) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* row = logits + n * A;
+  float mx = -INFINITY;
+  for (int a = 0; a < A; ++a) mx = fmaxf(mx, __ldg(row + a));
+  float se = 0.f;
+  for (int a = 0; a < A; ++a) se += expf(__ldg(row + a) - mx);
+  const float lse = logf(se);
+  const float wl = w_logp ? __ldg(w_logp + n) : 0.f, we = w_ent ? __ldg(w_ent + n) : 0.f;
+  float e = 0.f;
+  if (w_ent)
+    for (int a = 0; a < A; ++a) { const float lp = (__ldg(row + a) - mx) - lse; e += expf(lp) * lp; }
+  const int act = actions ? ld_action(actions + n, A) : -1;
+  for (int a = 0; a < A; ++a) {
+    const float lp = (__ldg(row + a) - mx) - lse, p = expf(lp);
+    dlogits[n * A + a] = wl * ((a == act ? 1.f : 0.f) - p) + we * p * (lp - e);
+  }
+}
+// out[0] = scale * sum_i x[i]  or  scale * sum_i x[i]^2 (square != 0); ONE block, fixed order: deterministic
+__global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ x, int64_t n, int square, float scale, float* __restrict__ out) {
+  __shared__ float part[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) { const float v = __ldg(x + i); s += square ? v * v : v; }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = part[threadIdx.x];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) out[0] = scale * t;
+  }
+}
+cudaError_t launch_policy_rows_fwd(const float* logits, const int64_t* actions, int64_t N, int A, float* logp, float* ent, cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  policy_rows_fwd_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(logits, actions, N, A, logp, ent);
+  return cudaGetLastError();
+}
+cudaError_t launch_policy_rows_bwd(const float* logits, const int64_t* actions, const float* w_logp, const float* w_ent, int64_t N, int A,
+                                   float* dlogits, cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  policy_rows_bwd_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(logits, actions, w_logp, w_ent, N, A, dlogits);
+  return cudaGetLastError();
+}
+cudaError_t launch_reduce_sum(const float* x, int64_t n, int square, float scale, float* out, cudaStream_t st) {
+  reduce_sum_kernel<<<1, 1024, 0, st>>>(x, n, square, scale, out);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_vtrace_iw(const float* log_rhos, const float* discounts, const float* rewards, const float* values,
                              const float* bootstrap, int T, int B, float clip_rho, float clip_pg, float* vs, float* pg, int variant,
@@ -426,7 +503,8 @@ cudaError_t launch_vtrace_logits(const float* bl, const float* tl, const int64_t
 // latency-bound kernels become one.  Needs (T+1) * 2 KB of shared memory: used when that fits, B <= 512, A <= 32.
 // AMAX (8 or 32) bounds the unrolled per-action loops: their predicated-off iterations still cost issue slots.
 // ------------------------------------------------------------------------------------------------
-constexpr int COL_THREADS = 1024, COL_MAX_A = 32;      // 32 warps: every frame of a T <= 31 column in one pass of phase A
+constexpr int COL_THREADS = 1024, COL_MAX_A = 31;      // lane a == A computes the baseline: A + 1 <= 32 lanes
+//      // 32 warps: every frame of a T <= 31 column in one pass of phase A
 template <int NSPLIT, int AMAX, bool DBG>
 __global__ void __launch_bounds__(COL_THREADS) column_step_kernel(
     const float* __restrict__ hpart, const float* __restrict__ bfc, float* __restrict__ h, const float* __restrict__ reward,
@@ -469,7 +547,7 @@ __global__ void __launch_bounds__(COL_THREADS) column_step_kernel(
     int pre_act = 0;
     if (lane <= A) {
       pre_r = __ldg(reward + n);
-      pre_act = (int)__ldg(action + n);
+      pre_act = ld_action(action + n, A);
       pre_bias = lane < A ? __ldg(bp + lane) : __ldg(bb);
     }
     float4 x[4];
@@ -584,13 +662,17 @@ cudaError_t launch_column_step(const float* hpart, int nsplit, const float* bfc,
                                float baseline_cost, float entropy_cost, float* logits, float* baseline, float* vs, float* pg,
                                float* dlogits, float* dbaseline, __nv_bfloat16* dh, float* losses, float* scratch, cudaStream_t st) {
   if (!column_step_supported(T, B, A) || nsplit != 4) return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(column_step_kernel<4, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(column_step_kernel<4, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(column_step_kernel<4, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
+  static PerDeviceOnce once;
+  {
+    bool first;
+    const int dev = once.device(&first);
+    if (first) {
+      cudaError_t e = cudaFuncSetAttribute(column_step_kernel<4, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(column_step_kernel<4, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(column_step_kernel<4, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return e;
+      once.mark(dev);
+    }
   }
   static const bool dbg = [] { const char* e = getenv("SRL_COLUMN_DEBUG"); return e && atoi(e) != 0; }();   // prints phase times
 #define SRL_COL_ARGS dim3(B), dim3(COL_THREADS), column_smem_bytes(T, A), st, hpart, bfc, h, reward, action, done, bl, Wp, bp, Wb, bb, T, B, A, \

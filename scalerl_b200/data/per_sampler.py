@@ -19,6 +19,7 @@ class GpuPrioritizedSampler:
         h = C.c_void_p()
         self._check(self._L.srl_per_create(self.memory_size, self.alpha, C.byref(h)), 'srl_per_create')
         self._h = h
+        self._invalid_seen = 0
 
     def _check(self, rc, what):
         if rc != 0:
@@ -39,12 +40,20 @@ class GpuPrioritizedSampler:
         """n new transitions enter with priority max_priority ** alpha (replay_buffer.py:318-322)"""
         self._check(self._L.srl_per_add(self._h, int(n), self._stream()), 'srl_per_add')
 
-    def update_priorities(self, idxs: torch.Tensor, priorities: torch.Tensor):
+    def update_priorities(self, idxs: torch.Tensor, priorities: torch.Tensor, validate: bool = True):
+        """replay_buffer.py:346-351.  The reference asserts ``priority > 0`` and ``0 <= idx < len(self)``; with ``validate``
+        (default) a violation raises AssertionError-like ValueError after the launch (one 8-byte D2H read + stream sync);
+        the kernel itself never writes out of bounds (invalid pairs are skipped) so ``validate=False`` is safe and sync-free."""
         idxs = idxs.to(self.device, torch.int64).contiguous()
         pr = priorities.to(self.device, torch.float64).contiguous()
         if idxs.numel() != pr.numel():
             raise ValueError('idxs and priorities must have the same length')
         self._check(self._L.srl_per_update_priorities(self._h, idxs.data_ptr(), pr.data_ptr(), idxs.numel(), self._stream()), 'srl_per_update_priorities')
+        if validate:
+            bad = int(self._L.srl_per_invalid_updates(self._h, self._stream()))
+            if bad != self._invalid_seen:
+                n_new, self._invalid_seen = bad - self._invalid_seen, bad
+                raise ValueError(f'update_priorities: {n_new} pair(s) with idx outside [0, {len(self)}) or priority <= 0 were skipped')
 
     def sample(self, batch_size: int, beta: float = 0.4, uniforms: torch.Tensor = None, generator=None):
         """-> (idxs int64 [batch], weights float32 [batch]); ``uniforms`` (float64 in [0,1)) may be supplied for reproducibility"""

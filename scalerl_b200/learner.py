@@ -21,10 +21,76 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
+from .algorithms.base import BaseAgent
 
 PARAM_NAMES = ('conv1.weight', 'conv1.bias', 'conv2.weight', 'conv2.bias', 'conv3.weight', 'conv3.bias',
                'fc.weight', 'fc.bias', 'policy.weight', 'policy.bias', 'baseline.weight', 'baseline.bias')
 LSTM_PARAM_NAMES = tuple(f'rnn_layer.{w}_l{l}' for l in (0, 1) for w in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh'))
+
+
+def reference_param_order(use_lstm: bool = False):
+    """names in ``AtariNet.parameters()`` order (atari_model.py:30-59: conv1, conv2, conv3, fc, [rnn_layer], policy,
+    baseline) -- the integer keys of ``torch.optim.Optimizer.state_dict()['state']`` in a reference checkpoint"""
+    return PARAM_NAMES[:8] + (LSTM_PARAM_NAMES if use_lstm else ()) + PARAM_NAMES[8:]
+
+
+def _torch_param_groups(hp: 'ImpalaHParams', n: int):
+    """param_groups exactly as the installed torch writes them for the reference's optimizer (impala_atari.py:99-105)"""
+    dummy = [torch.nn.Parameter(torch.zeros(1)) for _ in range(n)]
+    if hp.optimizer == 'rmsprop':
+        opt = torch.optim.RMSprop(dummy, lr=hp.learning_rate, momentum=hp.momentum, eps=hp.epsilon, alpha=hp.alpha)
+    else:
+        opt = torch.optim.Adam(dummy, lr=hp.learning_rate, betas=(hp.adam_beta1, hp.adam_beta2), eps=hp.adam_eps)
+    return opt.state_dict()['param_groups']
+
+
+def to_torch_optimizer_state(hp: 'ImpalaHParams', tensors: Dict[str, Dict[str, torch.Tensor]], step: int) -> dict:
+    """``torch.optim.RMSprop(...).state_dict()`` / ``Adam`` layout (what ImpalaTrainer.save_checkpoint stores,
+    impala_atari.py:506-511): {'state': {i: {'step', 'square_avg' | 'exp_avg','exp_avg_sq'}}, 'param_groups': [...]},
+    i = index in AtariNet.parameters() order.  ``tensors``: kind -> name -> tensor.  No state before the first step,
+    as torch (state is created lazily)."""
+    order = reference_param_order(hp.use_lstm)
+    state = {}
+    if step > 0:
+        for i, n in enumerate(order):
+            st = {'step': torch.tensor(float(step))}
+            for kind, d in tensors.items():
+                st[kind] = d[n].detach().cpu().clone()
+            state[i] = st
+    return {'state': state, 'param_groups': _torch_param_groups(hp, len(order))}
+
+
+def from_torch_optimizer_state(sd: dict, use_lstm: bool):
+    """inverse of to_torch_optimizer_state; also accepts round 1's {'step', 'state': {kind: {name: tensor}}} layout.
+    -> (step, {kind: {name: tensor}}).  Unknown layouts raise (never silently skipped)."""
+    if not sd:
+        return 0, {}
+    state = sd.get('state', {})
+    if 'param_groups' not in sd:                 # legacy layout of this package (round 1)
+        kinds = {k: v for k, v in state.items() if k in ('square_avg', 'exp_avg', 'exp_avg_sq')}
+        if state and not kinds:
+            raise ValueError(f'optimizer_state_dict: unknown layout (keys {list(state)[:4]})')
+        return int(sd.get('step', 0)), kinds
+    order = reference_param_order(use_lstm)
+    if not state:
+        return 0, {}
+    if sorted(state) != list(range(len(order))):
+        raise ValueError(f'optimizer_state_dict: expected state for params 0..{len(order) - 1}, got keys {sorted(state)[:6]}...')
+    out: Dict[str, Dict[str, torch.Tensor]] = {}
+    steps = set()
+    for i, n in enumerate(order):
+        for kind, v in state[i].items():
+            if kind == 'step':
+                steps.add(int(float(v)))
+            elif kind in ('square_avg', 'exp_avg', 'exp_avg_sq'):
+                out.setdefault(kind, {})[n] = v
+            elif kind in ('momentum_buffer', 'grad_avg', 'max_exp_avg_sq'):
+                raise ValueError(f"optimizer_state_dict: '{kind}' (momentum / centered / amsgrad) is not supported by the fused optimizer")
+            else:
+                raise ValueError(f"optimizer_state_dict: unknown per-parameter entry '{kind}'")
+    if len(steps) != 1:
+        raise ValueError(f'optimizer_state_dict: parameters disagree on the step count: {sorted(steps)}')
+    return steps.pop(), out
 
 
 def param_shapes(num_actions: int, use_lstm: bool = False):
@@ -92,22 +158,26 @@ class ImpalaHParams:
         return c
 
 
-class B200ImpalaLearner:
+class B200ImpalaLearner(BaseAgent):
     """One learner process per GPU.  ``learn(batch)`` consumes the reference's batch dict
     (keys of create_buffers, impala_atari.py:122-151; tensors [T+1, B_local, ...]) and returns the
     reference's stats dict (impala_atari.py:333-340)."""
 
     def __init__(self, hp: ImpalaHParams, device: Optional[torch.device] = None, process_group=None,
-                 init_state_dict: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0, use_graph: bool = True):
+                 init_state_dict: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0, use_graph: bool = True,
+                 validate_inputs: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError('B200ImpalaLearner needs a CUDA device: scalerl_b200 has no CPU fallback')
+        super().__init__(hp)                 # BaseAgent keeps the arguments as self.args (algorithms/base.py:14-21)
         self.hp = hp
+        self.validate_inputs = validate_inputs      # raise on out-of-range actions like F.one_hot does (one extra sync per step)
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         # process_group: None -> default group when torch.distributed is initialised; False -> never all-reduce
         self.pg = process_group
         dist = torch.distributed
         self._dist = (process_group is not False and dist.is_available() and dist.is_initialized()
                       and dist.get_world_size(process_group or None) > 1)
+        self.world_size = dist.get_world_size(process_group or None) if self._dist else 1
         self._L = _lib.lib()
         with torch.cuda.device(self.device):
             self.names = PARAM_NAMES + (LSTM_PARAM_NAMES if hp.use_lstm else ())
@@ -224,15 +294,42 @@ class B200ImpalaLearner:
     def set_weights(self, weights):   # BaseAgent.set_weights (algorithms/base.py:94-100)
         self.load_state_dict(weights)
 
-    def optimizer_state_dict(self):
-        names = ('square_avg',) if self.hp.optimizer == 'rmsprop' else ('exp_avg', 'exp_avg_sq')
+    def _opt_tensors(self):
+        kinds = ('square_avg',) if self.hp.optimizer == 'rmsprop' else ('exp_avg', 'exp_avg_sq')
         flats = (self.opt_state0,) if self.hp.optimizer == 'rmsprop' else (self.opt_state0, self.opt_state1)
-        return {'step': self.global_opt_step, 'state': {nm: OrderedDict((n, self._view(f, i).detach().clone())
-                                                                     for i, n in enumerate(self.names)) for nm, f in zip(names, flats)}}
+        return {k: OrderedDict((n, self._view(f, i)) for i, n in enumerate(self.names)) for k, f in zip(kinds, flats)}
+
+    def optimizer_state_dict(self):
+        """torch.optim state_dict layout of the reference's optimizer (impala_atari.py:99-105,509): loadable by
+        ``torch.optim.RMSprop(AtariNet(...).parameters(), ...).load_state_dict`` and back"""
+        return to_torch_optimizer_state(self.hp, self._opt_tensors(), self.global_opt_step)
+
+    def load_optimizer_state_dict(self, sd) -> None:
+        step, kinds = from_torch_optimizer_state(sd, self.hp.use_lstm)
+        mine = self._opt_tensors()
+        for kind in kinds:
+            if kind not in mine:
+                raise ValueError(f"optimizer_state_dict holds '{kind}' but this learner runs {self.hp.optimizer}")
+        for kind, views in mine.items():
+            if kind in kinds:
+                for n, v in views.items():
+                    v.copy_(kinds[kind][n])
+            elif step > 0:
+                raise ValueError(f"optimizer_state_dict lacks '{kind}' for {self.hp.optimizer}")
+        self._set_opt_step(step)
 
     @property
     def global_opt_step(self):
         return getattr(self, '_opt_steps', 0)
+
+    def _set_opt_step(self, step: int) -> None:
+        """optimizer step count = Adam's bias-correction t (host copy + the device counter the captured graphs read)"""
+        _lib.check(self._L.srl_learner_set_step(self._h, int(step), self._stream()), 'srl_learner_set_step')
+        self._opt_steps = int(step)
+
+    def device_opt_step(self) -> int:
+        """the step count as the kernels see it (device counter; synchronises)"""
+        return int(self._L.srl_learner_get_step(self._h, self._stream()))
 
     def save_checkpoint(self, path: str) -> None:
         """same dict keys as ImpalaTrainer.save_checkpoint (impala_atari.py:506-511)"""
@@ -242,11 +339,7 @@ class B200ImpalaLearner:
     def load_checkpoint(self, path: str) -> None:
         ck = torch.load(path, map_location='cpu', weights_only=False)
         self.load_state_dict(ck['model_state_dict'])
-        st = ck.get('optimizer_state_dict', {}).get('state', {})
-        for nm, flat in (('square_avg', self.opt_state0), ('exp_avg', self.opt_state0), ('exp_avg_sq', self.opt_state1)):
-            if nm in st and flat is not None:
-                for i, n in enumerate(self.names):
-                    self._view(flat, i).copy_(st[nm][n])
+        self.load_optimizer_state_dict(ck.get('optimizer_state_dict', {}))
 
     # ------------------------------------------------------------------ compute
     def _stream(self):
@@ -297,7 +390,87 @@ class B200ImpalaLearner:
                                                rows, logits.data_ptr(), baseline.data_ptr(), self._stream()), 'srl_learner_forward')
         return dict(policy_logits=logits, baseline=baseline)
 
-    predict = forward
+    # ------------------------------------------------------------------ BaseAgent surface (algorithms/base.py:23-66)
+    def _validate(self, batch):
+        """what F.one_hot / gather raise on in the reference (atari_model.py:104, vtrace.py:35-40): actions outside [0, A)"""
+        a = batch['action']
+        if bool(((a < 0) | (a >= self.hp.num_actions)).any()):
+            raise RuntimeError(f'Class values must be smaller than num_classes ({self.hp.num_actions}) and non-negative: '
+                               f"batch['action'] has min {int(a.min())}, max {int(a.max())}")
+
+    def _policy(self, batch, initial_rnn_state=()):
+        out = self.forward(batch, initial_rnn_state)
+        return out[0] if isinstance(out, tuple) else out
+
+    @torch.no_grad()
+    def get_action(self, batch: Dict[str, torch.Tensor], initial_rnn_state=(), generator=None) -> torch.Tensor:
+        """BaseAgent.get_action: exploration-time actions = a multinomial sample of softmax(policy_logits), as
+        AtariNet.forward does in training mode (atari_model.py:130-132).  batch: [R, B, ...] rows, R <= T+1."""
+        lg = self._policy(batch, initial_rnn_state)['policy_logits']
+        R, B, A = lg.shape
+        return torch.multinomial(torch.softmax(lg.view(R * B, A), dim=1), num_samples=1, generator=generator).view(R, B)
+
+    @torch.no_grad()
+    def predict(self, batch: Dict[str, torch.Tensor], initial_rnn_state=()) -> torch.Tensor:
+        """BaseAgent.predict: evaluation-time actions = argmax of the policy logits (AtariNet in eval mode, atari_model.py:133-134)"""
+        return torch.argmax(self._policy(batch, initial_rnn_state)['policy_logits'], dim=-1)
+
+    @torch.no_grad()
+    def get_value(self, batch: Dict[str, torch.Tensor], initial_rnn_state=()) -> torch.Tensor:
+        """BaseAgent.get_value: the baseline head V(s) [R, B]"""
+        return self._policy(batch, initial_rnn_state)['baseline']
+
+    def set_option(self, name: str, value: int) -> None:
+        """run-time switch of the C context (e.g. 'column_fusion')"""
+        _lib.check(self._L.srl_learner_set_option(self._h, name.encode(), int(value)), 'srl_learner_set_option')
+
+    def snapshot_params(self, out: torch.Tensor, only_if_finite: bool = True) -> None:
+        """device-to-device copy of the flat fp32 parameters on the current stream (6.75 MB: a few microseconds of HBM
+        time): the weight publish reads the snapshot while the next step already updates the live parameters.  With
+        ``only_if_finite`` the copy is skipped ON THE DEVICE when the last step's total loss is NaN/Inf (the snapshot keeps
+        the last good weights; poisoned parameters never reach the actors)."""
+        _lib.check(self._L.srl_learner_snapshot_params(self._h, out.data_ptr(), self._losses.data_ptr() if only_if_finite else None,
+                                                       self._stream()), 'srl_learner_snapshot_params')
+
+    # ------------------------------------------------------------------ pipelined step (no host synchronisation)
+    def learn_async(self, batch: Dict[str, torch.Tensor], initial_rnn_state=()) -> int:
+        """Enqueue one learner step and the D2H read of its result (4 losses, grad norm, clip coefficient and the
+        [T,B] episode_return / done rows the stats need) into a pinned result slot; returns a ticket for ``result``.
+        Nothing here waits for the GPU: the caller can enqueue the next batch's copies and the weight publish first."""
+        hp = self.hp
+        if not hasattr(self, '_res'):
+            T, B = hp.rollout_length, hp.batch_size
+            self._res_depth = 4
+            self._res = [dict(scal=torch.zeros(8, dtype=torch.float32).pin_memory(), ep=torch.zeros(T, B, dtype=torch.float32).pin_memory(),
+                              done=torch.zeros(T, B, dtype=torch.uint8).pin_memory(), ev=torch.cuda.Event(), has_ep=False)
+                         for _ in range(self._res_depth)]
+            self._tickets = 0
+        self.learn(batch, initial_rnn_state, sync_stats=False)
+        k = self._tickets
+        r = self._res[k % self._res_depth]
+        if self._dist:
+            torch.distributed.all_reduce(self._losses, op=torch.distributed.ReduceOp.SUM, group=self.pg or None)
+        r['scal'][:4].copy_(self._losses, non_blocking=True)
+        r['scal'][4:6].copy_(self._coef, non_blocking=True)
+        r['has_ep'] = 'episode_return' in batch
+        if r['has_ep']:
+            r['ep'].copy_(batch['episode_return'][1:], non_blocking=True)
+            r['done'].copy_(self._done_u8(batch)[1:], non_blocking=True)
+        r['ev'].record(torch.cuda.current_stream(self.device))
+        self._tickets = k + 1
+        return k
+
+    def result(self, ticket: int) -> Dict[str, object]:
+        """block until step ``ticket`` finished; the reference's stats dict (impala_atari.py:332-340) + grad_norm"""
+        if not (self._tickets - self._res_depth <= ticket < self._tickets):
+            raise ValueError(f'result({ticket}): only the last {self._res_depth} steps are kept (newest ticket {self._tickets - 1})')
+        r = self._res[ticket % self._res_depth]
+        r['ev'].synchronize()
+        h = r['scal']
+        ep = r['ep'][r['done'].bool()] if r['has_ep'] else torch.empty(0)
+        return {'episode_returns': tuple(ep.numpy()), 'mean_episode_return': float(ep.mean()) if ep.numel() else float('nan'),
+                'total_loss': float(h[3]), 'pg_loss': float(h[0]), 'baseline_loss': float(h[1]), 'entropy_loss': float(h[2]),
+                'grad_norm': float(h[4])}
 
     @torch.no_grad()
     def forward_backward(self, batch):
@@ -344,14 +517,16 @@ class B200ImpalaLearner:
     @torch.no_grad()
     def apply_gradients(self):
         _lib.check(self._L.srl_learner_apply_gradients(self._h, self._coef.data_ptr(), self._stream()), 'srl_learner_apply_gradients')
-        self._opt_steps = self.global_opt_step + 1
+        if not torch.cuda.is_current_stream_capturing():     # a capture executes nothing: the replay counts the step
+            self._opt_steps = self.global_opt_step + 1
 
     @torch.no_grad()
     def apply_gradients_dp(self):
         """all ranks: SUM-reduce the gradients over peer memory, clip, optimizer step -- one kernel, no NCCL"""
         _lib.check(self._L.srl_learner_apply_gradients_dp(self._h, C.byref(self._peers), self._coef.data_ptr(), self._stream()),
                    'srl_learner_apply_gradients_dp')
-        self._opt_steps = self.global_opt_step + 1
+        if not torch.cuda.is_current_stream_capturing():
+            self._opt_steps = self.global_opt_step + 1
 
     def _enqueue_step(self, batch):
         """forward_backward -> apply_gradients on the current stream; with world_size > 1 the fc.weight gradient is
@@ -457,13 +632,16 @@ class B200ImpalaLearner:
               use_graph: Optional[bool] = None) -> Dict[str, object]:
         """One learner step (impala_atari.py:288-346).  Returns the reference's stats dict when sync_stats
         (one D2H read of 6 floats), else {} with everything left enqueued on the stream."""
+        if self.validate_inputs:
+            self._validate(batch)
         if self.hp.use_lstm:
             self._set_rnn_state(initial_rnn_state)
         if self.use_graph if use_graph is None else use_graph:
             self._graph_step(batch)
         else:
             self._enqueue_step(batch)
-        self.global_step += self.hp.rollout_length * self.hp.batch_size
+        # the reference counts the frames of the GLOBAL batch (impala_atari.py:391); a rank processes B_local columns of it
+        self.global_step += self.hp.rollout_length * self.hp.batch_size * self.world_size
         if not sync_stats:
             return {}
         host = self._stats_host

@@ -30,6 +30,31 @@ def test_header_symbols_exported(lib):
     assert sorted(_lib.EXPORTS) == names, 'ctypes binding table and header disagree'
 
 
+def test_testhooks_library_is_separate():
+    """unit-test entry points live in libscalerl_b200_testhooks.so, declared in their own header; the product library
+    exports none of them"""
+    src = open(os.path.join(ROOT, 'include', 'scalerl_b200_testhooks.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    names = sorted(set(re.findall(r'\b(srl_[a-z0-9_]+)\s*\(', src)))
+    srl_build.build()
+    H = ctypes.CDLL(_lib.HOOKS_PATH)
+    P = ctypes.CDLL(_lib.LIB_PATH)
+    assert names == sorted(_lib.HOOK_EXPORTS)
+    for n in names:
+        assert hasattr(H, n), n
+        assert not hasattr(P, n), f'{n} must not ship in the product library'
+
+
+def test_action_count_limit():
+    """A = 32 would need a 33rd warp lane for the baseline: rejected at creation"""
+    L = _lib.lib()
+    cfg = _lib.SrlConfig()
+    cfg.T, cfg.B, cfg.A = 20, 32, 32
+    h = ctypes.c_void_p()
+    assert L.srl_learner_create(ctypes.byref(cfg), None, None, None, None, ctypes.byref(h)) == -1
+    assert b'[1,31]' in L.srl_last_error()
+
+
 def test_param_layout_matches_atarinet():
     total, off, cnt = _lib.param_layout(6)
     assert sum(cnt) == 1687768        # AtariNet((4,84,84), 6) parameter count (SURVEY.md §8)

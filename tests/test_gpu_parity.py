@@ -273,7 +273,7 @@ def test_learn_step_ignores_stale_shared_memory(T, B):
         L, _ = _learner(T, B, A, 4, learning_rate=0.0)     # lr = 0: the three steps see identical weights
         for _ in range(3):                      # eager, capture, replay
             if poison:
-                _lib.check(_lib.lib().srl_test_poison_smem(None))
+                _lib.check_hook(_lib.hooks().srl_test_poison_smem(None))
                 torch.cuda.synchronize()
             L.learn(batch)
         g = L.flat_grads.clone()
@@ -435,7 +435,7 @@ def test_shifted_operand_descriptors(mn_major):
     """Hardware property the resident-window kernels rely on: a UMMA operand descriptor may start at ANY 128-byte row
     of a SWIZZLE_128B tile with base_offset = 0 (the swizzle is applied to absolute shared-memory address bits)."""
     from scalerl_b200 import _lib
-    Lb = _lib.lib()
+    Lb = _lib.hooks()
     g = torch.Generator().manual_seed(mn_major)
     if mn_major == 0:
         A = torch.randn(160, 64, generator=g).bfloat16().cuda()
@@ -445,7 +445,7 @@ def test_shifted_operand_descriptors(mn_major):
         Bm = torch.randn(96, 64, generator=g).bfloat16().cuda()
     for shift in range(0, 25):
         D = torch.zeros(128, 64, device='cuda')
-        _lib.check(Lb.srl_test_shifted_operand(A.data_ptr(), Bm.data_ptr(), D.data_ptr(), shift, mn_major, 0, None))
+        _lib.check_hook(Lb.srl_test_shifted_operand(A.data_ptr(), Bm.data_ptr(), D.data_ptr(), shift, mn_major, 0, None))
         torch.cuda.synchronize()
         ref = (A[shift:shift + 128].float() @ Bm.float().t()) if mn_major == 0 else (A[shift:shift + 64].float().t() @ Bm[shift:shift + 64].float())
         assert_close(D, ref, 1e-5, f'shift {shift}')
@@ -491,13 +491,13 @@ def test_programmatic_dependent_launch_waits_for_the_primary_grid():
     then sets a flag, kernel B (512 blocks, launched with the attribute) records the flag after its wait -- on the
     legacy default stream and on a created stream."""
     from scalerl_b200 import _lib
-    L = _lib.lib()
+    L = _lib.hooks()
     flag = torch.zeros(1, dtype=torch.int32, device='cuda')
     out = torch.zeros(512, dtype=torch.int32, device='cuda')
     for st in (None, torch.cuda.Stream()):
         for _ in range(20):
             out.zero_()
             torch.cuda.synchronize()
-            _lib.check(L.srl_test_pdl(flag.data_ptr(), out.data_ptr(), 512, 20000, st.cuda_stream if st else None))
+            _lib.check_hook(L.srl_test_pdl(flag.data_ptr(), out.data_ptr(), 512, 20000, st.cuda_stream if st else None))
             torch.cuda.synchronize()
             assert int((out != 1).sum()) == 0
