@@ -12,14 +12,16 @@ columns, global batch = 32*N.
 
 Printed JSON (one line, rank 0):
   value     device-resident whole-job frames/s (inputs already in HBM), CUDA events, max over ranks
-  e2e       same metric through the public host-batch API (HostBatchFeeder + B200ImpalaLearner.learn): pinned-host
-            H2D of every step's batch and D2H of the step's losses inside the timed region
+  e2e       same metric through the reference-facing API, ImpalaTrainer.get_batch + ImpalaTrainer.learn (impala_atari.py:222-349):
+            every step copies its batch from the pinned shared-memory trajectory ring to the device, runs the learner step,
+            reads the step's stats back and publishes the new weights (6.75 MB D2H) into the shared actor parameters -- all
+            inside the timed region (e2e.feeder_* keeps round 1's HostBatchFeeder loop for comparison)
   roofline  dominant kernel of the step: algorithmic FLOPs per launch / per-launch duration (CUDA events recorded
             around every launch, srl_learner_set_profiling) vs MEASURED_PEAKS.json
   cpu_baseline  the oracle port of the reference learner step timed on this box's host cores (rank 0, N=1)
-`--impl reference` times that CPU learner alone (the reference is pure Python + torch-CPU; its own trainer cannot
-be imported -- SURVEY.md §0 -- so the arm runs oracle/impala_oracle.py, the restatement pinned to the reference's
-modules by tests/golden).
+`--impl reference` times that CPU learner alone: the reference's own AtariNet / vtrace / loss_fn modules (oracle/_ref, built by
+oracle/make_ref.py in the build container) under the learn() statements of impala_atari.py:288-346 -- the trainer module
+itself cannot be imported; without oracle/_ref the arm falls back to the oracle port and says so (kind).
 """
 import argparse
 import json
@@ -111,6 +113,14 @@ class ClockSampler:
         return {'sm_mhz': med, 'sm_max_mhz': mx, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def workload_config(T, B, A, world, use_lstm=False):
+    """the workload both arms run -- identical dict in the b200 and the reference line (the driver compares them)"""
+    return {'workload': f'IMPALA Pong 84x84x4 uint8, T={T}, B={B}/GPU, A={A}, synthetic trajectories (BASELINE.json configs[1] per GPU)',
+            'rollout_length': T, 'columns_per_gpu': B, 'global_batch': B * world, 'num_actions': A, 'optimizer': 'rmsprop',
+            'use_lstm': bool(use_lstm), 'reward_clipping': 'abs_one', 'discounting': 0.99, 'baseline_cost': 0.5, 'entropy_cost': 0.0006,
+            'max_grad_norm': 40.0, 'learning_rate': 1e-4}
+
+
 def make_host_pool(T, B, A, n, seed):
     """n distinct synthetic [T+1,B] batches in pinned host memory (distributions of SURVEY.md §8d)."""
     import numpy as np
@@ -137,21 +147,50 @@ def usable_cores():
         return os.cpu_count() or 1
 
 
-def pick_threads(T, B, A):
+class _CpuLearner:
+    """the CPU learner step of the reference: its OWN modules from oracle/_ref (kind "reference") when that build output is
+    present, else the oracle port (kind "port")"""
+
+    def __init__(self, T, B, A, use_lstm=False):
+        from oracle import impala_oracle as O
+        from oracle import ref_learner as R
+        self.O = O
+        self.params = O.init_params(A, seed=0)
+        self.batch = O.synthetic_batch(T, B, A, seed=0)
+        self.use_lstm = use_lstm
+        self.state = ()
+        if R.available():
+            self.kind = 'reference'
+            sd = dict(self.params)
+            if use_lstm:
+                sd.update(O.init_lstm_params(A, seed=0))
+            self.ref = R.ReferenceLearner(A, use_lstm=use_lstm, state_dict=sd)
+            if use_lstm:
+                import torch
+                self.state = tuple(torch.zeros(2, B, 513 + A) for _ in range(2))
+        else:
+            if use_lstm:
+                raise RuntimeError('the LSTM CPU arm needs oracle/_ref (python oracle/make_ref.py)')
+            self.kind = 'port'
+            self.opt = O.new_opt_state(self.params)
+
+    def step(self):
+        if self.kind == 'reference':
+            return self.ref.learn(self.batch, self.state)
+        return self.O.learn_step(self.params, self.opt, self.batch, use_autograd=True)
+
+
+def pick_threads(cpu):
     """torch-CPU convs on this small batch do not scale to every core of a 128-core host: try a few intra-op
     thread counts (one step each) and keep the fastest -- the baseline gets its best configuration."""
     import torch
-    from oracle import impala_oracle as O
-    params = O.init_params(A, seed=0)
-    opt = O.new_opt_state(params)
-    batch = O.synthetic_batch(T, B, A, seed=0)
     cores = usable_cores()
     best, best_t = None, None
     for n in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
         torch.set_num_threads(n)
-        O.learn_step(params, opt, batch, use_autograd=True, update=False)
+        cpu.step()
         t0 = time.perf_counter()
-        O.learn_step(params, opt, batch, use_autograd=True, update=False)
+        cpu.step()
         dt = time.perf_counter() - t0
         if best_t is None or dt < best_t:
             best, best_t = n, dt
@@ -160,48 +199,41 @@ def pick_threads(T, B, A):
 
 
 def cpu_learner_fps(T, B, A, budget_s, warmup=1, max_steps=50, min_steps=3):
-    """oracle port of ImpalaTrainer.learn (fp32, autograd, RMSprop) on the host cores."""
-    import torch
-    from oracle import impala_oracle as O
-    cores, avail = pick_threads(T, B, A)
-    params = O.init_params(A, seed=0)
-    opt = O.new_opt_state(params)
-    batch = O.synthetic_batch(T, B, A, seed=0)
+    """the reference's CPU learner step (fp32, autograd, RMSprop) on the host cores"""
+    cpu = _CpuLearner(T, B, A)
+    cores, avail = pick_threads(cpu)
     for _ in range(warmup):
-        O.learn_step(params, opt, batch, use_autograd=True)
+        cpu.step()
     n, t0 = 0, time.perf_counter()
     while n < max_steps and (n < min_steps or time.perf_counter() - t0 < budget_s):
-        O.learn_step(params, opt, batch, use_autograd=True)
+        cpu.step()
         n += 1
     dt = time.perf_counter() - t0
-    return n * T * B / dt, n, dt / n, cores
+    return n * T * B / dt, n, dt / n, cores, cpu.kind
 
 
 def run_reference(args, rank, world, real_stdout):
     if rank != 0:
         return
     T, B, A = args.T, args.B, args.A
-    import torch
-    from oracle import impala_oracle as O
-    cores, avail = pick_threads(T, B, A)
-    params = O.init_params(A, seed=0)
-    opt = O.new_opt_state(params)
-    batch = O.synthetic_batch(T, B, A, seed=0)
+    cpu = _CpuLearner(T, B, A, use_lstm=args.use_lstm)
+    cores, avail = pick_threads(cpu)
     for _ in range(args.warmup):
-        O.learn_step(params, opt, batch, use_autograd=True)
+        cpu.step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.learn_step(params, opt, batch, use_autograd=True)
+        cpu.step()
     dt = time.perf_counter() - t0
     fps = args.steps * T * B / dt
-    sample = (f'{args.steps} learner steps of T={T}, B={B} columns (one GPU-rank shard of the global batch {B * world}), fp32 torch-CPU, '
+    what = ("the reference's own AtariNet / vtrace / loss_fn modules (oracle/_ref) under the learn() statements of impala_atari.py:288-346"
+            if cpu.kind == 'reference' else 'the oracle port of the reference learner step')
+    sample = (f'{args.steps} learner steps of T={T}, B={B} columns (one GPU-rank shard of the global batch {B * world}), fp32 torch-CPU, {what}, '
               f'{cores} intra-op threads (fastest of the tried counts; {avail} cores usable)')
     out = {'impl': 'reference', 'metric': 'learner_frames_per_sec', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': f'IMPALA Pong 84x84x4 uint8, T={T}, B={B}/GPU, A={A}, synthetic trajectories', 'rollout_length': T,
-                      'columns_per_gpu': B, 'global_batch': B * world, 'num_actions': A, 'optimizer': 'rmsprop'},
-           'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+           'config': workload_config(T, B, A, world, args.use_lstm),
+           'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': cpu.kind, 'sample': sample},
            'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     emit(real_stdout, out)
 
@@ -231,6 +263,7 @@ def _main(real_stdout):
     ap.add_argument('--A', type=int, default=A_DEFAULT)
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU-baseline work (rank 0, N=1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the other_configs / per_sampler measurements')
     ap.add_argument('--use-lstm', action='store_true', help='AtariNet(use_lstm=True) learner (BASELINE.json configs[4]: use with --T 100)')
     args = ap.parse_args()
     if args.warmup < 3:
@@ -254,6 +287,8 @@ def _main(real_stdout):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    from scalerl_b200.utils.numa import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local_rank)            # before any pinned allocation: first touch lands on the GPU's node
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
@@ -336,6 +371,45 @@ def _main(real_stdout):
     e2e_eager_ms = (time.perf_counter() - t0) / K * 1e3
     learner.use_graph = True
 
+    # ---------------- end to end through ImpalaTrainer.get_batch / learn (ring -> device, step, stats, weight publish) ----------------
+    import tempfile
+    from scalerl_b200.algorithms.impala.impala_atari import ImpalaArguments, ImpalaTrainer
+    from scalerl_b200.data.slot_queue import SlotQueue
+    targs = ImpalaArguments(num_actors=1, batch_size=B, rollout_length=T, num_buffers=POOL * B, num_actions=A, use_lstm=args.use_lstm,
+                            output_dir=tempfile.mkdtemp(prefix='srl_bench_'), disable_checkpoint=True)
+    trainer = ImpalaTrainer(targs, learner=learner)
+    for i, hb in enumerate(host_pool):                      # slot i*B + b = column b of pool batch i (what B actors would have written)
+        for b in range(B):
+            for k in H2D_KEYS:
+                trainer.buffers[k][i * B + b].copy_(hb[k][:, b])
+    free_q, full_q = SlotQueue(4 * POOL * B), SlotQueue(4 * POOL * B)
+
+    def trainer_loop(n, off):
+        st = None
+        for i in range(n):
+            base = ((off + i) % POOL) * B
+            for b in range(B):
+                full_q.put(base + b)
+            batch, state = trainer.get_batch(free_q, full_q)
+            st = trainer.learn(trainer.actor_model, None, batch, state)
+            while not free_q.empty():
+                free_q.get_nowait()
+        trainer.flush()
+        return st
+    trainer_loop(max(W, 6), 0)
+    barrier()
+    t0 = time.perf_counter()
+    tstats = trainer_loop(K, W)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+    tr_s = max_over_ranks(dt)
+    tr_value = frames / tr_s
+    tr_h2d = B * trainer.ring.slot_bytes + (trainer._rnn_host[0].numel() * 4 if args.use_lstm else 0)
+    tr_d2h = learner.numel * 4 + 8 + (8 * 4 + T * B * 5)       # weight publish + version counter + step result (scalars, episode_return, done)
+    published = int(trainer.weights_version[0])
+
     # ---------------- per-kernel durations (events around every launch) ----------------
     L = _lib.lib()
     _lib.check(L.srl_learner_set_profiling(learner._h, 1))
@@ -405,59 +479,166 @@ def _main(real_stdout):
                                  'bound': v['bound']} for k, v in gemm.items()}}
 
     # ---------------- stand-alone V-trace kernel: GB/s vs measured HBM peak (BASELINE.json metric, second half) ----------------
+    # Kernel-only: a CUDA graph of 100 C-ABI launches on preallocated buffers, CUDA events around the replay -> time per launch
+    # INCLUDING the ~1-2 us between dependent graph nodes (a lone launch cannot be timed finer with events).  At the spec size
+    # (T=20,B=512: 248 KB) the inputs are L2-resident and the kernel is latency-bound; the bandwidth-regime rows rotate inputs > L2.
     vtrace = None
     if rank == 0:
-        from scalerl_b200 import ops
+        Lc = _lib.lib()
         vtrace = {}
-        for (vt, vb, variant) in ((20, 512, 1), (20, 512, 0), (20, 1 << 20, 0), (20, 1 << 22, 0)):
+        for (vt, vb, variant) in ((20, 512, 1), (20, 512, 0), (100, 128, 1), (100, 128, 0), (20, 1 << 20, 0), (20, 1 << 22, 0)):
             g = torch.Generator(device=dev).manual_seed(1)
-            nrot = 1 if vb < (1 << 18) else max(2, int(200e6 // (24 * vt * vb)) + 1)   # rotate > L2 worth of inputs at the large sizes
+            big = vb >= (1 << 18)
+            nrot = max(2, int(200e6 // (24 * vt * vb)) + 1) if big else 1          # rotate > L2 worth of inputs at the large sizes
             sets = [[torch.randn(vt, vb, device=dev, generator=g) * 0.5, (torch.rand(vt, vb, device=dev, generator=g) > 0.02).float() * 0.99,
                      torch.randn(vt, vb, device=dev, generator=g), torch.randn(vt, vb, device=dev, generator=g),
                      torch.randn(vb, device=dev, generator=g)] for _ in range(nrot)]
+            o_vs, o_pg = torch.empty(vt, vb, device=dev), torch.empty(vt, vb, device=dev)
+
+            def launch(i):
+                a = sets[i % nrot]
+                _lib.check(Lc.srl_vtrace_from_importance_weights(a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr(), a[3].data_ptr(), a[4].data_ptr(),
+                                                                 vt, vb, 1.0, 1.0, o_vs.data_ptr(), o_pg.data_ptr(), variant,
+                                                                 torch.cuda.current_stream().cuda_stream), 'vtrace')
+            nl = 20 if big else 100
             for i in range(3):
-                ops.from_importance_weights(*sets[i % nrot], variant=variant)
+                launch(i)
             torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 20
-            a.record()
-            for i in range(reps):
-                ops.from_importance_weights(*sets[i % nrot], variant=variant)
-            b.record()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for i in range(nl):
+                    launch(i)
+            gr.replay()
             torch.cuda.synchronize()
-            ms = a.elapsed_time(b) / reps
+            a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            a_ev.record()
+            for _ in range(reps):
+                gr.replay()
+            b_ev.record()
+            torch.cuda.synchronize()
+            ms = a_ev.elapsed_time(b_ev) / (reps * nl)
             nbytes = 24 * vt * vb + 4 * vb
             vtrace[f'T{vt}_B{vb}_{"scan" if variant else "seq"}'] = {
                 'us': ms * 1e3, 'algorithmic_bytes': nbytes, 'GBps': nbytes / (ms * 1e-3) / 1e9,
-                'frac_of_hbm_peak': nbytes / (ms * 1e-3) / 1e9 / pk['hbm_gbs'], 'includes': 'torch.empty of 2 outputs + launch (host-timed ops wrapper)'}
+                'frac_of_hbm_peak': nbytes / (ms * 1e-3) / 1e9 / pk['hbm_gbs'],
+                'how': f'CUDA graph of {nl} srl_vtrace_from_importance_weights launches, events around {reps} replays; '
+                       + ('inputs rotate through > L2 worth of buffers' if big else 'inputs L2-resident (spec size)')}
+            del gr
 
     # ---------------- CPU baseline (rank 0, N=1) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, n, s_per, cores = cpu_learner_fps(T, B, A, args.cpu_budget)
-        cpu = {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-               'sample': f'{n} full learner steps of the same workload (T={T}, B={B}, fp32 torch-CPU autograd + RMSprop), {s_per * 1e3:.1f} ms/step'}
+        fps, n, s_per, cores, kind = cpu_learner_fps(T, B, A, args.cpu_budget)
+        cpu = {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': kind,
+               'sample': f'{n} full learner steps of the same workload (T={T}, B={B}, fp32 torch-CPU autograd + RMSprop; '
+                         + ("the reference's own modules from oracle/_ref" if kind == 'reference' else 'oracle port') + f'), {s_per * 1e3:.1f} ms/step'}
+
+    # ---------------- further BASELINE.json configurations, measured in the same run (short, device-resident) ----------------
+    def short_run(hp2, steps=10, warm=6, pool=3):
+        """ms/step of a second learner configuration (weak-scaling shard of this rank), device-resident, max over ranks"""
+        L2 = B200ImpalaLearner(hp2, device=dev, seed=0)
+        hp_ = make_host_pool(hp2.rollout_length, hp2.batch_size, hp2.num_actions, pool, seed=100 + rank)
+        dp_ = [{k: v.to(dev, non_blocking=True) for k, v in hb.items()} for hb in hp_]
+        st_ = ()
+        if hp2.use_lstm:
+            st_ = tuple(torch.zeros(2, hp2.batch_size, 513 + hp2.num_actions, device=dev) for _ in range(2))
+        for i in range(max(warm, 2 * pool)):
+            L2.learn(dp_[i % pool], st_, sync_stats=False)
+        barrier()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for i in range(steps):
+            L2.learn(dp_[i % pool], st_, sync_stats=False)
+        b_.record()
+        barrier()
+        ms_ = max_over_ranks(a_.elapsed_time(b_)) / steps
+        fin = bool(torch.isfinite(L2._losses).all().item())
+        L2.release_graphs()
+        L2.close()
+        fr = hp2.rollout_length * hp2.batch_size * world
+        return {'ms_per_step': ms_, 'frames_per_sec': fr / (ms_ * 1e-3), 'global_batch': hp2.batch_size * world, 'columns_per_gpu': hp2.batch_size,
+                'rollout_length': hp2.rollout_length, 'num_actions': hp2.num_actions, 'use_lstm': hp2.use_lstm, 'losses_finite': fin}
+
+    extra_cfg = {}
+    if not args.use_lstm and (T, B, A) == (T_DEFAULT, B_DEFAULT, A_DEFAULT) and not args.no_extras:
+        try:      # configs[2]: IMPALA Breakout T=20, B=512 over 8 GPUs = 64 columns per GPU, A=4 (global B = 64 N here)
+            extra_cfg['config3_breakout_64col'] = short_run(ImpalaHParams(rollout_length=20, batch_size=64, num_actions=4))
+        except Exception as e:      # noqa: BLE001
+            extra_cfg['config3_breakout_64col'] = {'error': repr(e)}
+        if world in (1, 2, 4, 8):
+            try:  # configs[4]: IMPALA + LSTM, T=100, global B=128 split over the ranks
+                extra_cfg['config5_lstm_T100_B128'] = short_run(ImpalaHParams(rollout_length=100, batch_size=128 // world, num_actions=6, use_lstm=True),
+                                                                steps=5, warm=4, pool=2)
+            except Exception as e:  # noqa: BLE001
+                extra_cfg['config5_lstm_T100_B128'] = {'error': repr(e)}
+
+    # ---------------- configs[3]: GPU prioritized-replay sampler vs the reference's CPU segment trees (rank 0, N=1) ----------------
+    per = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            from scalerl_b200.data.per_sampler import GpuPrioritizedSampler
+            from oracle import per_oracle as PO
+            cap, bsz = 1 << 20, 512
+            smp = GpuPrioritizedSampler(cap, alpha=0.6)
+            smp.add(cap)
+            gidx = torch.randint(0, cap, (bsz,), device=dev)
+            gpr = torch.rand(bsz, device=dev, dtype=torch.float64) + 0.01
+            for _ in range(3):
+                smp.sample(bsz, 0.4); smp.update_priorities(gidx, gpr, validate=False)
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nit = 200
+            a_.record()
+            for _ in range(nit):
+                smp.sample(bsz, 0.4); smp.update_priorities(gidx, gpr, validate=False)
+            b_.record()
+            torch.cuda.synchronize()
+            gpu_us = a_.elapsed_time(b_) / nit * 1e3
+            cpu_cap = 1 << 16           # the pure-Python trees of the reference are slow: smaller buffer, bounded time
+            ref_t = PO.RefPER(cpu_cap, 0.6) if hasattr(PO, 'RefPER') else None
+            cpu_us = None
+            if ref_t is not None:
+                ref_t.add(cpu_cap)
+                import numpy as np
+                rng = np.random.RandomState(0)
+                t0 = time.perf_counter(); n = 0
+                while time.perf_counter() - t0 < 3.0:
+                    ref_t.sample(bsz, 0.4, rng.rand(bsz)); ref_t.update_priorities(rng.randint(0, cpu_cap, bsz), rng.rand(bsz) + 0.01); n += 1
+                cpu_us = (time.perf_counter() - t0) / n * 1e6
+            per = {'batch': bsz, 'gpu_capacity': cap, 'gpu_us_per_sample_plus_update': gpu_us, 'gpu_transitions_per_sec': bsz / (gpu_us * 1e-6),
+                   'cpu_capacity': cpu_cap, 'cpu_us_per_sample_plus_update': cpu_us,
+                   'cpu_transitions_per_sec': (bsz / (cpu_us * 1e-6)) if cpu_us else None,
+                   'what': 'stratified proportional sample of 512 + priority update of 512 (float64 sum/min trees; replay_buffer.py:346-381)'}
+            smp.close()
+        except Exception as e:      # noqa: BLE001
+            per = {'error': repr(e)}
 
     if rank == 0:
+        peer = getattr(learner, '_peers', None) is not None
+        cfg = workload_config(T, B, A, world, args.use_lstm)
+        impl = {'parallelism': f'dp{world}' if world > 1 else 'single',
+                'grad_allreduce': 'none' if world == 1 else ('peer memory (NVLink loads) fused into the clip+optimizer kernel' if peer else 'nccl sum'),
+                'l2': f'inputs cycle through {POOL} distinct batches ({POOL * feeder.h2d_bytes / 1e6:.0f} MB > 126 MB L2)',
+                'operands': 'bf16 tensor-core operands, fp32 accumulate, fp32 master weights / V-trace / optimizer',
+                'launch': 'one CUDA graph per step (wgrad GEMMs on parallel branches, programmatic dependent launch)'
+                          if (world == 1 or peer) else 'CUDA graphs begin|finish|apply; NCCL all-reduce of fc.weight overlaps the conv backward',
+                'numa': numa}
         out = {'metric': 'learner_frames_per_sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': W,
                'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
-               'data': 'synthetic',
-               'config': {'workload': f'IMPALA Pong 84x84x4 uint8, T={T}, B={B}/GPU, A={A}, synthetic trajectories (BASELINE.json configs[1] per GPU)',
-                          'rollout_length': T, 'columns_per_gpu': B, 'global_batch': B * world, 'num_actions': A, 'optimizer': 'rmsprop', 'use_lstm': bool(args.use_lstm),
-                          'parallelism': f'dp{world}' if world > 1 else 'single',
-                          'grad_allreduce': 'none' if world == 1 else ('peer memory (NVLink loads) fused into the clip+optimizer kernel'
-                                                                     if getattr(learner, '_peers', None) is not None else 'nccl sum'),
-                          'l2': f'inputs cycle through {POOL} distinct batches ({POOL * feeder.h2d_bytes / 1e6:.0f} MB > 126 MB L2)',
-                          'operands': 'bf16 tensor-core operands, fp32 accumulate, fp32 master weights / V-trace / optimizer',
-                          'launch': 'one CUDA graph per step (wgrad GEMMs on parallel branches, programmatic dependent launch)'
-                                    if (world == 1 or getattr(learner, '_peers', None) is not None) else
-                                    'CUDA graphs begin|finish|apply; NCCL all-reduce of fc.weight overlaps the conv backward'},
-               'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': feeder.h2d_bytes, 'd2h_bytes_per_step': feeder.d2h_bytes,
-                       'ms_per_step': e2e_s / K * 1e3, 'api': 'HostBatchFeeder.submit/learn/result + B200ImpalaLearner.learn (pinned host batches)',
-                       'last_total_loss': stats['total_loss'], 'h2d_only_ms_per_step': h2d_only_ms, 'eager_launch_ms_per_step': e2e_eager_ms},
+               'data': 'synthetic', 'config': cfg, 'impl_details': impl,
+               'e2e': {'value': tr_value, 'unit': 'frames/s', 'h2d_bytes_per_step': tr_h2d, 'd2h_bytes_per_step': tr_d2h,
+                       'ms_per_step': tr_s / K * 1e3,
+                       'api': 'ImpalaTrainer.get_batch + ImpalaTrainer.learn (pinned shared-memory trajectory ring -> device, step, lagged stats, '
+                              'asynchronous versioned weight publish into the shared actor parameters)',
+                       'weights_published': published, 'last_total_loss': tstats['total_loss'],
+                       'feeder_value': e2e_value, 'feeder_ms_per_step': e2e_s / K * 1e3, 'feeder_h2d_bytes_per_step': feeder.h2d_bytes,
+                       'feeder_api': 'HostBatchFeeder.submit/learn/result (time-major pinned batches, no ring, no weight publish: round-1 e2e)',
+                       'h2d_only_ms_per_step': h2d_only_ms, 'eager_launch_ms_per_step': e2e_eager_ms},
                'gpu_launches': 17 * K, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'losses_finite': losses_finite,
-               'vtrace_standalone': vtrace}
+               'vtrace_standalone': vtrace, 'other_configs': extra_cfg, 'per_sampler': per}
         emit(real_stdout, out)
+    trainer.close() if False else None
     learner.release_graphs()
     if world > 1:
         torch.cuda.synchronize()

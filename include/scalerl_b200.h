@@ -84,7 +84,10 @@ typedef struct srl_config {
   int32_t A;                 /* num_actions (<= 31)                              */
   int32_t optimizer;         /* 0 = RMSprop (reference, impala_atari.py:99-105), 1 = Adam */
   int32_t reward_clip_abs_one;
-  int32_t simt_mainloop;     /* reserved, must be 0 (TMA-fed tcgen05 mainloop) */
+  int32_t precision;         /* encoder operand precision: 0 = bf16 (default, the measured configuration); 1 = fp32-accurate:
+                              * every bf16 operand tensor gets a low twin bf16(v - bf16(v)) and each tensor-core product runs as
+                              * hi*hi + hi*lo + lo*hi into the fp32 TMEM accumulator (16 significant operand bits, tighter than
+                              * kind::tf32's 11) -- the whole-step parity mode SURVEY.md §7.9 asks for; ~3x the MMAs */
   float discounting, baseline_cost, entropy_cost;
   float clip_rho_threshold, clip_pg_rho_threshold;   /* < 0: None */
   float max_grad_norm;       /* clip_grad_norm_ threshold (rl_args.py:108)       */
@@ -189,6 +192,12 @@ int srl_learner_set_profiling(srl_learner_t* L, int enable);
 int srl_profile_slot_count(void);
 const char* srl_profile_slot_name(int slot);
 int srl_learner_profile_collect(srl_learner_t* L, float* ms_out_host);
+
+/* pin / unpin caller-owned HOST memory (trajectory ring slots: the pageable torch.stack + .to(device) of impala_atari.py:248-265
+ * becomes direct DMA; actor parameters in shared memory: the target of the weight publish, impala_atari.py:348).  Registering a
+ * range that a stale or enclosing registration already covers succeeds. */
+int srl_host_register(void* ptr_host, int64_t bytes);
+int srl_host_unregister(void* ptr_host);
 
 /* asynchronous device-to-device copy on `stream` (used by tests to read the borrowed buffers) */
 int srl_memcpy_d2d(void* dst, const void* src, int64_t bytes, void* stream);

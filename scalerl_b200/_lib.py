@@ -20,7 +20,7 @@ class SrlDpPeers(C.Structure):
 class SrlConfig(C.Structure):
     """mirror of srl_config_t"""
     _fields_ = [('T', C.c_int32), ('B', C.c_int32), ('A', C.c_int32), ('optimizer', C.c_int32),
-                ('reward_clip_abs_one', C.c_int32), ('simt_mainloop', C.c_int32),
+                ('reward_clip_abs_one', C.c_int32), ('precision', C.c_int32),
                 ('discounting', C.c_float), ('baseline_cost', C.c_float), ('entropy_cost', C.c_float),
                 ('clip_rho_threshold', C.c_float), ('clip_pg_rho_threshold', C.c_float),
                 ('max_grad_norm', C.c_float), ('learning_rate', C.c_float), ('alpha', C.c_float), ('epsilon', C.c_float),
@@ -68,6 +68,8 @@ _SIGS = {
     'srl_learner_snapshot_params': [_P, _P, _P, _P],
     'srl_learner_set_step': [_P, _L, _P],
     'srl_memcpy_d2d': [_P, _P, _L, _P],
+    'srl_host_register': [_P, _L],
+    'srl_host_unregister': [_P],
     'srl_learner_set_profiling': [_P, _I],
     'srl_profile_slot_count': [],
     'srl_learner_profile_collect': [_P, _P],

@@ -92,10 +92,20 @@ def slot_layout(T: int, A: int, obs_shape=(4, 84, 84)):
     return out, off
 
 
+_REGISTERED: Dict[int, torch.Tensor] = {}       # data_ptr -> tensor (kept alive while pinned)
+
+
 def _host_register(t: torch.Tensor) -> None:
-    rc = int(torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0))
-    if rc not in (0, 712):               # 712 = cudaErrorHostMemoryAlreadyRegistered (e.g. two tensors on one page)
-        raise RuntimeError(f'cudaHostRegister failed: {rc}')
+    """pin a host tensor for DMA (srl_host_register); it must be unpinned (_host_unregister) before its memory goes away"""
+    from ... import _lib
+    _lib.check(_lib.lib().srl_host_register(t.data_ptr(), t.numel() * t.element_size()), 'srl_host_register')
+    _REGISTERED[t.data_ptr()] = t
+
+
+def _host_unregister(t: torch.Tensor) -> None:
+    from ... import _lib
+    if _REGISTERED.pop(t.data_ptr(), None) is not None:
+        _lib.lib().srl_host_unregister(t.data_ptr())
 
 
 class TrajectoryRing:
@@ -120,7 +130,7 @@ class TrajectoryRing:
 
     def unpin(self):
         if self._pinned:
-            torch.cuda.cudart().cudaHostUnregister(self.block.data_ptr())
+            _host_unregister(self.block)
             self._pinned = False
 
 
@@ -128,8 +138,10 @@ class ImpalaTrainer:
     stat_keys = ['total_loss', 'mean_episode_return', 'pg_loss', 'baseline_loss', 'entropy_loss']
 
     def __init__(self, args: ImpalaArguments, env_fn: Optional[Callable[[], Any]] = None,
-                 actor_model_fn: Optional[Callable[[], torch.nn.Module]] = None) -> None:
+                 actor_model_fn: Optional[Callable[[], torch.nn.Module]] = None, learner: Optional[B200ImpalaLearner] = None) -> None:
+        """``learner``: adopt an existing B200ImpalaLearner (same T / B / A) instead of creating one at the first learner call"""
         self.args = args
+        self._adopt = learner
         if args.num_buffers is None:                                   # impala_atari.py:72-73, applied BEFORE create_buffers
             args.num_buffers = max(2 * args.num_actors, args.batch_size)
         if args.num_actors >= args.num_buffers:                        # :74-75
@@ -228,8 +240,14 @@ class ImpalaTrainer:
             return
         if not (self.args.use_cuda and torch.cuda.is_available()):
             raise RuntimeError('the B200 ImpalaTrainer needs CUDA (no CPU learner path)')
-        sd = {k: v.detach().clone() for k, v in self.actor_model.state_dict().items()}
-        self.learner = B200ImpalaLearner(self.hparams(), init_state_dict=sd, process_group=None)
+        if self._adopt is not None:
+            hp, want = self._adopt.hp, self.hparams()
+            if (hp.rollout_length, hp.batch_size, hp.num_actions, hp.use_lstm) != (want.rollout_length, want.batch_size, want.num_actions, want.use_lstm):
+                raise ValueError('the adopted learner was built for another T / B / A / use_lstm')
+            self.learner = self._adopt
+        else:
+            sd = {k: v.detach().clone() for k, v in self.actor_model.state_dict().items()}
+            self.learner = B200ImpalaLearner(self.hparams(), init_state_dict=sd, process_group=None)
         self.ring.pin()
         from ...data.feeder import batch_specs, H2D_KEYS
         hp = self.learner.hp
@@ -258,6 +276,29 @@ class ImpalaTrainer:
         self._registered_actor = None
         self._steps_done = 0
 
+    def close(self) -> None:
+        """drain the GPU work, unpin the shared host memory and drop the learner (safe to call twice)"""
+        if self.learner is None:
+            return
+        try:
+            self.flush()
+        finally:
+            for t in getattr(self, '_actor_targets', []):
+                _host_unregister(t)
+            self._actor_targets = []
+            self._registered_actor = None
+            _host_unregister(self.weights_version)
+            self.ring.unpin()
+            self.learner.release_graphs()
+            self.learner.close()
+            self.learner = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # noqa: BLE001 -- interpreter shutdown
+            pass
+
     def _poll_releases(self) -> None:
         """hand slots whose H2D copy has finished back to the actors (never blocks)"""
         while self._pending_release and self._pending_release[0][0].query():
@@ -285,10 +326,10 @@ class ImpalaTrainer:
         if lock is not None:
             with lock:
                 timings.time('lock')
-                indices = [self._dequeue(full_queue) for _ in range(self.args.batch_size)]
+                indices = self._dequeue_batch(full_queue)
         else:
             timings.time('lock')
-            indices = [self._dequeue(full_queue) for _ in range(self.args.batch_size)]
+            indices = self._dequeue_batch(full_queue)
         timings.time('dequeue')
         s = self._slot
         self._slot ^= 1
@@ -301,8 +342,14 @@ class ImpalaTrainer:
                 self._copy_stream.wait_event(self._consumed[s])          # the step that read this device batch has finished
             if buffers is self.buffers:       # ring slots: ONE pinned H2D copy per slot, then scatter on the device
                 stg = self._staging[s]
-                for b, m in enumerate(indices):
-                    stg[b].copy_(self.ring.block[m * sb:(m + 1) * sb], non_blocking=True)
+                b = 0
+                while b < len(indices):                  # runs of consecutive slots travel as ONE copy
+                    e = b + 1
+                    while e < len(indices) and indices[e] == indices[e - 1] + 1:
+                        e += 1
+                    m = indices[b]
+                    stg[b:e].view(-1).copy_(self.ring.block[m * sb:(m + e - b) * sb], non_blocking=True)
+                    b = e
                 _lib.check(_lib.lib().srl_unpack_slots(
                     stg.data_ptr(), sb, self._slot_off, hp.rollout_length, hp.batch_size, hp.num_actions, dst['obs'].data_ptr(),
                     dst['reward'].data_ptr(), dst['done'].data_ptr(), dst['action'].data_ptr(), dst['policy_logits'].data_ptr(),
@@ -336,6 +383,24 @@ class ImpalaTrainer:
         self._cur_slot = s
         timings.time('device')
         return dst, state
+
+    def _dequeue_batch(self, full_queue) -> List[int]:
+        """B indices from the full queue: in bulk when the queue offers ``get_many`` (SlotQueue), else one ``get`` each"""
+        B = self.args.batch_size
+        if not hasattr(full_queue, 'get_many'):
+            return [self._dequeue(full_queue) for _ in range(B)]
+        out: List[int] = []
+        while len(out) < B:
+            got = full_queue.get_many(B - len(out), timeout=0.0005)
+            out.extend(got)
+            if not got:
+                self._poll_releases()
+                actors = getattr(self, '_actors', None)
+                if actors:
+                    dead = [p.name for p in actors if not p.is_alive()]
+                    if dead:
+                        raise RuntimeError(f'actor process(es) exited while the learner was waiting for trajectories: {dead}')
+        return out
 
     def _dequeue(self, full_queue):
         """full_queue.get() that (a) keeps releasing slots whose copies finish meanwhile -- the actors may be waiting for
@@ -392,6 +457,15 @@ class ImpalaTrainer:
         if missing:
             raise KeyError(f'actor_model.state_dict() lacks {missing}')
         self._actor_targets = []
+        self._actor_flat = None
+        flat = getattr(actor_model, 'flat_params', None)
+        if (isinstance(flat, torch.Tensor) and flat.numel() == self.learner.numel and flat.is_shared() and flat.dtype == torch.float32 and
+                all(sd[n].data_ptr() == flat.data_ptr() + 4 * self.learner._off[i] for i, n in enumerate(self.learner.names))):
+            _host_register(flat)             # the actor keeps ONE flat buffer in the learner's layout: one D2H copy per publish
+            self._actor_flat = flat
+            self._actor_targets = [flat]
+            self._registered_actor = actor_model
+            return
         for n in self.learner.names:
             t = sd[n]
             if tuple(t.shape) != tuple(self.learner.shapes[n]) or t.dtype != torch.float32 or not t.is_contiguous():
@@ -420,8 +494,11 @@ class ImpalaTrainer:
         self._version = version
         with torch.cuda.stream(self._publish_stream):
             self._publish_stream.wait_event(snap_ev)
-            for i, t in enumerate(self._actor_targets):
-                t.copy_(L._view(self._snapshot, i), non_blocking=True)
+            if self._actor_flat is not None:
+                self._actor_flat.copy_(self._snapshot, non_blocking=True)
+            else:
+                for i, t in enumerate(self._actor_targets):
+                    t.copy_(L._view(self._snapshot, i), non_blocking=True)
             self._version_dev.fill_(version)
             self.weights_version.copy_(self._version_dev, non_blocking=True)
             self._pub_done = torch.cuda.Event()
@@ -453,7 +530,8 @@ class ImpalaTrainer:
     def train(self, log_every_s: float = 5.0, learner_in_process: bool = True) -> Dict[str, Any]:
         """impala_atari.py:403-494.  Actors are forked BEFORE CUDA is touched; the learner loop then runs in this
         process (learner_in_process) -- one learner per GPU; multi-GPU runs launch one trainer per rank (torchrun)."""
-        free_queue, full_queue = self._ctx.SimpleQueue(), self._ctx.SimpleQueue()
+        from ...data.slot_queue import SlotQueue          # mp.SimpleQueue's put/get/empty over a shared-memory index ring
+        free_queue, full_queue = SlotQueue(2 * self.args.num_buffers + self.args.num_actors + 4, self._ctx), SlotQueue(2 * self.args.num_buffers + 4, self._ctx)
         actors = []
         for i in range(self.args.num_actors):
             p = self._ctx.Process(target=self.get_action, name=f'actor-process-{i}',

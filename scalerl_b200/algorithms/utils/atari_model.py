@@ -15,7 +15,7 @@ from collections import OrderedDict
 import torch
 import torch.nn.functional as F
 
-from ...learner import LSTM_PARAM_NAMES, PARAM_NAMES, param_shapes, reference_param_order
+from ...learner import param_shapes, reference_param_order
 
 
 class ActorNet(torch.nn.Module):
@@ -29,6 +29,14 @@ class ActorNet(torch.nn.Module):
         g = torch.Generator().manual_seed(seed)
         fan = 1
         shapes = param_shapes(num_actions, self.use_lstm)
+        # All parameters are views of ONE flat fp32 buffer laid out like the learner's flat parameter buffer
+        # (srl_param_layout_ex): the weight publish is then a single D2H copy into shared memory (impala_atari.py:348).
+        from ... import _lib
+        from ...learner import PARAM_NAMES, LSTM_PARAM_NAMES
+        total, off, cnt = _lib.param_layout(self.num_actions, self.use_lstm)
+        lay_names = PARAM_NAMES + (LSTM_PARAM_NAMES if self.use_lstm else ())
+        self.flat_layout = {n: (off[i], cnt[i]) for i, n in enumerate(lay_names)}
+        self.flat_params = torch.zeros(total)
         for n in self.names:
             shp = shapes[n]
             if n.startswith('rnn_layer.'):
@@ -38,8 +46,18 @@ class ActorNet(torch.nn.Module):
                 for d in shp[1:]:
                     fan *= d
             bound = 1.0 / fan ** 0.5
-            self.register_parameter(n.replace('.', '_'), torch.nn.Parameter((torch.rand(shp, generator=g) * 2 - 1) * bound,
-                                                                           requires_grad=False))
+            o, c = self.flat_layout[n]
+            view = self.flat_params[o:o + c].view(shp)
+            view.copy_((torch.rand(shp, generator=g) * 2 - 1) * bound)
+            self.register_parameter(n.replace('.', '_'), torch.nn.Parameter(view, requires_grad=False))
+
+    def share_memory(self):
+        """moves the ONE underlying storage to shared memory; every parameter stays a view of it"""
+        self.flat_params.share_memory_()
+        for n in self.names:
+            o, c = self.flat_layout[n]
+            self._p(n).data = self.flat_params[o:o + c].view(self._p(n).shape)
+        return self
 
     def _p(self, n):
         return getattr(self, n.replace('.', '_'))

@@ -178,6 +178,8 @@ struct srl_learner {
   int step;                       // optimizer step count (Adam bias correction)
   bool have_fwd;
   TmaMaps maps;                   // tensor maps of the TMA mainloop
+  TmaMapsLo maps_lo;              // ... over the low operand tensors (precision = 1 only)
+  char* lo_arena;
   SideStream ss;                  // wgrad side stream + fork/join events
   int* dstep;                     // device-side optimizer step count (graph-replay safe Adam bias correction)
   srl_lstm_t* lstm;               // use_lstm: the 2-layer LSTM core (csrc/lstm.cu) working on views of params/grads
@@ -201,7 +203,8 @@ static int check_cfg(const srl_config_t* c) {
   REQ((int64_t)(c->T + 1) * c->B <= 65536, "config: (T+1)*B=%lld frames per GPU exceeds 65536", (long long)(c->T + 1) * c->B);
   REQ(c->optimizer == 0 || c->optimizer == 1, "config: optimizer must be 0 (rmsprop) or 1 (adam)");
   REQ(c->use_lstm == 0 || c->use_lstm == 1, "config: use_lstm must be 0 or 1");
-  REQ(c->simt_mainloop == 0, "config: only mainloop 0 (TMA-fed tcgen05) exists; the register-gather triage modes were retired with the grid layouts");
+  REQ(c->precision == 0 || c->precision == 1, "config: precision must be 0 (bf16 operands) or 1 (fp32-accurate split operands)");
+  REQ(!(c->precision == 1 && c->use_lstm), "config: the fp32-accurate operand mode covers the non-LSTM learner only");
   return 0;
 }
 
@@ -216,6 +219,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   REQ(L, "out of host memory");
   L->cfg = *cfg; L->params = params; L->grads = grads; L->opt0 = opt0; L->opt1 = opt1;
   L->nparams = layout_ex(cfg->A, cfg->use_lstm, nullptr, nullptr);
+  L->lo_arena = nullptr;
   L->lstm = nullptr; L->lstm_arena = nullptr; L->core = L->lstm_out = L->dout = L->dcore = nullptr; L->lstm_off0 = L->lstm_len = 0;
   L->P = make_ptrs(params, cfg->A);
   L->G = make_ptrs(grads, cfg->A);
@@ -280,9 +284,32 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   for (int e2 = 0; e2 < 12 && L->ss.side; ++e2)
     if (cudaEventCreateWithFlags(&L->ss.ev[e2], cudaEventDisableTiming) != cudaSuccess) { L->ss.side = nullptr; }
   cudaGetLastError();
+  if (cfg->precision == 1) {      // low twins of every bf16 operand tensor (same layouts), zero-initialised like the originals
+    const int64_t lo_sizes[8] = {al(NF * 400 * 32 * 2), al(NF * 81 * 64 * 2), al(NF * 49 * 64 * 2), al(NB * 512 * 2), al(NB * 81 * 64 * 2),
+                                 al(NB * 100 * 64 * 2), al(NB * 441 * 64 * 2), al(WPack::TOTAL * 2)};
+    int64_t lo_total = 0;
+    for (int j = 0; j < 8; ++j) lo_total += lo_sizes[j];
+    if (cudaMalloc(&L->lo_arena, lo_total) != cudaSuccess || cudaMemset(L->lo_arena, 0, lo_total) != cudaSuccess) {
+      if (L->lo_arena) cudaFree(L->lo_arena);
+      cudaFree(L->arena); delete L;
+      return fail(SRL_ESTATE, "learner_create: cudaMalloc of the low operand tensors failed");
+    }
+    L->arena_bytes += lo_total;
+    char* ql = L->lo_arena; int j = 0;
+    L->buf.a1_lo = (__nv_bfloat16*)ql; ql += lo_sizes[j++];
+    L->buf.a2_lo = (__nv_bfloat16*)ql; ql += lo_sizes[j++];
+    L->buf.a3_lo = (__nv_bfloat16*)ql; ql += lo_sizes[j++];
+    L->buf.dh_lo = (__nv_bfloat16*)ql; ql += lo_sizes[j++];
+    L->buf.da3_lo = (__nv_bfloat16*)ql; ql += lo_sizes[j++];
+    L->buf.da2_lo = (__nv_bfloat16*)ql; ql += lo_sizes[j++];
+    L->buf.da1_lo = (__nv_bfloat16*)ql; ql += lo_sizes[j++];
+    L->buf.wpack_lo = (__nv_bfloat16*)ql; ql += lo_sizes[j++];
+  }
   {
     const char* why = nullptr;
-    if (build_tma_maps(L->buf, (int)NF, (int)NB, &L->maps, &why) != cudaSuccess) {
+    if (build_tma_maps(L->buf, (int)NF, (int)NB, &L->maps, &why) != cudaSuccess ||
+        (cfg->precision == 1 && build_tma_maps_lo(L->buf, (int)NF, (int)NB, &L->maps_lo, &why) != cudaSuccess)) {
+      if (L->lo_arena) cudaFree(L->lo_arena);
       cudaFree(L->arena);
       delete L;
       return fail(SRL_ESTATE, "learner_create: building TMA tensor map '%s' failed (driver without cuTensorMapEncodeTiled?)", why ? why : "?");
@@ -322,6 +349,7 @@ extern "C" int srl_learner_destroy(srl_learner_t* L) {
   if (L->ss.side3) cudaStreamDestroy(L->ss.side3);
   if (L->lstm) srl_lstm_destroy(L->lstm);
   if (L->lstm_arena) cudaFree(L->lstm_arena);
+  if (L->lo_arena) cudaFree(L->lo_arena);
   cudaFree(L->arena);
   delete L;
   return 0;
@@ -333,7 +361,7 @@ extern "C" int srl_learner_set_config(srl_learner_t* L, const srl_config_t* cfg)
   int rc = check_cfg(cfg);
   if (rc) return rc;
   REQ(cfg->T == L->cfg.T && cfg->B == L->cfg.B && cfg->A == L->cfg.A && cfg->optimizer == L->cfg.optimizer &&
-      cfg->simt_mainloop == L->cfg.simt_mainloop && cfg->use_lstm == L->cfg.use_lstm, "set_config: T/B/A/optimizer/mainloop/use_lstm are fixed at creation");
+      cfg->precision == L->cfg.precision && cfg->use_lstm == L->cfg.use_lstm, "set_config: T/B/A/optimizer/precision/use_lstm are fixed at creation");
   L->cfg = *cfg;
   return 0;
 }
@@ -362,7 +390,7 @@ extern "C" int64_t srl_learner_get_step(srl_learner_t* L, void* stream) {
 
 extern "C" int srl_learner_pack_weights(srl_learner_t* L, void* stream) {
   REQ(L, "learner is NULL");
-  CU(launch_pack_weights(L->P, L->buf.wpack, (cudaStream_t)stream), "pack_weights");
+  CU(launch_pack_weights(L->P, L->buf.wpack, (cudaStream_t)stream, L->buf.wpack_lo), "pack_weights");
   return 0;
 }
 
@@ -399,7 +427,7 @@ static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStrea
       layout(L->cfg.A, off, cnt);
       CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), L->ss.side), "zero small grads");
     }
-    CU(launch_pack_weights(L->P, L->buf.wpack, L->ss.side), "pack_weights");
+    CU(launch_pack_weights(L->P, L->buf.wpack, L->ss.side, L->buf.wpack_lo), "pack_weights");
     CU(cudaEventRecord(L->ss.ev[6], L->ss.side), "join pack");
     packed = L->ss.ev[6];
   } else {
@@ -411,10 +439,10 @@ static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStrea
       L->pf.e(PS_ZERO_GRADS);
     }
     L->pf.b(PS_PACK);
-    CU(launch_pack_weights(L->P, L->buf.wpack, st), "pack_weights");
+    CU(launch_pack_weights(L->P, L->buf.wpack, st, L->buf.wpack_lo), "pack_weights");
     L->pf.e(PS_PACK);
   }
-  CU(encoder_forward(obs, frames, L->P, L->buf, L->maps, L->cfg.simt_mainloop, st, L->pf, packed), "encoder_forward");
+  CU(encoder_forward(obs, frames, L->P, L->buf, L->maps, L->cfg.precision, st, L->pf, packed, &L->maps_lo), "encoder_forward");
   return 0;
 }
 
@@ -453,7 +481,7 @@ static int fb_begin(srl_learner* L, const uint8_t* obs, const float* reward, con
     CU(launch_column_step(L->buf.hpart, FC_SPLITS, L->P.bf, L->buf.h, reward, action, done, behavior_logits, L->P.wp, L->P.bp, L->P.wb,
                           L->P.bb, c.T, c.B, c.A, c.discounting, c.reward_clip_abs_one, c.clip_rho_threshold, c.clip_pg_rho_threshold,
                           c.baseline_cost, c.entropy_cost, L->logits, L->baseline, vs, pg_advantages, L->dlogits, L->dbaseline, L->buf.dh,
-                          losses, L->scratch, st), "column_step");
+                          losses, L->scratch, st, L->buf.dh_lo), "column_step");
     L->pf.e(PS_TAIL);
   } else {
     rc = forward_impl(L, obs, reward, action, NF, L->logits, L->baseline, st, true);
@@ -470,10 +498,10 @@ static int fb_begin(srl_learner* L, const uint8_t* obs, const float* reward, con
     cudaStream_t sw = fork ? L->ss.side : st;
     if (fork) { CU(cudaEventRecord(L->ss.ev[8], st), "fork head wgrad"); CU(cudaStreamWaitEvent(sw, L->ss.ev[8], 0), "fork head wgrad"); }
     CU(launch_head_bwd(L->dlogits, L->dbaseline, L->buf.h, reward, action, L->P.wp, L->P.wb, NB, c.A, L->buf.dh, L->G.wp, L->G.bp, L->G.wb,
-                       L->G.bb, st, sw, !fused), "head_bwd");      // side stream `side` is joined by encoder_backward (after the fc wgrad)
+                       L->G.bb, st, sw, !fused, L->buf.dh_lo), "head_bwd");      // side stream `side` is joined by encoder_backward (after the fc wgrad)
   }
   L->pf.e(PS_HEAD_BWD);
-  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.simt_mainloop, st, L->pf, L->ss, phase), "encoder_backward");
+  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.precision, st, L->pf, L->ss, phase, &L->maps_lo), "encoder_backward");
   L->have_fwd = true;
   return 0;
 }
@@ -500,7 +528,7 @@ extern "C" int srl_learner_backward_finish(srl_learner_t* L, const uint8_t* obs,
   const srl_config_t& c = L->cfg;
   L->pf.st = (cudaStream_t)stream;
   pdl_set_active(!L->pf.on);
-  CU(encoder_backward(obs, c.T * c.B, L->buf, L->G, L->maps, c.simt_mainloop, (cudaStream_t)stream, L->pf, L->ss, 1), "encoder_backward");
+  CU(encoder_backward(obs, c.T * c.B, L->buf, L->G, L->maps, c.precision, (cudaStream_t)stream, L->pf, L->ss, 1, &L->maps_lo), "encoder_backward");
   return 0;
 }
 
@@ -548,7 +576,7 @@ extern "C" int srl_learner_forward_backward_lstm(srl_learner_t* L, const uint8_t
   rc = srl_lstm_backward(L->lstm, L->dout, done, L->dcore, st);
   if (rc) return fail(rc, "lstm_backward: %s", srl_lstm_last_error());
   CU(launch_dcore_to_dh(L->dcore, L->buf.h, NB, c.A, L->buf.dh, st), "dcore_to_dh");
-  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.simt_mainloop, st, L->pf, L->ss, 2), "encoder_backward");
+  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.precision, st, L->pf, L->ss, 2, &L->maps_lo), "encoder_backward");
   L->have_fwd = true;
   return 0;
 }
@@ -633,6 +661,29 @@ extern "C" int srl_learner_snapshot_params(srl_learner_t* L, float* dst, const f
   return 0;
 }
 
+// Pinning of caller-owned HOST memory (the shared-memory trajectory ring, the actors' shared parameter tensors) so that the
+// copy engine reads / writes it directly.  A stale registration left by a freed mapping at the same address (or a second tensor
+// on an already pinned page) is replaced instead of failing, and no sticky error is left behind for the next CUDA call.
+extern "C" int srl_host_register(void* ptr_host, int64_t bytes) {
+  REQ(ptr_host && bytes > 0, "host_register: bad argument");
+  cudaError_t e = cudaHostRegister(ptr_host, (size_t)bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    cudaHostUnregister(ptr_host);
+    cudaGetLastError();
+    e = cudaHostRegister(ptr_host, (size_t)bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }     // part of a larger live registration: fine
+  }
+  if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(e, "cudaHostRegister"); }
+  return 0;
+}
+extern "C" int srl_host_unregister(void* ptr_host) {
+  REQ(ptr_host, "host_unregister: NULL");
+  cudaError_t e = cudaHostUnregister(ptr_host);
+  cudaGetLastError();
+  return (e == cudaSuccess || e == cudaErrorHostMemoryNotRegistered) ? 0 : cuda_fail(e, "cudaHostUnregister");
+}
+
 extern "C" int srl_memcpy_d2d(void* dst, const void* src, int64_t bytes, void* stream) {
   REQ(dst && src && bytes >= 0, "memcpy_d2d: bad argument");
   CU(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "memcpy_d2d");
@@ -646,8 +697,14 @@ extern "C" int srl_learner_debug_buffer(srl_learner_t* L, const char* name, void
       {"xs", L->buf.xs, NF * 441 * 64}, {"a1", L->buf.a1, NF * 400 * 32}, {"a2", L->buf.a2, NF * 81 * 64}, {"a3", L->buf.a3, NF * 49 * 64}, {"h", L->buf.h, NF * 512},
       {"logits", L->logits, NF * A}, {"baseline", L->baseline, NF}, {"dlogits", L->dlogits, NB * A}, {"dbaseline", L->dbaseline, NB},
       {"dh", L->buf.dh, NB * 512}, {"da3", L->buf.da3, NB * 81 * 64}, {"da2", L->buf.da2, NB * 100 * 64},
-      {"da1", L->buf.da1, NB * 441 * 64}, {"wpack", L->buf.wpack, WPack::TOTAL}};
+      {"da1", L->buf.da1, NB * 441 * 64}, {"wpack", L->buf.wpack, WPack::TOTAL},
+      {"a1_lo", L->buf.a1_lo, NF * 400 * 32}, {"a2_lo", L->buf.a2_lo, NF * 81 * 64}, {"a3_lo", L->buf.a3_lo, NF * 49 * 64},
+      {"dh_lo", L->buf.dh_lo, NB * 512}, {"da3_lo", L->buf.da3_lo, NB * 81 * 64}, {"da2_lo", L->buf.da2_lo, NB * 100 * 64},
+      {"da1_lo", L->buf.da1_lo, NB * 441 * 64}, {"wpack_lo", L->buf.wpack_lo, WPack::TOTAL}};
   for (auto& t : tab)
-    if (strcmp(t.n, name) == 0) { *ptr = t.p; *count = t.c; return 0; }
+    if (strcmp(t.n, name) == 0) {
+      if (!t.p) return fail(SRL_ESTATE, "debug_buffer: '%s' exists only in the fp32-accurate operand mode (precision = 1)", name);
+      *ptr = t.p; *count = t.c; return 0;
+    }
   return fail(SRL_EINVAL, "debug_buffer: unknown buffer '%s'", name);
 }

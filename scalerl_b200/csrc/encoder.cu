@@ -9,7 +9,7 @@
 namespace srl {
 
 // fp32 master parameters (PyTorch layouts) -> bf16 operand copies in the layouts the GEMMs consume.
-__global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __restrict__ out) {
+__global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __restrict__ out, bf16* __restrict__ out_lo) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < WPack::TOTAL; i += (int64_t)gridDim.x * blockDim.x) {
     float v;
     if (i < WPack::W2K) {                       // w1k[co][(kh2*2+kw2)*64 + c*16 + dy*4 + dx] = W1[co][c][4kh2+dy][4kw2+dx]
@@ -36,7 +36,9 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __
       const int kh = (cls >> 1) + 2 * (t >> 1), kw = (cls & 1) + 2 * (t & 1);
       v = p.w2[((co * 32 + c) << 4) + kh * 4 + kw];
     }
-    out[i] = __float2bfloat16_rn(v);
+    const bf16 hi = __float2bfloat16_rn(v);
+    out[i] = hi;
+    if (out_lo) out_lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));     // fp32-accurate mode: w = hi + lo to 16 significant bits
   }
 }
 
@@ -72,8 +74,8 @@ __global__ void __launch_bounds__(352) obs_s2d_kernel(const uint8_t* __restrict_
   }
 }
 
-cudaError_t launch_pack_weights(const ParamPtrs& p, bf16* wpack, cudaStream_t st) {
-  pack_weights_kernel<<<1184, 256, 0, st>>>(p, wpack);
+cudaError_t launch_pack_weights(const ParamPtrs& p, bf16* wpack, cudaStream_t st, bf16* wpack_lo) {
+  pack_weights_kernel<<<1184, 256, 0, st>>>(p, wpack, wpack_lo);
   return cudaGetLastError();
 }
 
@@ -154,6 +156,43 @@ cudaError_t build_tma_maps(const EncoderBuffers& b, int NF, int NB, TmaMaps* M, 
   return ok ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+cudaError_t build_tma_maps_lo(const EncoderBuffers& b, int NF, int NB, TmaMapsLo* M, const char** why) {
+  const uint64_t nf = NF, nb = NB;
+  bool ok = true;
+  auto mk = [&](CUtensorMap* m, const void* base, std::initializer_list<uint64_t> dims, std::initializer_list<uint64_t> strides,
+                std::initializer_list<uint32_t> box, const char* name) {
+    if (!ok) return;
+    uint64_t d[5], s[4]; uint32_t bx[5];
+    int i = 0; for (auto v : dims) d[i++] = v;
+    i = 0; for (auto v : strides) s[i++] = v;
+    i = 0; for (auto v : box) bx[i++] = v;
+    if (!make_map(m, base, 2, d, s, bx)) { ok = false; if (why) *why = name; }
+  };
+  auto rows = [&](CUtensorMap* m, const void* base, uint64_t nrows, uint32_t boxrows, const char* name) { mk(m, base, {64, nrows}, {64}, {64, boxrows}, name); };
+  rows(&M->a1p0_w, b.a1_lo, nf * 100, RConv2Fwd::WROWS, "a1p0_w_lo");
+  rows(&M->a1p1_w, b.a1_lo + (size_t)nf * 100 * 64, nf * 100, RConv2Fwd::WROWS, "a1p1_w_lo");
+  rows(&M->a2_w, b.a2_lo, nf * 81, RConv3Fwd::WROWS, "a2_w_lo");
+  rows(&M->da3g_w, b.da3_lo, nb * 81, RConv3Dgrad::WROWS, "da3g_w_lo");
+  rows(&M->da3g_b, b.da3_lo, nb * 81, 128, "da3g_b_lo");
+  rows(&M->da2g_w, b.da2_lo, nb * 100, RConv2Dgrad::WROWS, "da2g_w_lo");
+  rows(&M->da2g_b, b.da2_lo, nb * 100, 128, "da2g_b_lo");
+  rows(&M->da1g_b, b.da1_lo, nb * 441, 128, "da1g_b_lo");
+  mk(&M->a3m128, b.a3_lo, {3136, nf}, {3136}, {64, 128}, "a3m128_lo");
+  mk(&M->a3m64, b.a3_lo, {3136, nf}, {3136}, {64, 64}, "a3m64_lo");
+  mk(&M->dhm128, b.dh_lo, {512, nb}, {512}, {64, 128}, "dhm128_lo");
+  mk(&M->dhm64, b.dh_lo, {512, nb}, {512}, {64, 64}, "dhm64_lo");
+  const bf16* w = b.wpack_lo;
+  mk(&M->w1k, w + WPack::W1K, {256, 32}, {256}, {64, 32}, "w1k_lo");
+  mk(&M->w2k, w + WPack::W2K, {512, 64}, {512}, {64, 64}, "w2k_lo");
+  mk(&M->w3k, w + WPack::W3K, {576, 64}, {576}, {64, 64}, "w3k_lo");
+  mk(&M->wfk, w + WPack::WFK, {3136, 512}, {3136}, {64, 64}, "wfk_lo");
+  mk(&M->wfd, w + WPack::WFD, {512, 3136}, {512}, {64, 64}, "wfd_lo");
+  mk(&M->w3d, w + WPack::W3D, {576, 64}, {576}, {64, 64}, "w3d_lo");
+  mk(&M->w2d, w + WPack::W2D, {256, 128}, {256}, {64, 128}, "w2d_lo");
+  M->valid = ok;
+  return ok ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 static cudaError_t launch_s2d(const uint8_t* obs, int frames, bf16* xs, cudaStream_t st) {
   static const int ygroup = [] { const char* e = getenv("SRL_S2D_Y"); const int v = e ? atoi(e) : 21; return (v == 3 || v == 7) ? v : 21; }();
   if (ygroup == 3) SRL_TRY(launch_chain<PDL_SIMT>(obs_s2d_kernel<3>, dim3(frames * 7), dim3(352), 0, st, obs, xs));
@@ -197,20 +236,27 @@ __global__ void __launch_bounds__(256) conv_wgrad_finalize_kernel(float* __restr
 }
 
 cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, const TmaMaps& maps, int mode,
-                            cudaStream_t st, const Profiler& pf, cudaEvent_t wait_before_conv1) {
+                            cudaStream_t st, const Profiler& pf, cudaEvent_t wait_before_conv1, const TmaMapsLo* lo) {
   if (frames <= 0) return cudaSuccess;
-  if (mode != 0 || !maps.valid) return cudaErrorInvalidValue;
+  if ((mode != 0 && mode != 1) || !maps.valid) return cudaErrorInvalidValue;
+  const int sp = mode;                                    // 1: fp32-accurate split operands
+  TmaMapsLo dummy;                                        // bf16 mode: the low maps are never touched by the kernels
+  if (sp && (!lo || !lo->valid)) return cudaErrorInvalidValue;
+  const TmaMapsLo& L = sp ? *lo : dummy;
   pf.b(PS_S2D); SRL_TRY(launch_s2d(obs, frames, buf.xs, st)); pf.e(PS_S2D);
   if (wait_before_conv1) SRL_TRY(cudaStreamWaitEvent(st, wait_before_conv1, 0));
-  { RConv1Fwd::Params q{maps.xs_w, maps.w1k, p.b1, buf.a1, frames};
-    pf.b(PS_CONV1_FWD); SRL_TRY(res_fwd_launch<RConv1Fwd>(q, cdiv(frames * 441, 128), 2 * kPersistentCtas, st)); pf.e(PS_CONV1_FWD); }
-  { RConv2Fwd::Params q{maps.a1p0_w, maps.a1p1_w, maps.w2k, p.b2, buf.a2, frames};
-    pf.b(PS_CONV2_FWD); SRL_TRY(res_fwd_launch<RConv2Fwd>(q, cdiv(frames * 100, 128), kPersistentCtas, st)); pf.e(PS_CONV2_FWD); }
-  { RConv3Fwd::Params q{maps.a2_w, maps.w3k, p.b3, buf.a3, frames};
-    pf.b(PS_CONV3_FWD); SRL_TRY(res_fwd_launch<RConv3Fwd>(q, cdiv(frames * 81, 128), kPersistentCtas, st)); pf.e(PS_CONV3_FWD); }
-  { TFcFwd::Params q{maps.a3m128, maps.wfk, buf.hpart, frames};
+  { RConv1Fwd::Params q{maps.xs_w, maps.w1k, L.w1k, p.b1, buf.a1, buf.a1_lo, frames};
+    pf.b(PS_CONV1_FWD); SRL_TRY(res_fwd_launch<RConv1Fwd>(q, cdiv(frames * 441, 128), 2 * kPersistentCtas, st, sp)); pf.e(PS_CONV1_FWD); }
+  { RConv2Fwd::Params q{maps.a1p0_w, maps.a1p1_w, maps.w2k, L.a1p0_w, L.a1p1_w, L.w2k, p.b2, buf.a2, buf.a2_lo, frames};
+    pf.b(PS_CONV2_FWD); SRL_TRY(res_fwd_launch<RConv2Fwd>(q, cdiv(frames * 100, 128), kPersistentCtas, st, sp)); pf.e(PS_CONV2_FWD); }
+  { RConv3Fwd::Params q{maps.a2_w, maps.w3k, L.a2_w, L.w3k, p.b3, buf.a3, buf.a3_lo, frames};
+    pf.b(PS_CONV3_FWD); SRL_TRY(res_fwd_launch<RConv3Fwd>(q, cdiv(frames * 81, 128), kPersistentCtas, st, sp)); pf.e(PS_CONV3_FWD); }
+  { TFcFwd::Params q{maps.a3m128, maps.wfk, L.a3m128, L.wfk, buf.hpart, frames};
     static_assert(TFcFwd::SPLITS == FC_SPLITS, "split count");
-    pf.b(PS_FC_FWD); SRL_TRY(igemm_tma_launch<TFcFwd>(q, dim3(cdiv(frames, 128), 8 * FC_SPLITS), st)); pf.e(PS_FC_FWD); }
+    pf.b(PS_FC_FWD);
+    if (sp) SRL_TRY((igemm_tma_launch<TFcFwd, 1>(q, dim3(cdiv(frames, 128), 8 * FC_SPLITS), st)));
+    else SRL_TRY((igemm_tma_launch<TFcFwd, 0>(q, dim3(cdiv(frames, 128), 8 * FC_SPLITS), st)));
+    pf.e(PS_FC_FWD); }
   return cudaSuccess;
 }
 
@@ -220,10 +266,14 @@ int side_mode() {
 }
 
 cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
-                             cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase) {
+                             cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase, const TmaMapsLo* lo) {
   (void)obs;
   if (frames <= 0) return cudaSuccess;
-  if (mode != 0 || !maps.valid) return cudaErrorInvalidValue;
+  if ((mode != 0 && mode != 1) || !maps.valid) return cudaErrorInvalidValue;
+  const int sp = mode;
+  TmaMapsLo dummy;
+  if (sp && (!lo || !lo->valid)) return cudaErrorInvalidValue;
+  const TmaMapsLo& L = sp ? *lo : dummy;
   const bool do_fc = phase != 1, do_conv = phase != 0;
   // The wgrad GEMMs only feed the optimizer: each runs on its own side stream beside the dgrad chain
   // (dh -> da3 -> da2 -> da1) and beside each other.  With per-kernel profiling on everything stays on `st`.
@@ -233,26 +283,30 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
   Profiler p1 = pf, p2 = pf, p3 = pf; p1.st = s1; p2.st = s2; p3.st = s3;
   if (do_fc) {
     if (fork) { SRL_TRY(cudaEventRecord(ss.ev[0], st)); SRL_TRY(cudaStreamWaitEvent(s1, ss.ev[0], 0)); }
-    { TFcWgrad::Params q{maps.dhm64, maps.a3m64, g.wf, g.bf, frames};
-      p1.b(PS_FC_WGRAD); SRL_TRY(igemm_tma_launch<TFcWgrad>(q, dim3(1, 4 * 50), s1)); p1.e(PS_FC_WGRAD); }
-    { TFcDgrad::Params q{maps.dhm128, maps.wfd, buf.a3, buf.da3, frames};
-      pf.b(PS_FC_DGRAD); SRL_TRY(igemm_tma_launch<TFcDgrad>(q, dim3(cdiv(frames, 128), 49), st)); pf.e(PS_FC_DGRAD); }
+    { TFcWgrad::Params q{maps.dhm64, maps.a3m64, L.dhm64, L.a3m64, g.wf, g.bf, frames};
+      p1.b(PS_FC_WGRAD);
+      if (sp) SRL_TRY((igemm_tma_launch<TFcWgrad, 1>(q, dim3(1, 4 * 50), s1))); else SRL_TRY((igemm_tma_launch<TFcWgrad, 0>(q, dim3(1, 4 * 50), s1)));
+      p1.e(PS_FC_WGRAD); }
+    { TFcDgrad::Params q{maps.dhm128, maps.wfd, L.dhm128, L.wfd, buf.a3, buf.da3, buf.da3_lo, frames};
+      pf.b(PS_FC_DGRAD);
+      if (sp) SRL_TRY((igemm_tma_launch<TFcDgrad, 1>(q, dim3(cdiv(frames, 128), 49), st))); else SRL_TRY((igemm_tma_launch<TFcDgrad, 0>(q, dim3(cdiv(frames, 128), 49), st)));
+      pf.e(PS_FC_DGRAD); }
     if (fork) { SRL_TRY(cudaEventRecord(ss.ev[4], s1)); }
     if (fork && !do_conv) { SRL_TRY(cudaStreamWaitEvent(st, ss.ev[4], 0)); }
   }
   if (!do_conv) return cudaSuccess;
   if (fork) { SRL_TRY(cudaEventRecord(ss.ev[1], st)); SRL_TRY(cudaStreamWaitEvent(s2, ss.ev[1], 0)); }
-  { RConv3Wgrad::Params q{maps.a2_w, maps.da3g_b, buf.wgrad_ws + WS_W3, g.b3, frames * 81, 0};
-    p2.b(PS_CONV3_WGRAD); SRL_TRY(res_wgrad_launch<RConv3Wgrad>(q, 64, s2)); p2.e(PS_CONV3_WGRAD); }
-  { RConv3Dgrad::Params q{maps.da3g_w, maps.w3d, buf.a2, buf.da2, frames};
-    pf.b(PS_CONV3_DGRAD); SRL_TRY(res_fwd_launch<RConv3Dgrad>(q, cdiv(frames * 81, 128), kPersistentCtas, st)); pf.e(PS_CONV3_DGRAD); }
+  { RConv3Wgrad::Params q{maps.a2_w, maps.da3g_b, L.a2_w, L.da3g_b, buf.wgrad_ws + WS_W3, g.b3, frames * 81, 0};
+    p2.b(PS_CONV3_WGRAD); SRL_TRY(res_wgrad_launch<RConv3Wgrad>(q, 64, s2, sp)); p2.e(PS_CONV3_WGRAD); }
+  { RConv3Dgrad::Params q{maps.da3g_w, maps.w3d, L.da3g_w, L.w3d, buf.a2, buf.da2, buf.da2_lo, frames};
+    pf.b(PS_CONV3_DGRAD); SRL_TRY(res_fwd_launch<RConv3Dgrad>(q, cdiv(frames * 81, 128), kPersistentCtas, st, sp)); pf.e(PS_CONV3_DGRAD); }
   if (fork) { SRL_TRY(cudaEventRecord(ss.ev[2], st)); SRL_TRY(cudaStreamWaitEvent(s3, ss.ev[2], 0)); }
-  { RConv2Wgrad::Params q{maps.a1p0_w, maps.a1p1_w, maps.da2g_b, buf.wgrad_ws + WS_W2, g.b2, frames * 100, 0};
-    p3.b(PS_CONV2_WGRAD); SRL_TRY(res_wgrad_launch<RConv2Wgrad>(q, 64, s3)); p3.e(PS_CONV2_WGRAD); }
-  { RConv2Dgrad::Params q{maps.da2g_w, maps.w2d, buf.a1, buf.da1, frames, buf.NF};
-    pf.b(PS_CONV2_DGRAD); SRL_TRY(res_fwd_launch<RConv2Dgrad>(q, cdiv(frames * 100, 128), kPersistentCtas, st)); pf.e(PS_CONV2_DGRAD); }
-  { RConv1Wgrad::Params q{maps.xs_w, maps.da1g_b, buf.wgrad_ws + WS_W1, g.b1, frames * 441, 0};
-    pf.b(PS_CONV1_WGRAD); SRL_TRY(res_wgrad_launch<RConv1Wgrad>(q, kPersistentCtas, st)); pf.e(PS_CONV1_WGRAD); }
+  { RConv2Wgrad::Params q{maps.a1p0_w, maps.a1p1_w, maps.da2g_b, L.a1p0_w, L.a1p1_w, L.da2g_b, buf.wgrad_ws + WS_W2, g.b2, frames * 100, 0};
+    p3.b(PS_CONV2_WGRAD); SRL_TRY(res_wgrad_launch<RConv2Wgrad>(q, 64, s3, sp)); p3.e(PS_CONV2_WGRAD); }
+  { RConv2Dgrad::Params q{maps.da2g_w, maps.w2d, L.da2g_w, L.w2d, buf.a1, buf.da1, buf.da1_lo, frames, buf.NF};
+    pf.b(PS_CONV2_DGRAD); SRL_TRY(res_fwd_launch<RConv2Dgrad>(q, cdiv(frames * 100, 128), kPersistentCtas, st, sp)); pf.e(PS_CONV2_DGRAD); }
+  { RConv1Wgrad::Params q{maps.xs_w, maps.da1g_b, L.da1g_b, buf.wgrad_ws + WS_W1, g.b1, frames * 441, 0};
+    pf.b(PS_CONV1_WGRAD); SRL_TRY(res_wgrad_launch<RConv1Wgrad>(q, kPersistentCtas, st, sp)); pf.e(PS_CONV1_WGRAD); }
   if (fork) {      // join: fc wgrad (phase 2 only: phase 1 was joined by the caller of phase 0), conv3 wgrad, conv2 wgrad
     if (do_fc) { SRL_TRY(cudaStreamWaitEvent(st, ss.ev[4], 0)); }
     SRL_TRY(cudaEventRecord(ss.ev[3], s2)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[3], 0));

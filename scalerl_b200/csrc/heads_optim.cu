@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
 // dh[n][j] = (sum_a dlogits[n][a] Wp[a][j] + dV[n] Wb[j]) * (h[n][j] > 0)  -> bf16 (operand of the fc dgrad/wgrad GEMMs)
 __global__ void __launch_bounds__(128) head_bwd_dh_kernel(const float* __restrict__ dlogits, const float* __restrict__ dbaseline,
                                                           const float* __restrict__ h, const float* __restrict__ Wp,
-                                                          const float* __restrict__ Wb, int N, int A, __nv_bfloat16* __restrict__ dh) {
+                                                          const float* __restrict__ Wb, int N, int A, __nv_bfloat16* __restrict__ dh,
+                                                          __nv_bfloat16* __restrict__ dh_lo) {
   pdl_wait();      // launched with programmatic stream serialization: see common.cuh
   pdl_launch();
   const int n = blockIdx.x;
@@ -74,7 +75,9 @@ __global__ void __launch_bounds__(128) head_bwd_dh_kernel(const float* __restric
   float s = __ldg(dbaseline + n) * __ldg(Wb + j);
   for (int a = 0; a < A; ++a) s = fmaf(__ldg(dlogits + (size_t)n * A + a), __ldg(Wp + (size_t)a * CORE + j), s);
   if (!(__ldg(h + (size_t)n * 512 + j) > 0.f)) s = 0.f;
-  dh[(size_t)n * 512 + j] = __float2bfloat16_rn(s);
+  const __nv_bfloat16 hi = __float2bfloat16_rn(s);
+  dh[(size_t)n * 512 + j] = hi;
+  if (dh_lo) dh_lo[(size_t)n * 512 + j] = __float2bfloat16_rn(s - __bfloat162float(hi));     // fp32-accurate operand mode
 }
 
 // head weight/bias gradients: thread = one column j of `core` (j == CORE is the bias "ones" column),
@@ -354,9 +357,9 @@ cudaError_t launch_head_fwd(const float* hpart, int nsplit, const float* bfc, fl
 }
 cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const float* h, const float* reward, const int64_t* action,
                             const float* Wp, const float* Wb, int N, int A, __nv_bfloat16* dh, float* gWp, float* gbp, float* gWb,
-                            float* gbb, cudaStream_t st, cudaStream_t st_wgrad, bool do_dh) {
+                            float* gbb, cudaStream_t st, cudaStream_t st_wgrad, bool do_dh, __nv_bfloat16* dh_lo) {
   if (N <= 0) return cudaSuccess;
-  if (do_dh) SRL_TRY(launch_chain<PDL_SIMT>(head_bwd_dh_kernel, dim3(N, 4), dim3(128), 0, st, dlogits, dbaseline, h, Wp, Wb, N, A, dh));
+  if (do_dh) SRL_TRY(launch_chain<PDL_SIMT>(head_bwd_dh_kernel, dim3(N, 4), dim3(128), 0, st, dlogits, dbaseline, h, Wp, Wb, N, A, dh, dh_lo));
   const int CORE = 513 + A;
   // the head weight gradients only feed the optimizer: they may run on a side stream (st_wgrad) beside the fc backward
   head_wgrad_kernel<<<dim3((CORE + 1 + 127) / 128, (N + HEAD_SLAB - 1) / HEAD_SLAB), 128, 0, st_wgrad>>>(dlogits, dbaseline, h, reward, action, N, A,

@@ -32,28 +32,41 @@ constexpr int RES_MAX_TAPS = 10;
 //      128 + max shift - min shift), SHIFT_MIN, STAGES, Params{ in[NWIN] maps, w map, ... },
 //      tap_win(j), tap_shift(j) (relative to SHIFT_MIN, i.e. >= 0), num_tiles(p), epilogue16(p, tile, row, c0, v)
 // ------------------------------------------------------------------------------------------------------------------
-template <class P>
+//
+// SPLIT = 1 is the fp32-accurate operand mode (srl_config_t.precision = 1): every bf16 operand tensor has a second, "low"
+// tensor holding bf16(v - bf16(v)), and each product is issued as hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator
+// (the dropped lo*lo term is ~2^-18 relative; operands carry 16 significant bits, tighter than kind::tf32's 11).  Layouts,
+// descriptors and tensor maps are those of the bf16 mode -- the low tensors are simply a second copy of everything -- so
+// the mode exercises exactly the same data paths the fast mode uses.  It is for whole-step parity, not speed: 3x (2x where an
+// operand is exact: the u8 frames) the MMAs, twice the operand traffic, fewer pipeline stages.
+template <class P, int SPLIT>
 struct ResFwdCfg {
+  static constexpr int ALO = (SPLIT && P::A_LO) ? 1 : 0;          // the A operand has a low tensor (everything but the u8 frames)
+  static constexpr int STAGES = SPLIT ? P::SPLIT_STAGES : P::STAGES;
   static constexpr int WIN_BYTES = ((P::WROWS * 128 + 1023) / 1024) * 1024;
-  static constexpr int IN_BYTES = P::NWIN * WIN_BYTES;
-  static constexpr int W_BYTES = P::NT * P::BN * 128;
-  static constexpr int SMEM_BYTES = W_BYTES + P::STAGES * IN_BYTES + 1024 + 256;
+  static constexpr int IN_HI_BYTES = P::NWIN * WIN_BYTES;
+  static constexpr int IN_BYTES = IN_HI_BYTES * (1 + ALO);
+  static constexpr int W_HI_BYTES = P::NT * P::BN * 128;
+  static constexpr int W_BYTES = W_HI_BYTES * (1 + SPLIT);
+  static constexpr int SMEM_BYTES = W_BYTES + STAGES * IN_BYTES + 1024 + 256;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
   static constexpr int TMEM_COLS = 2 * P::BN <= 32 ? 32 : (2 * P::BN <= 64 ? 64 : (2 * P::BN <= 128 ? 128 : 256));
   static_assert(W_BYTES % 1024 == 0, "weight block alignment");
   static_assert(2 * P::BN <= 256, "two accumulators must fit");
 };
 
-template <class P>
+template <class P, int SPLIT>
 __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_constant__ typename P::Params p) {
-  using C = ResFwdCfg<P>;
+  using C = ResFwdCfg<P, SPLIT>;
+  constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
   uint8_t* sIn = smem + C::W_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + P::STAGES * C::IN_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + STAGES * C::IN_BYTES);
   uint64_t* in_full = bars;
-  uint64_t* in_empty = bars + P::STAGES;
-  uint64_t* acc_full = bars + 2 * P::STAGES;
+  uint64_t* in_empty = bars + STAGES;
+  uint64_t* acc_full = bars + 2 * STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* w_full = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
@@ -62,7 +75,7 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
 
   if (warp == 4) {
     if ((tid & 31) == 0) {
-      for (int s = 0; s < P::STAGES; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
       mbar_init(w_full, 1);
       mbar_fence_init();
@@ -83,14 +96,17 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
       // kernel's tail; the activations are only touched after pdl_wait()
       mbar_arrive_expect_tx(w_full, C::W_BYTES);
       for (int j = 0; j < P::NT; ++j) tma_load_2d(sW + j * P::BN * 128, &p.w, w_full, j * 64, 0);
+      if constexpr (SPLIT)
+        for (int j = 0; j < P::NT; ++j) tma_load_2d(sW + C::W_HI_BYTES + j * P::BN * 128, &p.w_lo, w_full, j * 64, 0);
       pdl_wait();
       pdl_launch();
       int it = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int s = it % P::STAGES;
-        mbar_wait(&in_empty[s], ((it / P::STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&in_full[s], P::NWIN * P::WROWS * 128);
-        P::load_windows(p, t, sIn + s * C::IN_BYTES, C::WIN_BYTES, &in_full[s]);
+        const int s = it % STAGES;
+        mbar_wait(&in_empty[s], ((it / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&in_full[s], P::NWIN * P::WROWS * 128 * (1 + C::ALO));
+        P::load_windows(p, t, sIn + s * C::IN_BYTES, C::WIN_BYTES, &in_full[s], false);
+        if constexpr (C::ALO) P::load_windows(p, t, sIn + s * C::IN_BYTES + C::IN_HI_BYTES, C::WIN_BYTES, &in_full[s], true);
       }
     }
   } else if (warp == 5) {
@@ -99,9 +115,9 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
       mbar_wait(w_full, 0);
       int it = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int s = it % P::STAGES, b = it & 1;
+        const int s = it % STAGES, b = it & 1;
         mbar_wait(&acc_empty[b], ((it >> 1) & 1) ^ 1);       // epilogue drained this accumulator (two tiles ago)
-        mbar_wait(&in_full[s], (it / P::STAGES) & 1);
+        mbar_wait(&in_full[s], (it / STAGES) & 1);
         tc_fence_after();
         const uint32_t in0 = smem_u32(sIn + s * C::IN_BYTES), w0 = smem_u32(sW);
         const uint32_t acc = tmem_base + b * P::BN;
@@ -110,8 +126,13 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
           const uint32_t a0 = in0 + P::tap_win(j) * C::WIN_BYTES + P::tap_shift(j) * 128;
           const uint32_t b0 = w0 + j * P::BN * 128;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
+          for (int k = 0; k < 4; ++k) {
             umma_bf16(acc, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc, (j | k) != 0);
+            if constexpr (SPLIT)          // hi * lo(weights)
+              umma_bf16(acc, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + C::W_HI_BYTES + k * 32, 16, 1024), idesc, 1);
+            if constexpr (C::ALO)         // lo(activations) * hi
+              umma_bf16(acc, make_smem_desc(a0 + C::IN_HI_BYTES + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc, 1);
+          }
         }
         umma_commit(&in_empty[s]);
         umma_commit(&acc_full[b]);
@@ -137,7 +158,7 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        P::epilogue16(p, t, tid, c * 16, v, pre[c]);
+        P::template epilogue16<SPLIT>(p, t, tid, c * 16, v, pre[c]);
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[b]);
@@ -150,14 +171,18 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
   }
 }
 
-template <class P>
-cudaError_t res_fwd_launch(const typename P::Params& p, int ntiles, int max_ctas, cudaStream_t stream) {
-  using C = ResFwdCfg<P>;
+template <class P, int SPLIT>
+cudaError_t res_fwd_launch_t(const typename P::Params& p, int ntiles, int max_ctas, cudaStream_t stream) {
+  using C = ResFwdCfg<P, SPLIT>;
   if (ntiles <= 0) return cudaSuccess;
   static PerDeviceOnce once;
-  { cudaError_t e = ensure_max_dynamic_smem(once, res_fwd_kernel<P>, C::SMEM_BYTES); if (e != cudaSuccess) return e; }
+  { cudaError_t e = ensure_max_dynamic_smem(once, res_fwd_kernel<P, SPLIT>, C::SMEM_BYTES); if (e != cudaSuccess) return e; }
   const int grid = ntiles < max_ctas ? ntiles : max_ctas;
-  return launch_chain<PDL_RESFWD>(res_fwd_kernel<P>, dim3(grid), dim3(RES_THREADS), C::SMEM_BYTES, stream, p);
+  return launch_chain<PDL_RESFWD>(res_fwd_kernel<P, SPLIT>, dim3(grid), dim3(RES_THREADS), C::SMEM_BYTES, stream, p);
+}
+template <class P>
+cudaError_t res_fwd_launch(const typename P::Params& p, int ntiles, int max_ctas, cudaStream_t stream, int split = 0) {
+  return split ? res_fwd_launch_t<P, 1>(p, ntiles, max_ctas, stream) : res_fwd_launch_t<P, 0>(p, ntiles, max_ctas, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -166,28 +191,36 @@ cudaError_t res_fwd_launch(const typename P::Params& p, int ntiles, int max_ctas
 //      acc_win(a), acc_shift0(a), acc_shift1(a) (block 1 = -1 -> the all-ones block: bias gradient),
 //      Params{ in[NWIN] maps, dy map, P (positions), chunks_per_cta }, epilogue16(p, acc, row, c0, v)
 // ------------------------------------------------------------------------------------------------------------------
-template <class P>
+template <class P, int SPLIT>
 struct ResWgradCfg {
+  static constexpr int ALO = (SPLIT && P::A_LO) ? 1 : 0;          // the input window has a low tensor (not conv1: exact u8 frames)
+  static constexpr int STAGES = SPLIT ? P::SPLIT_STAGES : P::STAGES;
+  static constexpr bool BIAS_SMEM = P::SMEM_BIAS || SPLIT;        // split mode: bias gradient always from the staged dY tiles
   static constexpr int WIN_BYTES = ((P::WROWS * 128 + 1023) / 1024) * 1024;
   static constexpr int DY_BYTES = 128 * 128;
-  static constexpr int STAGE_BYTES = P::NWIN * WIN_BYTES + DY_BYTES;
+  static constexpr int X_HI_BYTES = P::NWIN * WIN_BYTES;
+  static constexpr int X_BYTES = X_HI_BYTES * (1 + ALO);
+  static constexpr int STAGE_BYTES = X_BYTES + DY_BYTES * (1 + SPLIT);     // [windows hi][windows lo][dY hi][dY lo]
   static constexpr int ONES_BYTES = 128 * 128;
-  static constexpr int SMEM_BYTES = ONES_BYTES + P::STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = ONES_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
   static constexpr int TMEM_COLS = P::NACC * 64 <= 64 ? 64 : (P::NACC * 64 <= 128 ? 128 : (P::NACC * 64 <= 256 ? 256 : 512));
   static_assert(P::NACC * 64 <= 512, "accumulators must fit TMEM");
 };
 
-template <class P>
+template <class P, int SPLIT>
 __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_constant__ typename P::Params p) {
-  using C = ResWgradCfg<P>;
+  using C = ResWgradCfg<P, SPLIT>;
+  constexpr int STAGES = C::STAGES;
+  constexpr bool BIAS_SMEM = C::BIAS_SMEM;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sSt = smem;
-  uint8_t* sOnes = smem + P::STAGES * C::STAGE_BYTES;     // after the stages: block-1 - block-0 distances stay positive
+  uint8_t* sOnes = smem + STAGES * C::STAGE_BYTES;     // after the stages: block-1 - block-0 distances stay positive
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + C::ONES_BYTES);
   uint64_t* full = bars;
-  uint64_t* empty = bars + P::STAGES;
-  uint64_t* done = bars + 2 * P::STAGES;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* done = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int nchunks_total = (p.P + 127) >> 7;
@@ -195,7 +228,7 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
   const int c_end = min(nchunks_total, c_begin + p.chunks_per_cta);
   const int nch = max(0, c_end - c_begin);
 
-  if constexpr (!P::SMEM_BIAS) {  // all-ones block (bf16 1.0) for the bias-gradient accumulator
+  if constexpr (!BIAS_SMEM) {  // all-ones block (bf16 1.0) for the bias-gradient accumulator
     uint4* q = reinterpret_cast<uint4*>(sOnes);
     for (int i = tid; i < C::ONES_BYTES / 16; i += RES_THREADS) q[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
@@ -204,7 +237,7 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
     if ((tid & 31) == 0) {
       // SMEM_BIAS: the four epilogue warps also read every dy tile (bias-gradient column sums), so a stage is free
       // only after the MMA commit AND their four arrivals
-      for (int s = 0; s < P::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], P::SMEM_BIAS ? 5 : 1); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], BIAS_SMEM ? 5 : 1); }
       mbar_init(done, 1);
       mbar_fence_init();
       P::prefetch(p);
@@ -222,12 +255,14 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
   if (warp == 4) {
     if ((tid & 31) == 0) {
       for (int i = 0; i < nch; ++i) {
-        const int s = i % P::STAGES;
-        mbar_wait(&empty[s], ((i / P::STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[s], P::NWIN * P::WROWS * 128 + C::DY_BYTES);
+        const int s = i % STAGES;
+        mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], P::NWIN * P::WROWS * 128 * (1 + C::ALO) + C::DY_BYTES * (1 + SPLIT));
         uint8_t* st = sSt + s * C::STAGE_BYTES;
-        P::load_windows(p, c_begin + i, st, C::WIN_BYTES, &full[s]);
-        tma_load_2d(st + P::NWIN * C::WIN_BYTES, &p.dy, &full[s], 0, (c_begin + i) * 128);
+        P::load_windows(p, c_begin + i, st, C::WIN_BYTES, &full[s], false);
+        if constexpr (C::ALO) P::load_windows(p, c_begin + i, st + C::X_HI_BYTES, C::WIN_BYTES, &full[s], true);
+        tma_load_2d(st + C::X_BYTES, &p.dy, &full[s], 0, (c_begin + i) * 128);
+        if constexpr (SPLIT) tma_load_2d(st + C::X_BYTES + C::DY_BYTES, &p.dy_lo, &full[s], 0, (c_begin + i) * 128);
       }
     }
   } else if (warp == 5) {
@@ -235,27 +270,37 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
       constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
       const uint32_t ones = smem_u32(sOnes);
       for (int i = 0; i < nch; ++i) {
-        const int s = i % P::STAGES;
-        mbar_wait(&full[s], (i / P::STAGES) & 1);
+        const int s = i % STAGES;
+        mbar_wait(&full[s], (i / STAGES) & 1);
         tc_fence_after();
         const uint32_t st = smem_u32(sSt + s * C::STAGE_BYTES);
-        const uint32_t dy0 = st + P::NWIN * C::WIN_BYTES;
+        const uint32_t dy0 = st + C::X_BYTES;
 #pragma unroll
         for (int a = 0; a < P::NACC; ++a) {
           const uint32_t blk0 = st + P::acc_win(a) * C::WIN_BYTES + P::acc_shift0(a) * 128;
-          const uint32_t blk1 = P::acc_shift1(a) >= 0 ? st + P::acc_win1(a) * C::WIN_BYTES + P::acc_shift1(a) * 128 : ones;
+          // a half-empty accumulator (conv3's tenth "tap"): the all-ones block (bias gradient) in the bf16 mode; in the split
+          // mode the bias comes from the staged dY tiles and the spare half just re-reads the window one row further (ignored)
+          const uint32_t blk1 = P::acc_shift1(a) >= 0 ? st + P::acc_win1(a) * C::WIN_BYTES + P::acc_shift1(a) * 128
+                                                      : (BIAS_SMEM ? blk0 + 128 : ones);
           const uint32_t lbo = blk1 - blk0;      // byte distance between the two 64-row M blocks (any multiple of 16)
 #pragma unroll
-          for (int k = 0; k < 8; ++k)            // 128 positions = 8 x (K = 16)
+          for (int k = 0; k < 8; ++k) {          // 128 positions = 8 x (K = 16)
             umma_bf16(tmem_base + a * 64, make_smem_desc(blk0 + k * 2048, lbo, 1024), make_smem_desc(dy0 + k * 2048, 8192, 1024), idesc,
                       (i | k) != 0);
+            if constexpr (SPLIT)         // hi(x) * lo(dy)
+              umma_bf16(tmem_base + a * 64, make_smem_desc(blk0 + k * 2048, lbo, 1024), make_smem_desc(dy0 + C::DY_BYTES + k * 2048, 8192, 1024),
+                        idesc, 1);
+            if constexpr (C::ALO)        // lo(x) * hi(dy)
+              umma_bf16(tmem_base + a * 64, make_smem_desc(blk0 + C::X_HI_BYTES + k * 2048, lbo, 1024), make_smem_desc(dy0 + k * 2048, 8192, 1024),
+                        idesc, 1);
+          }
         }
         umma_commit(&empty[s]);
       }
       umma_commit(done);
     }
   } else {
-    if constexpr (P::SMEM_BIAS) {
+    if constexpr (BIAS_SMEM) {
       // bias gradient = column sums of dy, taken from the staged dy tiles while the MMAs run (no all-ones accumulator).
       // dy tile: 128 position rows of 128 B (64 channels), SWIZZLE_128B.  thread -> 16-byte channel group g, rows q + 16k.
       const int g = tid & 7, q = tid >> 3;
@@ -269,16 +314,19 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
       // and the arrive (release) is ordered after the store.
       const uint32_t dep_slot = smem_u32(sOnes) + 4096 + tid * 4;
       for (int i = 0; i < nch; ++i) {
-        const int s = i % P::STAGES;
-        mbar_wait(&full[s], (i / P::STAGES) & 1);
-        const uint32_t dyt = smem_u32(sSt + s * C::STAGE_BYTES + P::NWIN * C::WIN_BYTES);
+        const int s = i % STAGES;
+        mbar_wait(&full[s], (i / STAGES) & 1);
+        const uint32_t dyt = smem_u32(sSt + s * C::STAGE_BYTES + C::X_BYTES);
         float dep = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint4 v = lds128(dyt + swz128(q + 16 * k, g));
-          bs[0] += bf16_lo(v.x); bs[1] += bf16_hi(v.x); bs[2] += bf16_lo(v.y); bs[3] += bf16_hi(v.y);
-          bs[4] += bf16_lo(v.z); bs[5] += bf16_hi(v.z); bs[6] += bf16_lo(v.w); bs[7] += bf16_hi(v.w);
-          dep += __uint_as_float(v.x ^ v.y ^ v.z ^ v.w);
+        for (int part = 0; part <= SPLIT; ++part) {        // split mode: the low tile's column sums are added too
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint4 v = lds128(dyt + part * C::DY_BYTES + swz128(q + 16 * k, g));
+            bs[0] += bf16_lo(v.x); bs[1] += bf16_hi(v.x); bs[2] += bf16_lo(v.y); bs[3] += bf16_hi(v.y);
+            bs[4] += bf16_lo(v.z); bs[5] += bf16_hi(v.z); bs[6] += bf16_lo(v.w); bs[7] += bf16_hi(v.w);
+            dep += __uint_as_float(v.x ^ v.y ^ v.z ^ v.w);
+          }
         }
         sts_volatile_f32(dep_slot, dep);
         __syncwarp();
@@ -311,7 +359,7 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          P::epilogue16(p, a, tid, c0, v);
+          P::template epilogue16<SPLIT>(p, a, tid, c0, v);
         }
       }
       tc_fence_before();
@@ -324,16 +372,20 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
   }
 }
 
-template <class P>
-cudaError_t res_wgrad_launch(typename P::Params p, int target_ctas, cudaStream_t stream) {
-  using C = ResWgradCfg<P>;
+template <class P, int SPLIT>
+cudaError_t res_wgrad_launch_t(typename P::Params p, int target_ctas, cudaStream_t stream) {
+  using C = ResWgradCfg<P, SPLIT>;
   const int nchunks = (p.P + 127) >> 7;
   if (nchunks <= 0) return cudaSuccess;
   static PerDeviceOnce once;
-  { cudaError_t e = ensure_max_dynamic_smem(once, res_wgrad_kernel<P>, C::SMEM_BYTES); if (e != cudaSuccess) return e; }
+  { cudaError_t e = ensure_max_dynamic_smem(once, res_wgrad_kernel<P, SPLIT>, C::SMEM_BYTES); if (e != cudaSuccess) return e; }
   p.chunks_per_cta = (nchunks + target_ctas - 1) / target_ctas;
   const int grid = (nchunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
-  return launch_chain<PDL_RESWGRAD>(res_wgrad_kernel<P>, dim3(grid), dim3(RES_THREADS), C::SMEM_BYTES, stream, p);
+  return launch_chain<PDL_RESWGRAD>(res_wgrad_kernel<P, SPLIT>, dim3(grid), dim3(RES_THREADS), C::SMEM_BYTES, stream, p);
+}
+template <class P>
+cudaError_t res_wgrad_launch(const typename P::Params& p, int target_ctas, cudaStream_t stream, int split = 0) {
+  return split ? res_wgrad_launch_t<P, 1>(p, target_ctas, stream) : res_wgrad_launch_t<P, 0>(p, target_ctas, stream);
 }
 
 }  // namespace srl

@@ -49,14 +49,19 @@ SRL_DEVINL void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int 
 
 constexpr int IGT_THREADS = 192;
 
-template <class P>
+// SPLIT = 1: fp32-accurate operand mode (see igemm_res.cuh): a stage holds [A hi][B hi][A lo][B lo]; the problem supplies
+// issue_split(p, tm, ty, kb, stage_base, half_bytes, bar) (one expect_tx + the loads of all four tiles) and
+// epilogue16<SPLIT>.  Problems that never run split (the LSTM GEMMs) only need the SPLIT = 0 interface.
+template <class P, int SPLIT = 0>
 struct TmaCfg {
   static constexpr int KROWS = P::A_MN ? P::KROWS : 64;
   static constexpr int A_BYTES = P::A_MN ? 2 * KROWS * 128 : 128 * 128;
   static constexpr int B_BLOCKS = (P::BN + 63) / 64;
   static constexpr int B_BYTES = P::B_MN ? B_BLOCKS * KROWS * 128 : P::BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int HALF_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = HALF_BYTES * (1 + SPLIT);
   static constexpr int SMEM_BYTES = P::STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
   static constexpr int TMEM_COLS = P::BN <= 32 ? 32 : (P::BN <= 64 ? 64 : (P::BN <= 128 ? 128 : 256));
   static constexpr int MMAS = P::A_MN ? KROWS / 16 : 4;
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must keep 1024 B alignment (SWIZZLE_128B atoms)");
@@ -64,9 +69,18 @@ struct TmaCfg {
   static_assert(KROWS % 16 == 0, "contraction rows per stage must be a multiple of UMMA K = 16");
 };
 
-template <class P>
+template <class P, int SPLIT>
+SRL_DEVINL void igt_epilogue(const typename P::Params& p, int tm, int ty, int row, int c0, float (&v)[16]) {
+  if constexpr (SPLIT) P::template epilogue16<1>(p, tm, ty, row, c0, v); else P::epilogue16(p, tm, ty, row, c0, v);
+}
+template <class P, int SPLIT>
+SRL_DEVINL void igt_epilogue(const typename P::Params& p, int tm, int ty, int row, int c0, float (&v)[16], const uint4 (&pre)[2]) {
+  if constexpr (SPLIT) P::template epilogue16<1>(p, tm, ty, row, c0, v, pre); else P::epilogue16(p, tm, ty, row, c0, v, pre);
+}
+
+template <class P, int SPLIT = 0>
 __global__ void __launch_bounds__(IGT_THREADS) igemm_tma_kernel(const __grid_constant__ typename P::Params p) {
-  using C = TmaCfg<P>;
+  using C = TmaCfg<P, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::STAGES * C::STAGE_BYTES);
@@ -110,7 +124,8 @@ __global__ void __launch_bounds__(IGT_THREADS) igemm_tma_kernel(const __grid_con
         const int s = kb % P::STAGES;
         mbar_wait(&empty[s], ((kb / P::STAGES) & 1) ^ 1);
         uint8_t* sA = smem + s * C::STAGE_BYTES;
-        P::issue(p, tm, ty, kb, sA, sA + C::A_BYTES, &full[s]);
+        if constexpr (SPLIT) P::issue_split(p, tm, ty, kb, sA, C::A_BYTES, C::HALF_BYTES, &full[s]);
+        else P::issue(p, tm, ty, kb, sA, sA + C::A_BYTES, &full[s]);
       }
     }
   } else if (warp == 5) {
@@ -127,6 +142,13 @@ __global__ void __launch_bounds__(IGT_THREADS) igemm_tma_kernel(const __grid_con
           const uint64_t ad = P::A_MN ? make_smem_desc(a0 + k * 2048, C::KROWS * 128, 1024) : make_smem_desc(a0 + k * 32, 16, 1024);
           const uint64_t bd = P::B_MN ? make_smem_desc(b0 + k * 2048, C::KROWS * 128, 1024) : make_smem_desc(b0 + k * 32, 16, 1024);
           umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0);
+          if constexpr (SPLIT) {        // hi * lo, lo * hi (the low tiles sit HALF_BYTES further into the stage)
+            const uint32_t a1 = a0 + C::HALF_BYTES, b1 = b0 + C::HALF_BYTES;
+            const uint64_t adl = P::A_MN ? make_smem_desc(a1 + k * 2048, C::KROWS * 128, 1024) : make_smem_desc(a1 + k * 32, 16, 1024);
+            const uint64_t bdl = P::B_MN ? make_smem_desc(b1 + k * 2048, C::KROWS * 128, 1024) : make_smem_desc(b1 + k * 32, 16, 1024);
+            umma_bf16(tmem_base, ad, bdl, idesc, 1);
+            umma_bf16(tmem_base, adl, bd, idesc, 1);
+          }
         }
         umma_commit(&empty[s]);
       }
@@ -149,7 +171,7 @@ __global__ void __launch_bounds__(IGT_THREADS) igemm_tma_kernel(const __grid_con
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        P::epilogue16(p, tm, ty, row, c * 16, v, pre[c]);
+        igt_epilogue<P, SPLIT>(p, tm, ty, row, c * 16, v, pre[c]);
       }
     } else {
     if (nkb > 0) {
@@ -169,7 +191,7 @@ __global__ void __launch_bounds__(IGT_THREADS) igemm_tma_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
       }
-      P::epilogue16(p, tm, ty, row, c0, v);
+      igt_epilogue<P, SPLIT>(p, tm, ty, row, c0, v);
     }
     }
     tc_fence_before();
@@ -181,13 +203,13 @@ __global__ void __launch_bounds__(IGT_THREADS) igemm_tma_kernel(const __grid_con
   }
 }
 
-template <class P>
+template <class P, int SPLIT = 0>
 cudaError_t igemm_tma_launch(const typename P::Params& p, dim3 grid, cudaStream_t stream) {
-  using C = TmaCfg<P>;
+  using C = TmaCfg<P, SPLIT>;
   if (grid.x == 0 || grid.y == 0) return cudaSuccess;
   static PerDeviceOnce once;      // set once per device (outside any stream capture: the first step always runs eagerly)
-  { cudaError_t e = ensure_max_dynamic_smem(once, igemm_tma_kernel<P>, C::SMEM_BYTES); if (e != cudaSuccess) return e; }
-  return launch_chain<PDL_IGEMM>(igemm_tma_kernel<P>, grid, dim3(IGT_THREADS), C::SMEM_BYTES, stream, p);
+  { cudaError_t e = ensure_max_dynamic_smem(once, igemm_tma_kernel<P, SPLIT>, C::SMEM_BYTES); if (e != cudaSuccess) return e; }
+  return launch_chain<PDL_IGEMM>(igemm_tma_kernel<P, SPLIT>, grid, dim3(IGT_THREADS), C::SMEM_BYTES, stream, p);
 }
 
 }  // namespace srl

@@ -84,7 +84,8 @@ cudaError_t launch_column_step(const float* hpart, int nsplit, const float* bfc,
                                const uint8_t* done, const float* bl, const float* Wp, const float* bp, const float* Wb, const float* bb,
                                int T, int B, int A, float discounting, int clip_reward, float clip_rho, float clip_pg,
                                float baseline_cost, float entropy_cost, float* logits, float* baseline, float* vs, float* pg,
-                               float* dlogits, float* dbaseline, __nv_bfloat16* dh, float* losses, float* scratch, cudaStream_t st);
+                               float* dlogits, float* dbaseline, __nv_bfloat16* dh, float* losses, float* scratch, cudaStream_t st,
+                               __nv_bfloat16* dh_lo = nullptr);
 cudaError_t launch_impala_tail(const float* bl, const float* tl, const float* baseline, const int64_t* action, const float* reward,
                                const uint8_t* done, int T, int B, int A, float discounting, int clip_reward, float clip_rho,
                                float clip_pg, float baseline_cost, float entropy_cost, float* vs, float* pg, float* dlogits,
@@ -97,7 +98,7 @@ cudaError_t launch_head_fwd(const float* hpart, int nsplit, const float* bfc, fl
                             float* baseline, cudaStream_t st);
 cudaError_t launch_head_bwd(const float* dlogits, const float* dbaseline, const float* h, const float* reward, const int64_t* action,
                             const float* Wp, const float* Wb, int N, int A, __nv_bfloat16* dh, float* gWp, float* gbp, float* gWb,
-                            float* gbb, cudaStream_t st, cudaStream_t st_wgrad, bool do_dh = true);
+                            float* gbb, cudaStream_t st, cudaStream_t st_wgrad, bool do_dh = true, __nv_bfloat16* dh_lo = nullptr);
 cudaError_t launch_core_build(const float* hpart, int nsplit, const float* bfc, const float* reward, const int64_t* action, int N, int A, float* h,
                               float* core, cudaStream_t st);
 cudaError_t launch_head_dense_fwd(const float* X, const float* Wp, const float* bp, const float* Wb, const float* bb, int N, int A, float* logits,
@@ -146,6 +147,10 @@ struct EncoderBuffers {   // row layouts: see res_problems.cuh
   __nv_bfloat16* wpack;
   float* wgrad_ws;                      // conv weight-gradient accumulation workspace (res_problems.cuh: WS_TOTAL floats)
   int NF;                               // frames the forward buffers were sized for (plane stride of a1)
+  // fp32-accurate operand mode (srl_config_t.precision = 1): the "low" twin bf16(v - bf16(v)) of every operand tensor above
+  // (same layouts; nullptr in the bf16 mode).  xs has none: u8 frames are exact in bf16.
+  __nv_bfloat16 *a1_lo = nullptr, *a2_lo = nullptr, *a3_lo = nullptr, *dh_lo = nullptr, *da3_lo = nullptr, *da2_lo = nullptr, *da1_lo = nullptr,
+                *wpack_lo = nullptr;
 };
 // tensor maps of the TMA kernels (built once per learner context: every operand buffer is fixed).
 // Activations are [rows][64] bf16; "w" = window box (128 + max tap shift rows), "b" = 128-row box.
@@ -155,19 +160,27 @@ struct TmaMaps {
   alignas(64) CUtensorMap w1k, w2k, w3k, wfk, wfd, w3d, w2d;
   bool valid = false;
 };
+struct TmaMapsLo {      // the same maps over the low tensors (built only in the fp32-accurate mode)
+  alignas(64) CUtensorMap a1p0_w, a1p1_w, a2_w, da3g_w, da3g_b, da2g_w, da2g_b, da1g_b, a3m128, a3m64, dhm128, dhm64;
+  alignas(64) CUtensorMap w1k, w2k, w3k, wfk, wfd, w3d, w2d;
+  bool valid = false;
+};
 // bf16 tensor map, dims innermost-first, strides in ELEMENTS for dims 1..rank-1, SWIZZLE_128B, zero OOB fill (encoder.cu)
 bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box);
 // returns cudaSuccess or an error; `why` gets a message on failure
 cudaError_t build_tma_maps(const EncoderBuffers& buf, int NF, int NB, TmaMaps* maps, const char** why);
-cudaError_t launch_pack_weights(const ParamPtrs& p, __nv_bfloat16* wpack, cudaStream_t st);
+cudaError_t build_tma_maps_lo(const EncoderBuffers& buf, int NF, int NB, TmaMapsLo* maps, const char** why);
+// wpack_lo != nullptr: also the low copies bf16(w - bf16(w)) in the same layouts
+cudaError_t launch_pack_weights(const ParamPtrs& p, __nv_bfloat16* wpack, cudaStream_t st, __nv_bfloat16* wpack_lo = nullptr);
 // wait_before_conv1: optional event (weight re-pack running on the side stream) that conv1 must wait for
+// mode: 0 = bf16 operands, 1 = fp32-accurate split operands (maps_lo must be valid)
 cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, const TmaMaps& maps, int mode,
-                            cudaStream_t st, const Profiler& pf, cudaEvent_t wait_before_conv1);
+                            cudaStream_t st, const Profiler& pf, cudaEvent_t wait_before_conv1, const TmaMapsLo* maps_lo = nullptr);
 // backward for the first `frames` frames given buf.dh; accumulates into the (pre-zeroed) gradient tensors in `g`
 // phase: 0 = fc layer only (fc.weight / fc.bias gradients complete and joined to `st` on return: 95 % of the gradient
 //        bytes, ready for an early all-reduce), 1 = conv layers only, 2 = both
 cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
-                             cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase);
+                             cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase, const TmaMapsLo* maps_lo = nullptr);
 cudaError_t test_shift(const void* A, const void* B, float* D, int shift, int mn_major, int bo_mode, cudaStream_t st);
 cudaError_t test_poison_smem(cudaStream_t st);
 cudaError_t test_pdl(int* flag, int* out, int nblk, unsigned delay_ns, cudaStream_t st);

@@ -14,9 +14,19 @@ struct TFcFwd {
   static constexpr int BN = 64, STAGES = 4, SPLITS = 4;
   static constexpr bool A_MN = false, B_MN = false, ZERO_INIT = false;
   static constexpr int KROWS = 64;
-  struct Params { SRL_TMAP a3m; SRL_TMAP w; float* out; int M; };
+  struct Params { SRL_TMAP a3m; SRL_TMAP w; SRL_TMAP a3m_lo; SRL_TMAP w_lo; float* out; int M; };
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.a3m); tma_prefetch_desc(&p.w); }
   SRL_DEVINL static int kb_begin(int split) { return (49 * split) / SPLITS; }
+  SRL_DEVINL static void issue_split(const Params& p, int tm, int ty, int kb, uint8_t* st, int a_bytes, int half, uint64_t* bar) {
+    const int k = (kb_begin(ty % SPLITS) + kb) * 64;
+    mbar_arrive_expect_tx(bar, 2 * (128 * 128 + 64 * 128));
+    tma_load_2d(st, &p.a3m, bar, k, tm * 128);
+    tma_load_2d(st + a_bytes, &p.w, bar, k, (ty / SPLITS) * 64);
+    tma_load_2d(st + half, &p.a3m_lo, bar, k, tm * 128);
+    tma_load_2d(st + half + a_bytes, &p.w_lo, bar, k, (ty / SPLITS) * 64);
+  }
+  template <int SPLIT>
+  SRL_DEVINL static void epilogue16(const Params& p, int tm, int ty, int row, int c0, float (&v)[16]) { epilogue16(p, tm, ty, row, c0, v); }
   SRL_DEVINL static int num_kblocks(const Params&, int, int ty) { const int sp = ty % SPLITS; return kb_begin(sp + 1) - kb_begin(sp); }
   SRL_DEVINL static void issue(const Params& p, int tm, int ty, int kb, uint8_t* sA, uint8_t* sB, uint64_t* bar) {
     const int k = (kb_begin(ty % SPLITS) + kb) * 64;
@@ -38,9 +48,16 @@ struct TFcDgrad {
   static constexpr int BN = 64, STAGES = 4;
   static constexpr bool A_MN = false, B_MN = false, ZERO_INIT = false;
   static constexpr int KROWS = 64;
-  struct Params { SRL_TMAP dhm; SRL_TMAP w; const bf16* a3; bf16* da3; int M; };
+  struct Params { SRL_TMAP dhm; SRL_TMAP w; SRL_TMAP dhm_lo; SRL_TMAP w_lo; const bf16* a3; bf16* da3; bf16* da3_lo; int M; };
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.dhm); tma_prefetch_desc(&p.w); }
   SRL_DEVINL static int num_kblocks(const Params&, int, int) { return 8; }
+  SRL_DEVINL static void issue_split(const Params& p, int tm, int ty, int kb, uint8_t* st, int a_bytes, int half, uint64_t* bar) {
+    mbar_arrive_expect_tx(bar, 2 * (128 * 128 + 64 * 128));
+    tma_load_2d(st, &p.dhm, bar, kb * 64, tm * 128);
+    tma_load_2d(st + a_bytes, &p.w, bar, kb * 64, ty * 64);
+    tma_load_2d(st + half, &p.dhm_lo, bar, kb * 64, tm * 128);
+    tma_load_2d(st + half + a_bytes, &p.w_lo, bar, kb * 64, ty * 64);
+  }
   SRL_DEVINL static void issue(const Params& p, int tm, int ty, int kb, uint8_t* sA, uint8_t* sB, uint64_t* bar) {
     mbar_arrive_expect_tx(bar, 128 * 128 + 64 * 128);
     tma_load_2d(sA, &p.dhm, bar, kb * 64, tm * 128);
@@ -51,11 +68,22 @@ struct TFcDgrad {
     if (m < p.M) ld_mask16(p.a3 + (size_t)m * 3136 + ty * 64 + c0, mk);
   }
   SRL_DEVINL static void epilogue16(const Params& p, int tm, int ty, int row, int c0, float (&v)[16], const uint4 (&mk)[2]) {
+    epilogue16<0>(p, tm, ty, row, c0, v, mk);
+  }
+  template <int SPLIT>
+  SRL_DEVINL static void epilogue16(const Params& p, int tm, int ty, int row, int c0, float (&v)[16], const uint4 (&mk)[2]) {
     const int m = tm * 128 + row;
     if (m >= p.M) return;
     relu_mask16_pre(mk, v);
     // N-tile ty == one output pixel hw of conv3; da3g lives on conv3's 9x9 input grid (zeros outside the 7x7 outputs)
-    store_bf16x16(p.da3 + ((size_t)m * 81 + (ty / 7) * 9 + ty % 7) * 64 + c0, v);
+    const size_t o = ((size_t)m * 81 + (ty / 7) * 9 + ty % 7) * 64 + c0;
+    store_bf16x16(p.da3 + o, v);
+    if constexpr (SPLIT) {
+      float r[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+      store_bf16x16(p.da3_lo + o, r);
+    }
   }
 };
 
@@ -68,8 +96,23 @@ struct TFcWgrad {
   static constexpr bool PREFETCH = false;   // grid = (1, 4*50): ty = hw*4 + jt, hw == 49 is the ones slice (B = ones -> dbfc); stage = 64 frames
   static constexpr int BN = 64, STAGES = 4, KROWS = 64;
   static constexpr bool A_MN = true, B_MN = true, ZERO_INIT = true;
-  struct Params { SRL_TMAP dhm; SRL_TMAP a3m; float* dw; float* db; int M; };
+  struct Params { SRL_TMAP dhm; SRL_TMAP a3m; SRL_TMAP dhm_lo; SRL_TMAP a3m_lo; float* dw; float* db; int M; };
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.dhm); tma_prefetch_desc(&p.a3m); }
+  // split mode: the ones slice keeps B lo = 0 (zero-initialised once, never loaded), so only dh hi/lo . ones contribute
+  SRL_DEVINL static void issue_split(const Params& p, int, int ty, int kb, uint8_t* st, int a_bytes, int half, uint64_t* bar) {
+    const int hw = ty >> 2, j0 = (ty & 3) * 128;
+    mbar_arrive_expect_tx(bar, (hw < 49 ? 6 : 4) * 64 * 128);
+    tma_load_2d(st, &p.dhm, bar, j0, kb * 64);
+    tma_load_2d(st + KROWS * 128, &p.dhm, bar, j0 + 64, kb * 64);
+    tma_load_2d(st + half, &p.dhm_lo, bar, j0, kb * 64);
+    tma_load_2d(st + half + KROWS * 128, &p.dhm_lo, bar, j0 + 64, kb * 64);
+    if (hw < 49) {
+      tma_load_2d(st + a_bytes, &p.a3m, bar, hw * 64, kb * 64);
+      tma_load_2d(st + half + a_bytes, &p.a3m_lo, bar, hw * 64, kb * 64);
+    }
+  }
+  template <int SPLIT>
+  SRL_DEVINL static void epilogue16(const Params& p, int tm, int ty, int row, int c0, float (&v)[16]) { epilogue16(p, tm, ty, row, c0, v); }
   SRL_DEVINL static int num_kblocks(const Params& p, int, int) { return (p.M + 63) >> 6; }
   SRL_DEVINL static void init_smem(const Params&, int, int ty, uint8_t* smem, int stage_bytes, int tid) {
     if ((ty >> 2) == 49)

@@ -512,7 +512,8 @@ __global__ void __launch_bounds__(COL_THREADS) column_step_kernel(
     const float* __restrict__ bp, const float* __restrict__ Wb, const float* __restrict__ bb, int T, int B, int A, float discounting,
     int clip_reward, float clip_rho, float clip_pg, float baseline_cost, float entropy_cost, float* __restrict__ logits,
     float* __restrict__ baseline, float* __restrict__ vs, float* __restrict__ pg, float* __restrict__ dlogits,
-    float* __restrict__ dbaseline, __nv_bfloat16* __restrict__ dh, float* __restrict__ losses, float* __restrict__ scratch) {
+    float* __restrict__ dbaseline, __nv_bfloat16* __restrict__ dh, float* __restrict__ losses, float* __restrict__ scratch,
+    __nv_bfloat16* __restrict__ dh_lo) {
   extern __shared__ __align__(16) float csm[];
   const int CORE = 513 + A, WS = (CORE + 3) & ~3, N = (T + 1) * B;
   float* s_w = csm;                                   // [A+1][WS]: policy rows, then the baseline row
@@ -638,7 +639,10 @@ __global__ void __launch_bounds__(COL_THREADS) column_step_kernel(
 #pragma unroll
       for (int a = 0; a <= AMAX; ++a) if (a <= A) acc = fmaf(d[a], w[a], acc);
       const float hv = s_h[(size_t)t * 512 + j];
-      dh[((size_t)t * B + b) * 512 + j] = __float2bfloat16_rn(hv > 0.f ? acc : 0.f);
+      const float dv = hv > 0.f ? acc : 0.f;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(dv);
+      dh[((size_t)t * B + b) * 512 + j] = hi;
+      if (dh_lo) dh_lo[((size_t)t * B + b) * 512 + j] = __float2bfloat16_rn(dv - __bfloat162float(hi));   // fp32-accurate operand mode
     }
   }
   if (DBG) {
@@ -660,7 +664,8 @@ cudaError_t launch_column_step(const float* hpart, int nsplit, const float* bfc,
                                const uint8_t* done, const float* bl, const float* Wp, const float* bp, const float* Wb, const float* bb,
                                int T, int B, int A, float discounting, int clip_reward, float clip_rho, float clip_pg,
                                float baseline_cost, float entropy_cost, float* logits, float* baseline, float* vs, float* pg,
-                               float* dlogits, float* dbaseline, __nv_bfloat16* dh, float* losses, float* scratch, cudaStream_t st) {
+                               float* dlogits, float* dbaseline, __nv_bfloat16* dh, float* losses, float* scratch, cudaStream_t st,
+                               __nv_bfloat16* dh_lo) {
   if (!column_step_supported(T, B, A) || nsplit != 4) return cudaErrorInvalidValue;
   static PerDeviceOnce once;
   {
@@ -677,7 +682,7 @@ cudaError_t launch_column_step(const float* hpart, int nsplit, const float* bfc,
   static const bool dbg = [] { const char* e = getenv("SRL_COLUMN_DEBUG"); return e && atoi(e) != 0; }();   // prints phase times
 #define SRL_COL_ARGS dim3(B), dim3(COL_THREADS), column_smem_bytes(T, A), st, hpart, bfc, h, reward, action, done, bl, Wp, bp, Wb, bb, T, B, A, \
                      discounting, clip_reward, clip_rho, clip_pg, baseline_cost, entropy_cost, logits, baseline, vs, pg, dlogits, dbaseline, dh, \
-                     losses, scratch
+                     losses, scratch, dh_lo
   if (A <= 8) return dbg ? launch_chain<PDL_SIMT>(column_step_kernel<4, 8, true>, SRL_COL_ARGS)
                          : launch_chain<PDL_SIMT>(column_step_kernel<4, 8, false>, SRL_COL_ARGS);
   return launch_chain<PDL_SIMT>(column_step_kernel<4, 32, false>, SRL_COL_ARGS);

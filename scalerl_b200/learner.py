@@ -133,7 +133,7 @@ class ImpalaHParams:
     adam_beta1: float = 0.9
     adam_beta2: float = 0.999
     adam_eps: float = 1e-8
-    simt_mainloop: int = 0               # reserved (must be 0: TMA-fed tcgen05 mainloop)
+    precision: str = 'bf16'              # encoder operands: 'bf16' | 'fp32_split' (fp32-accurate hi/lo bf16 pairs; whole-step parity mode)
     use_lstm: bool = False               # AtariNet(use_lstm=True): 2-layer LSTM core (impala_atari.py:56; config 5)
 
     def to_c(self) -> _lib.SrlConfig:
@@ -147,7 +147,9 @@ class ImpalaHParams:
         c.T, c.B, c.A = self.rollout_length, self.batch_size, self.num_actions
         c.optimizer = 0 if self.optimizer == 'rmsprop' else 1
         c.reward_clip_abs_one = 1 if self.reward_clipping == 'abs_one' else 0
-        c.simt_mainloop = int(self.simt_mainloop)
+        if self.precision not in ('bf16', 'fp32_split'):
+            raise ValueError("precision must be 'bf16' or 'fp32_split'")
+        c.precision = 0 if self.precision == 'bf16' else 1
         c.discounting, c.baseline_cost, c.entropy_cost = self.discounting, self.baseline_cost, self.entropy_cost
         c.clip_rho_threshold = -1.0 if self.clip_rho_threshold is None else self.clip_rho_threshold
         c.clip_pg_rho_threshold = -1.0 if self.clip_pg_rho_threshold is None else self.clip_pg_rho_threshold

@@ -1,0 +1,48 @@
+"""Multi-GPU data-parallel correctness, collected by pytest: spawns ``torchrun tests/dp_check.py`` on
+every visible power-of-two GPU count >= 2 (skipped on a single-GPU box).  dp_check compares, every step, the column-sharded
+learners (gradient SUM inside the step: peer-memory apply kernel, or NCCL) against a full-batch learner on rank 0 and checks
+that the replicas stay bit-identical -- for RMSprop and Adam.  The log of the largest run is kept under gpurun_out/."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _counts():
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    return [w for w in (2, 4, 8) if w <= n]
+
+
+@pytest.mark.parametrize('world', [2, 4, 8])
+@pytest.mark.parametrize('fused', ['peer_memory', 'nccl'])
+def test_dp_check(world, fused):
+    if world not in _counts():
+        pytest.skip(f'{world} GPUs not visible')
+    env = dict(os.environ)
+    env['SRL_DP_FUSED'] = '1' if fused == 'peer_memory' else '0'
+    env['MASTER_ADDR'] = '127.0.0.1'
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}', '--master-addr', '127.0.0.1',
+           '--master-port', str(_free_port()), os.path.join(ROOT, 'tests', 'dp_check.py')]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    out = r.stdout + '\n' + r.stderr
+    d = os.path.join(ROOT, 'gpurun_out')
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, f'dp_check_n{world}_{fused}.log'), 'w') as f:
+        f.write(out)
+    assert r.returncode == 0 and 'DP CHECK OK' in out, out[-4000:]
+    want = 'peer memory' if fused == 'peer_memory' else 'NCCL all-reduce'
+    assert f'gradient path = {want}' in out, out[-2000:]

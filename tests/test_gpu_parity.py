@@ -254,8 +254,7 @@ def test_learn_step_vs_emulating_oracle(T, B, optimizer):
         # re-synchronise the oracle to the device state
         for k in O.PARAM_ORDER:
             params[k].copy_(L.params[k].cpu())
-        st = L.optimizer_state_dict()['state']
-        for name, d in st.items():
+        for name, d in L._opt_tensors().items():
             for k in O.PARAM_ORDER:
                 opt[name][k].copy_(d[k].cpu())
 
