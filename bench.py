@@ -376,7 +376,7 @@ def _main(real_stdout):
     from scalerl_b200.algorithms.impala.impala_atari import ImpalaArguments, ImpalaTrainer
     from scalerl_b200.data.slot_queue import SlotQueue
     targs = ImpalaArguments(num_actors=1, batch_size=B, rollout_length=T, num_buffers=POOL * B, num_actions=A, use_lstm=args.use_lstm,
-                            output_dir=tempfile.mkdtemp(prefix='srl_bench_'), disable_checkpoint=True)
+                            output_dir=tempfile.mkdtemp(prefix='srl_bench_'), disable_checkpoint=True, stats_lag=2)
     trainer = ImpalaTrainer(targs, learner=learner)
     for i, hb in enumerate(host_pool):                      # slot i*B + b = column b of pool batch i (what B actors would have written)
         for b in range(B):
@@ -398,6 +398,7 @@ def _main(real_stdout):
         return st
     trainer_loop(max(W, 6), 0)
     barrier()
+    trainer.wait_seconds = 0.0
     t0 = time.perf_counter()
     tstats = trainer_loop(K, W)
     torch.cuda.synchronize()
@@ -406,6 +407,7 @@ def _main(real_stdout):
         dist.barrier(device_ids=[local_rank])
     tr_s = max_over_ranks(dt)
     tr_value = frames / tr_s
+    tr_host_ms = (dt - trainer.wait_seconds) / K * 1e3          # host time per step outside the wait for the lagged result
     tr_h2d = B * trainer.ring.slot_bytes + (trainer._rnn_host[0].numel() * 4 if args.use_lstm else 0)
     tr_d2h = learner.numel * 4 + 8 + (8 * 4 + T * B * 5)       # weight publish + version counter + step result (scalars, episode_return, done)
     published = int(trainer.weights_version[0])
@@ -596,16 +598,14 @@ def _main(real_stdout):
             torch.cuda.synchronize()
             gpu_us = a_.elapsed_time(b_) / nit * 1e3
             cpu_cap = 1 << 16           # the pure-Python trees of the reference are slow: smaller buffer, bounded time
-            ref_t = PO.RefPER(cpu_cap, 0.6) if hasattr(PO, 'RefPER') else None
-            cpu_us = None
-            if ref_t is not None:
-                ref_t.add(cpu_cap)
-                import numpy as np
-                rng = np.random.RandomState(0)
-                t0 = time.perf_counter(); n = 0
-                while time.perf_counter() - t0 < 3.0:
-                    ref_t.sample(bsz, 0.4, rng.rand(bsz)); ref_t.update_priorities(rng.randint(0, cpu_cap, bsz), rng.rand(bsz) + 0.01); n += 1
-                cpu_us = (time.perf_counter() - t0) / n * 1e6
+            import numpy as np
+            ref_t = PO.PerOracle(cpu_cap, 0.6)      # the reference's tree arithmetic (segment_tree.py / replay_buffer.py) restated on the CPU
+            ref_t.add(cpu_cap)
+            rng = np.random.RandomState(0)
+            t0 = time.perf_counter(); n = 0
+            while n < 3 or time.perf_counter() - t0 < 3.0:
+                ref_t.sample(rng.rand(bsz), 0.4); ref_t.update_priorities(rng.randint(0, cpu_cap, bsz), rng.rand(bsz) + 0.01); n += 1
+            cpu_us = (time.perf_counter() - t0) / n * 1e6
             per = {'batch': bsz, 'gpu_capacity': cap, 'gpu_us_per_sample_plus_update': gpu_us, 'gpu_transitions_per_sec': bsz / (gpu_us * 1e-6),
                    'cpu_capacity': cpu_cap, 'cpu_us_per_sample_plus_update': cpu_us,
                    'cpu_transitions_per_sec': (bsz / (cpu_us * 1e-6)) if cpu_us else None,
@@ -631,7 +631,8 @@ def _main(real_stdout):
                        'ms_per_step': tr_s / K * 1e3,
                        'api': 'ImpalaTrainer.get_batch + ImpalaTrainer.learn (pinned shared-memory trajectory ring -> device, step, lagged stats, '
                               'asynchronous versioned weight publish into the shared actor parameters)',
-                       'weights_published': published, 'last_total_loss': tstats['total_loss'],
+                       'weights_published': published, 'last_total_loss': tstats['total_loss'], 'host_ms_per_step': tr_host_ms,
+                       'stats_lag_steps': targs.stats_lag,
                        'feeder_value': e2e_value, 'feeder_ms_per_step': e2e_s / K * 1e3, 'feeder_h2d_bytes_per_step': feeder.h2d_bytes,
                        'feeder_api': 'HostBatchFeeder.submit/learn/result (time-major pinned batches, no ring, no weight publish: round-1 e2e)',
                        'h2d_only_ms_per_step': h2d_only_ms, 'eager_launch_ms_per_step': e2e_eager_ms},

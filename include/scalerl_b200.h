@@ -72,6 +72,9 @@ int srl_policy_rows_forward(const float* logits, const int64_t* actions, int64_t
 int srl_policy_rows_backward(const float* logits, const int64_t* actions, const float* w_logp, const float* w_ent, int64_t N, int A,
                              float* dlogits, void* stream);
 int srl_reduce_sum(const float* x, int64_t n, int square, float scale, float* out, void* stream);
+/* actions[n] ~ softmax(logits[n]) through the inverse CDF of uniforms[n] in [0,1) (torch.multinomial of AtariNet.forward in training
+ * mode, atari_model.py:130-132); uniforms == NULL: argmax (evaluation mode, :133-134).  logits f32 [N,A], actions i64 [N]. */
+int srl_sample_actions(const float* logits, const float* uniforms, int64_t N, int A, int64_t* actions, void* stream);
 
 /* ---- learner context: encoder fwd/bwd on tcgen05 + heads + optimizer ------------------------------------
  * replaces AtariNet.forward (scalerl/algorithms/utils/atari_model.py:77-143, use_lstm=False) and
@@ -171,7 +174,11 @@ int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_out, void* st
  * mapped into this process (symmetric memory / CUDA IPC); grads[rank] must be the buffer given to srl_learner_create; the
  * control blocks start zeroed.  Every rank must call it once per step.  On return (stream order) the
  * local gradient buffer holds the SUM over ranks, as after ncclAllReduce. */
-typedef struct { void* grads[8]; void* exchange[8]; void* ctl[8]; int rank; int world; } srl_dp_peers_t;
+typedef struct {
+  void* grads[8]; void* exchange[8]; void* ctl[8]; int rank; int world;
+  void* grads_multicast;   /* NVLS multicast address of the gradient buffers (NULL: peer loads).  When set, the reduce-scatter is one
+                            * multimem.ld_reduce per 16 bytes (the NVSwitch adds the copies) and the all-gather one multimem.st */
+} srl_dp_peers_t;
 int srl_learner_apply_gradients_dp(srl_learner_t* L, const srl_dp_peers_t* peers, float* grad_norm_and_coef_out, void* stream);
 
 /* Weight-publish snapshot (impala_atari.py:348, actor_model.load_state_dict(learner_model.state_dict())): copies the flat fp32

@@ -14,7 +14,8 @@ _lib = None
 
 class SrlDpPeers(C.Structure):
     """mirror of srl_dp_peers_t: peer-mapped gradient buffers and control blocks of a data-parallel group (<= 8 ranks)"""
-    _fields_ = [('grads', C.c_void_p * 8), ('exchange', C.c_void_p * 8), ('ctl', C.c_void_p * 8), ('rank', C.c_int32), ('world', C.c_int32)]
+    _fields_ = [('grads', C.c_void_p * 8), ('exchange', C.c_void_p * 8), ('ctl', C.c_void_p * 8), ('rank', C.c_int32), ('world', C.c_int32),
+                ('grads_multicast', C.c_void_p)]
 
 
 class SrlConfig(C.Structure):
@@ -37,6 +38,7 @@ _SIGS = {
     'srl_policy_rows_forward': [_P, _P, _L, _I, _P, _P, _P],
     'srl_policy_rows_backward': [_P, _P, _P, _P, _L, _I, _P, _P],
     'srl_reduce_sum': [_P, _L, _I, _F, _P, _P],
+    'srl_sample_actions': [_P, _P, _L, _I, _P, _P],
     'srl_learner_create': [C.POINTER(SrlConfig), _P, _P, _P, _P, C.POINTER(_P)],
     'srl_learner_destroy': [_P],
     'srl_learner_set_config': [_P, C.POINTER(SrlConfig)],

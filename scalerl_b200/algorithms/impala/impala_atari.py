@@ -234,6 +234,46 @@ class ImpalaTrainer:
             traceback.print_exc()
             raise
 
+    def get_action_batched(self, actor_index, free_queue, full_queue, actor_model, buffers, rnn_state_buffers, num_envs: int) -> None:
+        """One actor process driving ``num_envs`` environments with ONE model call per step (batched actor
+        inference, e.g. ``gpu_actor.B200ActorModel`` or any model with the reference's calling convention evaluated at batch N).
+        Same slot protocol as ``get_action`` (impala_atari.py:153-220): environment e fills its own trajectory slot."""
+        try:
+            torch.set_num_threads(1)
+            envs = [self.env_fn() for _ in range(num_envs)]
+            cat = lambda outs: {k: torch.cat([o[k] for o in outs], dim=1) for k in outs[0]}          # [1, N, ...]
+            env_output = cat([e.reset() for e in envs])
+            agent_state = actor_model.initial_hidden_state(batch_size=num_envs)
+            agent_output, unused_state = actor_model(env_output, agent_state)
+            T = self.args.rollout_length
+            while True:
+                indices = [free_queue.get() for _ in range(num_envs)]
+                if any(i is None for i in indices):
+                    break
+                for e, index in enumerate(indices):
+                    for key in env_output:
+                        buffers[key][index][0, ...] = env_output[key][0, e]
+                    for key in agent_output:
+                        buffers[key][index][0, ...] = agent_output[key][0, e]
+                    for i, tensor in enumerate(agent_state):
+                        rnn_state_buffers[index][i][...] = tensor[:, e:e + 1]
+                for t in range(T):
+                    with torch.no_grad():
+                        agent_output, agent_state = actor_model(env_output, agent_state)
+                    env_output = cat([env.step(agent_output['action'][0, e]) for e, env in enumerate(envs)])
+                    for e, index in enumerate(indices):
+                        for key in env_output:
+                            buffers[key][index][t + 1, ...] = env_output[key][0, e]
+                        for key in agent_output:
+                            buffers[key][index][t + 1, ...] = agent_output[key][0, e]
+                for index in indices:
+                    full_queue.put(index)
+        except KeyboardInterrupt:
+            pass
+        except Exception:
+            traceback.print_exc()
+            raise
+
     # ------------------------------------------------------------------------------------------------- learner
     def _ensure_learner(self):
         if self.learner is not None:
@@ -437,7 +477,9 @@ class ImpalaTrainer:
         lag = max(0, int(self.args.stats_lag))
         while len(self._tickets) > lag + 1:
             self._tickets.popleft()
+        t_wait = time.perf_counter()
         stats = L.result(self._tickets[0])
+        self.wait_seconds = getattr(self, 'wait_seconds', 0.0) + (time.perf_counter() - t_wait)     # time blocked on the GPU (diagnostics)
         self._poll_releases()
         if not math.isfinite(stats['total_loss']):          # the device-side guard already kept these weights from the actors
             raise FloatingPointError(f'non-finite learner loss: {stats}')

@@ -82,6 +82,13 @@ extern "C" int srl_policy_rows_backward(const float* logits, const int64_t* acti
   CU(launch_policy_rows_bwd(logits, actions, w_logp, w_ent, N, A, dlogits, (cudaStream_t)stream), "policy_rows_backward");
   return 0;
 }
+extern "C" int srl_sample_actions(const float* logits, const float* uniforms, int64_t N, int A, int64_t* actions, void* stream) {
+  REQ(N >= 0 && A >= 1, "sample_actions: bad shape N=%lld A=%d", (long long)N, A);
+  if (N == 0) return 0;
+  REQ(logits && actions, "sample_actions: NULL pointer");
+  CU(launch_sample_actions(logits, uniforms, N, A, actions, (cudaStream_t)stream), "sample_actions");
+  return 0;
+}
 extern "C" int srl_reduce_sum(const float* x, int64_t n, int square, float scale, float* out, void* stream) {
   REQ(n >= 0 && out && (x || n == 0), "reduce_sum: bad argument");
   CU(launch_reduce_sum(x, n, square, scale, out, (cudaStream_t)stream), "reduce_sum");
@@ -615,7 +622,7 @@ extern "C" int srl_learner_apply_gradients_dp(srl_learner_t* L, const srl_dp_pee
     P.rs[i] = i < peers->world ? (float*)peers->exchange[i] : nullptr;
     REQ(i >= peers->world || (P.g[i] && P.ctl[i] && P.rs[i]), "apply_gradients_dp: NULL peer pointer %d", i);
   }
-  P.rank = peers->rank; P.world = peers->world;
+  P.rank = peers->rank; P.world = peers->world; P.mc_g = (float*)peers->grads_multicast;
   L->pf.st = st;
   L->step += 1;
   L->pf.b(PS_OPTIMIZER);

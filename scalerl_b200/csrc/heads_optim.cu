@@ -537,6 +537,24 @@ SRL_DEVINL unsigned long long global_ns() {
 SRL_DEVINL void st_sys_v4(float* p, const float4& v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// NVLS (NVLink SHARP) multicast accesses: `p` is an address inside a multicast mapping of a symmetric buffer.  ld_reduce returns
+// the SUM over every rank's copy, computed in the switch (one request instead of world-1 peer loads); st writes every copy.
+SRL_DEVINL float4 multimem_ld_reduce_v4(const float* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+SRL_DEVINL float multimem_ld_reduce_f32(const float* p) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+SRL_DEVINL void multimem_st_v4(float* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+SRL_DEVINL void multimem_st_f32(float* p, float v) { asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
 // cross-GPU barrier, split in two: one block signals every rank, EVERY block waits on the local flags (thread q < world
 // waits for rank q).  Waits are bounded: 30 s of globaltimer, then trap.
 // fence = true when this block wrote remote memory that the flag publishes (the release store is cumulative over what the
@@ -559,7 +577,12 @@ SRL_DEVINL void dp_wait(const DpPeers& P, unsigned epoch) {        // all thread
   __syncthreads();
 }
 
-template <int OPT>
+// NVLS = true (the symmetric gradient buffer has a multicast mapping, P.mc_g): phase 1 is ONE multimem.ld_reduce per float4 of
+// the rank's slice (the switch adds the world copies) followed by a multimem.st that writes the sum into EVERY rank's gradient
+// buffer; after barrier 2 each rank holds the complete reduced gradient locally, so phase 2 is the plain single-GPU clip +
+// optimizer pass -- no peer pulls, no exchange buffer.  An element is read and then overwritten only by its slice's owner, so
+// the in-place broadcast cannot race with another rank's reduction.  All replicas consume the owner's bits: bit-identical.
+template <int OPT, bool NVLS>
 __global__ void __launch_bounds__(512) dp_clip_optim_kernel(float* __restrict__ p, float* g, float* __restrict__ s0, float* __restrict__ s1,
                                                             int64_t n, float max_norm, float* coef, float* scratch, float lr, float a,
                                                             float b, float eps, int step, int* dstep, const DpPeers P, int dbg) {
@@ -579,6 +602,29 @@ __global__ void __launch_bounds__(512) dp_clip_optim_kernel(float* __restrict__ 
   //      in phase 2) and, in place, to my gradient buffer
   float s = 0.f;
   float* rs_mine = P.rs[R];
+  if constexpr (NVLS) {
+    constexpr int PF = 4;                                  // PF switch reductions in flight per thread
+    for (int64_t ib = lo + i0; ib < hi; ib += PF * stride) {
+      float4 acc[PF];
+#pragma unroll
+      for (int u = 0; u < PF; ++u) { const int64_t i = ib + u * stride; if (i < hi) acc[u] = multimem_ld_reduce_v4(P.mc_g + 4 * i); }
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int64_t i = ib + u * stride;
+        if (i < hi) {
+          multimem_st_v4(P.mc_g + 4 * i, acc[u]);          // every rank's gradient buffer (mine included) receives the sum
+          s += acc[u].x * acc[u].x + acc[u].y * acc[u].y + acc[u].z * acc[u].z + acc[u].w * acc[u].w;
+        }
+      }
+    }
+    if (R == W - 1 && blockIdx.x == 0 && (int64_t)threadIdx.x < (n & 3)) {
+      const int64_t i = n4 * 4 + threadIdx.x;
+      const float acc = multimem_ld_reduce_f32(P.mc_g + i);
+      multimem_st_f32(P.mc_g + i, acc);
+      s += acc * acc;
+    }
+    __threadfence_system();                                // my remote stores are performed before the flag of barrier 2 is published
+  } else {
   for (int64_t i = lo + i0; i < hi; i += stride) {
     float4 acc = ld_sys_v4(P.g[0] + 4 * i);
     for (int q = 1; q < W; ++q) {
@@ -596,6 +642,7 @@ __global__ void __launch_bounds__(512) dp_clip_optim_kernel(float* __restrict__ 
     rs_mine[4 * chunk + threadIdx.x] = acc;
     g[i] = acc;
     s += acc * acc;
+  }
   }
   __shared__ float red[16];
   __shared__ float c_sh;
@@ -655,7 +702,9 @@ __global__ void __launch_bounds__(512) dp_clip_optim_kernel(float* __restrict__ 
       const int64_t i = ib + u * stride;
       if (i < n4) {
         const int owner = (int)min((int64_t)(W - 1), i / chunk);
-        gpre[u] = owner == R ? reinterpret_cast<const float4*>(g)[i] : ld_sys_v4(P.rs[owner] + 4 * (i - owner * chunk));
+        // NVLS: the owner's multimem.st already put the sum into my buffer (written by a peer: read past L1 with ld.volatile)
+        gpre[u] = NVLS ? ld_sys_v4(g + 4 * i)
+                       : (owner == R ? reinterpret_cast<const float4*>(g)[i] : ld_sys_v4(P.rs[owner] + 4 * (i - owner * chunk)));
       }
     }
 #pragma unroll
@@ -663,7 +712,7 @@ __global__ void __launch_bounds__(512) dp_clip_optim_kernel(float* __restrict__ 
       const int64_t i = ib + u * stride;
       if (i >= n4) break;
       const float4 gg = gpre[u];
-      if ((int)min((int64_t)(W - 1), i / chunk) != R) reinterpret_cast<float4*>(g)[i] = gg;       // keep a copy: all-gather
+      if (!NVLS && (int)min((int64_t)(W - 1), i / chunk) != R) reinterpret_cast<float4*>(g)[i] = gg;       // keep a copy: all-gather
       float4 pp = reinterpret_cast<float4*>(p)[i], vv = reinterpret_cast<float4*>(s0)[i];
       float* Pp = &pp.x; float* V = &vv.x; const float* G = &gg.x;
       if (OPT == 0) {
@@ -692,7 +741,8 @@ __global__ void __launch_bounds__(512) dp_clip_optim_kernel(float* __restrict__ 
   if (blockIdx.x == 0 && (int64_t)threadIdx.x < (n & 3)) {
     const int64_t i = n4 * 4 + threadIdx.x;
     float gv;
-    if (R == W - 1) gv = g[i];
+    if (NVLS) gv = ld_sys_f32(g + i);
+    else if (R == W - 1) gv = g[i];
     else { gv = ld_sys_f32(P.rs[W - 1] + 4 * chunk + threadIdx.x); g[i] = gv; }
     const float gk = gv * c;
     if (OPT == 0) {
@@ -710,7 +760,7 @@ __global__ void __launch_bounds__(512) dp_clip_optim_kernel(float* __restrict__ 
            ts[1] - ts[0], ts[2] - ts[1], ts[3] - ts[2], ts[4] - ts[3], ts[5] - ts[4], global_ns() - ts[5]);
 }
 
-template <int OPT>
+template <int OPT, bool NVLS>
 static cudaError_t launch_dp_clip_optim_t(float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef, float* scratch,
                                           float lr, float a, float b, float eps, int step, int* dstep, DpPeers P, cudaStream_t st) {
   static int per_sm_dev[64] = {}, sms_dev[64] = {};      // per device: one process may drive several GPUs
@@ -720,7 +770,7 @@ static cudaError_t launch_dp_clip_optim_t(float* p, float* g, float* s0, float* 
   if (!per_sm_dev[dev]) {
     int sm_count = 0, occ = 0;
     SRL_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    SRL_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dp_clip_optim_kernel<OPT>, 512, 0));
+    SRL_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (dp_clip_optim_kernel<OPT, NVLS>), 512, 0));
     if (occ < 1) return cudaErrorLaunchOutOfResources;
     sms_dev[dev] = sm_count; per_sm_dev[dev] = occ;
   }
@@ -731,7 +781,7 @@ static cudaError_t launch_dp_clip_optim_t(float* p, float* g, float* s0, float* 
   if (blocks > cap) blocks = cap;
   static int dbg = [] { const char* e = getenv("SRL_DP_DEBUG"); return e ? atoi(e) : 0; }();
   void* args[] = {&p, &g, &s0, &s1, &n, &max_norm, &coef, &scratch, &lr, &a, &b, &eps, &step, &dstep, &P, &dbg};
-  return cudaLaunchCooperativeKernel((const void*)dp_clip_optim_kernel<OPT>, dim3(blocks), dim3(512), args, 0, st);
+  return cudaLaunchCooperativeKernel((const void*)dp_clip_optim_kernel<OPT, NVLS>, dim3(blocks), dim3(512), args, 0, st);
 }
 // Weight-publish snapshot (impala_atari.py:348): dst = src when the step's total loss is finite, else dst keeps the last good
 // weights -- so the asynchronous D2H that follows never hands poisoned parameters to the actors.
@@ -755,8 +805,11 @@ cudaError_t launch_snapshot_if_finite(float* dst, const float* src, int64_t n, c
 cudaError_t launch_dp_clip_optim(int optimizer, float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
                                  float* scratch, float lr, float a, float b, float eps, int step, int* dstep, const DpPeers& P,
                                  cudaStream_t st) {
-  return optimizer == 0 ? launch_dp_clip_optim_t<0>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, P, st)
-                        : launch_dp_clip_optim_t<1>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, P, st);
+  if (P.mc_g)
+    return optimizer == 0 ? launch_dp_clip_optim_t<0, true>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, P, st)
+                          : launch_dp_clip_optim_t<1, true>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, P, st);
+  return optimizer == 0 ? launch_dp_clip_optim_t<0, false>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, P, st)
+                        : launch_dp_clip_optim_t<1, false>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, P, st);
 }
 
 }  // namespace srl

@@ -78,6 +78,7 @@ cudaError_t launch_vtrace_logits(const float* bl, const float* tl, const int64_t
 cudaError_t launch_policy_rows_fwd(const float* logits, const int64_t* actions, int64_t N, int A, float* logp, float* ent, cudaStream_t st);
 cudaError_t launch_policy_rows_bwd(const float* logits, const int64_t* actions, const float* w_logp, const float* w_ent, int64_t N, int A,
                                    float* dlogits, cudaStream_t st);
+cudaError_t launch_sample_actions(const float* logits, const float* u, int64_t N, int A, int64_t* actions, cudaStream_t st);
 cudaError_t launch_reduce_sum(const float* x, int64_t n, int square, float scale, float* out, cudaStream_t st);
 bool column_step_supported(int T, int B, int A);
 cudaError_t launch_column_step(const float* hpart, int nsplit, const float* bfc, float* h, const float* reward, const int64_t* action,
@@ -110,7 +111,7 @@ cudaError_t launch_unpack_slots(const uint8_t* staging, int64_t slot_bytes, cons
                                 uint8_t* done, int64_t* action, float* logits, float* episode_return, cudaStream_t st);
 cudaError_t launch_clip_optim(int optimizer, float* p, const float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
                               float* scratch, float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st);
-struct DpPeers { float* g[8]; float* rs[8]; unsigned* ctl[8]; int rank, world; };      // peer-mapped gradient buffers / control blocks
+struct DpPeers { float* g[8]; float* rs[8]; unsigned* ctl[8]; int rank, world; float* mc_g; };      // peer-mapped gradient buffers / control blocks; mc_g: NVLS multicast address of the gradient buffers (or null)
 cudaError_t launch_dp_clip_optim(int optimizer, float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
                                  float* scratch, float lr, float a, float b, float eps, int step, int* dstep, const DpPeers& P,
                                  cudaStream_t st);

@@ -445,6 +445,33 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restric
     if (threadIdx.x == 0) out[0] = scale * t;
   }
 }
+// action[n] ~ softmax(logits[n]) by inverse CDF of the uniform u[n] in [0,1)  (AtariNet.forward's torch.multinomial in training mode,
+// atari_model.py:130-132);  u == NULL: argmax (evaluation mode, :133-134).  One thread per row.
+__global__ void __launch_bounds__(128) sample_actions_kernel(const float* __restrict__ logits, const float* __restrict__ u, int64_t N, int A,
+                                                             int64_t* __restrict__ actions) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* row = logits + n * A;
+  float mx = -INFINITY;
+  int arg = 0;
+  for (int a = 0; a < A; ++a) { const float v = __ldg(row + a); if (v > mx) { mx = v; arg = a; } }
+  if (!u) { actions[n] = arg; return; }
+  float se = 0.f;
+  for (int a = 0; a < A; ++a) se += expf(__ldg(row + a) - mx);
+  const float target = __ldg(u + n) * se;
+  float c = 0.f;
+  int pick = A - 1;
+  for (int a = 0; a < A; ++a) {
+    c += expf(__ldg(row + a) - mx);
+    if (target < c) { pick = a; break; }
+  }
+  actions[n] = pick;
+}
+cudaError_t launch_sample_actions(const float* logits, const float* u, int64_t N, int A, int64_t* actions, cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  sample_actions_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(logits, u, N, A, actions);
+  return cudaGetLastError();
+}
 cudaError_t launch_policy_rows_fwd(const float* logits, const int64_t* actions, int64_t N, int A, float* logp, float* ent, cudaStream_t st) {
   if (N <= 0) return cudaSuccess;
   policy_rows_fwd_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(logits, actions, N, A, logp, ent);

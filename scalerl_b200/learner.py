@@ -207,8 +207,9 @@ class B200ImpalaLearner(BaseAgent):
             if hp.use_lstm:     # static copies of the initial LSTM state (graph-replay safe addresses)
                 self._h0 = torch.zeros(2, B, 513 + A, device=self.device)
                 self._c0 = torch.zeros(2, B, 513 + A, device=self.device)
-            self._losses = torch.zeros(4, device=self.device)
-            self._coef = torch.zeros(2, device=self.device)
+            self._resdev = torch.zeros(8, device=self.device)      # {pg, baseline, entropy, total loss | grad norm, clip coef | pad}: ONE D2H per step
+            self._losses = self._resdev[:4]
+            self._coef = self._resdev[4:6]
             self._vs = torch.empty(T, B, device=self.device)
             self._pg_adv = torch.empty(T, B, device=self.device)
             self._stats_host = torch.zeros(8, dtype=torch.float32).pin_memory()
@@ -243,6 +244,11 @@ class B200ImpalaLearner(BaseAgent):
             peers.rank, peers.world = rank, world
             if int(hg.buffer_ptrs[rank]) != grads.data_ptr():
                 raise RuntimeError('symmetric buffer is not at the tensor address')
+            mc = int(getattr(hg, 'multicast_ptr', 0) or 0) if os.environ.get('SRL_DP_NVLS', '1') != '0' else 0
+            flag = torch.tensor([1 if mc else 0], device=self.device)          # NVLS only when EVERY rank has the multicast mapping
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg or None)
+            peers.grads_multicast = mc if bool(flag.item()) else None
+            self.dp_path = 'nvls multimem' if peers.grads_multicast else 'peer loads' 
             self._symm_keep = (grads, ctl, hg, hc, exch, hx)
         except Exception as e:         # noqa: BLE001 -- any failure means "use NCCL"
             import warnings
@@ -452,8 +458,7 @@ class B200ImpalaLearner(BaseAgent):
         r = self._res[k % self._res_depth]
         if self._dist:
             torch.distributed.all_reduce(self._losses, op=torch.distributed.ReduceOp.SUM, group=self.pg or None)
-        r['scal'][:4].copy_(self._losses, non_blocking=True)
-        r['scal'][4:6].copy_(self._coef, non_blocking=True)
+        r['scal'].copy_(self._resdev, non_blocking=True)
         r['has_ep'] = 'episode_return' in batch
         if r['has_ep']:
             r['ep'].copy_(batch['episode_return'][1:], non_blocking=True)

@@ -34,7 +34,8 @@ def main():
                                   init_state_dict=params)
         full = B200ImpalaLearner(ImpalaHParams(rollout_length=T, batch_size=B, num_actions=A, optimizer=optimizer),
                                  init_state_dict=params, process_group=False) if rank == 0 else None
-        path = 'peer memory (fused reduce+clip+optimizer kernel)' if shard._peers is not None else 'NCCL all-reduce'
+        path = (f'peer memory (fused reduce+clip+optimizer kernel; {getattr(shard, "dp_path", "?")})' if shard._peers is not None
+                else 'NCCL all-reduce')
         worst = 0.0
         for step in range(5):
             s = shard.learn(mine)

@@ -202,3 +202,30 @@ def test_trainer_validation_and_lstm_accepted(tmp_path):
     t = ImpalaTrainer(ImpalaArguments(use_lstm=True, num_actors=1, batch_size=2, output_dir=str(tmp_path)))
     assert t.hparams().use_lstm and t._rnn_block is not None and tuple(t._rnn_block.shape) == (2, 2, 2, 1, 519)
     assert int(t.weights_version[0]) == 0 and t.weights_version.is_shared()
+
+
+@pytest.mark.parametrize('use_lstm', [False, True])
+def test_get_action_batched_matches_the_slot_protocol(use_lstm, tmp_path):
+    """one actor process, N environments, one model call per step: every environment fills its own slot (same rows / keys /
+    initial LSTM state as get_action writes for a single environment)"""
+    a = ImpalaArguments(num_actors=1, batch_size=2, rollout_length=3, num_buffers=4, use_lstm=use_lstm, output_dir=str(tmp_path))
+    seeds = iter(range(100))
+    t = ImpalaTrainer(a, env_fn=lambda: SyntheticAtariEnv((4, 84, 84), a.num_actions, seed=next(seeds)))
+    import queue
+    free_q, full_q = queue.SimpleQueue(), queue.SimpleQueue()
+    for m in (3, 1, 0):
+        free_q.put(m)
+    for _ in range(3):
+        free_q.put(None)
+    th = threading.Thread(target=t.get_action_batched, args=(0, free_q, full_q, t.actor_model, t.buffers, t.rnn_state_buffers, 3))
+    th.start(); th.join(timeout=120)
+    assert not th.is_alive()
+    assert sorted(full_q.get() for _ in range(3)) == [0, 1, 3]
+    for m in (0, 1, 3):
+        assert int(t.buffers['obs'][m].sum()) > 0 and torch.isfinite(t.buffers['policy_logits'][m]).all()
+        assert [int(v) for v in t.buffers['episode_step'][m][1:]] == [1, 2, 3]
+        # the stored action of row t+1 is the agent's action that produced it (key collision kept as the reference behaves)
+        assert int(t.buffers['action'][m].max()) < a.num_actions
+    assert int(t.buffers['obs'][2].sum()) == 0
+    # distinct environments wrote distinct frames
+    assert not torch.equal(t.buffers['obs'][0], t.buffers['obs'][1])
