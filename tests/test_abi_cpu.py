@@ -68,8 +68,8 @@ def test_config_struct_size():
 
 
 def test_dp_peers_struct_and_argument_checks():
-    """srl_dp_peers_t: 3 x 8 pointers + rank + world; bad descriptors are rejected before any CUDA call"""
-    assert ctypes.sizeof(_lib.SrlDpPeers) == 3 * 8 * 8 + 8
+    """srl_dp_peers_t: 3 x 8 pointers + rank + world + the NVLS multicast pointer; bad descriptors are rejected before any CUDA call"""
+    assert ctypes.sizeof(_lib.SrlDpPeers) == 3 * 8 * 8 + 8 + 8
     L = _lib.lib()
     assert L.srl_learner_apply_gradients_dp(None, None, None, None) == -1
     assert b'NULL' in L.srl_last_error()
