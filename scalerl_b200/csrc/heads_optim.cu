@@ -391,17 +391,51 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n,
 // in a fixed slot each), grid barrier, every block adds the partials in the same fixed order (deterministic, identical
 // in all blocks), phase 2 applies the clipped update (g is re-read from L2).  OPT 0 = RMSprop, 1 = Adam.
 // ------------------------------------------------------------------------------------------------
+// workspace -> PyTorch-layout value of conv weight gradient element e of layer L (1, 2, 3); re-zeroes the slot (self-cleaning)
+SRL_DEVINL float wgrad_ws_take(float* ws, int layer, int e) {
+  float* q;
+  float scale = 1.0f;
+  if (layer == 3) {            // dW3[co][c][tap] = ws3[tap>>1][(tap&1)*64 + c][co]
+    const int co = e / 576, r = e - co * 576, c = r / 9, tap = r - c * 9;
+    q = ws + WS_W3 + ((tap >> 1) * 128 + (tap & 1) * 64 + c) * 64 + co;
+  } else if (layer == 2) {     // dW2[co][c][kh][kw] = ws2[kh][kw*32 + c][co]
+    const int co = e >> 9, r = e & 511, c = r >> 4, kh = (r >> 2) & 3, kw = r & 3;
+    q = ws + WS_W2 + (kh * 128 + kw * 32 + c) * 64 + co;
+  } else {                     // dW1[co][c][kh][kw] = ws1[kh>>2][(kw>>2)*64 + c*16 + (kh&3)*4 + (kw&3)][co] / 255
+    const int co = e >> 8, k = e & 255, c = k >> 6, kh = (k >> 3) & 7, kw = k & 7;
+    q = ws + WS_W1 + ((kh >> 2) * 128 + (kw >> 2) * 64 + c * 16 + (kh & 3) * 4 + (kw & 3)) * 32 + co;
+    scale = 1.0f / 255.0f;
+  }
+  const float v = __ldcg(q) * scale;      // written by red.global.add of other kernels: read at L2
+  *q = 0.f;
+  return v;
+}
+
 template <int OPT>
-__global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s0,
+__global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s0,
                                                          float* __restrict__ s1, int64_t n, float max_norm, float* __restrict__ coef,
                                                          float* __restrict__ scratch, float lr, float a, float b, float eps, int step,
-                                                         int* __restrict__ dstep) {
+                                                         int* __restrict__ dstep, const WgradFold fold) {
   cg::grid_group grid = cg::this_grid();
   const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int t = dstep ? *dstep + 1 : step;          // 1-based step count: Adam bias correction; counted for RMSprop too (checkpoints)
   float s = 0.f;
   for (int64_t i = i0; i < n4; i += stride) {
-    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    float4 v;
+    const int64_t e0 = 4 * i;
+    int layer = 0, e = 0;
+    if (fold.ws) {            // conv weight gradients come from the wgrad workspace (conv_wgrad_finalize folded in)
+      if (e0 >= fold.off_w1 && e0 < fold.off_w1 + 8192) { layer = 1; e = (int)(e0 - fold.off_w1); }
+      else if (e0 >= fold.off_w2 && e0 < fold.off_w2 + 32768) { layer = 2; e = (int)(e0 - fold.off_w2); }
+      else if (e0 >= fold.off_w3 && e0 < fold.off_w3 + 36864) { layer = 3; e = (int)(e0 - fold.off_w3); }
+    }
+    if (layer) {
+      v.x = wgrad_ws_take(fold.ws, layer, e); v.y = wgrad_ws_take(fold.ws, layer, e + 1);
+      v.z = wgrad_ws_take(fold.ws, layer, e + 2); v.w = wgrad_ws_take(fold.ws, layer, e + 3);
+      reinterpret_cast<float4*>(g)[i] = v;          // the gradient tensors end up complete, as after the finalize kernel
+    } else {
+      v = reinterpret_cast<const float4*>(g)[i];
+    }
     s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = g[n4 * 4 + threadIdx.x]; s += v * v; }
@@ -467,8 +501,8 @@ __global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, 
 }
 
 template <int OPT>
-static cudaError_t launch_clip_optim_t(float* p, const float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef, float* scratch,
-                                       float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st) {
+static cudaError_t launch_clip_optim_t(float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef, float* scratch,
+                                       float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st, WgradFold fold) {
   static int per_sm_dev[64] = {}, sms_dev[64] = {};      // per device: one process may drive several GPUs
   int dev = 0;
   SRL_TRY(cudaGetDevice(&dev));
@@ -485,13 +519,13 @@ static cudaError_t launch_clip_optim_t(float* p, const float* g, float* s0, floa
   int blocks = (int)(need < 1 ? 1 : need);
   int cap = per_sm * sms; if (cap > 592) cap = 592;          // scratch holds 592 partials
   if (blocks > cap) blocks = cap;
-  void* args[] = {&p, &g, &s0, &s1, &n, &max_norm, &coef, &scratch, &lr, &a, &b, &eps, &step, &dstep};
+  void* args[] = {&p, &g, &s0, &s1, &n, &max_norm, &coef, &scratch, &lr, &a, &b, &eps, &step, &dstep, &fold};
   return cudaLaunchCooperativeKernel((const void*)clip_optim_kernel<OPT>, dim3(blocks), dim3(512), args, 0, st);
 }
-cudaError_t launch_clip_optim(int optimizer, float* p, const float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
-                              float* scratch, float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st) {
-  return optimizer == 0 ? launch_clip_optim_t<0>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, st)
-                        : launch_clip_optim_t<1>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, st);
+cudaError_t launch_clip_optim(int optimizer, float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
+                              float* scratch, float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st, WgradFold fold) {
+  return optimizer == 0 ? launch_clip_optim_t<0>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, st, fold)
+                        : launch_clip_optim_t<1>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, st, fold);
 }
 
 // ------------------------------------------------------------------------------------------------

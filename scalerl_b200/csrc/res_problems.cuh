@@ -31,7 +31,7 @@ SRL_DEVINL void store_act16(bf16* hi, bf16* lo, size_t elem_off, const float (&v
 struct RConv1Fwd {   // 2x2 s1 over xs (== 8x8 s4 over the frame): taps (kh2,kw2) -> shifts {0, 1, 21, 22}
   static constexpr int BN = 32, NT = 4, NWIN = 1, WROWS = 128 + 22, STAGES = 4, SPLIT_STAGES = 4;
   static constexpr bool A_LO = false;        // the frames are exact in bf16: only the weights have a low tensor
-  struct Params { SRL_TMAP in0; SRL_TMAP w; SRL_TMAP w_lo; const float* bias; bf16* out; bf16* out_lo; int NF; };
+  struct Params { SRL_TMAP in0; SRL_TMAP w; SRL_TMAP w_lo; const float* bias; bf16* out; bf16* out_lo; int NF; int NFS; };   // NF frames now, NFS = frames the a1 planes are strided for
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.w); }
   SRL_DEVINL static int num_tiles(const Params& p) { return (p.NF * 441 + 127) >> 7; }
   SRL_DEVINL static constexpr int tap_win(int) { return 0; }
@@ -44,7 +44,7 @@ struct RConv1Fwd {   // 2x2 s1 over xs (== 8x8 s4 over the frame): taps (kh2,kw2
     if (n >= p.NF || oh >= 20 || ow >= 20) return;
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(fmaf(v[j], 1.0f / 255.0f, __ldg(p.bias + c0 + j)), 0.f);
-    const size_t prow = (size_t)(oh & 1) * p.NF * 100 + (size_t)n * 100 + (oh >> 1) * 10 + (ow >> 1);
+    const size_t prow = (size_t)(oh & 1) * p.NFS * 100 + (size_t)n * 100 + (oh >> 1) * 10 + (ow >> 1);    // plane stride: the buffer's frame capacity
     store_act16<SPLIT>(p.out, p.out_lo, prow * 64 + (ow & 1) * 32 + c0, v);
   }
 };
@@ -142,10 +142,7 @@ struct RConv2Dgrad {   // the 4 stride-parity classes share A (da2g at (i'-kh', 
 // The weight-gradient accumulators are added (16-byte vector reductions) into a zeroed fp32 workspace in the
 // kernels' native [tap-block][row][co] order; conv_wgrad_finalize_kernel (encoder.cu) then writes the PyTorch-layout
 // gradient tensors.  Workspace offsets (floats):
-constexpr int WS_W3 = 0;                       // [5 acc][128 rows][64 co]   (tap 9 half unused)
-constexpr int WS_W2 = WS_W3 + 5 * 128 * 64;    // [4 kh][128 rows][64 co]
-constexpr int WS_W1 = WS_W2 + 4 * 128 * 64;    // [2 kh2][128 rows][32 co]
-constexpr int WS_TOTAL = WS_W1 + 2 * 128 * 32;
+// (WS_W3 / WS_W2 / WS_W1 / WS_TOTAL are defined in kernels.h: the optimizer kernel reads the workspace too)
 struct RConv3Wgrad {   // acc a = taps (2a, 2a+1); acc 4 = (tap 8, ones -> db3).  ws: [10 taps][64 c][64 co] fp32 (co contiguous)
   static constexpr int NACC = 5, NWIN = 1, WROWS = 128 + 20, STAGES = 3, SPLIT_STAGES = 2;
   static constexpr bool A_LO = true;

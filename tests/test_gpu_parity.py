@@ -216,6 +216,19 @@ def test_forward_vs_emulating_oracle(T, B):
     assert rel_l2(out['policy_logits'].cpu(), lg32) < 2e-2
 
 
+@pytest.mark.parametrize('rows', [1, 3])
+def test_forward_with_fewer_rows_than_the_context_holds(rows):
+    """srl_learner_forward(rows < T+1) (the actor-inference use): round 1 strided conv1's output planes by the rows of the CALL
+    while conv2's tensor map is built for the context's capacity -- wrong logits whenever rows != T+1"""
+    T, B, A = 4, 5, 6
+    L, params = _learner(T, B, A, 2)
+    batch = O.synthetic_batch(T, B, A, seed=3)
+    sub = {k: v[:rows].contiguous() for k, v in batch.items()}
+    out = L.forward({k: dev(v) for k, v in sub.items()})
+    lg, bs = O.atari_forward(params, sub['obs'], sub['reward'], sub['action'], emulate_bf16=True)
+    assert rel_l2(out['policy_logits'].cpu(), lg) < 5e-3 and rel_l2(out['baseline'].cpu(), bs) < 5e-3
+
+
 @pytest.mark.parametrize('T,B,optimizer', [(5, 6, 'rmsprop'), (5, 6, 'adam'), (3, 1, 'rmsprop'), (7, 19, 'rmsprop')])
 def test_learn_step_vs_emulating_oracle(T, B, optimizer):
     """Two consecutive steps.  Gradients are compared with the bf16-emulating oracle; the integrated
