@@ -193,6 +193,7 @@ struct srl_learner {
   float *core, *lstm_out, *dout, *dcore;   // [NF][H], [NF][H], [NB][H], [NB][H]
   char* lstm_arena;
   int64_t lstm_off0, lstm_len;    // LSTM gradient range inside the flat buffer
+  bool fused_front;               // frame conversion + conv1 + conv2 as one kernel (SRL_FUSED_FWD / srl_learner_set_option "fused_fwd")
   bool defer_finalize;            // conv_wgrad_finalize folded into the optimizer kernel (set around a fused forward_backward + apply)
   bool column_fusion;             // heads + V-trace/loss + dh in one column kernel (SRL_NO_COLUMN_FUSION / srl_learner_set_option)
   Profiler pf;                    // per-kernel event bracketing (off by default)
@@ -202,7 +203,7 @@ struct srl_learner {
 
 static const char* kSlotNames[PS_COUNT] = {"obs_s2d", "conv1_fwd", "conv2_fwd", "conv3_fwd", "fc_fwd", "head_fwd", "vtrace_loss_tail",
                                            "zero_grads", "head_bwd", "fc_wgrad", "fc_dgrad", "conv3_wgrad", "conv3_dgrad", "conv2_wgrad",
-                                           "conv2_dgrad", "conv1_wgrad", "conv_wgrad_finalize", "grad_norm", "optimizer", "pack_weights"};
+                                           "conv2_dgrad", "conv1_wgrad", "conv_wgrad_finalize", "grad_norm", "optimizer", "pack_weights", "enc_fused_fwd"};
 
 static int check_cfg(const srl_config_t* c) {
   REQ(c, "config is NULL");
@@ -233,6 +234,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   L->G = make_ptrs(grads, cfg->A);
   L->step = 0; L->have_fwd = false; L->defer_finalize = false;
   { const char* nf = getenv("SRL_NO_COLUMN_FUSION"); L->column_fusion = !(nf && atoi(nf) != 0); }   // read once, at creation
+  { const char* ff = getenv("SRL_FUSED_FWD"); L->fused_front = !(ff && atoi(ff) == 0); }
   for (int i = 0; i < 2 * PS_COUNT; ++i) L->events[i] = nullptr;
   for (int i = 0; i < PS_COUNT; ++i) L->slot_used[i] = false;
   const int64_t NF = (int64_t)(cfg->T + 1) * cfg->B, NB = (int64_t)cfg->T * cfg->B, A = cfg->A;
@@ -378,6 +380,7 @@ extern "C" int srl_learner_set_option(srl_learner_t* L, const char* name, int va
   REQ(L && name, "set_option: NULL argument");
   if (strcmp(name, "column_fusion") == 0) { L->column_fusion = value != 0; return 0; }
   if (strcmp(name, "defer_wgrad_finalize") == 0) { L->defer_finalize = value != 0; return 0; }
+  if (strcmp(name, "fused_fwd") == 0) { L->fused_front = value != 0; return 0; }
   return fail(SRL_EINVAL, "set_option: unknown option '%s'", name);
 }
 
@@ -451,7 +454,7 @@ static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStrea
     CU(launch_pack_weights(L->P, L->buf.wpack, st, L->buf.wpack_lo), "pack_weights");
     L->pf.e(PS_PACK);
   }
-  CU(encoder_forward(obs, frames, L->P, L->buf, L->maps, L->cfg.precision, st, L->pf, packed, &L->maps_lo), "encoder_forward");
+  CU(encoder_forward(obs, frames, L->P, L->buf, L->maps, L->cfg.precision, st, L->pf, packed, &L->maps_lo, L->fused_front), "encoder_forward");
   return 0;
 }
 

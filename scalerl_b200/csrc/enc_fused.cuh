@@ -1,0 +1,288 @@
+// Fused front of the encoder: u8 frame -> space-to-depth -> conv1 (8x8 s4, 4->32, ReLU) -> conv2 (4x4 s2, 32->64, ReLU), one
+// persistent kernel, one frame at a time per CTA, everything between the u8 frame and conv2's output kept on the SM
+// (reference: scalerl/algorithms/utils/atari_model.py:93-98: x.float()/255, relu(conv1), relu(conv2)).
+//
+// Replaces three dependent launches of the step's chain (obs_s2d_kernel, res_fwd_kernel<RConv1Fwd>, res_fwd_kernel<RConv2Fwd>)
+// and the HBM round trips between them; what the BACKWARD pass needs is still written out once: xs (the space-to-depth frame:
+// conv1 wgrad's operand) and a1 (conv2's wgrad operand and dgrad mask), plus a2, the input of conv3.
+//
+//   warp 8      producer: ONE cp.async.bulk (1-D TMA) per frame, 28,224 contiguous bytes of u8 -> shared memory, double-buffered
+//               (frame f+1 lands while frame f is being computed)
+//   warps 4-7   converters: u8 -> bf16 space-to-depth operand tile of conv1 (128 output positions + 22 halo rows of the 21x21
+//               grid, 64 channels (c,dy,dx), SWIZZLE_128B) written with generic stores + fence.proxy.async; two tiles in flight;
+//               the same values go to global `xs`
+//   warp 9      tcgen05.mma issuer: conv1 = 4 position tiles x (4 taps x 4 K-steps), N = 32, four TMEM accumulators; conv2 =
+//               8 taps x 4 K-steps, N = 64, reading conv1's output from SHARED memory (the two row-parity planes of the layout
+//               in res_problems.cuh, so a stride-2 tap is a row shift).  conv1 of frame f+1 is issued BEFORE conv2 of frame f,
+//               so the tensor pipe works while the epilogue warps turn conv1(f) into conv2's operand.
+//   warps 0-3   epilogues: TMEM -> registers -> (x/255 + b1, ReLU) -> bf16 -> shared a1 planes + global a1;  (+ b2, ReLU) -> global a2
+// The conv weights are converted from the fp32 master parameters inside the prologue (80 KB of bf16 per CTA, from L2), so the
+// kernel does not depend on pack_weights_kernel -- that kernel (needed by conv3 / fc) runs beside it.
+#pragma once
+#include "igemm_tma.cuh"
+#include "encoder_problems.cuh"
+
+namespace srl {
+
+constexpr int FF_THREADS = 320;
+constexpr int FF_W1_BYTES = 4 * 32 * 128;          // 4 taps x [32 co][64 k]
+constexpr int FF_W2_BYTES = 8 * 64 * 128;          // 8 taps x [64 co][64 k]
+constexpr int FF_U8_BYTES = 28 * 1024;             // one frame (28,224 B) rounded up
+constexpr int FF_X_BYTES = 19 * 1024;              // 150 rows x 128 B rounded up
+constexpr int FF_A1_PLANE = 13 * 1024;             // 100 rows x 128 B rounded up (13,312)
+constexpr int FF_A1_BYTES = 31 * 1024;             // plane 1 starts at 13,312; conv2 reads 139 rows of it -> 31,104 B
+constexpr int FF_OFF_W2 = FF_W1_BYTES;
+constexpr int FF_OFF_U8 = FF_OFF_W2 + FF_W2_BYTES;
+constexpr int FF_OFF_X = FF_OFF_U8 + 2 * FF_U8_BYTES;
+constexpr int FF_OFF_A1 = FF_OFF_X + 2 * FF_X_BYTES;
+constexpr int FF_OFF_BAR = FF_OFF_A1 + FF_A1_BYTES;
+constexpr int FF_SMEM_BYTES = FF_OFF_BAR + 256 + 1024;
+static_assert(FF_SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(FF_OFF_U8 % 1024 == 0 && FF_OFF_X % 1024 == 0 && FF_OFF_A1 % 1024 == 0, "swizzle atoms need 1024-byte aligned tiles");
+
+struct EncFusedParams {
+  const uint8_t* obs;        // [frames][4][84][84]
+  const float* w1;           // conv1.weight [32][4][8][8]   (fp32 master)
+  const float* b1;
+  const float* w2;           // conv2.weight [64][32][4][4]
+  const float* b2;
+  bf16* xs;                  // [frames*441][64]
+  bf16* a1;                  // [2 planes][NFS*100][64]
+  bf16* a2;                  // [frames*81][64]
+  int frames;
+  int NFS;                   // frame capacity of the a1 planes (plane stride)
+};
+
+SRL_DEVINL void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncFusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW1 = smem;
+  uint8_t* sW2 = smem + FF_OFF_W2;
+  uint8_t* sU8 = smem + FF_OFF_U8;
+  uint8_t* sX = smem + FF_OFF_X;
+  uint8_t* sA1 = smem + FF_OFF_A1;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FF_OFF_BAR);
+  uint64_t* u8_full = bars;            // [2] producer tx
+  uint64_t* u8_empty = bars + 2;       // [2] 4 converter warps
+  uint64_t* x_full = bars + 4;         // [2] 4 converter warps
+  uint64_t* x_empty = bars + 6;        // [2] tcgen05.commit
+  uint64_t* acc1_full = bars + 8;      // [4] tcgen05.commit
+  uint64_t* acc1_empty = bars + 12;    // [4] 4 epilogue warps
+  uint64_t* a1_full = bars + 16;       // 4 epilogue warps
+  uint64_t* a1_empty = bars + 17;      // tcgen05.commit
+  uint64_t* acc2_full = bars + 18;     // tcgen05.commit
+  uint64_t* acc2_empty = bars + 19;    // 4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nmine = p.frames > (int)blockIdx.x ? (p.frames - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) { mbar_init(&u8_full[i], 1); mbar_init(&u8_empty[i], 4); mbar_init(&x_full[i], 4); mbar_init(&x_empty[i], 1); }
+      for (int j = 0; j < 4; ++j) { mbar_init(&acc1_full[j], 1); mbar_init(&acc1_empty[j], 4); }
+      mbar_init(a1_full, 4); mbar_init(a1_empty, 1); mbar_init(acc2_full, 1); mbar_init(acc2_empty, 4);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);          // 4 x 32 columns (conv1 tiles) + 64 columns (conv2)
+  }
+  // the halo rows of the a1 planes that no epilogue ever writes (rows 100.. of plane 1) feed only discarded MMA rows: zero them once
+  for (int i = tid; i < (FF_A1_BYTES - 2 * FF_A1_PLANE) / 16; i += FF_THREADS)
+    reinterpret_cast<uint4*>(sA1 + 2 * FF_A1_PLANE)[i] = make_uint4(0, 0, 0, 0);
+  pdl_wait();                            // the parameters below were written by the previous step's optimizer kernel
+  pdl_launch();
+  // ---- conv weights: fp32 master -> bf16 K-major SWIZZLE_128B operand tiles (what pack_weights_kernel + TMA would deliver)
+  //  w1 tile j (= tap (kh2,kw2)): row co (32), k = c*16 + dy*4 + dx  <- W1[co][c][4kh2+dy][4kw2+dx]
+  for (int i = tid; i < 4 * 32 * 16; i += FF_THREADS) {          // item = (tap j, co, c, dy): 4 consecutive dx
+    const int j = i >> 9, r = i & 511, co = r >> 4, g = r & 15, c = g >> 2, dy = g & 3;
+    const float* src = p.w1 + co * 256 + c * 64 + (4 * (j >> 1) + dy) * 8 + 4 * (j & 1);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+    *reinterpret_cast<uint2*>(sW1 + j * 4096 + swz128(co, g >> 1) + (g & 1) * 8) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+  //  w2 tile j (= (kh, kww)): row co (64), k = kwl*32 + c (kw = 2kww + kwl)  <- W2[co][c][kh][kw]
+  for (int i = tid; i < 8 * 64 * 32; i += FF_THREADS) {          // item = (tap j, co, kwl, c pair)
+    const int j = i >> 11, r = i & 2047, co = r >> 5, q = r & 31, kwl = q >> 4, c = (q & 15) * 2;
+    const int kh = j >> 1, kw = 2 * (j & 1) + kwl;
+    const float v0 = __ldg(p.w2 + ((co * 32 + c) << 4) + kh * 4 + kw), v1 = __ldg(p.w2 + ((co * 32 + c + 1) << 4) + kh * 4 + kw);
+    const int k = kwl * 32 + c;                                   // element index inside the 64-wide K block
+    *reinterpret_cast<uint32_t*>(sW2 + j * 8192 + swz128(co, k >> 3) + (k & 7) * 2) = pack_bf16x2(v0, v1);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------------------------------------ producer
+    if (lane == 0) {
+      for (int it = 0; it < nmine; ++it) {
+        const int f = blockIdx.x + it * gridDim.x, ub = it & 1;
+        mbar_wait(&u8_empty[ub], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&u8_full[ub], 28224);
+        bulk_load_1d(sU8 + ub * FF_U8_BYTES, p.obs + (size_t)f * 28224, 28224, &u8_full[ub]);
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc_bf16(128, 32, 0, 0), idesc2 = make_idesc_bf16(128, 64, 0, 0);
+      const uint32_t w1 = smem_u32(sW1), w2 = smem_u32(sW2), a1s = smem_u32(sA1);
+      auto conv1 = [&](int it) {
+        for (int j = 0; j < 4; ++j) {
+          const int n = 4 * it + j, s = n & 1;
+          mbar_wait(&x_full[s], (n >> 1) & 1);
+          mbar_wait(&acc1_empty[j], (it & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t x0 = smem_u32(sX + s * FF_X_BYTES);
+#pragma unroll
+          for (int tap = 0; tap < 4; ++tap) {
+            const uint32_t a0 = x0 + ((tap >> 1) * 21 + (tap & 1)) * 128, b0 = w1 + tap * 4096;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + j * 32, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc1, (tap | k) != 0);
+          }
+          umma_commit(&x_empty[s]);
+          umma_commit(&acc1_full[j]);
+        }
+      };
+      if (nmine > 0) conv1(0);
+      for (int it = 0; it < nmine; ++it) {
+        if (it + 1 < nmine) conv1(it + 1);        // keep the tensor pipe busy while the epilogue warps build conv2's operand
+        mbar_wait(a1_full, it & 1);
+        mbar_wait(acc2_empty, (it & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int tap = 0; tap < 8; ++tap) {       // tap = (kh, kww): plane kh & 1, shift (kh >> 1) * 10 + kww
+          const uint32_t a0 = a1s + ((tap >> 1) & 1) * FF_A1_PLANE + ((tap >> 2) * 10 + (tap & 1)) * 128, b0 = w2 + tap * 8192;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + 128, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc2, (tap | k) != 0);
+        }
+        umma_commit(a1_empty);
+        umma_commit(acc2_full);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------------------------------------ converters (128 threads)
+    const int t = tid - 128;
+    for (int it = 0; it < nmine; ++it) {
+      const int f = blockIdx.x + it * gridDim.x, ub = it & 1;
+      mbar_wait(&u8_full[ub], (it >> 1) & 1);
+      const uint8_t* u8 = sU8 + ub * FF_U8_BYTES;
+      for (int j = 0; j < 4; ++j) {
+        const int n = 4 * it + j, s = n & 1;
+        mbar_wait(&x_empty[s], ((n >> 1) & 1) ^ 1);
+        uint8_t* x = sX + s * FF_X_BYTES;
+        for (int i = t; i < 150 * 16; i += 128) {          // item = (tile row, (c, dy)): the 4 dx bytes of one u32
+          const int row = i >> 4, g = i & 15, Q = j * 128 + row;
+          uint2 v = make_uint2(0u, 0u);
+          if (Q < 441) {
+            const int Y = Q / 21, X = Q - Y * 21;
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(u8 + (g >> 2) * 7056 + (4 * Y + (g & 3)) * 84 + 4 * X);
+            const float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - 8388608.f;
+            const float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - 8388608.f;
+            const float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388608.f;
+            const float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388608.f;
+            v = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3));
+            if (row < 128) *reinterpret_cast<uint2*>(p.xs + ((size_t)f * 441 + Q) * 64 + g * 4) = v;     // conv1 wgrad's operand
+          }
+          *reinterpret_cast<uint2*>(x + swz128(row, g >> 1) + (g & 1) * 8) = v;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x_full[s]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&u8_empty[ub]);
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------------ epilogues (warps 0-3)
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float b1r[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) b1r[c] = __ldg(p.b1 + c);
+    for (int it = 0; it < nmine; ++it) {
+      const int f = blockIdx.x + it * gridDim.x;
+      for (int j = 0; j < 4; ++j) {
+        mbar_wait(&acc1_full[j], it & 1);
+        tc_fence_after();
+        uint32_t r0[16], r1[16];
+        tmem_ld16(lane_base + j * 32, r0);
+        tmem_ld16(lane_base + j * 32 + 16, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc1_empty[j]);          // accumulator drained: conv1 of the next frame may reuse it
+        if (j == 0) mbar_wait(a1_empty, (it & 1) ^ 1);       // conv2 of the previous frame has finished reading the planes
+        const int Q = j * 128 + tid, oh = Q / 21, ow = Q - oh * 21;
+        if (Q < 441 && oh < 20 && ow < 20) {
+          float v[32];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            v[c] = fmaxf(fmaf(__uint_as_float(r0[c]), 1.0f / 255.0f, b1r[c]), 0.f);
+            v[16 + c] = fmaxf(fmaf(__uint_as_float(r1[c]), 1.0f / 255.0f, b1r[16 + c]), 0.f);
+          }
+          uint4 q[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            q[k] = make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]), pack_bf16x2(v[8 * k + 4], v[8 * k + 5]),
+                              pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+          const int prow = (oh >> 1) * 10 + (ow >> 1), half = ow & 1;      // plane oh & 1, channel (ow & 1) * 32 + c
+          uint8_t* pl = sA1 + (oh & 1) * FF_A1_PLANE;
+          uint4* gdst = reinterpret_cast<uint4*>(p.a1 + ((size_t)(oh & 1) * p.NFS * 100 + (size_t)f * 100 + prow) * 64 + half * 32);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            *reinterpret_cast<uint4*>(pl + swz128(prow, half * 4 + k)) = q[k];
+            gdst[k] = q[k];
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a1_full);
+      // ---- conv2 epilogue
+      mbar_wait(acc2_full, it & 1);
+      tc_fence_after();
+      const int oh2 = tid / 10, ow2 = tid - oh2 * 10;
+      const bool ok = tid < 100 && oh2 < 9 && ow2 < 9;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(lane_base + 128 + c0, r);
+        tmem_ld_wait();
+        if (c0 == 48) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc2_empty);
+        }
+        if (ok) {
+          float v[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] = fmaxf(__uint_as_float(r[c]) + __ldg(p.b2 + c0 + c), 0.f);
+          store_bf16x16(p.a2 + ((size_t)f * 81 + oh2 * 9 + ow2) * 64 + c0, v);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+inline cudaError_t enc_fused_fwd_launch(const EncFusedParams& p, int max_ctas, cudaStream_t stream) {
+  if (p.frames <= 0) return cudaSuccess;
+  static PerDeviceOnce once;
+  { cudaError_t e = ensure_max_dynamic_smem(once, enc_fused_fwd_kernel, FF_SMEM_BYTES); if (e != cudaSuccess) return e; }
+  const int grid = p.frames < max_ctas ? p.frames : max_ctas;
+  return launch_chain<PDL_RESFWD>(enc_fused_fwd_kernel, dim3(grid), dim3(FF_THREADS), FF_SMEM_BYTES, stream, p);
+}
+
+}  // namespace srl

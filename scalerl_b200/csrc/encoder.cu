@@ -2,6 +2,7 @@
 #include "encoder_problems.cuh"
 #include "tma_problems.cuh"
 #include "res_problems.cuh"
+#include "enc_fused.cuh"
 #include "kernels.h"
 #include <initializer_list>
 #include <stdlib.h>
@@ -236,19 +237,27 @@ __global__ void __launch_bounds__(256) conv_wgrad_finalize_kernel(float* __restr
 }
 
 cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, const EncoderBuffers& buf, const TmaMaps& maps, int mode,
-                            cudaStream_t st, const Profiler& pf, cudaEvent_t wait_before_conv1, const TmaMapsLo* lo) {
+                            cudaStream_t st, const Profiler& pf, cudaEvent_t wait_before_conv1, const TmaMapsLo* lo, bool fused_front) {
   if (frames <= 0) return cudaSuccess;
   if ((mode != 0 && mode != 1) || !maps.valid) return cudaErrorInvalidValue;
   const int sp = mode;                                    // 1: fp32-accurate split operands
   TmaMapsLo dummy;                                        // bf16 mode: the low maps are never touched by the kernels
   if (sp && (!lo || !lo->valid)) return cudaErrorInvalidValue;
   const TmaMapsLo& L = sp ? *lo : dummy;
+  // bf16 mode: frame conversion + conv1 + conv2 as ONE persistent kernel (enc_fused.cuh); SRL_FUSED_FWD=0 or the fp32-accurate
+  // operand mode use the three separate kernels
+  if (fused_front && !sp && (reinterpret_cast<uintptr_t>(obs) & 15) == 0) {
+    EncFusedParams q{obs, p.w1, p.b1, p.w2, p.b2, buf.xs, buf.a1, buf.a2, frames, buf.NF};
+    pf.b(PS_ENC_FUSED); SRL_TRY(enc_fused_fwd_launch(q, kPersistentCtas, st)); pf.e(PS_ENC_FUSED);
+    if (wait_before_conv1) SRL_TRY(cudaStreamWaitEvent(st, wait_before_conv1, 0));      // conv3 / fc read the packed weights
+  } else {
   pf.b(PS_S2D); SRL_TRY(launch_s2d(obs, frames, buf.xs, st)); pf.e(PS_S2D);
   if (wait_before_conv1) SRL_TRY(cudaStreamWaitEvent(st, wait_before_conv1, 0));
   { RConv1Fwd::Params q{maps.xs_w, maps.w1k, L.w1k, p.b1, buf.a1, buf.a1_lo, frames, buf.NF};
     pf.b(PS_CONV1_FWD); SRL_TRY(res_fwd_launch<RConv1Fwd>(q, cdiv(frames * 441, 128), 2 * kPersistentCtas, st, sp)); pf.e(PS_CONV1_FWD); }
   { RConv2Fwd::Params q{maps.a1p0_w, maps.a1p1_w, maps.w2k, L.a1p0_w, L.a1p1_w, L.w2k, p.b2, buf.a2, buf.a2_lo, frames};
     pf.b(PS_CONV2_FWD); SRL_TRY(res_fwd_launch<RConv2Fwd>(q, cdiv(frames * 100, 128), kPersistentCtas, st, sp)); pf.e(PS_CONV2_FWD); }
+  }
   { RConv3Fwd::Params q{maps.a2_w, maps.w3k, L.a2_w, L.w3k, p.b3, buf.a3, buf.a3_lo, frames};
     pf.b(PS_CONV3_FWD); SRL_TRY(res_fwd_launch<RConv3Fwd>(q, cdiv(frames * 81, 128), kPersistentCtas, st, sp)); pf.e(PS_CONV3_FWD); }
   { TFcFwd::Params q{maps.a3m128, maps.wfk, L.a3m128, L.wfk, buf.hpart, frames};

@@ -411,6 +411,25 @@ SRL_DEVINL float wgrad_ws_take(float* ws, int layer, int e) {
   return v;
 }
 
+// grid-stride over the 19,456 float4 groups of the three conv weight gradients: workspace -> g (PyTorch layout), returns the
+// thread's partial sum of squares
+__device__ __noinline__ float fold_conv_wgrads(const WgradFold fold, float* g, int64_t i0, int64_t stride) {
+  float s = 0.f;
+  for (int64_t q = i0; q < (8192 + 32768 + 36864) / 4; q += stride) {
+    int layer, e;
+    int64_t off;
+    if (q < 2048) { layer = 1; e = (int)q * 4; off = fold.off_w1; }
+    else if (q < 2048 + 8192) { layer = 2; e = (int)(q - 2048) * 4; off = fold.off_w2; }
+    else { layer = 3; e = (int)(q - 2048 - 8192) * 4; off = fold.off_w3; }
+    float4 v;
+    v.x = wgrad_ws_take(fold.ws, layer, e); v.y = wgrad_ws_take(fold.ws, layer, e + 1);
+    v.z = wgrad_ws_take(fold.ws, layer, e + 2); v.w = wgrad_ws_take(fold.ws, layer, e + 3);
+    *reinterpret_cast<float4*>(g + off + e) = v;          // the gradient tensors end up complete, as after the finalize kernel
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  return s;
+}
+
 template <int OPT>
 __global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s0,
                                                          float* __restrict__ s1, int64_t n, float max_norm, float* __restrict__ coef,
@@ -420,22 +439,14 @@ __global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, 
   const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int t = dstep ? *dstep + 1 : step;          // 1-based step count: Adam bias correction; counted for RMSprop too (checkpoints)
   float s = 0.f;
+  // conv_wgrad_finalize folded in: the 77,824 conv weight gradients come from the wgrad workspace (out of line: keeps the register
+  // count -- and with it two resident blocks per SM -- of the two streaming passes below)
+  if (fold.ws) s = fold_conv_wgrads(fold, g, i0, stride);
   for (int64_t i = i0; i < n4; i += stride) {
-    float4 v;
     const int64_t e0 = 4 * i;
-    int layer = 0, e = 0;
-    if (fold.ws) {            // conv weight gradients come from the wgrad workspace (conv_wgrad_finalize folded in)
-      if (e0 >= fold.off_w1 && e0 < fold.off_w1 + 8192) { layer = 1; e = (int)(e0 - fold.off_w1); }
-      else if (e0 >= fold.off_w2 && e0 < fold.off_w2 + 32768) { layer = 2; e = (int)(e0 - fold.off_w2); }
-      else if (e0 >= fold.off_w3 && e0 < fold.off_w3 + 36864) { layer = 3; e = (int)(e0 - fold.off_w3); }
-    }
-    if (layer) {
-      v.x = wgrad_ws_take(fold.ws, layer, e); v.y = wgrad_ws_take(fold.ws, layer, e + 1);
-      v.z = wgrad_ws_take(fold.ws, layer, e + 2); v.w = wgrad_ws_take(fold.ws, layer, e + 3);
-      reinterpret_cast<float4*>(g)[i] = v;          // the gradient tensors end up complete, as after the finalize kernel
-    } else {
-      v = reinterpret_cast<const float4*>(g)[i];
-    }
+    if (fold.ws && ((e0 >= fold.off_w1 && e0 < fold.off_w1 + 8192) || (e0 >= fold.off_w2 && e0 < fold.off_w2 + 32768) ||
+                    (e0 >= fold.off_w3 && e0 < fold.off_w3 + 36864))) continue;          // summed by fold_conv_wgrads
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
     s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = g[n4 * 4 + threadIdx.x]; s += v * v; }

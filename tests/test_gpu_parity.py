@@ -216,6 +216,27 @@ def test_forward_vs_emulating_oracle(T, B):
     assert rel_l2(out['policy_logits'].cpu(), lg32) < 2e-2
 
 
+@pytest.mark.parametrize('T,B', [(4, 5), (1, 1), (20, 32), (3, 50)])
+def test_fused_encoder_front_equals_three_kernels(T, B):
+    """enc_fused_fwd_kernel (u8 -> space-to-depth -> conv1 -> conv2 on the SM) writes the SAME bits as obs_s2d + conv1 + conv2: xs, both
+    a1 planes, a2 -- same MMA sequence per tile, same epilogue arithmetic -- and the whole step downstream is unchanged"""
+    A = 6
+    batch = {k: dev(v) for k, v in O.synthetic_batch(T, B, A, seed=9).items()}
+    got = {}
+    for fused in (1, 0):
+        L, _ = _learner(T, B, A, 2, learning_rate=0.0)
+        L.set_option('fused_fwd', fused)
+        L.use_graph = False
+        st = L.learn(batch)
+        got[fused] = (L.debug_buffer('xs'), L.debug_buffer('a1'), L.debug_buffer('a2'), L.debug_buffer('logits'), L.flat_grads.clone(), st)
+        L.close()
+    for i, nm in enumerate(('xs', 'a1', 'a2')):
+        assert torch.equal(got[1][i], got[0][i]), nm
+    assert torch.equal(got[1][3], got[0][3])
+    assert rel_l2(got[1][4].cpu(), got[0][4].cpu()) < 1e-5          # wgrad atomics order
+    assert abs(got[1][5]['total_loss'] - got[0][5]['total_loss']) <= 1e-6 * max(1.0, abs(got[0][5]['total_loss']))
+
+
 @pytest.mark.parametrize('rows', [1, 3])
 def test_forward_with_fewer_rows_than_the_context_holds(rows):
     """srl_learner_forward(rows < T+1) (the actor-inference use): round 1 strided conv1's output planes by the rows of the CALL

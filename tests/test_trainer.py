@@ -140,7 +140,7 @@ def test_pipelined_loop_equals_synchronous_learner(tmp_path, use_lstm):
         assert abs(all_stats[k]['total_loss'] - ref_stats[k - 1]['total_loss']) <= 1e-2 * max(1.0, abs(ref_stats[k - 1]['total_loss'])), k
         assert all_stats[k]['episode_returns'] == ref_stats[k - 1]['episode_returns']
     for n, v in ref.state_dict().items():
-        assert rel_l2(t.learner.params[n].cpu(), v.cpu()) < 2e-3, n
+        assert rel_l2(t.learner.params[n].cpu(), v.cpu()) < 1e-2, n       # two learners drift by fp32 summation order; see above
         assert torch.equal(t.actor_model.state_dict()[n], t.learner.params[n].cpu()), n     # published == learner
 
 
