@@ -39,7 +39,7 @@ T_DEFAULT, B_DEFAULT, A_DEFAULT = 20, 32, 6
 POOL = 8   # distinct batches cycled through: 8 x 19.5 MB = 156 MB > 126 MB L2, so a step's inputs are never L2-resident
 
 # algorithmic MACs per frame: conv1, conv2, conv3, fc
-MACS = {'conv1': 3276800, 'conv2': 2654208, 'conv3': 1806336, 'fc': 1605632}
+MACS = {'conv1': 3276800, 'conv2': 2654208, 'conv3': 1806336, 'fc': 1605632, 'conv1+conv2': 3276800 + 2654208}
 # Algorithmic HBM bytes per frame of each GEMM kernel: every operand read once and every result written once at the
 # storage precision (bf16 activations / gradients; xs = space-to-depth frame 21x21x64, a1 20x20x32, a2 9x9x64,
 # a3 7x7x64, h 512).  The dgrads also read the forward activation for the ReLU mask.  (fixed bytes: weights.)
@@ -48,11 +48,13 @@ SLOT_BYTES = {   # slot -> (bytes per frame, fixed bytes per launch)
     'conv1_fwd': (_XS + _A1, 8192 * 2), 'conv2_fwd': (_A1 + _A2, 32768 * 2), 'conv3_fwd': (_A2 + _A3, 36864 * 2),
     'fc_fwd': (_A3 + 512 * 4, 1605632 * 2), 'fc_dgrad': (_H + 2 * _A3, 1605632 * 2), 'fc_wgrad': (_H + _A3, 1605632 * 4),
     'conv3_dgrad': (_A3 + 2 * _A2, 36864 * 2), 'conv3_wgrad': (_A2 + _A3, 36864 * 4),
-    'conv2_dgrad': (_A2 + 2 * _A1, 32768 * 2), 'conv2_wgrad': (_A1 + _A2, 32768 * 4), 'conv1_wgrad': (_XS + _A1, 8192 * 4)}
+    'conv2_dgrad': (_A2 + 2 * _A1, 32768 * 2), 'conv2_wgrad': (_A1 + _A2, 32768 * 4), 'conv1_wgrad': (_XS + _A1, 8192 * 4),
+    # fused front (u8 frame -> space-to-depth -> conv1 -> conv2): reads the u8 frame once, writes xs / a1 (for the backward) and a2
+    'enc_fused_fwd': (28224 + _XS + _A1 + _A2, (8192 + 32768) * 4)}
 SLOT_FLOPS = {  # slot -> (MACs per frame, frames = 'fwd' (T+1)*B or 'bwd' T*B)
     'conv1_fwd': ('conv1', 'fwd'), 'conv2_fwd': ('conv2', 'fwd'), 'conv3_fwd': ('conv3', 'fwd'), 'fc_fwd': ('fc', 'fwd'),
     'fc_wgrad': ('fc', 'bwd'), 'fc_dgrad': ('fc', 'bwd'), 'conv3_wgrad': ('conv3', 'bwd'), 'conv3_dgrad': ('conv3', 'bwd'),
-    'conv2_wgrad': ('conv2', 'bwd'), 'conv2_dgrad': ('conv2', 'bwd'), 'conv1_wgrad': ('conv1', 'bwd')}
+    'conv2_wgrad': ('conv2', 'bwd'), 'conv2_dgrad': ('conv2', 'bwd'), 'conv1_wgrad': ('conv1', 'bwd'), 'enc_fused_fwd': ('conv1+conv2', 'fwd')}
 
 
 def peaks():
@@ -264,6 +266,7 @@ def _main(real_stdout):
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU-baseline work (rank 0, N=1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the other_configs / per_sampler measurements')
+    ap.add_argument('--publish-every', type=int, default=1, help='weight publish cadence of the end-to-end loop (reference: every step)')
     ap.add_argument('--use-lstm', action='store_true', help='AtariNet(use_lstm=True) learner (BASELINE.json configs[4]: use with --T 100)')
     args = ap.parse_args()
     if args.warmup < 3:
@@ -376,7 +379,7 @@ def _main(real_stdout):
     from scalerl_b200.algorithms.impala.impala_atari import ImpalaArguments, ImpalaTrainer
     from scalerl_b200.data.slot_queue import SlotQueue
     targs = ImpalaArguments(num_actors=1, batch_size=B, rollout_length=T, num_buffers=POOL * B, num_actions=A, use_lstm=args.use_lstm,
-                            output_dir=tempfile.mkdtemp(prefix='srl_bench_'), disable_checkpoint=True, stats_lag=2)
+                            output_dir=tempfile.mkdtemp(prefix='srl_bench_'), disable_checkpoint=True, stats_lag=2, publish_every=args.publish_every)
     trainer = ImpalaTrainer(targs, learner=learner)
     for i, hb in enumerate(host_pool):                      # slot i*B + b = column b of pool batch i (what B actors would have written)
         for b in range(B):
@@ -439,12 +442,12 @@ def _main(real_stdout):
         nfr = NF if which == 'fwd' else NBk
         fl = 2.0 * MACS[layer] * nfr
         by = SLOT_BYTES[slot][0] * nfr + SLOT_BYTES[slot][1]
-        ms = per_kernel_ms[slot]
+        ms = per_kernel_ms.get(slot, 0.0)
         gemm[slot] = {'ms': ms, 'gflop': fl / 1e9, 'tflops': fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, 'bytes': by,
                       'gbs': by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0, 'intensity': fl / by,
                       'bound': 'tensor' if fl / by >= ridge else 'hbm'}
     # dominant kernel = the longest GEMM on the step's critical chain (fc/conv3/conv2 wgrad run on side branches beside it)
-    CHAIN = ('conv1_fwd', 'conv2_fwd', 'conv3_fwd', 'fc_fwd', 'fc_dgrad', 'conv3_dgrad', 'conv2_dgrad', 'conv1_wgrad')
+    CHAIN = ('enc_fused_fwd', 'conv1_fwd', 'conv2_fwd', 'conv3_fwd', 'fc_fwd', 'fc_dgrad', 'conv3_dgrad', 'conv2_dgrad', 'conv1_wgrad')
     dom = max(CHAIN, key=lambda s: gemm[s]['ms'])
     traffic, traffic_src, tensor_pct = None, None, None
     tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
@@ -632,7 +635,7 @@ def _main(real_stdout):
                        'api': 'ImpalaTrainer.get_batch + ImpalaTrainer.learn (pinned shared-memory trajectory ring -> device, step, lagged stats, '
                               'asynchronous versioned weight publish into the shared actor parameters)',
                        'weights_published': published, 'last_total_loss': tstats['total_loss'], 'host_ms_per_step': tr_host_ms,
-                       'stats_lag_steps': targs.stats_lag,
+                       'stats_lag_steps': targs.stats_lag, 'publish_every': targs.publish_every,
                        'feeder_value': e2e_value, 'feeder_ms_per_step': e2e_s / K * 1e3, 'feeder_h2d_bytes_per_step': feeder.h2d_bytes,
                        'feeder_api': 'HostBatchFeeder.submit/learn/result (time-major pinned batches, no ring, no weight publish: round-1 e2e)',
                        'h2d_only_ms_per_step': h2d_only_ms, 'eager_launch_ms_per_step': e2e_eager_ms},

@@ -123,10 +123,6 @@ int srl_learner_set_config(srl_learner_t* L, const srl_config_t* cfg);
 
 /* run-time switches of one learner context: "column_fusion" (default 1; 0 = three kernels head_fwd / impala_tail / head_bwd
  * instead of the fused column kernel -- the environment variable SRL_NO_COLUMN_FUSION is read once, at creation);
- * "defer_wgrad_finalize" (default 0): set to 1 around srl_learner_forward_backward* IMMEDIATELY followed by
- * srl_learner_apply_gradients on the same stream -- the backward then skips the kernel that writes the conv weight gradients in
- * PyTorch layout and the optimizer's first pass takes them from the wgrad workspace (one launch less on the step's critical chain);
- * with 0 the gradient buffer is complete when srl_learner_forward_backward* returns (all-reduce it, inspect it, ...);
  * "fused_fwd" (default 1, SRL_FUSED_FWD): u8 frame conversion + conv1 + conv2 as ONE persistent kernel (bf16 mode), 0 = three. */
 int srl_learner_set_option(srl_learner_t* L, const char* name, int value);
 

@@ -194,7 +194,6 @@ struct srl_learner {
   char* lstm_arena;
   int64_t lstm_off0, lstm_len;    // LSTM gradient range inside the flat buffer
   bool fused_front;               // frame conversion + conv1 + conv2 as one kernel (SRL_FUSED_FWD / srl_learner_set_option "fused_fwd")
-  bool defer_finalize;            // conv_wgrad_finalize folded into the optimizer kernel (set around a fused forward_backward + apply)
   bool column_fusion;             // heads + V-trace/loss + dh in one column kernel (SRL_NO_COLUMN_FUSION / srl_learner_set_option)
   Profiler pf;                    // per-kernel event bracketing (off by default)
   cudaEvent_t events[2 * PS_COUNT];
@@ -232,7 +231,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   L->lstm = nullptr; L->lstm_arena = nullptr; L->core = L->lstm_out = L->dout = L->dcore = nullptr; L->lstm_off0 = L->lstm_len = 0;
   L->P = make_ptrs(params, cfg->A);
   L->G = make_ptrs(grads, cfg->A);
-  L->step = 0; L->have_fwd = false; L->defer_finalize = false;
+  L->step = 0; L->have_fwd = false;
   { const char* nf = getenv("SRL_NO_COLUMN_FUSION"); L->column_fusion = !(nf && atoi(nf) != 0); }   // read once, at creation
   { const char* ff = getenv("SRL_FUSED_FWD"); L->fused_front = !(ff && atoi(ff) == 0); }
   for (int i = 0; i < 2 * PS_COUNT; ++i) L->events[i] = nullptr;
@@ -379,7 +378,6 @@ extern "C" int srl_learner_set_config(srl_learner_t* L, const srl_config_t* cfg)
 extern "C" int srl_learner_set_option(srl_learner_t* L, const char* name, int value) {
   REQ(L && name, "set_option: NULL argument");
   if (strcmp(name, "column_fusion") == 0) { L->column_fusion = value != 0; return 0; }
-  if (strcmp(name, "defer_wgrad_finalize") == 0) { L->defer_finalize = value != 0; return 0; }
   if (strcmp(name, "fused_fwd") == 0) { L->fused_front = value != 0; return 0; }
   return fail(SRL_EINVAL, "set_option: unknown option '%s'", name);
 }
@@ -513,7 +511,7 @@ static int fb_begin(srl_learner* L, const uint8_t* obs, const float* reward, con
                        L->G.bb, st, sw, !fused, L->buf.dh_lo), "head_bwd");      // side stream `side` is joined by encoder_backward (after the fc wgrad)
   }
   L->pf.e(PS_HEAD_BWD);
-  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.precision, st, L->pf, L->ss, phase, &L->maps_lo, !L->defer_finalize), "encoder_backward");
+  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.precision, st, L->pf, L->ss, phase, &L->maps_lo), "encoder_backward");
   L->have_fwd = true;
   return 0;
 }
@@ -540,7 +538,7 @@ extern "C" int srl_learner_backward_finish(srl_learner_t* L, const uint8_t* obs,
   const srl_config_t& c = L->cfg;
   L->pf.st = (cudaStream_t)stream;
   pdl_set_active(!L->pf.on);
-  CU(encoder_backward(obs, c.T * c.B, L->buf, L->G, L->maps, c.precision, (cudaStream_t)stream, L->pf, L->ss, 1, &L->maps_lo, !L->defer_finalize), "encoder_backward");
+  CU(encoder_backward(obs, c.T * c.B, L->buf, L->G, L->maps, c.precision, (cudaStream_t)stream, L->pf, L->ss, 1, &L->maps_lo), "encoder_backward");
   return 0;
 }
 
@@ -588,7 +586,7 @@ extern "C" int srl_learner_forward_backward_lstm(srl_learner_t* L, const uint8_t
   rc = srl_lstm_backward(L->lstm, L->dout, done, L->dcore, st);
   if (rc) return fail(rc, "lstm_backward: %s", srl_lstm_last_error());
   CU(launch_dcore_to_dh(L->dcore, L->buf.h, NB, c.A, L->buf.dh, st), "dcore_to_dh");
-  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.precision, st, L->pf, L->ss, 2, &L->maps_lo, !L->defer_finalize), "encoder_backward");
+  CU(encoder_backward(obs, NB, L->buf, L->G, L->maps, c.precision, st, L->pf, L->ss, 2, &L->maps_lo), "encoder_backward");
   L->have_fwd = true;
   return 0;
 }
@@ -601,18 +599,12 @@ extern "C" int srl_learner_apply_gradients(srl_learner_t* L, float* grad_norm_ou
   L->step += 1;
   // clip_grad_norm_ + optimizer in one cooperative kernel (profile slot: optimizer)
   L->pf.b(PS_OPTIMIZER);
-  WgradFold fold{nullptr, 0, 0, 0};
-  if (L->defer_finalize) {        // the backward skipped conv_wgrad_finalize: pass 1 of the optimizer reads the workspace
-    int64_t off[12];
-    layout(c.A, off, nullptr);
-    fold = WgradFold{L->buf.wgrad_ws, off[0], off[2], off[4]};
-  }
   if (c.optimizer == 0) {
     CU(launch_clip_optim(0, L->params, L->grads, L->opt0, nullptr, L->nparams, c.max_grad_norm, L->coef, L->scratch + 2048, c.learning_rate,
-                         c.alpha, 0.f, c.epsilon, L->step, L->dstep, st, fold), "clip+rmsprop");
+                         c.alpha, 0.f, c.epsilon, L->step, L->dstep, st), "clip+rmsprop");
   } else {
     CU(launch_clip_optim(1, L->params, L->grads, L->opt0, L->opt1, L->nparams, c.max_grad_norm, L->coef, L->scratch + 2048, c.learning_rate,
-                         c.adam_beta1, c.adam_beta2, c.adam_eps, L->step, L->dstep, st, fold), "clip+adam");
+                         c.adam_beta1, c.adam_beta2, c.adam_eps, L->step, L->dstep, st), "clip+adam");
   }
   L->pf.e(PS_OPTIMIZER);
   if (grad_norm_out) CU(cudaMemcpyAsync(grad_norm_out, L->coef, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy coef");

@@ -6,12 +6,12 @@
 // and the HBM round trips between them; what the BACKWARD pass needs is still written out once: xs (the space-to-depth frame:
 // conv1 wgrad's operand) and a1 (conv2's wgrad operand and dgrad mask), plus a2, the input of conv3.
 //
-//   warp 8      producer: ONE cp.async.bulk (1-D TMA) per frame, 28,224 contiguous bytes of u8 -> shared memory, double-buffered
+//   warp 12     producer: ONE cp.async.bulk (1-D TMA) per frame, 28,224 contiguous bytes of u8 -> shared memory, double-buffered
 //               (frame f+1 lands while frame f is being computed)
-//   warps 4-7   converters: u8 -> bf16 space-to-depth operand tile of conv1 (128 output positions + 22 halo rows of the 21x21
+//   warps 4-11  converters: u8 -> bf16 space-to-depth operand tile of conv1 (128 output positions + 22 halo rows of the 21x21
 //               grid, 64 channels (c,dy,dx), SWIZZLE_128B) written with generic stores + fence.proxy.async; two tiles in flight;
 //               the same values go to global `xs`
-//   warp 9      tcgen05.mma issuer: conv1 = 4 position tiles x (4 taps x 4 K-steps), N = 32, four TMEM accumulators; conv2 =
+//   warp 13     tcgen05.mma issuer: conv1 = 4 position tiles x (4 taps x 4 K-steps), N = 32, four TMEM accumulators; conv2 =
 //               8 taps x 4 K-steps, N = 64, reading conv1's output from SHARED memory (the two row-parity planes of the layout
 //               in res_problems.cuh, so a stride-2 tap is a row shift).  conv1 of frame f+1 is issued BEFORE conv2 of frame f,
 //               so the tensor pipe works while the epilogue warps turn conv1(f) into conv2's operand.
@@ -24,7 +24,8 @@
 
 namespace srl {
 
-constexpr int FF_THREADS = 320;
+constexpr int FF_THREADS = 448;          // warps 0-3 epilogues, 4-11 converters, 12 producer, 13 MMA issuer
+constexpr int FF_CONV_WARPS = 8;
 constexpr int FF_W1_BYTES = 4 * 32 * 128;          // 4 taps x [32 co][64 k]
 constexpr int FF_W2_BYTES = 8 * 64 * 128;          // 8 taps x [64 co][64 k]
 constexpr int FF_U8_BYTES = 28 * 1024;             // one frame (28,224 B) rounded up
@@ -81,9 +82,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nmine = p.frames > (int)blockIdx.x ? (p.frames - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  if (warp == 8) {
+  if (warp == 12) {
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) { mbar_init(&u8_full[i], 1); mbar_init(&u8_empty[i], 4); mbar_init(&x_full[i], 4); mbar_init(&x_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&u8_full[i], 1); mbar_init(&u8_empty[i], FF_CONV_WARPS); mbar_init(&x_full[i], FF_CONV_WARPS); mbar_init(&x_empty[i], 1); }
       for (int j = 0; j < 4; ++j) { mbar_init(&acc1_full[j], 1); mbar_init(&acc1_empty[j], 4); }
       mbar_init(a1_full, 4); mbar_init(a1_empty, 1); mbar_init(acc2_full, 1); mbar_init(acc2_empty, 4);
       mbar_fence_init();
@@ -96,21 +97,45 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
     reinterpret_cast<uint4*>(sA1 + 2 * FF_A1_PLANE)[i] = make_uint4(0, 0, 0, 0);
   pdl_wait();                            // the parameters below were written by the previous step's optimizer kernel
   pdl_launch();
-  // ---- conv weights: fp32 master -> bf16 K-major SWIZZLE_128B operand tiles (what pack_weights_kernel + TMA would deliver)
-  //  w1 tile j (= tap (kh2,kw2)): row co (32), k = c*16 + dy*4 + dx  <- W1[co][c][4kh2+dy][4kw2+dx]
-  for (int i = tid; i < 4 * 32 * 16; i += FF_THREADS) {          // item = (tap j, co, c, dy): 4 consecutive dx
-    const int j = i >> 9, r = i & 511, co = r >> 4, g = r & 15, c = g >> 2, dy = g & 3;
-    const float* src = p.w1 + co * 256 + c * 64 + (4 * (j >> 1) + dy) * 8 + 4 * (j & 1);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src));
-    *reinterpret_cast<uint2*>(sW1 + j * 4096 + swz128(co, g >> 1) + (g & 1) * 8) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  // ---- conv weights: fp32 master -> bf16 K-major SWIZZLE_128B operand tiles (what pack_weights_kernel + TMA would deliver).
+  //      Read in memory order as float4 (coalesced), several loads in flight per thread, scattered into the tiles.
+  //  w1 tile j (= tap (kh2,kw2)): row co (32), k = c*16 + dy*4 + dx  <- W1[co][c][4kh2+dy][4kw2+dx]; a float4 = the 4 dx of one (co,c,kh,kw2)
+  {
+    constexpr int NQ = 2048, U = 5;                      // 2048 float4 / 448 threads -> 5 each
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int q = tid + u * FF_THREADS; if (q < NQ) v[u] = __ldg(reinterpret_cast<const float4*>(p.w1) + q); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = tid + u * FF_THREADS;
+      if (q < NQ) {
+        const int co = q >> 6, c = (q >> 4) & 3, kh = (q >> 1) & 7, j = (kh >> 2) * 2 + (q & 1), g = c * 4 + (kh & 3);
+        *reinterpret_cast<uint2*>(sW1 + j * 4096 + swz128(co, g >> 1) + (g & 1) * 8) = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
+      }
+    }
   }
-  //  w2 tile j (= (kh, kww)): row co (64), k = kwl*32 + c (kw = 2kww + kwl)  <- W2[co][c][kh][kw]
-  for (int i = tid; i < 8 * 64 * 32; i += FF_THREADS) {          // item = (tap j, co, kwl, c pair)
-    const int j = i >> 11, r = i & 2047, co = r >> 5, q = r & 31, kwl = q >> 4, c = (q & 15) * 2;
-    const int kh = j >> 1, kw = 2 * (j & 1) + kwl;
-    const float v0 = __ldg(p.w2 + ((co * 32 + c) << 4) + kh * 4 + kw), v1 = __ldg(p.w2 + ((co * 32 + c + 1) << 4) + kh * 4 + kw);
-    const int k = kwl * 32 + c;                                   // element index inside the 64-wide K block
-    *reinterpret_cast<uint32_t*>(sW2 + j * 8192 + swz128(co, k >> 3) + (k & 7) * 2) = pack_bf16x2(v0, v1);
+  //  w2 tile j (= (kh, kww)): row co (64), k = kwl*32 + c (kw = 2kww + kwl)  <- W2[co][c][kh][kw]; a float4 = the 4 kw of one (co,c,kh)
+  {
+    constexpr int NQ = 8192, U = 10;                     // two rounds of 10 loads in flight per thread
+#pragma unroll 1
+    for (int base = 0; base < NQ; base += U * FF_THREADS) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const int q = base + tid + u * FF_THREADS; if (q < NQ) v[u] = __ldg(reinterpret_cast<const float4*>(p.w2) + q); }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int q = base + tid + u * FF_THREADS;
+        if (q < NQ) {
+          const int co = q >> 7, c = (q >> 2) & 31, kh = q & 3;
+          const float w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int kw = 0; kw < 4; ++kw) {
+            const int j = kh * 2 + (kw >> 1), k = (kw & 1) * 32 + c;
+            *reinterpret_cast<__nv_bfloat16*>(sW2 + j * 8192 + swz128(co, k >> 3) + (k & 7) * 2) = __float2bfloat16_rn(w[kw]);
+          }
+        }
+      }
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -118,7 +143,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == 12) {
     // ------------------------------------------------------------------------------------------------ producer
     if (lane == 0) {
       for (int it = 0; it < nmine; ++it) {
@@ -128,7 +153,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
         bulk_load_1d(sU8 + ub * FF_U8_BYTES, p.obs + (size_t)f * 28224, 28224, &u8_full[ub]);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // ------------------------------------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc1 = make_idesc_bf16(128, 32, 0, 0), idesc2 = make_idesc_bf16(128, 64, 0, 0);
@@ -169,30 +194,38 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------------------------------------ converters (128 threads)
-    const int t = tid - 128;
+    // ------------------------------------------------------------------------------------------------ converters (256 threads)
+    // thread = (16-byte half-chunk g = (c, dy), row slot rb); rows rb, rb + 16, ... of the 150-row tile: one u32 (4 dx bytes) -> 4 bf16
+    const int t = tid - 128, g = t & 15, rb = t >> 4;
+    const int src_g = (g >> 2) * 7056 + (g & 3) * 84;              // (c, dy) offset inside the u8 frame
     for (int it = 0; it < nmine; ++it) {
       const int f = blockIdx.x + it * gridDim.x, ub = it & 1;
       mbar_wait(&u8_full[ub], (it >> 1) & 1);
-      const uint8_t* u8 = sU8 + ub * FF_U8_BYTES;
+      const uint8_t* u8 = sU8 + ub * FF_U8_BYTES + src_g;
+      bf16* xs_f = p.xs + (size_t)f * 441 * 64 + g * 4;
       for (int j = 0; j < 4; ++j) {
         const int n = 4 * it + j, s = n & 1;
         mbar_wait(&x_empty[s], ((n >> 1) & 1) ^ 1);
-        uint8_t* x = sX + s * FF_X_BYTES;
-        for (int i = t; i < 150 * 16; i += 128) {          // item = (tile row, (c, dy)): the 4 dx bytes of one u32
-          const int row = i >> 4, g = i & 15, Q = j * 128 + row;
-          uint2 v = make_uint2(0u, 0u);
-          if (Q < 441) {
-            const int Y = Q / 21, X = Q - Y * 21;
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(u8 + (g >> 2) * 7056 + (4 * Y + (g & 3)) * 84 + 4 * X);
-            const float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - 8388608.f;
-            const float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - 8388608.f;
-            const float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388608.f;
-            const float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388608.f;
-            v = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3));
-            if (row < 128) *reinterpret_cast<uint2*>(p.xs + ((size_t)f * 441 + Q) * 64 + g * 4) = v;     // conv1 wgrad's operand
+        uint8_t* x = sX + s * FF_X_BYTES + (g & 1) * 8;
+        int Q = j * 128 + rb, Y = Q / 21, X = Q - Y * 21;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          const int row = rb + 16 * k;
+          if (row < 150) {
+            uint2 v = make_uint2(0u, 0u);
+            if (Q < 441) {
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(u8 + Y * 336 + 4 * X);
+              const float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - 8388608.f;
+              const float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - 8388608.f;
+              const float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388608.f;
+              const float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388608.f;
+              v = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3));
+              if (row < 128) *reinterpret_cast<uint2*>(xs_f + (size_t)Q * 64) = v;     // conv1 wgrad's operand
+            }
+            *reinterpret_cast<uint2*>(x + swz128(row, g >> 1)) = v;
           }
-          *reinterpret_cast<uint2*>(x + swz128(row, g >> 1) + (g & 1) * 8) = v;
+          Q += 16; X += 16;
+          if (X >= 21) { X -= 21; Y += 1; }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -271,7 +304,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
     }
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }

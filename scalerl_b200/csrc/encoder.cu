@@ -275,7 +275,7 @@ int side_mode() {
 }
 
 cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
-                             cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase, const TmaMapsLo* lo, bool finalize) {
+                             cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase, const TmaMapsLo* lo) {
   (void)obs;
   if (frames <= 0) return cudaSuccess;
   if ((mode != 0 && mode != 1) || !maps.valid) return cudaErrorInvalidValue;
@@ -321,7 +321,6 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
     SRL_TRY(cudaEventRecord(ss.ev[3], s2)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[3], 0));
     SRL_TRY(cudaEventRecord(ss.ev[7], s3)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[7], 0));
   }
-  if (!finalize) return cudaSuccess;       // the optimizer kernel takes the conv weight gradients from the workspace itself (WgradFold)
   pf.b(PS_WGRAD_FINALIZE);
   SRL_TRY(launch_chain<PDL_SIMT>(conv_wgrad_finalize_kernel, dim3((36864 + 32768 + 8192 + 255) / 256), dim3(256), 0, st, buf.wgrad_ws, g.w1, g.w2, g.w3));
   SRL_TRY(cudaGetLastError());

@@ -391,61 +391,16 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n,
 // in a fixed slot each), grid barrier, every block adds the partials in the same fixed order (deterministic, identical
 // in all blocks), phase 2 applies the clipped update (g is re-read from L2).  OPT 0 = RMSprop, 1 = Adam.
 // ------------------------------------------------------------------------------------------------
-// workspace -> PyTorch-layout value of conv weight gradient element e of layer L (1, 2, 3); re-zeroes the slot (self-cleaning)
-SRL_DEVINL float wgrad_ws_take(float* ws, int layer, int e) {
-  float* q;
-  float scale = 1.0f;
-  if (layer == 3) {            // dW3[co][c][tap] = ws3[tap>>1][(tap&1)*64 + c][co]
-    const int co = e / 576, r = e - co * 576, c = r / 9, tap = r - c * 9;
-    q = ws + WS_W3 + ((tap >> 1) * 128 + (tap & 1) * 64 + c) * 64 + co;
-  } else if (layer == 2) {     // dW2[co][c][kh][kw] = ws2[kh][kw*32 + c][co]
-    const int co = e >> 9, r = e & 511, c = r >> 4, kh = (r >> 2) & 3, kw = r & 3;
-    q = ws + WS_W2 + (kh * 128 + kw * 32 + c) * 64 + co;
-  } else {                     // dW1[co][c][kh][kw] = ws1[kh>>2][(kw>>2)*64 + c*16 + (kh&3)*4 + (kw&3)][co] / 255
-    const int co = e >> 8, k = e & 255, c = k >> 6, kh = (k >> 3) & 7, kw = k & 7;
-    q = ws + WS_W1 + ((kh >> 2) * 128 + (kw >> 2) * 64 + c * 16 + (kh & 3) * 4 + (kw & 3)) * 32 + co;
-    scale = 1.0f / 255.0f;
-  }
-  const float v = __ldcg(q) * scale;      // written by red.global.add of other kernels: read at L2
-  *q = 0.f;
-  return v;
-}
-
-// grid-stride over the 19,456 float4 groups of the three conv weight gradients: workspace -> g (PyTorch layout), returns the
-// thread's partial sum of squares
-__device__ __noinline__ float fold_conv_wgrads(const WgradFold fold, float* g, int64_t i0, int64_t stride) {
-  float s = 0.f;
-  for (int64_t q = i0; q < (8192 + 32768 + 36864) / 4; q += stride) {
-    int layer, e;
-    int64_t off;
-    if (q < 2048) { layer = 1; e = (int)q * 4; off = fold.off_w1; }
-    else if (q < 2048 + 8192) { layer = 2; e = (int)(q - 2048) * 4; off = fold.off_w2; }
-    else { layer = 3; e = (int)(q - 2048 - 8192) * 4; off = fold.off_w3; }
-    float4 v;
-    v.x = wgrad_ws_take(fold.ws, layer, e); v.y = wgrad_ws_take(fold.ws, layer, e + 1);
-    v.z = wgrad_ws_take(fold.ws, layer, e + 2); v.w = wgrad_ws_take(fold.ws, layer, e + 3);
-    *reinterpret_cast<float4*>(g + off + e) = v;          // the gradient tensors end up complete, as after the finalize kernel
-    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-  }
-  return s;
-}
-
 template <int OPT>
 __global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s0,
                                                          float* __restrict__ s1, int64_t n, float max_norm, float* __restrict__ coef,
                                                          float* __restrict__ scratch, float lr, float a, float b, float eps, int step,
-                                                         int* __restrict__ dstep, const WgradFold fold) {
+                                                         int* __restrict__ dstep) {
   cg::grid_group grid = cg::this_grid();
   const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int t = dstep ? *dstep + 1 : step;          // 1-based step count: Adam bias correction; counted for RMSprop too (checkpoints)
   float s = 0.f;
-  // conv_wgrad_finalize folded in: the 77,824 conv weight gradients come from the wgrad workspace (out of line: keeps the register
-  // count -- and with it two resident blocks per SM -- of the two streaming passes below)
-  if (fold.ws) s = fold_conv_wgrads(fold, g, i0, stride);
   for (int64_t i = i0; i < n4; i += stride) {
-    const int64_t e0 = 4 * i;
-    if (fold.ws && ((e0 >= fold.off_w1 && e0 < fold.off_w1 + 8192) || (e0 >= fold.off_w2 && e0 < fold.off_w2 + 32768) ||
-                    (e0 >= fold.off_w3 && e0 < fold.off_w3 + 36864))) continue;          // summed by fold_conv_wgrads
     const float4 v = reinterpret_cast<const float4*>(g)[i];
     s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
@@ -513,7 +468,7 @@ __global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, 
 
 template <int OPT>
 static cudaError_t launch_clip_optim_t(float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef, float* scratch,
-                                       float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st, WgradFold fold) {
+                                       float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st) {
   static int per_sm_dev[64] = {}, sms_dev[64] = {};      // per device: one process may drive several GPUs
   int dev = 0;
   SRL_TRY(cudaGetDevice(&dev));
@@ -530,13 +485,13 @@ static cudaError_t launch_clip_optim_t(float* p, float* g, float* s0, float* s1,
   int blocks = (int)(need < 1 ? 1 : need);
   int cap = per_sm * sms; if (cap > 592) cap = 592;          // scratch holds 592 partials
   if (blocks > cap) blocks = cap;
-  void* args[] = {&p, &g, &s0, &s1, &n, &max_norm, &coef, &scratch, &lr, &a, &b, &eps, &step, &dstep, &fold};
+  void* args[] = {&p, &g, &s0, &s1, &n, &max_norm, &coef, &scratch, &lr, &a, &b, &eps, &step, &dstep};
   return cudaLaunchCooperativeKernel((const void*)clip_optim_kernel<OPT>, dim3(blocks), dim3(512), args, 0, st);
 }
 cudaError_t launch_clip_optim(int optimizer, float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
-                              float* scratch, float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st, WgradFold fold) {
-  return optimizer == 0 ? launch_clip_optim_t<0>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, st, fold)
-                        : launch_clip_optim_t<1>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, st, fold);
+                              float* scratch, float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st) {
+  return optimizer == 0 ? launch_clip_optim_t<0>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, st)
+                        : launch_clip_optim_t<1>(p, g, s0, s1, n, max_norm, coef, scratch, lr, a, b, eps, step, dstep, st);
 }
 
 // ------------------------------------------------------------------------------------------------

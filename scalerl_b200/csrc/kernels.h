@@ -73,9 +73,6 @@ constexpr int WS_W3 = 0;                       // [5 acc][128 rows][64 co]   (ta
 constexpr int WS_W2 = WS_W3 + 5 * 128 * 64;    // [4 kh][128 rows][64 co]
 constexpr int WS_W1 = WS_W2 + 4 * 128 * 64;    // [2 kh2][128 rows][32 co]
 constexpr int WS_TOTAL = WS_W1 + 2 * 128 * 32;
-// Folding conv_wgrad_finalize into the optimizer (single-GPU step): the first pass of clip_optim_kernel takes the conv weight
-// gradients straight from the workspace (writing the PyTorch-layout gradient tensors and re-zeroing the workspace as it goes).
-struct WgradFold { float* ws; int64_t off_w1, off_w2, off_w3; };      // ws == nullptr: gradients are already final in g
 
 // ---- vtrace.cu
 cudaError_t launch_vtrace_iw(const float* log_rhos, const float* discounts, const float* rewards, const float* values,
@@ -119,8 +116,7 @@ cudaError_t launch_dcore_to_dh(const float* dcore, const float* h, int N, int A,
 cudaError_t launch_unpack_slots(const uint8_t* staging, int64_t slot_bytes, const int64_t* off6, int T, int B, int A, uint8_t* obs, float* reward,
                                 uint8_t* done, int64_t* action, float* logits, float* episode_return, cudaStream_t st);
 cudaError_t launch_clip_optim(int optimizer, float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
-                              float* scratch, float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st,
-                              WgradFold fold = WgradFold{nullptr, 0, 0, 0});
+                              float* scratch, float lr, float a, float b, float eps, int step, int* dstep, cudaStream_t st);
 struct DpPeers { float* g[8]; float* rs[8]; unsigned* ctl[8]; int rank, world; float* mc_g; };      // peer-mapped gradient buffers / control blocks; mc_g: NVLS multicast address of the gradient buffers (or null)
 cudaError_t launch_dp_clip_optim(int optimizer, float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef,
                                  float* scratch, float lr, float a, float b, float eps, int step, int* dstep, const DpPeers& P,
@@ -192,8 +188,7 @@ cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, 
 // phase: 0 = fc layer only (fc.weight / fc.bias gradients complete and joined to `st` on return: 95 % of the gradient
 //        bytes, ready for an early all-reduce), 1 = conv layers only, 2 = both
 cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffers& buf, const ParamPtrs& g, const TmaMaps& maps, int mode,
-                             cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase, const TmaMapsLo* maps_lo = nullptr,
-                             bool finalize = true);
+                             cudaStream_t st, const Profiler& pf, const SideStream& ss, int phase, const TmaMapsLo* maps_lo = nullptr);
 cudaError_t test_shift(const void* A, const void* B, float* D, int shift, int mn_major, int bo_mode, cudaStream_t st);
 cudaError_t test_poison_smem(cudaStream_t st);
 cudaError_t test_pdl(int* flag, int* out, int nblk, unsigned delay_ns, cudaStream_t st);

@@ -543,17 +543,10 @@ class B200ImpalaLearner(BaseAgent):
             self.apply_gradients_dp()
             return
         if not self._dist or self.hp.use_lstm:
-            fold = not self._dist and os.environ.get('SRL_FOLD_FINALIZE', '1') != '0'     # single GPU: apply follows the backward directly
-            if fold:
-                self.set_option('defer_wgrad_finalize', 1)
-            try:
-                self.forward_backward(batch)
-                if self._dist:          # LSTM path: one all-reduce of the whole flat gradient after BPTT
-                    self.all_reduce_gradients()
-                self.apply_gradients()
-            finally:
-                if fold:
-                    self.set_option('defer_wgrad_finalize', 0)
+            self.forward_backward(batch)
+            if self._dist:          # LSTM path: one all-reduce of the whole flat gradient after BPTT
+                self.all_reduce_gradients()
+            self.apply_gradients()
             return
         self._dp_step(batch, lambda: self.forward_backward_begin(batch), lambda: self.backward_finish(batch), self.apply_gradients)
 
@@ -628,7 +621,8 @@ class B200ImpalaLearner(BaseAgent):
             else:
                 g = (torch.cuda.CUDAGraph(),)
                 with torch.cuda.graph(g[0]):
-                    self._enqueue_step(batch)          # forward_backward + apply with the finalize kernel folded into the optimizer
+                    self.forward_backward(batch)
+                    self.apply_gradients()
             self._graphs[key] = g
         if len(g) == 3:
             self._dp_step(batch, g[0].replay, g[1].replay, g[2].replay)
