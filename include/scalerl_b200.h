@@ -123,7 +123,7 @@ int srl_learner_set_config(srl_learner_t* L, const srl_config_t* cfg);
 
 /* run-time switches of one learner context: "column_fusion" (default 1; 0 = three kernels head_fwd / impala_tail / head_bwd
  * instead of the fused column kernel -- the environment variable SRL_NO_COLUMN_FUSION is read once, at creation);
- * "fused_fwd" (default 1, SRL_FUSED_FWD): u8 frame conversion + conv1 + conv2 as ONE persistent kernel (bf16 mode), 0 = three. */
+ * "fused_fwd" (default 0, SRL_FUSED_FWD=1): u8 frame conversion + conv1 + conv2 as ONE persistent kernel (bf16 mode) instead of three. */
 int srl_learner_set_option(srl_learner_t* L, const char* name, int value);
 
 /* optimizer step count (Adam's bias-correction t; torch.optim state['step']): restore it when resuming from a checkpoint

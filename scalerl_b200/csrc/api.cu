@@ -233,7 +233,9 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   L->G = make_ptrs(grads, cfg->A);
   L->step = 0; L->have_fwd = false;
   { const char* nf = getenv("SRL_NO_COLUMN_FUSION"); L->column_fusion = !(nf && atoi(nf) != 0); }   // read once, at creation
-  { const char* ff = getenv("SRL_FUSED_FWD"); L->fused_front = !(ff && atoi(ff) == 0); }
+  // measured (profiles/r02_fused_front_timeline.md): one CTA per SM with ONE MMA-issuing thread paces the fused front at ~10 us per
+  // frame -- 52 us against 47 us for the three kernels it replaces -- so it is opt-in until it issues from two warps
+  { const char* ff = getenv("SRL_FUSED_FWD"); L->fused_front = ff && atoi(ff) != 0; }
   for (int i = 0; i < 2 * PS_COUNT; ++i) L->events[i] = nullptr;
   for (int i = 0; i < PS_COUNT; ++i) L->slot_used[i] = false;
   const int64_t NF = (int64_t)(cfg->T + 1) * cfg->B, NB = (int64_t)cfg->T * cfg->B, A = cfg->A;
@@ -708,6 +710,7 @@ extern "C" int srl_learner_debug_buffer(srl_learner_t* L, const char* name, void
       {"logits", L->logits, NF * A}, {"baseline", L->baseline, NF}, {"dlogits", L->dlogits, NB * A}, {"dbaseline", L->dbaseline, NB},
       {"dh", L->buf.dh, NB * 512}, {"da3", L->buf.da3, NB * 81 * 64}, {"da2", L->buf.da2, NB * 100 * 64},
       {"da1", L->buf.da1, NB * 441 * 64}, {"wpack", L->buf.wpack, WPack::TOTAL},
+      {"fused_dbg", g_fused_dbg, 5 * 8 * 8 * 4},        // u64 stamps, counted in bf16 units by the Python helper (x4)
       {"a1_lo", L->buf.a1_lo, NF * 400 * 32}, {"a2_lo", L->buf.a2_lo, NF * 81 * 64}, {"a3_lo", L->buf.a3_lo, NF * 49 * 64},
       {"dh_lo", L->buf.dh_lo, NB * 512}, {"da3_lo", L->buf.da3_lo, NB * 81 * 64}, {"da2_lo", L->buf.da2_lo, NB * 100 * 64},
       {"da1_lo", L->buf.da1_lo, NB * 441 * 64}, {"wpack_lo", L->buf.wpack_lo, WPack::TOTAL}};

@@ -52,7 +52,16 @@ struct EncFusedParams {
   bf16* a2;                  // [frames*81][64]
   int frames;
   int NFS;                   // frame capacity of the a1 planes (plane stride)
+  unsigned long long* dbg;   // diagnostics (SRL_FUSED_DEBUG): CTA 0 stamps %globaltimer at [role][frame][event]; nullptr = off
 };
+constexpr int FF_DBG_EVENTS = 8, FF_DBG_FRAMES = 8;       // per role: 8 frames x 8 events
+SRL_DEVINL void ff_stamp(const EncFusedParams& p, int role, int it, int ev) {
+  if (p.dbg && blockIdx.x == 0 && it < FF_DBG_FRAMES) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[(role * FF_DBG_FRAMES + it) * FF_DBG_EVENTS + ev] = t;
+  }
+}
 
 SRL_DEVINL void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -81,6 +90,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nmine = p.frames > (int)blockIdx.x ? (p.frames - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (tid == 0) ff_stamp(p, 0, 0, 0);
 
   if (warp == 12) {
     if (lane == 0) {
@@ -97,6 +107,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
     reinterpret_cast<uint4*>(sA1 + 2 * FF_A1_PLANE)[i] = make_uint4(0, 0, 0, 0);
   pdl_wait();                            // the parameters below were written by the previous step's optimizer kernel
   pdl_launch();
+  if (tid == 0) ff_stamp(p, 0, 0, 1);
   // ---- conv weights: fp32 master -> bf16 K-major SWIZZLE_128B operand tiles (what pack_weights_kernel + TMA would deliver).
   //      Read in memory order as float4 (coalesced), several loads in flight per thread, scattered into the tiles.
   //  w1 tile j (= tap (kh2,kw2)): row co (32), k = c*16 + dy*4 + dx  <- W1[co][c][4kh2+dy][4kw2+dx]; a float4 = the 4 dx of one (co,c,kh,kw2)
@@ -142,6 +153,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) ff_stamp(p, 0, 0, 2);
 
   if (warp == 12) {
     // ------------------------------------------------------------------------------------------------ producer
@@ -151,6 +163,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
         mbar_wait(&u8_empty[ub], ((it >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&u8_full[ub], 28224);
         bulk_load_1d(sU8 + ub * FF_U8_BYTES, p.obs + (size_t)f * 28224, 28224, &u8_full[ub]);
+        ff_stamp(p, 1, it, 0);
       }
     }
   } else if (warp == 13) {
@@ -174,6 +187,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
           }
           umma_commit(&x_empty[s]);
           umma_commit(&acc1_full[j]);
+          ff_stamp(p, 2, it, j);
         }
       };
       if (nmine > 0) conv1(0);
@@ -182,6 +196,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
         mbar_wait(a1_full, it & 1);
         mbar_wait(acc2_empty, (it & 1) ^ 1);
         tc_fence_after();
+        ff_stamp(p, 2, it, 4);
 #pragma unroll
         for (int tap = 0; tap < 8; ++tap) {       // tap = (kh, kww): plane kh & 1, shift (kh >> 1) * 10 + kww
           const uint32_t a0 = a1s + ((tap >> 1) & 1) * FF_A1_PLANE + ((tap >> 2) * 10 + (tap & 1)) * 128, b0 = w2 + tap * 8192;
@@ -191,6 +206,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
         }
         umma_commit(a1_empty);
         umma_commit(acc2_full);
+        ff_stamp(p, 2, it, 5);
       }
     }
   } else if (warp >= 4) {
@@ -201,6 +217,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
     for (int it = 0; it < nmine; ++it) {
       const int f = blockIdx.x + it * gridDim.x, ub = it & 1;
       mbar_wait(&u8_full[ub], (it >> 1) & 1);
+      if (t == 0) ff_stamp(p, 3, it, 0);
       const uint8_t* u8 = sU8 + ub * FF_U8_BYTES + src_g;
       bf16* xs_f = p.xs + (size_t)f * 441 * 64 + g * 4;
       for (int j = 0; j < 4; ++j) {
@@ -230,6 +247,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&x_full[s]);
+        if (t == 0) ff_stamp(p, 3, it, 1 + j);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&u8_empty[ub]);
@@ -245,6 +263,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
       for (int j = 0; j < 4; ++j) {
         mbar_wait(&acc1_full[j], it & 1);
         tc_fence_after();
+        if (tid == 0) ff_stamp(p, 4, it, j);
         uint32_t r0[16], r1[16];
         tmem_ld16(lane_base + j * 32, r0);
         tmem_ld16(lane_base + j * 32 + 16, r1);
@@ -279,9 +298,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(a1_full);
+      if (tid == 0) ff_stamp(p, 4, it, 4);
       // ---- conv2 epilogue
       mbar_wait(acc2_full, it & 1);
       tc_fence_after();
+      if (tid == 0) ff_stamp(p, 4, it, 5);
       const int oh2 = tid / 10, ow2 = tid - oh2 * 10;
       const bool ok = tid < 100 && oh2 < 9 && ow2 < 9;
 #pragma unroll
@@ -301,9 +322,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
           store_bf16x16(p.a2 + ((size_t)f * 81 + oh2 * 9 + ow2) * 64 + c0, v);
         }
       }
+      if (tid == 0) ff_stamp(p, 4, it, 6);
     }
   }
   __syncthreads();
+  if (tid == 0) ff_stamp(p, 0, 0, 3);
   if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);

@@ -194,6 +194,7 @@ cudaError_t build_tma_maps_lo(const EncoderBuffers& b, int NF, int NB, TmaMapsLo
   return ok ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+unsigned long long* g_fused_dbg = nullptr;
 static cudaError_t launch_s2d(const uint8_t* obs, int frames, bf16* xs, cudaStream_t st) {
   static const int ygroup = [] { const char* e = getenv("SRL_S2D_Y"); const int v = e ? atoi(e) : 21; return (v == 3 || v == 7) ? v : 21; }();
   if (ygroup == 3) SRL_TRY(launch_chain<PDL_SIMT>(obs_s2d_kernel<3>, dim3(frames * 7), dim3(352), 0, st, obs, xs));
@@ -247,7 +248,14 @@ cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, 
   // bf16 mode: frame conversion + conv1 + conv2 as ONE persistent kernel (enc_fused.cuh); SRL_FUSED_FWD=0 or the fp32-accurate
   // operand mode use the three separate kernels
   if (fused_front && !sp && (reinterpret_cast<uintptr_t>(obs) & 15) == 0) {
-    EncFusedParams q{obs, p.w1, p.b1, p.w2, p.b2, buf.xs, buf.a1, buf.a2, frames, buf.NF};
+    static unsigned long long* dbg_buf = [] {       // SRL_FUSED_DEBUG=1: CTA 0 stamps its phases (tests/diag/diag_fused.py prints them)
+      const char* e = getenv("SRL_FUSED_DEBUG");
+      unsigned long long* q = nullptr;
+      if (e && atoi(e) != 0 && cudaMalloc(&q, 5 * FF_DBG_FRAMES * FF_DBG_EVENTS * 8) == cudaSuccess) cudaMemset(q, 0, 5 * FF_DBG_FRAMES * FF_DBG_EVENTS * 8);
+      return q;
+    }();
+    EncFusedParams q{obs, p.w1, p.b1, p.w2, p.b2, buf.xs, buf.a1, buf.a2, frames, buf.NF, dbg_buf};
+    g_fused_dbg = dbg_buf;
     pf.b(PS_ENC_FUSED); SRL_TRY(enc_fused_fwd_launch(q, kPersistentCtas, st)); pf.e(PS_ENC_FUSED);
     if (wait_before_conv1) SRL_TRY(cudaStreamWaitEvent(st, wait_before_conv1, 0));      // conv3 / fc read the packed weights
   } else {

@@ -178,6 +178,7 @@ bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
 cudaError_t build_tma_maps(const EncoderBuffers& buf, int NF, int NB, TmaMaps* maps, const char** why);
 cudaError_t build_tma_maps_lo(const EncoderBuffers& buf, int NF, int NB, TmaMapsLo* maps, const char** why);
 // wpack_lo != nullptr: also the low copies bf16(w - bf16(w)) in the same layouts
+extern unsigned long long* g_fused_dbg;          // SRL_FUSED_DEBUG stamp buffer of the fused encoder front (device memory; 5 x 8 x 8 u64)
 cudaError_t launch_pack_weights(const ParamPtrs& p, __nv_bfloat16* wpack, cudaStream_t st, __nv_bfloat16* wpack_lo = nullptr);
 // wait_before_conv1: optional event (weight re-pack running on the side stream) that conv1 must wait for
 // mode: 0 = bf16 operands, 1 = fp32-accurate split operands (maps_lo must be valid)
