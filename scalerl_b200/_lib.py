@@ -82,6 +82,7 @@ _HOOK_SIGS = {
     'srl_test_gemm_kmajor': [_P, _P, _P, _I, _I, _I, _I, _P],
     'srl_test_gemm_mnmajor': [_P, _P, _P, _I, _I, _I, _I, _P],
     'srl_test_shifted_operand': [_P, _P, _P, _I, _I, _I, _P],
+    'srl_test_mma_rate': [_I, _I, _I, _I, _P, _P],
     'srl_test_poison_smem': [_P],
     'srl_test_pdl': [_P, _P, _I, C.c_uint, _P],
 }

@@ -133,4 +133,54 @@ cudaError_t test_pdl(int* flag, int* out, int nblk, unsigned delay_ns, cudaStrea
   return cudaLaunchKernelEx(&cfg, pdl_test_b, (volatile int*)flag, out);
 }
 
+// MMA issue-rate microbenchmark: `issuers` warps (1 or 2) of ONE CTA each issue `reps` back-to-back tcgen05.mma (M = 128, N, K = 16,
+// K-major SWIZZLE_128B operands already in shared memory, A descriptor starting `shift` rows into its tile) into their own TMEM
+// accumulator and time issue + completion with clock64.  out[2*w] = cycles until the last MMA was ISSUED, out[2*w+1] = until the
+// commit barrier fired.  Answers: what does one tcgen05.mma cost from a single thread, does a non-atom-aligned start row cost more,
+// and do two issuing warps overlap?
+__global__ void __launch_bounds__(96) mma_rate_kernel(int N, int shift, int reps, int issuers, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                   // 192 rows x 128 B
+  uint8_t* sB = smem + 24576;           // 256 rows x 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 24576 + 32768);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (24576 + 32768) / 16; i += 96) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+  fence_proxy_async_smem();
+  if (warp == 2) {
+    if ((tid & 31) == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp < issuers && (tid & 31) == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    const uint32_t a0 = smem_u32(sA) + shift * 128, b0 = smem_u32(sB), acc = tmem_base + warp * 256;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      const int k = r & 3;
+      umma_bf16(acc, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc, r != 0);
+    }
+    const long long t1 = clock64();
+    umma_commit(&bars[warp]);
+    mbar_wait(&bars[warp], 0);
+    const long long t2 = clock64();
+    out[2 * warp] = t1 - t0;
+    out[2 * warp + 1] = t2 - t0;
+  }
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+cudaError_t test_mma_rate(int N, int shift, int reps, int issuers, long long* out, cudaStream_t st) {
+  const int smem = 24576 + 32768 + 256 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  mma_rate_kernel<<<1, 96, smem, st>>>(N, shift, reps, issuers, out);
+  return cudaGetLastError();
+}
+
 }  // namespace srl

@@ -64,6 +64,11 @@ extern "C" int srl_test_pdl(int* flag, int* out, int nblk, unsigned delay_ns, vo
   CU(test_pdl(flag, out, nblk, delay_ns, (cudaStream_t)stream), "test_pdl");
   return 0;
 }
+extern "C" int srl_test_mma_rate(int N, int shift, int reps, int issuers, long long* out_cycles, void* stream) {
+  REQ(out_cycles && reps >= 1 && (issuers == 1 || issuers == 2) && N >= 16 && N <= 256 && N % 16 == 0 && shift >= 0 && shift <= 32, "test_mma_rate: bad argument");
+  CU(test_mma_rate(N, shift, reps, issuers, out_cycles, (cudaStream_t)stream), "test_mma_rate");
+  return 0;
+}
 extern "C" int srl_test_poison_smem(void* stream) {
   CU(test_poison_smem((cudaStream_t)stream), "test_poison_smem");
   return 0;
