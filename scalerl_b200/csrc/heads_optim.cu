@@ -623,7 +623,9 @@ __global__ void __launch_bounds__(512) dp_clip_optim_kernel(float* __restrict__ 
       multimem_st_f32(P.mc_g + i, acc);
       s += acc * acc;
     }
-    __threadfence_system();                                // my remote stores are performed before the flag of barrier 2 is published
+    // no per-thread system fence here (it cost a full NVLink round trip per step, ~8 us at N = 8): the grid barrier below orders
+    // every thread's multimem.st before block 0's fence.sys + st.release of barrier 2, and fence cumulativity (PTX memory model)
+    // carries those writes to the acquiring peers -- the same rule the peer-load variant relies on for its exchange buffer
   } else {
   for (int64_t i = lo + i0; i < hi; i += stride) {
     float4 acc = ld_sys_v4(P.g[0] + 4 * i);
