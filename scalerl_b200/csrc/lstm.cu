@@ -130,7 +130,8 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ gx, const float* 
 //     biases, sigma / tanh, done-reset, c_t (kept in REGISTERS across the steps), h_t -- and writes gates / c / h / bf16 h and
 //     next step's operand hm[t+1];
 //   * a grid barrier (atomic counter, 36 co-resident CTAs) separates the steps: hm[t+1] is complete before anybody loads it.
-// Per step ~3 us instead of ~20 us of launch latency.  Used when B <= 128 (one M tile); larger batches keep the per-step kernels.
+// Design estimate was ~3 us per step; MEASURED ~15 us (see srl_lstm_create) -- kept opt-in for B <= 128 as the starting point of the
+// next iteration (more epilogue warps, barrier flags instead of an atomic counter).
 constexpr int LREC_THREADS = 192, LREC_STAGES = 4;
 struct LRecFwdParams {
   SRL_TMAP hm;               // [T1*B][Hp] bf16, box 128 rows x 64
@@ -609,7 +610,9 @@ extern "C" int srl_lstm_create(int T1, int B, int H, const float* const* weights
   L->dwpad = (float*)(a + o_dw); L->h_init = (float*)(a + o_hi); L->c_init = (float*)(a + o_ci);
   L->counters = (unsigned*)(a + o_cnt);
   L->dhm_part = (float*)(a + o_part);
-  { const char* e = getenv("SRL_LSTM_PERSISTENT"); L->persistent = B <= 128 && !(e && atoi(e) == 0); }
+  // opt-in (SRL_LSTM_PERSISTENT=1): measured SLOWER than the per-step launches on B200 (T1=101, B=128: forward 3.03 vs 2.33 ms, BPTT 6.07
+  // vs 3.88 ms; profiles/r02_lstm_persistent.md) -- ~15 us per step: grid barrier + post-barrier TMA latency + a 16-units-per-thread cell
+  { const char* e = getenv("SRL_LSTM_PERSISTENT"); L->persistent = B <= 128 && e && atoi(e) != 0; }
   bool ok = true;
   for (int l = 0; l < 2 && ok; ++l) {
     ok = ok && map2(&L->m_xin[l], L->xin[l], Hp, N1, 128) && map2(&L->m_xin64[l], L->xin[l], Hp, NB, 64) && map2(&L->m_hm[l], L->hm[l], Hp, N1, 128) &&
