@@ -377,6 +377,7 @@ class ImpalaTrainer:
         sb = self.ring.slot_bytes
         hp = self.learner.hp
         state: Tuple[torch.Tensor, ...] = tuple()
+        unpack = False
         with nvtx_range('get_batch'), torch.cuda.stream(self._copy_stream):
             if self._consumed[s] is not None:
                 self._copy_stream.wait_event(self._consumed[s])          # the step that read this device batch has finished
@@ -390,10 +391,8 @@ class ImpalaTrainer:
                     m = indices[b]
                     stg[b:e].view(-1).copy_(self.ring.block[m * sb:(m + e - b) * sb], non_blocking=True)
                     b = e
-                _lib.check(_lib.lib().srl_unpack_slots(
-                    stg.data_ptr(), sb, self._slot_off, hp.rollout_length, hp.batch_size, hp.num_actions, dst['obs'].data_ptr(),
-                    dst['reward'].data_ptr(), dst['done'].data_ptr(), dst['action'].data_ptr(), dst['policy_logits'].data_ptr(),
-                    dst['episode_return'].data_ptr(), self._copy_stream.cuda_stream), 'srl_unpack_slots')
+                unpack = True                 # the scatter kernel runs on the LEARNER stream (below): the copy stream stays pure DMA,
+                                              # so the next batch's H2D is not queued behind a kernel launch
             else:                             # foreign buffer dict (reference-style lists of tensors): per-key column copies
                 for b, m in enumerate(indices):
                     for k in H2D_KEYS:
@@ -419,7 +418,14 @@ class ImpalaTrainer:
         self._pending_release.append((ev, indices, free_queue))              # slots stay owned until their copy has finished
         self._poll_releases()
         timings.time('enqueue')
-        torch.cuda.current_stream(self.learner.device).wait_event(ev)        # device-side wait: the host moves on
+        cur = torch.cuda.current_stream(self.learner.device)
+        cur.wait_event(ev)                                                   # device-side wait: the host moves on
+        if unpack:
+            stg = self._staging[s]
+            _lib.check(_lib.lib().srl_unpack_slots(
+                stg.data_ptr(), sb, self._slot_off, hp.rollout_length, hp.batch_size, hp.num_actions, dst['obs'].data_ptr(),
+                dst['reward'].data_ptr(), dst['done'].data_ptr(), dst['action'].data_ptr(), dst['policy_logits'].data_ptr(),
+                dst['episode_return'].data_ptr(), cur.cuda_stream), 'srl_unpack_slots')
         self._cur_slot = s
         timings.time('device')
         return dst, state
