@@ -476,8 +476,8 @@ class ImpalaTrainer:
             if self._cur_slot is not None:
                 self._consumed[self._cur_slot] = ev
             self._steps_done += 1
-            if self._steps_done % max(1, self.args.publish_every) == 0:
-                self.publish_weights(actor_model, wait=False)
+            if self._steps_done % max(1, self.args.publish_every) == 0 and not getattr(self, '_publish_rank0_only', False):
+                self.publish_weights(actor_model, wait=False)      # data-parallel learners: replicas are identical, rank 0 publishes
         self._tickets.append(ticket)
         self._poll_releases()
         lag = max(0, int(self.args.stats_lag))
@@ -555,11 +555,15 @@ class ImpalaTrainer:
             self._pub_done.synchronize()
         return version
 
-    def learn_process(self, threading_id, actor_model, learner_model, free_queue, full_queue, buffers, rnn_state_buffers, lock=None):
-        """impala_atari.py:351-401"""
+    def learn_process(self, threading_id, actor_model, learner_model, free_queue, full_queue, buffers, rnn_state_buffers, lock=None,
+                      max_iters: Optional[int] = None):
+        """impala_atari.py:351-401.  ``max_iters``: run exactly that many steps (data-parallel learners must agree on the count:
+        every step contains a collective) instead of watching the shared ``global_step``."""
         try:
             timings = Timings()
-            while self.global_step < self.args.total_steps:
+            it = 0
+            while (it < max_iters) if max_iters is not None else (self.global_step < self.args.total_steps):
+                it += 1
                 timings.reset()
                 batch, state = self.get_batch(free_queue, full_queue, buffers, rnn_state_buffers, timings, lock)
                 stats = self.learn(actor_model, learner_model, batch, state, lock)
@@ -575,9 +579,75 @@ class ImpalaTrainer:
             traceback.print_exc()
             raise
 
+    def _learner_worker(self, rank, world, port, free_queue, full_queue, deq_lock, iters, result_q):
+        """one data-parallel learner process (forked before any CUDA use): GPU `rank`, NCCL group over the `world` learners, its
+        batch = whichever ``batch_size`` slots of the SHARED ring it dequeues (the columns of a batch are exchangeable, so any
+        disjoint slot sets form a valid sharding of the global batch of batch_size * world columns)"""
+        try:
+            import torch.distributed as dist
+            from ...utils.numa import bind_to_gpu_numa
+            torch.cuda.set_device(rank)
+            bind_to_gpu_numa(rank)
+            os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+            dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+            self._publish_rank0_only = rank != 0
+            self.learn_process(rank, self.actor_model, None, free_queue, full_queue, self.buffers, self.rnn_state_buffers, deq_lock, max_iters=iters)
+            self.flush()
+            chk = int(self.learner.flat_params.view(torch.int32).to(torch.int64).sum())
+            result_q.put((rank, dict(getattr(self, 'last_stats', {})), chk, getattr(self.learner, 'dp_path', 'nccl')))
+            if rank == 0:
+                self.save_checkpoint(os.path.join(self.args.output_dir, self.args.project, 'model.tar'))
+            self.learner.release_graphs()
+            dist.barrier(device_ids=[rank])
+            os._exit(0)                    # skip NCCL teardown at interpreter exit (seen to hang)
+        except Exception:
+            traceback.print_exc()
+            result_q.put((rank, None, None, None))
+            os._exit(1)
+
+    def _train_multi_learner(self) -> Dict[str, Any]:
+        """``num_learners`` > 1 (impala_atari.py:420-456 starts that many learner threads on one device): here one learner PROCESS per
+        GPU, all dequeuing from the same trajectory ring, gradients SUM-reduced inside the step (NVLS / peer memory / NCCL)."""
+        from ...data.slot_queue import SlotQueue
+        import socket
+        a = self.args
+        world = a.num_learners
+        free_queue, full_queue = SlotQueue(2 * a.num_buffers + a.num_actors + 4, self._ctx), SlotQueue(2 * a.num_buffers + 4, self._ctx)
+        sock = socket.socket(); sock.bind(('127.0.0.1', 0)); port = sock.getsockname()[1]; sock.close()
+        per_step = a.rollout_length * a.batch_size * world
+        iters = (a.total_steps + per_step - 1) // per_step
+        deq_lock, result_q = self._ctx.Lock(), self._ctx.SimpleQueue()
+        actors = [self._ctx.Process(target=self.get_action, name=f'actor-process-{i}',
+                                    args=(i, free_queue, full_queue, self.actor_model, self.buffers, self.rnn_state_buffers)) for i in range(a.num_actors)]
+        learners = [self._ctx.Process(target=self._learner_worker, name=f'learner-process-{r}',
+                                      args=(r, world, port, free_queue, full_queue, deq_lock, iters, result_q)) for r in range(world)]
+        for p in actors + learners:
+            p.start()
+        for m in range(a.num_buffers):
+            free_queue.put(m)
+        t0 = timeit.default_timer()
+        results = [result_q.get() for _ in range(world)]
+        dt = timeit.default_timer() - t0
+        for p in learners:
+            p.join(timeout=30)
+        for _ in range(a.num_actors):
+            free_queue.put(None)
+        for p in actors:
+            p.join(timeout=2)
+            if p.is_alive():
+                p.terminate()
+        if any(r[1] is None for r in results):
+            raise RuntimeError('a learner process failed (see its traceback above)')
+        results.sort(key=lambda r: r[0])
+        return dict(steps=self.global_step, sps=self.global_step / max(dt, 1e-9), weights_version=int(self.weights_version[0]), learners=world,
+                    replica_checksums=[r[2] for r in results], grad_path=results[0][3], **results[0][1])
+
     def train(self, log_every_s: float = 5.0, learner_in_process: bool = True) -> Dict[str, Any]:
-        """impala_atari.py:403-494.  Actors are forked BEFORE CUDA is touched; the learner loop then runs in this
-        process (learner_in_process) -- one learner per GPU; multi-GPU runs launch one trainer per rank (torchrun)."""
+        """impala_atari.py:403-494.  Actors are forked BEFORE CUDA is touched; with ``num_learners == 1`` the learner loop runs in this
+        process; with ``num_learners > 1`` one learner process per GPU is forked as well (data parallel over a shared ring) --
+        alternatively launch one trainer per rank with torchrun (each with its own actors and ring)."""
+        if self.args.num_learners > 1:
+            return self._train_multi_learner()
         from ...data.slot_queue import SlotQueue          # mp.SimpleQueue's put/get/empty over a shared-memory index ring
         free_queue, full_queue = SlotQueue(2 * self.args.num_buffers + self.args.num_actors + 4, self._ctx), SlotQueue(2 * self.args.num_buffers + 4, self._ctx)
         actors = []

@@ -49,3 +49,33 @@ def test_dp_check(world, fused):
     if fused == 'nvls' and 'nvls multimem' not in out:
         pytest.skip('no NVLS multicast mapping on this box (torch symmetric memory reported multicast_ptr = 0): ran on peer loads')
     assert want in out, out[-2000:]
+
+
+def test_multi_learner_trainer_shares_one_ring(tmp_path):
+    """ImpalaTrainer(num_learners=2): two learner PROCESSES (one per GPU) dequeue from ONE pinned trajectory ring fed by the same
+    actors, gradients SUM-reduced inside the step; replicas end bit-identical and rank 0 published the weights.
+    Runs in a child interpreter: the trainer forks before CUDA is touched, which a pytest process that already used CUDA cannot do."""
+    if 2 not in _counts():
+        pytest.skip('2 GPUs not visible')
+    code = f"""
+import sys, json, torch
+sys.path.insert(0, {ROOT!r})
+from scalerl_b200.algorithms.impala.impala_atari import ImpalaArguments, ImpalaTrainer
+a = ImpalaArguments(num_actors=3, num_learners=2, batch_size=4, rollout_length=5, num_buffers=24, total_steps=2 * 4 * 5 * 6, output_dir={str(tmp_path)!r})
+t = ImpalaTrainer(a)
+w0 = t.actor_model.state_dict()['fc.weight'].clone()
+out = t.train()
+ck = torch.load({str(tmp_path)!r} + '/impala/model.tar', weights_only=False)
+same = all(torch.equal(ck['model_state_dict'][k], v) for k, v in t.actor_model.state_dict().items())
+print('RESULT ' + json.dumps(dict(steps=out['steps'], learners=out['learners'], checks=out['replica_checksums'], version=out['weights_version'],
+      loss=out['total_loss'], moved=not torch.equal(w0, t.actor_model.state_dict()['fc.weight']), actor_equals_checkpoint=same, path=out['grad_path'])))
+"""
+    r = subprocess.run([sys.executable, '-c', code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    out = r.stdout + '\n' + r.stderr
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith('RESULT ')]
+    assert r.returncode == 0 and line, out[-4000:]
+    import json
+    res = json.loads(line[0][7:])
+    assert res['steps'] == 2 * 4 * 5 * 6 and res['learners'] == 2
+    assert len(set(res['checks'])) == 1, res                       # replicas bit-identical
+    assert res['version'] == 6 and res['moved'] and res['actor_equals_checkpoint'], res
