@@ -411,6 +411,14 @@ def _main(real_stdout):
     tr_s = max_over_ranks(dt)
     tr_value = frames / tr_s
     tr_host_ms = (dt - trainer.wait_seconds) / K * 1e3          # host time per step outside the wait for the lagged result
+    # diagnostic: the ring -> device DMA alone (one merged copy of B slots from the pinned shared-memory block)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        base = (i % POOL) * B
+        trainer._staging[0].view(-1).copy_(trainer.ring.block[base * trainer.ring.slot_bytes:(base + B) * trainer.ring.slot_bytes], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ring_h2d_ms = (time.perf_counter() - t0) / K * 1e3
     tr_h2d = B * trainer.ring.slot_bytes + (trainer._rnn_host[0].numel() * 4 if args.use_lstm else 0)
     tr_d2h = learner.numel * 4 + 8 + (8 * 4 + T * B * 5)       # weight publish + version counter + step result (scalars, episode_return, done)
     published = int(trainer.weights_version[0])
@@ -634,7 +642,7 @@ def _main(real_stdout):
                        'ms_per_step': tr_s / K * 1e3,
                        'api': 'ImpalaTrainer.get_batch + ImpalaTrainer.learn (pinned shared-memory trajectory ring -> device, step, lagged stats, '
                               'asynchronous versioned weight publish into the shared actor parameters)',
-                       'weights_published': published, 'last_total_loss': tstats['total_loss'], 'host_ms_per_step': tr_host_ms,
+                       'weights_published': published, 'last_total_loss': tstats['total_loss'], 'host_ms_per_step': tr_host_ms, 'ring_h2d_only_ms_per_step': ring_h2d_ms,
                        'stats_lag_steps': targs.stats_lag, 'publish_every': targs.publish_every,
                        'feeder_value': e2e_value, 'feeder_ms_per_step': e2e_s / K * 1e3, 'feeder_h2d_bytes_per_step': feeder.h2d_bytes,
                        'feeder_api': 'HostBatchFeeder.submit/learn/result (time-major pinned batches, no ring, no weight publish: round-1 e2e)',
