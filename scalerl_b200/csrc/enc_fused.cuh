@@ -6,16 +6,18 @@
 // and the HBM round trips between them; what the BACKWARD pass needs is still written out once: xs (the space-to-depth frame:
 // conv1 wgrad's operand) and a1 (conv2's wgrad operand and dgrad mask), plus a2, the input of conv3.
 //
-//   warp 12     producer: ONE cp.async.bulk (1-D TMA) per frame, 28,224 contiguous bytes of u8 -> shared memory, double-buffered
+//   warp 16     producer: ONE cp.async.bulk (1-D TMA) per frame, 28,224 contiguous bytes of u8 -> shared memory, double-buffered
 //               (frame f+1 lands while frame f is being computed)
-//   warps 4-11  converters: u8 -> bf16 space-to-depth operand tile of conv1 (128 output positions + 22 halo rows of the 21x21
+//   warps 8-15  converters: u8 -> bf16 space-to-depth operand tile of conv1 (128 output positions + 22 halo rows of the 21x21
 //               grid, 64 channels (c,dy,dx), SWIZZLE_128B) written with generic stores + fence.proxy.async; two tiles in flight;
 //               the same values go to global `xs`
-//   warp 13     tcgen05.mma issuer: conv1 = 4 position tiles x (4 taps x 4 K-steps), N = 32, four TMEM accumulators; conv2 =
-//               8 taps x 4 K-steps, N = 64, reading conv1's output from SHARED memory (the two row-parity planes of the layout
-//               in res_problems.cuh, so a stride-2 tap is a row shift).  conv1 of frame f+1 is issued BEFORE conv2 of frame f,
-//               so the tensor pipe works while the epilogue warps turn conv1(f) into conv2's operand.
-//   warps 0-3   epilogues: TMEM -> registers -> (x/255 + b1, ReLU) -> bf16 -> shared a1 planes + global a1;  (+ b2, ReLU) -> global a2
+//   warps 17/18 TWO tcgen05.mma issuers (one thread each): conv1 = 4 position tiles x (4 taps x 4 K-steps), N = 32, four TMEM
+//               accumulators; conv2 = 8 taps x 4 K-steps, N = 64, reading conv1's output from SHARED memory (the two row-parity
+//               planes of the layout in res_problems.cuh, so a stride-2 tap is a row shift).  Two issuers because one thread
+//               cannot keep the pipe busy with N <= 64 MMAs (56 clk each from one issuer, 40-48 in aggregate from two:
+//               profiles/r02_mma_issue_rate.md) and because conv2(f) must not queue behind conv1(f+1).
+//   warps 0-3   conv1 epilogue: TMEM -> registers -> (x/255 + b1, ReLU) -> bf16 -> shared a1 planes + global a1
+//   warps 4-7   conv2 epilogue: (+ b2, ReLU) -> global a2
 // The conv weights are converted from the fp32 master parameters inside the prologue (80 KB of bf16 per CTA, from L2), so the
 // kernel does not depend on pack_weights_kernel -- that kernel (needed by conv3 / fc) runs beside it.
 #pragma once
@@ -24,7 +26,7 @@
 
 namespace srl {
 
-constexpr int FF_THREADS = 448;          // warps 0-3 epilogues, 4-11 converters, 12 producer, 13 MMA issuer
+constexpr int FF_THREADS = 608;          // warps 0-3 conv1 epilogue, 4-7 conv2 epilogue, 8-15 converters, 16 producer, 17 / 18 MMA issuers (conv1 / conv2)
 constexpr int FF_CONV_WARPS = 8;
 constexpr int FF_W1_BYTES = 4 * 32 * 128;          // 4 taps x [32 co][64 k]
 constexpr int FF_W2_BYTES = 8 * 64 * 128;          // 8 taps x [64 co][64 k]
@@ -37,7 +39,7 @@ constexpr int FF_OFF_U8 = FF_OFF_W2 + FF_W2_BYTES;
 constexpr int FF_OFF_X = FF_OFF_U8 + 2 * FF_U8_BYTES;
 constexpr int FF_OFF_A1 = FF_OFF_X + 2 * FF_X_BYTES;
 constexpr int FF_OFF_BAR = FF_OFF_A1 + FF_A1_BYTES;
-constexpr int FF_SMEM_BYTES = FF_OFF_BAR + 256 + 1024;
+constexpr int FF_SMEM_BYTES = FF_OFF_BAR + 1024 + 1024;      // barriers + the two bias vectors
 static_assert(FF_SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(FF_OFF_U8 % 1024 == 0 && FF_OFF_X % 1024 == 0 && FF_OFF_A1 % 1024 == 0, "swizzle atoms need 1024-byte aligned tiles");
 
@@ -63,6 +65,15 @@ SRL_DEVINL void ff_stamp(const EncFusedParams& p, int role, int it, int ev) {
   }
 }
 
+// mbarrier wait for the roles that are not on the critical issue path: back off between polls so the spinning warps do not
+// take issue slots from the converter / epilogue warps sharing their schedulers
+SRL_DEVINL void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);
+    if (++spins > SRL_SPIN_LIMIT) __trap();
+  }
+}
 SRL_DEVINL void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -92,7 +103,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
   const int nmine = p.frames > (int)blockIdx.x ? (p.frames - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (tid == 0) ff_stamp(p, 0, 0, 0);
 
-  if (warp == 12) {
+  float* s_b1 = reinterpret_cast<float*>(smem + FF_OFF_BAR + 256);      // [32]
+  float* s_b2 = s_b1 + 32;                                               // [64]
+  if (tid < 32) s_b1[tid] = __ldg(p.b1 + tid);
+  else if (tid < 96) s_b2[tid - 32] = __ldg(p.b2 + tid - 32);
+  if (warp == 16) {
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) { mbar_init(&u8_full[i], 1); mbar_init(&u8_empty[i], FF_CONV_WARPS); mbar_init(&x_full[i], FF_CONV_WARPS); mbar_init(&x_empty[i], 1); }
       for (int j = 0; j < 4; ++j) { mbar_init(&acc1_full[j], 1); mbar_init(&acc1_empty[j], 4); }
@@ -112,7 +127,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
   //      Read in memory order as float4 (coalesced), several loads in flight per thread, scattered into the tiles.
   //  w1 tile j (= tap (kh2,kw2)): row co (32), k = c*16 + dy*4 + dx  <- W1[co][c][4kh2+dy][4kw2+dx]; a float4 = the 4 dx of one (co,c,kh,kw2)
   {
-    constexpr int NQ = 2048, U = 5;                      // 2048 float4 / 448 threads -> 5 each
+    constexpr int NQ = 2048, U = 4;                      // 2048 float4 / 608 threads -> <= 4 each
     float4 v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) { const int q = tid + u * FF_THREADS; if (q < NQ) v[u] = __ldg(reinterpret_cast<const float4*>(p.w1) + q); }
@@ -127,7 +142,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
   }
   //  w2 tile j (= (kh, kww)): row co (64), k = kwl*32 + c (kw = 2kww + kwl)  <- W2[co][c][kh][kw]; a float4 = the 4 kw of one (co,c,kh)
   {
-    constexpr int NQ = 8192, U = 10;                     // two rounds of 10 loads in flight per thread
+    constexpr int NQ = 8192, U = 7;                      // two rounds of 7 loads in flight per thread
 #pragma unroll 1
     for (int base = 0; base < NQ; base += U * FF_THREADS) {
       float4 v[U];
@@ -155,7 +170,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) ff_stamp(p, 0, 0, 2);
 
-  if (warp == 12) {
+  if (warp == 16) {
     // ------------------------------------------------------------------------------------------------ producer
     if (lane == 0) {
       for (int it = 0; it < nmine; ++it) {
@@ -166,12 +181,12 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
         ff_stamp(p, 1, it, 0);
       }
     }
-  } else if (warp == 13) {
-    // ------------------------------------------------------------------------------------------------ MMA issuer
+  } else if (warp == 17) {
+    // ------------------------------------------------------------------------------------------------ MMA issuer: conv1
     if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_bf16(128, 32, 0, 0), idesc2 = make_idesc_bf16(128, 64, 0, 0);
-      const uint32_t w1 = smem_u32(sW1), w2 = smem_u32(sW2), a1s = smem_u32(sA1);
-      auto conv1 = [&](int it) {
+      constexpr uint32_t idesc1 = make_idesc_bf16(128, 32, 0, 0);
+      const uint32_t w1 = smem_u32(sW1);
+      for (int it = 0; it < nmine; ++it) {
         for (int j = 0; j < 4; ++j) {
           const int n = 4 * it + j, s = n & 1;
           mbar_wait(&x_full[s], (n >> 1) & 1);
@@ -189,10 +204,14 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
           umma_commit(&acc1_full[j]);
           ff_stamp(p, 2, it, j);
         }
-      };
-      if (nmine > 0) conv1(0);
+      }
+    }
+  } else if (warp == 18) {
+    // ------------------------------------------------------------------------------------------------ MMA issuer: conv2
+    if (lane == 0) {
+      constexpr uint32_t idesc2 = make_idesc_bf16(128, 64, 0, 0);
+      const uint32_t w2 = smem_u32(sW2), a1s = smem_u32(sA1);
       for (int it = 0; it < nmine; ++it) {
-        if (it + 1 < nmine) conv1(it + 1);        // keep the tensor pipe busy while the epilogue warps build conv2's operand
         mbar_wait(a1_full, it & 1);
         mbar_wait(acc2_empty, (it & 1) ^ 1);
         tc_fence_after();
@@ -209,39 +228,36 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
         ff_stamp(p, 2, it, 5);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 8) {
     // ------------------------------------------------------------------------------------------------ converters (256 threads)
-    // thread = (16-byte half-chunk g = (c, dy), row slot rb); rows rb, rb + 16, ... of the 150-row tile: one u32 (4 dx bytes) -> 4 bf16
-    const int t = tid - 128, g = t & 15, rb = t >> 4;
-    const int src_g = (g >> 2) * 7056 + (g & 3) * 84;              // (c, dy) offset inside the u8 frame
+    // thread = (16-byte chunk gp = (c, dy pair), row slot rb); rows rb, rb + 32, ... of the 150-row tile: two u32 (2 x 4 dx bytes) -> 8 bf16
+    const int t = tid - 256, gp = t & 7, rb = t >> 3;
+    const int src_g = (gp >> 1) * 7056 + (gp & 1) * 168;           // (c, dy0 = 2 (gp & 1)) offset inside the u8 frame
     for (int it = 0; it < nmine; ++it) {
       const int f = blockIdx.x + it * gridDim.x, ub = it & 1;
-      mbar_wait(&u8_full[ub], (it >> 1) & 1);
+      mbar_wait_relaxed(&u8_full[ub], (it >> 1) & 1);
       if (t == 0) ff_stamp(p, 3, it, 0);
       const uint8_t* u8 = sU8 + ub * FF_U8_BYTES + src_g;
-      bf16* xs_f = p.xs + (size_t)f * 441 * 64 + g * 4;
+      bf16* xs_f = p.xs + (size_t)f * 441 * 64 + gp * 8;
       for (int j = 0; j < 4; ++j) {
         const int n = 4 * it + j, s = n & 1;
-        mbar_wait(&x_empty[s], ((n >> 1) & 1) ^ 1);
-        uint8_t* x = sX + s * FF_X_BYTES + (g & 1) * 8;
+        mbar_wait_relaxed(&x_empty[s], ((n >> 1) & 1) ^ 1);
+        uint8_t* x = sX + s * FF_X_BYTES;
         int Q = j * 128 + rb, Y = Q / 21, X = Q - Y * 21;
 #pragma unroll
-        for (int k = 0; k < 10; ++k) {
-          const int row = rb + 16 * k;
+        for (int k = 0; k < 5; ++k) {
+          const int row = rb + 32 * k;
           if (row < 150) {
-            uint2 v = make_uint2(0u, 0u);
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (Q < 441) {
-              const uint32_t w = *reinterpret_cast<const uint32_t*>(u8 + Y * 336 + 4 * X);
-              const float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - 8388608.f;
-              const float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - 8388608.f;
-              const float f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388608.f;
-              const float f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388608.f;
-              v = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, f3));
-              if (row < 128) *reinterpret_cast<uint2*>(xs_f + (size_t)Q * 64) = v;     // conv1 wgrad's operand
+              const uint32_t w0 = *reinterpret_cast<const uint32_t*>(u8 + Y * 336 + 4 * X);
+              const uint32_t w1 = *reinterpret_cast<const uint32_t*>(u8 + Y * 336 + 84 + 4 * X);
+              v = u8x8_to_bf16x8(w0, w1);
+              if (row < 128) *reinterpret_cast<uint4*>(xs_f + (size_t)Q * 64) = v;     // conv1 wgrad's operand
             }
-            *reinterpret_cast<uint2*>(x + swz128(row, g >> 1)) = v;
+            *reinterpret_cast<uint4*>(x + swz128(row, gp)) = v;
           }
-          Q += 16; X += 16;
+          Q += 32; X += 11; Y += 1;                       // 32 = 21 + 11
           if (X >= 21) { X -= 21; Y += 1; }
         }
         fence_proxy_async_smem();
@@ -252,16 +268,13 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
       __syncwarp();
       if (lane == 0) mbar_arrive(&u8_empty[ub]);
     }
-  } else {
-    // ------------------------------------------------------------------------------------------------ epilogues (warps 0-3)
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------------------------------------ conv1 epilogue (warps 0-3)
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float b1r[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) b1r[c] = __ldg(p.b1 + c);
     for (int it = 0; it < nmine; ++it) {
       const int f = blockIdx.x + it * gridDim.x;
       for (int j = 0; j < 4; ++j) {
-        mbar_wait(&acc1_full[j], it & 1);
+        mbar_wait_relaxed(&acc1_full[j], it & 1);
         tc_fence_after();
         if (tid == 0) ff_stamp(p, 4, it, j);
         uint32_t r0[16], r1[16];
@@ -271,14 +284,14 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc1_empty[j]);          // accumulator drained: conv1 of the next frame may reuse it
-        if (j == 0) mbar_wait(a1_empty, (it & 1) ^ 1);       // conv2 of the previous frame has finished reading the planes
+        if (j == 0) mbar_wait_relaxed(a1_empty, (it & 1) ^ 1);   // conv2 of the previous frame has finished reading the planes
         const int Q = j * 128 + tid, oh = Q / 21, ow = Q - oh * 21;
         if (Q < 441 && oh < 20 && ow < 20) {
           float v[32];
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
-            v[c] = fmaxf(fmaf(__uint_as_float(r0[c]), 1.0f / 255.0f, b1r[c]), 0.f);
-            v[16 + c] = fmaxf(fmaf(__uint_as_float(r1[c]), 1.0f / 255.0f, b1r[16 + c]), 0.f);
+            v[c] = fmaxf(fmaf(__uint_as_float(r0[c]), 1.0f / 255.0f, s_b1[c]), 0.f);
+            v[16 + c] = fmaxf(fmaf(__uint_as_float(r1[c]), 1.0f / 255.0f, s_b1[16 + c]), 0.f);
           }
           uint4 q[4];
 #pragma unroll
@@ -299,35 +312,40 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
       __syncwarp();
       if (lane == 0) mbar_arrive(a1_full);
       if (tid == 0) ff_stamp(p, 4, it, 4);
-      // ---- conv2 epilogue
-      mbar_wait(acc2_full, it & 1);
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------------ conv2 epilogue (warps 4-7)
+    const int row = tid - 128;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int oh2 = row / 10, ow2 = row - oh2 * 10;
+    const bool ok = row < 100 && oh2 < 9 && ow2 < 9;
+    for (int it = 0; it < nmine; ++it) {
+      const int f = blockIdx.x + it * gridDim.x;
+      mbar_wait_relaxed(acc2_full, it & 1);
       tc_fence_after();
-      if (tid == 0) ff_stamp(p, 4, it, 5);
-      const int oh2 = tid / 10, ow2 = tid - oh2 * 10;
-      const bool ok = tid < 100 && oh2 < 9 && ow2 < 9;
+      if (row == 0) ff_stamp(p, 4, it, 5);
+      uint32_t r[4][16];
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(lane_base + 128 + c0, r);
-        tmem_ld_wait();
-        if (c0 == 48) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc2_empty);
-        }
-        if (ok) {
+      for (int q = 0; q < 4; ++q) tmem_ld16(lane_base + 128 + q * 16, r[q]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc2_empty);
+      if (ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
           float v[16];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] = fmaxf(__uint_as_float(r[c]) + __ldg(p.b2 + c0 + c), 0.f);
-          store_bf16x16(p.a2 + ((size_t)f * 81 + oh2 * 9 + ow2) * 64 + c0, v);
+          for (int c = 0; c < 16; ++c) v[c] = fmaxf(__uint_as_float(r[q][c]) + s_b2[q * 16 + c], 0.f);
+          store_bf16x16(p.a2 + ((size_t)f * 81 + oh2 * 9 + ow2) * 64 + q * 16, v);
         }
       }
-      if (tid == 0) ff_stamp(p, 4, it, 6);
+      if (row == 0) ff_stamp(p, 4, it, 6);
     }
   }
   __syncthreads();
   if (tid == 0) ff_stamp(p, 0, 0, 3);
-  if (warp == 12) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
