@@ -584,12 +584,19 @@ class ImpalaTrainer:
         batch = whichever ``batch_size`` slots of the SHARED ring it dequeues (the columns of a batch are exchangeable, so any
         disjoint slot sets form a valid sharding of the global batch of batch_size * world columns)"""
         try:
+            import sys
             import torch.distributed as dist
             from ...utils.numa import bind_to_gpu_numa
+            say = lambda msg: (sys.stderr.write(f'[learner {rank}] {msg}\n'), sys.stderr.flush())
+            torch.set_num_threads(1)           # forked child: the parent's OpenMP pool does not exist here (a parallel CPU op would hang)
             torch.cuda.set_device(rank)
             bind_to_gpu_numa(rank)
             os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+            say('init_process_group')
             dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+            say('process group up; building the learner')
+            self._ensure_learner()
+            say(f'learner ready (gradient path: {getattr(self.learner, "dp_path", "nccl")}); {iters} steps')
             self._publish_rank0_only = rank != 0
             self.learn_process(rank, self.actor_model, None, free_queue, full_queue, self.buffers, self.rnn_state_buffers, deq_lock, max_iters=iters)
             self.flush()
@@ -626,7 +633,19 @@ class ImpalaTrainer:
         for m in range(a.num_buffers):
             free_queue.put(m)
         t0 = timeit.default_timer()
-        results = [result_q.get() for _ in range(world)]
+        results = []
+        limit = float(os.environ.get('SRL_LEARNER_TIMEOUT_S', '3600'))
+        while len(results) < world:             # a learner that died without reporting must not hang the trainer
+            if not result_q.empty():
+                results.append(result_q.get())
+                continue
+            dead = [p.name for p in learners if not p.is_alive() and p.exitcode not in (0, None)]
+            if dead or timeit.default_timer() - t0 > limit:
+                for p in learners + actors:
+                    if p.is_alive():
+                        p.terminate()
+                raise RuntimeError(f'learner processes failed or timed out after {timeit.default_timer() - t0:.0f} s (dead: {dead}, reported: {len(results)}/{world})')
+            time.sleep(0.01)
         dt = timeit.default_timer() - t0
         for p in learners:
             p.join(timeout=30)

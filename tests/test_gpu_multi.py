@@ -70,7 +70,8 @@ same = all(torch.equal(ck['model_state_dict'][k], v) for k, v in t.actor_model.s
 print('RESULT ' + json.dumps(dict(steps=out['steps'], learners=out['learners'], checks=out['replica_checksums'], version=out['weights_version'],
       loss=out['total_loss'], moved=not torch.equal(w0, t.actor_model.state_dict()['fc.weight']), actor_equals_checkpoint=same, path=out['grad_path'])))
 """
-    r = subprocess.run([sys.executable, '-c', code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, SRL_LEARNER_TIMEOUT_S='150')
+    r = subprocess.run([sys.executable, '-c', code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
     out = r.stdout + '\n' + r.stderr
     line = [ln for ln in r.stdout.splitlines() if ln.startswith('RESULT ')]
     assert r.returncode == 0 and line, out[-4000:]
