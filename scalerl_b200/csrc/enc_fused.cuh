@@ -37,7 +37,8 @@ constexpr int FF_A1_BYTES = 31 * 1024;             // plane 1 starts at 13,312; 
 constexpr int FF_OFF_W2 = FF_W1_BYTES;
 constexpr int FF_OFF_U8 = FF_OFF_W2 + FF_W2_BYTES;
 constexpr int FF_OFF_X = FF_OFF_U8 + 2 * FF_U8_BYTES;
-constexpr int FF_OFF_A1 = FF_OFF_X + 2 * FF_X_BYTES;
+constexpr int FF_XS = 3;                     // X-tile stages: each (convert -> 16 MMAs -> commit) chain is latency-bound, three run interleaved
+constexpr int FF_OFF_A1 = FF_OFF_X + FF_XS * FF_X_BYTES;
 constexpr int FF_OFF_BAR = FF_OFF_A1 + FF_A1_BYTES;
 constexpr int FF_SMEM_BYTES = FF_OFF_BAR + 1024 + 1024;      // barriers + the two bias vectors
 static_assert(FF_SMEM_BYTES <= 232448, "shared memory budget");
@@ -54,6 +55,7 @@ struct EncFusedParams {
   bf16* a2;                  // [frames*81][64]
   int frames;
   int NFS;                   // frame capacity of the a1 planes (plane stride)
+  int exp_flags;             // diagnostics only (SRL_FUSED_EXP, results invalid): 1 converters skip the X-tile stores, 2 skip xs global stores, 4 conv1 epilogue skips its stores, 8 conv2 epilogue skips its stores
   unsigned long long* dbg;   // diagnostics (SRL_FUSED_DEBUG): CTA 0 stamps %globaltimer at [role][frame][event]; nullptr = off
 };
 constexpr int FF_DBG_EVENTS = 8, FF_DBG_FRAMES = 8;       // per role: 8 frames x 8 events
@@ -89,16 +91,17 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
   uint8_t* sA1 = smem + FF_OFF_A1;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FF_OFF_BAR);
   uint64_t* u8_full = bars;            // [2] producer tx
-  uint64_t* u8_empty = bars + 2;       // [2] 4 converter warps
-  uint64_t* x_full = bars + 4;         // [2] 4 converter warps
-  uint64_t* x_empty = bars + 6;        // [2] tcgen05.commit
-  uint64_t* acc1_full = bars + 8;      // [4] tcgen05.commit
-  uint64_t* acc1_empty = bars + 12;    // [4] 4 epilogue warps
-  uint64_t* a1_full = bars + 16;       // 4 epilogue warps
-  uint64_t* a1_empty = bars + 17;      // tcgen05.commit
-  uint64_t* acc2_full = bars + 18;     // tcgen05.commit
-  uint64_t* acc2_empty = bars + 19;    // 4 epilogue warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* u8_empty = bars + 2;       // [2] 8 converter warps
+  uint64_t* x_full = bars + 4;         // [FF_XS] 8 converter warps
+  uint64_t* x_empty = bars + 7;        // [FF_XS] tcgen05.commit
+  uint64_t* acc1_full = bars + 10;     // [4] tcgen05.commit
+  uint64_t* acc1_empty = bars + 14;    // [4] 4 epilogue warps
+  uint64_t* a1_full = bars + 18;       // 4 epilogue warps
+  uint64_t* a1_empty = bars + 19;      // tcgen05.commit
+  uint64_t* acc2_full = bars + 20;     // tcgen05.commit
+  uint64_t* acc2_empty = bars + 21;    // 4 epilogue warps
+  uint64_t* exp_done = bars + 22;      // [2] diagnostics (exp_flags & 16)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nmine = p.frames > (int)blockIdx.x ? (p.frames - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (tid == 0) ff_stamp(p, 0, 0, 0);
@@ -109,9 +112,10 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
   else if (tid < 96) s_b2[tid - 32] = __ldg(p.b2 + tid - 32);
   if (warp == 16) {
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) { mbar_init(&u8_full[i], 1); mbar_init(&u8_empty[i], FF_CONV_WARPS); mbar_init(&x_full[i], FF_CONV_WARPS); mbar_init(&x_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&u8_full[i], 1); mbar_init(&u8_empty[i], FF_CONV_WARPS); }
+      for (int i = 0; i < FF_XS; ++i) { mbar_init(&x_full[i], FF_CONV_WARPS); mbar_init(&x_empty[i], 1); }
       for (int j = 0; j < 4; ++j) { mbar_init(&acc1_full[j], 1); mbar_init(&acc1_empty[j], 4); }
-      mbar_init(a1_full, 4); mbar_init(a1_empty, 1); mbar_init(acc2_full, 1); mbar_init(acc2_empty, 4);
+      mbar_init(a1_full, 4); mbar_init(a1_empty, 1); mbar_init(acc2_full, 1); mbar_init(acc2_empty, 4); mbar_init(&exp_done[0], 1); mbar_init(&exp_done[1], 1);
       mbar_fence_init();
     }
     __syncwarp();
@@ -170,7 +174,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) ff_stamp(p, 0, 0, 2);
 
-  if (warp == 16) {
+  const bool free_run = (p.exp_flags & 16) != 0;     // diagnostics: only the two MMA issuers run, without waiting for anybody
+  if (free_run && warp != 17 && warp != 18) {
+  } else if (warp == 16) {
     // ------------------------------------------------------------------------------------------------ producer
     if (lane == 0) {
       for (int it = 0; it < nmine; ++it) {
@@ -188,9 +194,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
       const uint32_t w1 = smem_u32(sW1);
       for (int it = 0; it < nmine; ++it) {
         for (int j = 0; j < 4; ++j) {
-          const int n = 4 * it + j, s = n & 1;
-          mbar_wait(&x_full[s], (n >> 1) & 1);
+          const int n = 4 * it + j, s = n % FF_XS;
+          if (!free_run) {
+          mbar_wait(&x_full[s], (n / FF_XS) & 1);
           mbar_wait(&acc1_empty[j], (it & 1) ^ 1);
+          }
           tc_fence_after();
           const uint32_t x0 = smem_u32(sX + s * FF_X_BYTES);
 #pragma unroll
@@ -205,6 +213,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
           ff_stamp(p, 2, it, j);
         }
       }
+      if (free_run) { umma_commit(&exp_done[0]); mbar_wait(&exp_done[0], 0); }
     }
   } else if (warp == 18) {
     // ------------------------------------------------------------------------------------------------ MMA issuer: conv2
@@ -212,8 +221,10 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
       constexpr uint32_t idesc2 = make_idesc_bf16(128, 64, 0, 0);
       const uint32_t w2 = smem_u32(sW2), a1s = smem_u32(sA1);
       for (int it = 0; it < nmine; ++it) {
+        if (!free_run) {
         mbar_wait(a1_full, it & 1);
         mbar_wait(acc2_empty, (it & 1) ^ 1);
+        }
         tc_fence_after();
         ff_stamp(p, 2, it, 4);
 #pragma unroll
@@ -227,6 +238,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
         umma_commit(acc2_full);
         ff_stamp(p, 2, it, 5);
       }
+      if (free_run) { umma_commit(&exp_done[1]); mbar_wait(&exp_done[1], 0); }
     }
   } else if (warp >= 8) {
     // ------------------------------------------------------------------------------------------------ converters (256 threads)
@@ -240,25 +252,36 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
       const uint8_t* u8 = sU8 + ub * FF_U8_BYTES + src_g;
       bf16* xs_f = p.xs + (size_t)f * 441 * 64 + gp * 8;
       for (int j = 0; j < 4; ++j) {
-        const int n = 4 * it + j, s = n & 1;
-        mbar_wait_relaxed(&x_empty[s], ((n >> 1) & 1) ^ 1);
+        const int n = 4 * it + j, s = n % FF_XS;
+        // all ten source words of the thread's five rows first (the compiler cannot hoist shared loads above the shared stores below)
+        uint32_t w0[5], w1[5];
+        int Qs[5];
+        {
+          int Q = j * 128 + rb, Y = Q / 21, X = Q - Y * 21;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            Qs[k] = Q;
+            if (rb + 32 * k < 150 && Q < 441) {
+              w0[k] = *reinterpret_cast<const uint32_t*>(u8 + Y * 336 + 4 * X);
+              w1[k] = *reinterpret_cast<const uint32_t*>(u8 + Y * 336 + 84 + 4 * X);
+            }
+            Q += 32; X += 11; Y += 1;                     // 32 = 21 + 11
+            if (X >= 21) { X -= 21; Y += 1; }
+          }
+        }
+        mbar_wait(&x_empty[s], ((n / FF_XS) & 1) ^ 1);    // on the critical cycle (MMA commit -> refill): tight poll
         uint8_t* x = sX + s * FF_X_BYTES;
-        int Q = j * 128 + rb, Y = Q / 21, X = Q - Y * 21;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
           const int row = rb + 32 * k;
           if (row < 150) {
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (Q < 441) {
-              const uint32_t w0 = *reinterpret_cast<const uint32_t*>(u8 + Y * 336 + 4 * X);
-              const uint32_t w1 = *reinterpret_cast<const uint32_t*>(u8 + Y * 336 + 84 + 4 * X);
-              v = u8x8_to_bf16x8(w0, w1);
-              if (row < 128) *reinterpret_cast<uint4*>(xs_f + (size_t)Q * 64) = v;     // conv1 wgrad's operand
+            if (Qs[k] < 441) {
+              v = u8x8_to_bf16x8(w0[k], w1[k]);
+              if (row < 128 && !(p.exp_flags & 2)) *reinterpret_cast<uint4*>(xs_f + (size_t)Qs[k] * 64) = v;     // conv1 wgrad's operand
             }
-            *reinterpret_cast<uint4*>(x + swz128(row, gp)) = v;
+            if (!(p.exp_flags & 1)) *reinterpret_cast<uint4*>(x + swz128(row, gp)) = v;
           }
-          Q += 32; X += 11; Y += 1;                       // 32 = 21 + 11
-          if (X >= 21) { X -= 21; Y += 1; }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -286,7 +309,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
         if (lane == 0) mbar_arrive(&acc1_empty[j]);          // accumulator drained: conv1 of the next frame may reuse it
         if (j == 0) mbar_wait_relaxed(a1_empty, (it & 1) ^ 1);   // conv2 of the previous frame has finished reading the planes
         const int Q = j * 128 + tid, oh = Q / 21, ow = Q - oh * 21;
-        if (Q < 441 && oh < 20 && ow < 20) {
+        if (Q < 441 && oh < 20 && ow < 20 && !(p.exp_flags & 4)) {
           float v[32];
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
@@ -331,7 +354,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc2_empty);
-      if (ok) {
+      if (ok && !(p.exp_flags & 8)) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float v[16];
@@ -355,7 +378,10 @@ inline cudaError_t enc_fused_fwd_launch(const EncFusedParams& p, int max_ctas, c
   if (p.frames <= 0) return cudaSuccess;
   static PerDeviceOnce once;
   { cudaError_t e = ensure_max_dynamic_smem(once, enc_fused_fwd_kernel, FF_SMEM_BYTES); if (e != cudaSuccess) return e; }
-  const int grid = p.frames < max_ctas ? p.frames : max_ctas;
+  // balanced grid: 672 frames on 148 SMs would be 80 CTAs x 5 + 68 x 4 frames, exactly as slow as 135 x 5; the SMs left free run
+  // the weight re-pack kernel (needed only by conv3 / fc) undisturbed
+  const int per = (p.frames + max_ctas - 1) / max_ctas;
+  const int grid = (p.frames + per - 1) / per;
   return launch_chain<PDL_RESFWD>(enc_fused_fwd_kernel, dim3(grid), dim3(FF_THREADS), FF_SMEM_BYTES, stream, p);
 }
 

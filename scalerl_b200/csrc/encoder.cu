@@ -10,36 +10,85 @@
 namespace srl {
 
 // fp32 master parameters (PyTorch layouts) -> bf16 operand copies in the layouts the GEMMs consume.
+// One launch, three block roles (fc.weight is 96 % of the elements and is written twice -- K-major for the forward GEMM, transposed
+// for dgrad -- so both copies go through a shared-memory tile: coalesced fp32 reads, >= 128-byte contiguous bf16 writes):
+//   blocks [0, 256)    wfk[j][hw*64 + c] = Wfc[j][c*49 + hw]        two rows j per block
+//   blocks [256, 512)  wfd[hw*64 + c][j] = Wfc[j][c*49 + hw]        tile = 64 j x 2 c (98 consecutive source columns)
+//   blocks [512, 800)  the conv weight copies (147,456 elements), two elements per thread
+constexpr int PACK_BLOCKS_FK = 256, PACK_BLOCKS_FD = 256, PACK_BLOCKS_CONV = 288;
+SRL_DEVINL void pack_store(bf16* __restrict__ out, bf16* __restrict__ out_lo, int64_t i, float v) {
+  const bf16 hi = __float2bfloat16_rn(v);
+  out[i] = hi;
+  if (out_lo) out_lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));     // fp32-accurate mode: w = hi + lo to 16 significant bits
+}
+SRL_DEVINL void pack_store2(bf16* __restrict__ out, bf16* __restrict__ out_lo, int64_t i, float v0, float v1) {      // i even
+  const bf16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+  *reinterpret_cast<uint32_t*>(out + i) = pack_bf16x2(v0, v1);
+  if (out_lo) *reinterpret_cast<uint32_t*>(out_lo + i) = pack_bf16x2(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
+}
 __global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __restrict__ out, bf16* __restrict__ out_lo) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < WPack::TOTAL; i += (int64_t)gridDim.x * blockDim.x) {
-    float v;
-    if (i < WPack::W2K) {                       // w1k[co][(kh2*2+kw2)*64 + c*16 + dy*4 + dx] = W1[co][c][4kh2+dy][4kw2+dx]
-      const int e = (int)(i - WPack::W1K), co = e >> 8, k = e & 255, tap = k >> 6, q = k & 63;
-      const int c = q >> 4, dy = (q >> 2) & 3, dx = q & 3, kh = 4 * (tap >> 1) + dy, kw = 4 * (tap & 1) + dx;
-      v = p.w1[co * 256 + c * 64 + kh * 8 + kw];
-    } else if (i < WPack::W3K) {                // w2k[co][(kh*4+kw)*32 + c]
-      const int e = (int)(i - WPack::W2K), co = e >> 9, k = e & 511, tap = k >> 5, c = k & 31;
-      v = p.w2[((co * 32 + c) << 4) + tap];
-    } else if (i < WPack::WFK) {                // w3k[co][(kh*3+kw)*64 + c]
-      const int e = (int)(i - WPack::W3K), co = e / 576, k = e - co * 576, tap = k >> 6, c = k & 63;
-      v = p.w3[(co * 64 + c) * 9 + tap];
-    } else if (i < WPack::WFD) {                // wfk[j][hw*64 + c] = Wfc[j][c*49 + hw]
-      const int e = (int)(i - WPack::WFK), j = e / 3136, k = e - j * 3136, hw = k >> 6, c = k & 63;
-      v = p.wf[(size_t)j * 3136 + c * 49 + hw];
-    } else if (i < WPack::W3D) {                // wfd[hw*64 + c][j]
-      const int e = (int)(i - WPack::WFD), row = e >> 9, j = e & 511, hw = row >> 6, c = row & 63;
-      v = p.wf[(size_t)j * 3136 + c * 49 + hw];
-    } else if (i < WPack::W2D) {                // w3d[c][(kh*3+kw)*64 + co]
-      const int e = (int)(i - WPack::W3D), c = e / 576, k = e - c * 576, tap = k >> 6, co = k & 63;
-      v = p.w3[(co * 64 + c) * 9 + tap];
-    } else {                                    // w2d[cls][c][(kh'*2+kw')*64 + co], kh = ph + 2kh', kw = pw + 2kw'
-      const int e = (int)(i - WPack::W2D), cls = e >> 13, r = e & 8191, c = r >> 8, k = r & 255, t = k >> 6, co = k & 63;
-      const int kh = (cls >> 1) + 2 * (t >> 1), kw = (cls & 1) + 2 * (t & 1);
-      v = p.w2[((co * 32 + c) << 4) + kh * 4 + kw];
+  __shared__ __align__(16) float tile[64 * 99];                 // role 1: two fc rows (2 x 3136); role 2: [64 j][99]
+  const int t = threadIdx.x, b = blockIdx.x;
+  if (b < PACK_BLOCKS_FK) {
+    const float4* src = reinterpret_cast<const float4*>(p.wf + (size_t)(2 * b) * 3136);       // rows 2b, 2b+1: 1568 float4, all loads in flight
+    float4 v[7];
+#pragma unroll
+    for (int u = 0; u < 7; ++u) { const int q = t + 256 * u; if (q < 1568) v[u] = __ldg(src + q); }
+#pragma unroll
+    for (int u = 0; u < 7; ++u) { const int q = t + 256 * u; if (q < 1568) *reinterpret_cast<float4*>(tile + 4 * q) = v[u]; }
+    __syncthreads();
+#pragma unroll 4
+    for (int pp = t; pp < 2 * 1568; pp += 256) {   // output pair: row r, k = 2 pp' = hw*64 + c
+      const int r = pp >= 1568, k = 2 * (pp - r * 1568), hw = k >> 6, c = k & 63;
+      const float* row = tile + r * 3136;
+      pack_store2(out, out_lo, WPack::WFK + (int64_t)(2 * b + r) * 3136 + k, row[c * 49 + hw], row[(c + 1) * 49 + hw]);
     }
-    const bf16 hi = __float2bfloat16_rn(v);
-    out[i] = hi;
-    if (out_lo) out_lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));     // fp32-accurate mode: w = hi + lo to 16 significant bits
+  } else if (b < PACK_BLOCKS_FK + PACK_BLOCKS_FD) {
+    const int bb = b - PACK_BLOCKS_FK, j0 = (bb & 7) * 64, c0 = (bb >> 3) * 2;
+    // 64 rows x 49 float2 (98 consecutive source columns c0*49 .. c0*49+97), all 13 loads of a thread in flight together
+    float2 v[13];
+#pragma unroll
+    for (int u = 0; u < 13; ++u) {
+      const int q = t + 256 * u, jj = q / 49, e = q - jj * 49;
+      if (q < 64 * 49) v[u] = __ldg(reinterpret_cast<const float2*>(p.wf + (size_t)(j0 + jj) * 3136 + c0 * 49 + 2 * e));
+    }
+#pragma unroll
+    for (int u = 0; u < 13; ++u) {
+      const int q = t + 256 * u, jj = q / 49, e = q - jj * 49;
+      if (q < 64 * 49) { tile[jj * 99 + 2 * e] = v[u].x; tile[jj * 99 + 2 * e + 1] = v[u].y; }
+    }
+    __syncthreads();
+    const int lane = t & 31, warp = t >> 5;
+    for (int kk = warp; kk < 98; kk += 8) {      // source column kk = cc*49 + hw -> destination row hw*64 + c0 + cc
+      const int cc = kk >= 49, hw = kk - cc * 49;
+      pack_store2(out, out_lo, WPack::WFD + (int64_t)(hw * 64 + c0 + cc) * 512 + j0 + 2 * lane, tile[(2 * lane) * 99 + kk], tile[(2 * lane + 1) * 99 + kk]);
+    }
+  } else {
+    const int bb = b - PACK_BLOCKS_FK - PACK_BLOCKS_FD;
+    constexpr int64_t NCONV = WPack::WFK + (WPack::TOTAL - WPack::W3D);       // the copies before and after the two fc blocks
+    for (int64_t n = (int64_t)bb * 256 + t; n < NCONV; n += (int64_t)PACK_BLOCKS_CONV * 256) {
+      const int64_t i = n < WPack::WFK ? n : n - WPack::WFK + WPack::W3D;
+      float v;
+      if (i < WPack::W2K) {                       // w1k[co][(kh2*2+kw2)*64 + c*16 + dy*4 + dx] = W1[co][c][4kh2+dy][4kw2+dx]
+        const int e = (int)(i - WPack::W1K), co = e >> 8, k = e & 255, tap = k >> 6, q = k & 63;
+        const int c = q >> 4, dy = (q >> 2) & 3, dx = q & 3, kh = 4 * (tap >> 1) + dy, kw = 4 * (tap & 1) + dx;
+        v = p.w1[co * 256 + c * 64 + kh * 8 + kw];
+      } else if (i < WPack::W3K) {                // w2k[co][(kh*4+kw)*32 + c]
+        const int e = (int)(i - WPack::W2K), co = e >> 9, k = e & 511, tap = k >> 5, c = k & 31;
+        v = p.w2[((co * 32 + c) << 4) + tap];
+      } else if (i < WPack::WFK) {                // w3k[co][(kh*3+kw)*64 + c]
+        const int e = (int)(i - WPack::W3K), co = e / 576, k = e - co * 576, tap = k >> 6, c = k & 63;
+        v = p.w3[(co * 64 + c) * 9 + tap];
+      } else if (i < WPack::W2D) {                // w3d[c][(kh*3+kw)*64 + co]
+        const int e = (int)(i - WPack::W3D), c = e / 576, k = e - c * 576, tap = k >> 6, co = k & 63;
+        v = p.w3[(co * 64 + c) * 9 + tap];
+      } else {                                    // w2d[cls][c][(kh'*2+kw')*64 + co], kh = ph + 2kh', kw = pw + 2kw'
+        const int e = (int)(i - WPack::W2D), cls = e >> 13, r = e & 8191, c = r >> 8, k = r & 255, tt = k >> 6, co = k & 63;
+        const int kh = (cls >> 1) + 2 * (tt >> 1), kw = (cls & 1) + 2 * (tt & 1);
+        v = p.w2[((co * 32 + c) << 4) + kh * 4 + kw];
+      }
+      pack_store(out, out_lo, i, v);
+    }
   }
 }
 
@@ -76,7 +125,7 @@ __global__ void __launch_bounds__(352) obs_s2d_kernel(const uint8_t* __restrict_
 }
 
 cudaError_t launch_pack_weights(const ParamPtrs& p, bf16* wpack, cudaStream_t st, bf16* wpack_lo) {
-  pack_weights_kernel<<<1184, 256, 0, st>>>(p, wpack, wpack_lo);
+  pack_weights_kernel<<<PACK_BLOCKS_FK + PACK_BLOCKS_FD + PACK_BLOCKS_CONV, 256, 0, st>>>(p, wpack, wpack_lo);
   return cudaGetLastError();
 }
 
@@ -254,7 +303,8 @@ cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, 
       if (e && atoi(e) != 0 && cudaMalloc(&q, 5 * FF_DBG_FRAMES * FF_DBG_EVENTS * 8) == cudaSuccess) cudaMemset(q, 0, 5 * FF_DBG_FRAMES * FF_DBG_EVENTS * 8);
       return q;
     }();
-    EncFusedParams q{obs, p.w1, p.b1, p.w2, p.b2, buf.xs, buf.a1, buf.a2, frames, buf.NF, dbg_buf};
+    static const int exp_flags = [] { const char* e = getenv("SRL_FUSED_EXP"); return e ? atoi(e) : 0; }();
+    EncFusedParams q{obs, p.w1, p.b1, p.w2, p.b2, buf.xs, buf.a1, buf.a2, frames, buf.NF, exp_flags, dbg_buf};
     g_fused_dbg = dbg_buf;
     pf.b(PS_ENC_FUSED); SRL_TRY(enc_fused_fwd_launch(q, kPersistentCtas, st)); pf.e(PS_ENC_FUSED);
     if (wait_before_conv1) SRL_TRY(cudaStreamWaitEvent(st, wait_before_conv1, 0));      // conv3 / fc read the packed weights

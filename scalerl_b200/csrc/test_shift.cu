@@ -144,12 +144,12 @@ __global__ void __launch_bounds__(96) mma_rate_kernel(int N, int shift, int reps
   uint8_t* sA = smem;                   // 192 rows x 128 B
   uint8_t* sB = smem + 24576;           // 256 rows x 128 B
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 24576 + 32768);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (24576 + 32768) / 16; i += 96) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
   fence_proxy_async_smem();
   if (warp == 2) {
-    if ((tid & 31) == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    if ((tid & 31) == 0) { for (int i = 0; i < 12; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
     __syncwarp();
     tmem_alloc(tmem_slot, 512);
   }
@@ -159,11 +159,17 @@ __global__ void __launch_bounds__(96) mma_rate_kernel(int N, int shift, int reps
   const uint32_t tmem_base = *tmem_slot;
   if (warp < issuers && (tid & 31) == 0) {
     const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    // shift packs three fields: bits 0-7 the A start row, bits 8-15 'commit every n MMAs' (0 = only at the end), bits 16-19 commits per point
+    const int commit_every = (shift >> 8) & 255, ncommit = (shift >> 16) & 15;
+    shift &= 255;
     const uint32_t a0 = smem_u32(sA) + shift * 128, b0 = smem_u32(sB), acc = tmem_base + warp * 256;
+    uint64_t* scratch = bars + 4 + warp * 4;      // barriers nobody waits on (phases just advance)
     const long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
       const int k = r & 3;
       umma_bf16(acc, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc, r != 0);
+      if (commit_every && (r + 1) % commit_every == 0)
+        for (int c = 0; c < ncommit; ++c) umma_commit(&scratch[c]);
     }
     const long long t1 = clock64();
     umma_commit(&bars[warp]);

@@ -65,7 +65,7 @@ extern "C" int srl_test_pdl(int* flag, int* out, int nblk, unsigned delay_ns, vo
   return 0;
 }
 extern "C" int srl_test_mma_rate(int N, int shift, int reps, int issuers, long long* out_cycles, void* stream) {
-  REQ(out_cycles && reps >= 1 && (issuers == 1 || issuers == 2) && N >= 16 && N <= 256 && N % 16 == 0 && shift >= 0 && shift <= 32, "test_mma_rate: bad argument");
+  REQ(out_cycles && reps >= 1 && (issuers == 1 || issuers == 2) && N >= 16 && N <= 256 && N % 16 == 0 && shift >= 0 && (shift & 255) <= 32, "test_mma_rate: bad argument");
   CU(test_mma_rate(N, shift, reps, issuers, out_cycles, (cudaStream_t)stream), "test_mma_rate");
   return 0;
 }

@@ -4,6 +4,7 @@ import os
 import sys
 
 os.environ['SRL_FUSED_DEBUG'] = '1'
+os.environ['SRL_FUSED_FWD'] = '1'
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch                                    # noqa: E402

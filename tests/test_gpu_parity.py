@@ -216,6 +216,34 @@ def test_forward_vs_emulating_oracle(T, B):
     assert rel_l2(out['policy_logits'].cpu(), lg32) < 2e-2
 
 
+@pytest.mark.parametrize('precision', ['bf16', 'fp32_split'])
+def test_packed_weight_copies_are_the_documented_permutations(precision):
+    """pack_weights_kernel: every bf16 operand copy (kernels.h WPack) is bit-for-bit the bf16 rounding of the fp32 master in the
+    documented layout -- and in the fp32-accurate mode the low copy is the rounding of the remainder"""
+    A = 6
+    L, params = _learner(2, 2, A, 5, precision=precision)
+    L.forward({k: dev(v) for k, v in O.synthetic_batch(2, 2, A, seed=1).items()})       # runs the pack
+    w1, w2, w3, wf = (params[k].float() for k in ('conv1.weight', 'conv2.weight', 'conv3.weight', 'fc.weight'))
+    want = [
+        w1.view(32, 4, 2, 4, 2, 4).permute(0, 2, 4, 1, 3, 5).reshape(-1),                # w1k[co][(kh2,kw2)][c,dy,dx]
+        w2.permute(0, 2, 3, 1).reshape(-1),                                              # w2k[co][(kh,kw)][c]
+        w3.permute(0, 2, 3, 1).reshape(-1),                                              # w3k[co][(kh,kw)][c]
+        wf.view(512, 64, 49).permute(0, 2, 1).reshape(-1),                               # wfk[j][hw][c]
+        wf.view(512, 64, 49).permute(2, 1, 0).reshape(-1),                               # wfd[hw][c][j]
+        w3.permute(1, 2, 3, 0).reshape(-1),                                              # w3d[c][(kh,kw)][co]
+        w2.view(64, 32, 2, 2, 2, 2).permute(3, 5, 1, 2, 4, 0).reshape(-1),               # w2d[(ph,pw)][c][(kh',kw')][co], kh = ph + 2 kh'
+    ]
+    want = torch.cat(want)
+    hi = want.to(torch.bfloat16)
+    got = L.debug_buffer('wpack').cpu()
+    assert got.numel() == want.numel()
+    assert torch.equal(got.view(torch.int16), hi.view(torch.int16))
+    if precision == 'fp32_split':
+        lo = (want - hi.float()).to(torch.bfloat16)
+        assert torch.equal(L.debug_buffer('wpack_lo').cpu().view(torch.int16), lo.view(torch.int16))
+    L.close()
+
+
 @pytest.mark.parametrize('T,B', [(4, 5), (1, 1), (20, 32), (3, 50)])
 def test_fused_encoder_front_equals_three_kernels(T, B):
     """enc_fused_fwd_kernel (u8 -> space-to-depth -> conv1 -> conv2 on the SM) writes the SAME bits as obs_s2d + conv1 + conv2: xs, both
