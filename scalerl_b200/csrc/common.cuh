@@ -83,6 +83,12 @@ SRL_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// one lane of the (converged) warp: the form the compiler recognises as 'exactly one thread' for the tcgen05 / TMA issue paths
+SRL_DEVINL uint32_t elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc]; one thread issues.
 SRL_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

@@ -189,57 +189,62 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
     }
   } else if (warp == 17) {
     // ------------------------------------------------------------------------------------------------ MMA issuer: conv1
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_bf16(128, 32, 0, 0);
-      const uint32_t w1 = smem_u32(sW1);
-      for (int it = 0; it < nmine; ++it) {
-        for (int j = 0; j < 4; ++j) {
-          const int n = 4 * it + j, s = n % FF_XS;
-          if (!free_run) {
+    // The whole warp runs this code converged and ONE elected lane issues: with `elect.sync` the compiler keeps descriptors in uniform
+    // registers and emits the 16 tcgen05.mma of a tile back to back (40 clk each for N = 32); under `if (lane == 0)` it wraps every MMA in a
+    // vote loop (57+ clk each) -- profiles/r02_mma_issue_rate.md.  Descriptors are base + constant (the 14-bit address field cannot carry).
+    const uint32_t leader = elect_one_sync();
+    constexpr uint32_t idesc1 = make_idesc_bf16(128, 32, 0, 0);
+    const uint64_t w1d = make_smem_desc(smem_u32(sW1), 16, 1024);
+    for (int it = 0; it < nmine; ++it) {
+      for (int j = 0; j < 4; ++j) {
+        const int n = 4 * it + j, s = n % FF_XS;
+        if (!free_run) {
           mbar_wait(&x_full[s], (n / FF_XS) & 1);
           mbar_wait(&acc1_empty[j], (it & 1) ^ 1);
-          }
-          tc_fence_after();
-          const uint32_t x0 = smem_u32(sX + s * FF_X_BYTES);
+        }
+        tc_fence_after();
+        const uint64_t xd = make_smem_desc(smem_u32(sX + s * FF_X_BYTES), 16, 1024);
+        const uint32_t acc = tmem_base + j * 32;
+        if (leader) {
 #pragma unroll
-          for (int tap = 0; tap < 4; ++tap) {
-            const uint32_t a0 = x0 + ((tap >> 1) * 21 + (tap & 1)) * 128, b0 = w1 + tap * 4096;
+          for (int tap = 0; tap < 4; ++tap)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + j * 32, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc1, (tap | k) != 0);
-          }
+              umma_bf16(acc, xd + (uint64_t)(((tap >> 1) * 21 + (tap & 1)) * 8 + k * 2), w1d + (uint64_t)(tap * 256 + k * 2), idesc1, (tap | k) != 0);
           umma_commit(&x_empty[s]);
           umma_commit(&acc1_full[j]);
           ff_stamp(p, 2, it, j);
         }
+        __syncwarp();
       }
-      if (free_run) { umma_commit(&exp_done[0]); mbar_wait(&exp_done[0], 0); }
     }
+    if (free_run) { if (leader) umma_commit(&exp_done[0]); __syncwarp(); mbar_wait(&exp_done[0], 0); }
   } else if (warp == 18) {
     // ------------------------------------------------------------------------------------------------ MMA issuer: conv2
-    if (lane == 0) {
-      constexpr uint32_t idesc2 = make_idesc_bf16(128, 64, 0, 0);
-      const uint32_t w2 = smem_u32(sW2), a1s = smem_u32(sA1);
-      for (int it = 0; it < nmine; ++it) {
-        if (!free_run) {
+    const uint32_t leader = elect_one_sync();
+    constexpr uint32_t idesc2 = make_idesc_bf16(128, 64, 0, 0);
+    const uint64_t w2d = make_smem_desc(smem_u32(sW2), 16, 1024), a1d = make_smem_desc(smem_u32(sA1), 16, 1024);
+    for (int it = 0; it < nmine; ++it) {
+      if (!free_run) {
         mbar_wait(a1_full, it & 1);
         mbar_wait(acc2_empty, (it & 1) ^ 1);
-        }
-        tc_fence_after();
+      }
+      tc_fence_after();
+      if (leader) {
         ff_stamp(p, 2, it, 4);
 #pragma unroll
-        for (int tap = 0; tap < 8; ++tap) {       // tap = (kh, kww): plane kh & 1, shift (kh >> 1) * 10 + kww
-          const uint32_t a0 = a1s + ((tap >> 1) & 1) * FF_A1_PLANE + ((tap >> 2) * 10 + (tap & 1)) * 128, b0 = w2 + tap * 8192;
+        for (int tap = 0; tap < 8; ++tap)         // tap = (kh, kww): plane kh & 1, shift (kh >> 1) * 10 + kww
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + 128, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc2, (tap | k) != 0);
-        }
+            umma_bf16(tmem_base + 128, a1d + (uint64_t)((((tap >> 1) & 1) * FF_A1_PLANE + ((tap >> 2) * 10 + (tap & 1)) * 128) / 16 + k * 2),
+                      w2d + (uint64_t)(tap * 512 + k * 2), idesc2, (tap | k) != 0);
         umma_commit(a1_empty);
         umma_commit(acc2_full);
         ff_stamp(p, 2, it, 5);
       }
-      if (free_run) { umma_commit(&exp_done[1]); mbar_wait(&exp_done[1], 0); }
+      __syncwarp();
     }
+    if (free_run) { if (leader) umma_commit(&exp_done[1]); __syncwarp(); mbar_wait(&exp_done[1], 0); }
   } else if (warp >= 8) {
     // ------------------------------------------------------------------------------------------------ converters (256 threads)
     // thread = (16-byte chunk gp = (c, dy pair), row slot rb); rows rb, rb + 32, ... of the 150-row tile: two u32 (2 x 4 dx bytes) -> 8 bf16

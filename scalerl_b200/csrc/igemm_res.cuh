@@ -110,33 +110,39 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
       }
     }
   } else if (warp == 5) {
-    if ((tid & 31) == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, P::BN, 0, 0);
-      mbar_wait(w_full, 0);
-      int it = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int s = it % STAGES, b = it & 1;
-        mbar_wait(&acc_empty[b], ((it >> 1) & 1) ^ 1);       // epilogue drained this accumulator (two tiles ago)
-        mbar_wait(&in_full[s], (it / STAGES) & 1);
-        tc_fence_after();
-        const uint32_t in0 = smem_u32(sIn + s * C::IN_BYTES), w0 = smem_u32(sW);
-        const uint32_t acc = tmem_base + b * P::BN;
+    // The warp stays converged and ONE elected lane issues: with elect.sync the compiler keeps the descriptors in uniform registers and
+    // emits a tile's tcgen05.mma back to back (40 / 48 clk each for N = 32 / 64); under `if (lane == 0)` every MMA sits in a vote loop
+    // (57+ clk) -- profiles/r02_mma_issue_rate.md.  Descriptors are base + constant: the 14-bit address field cannot carry.
+    const uint32_t leader = elect_one_sync();
+    constexpr uint32_t idesc = make_idesc_bf16(128, P::BN, 0, 0);
+    mbar_wait(w_full, 0);
+    const uint64_t wd = make_smem_desc(smem_u32(sW), 16, 1024);
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = it % STAGES, b = it & 1;
+      mbar_wait(&acc_empty[b], ((it >> 1) & 1) ^ 1);       // epilogue drained this accumulator (two tiles ago)
+      mbar_wait(&in_full[s], (it / STAGES) & 1);
+      tc_fence_after();
+      const uint64_t ind = make_smem_desc(smem_u32(sIn + s * C::IN_BYTES), 16, 1024);
+      const uint32_t acc = tmem_base + b * P::BN;
+      if (leader) {
 #pragma unroll
         for (int j = 0; j < P::NT; ++j) {
-          const uint32_t a0 = in0 + P::tap_win(j) * C::WIN_BYTES + P::tap_shift(j) * 128;
-          const uint32_t b0 = w0 + j * P::BN * 128;
+          const uint64_t ad = ind + (uint64_t)((P::tap_win(j) * C::WIN_BYTES + P::tap_shift(j) * 128) / 16);
+          const uint64_t bd = wd + (uint64_t)(j * P::BN * 128 / 16);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_bf16(acc, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc, (j | k) != 0);
+            umma_bf16(acc, ad + 2 * k, bd + 2 * k, idesc, (j | k) != 0);
             if constexpr (SPLIT)          // hi * lo(weights)
-              umma_bf16(acc, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + C::W_HI_BYTES + k * 32, 16, 1024), idesc, 1);
+              umma_bf16(acc, ad + 2 * k, bd + (uint64_t)(C::W_HI_BYTES / 16 + 2 * k), idesc, 1);
             if constexpr (C::ALO)         // lo(activations) * hi
-              umma_bf16(acc, make_smem_desc(a0 + C::IN_HI_BYTES + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc, 1);
+              umma_bf16(acc, ad + (uint64_t)(C::IN_HI_BYTES / 16 + 2 * k), bd + 2 * k, idesc, 1);
           }
         }
         umma_commit(&in_empty[s]);
         umma_commit(&acc_full[b]);
       }
+      __syncwarp();
     }
   } else {
     int it = 0;
@@ -266,15 +272,16 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
       }
     }
   } else if (warp == 5) {
-    if ((tid & 31) == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
-      const uint32_t ones = smem_u32(sOnes);
-      for (int i = 0; i < nch; ++i) {
-        const int s = i % STAGES;
-        mbar_wait(&full[s], (i / STAGES) & 1);
-        tc_fence_after();
-        const uint32_t st = smem_u32(sSt + s * C::STAGE_BYTES);
-        const uint32_t dy0 = st + C::X_BYTES;
+    const uint32_t leader = elect_one_sync();        // converged warp, one elected issuing lane (see res_fwd_kernel)
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+    const uint32_t ones = smem_u32(sOnes);
+    for (int i = 0; i < nch; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(&full[s], (i / STAGES) & 1);
+      tc_fence_after();
+      const uint32_t st = smem_u32(sSt + s * C::STAGE_BYTES);
+      const uint64_t dyd = make_smem_desc(st + C::X_BYTES, 8192, 1024);
+      if (leader) {
 #pragma unroll
         for (int a = 0; a < P::NACC; ++a) {
           const uint32_t blk0 = st + P::acc_win(a) * C::WIN_BYTES + P::acc_shift0(a) * 128;
@@ -283,22 +290,22 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
           const uint32_t blk1 = P::acc_shift1(a) >= 0 ? st + P::acc_win1(a) * C::WIN_BYTES + P::acc_shift1(a) * 128
                                                       : (BIAS_SMEM ? blk0 + 128 : ones);
           const uint32_t lbo = blk1 - blk0;      // byte distance between the two 64-row M blocks (any multiple of 16)
+          const uint64_t xd = make_smem_desc(blk0, lbo, 1024);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {          // 128 positions = 8 x (K = 16)
-            umma_bf16(tmem_base + a * 64, make_smem_desc(blk0 + k * 2048, lbo, 1024), make_smem_desc(dy0 + k * 2048, 8192, 1024), idesc,
-                      (i | k) != 0);
+          for (int k = 0; k < 8; ++k) {          // 128 positions = 8 x (K = 16): +2048 B per step
+            umma_bf16(tmem_base + a * 64, xd + 128 * k, dyd + 128 * k, idesc, (i | k) != 0);
             if constexpr (SPLIT)         // hi(x) * lo(dy)
-              umma_bf16(tmem_base + a * 64, make_smem_desc(blk0 + k * 2048, lbo, 1024), make_smem_desc(dy0 + C::DY_BYTES + k * 2048, 8192, 1024),
-                        idesc, 1);
+              umma_bf16(tmem_base + a * 64, xd + 128 * k, dyd + (uint64_t)(C::DY_BYTES / 16 + 128 * k), idesc, 1);
             if constexpr (C::ALO)        // lo(x) * hi(dy)
-              umma_bf16(tmem_base + a * 64, make_smem_desc(blk0 + C::X_HI_BYTES + k * 2048, lbo, 1024), make_smem_desc(dy0 + k * 2048, 8192, 1024),
-                        idesc, 1);
+              umma_bf16(tmem_base + a * 64, xd + (uint64_t)(C::X_HI_BYTES / 16 + 128 * k), dyd + 128 * k, idesc, 1);
           }
         }
         umma_commit(&empty[s]);
       }
-      umma_commit(done);
+      __syncwarp();
     }
+    if (leader) umma_commit(done);
+    __syncwarp();
   } else {
     if constexpr (BIAS_SMEM) {
       // bias gradient = column sums of dy, taken from the staged dy tiles while the MMAs run (no all-ones accumulator).

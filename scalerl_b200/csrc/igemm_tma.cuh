@@ -129,31 +129,32 @@ __global__ void __launch_bounds__(IGT_THREADS) igemm_tma_kernel(const __grid_con
       }
     }
   } else if (warp == 5) {
-    if ((tid & 31) == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, P::BN, P::A_MN ? 1 : 0, P::B_MN ? 1 : 0);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % P::STAGES;
-        mbar_wait(&full[s], (kb / P::STAGES) & 1);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(smem + s * C::STAGE_BYTES);
-        const uint32_t b0 = a0 + C::A_BYTES;
+    const uint32_t leader = elect_one_sync();        // converged warp, one elected issuing lane (see igemm_res.cuh res_fwd_kernel)
+    constexpr uint32_t idesc = make_idesc_bf16(128, P::BN, P::A_MN ? 1 : 0, P::B_MN ? 1 : 0);
+    constexpr uint32_t ASTEP = P::A_MN ? 2048 / 16 : 32 / 16, BSTEP = P::B_MN ? 2048 / 16 : 32 / 16;     // descriptor address units per K = 16
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % P::STAGES;
+      mbar_wait(&full[s], (kb / P::STAGES) & 1);
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(smem + s * C::STAGE_BYTES);
+      const uint64_t ad0 = P::A_MN ? make_smem_desc(a0, C::KROWS * 128, 1024) : make_smem_desc(a0, 16, 1024);
+      const uint64_t bd0 = P::B_MN ? make_smem_desc(a0 + C::A_BYTES, C::KROWS * 128, 1024) : make_smem_desc(a0 + C::A_BYTES, 16, 1024);
+      if (leader) {
 #pragma unroll
         for (int k = 0; k < C::MMAS; ++k) {
-          const uint64_t ad = P::A_MN ? make_smem_desc(a0 + k * 2048, C::KROWS * 128, 1024) : make_smem_desc(a0 + k * 32, 16, 1024);
-          const uint64_t bd = P::B_MN ? make_smem_desc(b0 + k * 2048, C::KROWS * 128, 1024) : make_smem_desc(b0 + k * 32, 16, 1024);
+          const uint64_t ad = ad0 + (uint64_t)(k * ASTEP), bd = bd0 + (uint64_t)(k * BSTEP);
           umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0);
           if constexpr (SPLIT) {        // hi * lo, lo * hi (the low tiles sit HALF_BYTES further into the stage)
-            const uint32_t a1 = a0 + C::HALF_BYTES, b1 = b0 + C::HALF_BYTES;
-            const uint64_t adl = P::A_MN ? make_smem_desc(a1 + k * 2048, C::KROWS * 128, 1024) : make_smem_desc(a1 + k * 32, 16, 1024);
-            const uint64_t bdl = P::B_MN ? make_smem_desc(b1 + k * 2048, C::KROWS * 128, 1024) : make_smem_desc(b1 + k * 32, 16, 1024);
-            umma_bf16(tmem_base, ad, bdl, idesc, 1);
-            umma_bf16(tmem_base, adl, bd, idesc, 1);
+            umma_bf16(tmem_base, ad, bd + (uint64_t)(C::HALF_BYTES / 16), idesc, 1);
+            umma_bf16(tmem_base, ad + (uint64_t)(C::HALF_BYTES / 16), bd, idesc, 1);
           }
         }
         umma_commit(&empty[s]);
       }
-      umma_commit(done);
+      __syncwarp();
     }
+    if (leader) umma_commit(done);
+    __syncwarp();
   } else {
     const int row = tid;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);

@@ -157,19 +157,32 @@ __global__ void __launch_bounds__(96) mma_rate_kernel(int N, int shift, int reps
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // shift packs fields: bits 0-7 the A start row, bits 8-15 'commit every n MMAs' (0 = only at the end), bits 16-19 commits per point,
+  // bits 20-23 the ISSUE-CODE variant: 0 = `if (lane == 0)` + make_smem_desc per MMA in a rolled loop (what the round-1 kernels do),
+  // 1 = same branch, 16 MMAs unrolled, descriptor = base + constant, 2 = warp-converged code, elect.sync-predicated unrolled MMAs
+  const int commit_every = (shift >> 8) & 255, ncommit = (shift >> 16) & 15, mode = (shift >> 20) & 15;
+  shift &= 255;
+  const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+  const uint32_t a0 = smem_u32(sA) + shift * 128, b0 = smem_u32(sB);
+  if (mode == 0 || mode == 1) {
   if (warp < issuers && (tid & 31) == 0) {
-    const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
-    // shift packs three fields: bits 0-7 the A start row, bits 8-15 'commit every n MMAs' (0 = only at the end), bits 16-19 commits per point
-    const int commit_every = (shift >> 8) & 255, ncommit = (shift >> 16) & 15;
-    shift &= 255;
-    const uint32_t a0 = smem_u32(sA) + shift * 128, b0 = smem_u32(sB), acc = tmem_base + warp * 256;
+    const uint32_t acc = tmem_base + warp * 256;
     uint64_t* scratch = bars + 4 + warp * 4;      // barriers nobody waits on (phases just advance)
     const long long t0 = clock64();
-    for (int r = 0; r < reps; ++r) {
-      const int k = r & 3;
-      umma_bf16(acc, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc, r != 0);
-      if (commit_every && (r + 1) % commit_every == 0)
-        for (int c = 0; c < ncommit; ++c) umma_commit(&scratch[c]);
+    if (mode == 0) {
+      for (int r = 0; r < reps; ++r) {
+        const int k = r & 3;
+        umma_bf16(acc, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc, r != 0);
+        if (commit_every && (r & (commit_every - 1)) == commit_every - 1)
+          for (int c = 0; c < ncommit; ++c) umma_commit(&scratch[c]);
+      }
+    } else {
+      const uint64_t ad = make_smem_desc(a0, 16, 1024), bd = make_smem_desc(b0, 16, 1024);
+      for (int r = 0; r < reps; r += 16) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) umma_bf16(acc, ad + 2 * (i & 3), bd + 2 * (i & 3), idesc, (r | i) != 0);
+        if (commit_every) for (int c = 0; c < ncommit; ++c) umma_commit(&scratch[c]);
+      }
     }
     const long long t1 = clock64();
     umma_commit(&bars[warp]);
@@ -177,6 +190,27 @@ __global__ void __launch_bounds__(96) mma_rate_kernel(int N, int shift, int reps
     const long long t2 = clock64();
     out[2 * warp] = t1 - t0;
     out[2 * warp + 1] = t2 - t0;
+  }
+  } else if (warp < issuers) {
+    const uint32_t acc = tmem_base + warp * 256;
+    uint64_t* scratch = bars + 4 + warp * 4;
+    const uint64_t ad = make_smem_desc(a0, 16, 1024), bd = make_smem_desc(b0, 16, 1024);
+    const uint32_t leader = elect_one_sync();
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r += 16) {
+      if (leader) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) umma_bf16(acc, ad + 2 * (i & 3), bd + 2 * (i & 3), idesc, (r | i) != 0);
+        if (commit_every) for (int c = 0; c < ncommit; ++c) umma_commit(&scratch[c]);
+      }
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (leader) umma_commit(&bars[warp]);
+    __syncwarp();
+    mbar_wait(&bars[warp], 0);
+    const long long t2 = clock64();
+    if (leader) { out[2 * warp] = t1 - t0; out[2 * warp + 1] = t2 - t0; }
   }
   __syncthreads();
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }

@@ -13,17 +13,18 @@ def main():
     H = _lib.hooks()
     out = torch.zeros(4, dtype=torch.int64, device='cuda')
     reps = 256
-    print('N every ncommit issuers | issue clk/MMA  total clk/MMA')
-    for N in (32, 64):
-        for every, nc in ((0, 0), (64, 1), (16, 1), (16, 2), (8, 1), (4, 1), (1, 1)):
-            for issuers in (1, 2):
-                out.zero_()
-                for _ in range(2):
-                    _lib.check_hook(H.srl_test_mma_rate(N, 21 | (every << 8) | (nc << 16), reps, issuers, out.data_ptr(), None))
-                torch.cuda.synchronize()
-                o = out.cpu().tolist()
-                s = '  '.join(f'w{w}: {o[2 * w] / reps:6.1f} {o[2 * w + 1] / reps:6.1f}' for w in range(issuers))
-                print(f'{N:3d} {every:3d} {nc} {issuers} | {s}')
+    print('mode N every ncommit issuers | issue clk/MMA  total clk/MMA')
+    for mode in (0, 1, 2):
+        for N in (32, 64, 128):
+            for every, nc in ((0, 0), (16, 1), (16, 2)):
+                for issuers in (1, 2):
+                    out.zero_()
+                    for _ in range(2):
+                        _lib.check_hook(H.srl_test_mma_rate(N, 21 | (every << 8) | (nc << 16) | (mode << 20), reps, issuers, out.data_ptr(), None))
+                    torch.cuda.synchronize()
+                    o = out.cpu().tolist()
+                    s = '  '.join(f'w{w}: {o[2 * w] / reps:6.1f} {o[2 * w + 1] / reps:6.1f}' for w in range(issuers))
+                    print(f'{mode} {N:3d} {every:3d} {nc} {issuers} | {s}')
 
 
 if __name__ == '__main__':
