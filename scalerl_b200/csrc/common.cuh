@@ -86,6 +86,7 @@ SRL_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 // one lane of the (converged) warp: the form the compiler recognises as 'exactly one thread' for the tcgen05 / TMA issue paths
 SRL_DEVINL uint32_t elect_one_sync() {
   uint32_t pred;
+  __syncwarp();      // elect.sync needs the full warp converged
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred;
 }

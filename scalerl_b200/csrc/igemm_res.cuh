@@ -88,26 +88,31 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (tid != 128) pdl_wait();
+  if (warp != 4) pdl_wait();
 
   if (warp == 4) {
-    if ((tid & 31) == 0) {
-      // the packed weights were complete before the first kernel of the chain started: their load overlaps the previous
-      // kernel's tail; the activations are only touched after pdl_wait()
+    const uint32_t leader = elect_one_sync();      // converged warp, one elected issuing lane: no vote loop around every TMA instruction
+    // the packed weights were complete before the first kernel of the chain started: their load overlaps the previous
+    // kernel's tail; the activations are only touched after pdl_wait()
+    if (leader) {
       mbar_arrive_expect_tx(w_full, C::W_BYTES);
       for (int j = 0; j < P::NT; ++j) tma_load_2d(sW + j * P::BN * 128, &p.w, w_full, j * 64, 0);
       if constexpr (SPLIT)
         for (int j = 0; j < P::NT; ++j) tma_load_2d(sW + C::W_HI_BYTES + j * P::BN * 128, &p.w_lo, w_full, j * 64, 0);
-      pdl_wait();
-      pdl_launch();
-      int it = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int s = it % STAGES;
-        mbar_wait(&in_empty[s], ((it / STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    pdl_wait();
+    if (leader) pdl_launch();
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = it % STAGES;
+      mbar_wait(&in_empty[s], ((it / STAGES) & 1) ^ 1);
+      if (leader) {
         mbar_arrive_expect_tx(&in_full[s], P::NWIN * P::WROWS * 128 * (1 + C::ALO));
         P::load_windows(p, t, sIn + s * C::IN_BYTES, C::WIN_BYTES, &in_full[s], false);
         if constexpr (C::ALO) P::load_windows(p, t, sIn + s * C::IN_BYTES + C::IN_HI_BYTES, C::WIN_BYTES, &in_full[s], true);
       }
+      __syncwarp();
     }
   } else if (warp == 5) {
     // The warp stays converged and ONE elected lane issues: with elect.sync the compiler keeps the descriptors in uniform registers and
@@ -259,10 +264,11 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
   if (tid == 128) pdl_launch();
 
   if (warp == 4) {
-    if ((tid & 31) == 0) {
-      for (int i = 0; i < nch; ++i) {
-        const int s = i % STAGES;
-        mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+    const uint32_t leader = elect_one_sync();
+    for (int i = 0; i < nch; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+      if (leader) {
         mbar_arrive_expect_tx(&full[s], P::NWIN * P::WROWS * 128 * (1 + C::ALO) + C::DY_BYTES * (1 + SPLIT));
         uint8_t* st = sSt + s * C::STAGE_BYTES;
         P::load_windows(p, c_begin + i, st, C::WIN_BYTES, &full[s], false);
@@ -270,6 +276,7 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
         tma_load_2d(st + C::X_BYTES, &p.dy, &full[s], 0, (c_begin + i) * 128);
         if constexpr (SPLIT) tma_load_2d(st + C::X_BYTES + C::DY_BYTES, &p.dy_lo, &full[s], 0, (c_begin + i) * 128);
       }
+      __syncwarp();
     }
   } else if (warp == 5) {
     const uint32_t leader = elect_one_sync();        // converged warp, one elected issuing lane (see res_fwd_kernel)

@@ -119,14 +119,16 @@ __global__ void __launch_bounds__(IGT_THREADS) igemm_tma_kernel(const __grid_con
   if (tid == 128) pdl_launch();
 
   if (warp == 4) {
-    if ((tid & 31) == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % P::STAGES;
-        mbar_wait(&empty[s], ((kb / P::STAGES) & 1) ^ 1);
+    const uint32_t leader = elect_one_sync();
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % P::STAGES;
+      mbar_wait(&empty[s], ((kb / P::STAGES) & 1) ^ 1);
+      if (leader) {
         uint8_t* sA = smem + s * C::STAGE_BYTES;
         if constexpr (SPLIT) P::issue_split(p, tm, ty, kb, sA, C::A_BYTES, C::HALF_BYTES, &full[s]);
         else P::issue(p, tm, ty, kb, sA, sA + C::A_BYTES, &full[s]);
       }
+      __syncwarp();
     }
   } else if (warp == 5) {
     const uint32_t leader = elect_one_sync();        // converged warp, one elected issuing lane (see igemm_res.cuh res_fwd_kernel)
