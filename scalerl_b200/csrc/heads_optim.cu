@@ -399,8 +399,23 @@ __global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, 
   cg::grid_group grid = cg::this_grid();
   const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int t = dstep ? *dstep + 1 : step;          // 1-based step count: Adam bias correction; counted for RMSprop too (checkpoints)
+  // The thread's first HOLD float4 of g (and, for RMSprop, of p and the state) stay in registers across the grid barrier: phase 2 then
+  // starts from registers instead of paying a second round of L2 / HBM latency (the grid covers n with <= HOLD items per thread).
+  constexpr int HOLD = 2;
+  float4 gh[HOLD], ph[HOLD], vh[HOLD];
   float s = 0.f;
-  for (int64_t i = i0; i < n4; i += stride) {
+#pragma unroll
+  for (int h = 0; h < HOLD; ++h) {
+    const int64_t i = i0 + h * stride;
+    if (i < n4) {
+      gh[h] = reinterpret_cast<const float4*>(g)[i];
+      if (OPT == 0) { ph[h] = reinterpret_cast<const float4*>(p)[i]; vh[h] = reinterpret_cast<const float4*>(s0)[i]; }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < HOLD; ++h)
+    if (i0 + h * stride < n4) s += gh[h].x * gh[h].x + gh[h].y * gh[h].y + gh[h].z * gh[h].z + gh[h].w * gh[h].w;
+  for (int64_t i = i0 + HOLD * stride; i < n4; i += stride) {
     const float4 v = reinterpret_cast<const float4*>(g)[i];
     s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
@@ -434,7 +449,24 @@ __global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, 
   __syncthreads();
   const float c = c_sh;
   if (OPT == 0) {
-    for (int64_t i = i0; i < n4; i += stride) {
+#pragma unroll
+    for (int h = 0; h < HOLD; ++h) {
+      const int64_t i = i0 + h * stride;
+      if (i < n4) {
+        float4 pp = ph[h], vv = vh[h];
+        const float4 gg = gh[h];
+        float* P = &pp.x; float* V = &vv.x; const float* G = &gg.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float gk = G[k] * c;
+          V[k] = a * V[k] + (1.f - a) * gk * gk;
+          P[k] = P[k] - lr * (gk / (sqrtf(V[k]) + eps));
+        }
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(s0)[i] = vv;
+      }
+    }
+    for (int64_t i = i0 + HOLD * stride; i < n4; i += stride) {
       float4 pp = reinterpret_cast<float4*>(p)[i], vv = reinterpret_cast<float4*>(s0)[i];
       const float4 gg = reinterpret_cast<const float4*>(g)[i];
       float* P = &pp.x; float* V = &vv.x; const float* G = &gg.x;
