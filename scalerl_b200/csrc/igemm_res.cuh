@@ -19,6 +19,9 @@
 //                       range of positions, streams (window, dY) chunks of 128 positions through a ring and keeps ALL
 //                       taps' accumulators in TMEM (tap pairs form M = 128; an all-ones block yields the bias gradient).
 #pragma once
+#ifdef SRL_WGRAD_STAMP
+#include <cstdio>
+#endif
 #include "igemm_tma.cuh"
 
 namespace srl {
@@ -219,6 +222,14 @@ struct ResWgradCfg {
   static_assert(P::NACC * 64 <= 512, "accumulators must fit TMEM");
 };
 
+// Diagnostics build (SRL_DEFINES=SRL_WGRAD_STAMP, tests/diag/diag_wgrad.py): CTA 0 of a two-accumulator wgrad (conv1) prints %globaltimer
+// stamps of its phases.  Never defined in the product build.
+#ifdef SRL_WGRAD_STAMP
+#define WG_STAMP(var) do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(var)); } while (0)
+#else
+#define WG_STAMP(var) do { } while (0)
+#endif
+
 template <class P, int SPLIT>
 __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_constant__ typename P::Params p) {
   using C = ResWgradCfg<P, SPLIT>;
@@ -260,8 +271,10 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  unsigned long long wg_t0 = 0; WG_STAMP(wg_t0);
   pdl_wait();
   if (tid == 128) pdl_launch();
+  unsigned long long wg_t1 = 0; WG_STAMP(wg_t1);
 
   if (warp == 4) {
     const uint32_t leader = elect_one_sync();
@@ -282,9 +295,15 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
     const uint32_t leader = elect_one_sync();        // converged warp, one elected issuing lane (see res_fwd_kernel)
     constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
     const uint32_t ones = smem_u32(sOnes);
+#ifdef SRL_WGRAD_STAMP
+    unsigned long long wg_full[20] = {};
+#endif
     for (int i = 0; i < nch; ++i) {
       const int s = i % STAGES;
       mbar_wait(&full[s], (i / STAGES) & 1);
+#ifdef SRL_WGRAD_STAMP
+      if (i < 20) WG_STAMP(wg_full[i]);
+#endif
       tc_fence_after();
       const uint32_t st = smem_u32(sSt + s * C::STAGE_BYTES);
       const uint64_t dyd = make_smem_desc(st + C::X_BYTES, 8192, 1024);
@@ -313,6 +332,15 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
     }
     if (leader) umma_commit(done);
     __syncwarp();
+#ifdef SRL_WGRAD_STAMP
+    if (P::NACC == 2 && blockIdx.x == 0 && leader) {
+      mbar_wait(done, 0);
+      unsigned long long td; WG_STAMP(td);
+      printf("wgrad cta0: prologue->pdl %llu ns; chunks full at (ns after pdl):", wg_t1 - wg_t0);
+      for (int i = 0; i < nch && i < 20; ++i) printf(" %llu", wg_full[i] - wg_t1);
+      printf("; all MMAs done %llu\n", td - wg_t1);
+    }
+#endif
   } else {
     if constexpr (BIAS_SMEM) {
       // bias gradient = column sums of dy, taken from the staged dy tiles while the MMAs run (no all-ones accumulator).
@@ -360,7 +388,9 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
       if (tid < P::BIAS_CH && nch > 0) atomicAdd(p.db + tid, red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]);
     }
     if (nch > 0) {
+      unsigned long long wg_e0 = 0, wg_e1 = 0, wg_e2 = 0; WG_STAMP(wg_e0);
       mbar_wait(done, 0);
+      WG_STAMP(wg_e1);
       tc_fence_after();
       const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
@@ -377,6 +407,10 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
         }
       }
       tc_fence_before();
+#ifdef SRL_WGRAD_STAMP
+      __threadfence(); WG_STAMP(wg_e2);
+      if (P::NACC == 2 && blockIdx.x == 0 && tid == 0) printf("wgrad cta0 epilogue: bias loop done %llu, accumulators ready %llu, reds issued+fenced %llu (ns after pdl)\n", wg_e0 - wg_t1, wg_e1 - wg_t1, wg_e2 - wg_t1);
+#endif
     }
   }
   __syncthreads();

@@ -190,7 +190,7 @@ struct RConv2Wgrad {   // acc a = kh (blocks kww = 0,1: rows = (kw = 2kww + wp, 
 };
 
 struct RConv1Wgrad {   // acc a = kh2 (blocks kw2 = 0,1: rows = (kw2, c, dy, dx)); db1 = column sums of the staged dy tiles
-  static constexpr int NACC = 2, NWIN = 1, WROWS = 128 + 22, STAGES = 3, SPLIT_STAGES = 3;
+  static constexpr int NACC = 2, NWIN = 1, WROWS = 128 + 22, STAGES = 5, SPLIT_STAGES = 3;
   static constexpr bool A_LO = false;          // the frames are exact in bf16
   static constexpr bool SMEM_BIAS = true;
   static constexpr int BIAS_CH = 32;           // da1g channels 32..63 are zero

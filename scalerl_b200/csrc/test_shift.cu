@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(96) mma_rate_kernel(int N, int shift, int reps
   shift &= 255;
   const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
   const uint32_t a0 = smem_u32(sA) + shift * 128, b0 = smem_u32(sB);
-  if (mode == 0 || mode == 1) {
+  if (mode == 0 || mode == 1) {   // (modes 2, 3: the converged elect.sync form below)
   if (warp < issuers && (tid & 31) == 0) {
     const uint32_t acc = tmem_base + warp * 256;
     uint64_t* scratch = bars + 4 + warp * 4;      // barriers nobody waits on (phases just advance)
@@ -192,15 +192,19 @@ __global__ void __launch_bounds__(96) mma_rate_kernel(int N, int shift, int reps
     out[2 * warp + 1] = t2 - t0;
   }
   } else if (warp < issuers) {
+    // mode 3: both operands MN-major (the wgrad kernels' form: 16 contraction rows of 128 B per K step, M = two 64-wide blocks LBO apart)
+    const bool mn = mode == 3;
     const uint32_t acc = tmem_base + warp * 256;
     uint64_t* scratch = bars + 4 + warp * 4;
-    const uint64_t ad = make_smem_desc(a0, 16, 1024), bd = make_smem_desc(b0, 16, 1024);
+    const uint64_t ad = mn ? make_smem_desc(a0, 128, 1024) : make_smem_desc(a0, 16, 1024), bd = mn ? make_smem_desc(b0, 8192, 1024) : make_smem_desc(b0, 16, 1024);
+    const uint32_t idesc_v = mn ? make_idesc_bf16(128, N, 1, 1) : idesc;
+    const uint32_t kstep = mn ? 128 : 2;
     const uint32_t leader = elect_one_sync();
     const long long t0 = clock64();
     for (int r = 0; r < reps; r += 16) {
       if (leader) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) umma_bf16(acc, ad + 2 * (i & 3), bd + 2 * (i & 3), idesc, (r | i) != 0);
+        for (int i = 0; i < 16; ++i) umma_bf16(acc, ad + kstep * (i & 3), bd + kstep * (i & 3), idesc_v, (r | i) != 0);
         if (commit_every) for (int c = 0; c < ncommit; ++c) umma_commit(&scratch[c]);
       }
       __syncwarp();

@@ -14,8 +14,8 @@ def main():
     out = torch.zeros(4, dtype=torch.int64, device='cuda')
     reps = 256
     print('mode N every ncommit issuers | issue clk/MMA  total clk/MMA')
-    for mode in (0, 1, 2):
-        for N in (32, 64, 128):
+    for mode in (0, 1, 2, 3):
+        for N in ((64, 128) if mode == 3 else (32, 64, 128)):
             for every, nc in ((0, 0), (16, 1), (16, 2)):
                 for issuers in (1, 2):
                     out.zero_()
