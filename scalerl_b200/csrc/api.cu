@@ -240,7 +240,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   for (int i = 0; i < PS_COUNT; ++i) L->slot_used[i] = false;
   const int64_t NF = (int64_t)(cfg->T + 1) * cfg->B, NB = (int64_t)cfg->T * cfg->B, A = cfg->A;
   // carve one arena (256-byte aligned pieces)
-  int64_t sizes[20]; int k = 0;
+  int64_t sizes[24]; int k = 0;
   auto al = [](int64_t b) { return (b + 255) & ~int64_t(255); };
   sizes[k++] = al(NF * 441 * 64 * 2);   // xs
   sizes[k++] = al((int64_t)FC_SPLITS * NF * 512 * 4);   // hpart
@@ -261,6 +261,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   sizes[k++] = al(16);                  // coef
   sizes[k++] = al(16);                  // dstep
   sizes[k++] = al(81920 * 4);           // conv wgrad workspace (res_problems.cuh WS_TOTAL = 81920 floats)
+  sizes[k++] = al(NF * 3136 * 2);       // a3t
   int64_t total = 0;
   for (int i = 0; i < k; ++i) total += sizes[i];
   cudaError_t e = cudaMalloc(&L->arena, total);
@@ -289,6 +290,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   L->coef = (float*)q; q += sizes[i++];
   L->dstep = (int*)q; q += sizes[i++];
   L->buf.wgrad_ws = (float*)q; q += sizes[i++];
+  L->buf.a3t = (__nv_bfloat16*)q; q += sizes[i++];
   if (cudaStreamCreateWithFlags(&L->ss.side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&L->ss.side2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&L->ss.side3, cudaStreamNonBlocking) != cudaSuccess) L->ss.side = nullptr;
@@ -706,7 +708,7 @@ extern "C" int srl_learner_debug_buffer(srl_learner_t* L, const char* name, void
   REQ(L && name && ptr && count, "debug_buffer: NULL argument");
   const int64_t NF = (int64_t)(L->cfg.T + 1) * L->cfg.B, NB = (int64_t)L->cfg.T * L->cfg.B, A = L->cfg.A;
   struct { const char* n; void* p; int64_t c; } tab[] = {
-      {"xs", L->buf.xs, NF * 441 * 64}, {"a1", L->buf.a1, NF * 400 * 32}, {"a2", L->buf.a2, NF * 81 * 64}, {"a3", L->buf.a3, NF * 49 * 64}, {"h", L->buf.h, NF * 512},
+      {"xs", L->buf.xs, NF * 441 * 64}, {"a1", L->buf.a1, NF * 400 * 32}, {"a2", L->buf.a2, NF * 81 * 64}, {"a3", L->buf.a3, NF * 49 * 64}, {"a3t", L->buf.a3t, NF * 49 * 64}, {"h", L->buf.h, NF * 512},
       {"logits", L->logits, NF * A}, {"baseline", L->baseline, NF}, {"dlogits", L->dlogits, NB * A}, {"dbaseline", L->dbaseline, NB},
       {"dh", L->buf.dh, NB * 512}, {"da3", L->buf.da3, NB * 81 * 64}, {"da2", L->buf.da2, NB * 100 * 64},
       {"da1", L->buf.da1, NB * 441 * 64}, {"wpack", L->buf.wpack, WPack::TOTAL},

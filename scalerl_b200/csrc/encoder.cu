@@ -124,6 +124,31 @@ __global__ void __launch_bounds__(352) obs_s2d_kernel(const uint8_t* __restrict_
   }
 }
 
+// a3 [n][hw][c] (NHWC rows, what conv3 writes and fc forward / dgrad consume) -> a3t [n][c*49 + hw], fc.weight's own column order:
+// with a3t as its B operand the fc weight-gradient GEMM produces 64 CONSECUTIVE columns of dW per row (16-byte stores) instead of 64
+// stores 196 B apart.  One frame per block through shared memory, 16-byte reads, 4-byte writes; runs on the wgrad side stream.
+__global__ void __launch_bounds__(256) a3_transpose_kernel(const bf16* __restrict__ a3, bf16* __restrict__ a3t) {
+  __shared__ __align__(16) uint16_t tile[49 * 66];        // row hw: 64 channels + 2 pad (132 B pitch: conflict-free column reads)
+  const int n = blockIdx.x, t = threadIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(a3 + (size_t)n * 3136);
+  for (int q = t; q < 392; q += 256) {                    // 392 x 16 B: row hw = q >> 3, channels 8 (q & 7) ..
+    const uint4 v = __ldg(src + q);
+    uint32_t* d = reinterpret_cast<uint32_t*>(tile + (q >> 3) * 66 + (q & 7) * 8);
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  uint32_t* dst = reinterpret_cast<uint32_t*>(a3t + (size_t)n * 3136);
+  for (int pp = t; pp < 1568; pp += 256) {                // output pair o = 2 pp = c*49 + hw
+    const int o = 2 * pp, c0 = o / 49, h0 = o - c0 * 49, o1 = o + 1, c1 = o1 / 49, h1 = o1 - c1 * 49;
+    dst[pp] = (uint32_t)tile[h0 * 66 + c0] | ((uint32_t)tile[h1 * 66 + c1] << 16);
+  }
+}
+cudaError_t launch_a3_transpose(const bf16* a3, bf16* a3t, int frames, cudaStream_t st) {
+  if (frames <= 0) return cudaSuccess;
+  a3_transpose_kernel<<<frames, 256, 0, st>>>(a3, a3t);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pack_weights(const ParamPtrs& p, bf16* wpack, cudaStream_t st, bf16* wpack_lo) {
   pack_weights_kernel<<<PACK_BLOCKS_FK + PACK_BLOCKS_FD + PACK_BLOCKS_CONV, 256, 0, st>>>(p, wpack, wpack_lo);
   return cudaGetLastError();
@@ -191,6 +216,7 @@ cudaError_t build_tma_maps(const EncoderBuffers& b, int NF, int NB, TmaMaps* M, 
                 "forward and wgrad share the window maps");
   mk(&M->a3m128, b.a3, 2, {3136, nf}, {3136}, {64, 128}, "a3m128");
   mk(&M->a3m64, b.a3, 2, {3136, nf}, {3136}, {64, 64}, "a3m64");
+  if (b.a3t) mk(&M->a3tm64, b.a3t, 2, {3136, nf}, {3136}, {64, 64}, "a3tm64");
   mk(&M->dhm128, b.dh, 2, {512, nb}, {512}, {64, 128}, "dhm128");
   mk(&M->dhm64, b.dh, 2, {512, nb}, {512}, {64, 64}, "dhm64");
   const bf16* w = b.wpack;
@@ -350,8 +376,10 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
   Profiler p1 = pf, p2 = pf, p3 = pf; p1.st = s1; p2.st = s2; p3.st = s3;
   if (do_fc) {
     if (fork) { SRL_TRY(cudaEventRecord(ss.ev[0], st)); SRL_TRY(cudaStreamWaitEvent(s1, ss.ev[0], 0)); }
-    { TFcWgrad::Params q{maps.dhm64, maps.a3m64, L.dhm64, L.a3m64, g.wf, g.bf, frames};
+    { const bool native = !sp && buf.a3t != nullptr;          // bf16 mode: B operand = a3 transposed into fc.weight's column order
+      TFcWgrad::Params q{maps.dhm64, native ? maps.a3tm64 : maps.a3m64, L.dhm64, L.a3m64, g.wf, g.bf, frames, native ? 1 : 0};
       p1.b(PS_FC_WGRAD);
+      if (native) SRL_TRY(launch_a3_transpose(buf.a3, buf.a3t, frames, s1));
       if (sp) SRL_TRY((igemm_tma_launch<TFcWgrad, 1>(q, dim3(1, 4 * 50), s1))); else SRL_TRY((igemm_tma_launch<TFcWgrad, 0>(q, dim3(1, 4 * 50), s1)));
       p1.e(PS_FC_WGRAD); }
     { TFcDgrad::Params q{maps.dhm128, maps.wfd, L.dhm128, L.wfd, buf.a3, buf.da3, buf.da3_lo, frames};

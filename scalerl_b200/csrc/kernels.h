@@ -148,6 +148,7 @@ constexpr int FC_SPLITS = 4;
 struct EncoderBuffers {   // row layouts: see res_problems.cuh
   __nv_bfloat16* xs;                    // space-to-depth bf16 copy of the u8 frames [NF*441][64], 64 = (c,dy,dx)
   __nv_bfloat16 *a1, *a2, *a3;          // a1 [2 planes][NF*100][64], a2 [NF*81][64], a3 [NF*49][64]
+  __nv_bfloat16* a3t = nullptr;         // [NF][64*49]: a3 of the learning frames in fc.weight's own column order (c,h,w) -- fc wgrad's B operand (bf16 mode)
   float* hpart;                         // [FC_SPLITS][NF][512] split-K partials of the fc layer
   float* h;                             // [NF][512] fc output (post-ReLU), fp32
   __nv_bfloat16 *dh, *da3, *da2, *da1;  // dh [NB][512]; da3g [NB*81][64], da2g [NB*100][64], da1g [NB*441][64] (grid layouts, zero-padded)
@@ -164,6 +165,7 @@ struct EncoderBuffers {   // row layouts: see res_problems.cuh
 struct TmaMaps {
   alignas(64) CUtensorMap xs_w, a1p0_w, a1p1_w, a2_w, da3g_w, da3g_b, da2g_w, da2g_b, da1g_b;      // conv layers (res_problems.cuh)
   alignas(64) CUtensorMap a3m128, a3m64, dhm128, dhm64;                                            // fc layer (tma_problems.cuh)
+  alignas(64) CUtensorMap a3tm64;                                                                  // a3 in fc.weight's native column order (c,h,w): fc wgrad's B operand
   alignas(64) CUtensorMap w1k, w2k, w3k, wfk, wfd, w3d, w2d;
   bool valid = false;
 };
