@@ -251,7 +251,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   sizes[k++] = al(NB * 512 * 2);        // dh
   sizes[k++] = al(NB * 81 * 64 * 2);    // da3g (9x9 grid)
   sizes[k++] = al(NB * 100 * 64 * 2);   // da2g (10x10 grid)
-  sizes[k++] = al(NB * 441 * 64 * 2);   // da1g (21x21 grid, 64-channel pitch, upper half zero)
+  sizes[k++] = al(NB * 441 * 32 * 2);   // da1g (21x21 grid, 32 channels)
   sizes[k++] = al(WPack::TOTAL * 2);    // wpack
   sizes[k++] = al(NF * A * 4);          // logits
   sizes[k++] = al(NF * 4);              // baseline
@@ -299,7 +299,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   cudaGetLastError();
   if (cfg->precision == 1) {      // low twins of every bf16 operand tensor (same layouts), zero-initialised like the originals
     const int64_t lo_sizes[8] = {al(NF * 400 * 32 * 2), al(NF * 81 * 64 * 2), al(NF * 49 * 64 * 2), al(NB * 512 * 2), al(NB * 81 * 64 * 2),
-                                 al(NB * 100 * 64 * 2), al(NB * 441 * 64 * 2), al(WPack::TOTAL * 2)};
+                                 al(NB * 100 * 64 * 2), al(NB * 441 * 32 * 2), al(WPack::TOTAL * 2)};
     int64_t lo_total = 0;
     for (int j = 0; j < 8; ++j) lo_total += lo_sizes[j];
     if (cudaMalloc(&L->lo_arena, lo_total) != cudaSuccess || cudaMemset(L->lo_arena, 0, lo_total) != cudaSuccess) {
@@ -711,11 +711,11 @@ extern "C" int srl_learner_debug_buffer(srl_learner_t* L, const char* name, void
       {"xs", L->buf.xs, NF * 441 * 64}, {"a1", L->buf.a1, NF * 400 * 32}, {"a2", L->buf.a2, NF * 81 * 64}, {"a3", L->buf.a3, NF * 49 * 64}, {"a3t", L->buf.a3t, NF * 49 * 64}, {"h", L->buf.h, NF * 512},
       {"logits", L->logits, NF * A}, {"baseline", L->baseline, NF}, {"dlogits", L->dlogits, NB * A}, {"dbaseline", L->dbaseline, NB},
       {"dh", L->buf.dh, NB * 512}, {"da3", L->buf.da3, NB * 81 * 64}, {"da2", L->buf.da2, NB * 100 * 64},
-      {"da1", L->buf.da1, NB * 441 * 64}, {"wpack", L->buf.wpack, WPack::TOTAL},
+      {"da1", L->buf.da1, NB * 441 * 32}, {"wpack", L->buf.wpack, WPack::TOTAL},
       {"fused_dbg", g_fused_dbg, 5 * 8 * 8 * 4},        // u64 stamps, counted in bf16 units by the Python helper (x4)
       {"a1_lo", L->buf.a1_lo, NF * 400 * 32}, {"a2_lo", L->buf.a2_lo, NF * 81 * 64}, {"a3_lo", L->buf.a3_lo, NF * 49 * 64},
       {"dh_lo", L->buf.dh_lo, NB * 512}, {"da3_lo", L->buf.da3_lo, NB * 81 * 64}, {"da2_lo", L->buf.da2_lo, NB * 100 * 64},
-      {"da1_lo", L->buf.da1_lo, NB * 441 * 64}, {"wpack_lo", L->buf.wpack_lo, WPack::TOTAL}};
+      {"da1_lo", L->buf.da1_lo, NB * 441 * 32}, {"wpack_lo", L->buf.wpack_lo, WPack::TOTAL}};
   for (auto& t : tab)
     if (strcmp(t.n, name) == 0) {
       if (!t.p) return fail(SRL_ESTATE, "debug_buffer: '%s' exists only in the fp32-accurate operand mode (precision = 1)", name);

@@ -130,6 +130,10 @@ SRL_DEVINL uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t 
   d |= (uint64_t)2 << 61;   // SWIZZLE_128B
   return d;
 }
+// the same descriptor for a SWIZZLE_64B tile (rows of 64 B, 8-row groups 512 B apart)
+SRL_DEVINL uint64_t make_smem_desc_sw64(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (make_smem_desc(saddr, lbo_bytes, sbo_bytes) & ~((uint64_t)7 << 61)) | ((uint64_t)4 << 61);
+}
 // kind::f16 instruction descriptor: bf16 x bf16 -> f32, dense
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                     // D format f32
@@ -141,6 +145,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 
 // 128B-swizzle: 16-byte chunk c (0..7) of 128-byte row r lands at chunk position c ^ (r & 7)
 SRL_DEVINL uint32_t swz128(uint32_t row, uint32_t chunk) { return row * 128u + ((chunk ^ (row & 7u)) << 4); }
+// 64B-swizzle: 16-byte chunk c (0..3) of 64-byte row r lands at chunk position c ^ ((r >> 1) & 3)   (address bits [4:5] ^= bits [7:8])
+SRL_DEVINL uint32_t swz64(uint32_t row, uint32_t chunk) { return row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4); }
 
 // ------------------------------------------------------------------------------------------
 // small numeric helpers

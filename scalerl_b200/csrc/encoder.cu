@@ -177,7 +177,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 // bf16 tensor, dims innermost-first, strides in ELEMENTS for dims 1..rank-1, SWIZZLE_128B, zero OOB fill
-bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box) {
+bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box,
+              bool swizzle64 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t gd[5], gs[4];
@@ -185,7 +186,8 @@ bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_elems[i] * 2;
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 cudaError_t build_tma_maps(const EncoderBuffers& b, int NF, int NB, TmaMaps* M, const char** why) {
@@ -211,7 +213,8 @@ cudaError_t build_tma_maps(const EncoderBuffers& b, int NF, int NB, TmaMaps* M, 
   rows(&M->da3g_b, b.da3, nb * 81, 128, "da3g_b");
   rows(&M->da2g_w, b.da2, nb * 100, RConv2Dgrad::WROWS, "da2g_w");
   rows(&M->da2g_b, b.da2, nb * 100, 128, "da2g_b");
-  rows(&M->da1g_b, b.da1, nb * 441, 128, "da1g_b");
+  { const uint64_t d[2] = {32, nb * 441}, st_[1] = {32}; const uint32_t bx[2] = {32, 128};      // da1g: 32-channel rows (64 B), SWIZZLE_64B
+    if (ok && !make_map(&M->da1g_b, b.da1, 2, d, st_, bx, true)) { ok = false; if (why) *why = "da1g_b"; } }
   static_assert(RConv1Wgrad::WROWS == RConv1Fwd::WROWS && RConv2Wgrad::WROWS == RConv2Fwd::WROWS && RConv3Wgrad::WROWS == RConv3Fwd::WROWS,
                 "forward and wgrad share the window maps");
   mk(&M->a3m128, b.a3, 2, {3136, nf}, {3136}, {64, 128}, "a3m128");
@@ -252,7 +255,8 @@ cudaError_t build_tma_maps_lo(const EncoderBuffers& b, int NF, int NB, TmaMapsLo
   rows(&M->da3g_b, b.da3_lo, nb * 81, 128, "da3g_b_lo");
   rows(&M->da2g_w, b.da2_lo, nb * 100, RConv2Dgrad::WROWS, "da2g_w_lo");
   rows(&M->da2g_b, b.da2_lo, nb * 100, 128, "da2g_b_lo");
-  rows(&M->da1g_b, b.da1_lo, nb * 441, 128, "da1g_b_lo");
+  { const uint64_t d[2] = {32, nb * 441}, st_[1] = {32}; const uint32_t bx[2] = {32, 128};
+    if (ok && !make_map(&M->da1g_b, b.da1_lo, 2, d, st_, bx, true)) { ok = false; if (why) *why = "da1g_b_lo"; } }
   mk(&M->a3m128, b.a3_lo, {3136, nf}, {3136}, {64, 128}, "a3m128_lo");
   mk(&M->a3m64, b.a3_lo, {3136, nf}, {3136}, {64, 64}, "a3m64_lo");
   mk(&M->dhm128, b.dh_lo, {512, nb}, {512}, {64, 128}, "dhm128_lo");

@@ -211,7 +211,7 @@ struct ResWgradCfg {
   static constexpr int STAGES = SPLIT ? P::SPLIT_STAGES : P::STAGES;
   static constexpr bool BIAS_SMEM = P::SMEM_BIAS || SPLIT;        // split mode: bias gradient always from the staged dY tiles
   static constexpr int WIN_BYTES = ((P::WROWS * 128 + 1023) / 1024) * 1024;
-  static constexpr int DY_BYTES = 128 * 128;
+  static constexpr int DY_BYTES = 128 * P::DY_CH * 2;             // 128 positions x DY_CH channels (64: SWIZZLE_128B rows, 32: SWIZZLE_64B rows)
   static constexpr int X_HI_BYTES = P::NWIN * WIN_BYTES;
   static constexpr int X_BYTES = X_HI_BYTES * (1 + ALO);
   static constexpr int STAGE_BYTES = X_BYTES + DY_BYTES * (1 + SPLIT);     // [windows hi][windows lo][dY hi][dY lo]
@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
     }
   } else if (warp == 5) {
     const uint32_t leader = elect_one_sync();        // converged warp, one elected issuing lane (see res_fwd_kernel)
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+    constexpr uint32_t idesc = make_idesc_bf16(128, P::DY_CH, 1, 1);
+    constexpr uint32_t DYK = P::DY_CH * 2;           // descriptor address units per K = 16 step of the dY tile (16 rows x row bytes / 16)
     const uint32_t ones = smem_u32(sOnes);
 #ifdef SRL_WGRAD_STAMP
     unsigned long long wg_full[20] = {};
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
 #endif
       tc_fence_after();
       const uint32_t st = smem_u32(sSt + s * C::STAGE_BYTES);
-      const uint64_t dyd = make_smem_desc(st + C::X_BYTES, 8192, 1024);
+      const uint64_t dyd = P::DY_CH == 64 ? make_smem_desc(st + C::X_BYTES, 8192, 1024) : make_smem_desc_sw64(st + C::X_BYTES, 4096, 512);
       if (leader) {
 #pragma unroll
         for (int a = 0; a < P::NACC; ++a) {
@@ -319,11 +320,11 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
           const uint64_t xd = make_smem_desc(blk0, lbo, 1024);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {          // 128 positions = 8 x (K = 16): +2048 B per step
-            umma_bf16(tmem_base + a * 64, xd + 128 * k, dyd + 128 * k, idesc, (i | k) != 0);
+            umma_bf16(tmem_base + a * 64, xd + 128 * k, dyd + DYK * k, idesc, (i | k) != 0);
             if constexpr (SPLIT)         // hi(x) * lo(dy)
-              umma_bf16(tmem_base + a * 64, xd + 128 * k, dyd + (uint64_t)(C::DY_BYTES / 16 + 128 * k), idesc, 1);
+              umma_bf16(tmem_base + a * 64, xd + 128 * k, dyd + (uint64_t)(C::DY_BYTES / 16 + DYK * k), idesc, 1);
             if constexpr (C::ALO)        // lo(x) * hi(dy)
-              umma_bf16(tmem_base + a * 64, xd + (uint64_t)(C::X_HI_BYTES / 16 + 128 * k), dyd + 128 * k, idesc, 1);
+              umma_bf16(tmem_base + a * 64, xd + (uint64_t)(C::X_HI_BYTES / 16 + 128 * k), dyd + DYK * k, idesc, 1);
           }
         }
         umma_commit(&empty[s]);
@@ -345,7 +346,9 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
     if constexpr (BIAS_SMEM) {
       // bias gradient = column sums of dy, taken from the staged dy tiles while the MMAs run (no all-ones accumulator).
       // dy tile: 128 position rows of 128 B (64 channels), SWIZZLE_128B.  thread -> 16-byte channel group g, rows q + 16k.
-      const int g = tid & 7, q = tid >> 3;
+      // dy tile rows: DY_CH channels = NG 16-byte groups; thread -> group g, rows q + RP k (RP rows per pass, NG passes)
+      constexpr int NG = P::DY_CH / 8, RP = 128 / NG;
+      const int g = tid & (NG - 1), q = tid / NG;
       float bs[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) bs[j] = 0.f;
@@ -363,8 +366,8 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
 #pragma unroll
         for (int part = 0; part <= SPLIT; ++part) {        // split mode: the low tile's column sums are added too
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint4 v = lds128(dyt + part * C::DY_BYTES + swz128(q + 16 * k, g));
+          for (int k = 0; k < NG; ++k) {
+            const uint4 v = lds128(dyt + part * C::DY_BYTES + (P::DY_CH == 64 ? swz128(q + RP * k, g) : swz64(q + RP * k, g)));
             bs[0] += bf16_lo(v.x); bs[1] += bf16_hi(v.x); bs[2] += bf16_lo(v.y); bs[3] += bf16_hi(v.y);
             bs[4] += bf16_lo(v.z); bs[5] += bf16_hi(v.z); bs[6] += bf16_lo(v.w); bs[7] += bf16_hi(v.w);
             dep += __uint_as_float(v.x ^ v.y ^ v.z ^ v.w);
@@ -377,10 +380,11 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
       float* red = reinterpret_cast<float*>(sOnes);          // the all-ones block is not used by these problems
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        if (NG == 4) bs[j] += __shfl_xor_sync(0xffffffffu, bs[j], 4);
         bs[j] += __shfl_xor_sync(0xffffffffu, bs[j], 8);
         bs[j] += __shfl_xor_sync(0xffffffffu, bs[j], 16);
       }
-      if ((tid & 31) < 8) {
+      if ((tid & 31) < NG) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) red[warp * 64 + g * 8 + j] = bs[j];
       }

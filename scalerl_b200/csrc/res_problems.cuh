@@ -8,7 +8,7 @@
 //   a3   [NF*49]    dense (the fc input)
 //   da3g [NB*81]    d(conv3 out) on conv3's 9x9 grid, zeros outside the 7x7 valid outputs (those zeros ARE the padding of dgrad)
 //   da2g [NB*100]   d(conv2 out) on conv2's 10x10 grid, zeros outside 9x9
-//   da1g [NB*441]   d(conv1 out) on conv1's 21x21 grid, zeros outside 20x20, channels 32..63 zero
+//   da1g [NB*441]   d(conv1 out) on conv1's 21x21 grid, zeros outside 20x20; 32 channels = 64 B per row (SWIZZLE_64B tiles)
 #pragma once
 #include "igemm_res.cuh"
 #include "encoder_problems.cuh"
@@ -134,7 +134,7 @@ struct RConv2Dgrad {   // the 4 stride-parity classes share A (da2g at (i'-kh', 
     if (n >= p.NB) return;
     const int cls = c0 >> 5, c = c0 & 31, ph = cls >> 1, pw = cls & 1;
     relu_mask16_pre(m, v);
-    store_act16<SPLIT>(p.dx, p.dx_lo, ((size_t)n * 441 + (2 * i + ph) * 21 + 2 * j + pw) * 64 + c, v);   // da1g: conv1's 21x21 grid
+    store_act16<SPLIT>(p.dx, p.dx_lo, ((size_t)n * 441 + (2 * i + ph) * 21 + 2 * j + pw) * 32 + c, v);   // da1g: conv1's 21x21 grid, 32-channel rows
   }
 };
 
@@ -147,7 +147,7 @@ struct RConv3Wgrad {   // acc a = taps (2a, 2a+1); acc 4 = (tap 8, ones -> db3).
   static constexpr int NACC = 5, NWIN = 1, WROWS = 128 + 20, STAGES = 3, SPLIT_STAGES = 2;
   static constexpr bool A_LO = true;
   static constexpr bool SMEM_BIAS = false;     // the ninth tap leaves half an accumulator free: the all-ones block rides along
-  static constexpr int BIAS_CH = 64;
+  static constexpr int BIAS_CH = 64, DY_CH = 64;
   struct Params { SRL_TMAP in0; SRL_TMAP dy; SRL_TMAP in0_lo; SRL_TMAP dy_lo; float* ws; float* db; int P; int chunks_per_cta; };
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.dy); }
   SRL_DEVINL static constexpr int sh(int tap) { return (tap / 3) * 9 + tap % 3; }
@@ -172,7 +172,7 @@ struct RConv2Wgrad {   // acc a = kh (blocks kww = 0,1: rows = (kw = 2kww + wp, 
   static constexpr int NACC = 4, NWIN = 2, WROWS = 128 + 11, STAGES = 3, SPLIT_STAGES = 1;
   static constexpr bool A_LO = true;
   static constexpr bool SMEM_BIAS = true;
-  static constexpr int BIAS_CH = 64;
+  static constexpr int BIAS_CH = 64, DY_CH = 64;
   struct Params { SRL_TMAP in0; SRL_TMAP in1; SRL_TMAP dy; SRL_TMAP in0_lo; SRL_TMAP in1_lo; SRL_TMAP dy_lo; float* ws; float* db; int P; int chunks_per_cta; };   // ws: [4 kh][128 (kw,c)][64 co]
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.in1); tma_prefetch_desc(&p.dy); }
   SRL_DEVINL static constexpr int acc_win(int a) { return a & 1; }
@@ -193,7 +193,8 @@ struct RConv1Wgrad {   // acc a = kh2 (blocks kw2 = 0,1: rows = (kw2, c, dy, dx)
   static constexpr int NACC = 2, NWIN = 1, WROWS = 128 + 22, STAGES = 5, SPLIT_STAGES = 3;
   static constexpr bool A_LO = false;          // the frames are exact in bf16
   static constexpr bool SMEM_BIAS = true;
-  static constexpr int BIAS_CH = 32;           // da1g channels 32..63 are zero
+  static constexpr int BIAS_CH = 32;
+  static constexpr int DY_CH = 32;             // da1g rows are 32 channels (64 B): SWIZZLE_64B dY tiles, N = 32 MMAs
   struct Params { SRL_TMAP in0; SRL_TMAP dy; SRL_TMAP dy_lo; float* ws; float* db; int P; int chunks_per_cta; };   // ws: [2 kh2][128 (kw2,c,dy,dx)][32 co]
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.dy); }
   SRL_DEVINL static constexpr int acc_win(int) { return 0; }
@@ -203,7 +204,7 @@ struct RConv1Wgrad {   // acc a = kh2 (blocks kw2 = 0,1: rows = (kw2, c, dy, dx)
   SRL_DEVINL static void load_windows(const Params& p, int chunk, uint8_t* dst, int, uint64_t* bar, bool) { tma_load_2d(dst, &p.in0, bar, 0, chunk * 128); }
   template <int SPLIT>
   SRL_DEVINL static void epilogue16(const Params& p, int a, int row, int c0, float (&v)[16]) {
-    if (c0 >= 32) return;                    // da1g channels 32..63 are zero
+    if (c0 >= 32) return;                    // N = 32: accumulator columns 32..63 are not written by the MMAs
     red_add_16(p.ws + ((size_t)(a * 128 + row)) * 32 + c0, v);
   }
 };

@@ -19,8 +19,8 @@ with ctx:
             _lib.check(_lib.lib().srl_test_poison_smem(None)); torch.cuda.synchronize()
         L.forward_backward(batch); torch.cuda.synchronize()
         gs.append({k: v.clone() for k, v in L.grads.items()})
-        da1 = L.debug_buffer('da1').float().view(-1, 64)
-        d1.append(da1.sum(0)[:32].clone())
+        da1 = L.debug_buffer('da1').float().view(-1, 32)
+        d1.append(da1.sum(0).clone())
         torch.cuda.synchronize()
 tag = 'PDL=%s MASK=%s SIDE=%s STREAM=%s' % tuple(os.environ.get(k, '-') for k in ('SRL_PDL', 'SRL_PDL_MASK', 'SRL_SIDE_MODE', 'DIAG_STREAM'))
 nbad = 0

@@ -57,7 +57,7 @@ def main():
     g2 = (a2.grad * (a2 > 0))[:NB]
     rep['da2'] = rel_l2(dbg('da2').view(NB, 10, 10, 64)[:, :9, :9].permute(0, 3, 1, 2), g2)
     g1 = (a1.grad * (a1 > 0))[:NB]
-    rep['da1'] = rel_l2(dbg('da1').view(NB, 21, 21, 64)[:, :20, :20, :32].permute(0, 3, 1, 2), g1)
+    rep['da1'] = rel_l2(dbg('da1').view(NB, 21, 21, 32)[:, :20, :20, :].permute(0, 3, 1, 2), g1)
     for k in O.PARAM_ORDER:
         rep['grad ' + k] = rel_l2(L.grads[k].cpu(), ps[k].grad)
     for k, v in rep.items():
