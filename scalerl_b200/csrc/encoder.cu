@@ -178,7 +178,7 @@ static EncodeTiledFn encode_fn() {
 
 // bf16 tensor, dims innermost-first, strides in ELEMENTS for dims 1..rank-1, SWIZZLE_128B, zero OOB fill
 bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box,
-              bool swizzle64 = false) {
+              bool swizzle64) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t gd[5], gs[4];
