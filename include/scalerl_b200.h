@@ -116,6 +116,10 @@ int64_t srl_param_layout_ex(int A, int use_lstm, int64_t* offsets20, int64_t* co
 int srl_learner_create(const srl_config_t* cfg, float* params, float* grads, float* opt_state0, float* opt_state1,
                        srl_learner_t** out);
 int srl_learner_destroy(srl_learner_t* L);
+/* Diagnostics builds only (SRL_DEFINES=SRL_KSTAMP; tests/diag/diag_timeline.py): `buffer` = 1 + 3*2000 uint64 of device memory, zeroed by the
+ * caller; every kernel then appends {kernel id, %globaltimer at entry, %globaltimer when its stream predecessor had completed} (word 0 = count).
+ * NULL switches the stamps off.  The product build returns SRL_ESTATE. */
+int srl_debug_kernel_timeline(void* buffer);
 /* bytes of device workspace held by the context */
 int64_t srl_learner_workspace_bytes(const srl_learner_t* L);
 /* update a hyper-parameter that does not change buffer sizes (lr, costs, clip...) */

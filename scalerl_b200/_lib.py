@@ -43,6 +43,7 @@ _SIGS = {
     'srl_learner_destroy': [_P],
     'srl_learner_set_config': [_P, C.POINTER(SrlConfig)],
     'srl_learner_pack_weights': [_P, _P],
+    'srl_debug_kernel_timeline': [_P],
     'srl_learner_forward': [_P, _P, _P, _P, _I, _P, _P, _P],
     'srl_learner_forward_backward': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     'srl_learner_forward_backward_begin': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P],

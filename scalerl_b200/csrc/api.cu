@@ -367,6 +367,17 @@ extern "C" int srl_learner_destroy(srl_learner_t* L) {
   delete L;
   return 0;
 }
+extern "C" int srl_debug_kernel_timeline(void* buffer) {
+#ifdef SRL_KSTAMP
+  kstamp_set_encoder((unsigned long long*)buffer); kstamp_set_vtrace((unsigned long long*)buffer); kstamp_set_heads((unsigned long long*)buffer);
+  cudaError_t e = cudaDeviceSynchronize();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "debug_kernel_timeline");
+#else
+  (void)buffer;
+  return fail(SRL_ESTATE, "debug_kernel_timeline: this library was not built with SRL_DEFINES=SRL_KSTAMP");
+#endif
+}
+
 extern "C" int64_t srl_learner_workspace_bytes(const srl_learner_t* L) { return L ? L->arena_bytes : 0; }
 
 extern "C" int srl_learner_set_config(srl_learner_t* L, const srl_config_t* cfg) {

@@ -54,7 +54,34 @@ SRL_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
 // prefetch, loads of data that was complete long before the predecessor started) overlaps the predecessor's tail;
 // pdl_wait() returns once the predecessor grid has completed and its memory is visible.  pdl_launch() lets the NEXT
 // kernel in the stream begin its own prologue.  Both are no-ops for a kernel launched without the attribute.
-SRL_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Diagnostics build (SRL_DEFINES=SRL_KSTAMP, tests/diag/diag_timeline.py): thread 0 of block 0 of every kernel appends {kernel id, %globaltimer at
+// entry, %globaltimer when its stream predecessor had completed} to a buffer -- the in-graph timeline of a step, which no profiler here can
+// show (ncu serialises the launches, per-kernel CUDA events break the programmatic dependencies).  Never defined in the product build.
+#ifdef SRL_KSTAMP
+static __device__ unsigned long long* g_kstamp = nullptr;      // one copy per translation unit: kstamp_set_<unit>() (kernels.h)
+SRL_DEVINL unsigned long long kstamp_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+SRL_DEVINL void kstamp_put(int kid, unsigned long long t0) {
+  if (g_kstamp && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    const unsigned long long t1 = kstamp_now(), i = atomicAdd(g_kstamp, 1ull);
+    if (i < 2000) { g_kstamp[1 + 3 * i] = (unsigned long long)kid; g_kstamp[2 + 3 * i] = t0; g_kstamp[3 + 3 * i] = t1; }
+  }
+}
+#define SRL_KSTAMP_SETTER(fn) void fn(unsigned long long* q) { cudaMemcpyToSymbol(g_kstamp, &q, sizeof q); }
+#else
+#define SRL_KSTAMP_SETTER(fn) void fn(unsigned long long*) {}
+#endif
+// kid: the kernel's id in the diagnostics timeline (ignored by the product build)
+SRL_DEVINL void pdl_wait(int kid = 0) {
+#ifdef SRL_KSTAMP
+  const unsigned long long t0 = kstamp_now();
+#endif
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef SRL_KSTAMP
+  if (kid) kstamp_put(kid, t0);
+#else
+  (void)kid;
+#endif
+}
 SRL_DEVINL void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // 16-byte shared-memory load through the shared pipe (LDS), never a generic LD: keeps it in order with mbarrier operations

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) enc_fused_fwd_kernel(const EncF
   // the halo rows of the a1 planes that no epilogue ever writes (rows 100.. of plane 1) feed only discarded MMA rows: zero them once
   for (int i = tid; i < (FF_A1_BYTES - 2 * FF_A1_PLANE) / 16; i += FF_THREADS)
     reinterpret_cast<uint4*>(sA1 + 2 * FF_A1_PLANE)[i] = make_uint4(0, 0, 0, 0);
-  pdl_wait();                            // the parameters below were written by the previous step's optimizer kernel
+  pdl_wait(54);                          // the parameters below were written by the previous step's optimizer kernel
   pdl_launch();
   if (tid == 0) ff_stamp(p, 0, 0, 1);
   // ---- conv weights: fp32 master -> bf16 K-major SWIZZLE_128B operand tiles (what pack_weights_kernel + TMA would deliver).

@@ -27,6 +27,7 @@ SRL_DEVINL void pack_store2(bf16* __restrict__ out, bf16* __restrict__ out_lo, i
   if (out_lo) *reinterpret_cast<uint32_t*>(out_lo + i) = pack_bf16x2(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
 }
 __global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __restrict__ out, bf16* __restrict__ out_lo) {
+  pdl_wait(2);     // (not launched with the attribute: returns at once; names the kernel in the diagnostics timeline)
   __shared__ __align__(16) float tile[64 * 99];                 // role 1: two fc rows (2 x 3136); role 2: [64 j][99]
   const int t = threadIdx.x, b = blockIdx.x;
   if (b < PACK_BLOCKS_FK) {
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __
 // S2D_Y x 21 x 128 B contiguously.  S2D_Y = 21 (a whole frame per block, 84 B of loads in flight per thread) by default.
 template <int S2D_Y>
 __global__ void __launch_bounds__(352) obs_s2d_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ xs) {
-  pdl_wait();      // launched with programmatic stream serialization: see common.cuh
+  pdl_wait(1);     // launched with programmatic stream serialization: see common.cuh
   pdl_launch();
   __shared__ uint32_t tile[S2D_Y][16][21];
   const int n = blockIdx.x / (21 / S2D_Y), Y0 = (blockIdx.x - n * (21 / S2D_Y)) * S2D_Y;
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(352) obs_s2d_kernel(const uint8_t* __restrict_
 // with a3t as its B operand the fc weight-gradient GEMM produces 64 CONSECUTIVE columns of dW per row (16-byte stores) instead of 64
 // stores 196 B apart.  One frame per block through shared memory, 16-byte reads, 4-byte writes; runs on the wgrad side stream.
 __global__ void __launch_bounds__(256) a3_transpose_kernel(const bf16* __restrict__ a3, bf16* __restrict__ a3t) {
+  pdl_wait(53);
   __shared__ __align__(16) uint16_t tile[49 * 66];        // row hw: 64 channels + 2 pad (132 B pitch: conflict-free column reads)
   const int n = blockIdx.x, t = threadIdx.x;
   const uint4* src = reinterpret_cast<const uint4*>(a3 + (size_t)n * 3136);
@@ -143,6 +145,8 @@ __global__ void __launch_bounds__(256) a3_transpose_kernel(const bf16* __restric
     dst[pp] = (uint32_t)tile[h0 * 66 + c0] | ((uint32_t)tile[h1 * 66 + c1] << 16);
   }
 }
+SRL_KSTAMP_SETTER(kstamp_set_encoder)
+
 cudaError_t launch_a3_transpose(const bf16* a3, bf16* a3t, int frames, cudaStream_t st) {
   if (frames <= 0) return cudaSuccess;
   a3_transpose_kernel<<<frames, 256, 0, st>>>(a3, a3t);
@@ -298,7 +302,7 @@ static int persistent_ctas() {
 // workspace [tap-block][row][co] -> PyTorch-layout conv weight gradients (plain stores), and re-zero what was read
 __global__ void __launch_bounds__(256) conv_wgrad_finalize_kernel(float* __restrict__ ws, float* __restrict__ g1, float* __restrict__ g2,
                                                                   float* __restrict__ g3) {
-  pdl_wait();      // launched with programmatic stream serialization: see common.cuh
+  pdl_wait(51);    // launched with programmatic stream serialization: see common.cuh
   pdl_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 36864) {                       // dW3[co][c][tap] = ws3[tap>>1][(tap&1)*64 + c][co]

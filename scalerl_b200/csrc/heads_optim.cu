@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ bp, const float* __restrict__ Wb,
                                                        const float* __restrict__ bb, int N, int A, float* __restrict__ logits,
                                                        float* __restrict__ baseline) {
-  pdl_wait();      // launched with programmatic stream serialization: see common.cuh
+  pdl_wait(46);    // launched with programmatic stream serialization: see common.cuh
   pdl_launch();
   __shared__ float part[2][4][HEAD_MAX_A + 1];
   const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3, f = threadIdx.x >> 7;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128) head_bwd_dh_kernel(const float* __restric
                                                           const float* __restrict__ h, const float* __restrict__ Wp,
                                                           const float* __restrict__ Wb, int N, int A, __nv_bfloat16* __restrict__ dh,
                                                           __nv_bfloat16* __restrict__ dh_lo) {
-  pdl_wait();      // launched with programmatic stream serialization: see common.cuh
+  pdl_wait(47);    // launched with programmatic stream serialization: see common.cuh
   pdl_launch();
   const int n = blockIdx.x;
   const int j = blockIdx.y * 128 + threadIdx.x;
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict
                                                          const int64_t* __restrict__ action, int N, int A, int rows_per_slab,
                                                          float* __restrict__ gWp, float* __restrict__ gbp, float* __restrict__ gWb,
                                                          float* __restrict__ gbb) {
+  pdl_wait(48);    // (side stream, no attribute: returns at once; names the kernel in the diagnostics timeline)
   __shared__ float sd[HEAD_SLAB][HEAD_MAX_A + 1];
   __shared__ float sr[HEAD_SLAB];
   __shared__ int sa[HEAD_SLAB];
@@ -397,6 +398,7 @@ __global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, 
                                                          float* __restrict__ scratch, float lr, float a, float b, float eps, int step,
                                                          int* __restrict__ dstep) {
   cg::grid_group grid = cg::this_grid();
+  pdl_wait(52);    // (cooperative launch, no attribute: returns at once; names the kernel in the diagnostics timeline)
   const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int t = dstep ? *dstep + 1 : step;          // 1-based step count: Adam bias correction; counted for RMSprop too (checkpoints)
   // The thread's first HOLD float4 of g (and, for RMSprop, of p and the state) stay in registers across the grid barrier: phase 2 then
@@ -497,6 +499,8 @@ __global__ void __launch_bounds__(512) clip_optim_kernel(float* __restrict__ p, 
     }
   }
 }
+
+SRL_KSTAMP_SETTER(kstamp_set_heads)
 
 template <int OPT>
 static cudaError_t launch_clip_optim_t(float* p, float* g, float* s0, float* s1, int64_t n, float max_norm, float* coef, float* scratch,

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp != 4) pdl_wait();
+  if (warp != 4) pdl_wait(P::KID);
 
   if (warp == 4) {
     const uint32_t leader = elect_one_sync();      // converged warp, one elected issuing lane: no vote loop around every TMA instruction
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(RES_THREADS) res_wgrad_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   unsigned long long wg_t0 = 0; WG_STAMP(wg_t0);
-  pdl_wait();
+  pdl_wait(P::KID);
   if (tid == 128) pdl_launch();
   unsigned long long wg_t1 = 0; WG_STAMP(wg_t1);
 

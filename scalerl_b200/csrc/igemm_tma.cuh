@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(IGT_THREADS) igemm_tma_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                         // prologue above overlaps the previous kernel's tail
+  pdl_wait(P::KID);                   // prologue above overlaps the previous kernel's tail
   if (tid == 128) pdl_launch();
 
   if (warp == 4) {

@@ -59,6 +59,7 @@ inline cudaError_t ensure_max_dynamic_smem(PerDeviceOnce& once, K kernel, int by
   return e;
 }
 
+void kstamp_set_encoder(unsigned long long*); void kstamp_set_vtrace(unsigned long long*); void kstamp_set_heads(unsigned long long*);   // diagnostics build (common.cuh)
 int side_mode();   // SRL_SIDE_MODE diagnostic bitmask: 1 = one wgrad side stream, 2 = head wgrad on the main stream, 4 = grad memset on the main stream
 
 struct SideStream {

@@ -21,6 +21,7 @@ namespace srl {
 
 // ------------------------------------------------------------------------------------------------ generic GEMM problems
 struct LGemmK {
+  static constexpr int KID = 34;
   static constexpr bool PREFETCH = false;      // C[c_row0 + m][n] = sum_k A[a_row0 + m][k] * B[n][k];  grid = (ceil(M/128), Npad/64)
   static constexpr int BN = 64, STAGES = 4, KROWS = 64;
   static constexpr bool A_MN = false, B_MN = false, ZERO_INIT = false;
@@ -41,6 +42,7 @@ struct LGemmK {
   }
 };
 struct LGemmMN {
+  static constexpr int KID = 35;
   static constexpr bool PREFETCH = false;     // C[i][j] = sum_r A[r][i] * B[r][j]  (rows r = samples, MN-major operands); grid = (Ipad/128, Jpad/64)
   static constexpr int BN = 64, STAGES = 4, KROWS = 64;
   static constexpr bool A_MN = true, B_MN = true, ZERO_INIT = false;

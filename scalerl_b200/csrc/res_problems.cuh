@@ -29,6 +29,7 @@ SRL_DEVINL void store_act16(bf16* hi, bf16* lo, size_t elem_off, const float (&v
 
 // ================================================================================================ forward
 struct RConv1Fwd {   // 2x2 s1 over xs (== 8x8 s4 over the frame): taps (kh2,kw2) -> shifts {0, 1, 21, 22}
+  static constexpr int KID = 11;        // diagnostics timeline id
   static constexpr int BN = 32, NT = 4, NWIN = 1, WROWS = 128 + 22, STAGES = 4, SPLIT_STAGES = 4;
   static constexpr bool A_LO = false;        // the frames are exact in bf16: only the weights have a low tensor
   struct Params { SRL_TMAP in0; SRL_TMAP w; SRL_TMAP w_lo; const float* bias; bf16* out; bf16* out_lo; int NF; int NFS; };   // NF frames now, NFS = frames the a1 planes are strided for
@@ -50,6 +51,7 @@ struct RConv1Fwd {   // 2x2 s1 over xs (== 8x8 s4 over the frame): taps (kh2,kw2
 };
 
 struct RConv2Fwd {   // 4x4 s2 over a1: tap j = (kh, kww): plane kh&1, shift (kh>>1)*10 + kww, K-block = (kh, kw in {2kww, 2kww+1}, c)
+  static constexpr int KID = 12;        // diagnostics timeline id
   static constexpr int BN = 64, NT = 8, NWIN = 2, WROWS = 128 + 11, STAGES = 3, SPLIT_STAGES = 1;
   static constexpr bool A_LO = true;
   struct Params { SRL_TMAP in0; SRL_TMAP in1; SRL_TMAP w; SRL_TMAP in0_lo; SRL_TMAP in1_lo; SRL_TMAP w_lo; const float* bias; bf16* out; bf16* out_lo; int NF; };
@@ -73,6 +75,7 @@ struct RConv2Fwd {   // 4x4 s2 over a1: tap j = (kh, kww): plane kh&1, shift (kh
 };
 
 struct RConv3Fwd {   // 3x3 s1 over a2: tap (kh,kw) -> shift kh*9 + kw
+  static constexpr int KID = 13;        // diagnostics timeline id
   static constexpr int BN = 64, NT = 9, NWIN = 1, WROWS = 128 + 20, STAGES = 4, SPLIT_STAGES = 2;
   static constexpr bool A_LO = true;
   struct Params { SRL_TMAP in0; SRL_TMAP w; SRL_TMAP in0_lo; SRL_TMAP w_lo; const float* bias; bf16* out; bf16* out_lo; int NF; };
@@ -94,6 +97,7 @@ struct RConv3Fwd {   // 3x3 s1 over a2: tap (kh,kw) -> shift kh*9 + kw
 
 // ================================================================================================ dgrad
 struct RConv3Dgrad {   // da2[ih,iw] = sum_{kh,kw} da3g[(ih-kh),(iw-kw)] W3[:, :, kh, kw]: shifts -(kh*9+kw); window starts 20 rows early
+  static constexpr int KID = 14;        // diagnostics timeline id
   static constexpr int BN = 64, NT = 9, NWIN = 1, WROWS = 128 + 20, STAGES = 4, SPLIT_STAGES = 2;
   static constexpr bool A_LO = true;
   struct Params { SRL_TMAP in0; SRL_TMAP w; SRL_TMAP in0_lo; SRL_TMAP w_lo; const bf16* act; bf16* dx; bf16* dx_lo; int NB; };
@@ -116,6 +120,7 @@ struct RConv3Dgrad {   // da2[ih,iw] = sum_{kh,kw} da3g[(ih-kh),(iw-kw)] W3[:, :
 };
 
 struct RConv2Dgrad {   // the 4 stride-parity classes share A (da2g at (i'-kh', j'-kw')): one N = 4 x 32 GEMM; shifts -(kh'*10 + kw')
+  static constexpr int KID = 15;        // diagnostics timeline id
   static constexpr int BN = 128, NT = 4, NWIN = 1, WROWS = 128 + 11, STAGES = 3, SPLIT_STAGES = 2;
   static constexpr bool A_LO = true;
   struct Params { SRL_TMAP in0; SRL_TMAP w; SRL_TMAP in0_lo; SRL_TMAP w_lo; const bf16* act; bf16* dx; bf16* dx_lo; int NB; int NF; };
@@ -144,6 +149,7 @@ struct RConv2Dgrad {   // the 4 stride-parity classes share A (da2g at (i'-kh', 
 // gradient tensors.  Workspace offsets (floats):
 // (WS_W3 / WS_W2 / WS_W1 / WS_TOTAL are defined in kernels.h: the optimizer kernel reads the workspace too)
 struct RConv3Wgrad {   // acc a = taps (2a, 2a+1); acc 4 = (tap 8, ones -> db3).  ws: [10 taps][64 c][64 co] fp32 (co contiguous)
+  static constexpr int KID = 21;        // diagnostics timeline id
   static constexpr int NACC = 5, NWIN = 1, WROWS = 128 + 20, STAGES = 3, SPLIT_STAGES = 2;
   static constexpr bool A_LO = true;
   static constexpr bool SMEM_BIAS = false;     // the ninth tap leaves half an accumulator free: the all-ones block rides along
@@ -169,6 +175,7 @@ struct RConv3Wgrad {   // acc a = taps (2a, 2a+1); acc 4 = (tap 8, ones -> db3).
 };
 
 struct RConv2Wgrad {   // acc a = kh (blocks kww = 0,1: rows = (kw = 2kww + wp, c)); db2 = column sums of the staged dy tiles
+  static constexpr int KID = 22;        // diagnostics timeline id
   static constexpr int NACC = 4, NWIN = 2, WROWS = 128 + 11, STAGES = 3, SPLIT_STAGES = 1;
   static constexpr bool A_LO = true;
   static constexpr bool SMEM_BIAS = true;
@@ -190,6 +197,7 @@ struct RConv2Wgrad {   // acc a = kh (blocks kww = 0,1: rows = (kw = 2kww + wp, 
 };
 
 struct RConv1Wgrad {   // acc a = kh2 (blocks kw2 = 0,1: rows = (kw2, c, dy, dx)); db1 = column sums of the staged dy tiles
+  static constexpr int KID = 23;        // diagnostics timeline id
   static constexpr int NACC = 2, NWIN = 1, WROWS = 128 + 22, STAGES = 5, SPLIT_STAGES = 3;
   static constexpr bool A_LO = false;          // the frames are exact in bf16
   static constexpr bool SMEM_BIAS = true;

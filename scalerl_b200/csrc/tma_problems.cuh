@@ -10,6 +10,7 @@ namespace srl {
 
 // ============================================================================================ fc
 struct TFcFwd {
+  static constexpr int KID = 31;        // diagnostics timeline id
   static constexpr bool PREFETCH = false;   // split-K partials; grid.y = 8 N-tiles x FC_SPLITS, ty = nt*FC_SPLITS + split
   static constexpr int BN = 64, STAGES = 4, SPLITS = 4;
   static constexpr bool A_MN = false, B_MN = false, ZERO_INIT = false;
@@ -44,6 +45,7 @@ struct TFcFwd {
 };
 
 struct TFcDgrad {
+  static constexpr int KID = 32;        // diagnostics timeline id
   static constexpr bool PREFETCH = true;   // da3[m][i] = (dh[m][:] . Wfc[:][i]) * (a3 > 0); grid = (ceil(M/128), 49)
   static constexpr int BN = 64, STAGES = 4;
   static constexpr bool A_MN = false, B_MN = false, ZERO_INIT = false;
@@ -93,6 +95,7 @@ SRL_DEVINL void fill_ones(uint8_t* dst, int bytes, int tid) {   // bf16 1.0 = 0x
 }
 
 struct TFcWgrad {
+  static constexpr int KID = 33;        // diagnostics timeline id
   static constexpr bool PREFETCH = false;   // grid = (1, 4*50): ty = hw*4 + jt, hw == 49 is the ones slice (B = ones -> dbfc); stage = 64 frames
   static constexpr int BN = 64, STAGES = 4, KROWS = 64;
   static constexpr bool A_MN = true, B_MN = true, ZERO_INIT = true;

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(128) impala_tail_kernel(const float* __restric
                                                           float baseline_cost, float entropy_cost, float* __restrict__ vs,
                                                           float* __restrict__ pg, float* __restrict__ dlogits, float* __restrict__ dbaseline,
                                                           float* __restrict__ losses, float* __restrict__ scratch) {
-  pdl_wait();      // launched with programmatic stream serialization: see common.cuh
+  pdl_wait(44);    // launched with programmatic stream serialization: see common.cuh
   pdl_launch();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l_pg = 0.f, l_bl = 0.f, l_ent = 0.f;
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(128) impala_tail_warp_kernel(const float* __re
                                                                float* __restrict__ vs, float* __restrict__ pg, float* __restrict__ dlogits,
                                                                float* __restrict__ dbaseline, float* __restrict__ losses,
                                                                float* __restrict__ scratch) {
-  pdl_wait();      // launched with programmatic stream serialization: see common.cuh
+  pdl_wait(45);    // launched with programmatic stream serialization: see common.cuh
   pdl_launch();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * 4 + warp;
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(COL_THREADS) column_step_kernel(
     for (int a = 0; a <= AMAX; ++a)
       if (a <= A) s_w[a * WS + j] = wv[a];
   }
-  pdl_wait();
+  pdl_wait(41);
   pdl_launch();
   __syncthreads();
   stamp(1);
@@ -684,6 +684,8 @@ static size_t column_smem_bytes(int T, int A) {
   const int CORE = 513 + A, WS = (CORE + 3) & ~3;
   return sizeof(float) * ((size_t)(A + 1) * WS + (size_t)(T + 1) * 512 + (size_t)(T + 1) * A + (T + 1) + (size_t)T * (A + 1));
 }
+SRL_KSTAMP_SETTER(kstamp_set_vtrace)
+
 bool column_step_supported(int T, int B, int A) {
   return T >= 1 && B >= 1 && B <= 512 && A >= 1 && A <= COL_MAX_A && column_smem_bytes(T, A) <= 200 * 1024;
 }

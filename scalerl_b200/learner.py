@@ -569,6 +569,15 @@ class B200ImpalaLearner(BaseAgent):
         self._graphs.clear()
         self._seen.clear()
 
+    def _capture_stream(self):
+        """The step is captured from a HIGH-priority stream: the kernels of the main chain (forward, dgrads, conv1's wgrad, optimizer) carry
+        that priority as graph nodes, the wgrad / re-pack kernels launched on the library's side streams keep the default (lowest) one -- when
+        both are ready the block scheduler places the critical chain first (profiles/r02_timeline.md).  SRL_CAPTURE_PRIORITY=0 switches it off."""
+        if getattr(self, '_cap_stream', None) is None:
+            prio = int(os.environ.get('SRL_CAPTURE_PRIORITY', '-1'))
+            self._cap_stream = torch.cuda.Stream(device=self.device, priority=prio)
+        return self._cap_stream
+
     def _graph_step(self, batch):
         """Replay the step as CUDA graph(s) keyed by the batch buffers' addresses.  First sight of a buffer set runs
         eagerly (warm-up: sets kernel attributes, allocator state), the second captures, later calls replay.
@@ -586,14 +595,14 @@ class B200ImpalaLearner(BaseAgent):
             torch.cuda.current_stream(self.device).synchronize()
             if self._dist and self._peers is not None:     # whole DP step in ONE graph: the reduction is inside the apply kernel
                 g = (torch.cuda.CUDAGraph(),)
-                with torch.cuda.graph(g[0]):
+                with torch.cuda.graph(g[0], stream=self._capture_stream()):
                     self.forward_backward(batch)
                     self.apply_gradients_dp()
             elif self._dist and self.hp.use_lstm:
                 g = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph())
-                with torch.cuda.graph(g[0]):
+                with torch.cuda.graph(g[0], stream=self._capture_stream()):
                     self.forward_backward(batch)
-                with torch.cuda.graph(g[1]):
+                with torch.cuda.graph(g[1], stream=self._capture_stream()):
                     self.apply_gradients()
             elif self._dist:
                 g = None
@@ -601,7 +610,7 @@ class B200ImpalaLearner(BaseAgent):
                     try:        # opt-in: ONE graph with the two NCCL all-reduces captured inside it (measured: no faster than split
                                 # graphs, and process-group teardown can hang while such graphs are alive -- call release_graphs() first)
                         g1 = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g1):
+                        with torch.cuda.graph(g1, stream=self._capture_stream()):
                             self._dp_step(batch, lambda: self.forward_backward_begin(batch), lambda: self.backward_finish(batch),
                                           self.apply_gradients)
                         g = (g1,)
@@ -612,15 +621,15 @@ class B200ImpalaLearner(BaseAgent):
                         g = None
                 if g is None:
                     g = tuple(torch.cuda.CUDAGraph() for _ in range(3))
-                    with torch.cuda.graph(g[0]):
+                    with torch.cuda.graph(g[0], stream=self._capture_stream()):
                         self.forward_backward_begin(batch)
-                    with torch.cuda.graph(g[1]):
+                    with torch.cuda.graph(g[1], stream=self._capture_stream()):
                         self.backward_finish(batch)
-                    with torch.cuda.graph(g[2]):
+                    with torch.cuda.graph(g[2], stream=self._capture_stream()):
                         self.apply_gradients()
             else:
                 g = (torch.cuda.CUDAGraph(),)
-                with torch.cuda.graph(g[0]):
+                with torch.cuda.graph(g[0], stream=self._capture_stream()):
                     self.forward_backward(batch)
                     self.apply_gradients()
             self._graphs[key] = g
