@@ -294,6 +294,11 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   if (cudaStreamCreateWithFlags(&L->ss.side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&L->ss.side2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&L->ss.side3, cudaStreamNonBlocking) != cudaSuccess) L->ss.side = nullptr;
+  {
+    int lo = 0, hi = 0;       // (numerically lowest = greatest priority)
+    if (L->ss.side && (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
+                       cudaStreamCreateWithPriority(&L->ss.pack, cudaStreamNonBlocking, hi) != cudaSuccess)) L->ss.side = nullptr;
+  }
   for (int e2 = 0; e2 < 12 && L->ss.side; ++e2)
     if (cudaEventCreateWithFlags(&L->ss.ev[e2], cudaEventDisableTiming) != cudaSuccess) { L->ss.side = nullptr; }
   cudaGetLastError();
@@ -360,6 +365,7 @@ extern "C" int srl_learner_destroy(srl_learner_t* L) {
   if (L->ss.side) cudaStreamDestroy(L->ss.side);
   if (L->ss.side2) cudaStreamDestroy(L->ss.side2);
   if (L->ss.side3) cudaStreamDestroy(L->ss.side3);
+  if (L->ss.pack) cudaStreamDestroy(L->ss.pack);
   if (L->lstm) srl_lstm_destroy(L->lstm);
   if (L->lstm_arena) cudaFree(L->lstm_arena);
   if (L->lo_arena) cudaFree(L->lo_arena);
@@ -446,14 +452,14 @@ static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStrea
   }
   if (L->ss.side && !L->pf.on) {
     CU(cudaEventRecord(L->ss.ev[5], st), "fork pack");
-    CU(cudaStreamWaitEvent(L->ss.side, L->ss.ev[5], 0), "fork pack");
+    CU(cudaStreamWaitEvent(L->ss.pack, L->ss.ev[5], 0), "fork pack");
     if (zero_small_grads) {   // the accumulated gradient segments (everything before fc.weight) are cleared under the frame conversion
       int64_t off[12], cnt[12];
       layout(L->cfg.A, off, cnt);
-      CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), L->ss.side), "zero small grads");
+      CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), L->ss.pack), "zero small grads");
     }
-    CU(launch_pack_weights(L->P, L->buf.wpack, L->ss.side, L->buf.wpack_lo), "pack_weights");
-    CU(cudaEventRecord(L->ss.ev[6], L->ss.side), "join pack");
+    CU(launch_pack_weights(L->P, L->buf.wpack, L->ss.pack, L->buf.wpack_lo), "pack_weights");
+    CU(cudaEventRecord(L->ss.ev[6], L->ss.pack), "join pack");
     packed = L->ss.ev[6];
   } else {
     if (zero_small_grads) {

@@ -66,6 +66,7 @@ struct SideStream {
   cudaStream_t side = nullptr;      // fc wgrad, weight re-pack
   cudaStream_t side2 = nullptr;     // conv3 wgrad
   cudaStream_t side3 = nullptr;     // conv2 wgrad
+  cudaStream_t pack = nullptr;      // weight re-pack + gradient memset at the start of a step: HIGHEST priority (conv2 waits for it), unlike the wgrad streams
   cudaEvent_t ev[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
