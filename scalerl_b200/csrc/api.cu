@@ -216,6 +216,7 @@ static int check_cfg(const srl_config_t* c) {
   return 0;
 }
 
+static int pack_priority(int least, int greatest);
 extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float* grads, float* opt0, float* opt1, srl_learner_t** out) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
@@ -297,7 +298,7 @@ extern "C" int srl_learner_create(const srl_config_t* cfg, float* params, float*
   {
     int lo = 0, hi = 0;       // (numerically lowest = greatest priority)
     if (L->ss.side && (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
-                       cudaStreamCreateWithPriority(&L->ss.pack, cudaStreamNonBlocking, hi) != cudaSuccess)) L->ss.side = nullptr;
+                       cudaStreamCreateWithPriority(&L->ss.pack, cudaStreamNonBlocking, pack_priority(lo, hi)) != cudaSuccess)) L->ss.side = nullptr;
   }
   for (int e2 = 0; e2 < 12 && L->ss.side; ++e2)
     if (cudaEventCreateWithFlags(&L->ss.ev[e2], cudaEventDisableTiming) != cudaSuccess) { L->ss.side = nullptr; }
@@ -437,6 +438,16 @@ int pdl_skip_mask() {
   return m;
 }
 }  // namespace srl
+
+// the re-pack stream sits one level BELOW the greatest priority (which the learner's capture stream uses for the main chain) and above the wgrad
+// streams (default = least): its short blocks fill the slots the frame conversion leaves free without delaying it.  SRL_PACK_PRIORITY overrides.
+static int pack_priority(int least, int greatest) {
+  const char* e = getenv("SRL_PACK_PRIORITY");
+  int v = e ? atoi(e) : greatest + 1;
+  if (v < greatest) v = greatest;
+  if (v > least) v = least;
+  return v;
+}
 
 static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStream_t st, bool zero_small_grads = false) {
   L->pf.st = st;

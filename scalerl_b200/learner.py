@@ -574,7 +574,7 @@ class B200ImpalaLearner(BaseAgent):
         that priority as graph nodes, the wgrad / re-pack kernels launched on the library's side streams keep the default (lowest) one -- when
         both are ready the block scheduler places the critical chain first (profiles/r02_timeline.md).  SRL_CAPTURE_PRIORITY=0 switches it off."""
         if getattr(self, '_cap_stream', None) is None:
-            prio = int(os.environ.get('SRL_CAPTURE_PRIORITY', '-1'))
+            prio = int(os.environ.get('SRL_CAPTURE_PRIORITY', '-100'))      # clamped to the device's greatest priority
             self._cap_stream = torch.cuda.Stream(device=self.device, priority=prio)
         return self._cap_stream
 
