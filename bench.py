@@ -629,7 +629,8 @@ def _main(real_stdout):
         peer = getattr(learner, '_peers', None) is not None
         cfg = workload_config(T, B, A, world, args.use_lstm)
         impl = {'parallelism': f'dp{world}' if world > 1 else 'single',
-                'grad_allreduce': 'none' if world == 1 else ('peer memory (NVLink loads) fused into the clip+optimizer kernel' if peer else 'nccl sum'),
+                'grad_allreduce': 'none' if world == 1 else ((('NVLS multimem.ld_reduce (in-switch sum)' if getattr(learner, 'dp_path', '') == 'nvls multimem'
+                                                                else 'peer memory (NVLink loads)') + ' fused into the clip+optimizer kernel') if peer else 'nccl sum'),
                 'l2': f'inputs cycle through {POOL} distinct batches ({POOL * feeder.h2d_bytes / 1e6:.0f} MB > 126 MB L2)',
                 'operands': 'bf16 tensor-core operands, fp32 accumulate, fp32 master weights / V-trace / optimizer',
                 'launch': 'one CUDA graph per step (wgrad GEMMs on parallel branches, programmatic dependent launch)'
