@@ -298,6 +298,11 @@ static int persistent_ctas() {
   return v;
 }
 #define kPersistentCtas persistent_ctas()
+// CTAs of the conv3 / conv2 weight-gradient kernels (side streams).  SRL_WGRAD_CTAS overrides (diagnostics).
+static int side_wgrad_ctas() {
+  static const int v = [] { const char* e = getenv("SRL_WGRAD_CTAS"); int x = e ? atoi(e) : 64; return x < 8 || x > 148 ? 64 : x; }();
+  return v;
+}
 
 // workspace [tap-block][row][co] -> PyTorch-layout conv weight gradients (plain stores), and re-zero what was read
 __global__ void __launch_bounds__(256) conv_wgrad_finalize_kernel(float* __restrict__ ws, float* __restrict__ g1, float* __restrict__ g2,
@@ -400,12 +405,12 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
   if (!do_conv) return cudaSuccess;
   if (fork) { SRL_TRY(cudaEventRecord(ss.ev[1], st)); SRL_TRY(cudaStreamWaitEvent(s2, ss.ev[1], 0)); }
   { RConv3Wgrad::Params q{maps.a2_w, maps.da3g_b, L.a2_w, L.da3g_b, buf.wgrad_ws + WS_W3, g.b3, frames * 81, 0};
-    p2.b(PS_CONV3_WGRAD); SRL_TRY(res_wgrad_launch<RConv3Wgrad>(q, 64, s2, sp)); p2.e(PS_CONV3_WGRAD); }
+    p2.b(PS_CONV3_WGRAD); SRL_TRY(res_wgrad_launch<RConv3Wgrad>(q, side_wgrad_ctas(), s2, sp)); p2.e(PS_CONV3_WGRAD); }
   { RConv3Dgrad::Params q{maps.da3g_w, maps.w3d, L.da3g_w, L.w3d, buf.a2, buf.da2, buf.da2_lo, frames};
     pf.b(PS_CONV3_DGRAD); SRL_TRY(res_fwd_launch<RConv3Dgrad>(q, cdiv(frames * 81, 128), kPersistentCtas, st, sp)); pf.e(PS_CONV3_DGRAD); }
   if (fork) { SRL_TRY(cudaEventRecord(ss.ev[2], st)); SRL_TRY(cudaStreamWaitEvent(s3, ss.ev[2], 0)); }
   { RConv2Wgrad::Params q{maps.a1p0_w, maps.a1p1_w, maps.da2g_b, L.a1p0_w, L.a1p1_w, L.da2g_b, buf.wgrad_ws + WS_W2, g.b2, frames * 100, 0};
-    p3.b(PS_CONV2_WGRAD); SRL_TRY(res_wgrad_launch<RConv2Wgrad>(q, 64, s3, sp)); p3.e(PS_CONV2_WGRAD); }
+    p3.b(PS_CONV2_WGRAD); SRL_TRY(res_wgrad_launch<RConv2Wgrad>(q, side_wgrad_ctas(), s3, sp)); p3.e(PS_CONV2_WGRAD); }
   { RConv2Dgrad::Params q{maps.da2g_w, maps.w2d, L.da2g_w, L.w2d, buf.a1, buf.da1, buf.da1_lo, frames, buf.NF};
     pf.b(PS_CONV2_DGRAD); SRL_TRY(res_fwd_launch<RConv2Dgrad>(q, cdiv(frames * 100, 128), kPersistentCtas, st, sp)); pf.e(PS_CONV2_DGRAD); }
   { RConv1Wgrad::Params q{maps.xs_w, maps.da1g_b, L.da1g_b, buf.wgrad_ws + WS_W1, g.b1, frames * 441, 0};
