@@ -469,7 +469,7 @@ static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStrea
       layout(L->cfg.A, off, cnt);
       CU(cudaMemsetAsync(L->grads, 0, off[6] * sizeof(float), L->ss.pack), "zero small grads");
     }
-    CU(launch_pack_weights(L->P, L->buf.wpack, L->ss.pack, L->buf.wpack_lo), "pack_weights");
+    CU(launch_pack_weights(L->P, L->buf.wpack, L->ss.pack, L->buf.wpack_lo, true), "pack_weights");
     CU(cudaEventRecord(L->ss.ev[6], L->ss.pack), "join pack");
     packed = L->ss.ev[6];
   } else {
@@ -481,7 +481,7 @@ static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStrea
       L->pf.e(PS_ZERO_GRADS);
     }
     L->pf.b(PS_PACK);
-    CU(launch_pack_weights(L->P, L->buf.wpack, st, L->buf.wpack_lo), "pack_weights");
+    CU(launch_pack_weights(L->P, L->buf.wpack, st, L->buf.wpack_lo, true), "pack_weights");
     L->pf.e(PS_PACK);
   }
   CU(encoder_forward(obs, frames, L->P, L->buf, L->maps, L->cfg.precision, st, L->pf, packed, &L->maps_lo, L->fused_front), "encoder_forward");

@@ -26,7 +26,7 @@ SRL_DEVINL void pack_store2(bf16* __restrict__ out, bf16* __restrict__ out_lo, i
   *reinterpret_cast<uint32_t*>(out + i) = pack_bf16x2(v0, v1);
   if (out_lo) *reinterpret_cast<uint32_t*>(out_lo + i) = pack_bf16x2(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
 }
-__global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __restrict__ out, bf16* __restrict__ out_lo) {
+__global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __restrict__ out, bf16* __restrict__ out_lo, int skip_w1k) {
   pdl_wait(2);     // (not launched with the attribute: returns at once; names the kernel in the diagnostics timeline)
   __shared__ __align__(16) float tile[64 * 99];                 // role 1: two fc rows (2 x 3136); role 2: [64 j][99]
   const int t = threadIdx.x, b = blockIdx.x;
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __
       const int64_t i = n < WPack::WFK ? n : n - WPack::WFK + WPack::W3D;
       float v;
       if (i < WPack::W2K) {                       // w1k[co][(kh2*2+kw2)*64 + c*16 + dy*4 + dx] = W1[co][c][4kh2+dy][4kw2+dx]
+        if (skip_w1k) continue;                   // written by obs_s2d_kernel's extra blocks inside a step
         const int e = (int)(i - WPack::W1K), co = e >> 8, k = e & 255, tap = k >> 6, q = k & 63;
         const int c = q >> 4, dy = (q >> 2) & 3, dx = q & 3, kh = 4 * (tap >> 1) + dy, kw = 4 * (tap & 1) + dx;
         v = p.w1[co * 256 + c * 64 + kh * 8 + kw];
@@ -98,9 +99,21 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs p, bf16* __
 // thread in flight together) into shared memory, then each thread converts u32 (4 x dx) -> 4 bf16 and the block writes
 // S2D_Y x 21 x 128 B contiguously.  S2D_Y = 21 (a whole frame per block, 84 B of loads in flight per thread) by default.
 template <int S2D_Y>
-__global__ void __launch_bounds__(352) obs_s2d_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ xs) {
+__global__ void __launch_bounds__(352) obs_s2d_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ xs, int frame_blocks,
+                                                      const float* __restrict__ w1, bf16* __restrict__ w1k, bf16* __restrict__ w1k_lo) {
   pdl_wait(1);     // launched with programmatic stream serialization: see common.cuh
   pdl_launch();
+  if ((int)blockIdx.x >= frame_blocks) {
+    // extra blocks: conv1's K-major weight copy w1k[co][(kh2*2+kw2)*64 + c*16 + dy*4 + dx] = W1[co][c][4kh2+dy][4kw2+dx] -- conv1 is the next kernel
+    // of the stream, so it never has to wait for pack_weights_kernel (which skips this copy when the step launches it)
+    const int e = ((int)blockIdx.x - frame_blocks) * 352 + (int)threadIdx.x;
+    if (e < 32 * 256 && w1k) {
+      const int co = e >> 8, k = e & 255, tap = k >> 6, q = k & 63;
+      const int c = q >> 4, dy = (q >> 2) & 3, dx = q & 3, kh = 4 * (tap >> 1) + dy, kw = 4 * (tap & 1) + dx;
+      pack_store(w1k, w1k_lo, e, __ldg(w1 + co * 256 + c * 64 + kh * 8 + kw));
+    }
+    return;
+  }
   __shared__ uint32_t tile[S2D_Y][16][21];
   const int n = blockIdx.x / (21 / S2D_Y), Y0 = (blockIdx.x - n * (21 / S2D_Y)) * S2D_Y;
   const int t = threadIdx.x;
@@ -153,8 +166,8 @@ cudaError_t launch_a3_transpose(const bf16* a3, bf16* a3t, int frames, cudaStrea
   return cudaGetLastError();
 }
 
-cudaError_t launch_pack_weights(const ParamPtrs& p, bf16* wpack, cudaStream_t st, bf16* wpack_lo) {
-  pack_weights_kernel<<<PACK_BLOCKS_FK + PACK_BLOCKS_FD + PACK_BLOCKS_CONV, 256, 0, st>>>(p, wpack, wpack_lo);
+cudaError_t launch_pack_weights(const ParamPtrs& p, bf16* wpack, cudaStream_t st, bf16* wpack_lo, bool skip_w1k) {
+  pack_weights_kernel<<<PACK_BLOCKS_FK + PACK_BLOCKS_FD + PACK_BLOCKS_CONV, 256, 0, st>>>(p, wpack, wpack_lo, skip_w1k ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -278,11 +291,12 @@ cudaError_t build_tma_maps_lo(const EncoderBuffers& b, int NF, int NB, TmaMapsLo
 }
 
 unsigned long long* g_fused_dbg = nullptr;
-static cudaError_t launch_s2d(const uint8_t* obs, int frames, bf16* xs, cudaStream_t st) {
+static cudaError_t launch_s2d(const uint8_t* obs, int frames, bf16* xs, cudaStream_t st, const float* w1, bf16* w1k, bf16* w1k_lo) {
   static const int ygroup = [] { const char* e = getenv("SRL_S2D_Y"); const int v = e ? atoi(e) : 21; return (v == 3 || v == 7) ? v : 21; }();
-  if (ygroup == 3) SRL_TRY(launch_chain<PDL_SIMT>(obs_s2d_kernel<3>, dim3(frames * 7), dim3(352), 0, st, obs, xs));
-  else if (ygroup == 7) SRL_TRY(launch_chain<PDL_SIMT>(obs_s2d_kernel<7>, dim3(frames * 3), dim3(352), 0, st, obs, xs));
-  else SRL_TRY(launch_chain<PDL_SIMT>(obs_s2d_kernel<21>, dim3(frames), dim3(352), 0, st, obs, xs));
+  constexpr int WB = (32 * 256 + 351) / 352;      // extra blocks that write conv1's weight copy
+  if (ygroup == 3) SRL_TRY(launch_chain<PDL_SIMT>(obs_s2d_kernel<3>, dim3(frames * 7 + WB), dim3(352), 0, st, obs, xs, frames * 7, w1, w1k, w1k_lo));
+  else if (ygroup == 7) SRL_TRY(launch_chain<PDL_SIMT>(obs_s2d_kernel<7>, dim3(frames * 3 + WB), dim3(352), 0, st, obs, xs, frames * 3, w1, w1k, w1k_lo));
+  else SRL_TRY(launch_chain<PDL_SIMT>(obs_s2d_kernel<21>, dim3(frames + WB), dim3(352), 0, st, obs, xs, frames, w1, w1k, w1k_lo));
   return cudaGetLastError();
 }
 
@@ -348,10 +362,10 @@ cudaError_t encoder_forward(const uint8_t* obs, int frames, const ParamPtrs& p, 
     pf.b(PS_ENC_FUSED); SRL_TRY(enc_fused_fwd_launch(q, kPersistentCtas, st)); pf.e(PS_ENC_FUSED);
     if (wait_before_conv1) SRL_TRY(cudaStreamWaitEvent(st, wait_before_conv1, 0));      // conv3 / fc read the packed weights
   } else {
-  pf.b(PS_S2D); SRL_TRY(launch_s2d(obs, frames, buf.xs, st)); pf.e(PS_S2D);
-  { RConv1Fwd::Params q{maps.xs_w, maps.w1k, L.w1k, p.b1, buf.a1, buf.a1_lo, frames, buf.NF, p.w1};
+  pf.b(PS_S2D); SRL_TRY(launch_s2d(obs, frames, buf.xs, st, p.w1, buf.wpack + WPack::W1K, sp ? buf.wpack_lo + WPack::W1K : nullptr)); pf.e(PS_S2D);
+  { RConv1Fwd::Params q{maps.xs_w, maps.w1k, L.w1k, p.b1, buf.a1, buf.a1_lo, frames, buf.NF};
     pf.b(PS_CONV1_FWD); SRL_TRY(res_fwd_launch<RConv1Fwd>(q, cdiv(frames * 441, 128), 2 * kPersistentCtas, st, sp)); pf.e(PS_CONV1_FWD); }
-  if (wait_before_conv1) SRL_TRY(cudaStreamWaitEvent(st, wait_before_conv1, 0));      // conv1 converts its own weights; conv2 is the first reader of the re-packed copies
+  if (wait_before_conv1) SRL_TRY(cudaStreamWaitEvent(st, wait_before_conv1, 0));      // conv1's weight copy comes from the frame-conversion kernel; conv2 is the first reader of the re-packed copies
   { RConv2Fwd::Params q{maps.a1p0_w, maps.a1p1_w, maps.w2k, L.a1p0_w, L.a1p1_w, L.w2k, p.b2, buf.a2, buf.a2_lo, frames};
     pf.b(PS_CONV2_FWD); SRL_TRY(res_fwd_launch<RConv2Fwd>(q, cdiv(frames * 100, 128), kPersistentCtas, st, sp)); pf.e(PS_CONV2_FWD); }
   }

@@ -87,10 +87,6 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
     __syncwarp();
     tmem_alloc(tmem_slot, C::TMEM_COLS);
   }
-  if constexpr (P::W_FROM_MASTER) {      // weights final since the previous step's optimizer: safe before griddepcontrol.wait
-    P::template convert_weights<SPLIT>(p, sW, C::W_HI_BYTES, tid, RES_THREADS);
-    fence_proxy_async_smem();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -100,16 +96,19 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
   if (warp == 4) {
     const uint32_t leader = elect_one_sync();      // converged warp, one elected issuing lane: no vote loop around every TMA instruction
     // the packed weights were complete before the first kernel of the chain started: their load overlaps the previous
-    // kernel's tail; the activations are only touched after pdl_wait()
-    if (leader && !P::W_FROM_MASTER) {
+    // kernel's tail; the activations are only touched after pdl_wait().  (W_AFTER_WAIT: the weights come from the stream predecessor.)
+    auto load_weights = [&]() {
       mbar_arrive_expect_tx(w_full, C::W_BYTES);
       for (int j = 0; j < P::NT; ++j) tma_load_2d(sW + j * P::BN * 128, &p.w, w_full, j * 64, 0);
       if constexpr (SPLIT)
         for (int j = 0; j < P::NT; ++j) tma_load_2d(sW + C::W_HI_BYTES + j * P::BN * 128, &p.w_lo, w_full, j * 64, 0);
-    }
+    };
+    if (leader && !P::W_AFTER_WAIT) load_weights();
     __syncwarp();
     pdl_wait();
     if (leader) pdl_launch();
+    if (leader && P::W_AFTER_WAIT) load_weights();
+    __syncwarp();
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int s = it % STAGES;
@@ -127,7 +126,7 @@ __global__ void __launch_bounds__(RES_THREADS) res_fwd_kernel(const __grid_const
     // (57+ clk) -- profiles/r02_mma_issue_rate.md.  Descriptors are base + constant: the 14-bit address field cannot carry.
     const uint32_t leader = elect_one_sync();
     constexpr uint32_t idesc = make_idesc_bf16(128, P::BN, 0, 0);
-    if constexpr (!P::W_FROM_MASTER) mbar_wait(w_full, 0);
+    mbar_wait(w_full, 0);
     const uint64_t wd = make_smem_desc(smem_u32(sW), 16, 1024);
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {

@@ -32,35 +32,12 @@ struct RConv1Fwd {   // 2x2 s1 over xs (== 8x8 s4 over the frame): taps (kh2,kw2
   static constexpr int KID = 11;        // diagnostics timeline id
   static constexpr int BN = 32, NT = 4, NWIN = 1, WROWS = 128 + 22, STAGES = 4, SPLIT_STAGES = 4;
   static constexpr bool A_LO = false;        // the frames are exact in bf16: only the weights have a low tensor
-  struct Params { SRL_TMAP in0; SRL_TMAP w; SRL_TMAP w_lo; const float* bias; bf16* out; bf16* out_lo; int NF; int NFS; const float* w_master; };   // NF frames now, NFS = frames the a1 planes are strided for
-  // conv1 is the first GEMM of the step: its 32 KB of weights are converted from the fp32 master by the CTA itself (before griddepcontrol.wait,
-  // under the frame conversion's tail) instead of TMA-loading pack_weights_kernel's copy -- the re-pack kernel is then needed only by conv2,
-  // ~20 us into the step, and is off the critical path (profiles/r02_timeline.md: conv1 used to wait ~8 us for it)
-  static constexpr bool W_FROM_MASTER = true;
-  // tile j (= tap (kh2,kw2)): row co (32), k = c*16 + dy*4 + dx  <- W1[co][c][4kh2+dy][4kw2+dx]; a float4 = the 4 dx of one (co,c,kh,kw2)
-  template <int SPLIT>
-  SRL_DEVINL static void convert_weights(const Params& p, uint8_t* sW, int w_hi_bytes, int tid, int nthreads) {
-    for (int q0 = 0; q0 < 2048; q0 += 4 * nthreads) {
-      float4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { const int q = q0 + tid + u * nthreads; if (q < 2048) v[u] = __ldg(reinterpret_cast<const float4*>(p.w_master) + q); }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int q = q0 + tid + u * nthreads;
-        if (q < 2048) {
-          const int co = q >> 6, c = (q >> 4) & 3, kh = (q >> 1) & 7, j = (kh >> 2) * 2 + (q & 1), g = c * 4 + (kh & 3);
-          uint8_t* d = sW + j * 4096 + swz128(co, g >> 1) + (g & 1) * 8;
-          *reinterpret_cast<uint2*>(d) = make_uint2(pack_bf16x2(v[u].x, v[u].y), pack_bf16x2(v[u].z, v[u].w));
-          if constexpr (SPLIT) {
-            const float r0 = v[u].x - __bfloat162float(__float2bfloat16_rn(v[u].x)), r1 = v[u].y - __bfloat162float(__float2bfloat16_rn(v[u].y));
-            const float r2 = v[u].z - __bfloat162float(__float2bfloat16_rn(v[u].z)), r3 = v[u].w - __bfloat162float(__float2bfloat16_rn(v[u].w));
-            *reinterpret_cast<uint2*>(d + w_hi_bytes) = make_uint2(pack_bf16x2(r0, r1), pack_bf16x2(r2, r3));
-          }
-        }
-      }
-    }
-  }
-  SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); }
+  struct Params { SRL_TMAP in0; SRL_TMAP w; SRL_TMAP w_lo; const float* bias; bf16* out; bf16* out_lo; int NF; int NFS; };   // NF frames now, NFS = frames the a1 planes are strided for
+  // conv1's K-major weight copy (w1k) is written by the frame-conversion kernel's extra blocks (obs_s2d_kernel, encoder.cu), not by
+  // pack_weights_kernel: conv1 then depends only on its stream predecessor and never waits for the re-pack (profiles/r02_timeline.md);
+  // the weight tiles are therefore loaded AFTER griddepcontrol.wait
+  static constexpr bool W_AFTER_WAIT = true;
+  SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.in0); tma_prefetch_desc(&p.w); }
   SRL_DEVINL static int num_tiles(const Params& p) { return (p.NF * 441 + 127) >> 7; }
   SRL_DEVINL static constexpr int tap_win(int) { return 0; }
   SRL_DEVINL static constexpr int tap_shift(int j) { return (j >> 1) * 21 + (j & 1); }
@@ -79,8 +56,7 @@ struct RConv1Fwd {   // 2x2 s1 over xs (== 8x8 s4 over the frame): taps (kh2,kw2
 
 struct RConv2Fwd {   // 4x4 s2 over a1: tap j = (kh, kww): plane kh&1, shift (kh>>1)*10 + kww, K-block = (kh, kw in {2kww, 2kww+1}, c)
   static constexpr int KID = 12;        // diagnostics timeline id
-  static constexpr bool W_FROM_MASTER = false;
-  template <int SPLIT, class PP> SRL_DEVINL static void convert_weights(const PP&, uint8_t*, int, int, int) {}
+  static constexpr bool W_AFTER_WAIT = false;
   static constexpr int BN = 64, NT = 8, NWIN = 2, WROWS = 128 + 11, STAGES = 3, SPLIT_STAGES = 1;
   static constexpr bool A_LO = true;
   struct Params { SRL_TMAP in0; SRL_TMAP in1; SRL_TMAP w; SRL_TMAP in0_lo; SRL_TMAP in1_lo; SRL_TMAP w_lo; const float* bias; bf16* out; bf16* out_lo; int NF; };
@@ -105,8 +81,7 @@ struct RConv2Fwd {   // 4x4 s2 over a1: tap j = (kh, kww): plane kh&1, shift (kh
 
 struct RConv3Fwd {   // 3x3 s1 over a2: tap (kh,kw) -> shift kh*9 + kw
   static constexpr int KID = 13;        // diagnostics timeline id
-  static constexpr bool W_FROM_MASTER = false;
-  template <int SPLIT, class PP> SRL_DEVINL static void convert_weights(const PP&, uint8_t*, int, int, int) {}
+  static constexpr bool W_AFTER_WAIT = false;
   static constexpr int BN = 64, NT = 9, NWIN = 1, WROWS = 128 + 20, STAGES = 4, SPLIT_STAGES = 2;
   static constexpr bool A_LO = true;
   struct Params { SRL_TMAP in0; SRL_TMAP w; SRL_TMAP in0_lo; SRL_TMAP w_lo; const float* bias; bf16* out; bf16* out_lo; int NF; };
@@ -129,8 +104,7 @@ struct RConv3Fwd {   // 3x3 s1 over a2: tap (kh,kw) -> shift kh*9 + kw
 // ================================================================================================ dgrad
 struct RConv3Dgrad {   // da2[ih,iw] = sum_{kh,kw} da3g[(ih-kh),(iw-kw)] W3[:, :, kh, kw]: shifts -(kh*9+kw); window starts 20 rows early
   static constexpr int KID = 14;        // diagnostics timeline id
-  static constexpr bool W_FROM_MASTER = false;
-  template <int SPLIT, class PP> SRL_DEVINL static void convert_weights(const PP&, uint8_t*, int, int, int) {}
+  static constexpr bool W_AFTER_WAIT = false;
   static constexpr int BN = 64, NT = 9, NWIN = 1, WROWS = 128 + 20, STAGES = 4, SPLIT_STAGES = 2;
   static constexpr bool A_LO = true;
   struct Params { SRL_TMAP in0; SRL_TMAP w; SRL_TMAP in0_lo; SRL_TMAP w_lo; const bf16* act; bf16* dx; bf16* dx_lo; int NB; };
@@ -154,8 +128,7 @@ struct RConv3Dgrad {   // da2[ih,iw] = sum_{kh,kw} da3g[(ih-kh),(iw-kw)] W3[:, :
 
 struct RConv2Dgrad {   // the 4 stride-parity classes share A (da2g at (i'-kh', j'-kw')): one N = 4 x 32 GEMM; shifts -(kh'*10 + kw')
   static constexpr int KID = 15;        // diagnostics timeline id
-  static constexpr bool W_FROM_MASTER = false;
-  template <int SPLIT, class PP> SRL_DEVINL static void convert_weights(const PP&, uint8_t*, int, int, int) {}
+  static constexpr bool W_AFTER_WAIT = false;
   static constexpr int BN = 128, NT = 4, NWIN = 1, WROWS = 128 + 11, STAGES = 3, SPLIT_STAGES = 2;
   static constexpr bool A_LO = true;
   struct Params { SRL_TMAP in0; SRL_TMAP w; SRL_TMAP in0_lo; SRL_TMAP w_lo; const bf16* act; bf16* dx; bf16* dx_lo; int NB; int NF; };
