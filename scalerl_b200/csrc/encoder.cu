@@ -312,6 +312,12 @@ static int persistent_ctas() {
   return v;
 }
 #define kPersistentCtas persistent_ctas()
+// persistent CTAs of the backward chain's resident-window kernels (conv3 / conv2 dgrad, conv1 wgrad): fewer than one per SM leaves SMs to the
+// lower-priority side-stream wgrads while the chain runs.  SRL_BWD_CTAS overrides (diagnostics).
+static int bwd_ctas() {
+  static const int v = [] { const char* e = getenv("SRL_BWD_CTAS"); int x = e ? atoi(e) : 0; return x < 16 || x > 148 ? 0 : x; }();
+  return v ? v : persistent_ctas() - persistent_ctas() / 9;      // 132 of 148: measured -1.5 us per step at T=20, B=32 (148: 0.1607, 132: 0.1591, 120: 0.1629 ms)
+}
 // CTAs of the conv3 / conv2 weight-gradient kernels (side streams).  SRL_WGRAD_CTAS overrides (diagnostics).
 static int side_wgrad_ctas() {
   static const int v = [] { const char* e = getenv("SRL_WGRAD_CTAS"); int x = e ? atoi(e) : 64; return x < 8 || x > 148 ? 64 : x; }();
@@ -421,14 +427,14 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
   { RConv3Wgrad::Params q{maps.a2_w, maps.da3g_b, L.a2_w, L.da3g_b, buf.wgrad_ws + WS_W3, g.b3, frames * 81, 0};
     p2.b(PS_CONV3_WGRAD); SRL_TRY(res_wgrad_launch<RConv3Wgrad>(q, side_wgrad_ctas(), s2, sp)); p2.e(PS_CONV3_WGRAD); }
   { RConv3Dgrad::Params q{maps.da3g_w, maps.w3d, L.da3g_w, L.w3d, buf.a2, buf.da2, buf.da2_lo, frames};
-    pf.b(PS_CONV3_DGRAD); SRL_TRY(res_fwd_launch<RConv3Dgrad>(q, cdiv(frames * 81, 128), kPersistentCtas, st, sp)); pf.e(PS_CONV3_DGRAD); }
+    pf.b(PS_CONV3_DGRAD); SRL_TRY(res_fwd_launch<RConv3Dgrad>(q, cdiv(frames * 81, 128), bwd_ctas(), st, sp)); pf.e(PS_CONV3_DGRAD); }
   if (fork) { SRL_TRY(cudaEventRecord(ss.ev[2], st)); SRL_TRY(cudaStreamWaitEvent(s3, ss.ev[2], 0)); }
   { RConv2Wgrad::Params q{maps.a1p0_w, maps.a1p1_w, maps.da2g_b, L.a1p0_w, L.a1p1_w, L.da2g_b, buf.wgrad_ws + WS_W2, g.b2, frames * 100, 0};
     p3.b(PS_CONV2_WGRAD); SRL_TRY(res_wgrad_launch<RConv2Wgrad>(q, side_wgrad_ctas(), s3, sp)); p3.e(PS_CONV2_WGRAD); }
   { RConv2Dgrad::Params q{maps.da2g_w, maps.w2d, L.da2g_w, L.w2d, buf.a1, buf.da1, buf.da1_lo, frames, buf.NF};
-    pf.b(PS_CONV2_DGRAD); SRL_TRY(res_fwd_launch<RConv2Dgrad>(q, cdiv(frames * 100, 128), kPersistentCtas, st, sp)); pf.e(PS_CONV2_DGRAD); }
+    pf.b(PS_CONV2_DGRAD); SRL_TRY(res_fwd_launch<RConv2Dgrad>(q, cdiv(frames * 100, 128), bwd_ctas(), st, sp)); pf.e(PS_CONV2_DGRAD); }
   { RConv1Wgrad::Params q{maps.xs_w, maps.da1g_b, L.da1g_b, buf.wgrad_ws + WS_W1, g.b1, frames * 441, 0};
-    pf.b(PS_CONV1_WGRAD); SRL_TRY(res_wgrad_launch<RConv1Wgrad>(q, kPersistentCtas, st, sp)); pf.e(PS_CONV1_WGRAD); }
+    pf.b(PS_CONV1_WGRAD); SRL_TRY(res_wgrad_launch<RConv1Wgrad>(q, bwd_ctas(), st, sp)); pf.e(PS_CONV1_WGRAD); }
   if (fork) {      // join: fc wgrad (phase 2 only: phase 1 was joined by the caller of phase 0), conv3 wgrad, conv2 wgrad
     if (do_fc) { SRL_TRY(cudaStreamWaitEvent(st, ss.ev[4], 0)); }
     SRL_TRY(cudaEventRecord(ss.ev[3], s2)); SRL_TRY(cudaStreamWaitEvent(st, ss.ev[3], 0));
