@@ -450,6 +450,7 @@ static int pack_priority(int least, int greatest) {
 }
 
 static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStream_t st, bool zero_small_grads = false) {
+  const bool zero_small_grads_in = zero_small_grads;      // true = called from the learner step (forward + backward)
   L->pf.st = st;
   pdl_set_active(!L->pf.on);
   // The bf16 operand copies are re-derived from the fp32 master weights at the START of every forward (not at the end
@@ -485,6 +486,15 @@ static int encode_impl(srl_learner* L, const uint8_t* obs, int frames, cudaStrea
     L->pf.e(PS_PACK);
   }
   CU(encoder_forward(obs, frames, L->P, L->buf, L->maps, L->cfg.precision, st, L->pf, packed, &L->maps_lo, L->fused_front), "encoder_forward");
+  // learner step (bf16 mode): a3 -> fc.weight column order for the fc weight-gradient GEMM, on the wgrad side stream right after the fc forward,
+  // i.e. under the column kernel (32 CTAs, the GPU is otherwise idle) instead of in the crowded backward phase
+  L->buf.a3t_ready = false;
+  if (zero_small_grads_in && L->ss.side && !L->pf.on && L->cfg.precision == 0 && L->buf.a3t && !L->cfg.use_lstm) {
+    CU(cudaEventRecord(L->ss.ev[10], st), "fork a3 transpose");
+    CU(cudaStreamWaitEvent(L->ss.side, L->ss.ev[10], 0), "fork a3 transpose");
+    CU(launch_a3_transpose(L->buf.a3, L->buf.a3t, L->cfg.T * L->cfg.B, L->ss.side), "a3_transpose");
+    L->buf.a3t_ready = true;
+  }
   return 0;
 }
 

@@ -412,7 +412,8 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
     { const bool native = !sp && buf.a3t != nullptr;          // bf16 mode: B operand = a3 transposed into fc.weight's column order
       TFcWgrad::Params q{maps.dhm64, native ? maps.a3tm64 : maps.a3m64, L.dhm64, L.a3m64, g.wf, g.bf, frames, native ? 1 : 0};
       p1.b(PS_FC_WGRAD);
-      if (native) SRL_TRY(launch_a3_transpose(buf.a3, buf.a3t, frames, s1));
+      if (native && !buf.a3t_ready) SRL_TRY(launch_a3_transpose(buf.a3, buf.a3t, frames, s1));
+      buf.a3t_ready = false;
       if (sp) SRL_TRY((igemm_tma_launch<TFcWgrad, 1>(q, dim3(1, 4 * 50), s1))); else SRL_TRY((igemm_tma_launch<TFcWgrad, 0>(q, dim3(1, 4 * 50), s1)));
       p1.e(PS_FC_WGRAD); }
     { TFcDgrad::Params q{maps.dhm128, maps.wfd, L.dhm128, L.wfd, buf.a3, buf.da3, buf.da3_lo, frames};

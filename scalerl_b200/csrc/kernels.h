@@ -150,6 +150,7 @@ constexpr int FC_SPLITS = 4;
 struct EncoderBuffers {   // row layouts: see res_problems.cuh
   __nv_bfloat16* xs;                    // space-to-depth bf16 copy of the u8 frames [NF*441][64], 64 = (c,dy,dx)
   __nv_bfloat16 *a1, *a2, *a3;          // a1 [2 planes][NF*100][64], a2 [NF*81][64], a3 [NF*49][64]
+  mutable bool a3t_ready = false;       // the transpose below was already launched for this step (early, under the column kernel: api.cu encode_impl)
   __nv_bfloat16* a3t = nullptr;         // [NF][64*49]: a3 of the learning frames in fc.weight's own column order (c,h,w) -- fc wgrad's B operand (bf16 mode)
   float* hpart;                         // [FC_SPLITS][NF][512] split-K partials of the fc layer
   float* h;                             // [NF][512] fc output (post-ReLU), fp32
@@ -183,6 +184,7 @@ cudaError_t build_tma_maps(const EncoderBuffers& buf, int NF, int NB, TmaMaps* m
 cudaError_t build_tma_maps_lo(const EncoderBuffers& buf, int NF, int NB, TmaMapsLo* maps, const char** why);
 // wpack_lo != nullptr: also the low copies bf16(w - bf16(w)) in the same layouts
 extern unsigned long long* g_fused_dbg;          // SRL_FUSED_DEBUG stamp buffer of the fused encoder front (device memory; 5 x 8 x 8 u64)
+cudaError_t launch_a3_transpose(const __nv_bfloat16* a3, __nv_bfloat16* a3t, int frames, cudaStream_t st);
 cudaError_t launch_pack_weights(const ParamPtrs& p, __nv_bfloat16* wpack, cudaStream_t st, __nv_bfloat16* wpack_lo = nullptr, bool skip_w1k = false);
 // wait_before_conv1: optional event (weight re-pack running on the side stream) that conv1 must wait for
 // mode: 0 = bf16 operands, 1 = fp32-accurate split operands (maps_lo must be valid)
