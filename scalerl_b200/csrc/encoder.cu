@@ -409,12 +409,17 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
   Profiler p1 = pf, p2 = pf, p3 = pf; p1.st = s1; p2.st = s2; p3.st = s3;
   if (do_fc) {
     if (fork) { SRL_TRY(cudaEventRecord(ss.ev[0], st)); SRL_TRY(cudaStreamWaitEvent(s1, ss.ev[0], 0)); }
-    { const bool native = !sp && buf.a3t != nullptr;          // bf16 mode: B operand = a3 transposed into fc.weight's column order
-      TFcWgrad::Params q{maps.dhm64, native ? maps.a3tm64 : maps.a3m64, L.dhm64, L.a3m64, g.wf, g.bf, frames, native ? 1 : 0};
+    { const bool native = !sp && buf.a3t != nullptr;          // bf16 mode: B operand = a3 transposed into fc.weight's column order, 256-column tiles
       p1.b(PS_FC_WGRAD);
-      if (native && !buf.a3t_ready) SRL_TRY(launch_a3_transpose(buf.a3, buf.a3t, frames, s1));
+      if (native) {
+        if (!buf.a3t_ready) SRL_TRY(launch_a3_transpose(buf.a3, buf.a3t, frames, s1));
+        TFcWgradN::Params q{maps.dhm64, maps.a3tm64, g.wf, g.bf, frames};
+        SRL_TRY((igemm_tma_launch<TFcWgradN, 0>(q, dim3(1, 4 * (TFcWgradN::NCT + 1)), s1)));
+      } else {
+        TFcWgrad::Params q{maps.dhm64, maps.a3m64, L.dhm64, L.a3m64, g.wf, g.bf, frames, 0};
+        if (sp) SRL_TRY((igemm_tma_launch<TFcWgrad, 1>(q, dim3(1, 4 * 50), s1))); else SRL_TRY((igemm_tma_launch<TFcWgrad, 0>(q, dim3(1, 4 * 50), s1)));
+      }
       buf.a3t_ready = false;
-      if (sp) SRL_TRY((igemm_tma_launch<TFcWgrad, 1>(q, dim3(1, 4 * 50), s1))); else SRL_TRY((igemm_tma_launch<TFcWgrad, 0>(q, dim3(1, 4 * 50), s1)));
       p1.e(PS_FC_WGRAD); }
     { TFcDgrad::Params q{maps.dhm128, maps.wfd, L.dhm128, L.wfd, buf.a3, buf.da3, buf.da3_lo, frames};
       pf.b(PS_FC_DGRAD);

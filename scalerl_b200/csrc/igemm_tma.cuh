@@ -95,8 +95,10 @@ __global__ void __launch_bounds__(IGT_THREADS) igemm_tma_kernel(const __grid_con
   const int nkb = P::num_kblocks(p, tm, ty);
 
   if constexpr (P::ZERO_INIT) {
-    uint4* z = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < P::STAGES * C::STAGE_BYTES / 16; i += IGT_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    if (P::zero_cta(ty)) {
+      uint4* z = reinterpret_cast<uint4*>(smem);
+      for (int i = tid; i < P::STAGES * C::STAGE_BYTES / 16; i += IGT_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
     P::init_smem(p, tm, ty, smem, C::STAGE_BYTES, tid);
     fence_proxy_async_smem();

@@ -116,6 +116,7 @@ struct TFcWgrad {
   }
   template <int SPLIT>
   SRL_DEVINL static void epilogue16(const Params& p, int tm, int ty, int row, int c0, float (&v)[16]) { epilogue16(p, tm, ty, row, c0, v); }
+  SRL_DEVINL static bool zero_cta(int) { return true; }
   SRL_DEVINL static int num_kblocks(const Params& p, int, int) { return (p.M + 63) >> 6; }
   SRL_DEVINL static void init_smem(const Params&, int, int ty, uint8_t* smem, int stage_bytes, int tid) {
     if ((ty >> 2) == 49)
@@ -138,6 +139,46 @@ struct TFcWgrad {
       } else {
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) p.dw[(size_t)j * 3136 + (c0 + jj) * 49 + hw] = v[jj];
+      }
+    } else if (c0 == 0) {
+      p.db[j] = v[0];
+    }
+  }
+};
+
+// The fc weight gradient in fc.weight's own column order (bf16 mode): B operand = a3t [frames][64*49] (a3 transposed, encoder.cu), one CTA =
+// 128 rows j x 256 CONSECUTIVE columns -> N = 256 MMAs run at the tensor array's own rate (128 clk, section 4.1: N = 64 costs 48 clk for a quarter
+// of the work), dh is re-read 13 times instead of 49, and a thread stores 64 float4 in a row.  grid = (1, 4 * 14): ty = ct*4 + jt; column tile
+// ct < 13 (the last one holds 64 valid columns, the rest of its B tile is never loaded and its columns are not stored), ct == 13 = the bias slice
+// (B block 0 = ones -> column 0 of the accumulator = dbfc).
+struct TFcWgradN {
+  static constexpr int KID = 36;
+  static constexpr bool PREFETCH = false;
+  static constexpr int BN = 256, STAGES = 4, KROWS = 64, NCT = 13;
+  static constexpr bool A_MN = true, B_MN = true, ZERO_INIT = true;
+  struct Params { SRL_TMAP dhm; SRL_TMAP a3tm; float* dw; float* db; int M; };
+  SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.dhm); tma_prefetch_desc(&p.a3tm); }
+  SRL_DEVINL static bool zero_cta(int ty) { return (ty >> 2) == NCT; }          // only the bias slice needs defined B tiles everywhere
+  SRL_DEVINL static int num_kblocks(const Params& p, int, int) { return (p.M + 63) >> 6; }
+  SRL_DEVINL static void init_smem(const Params&, int, int ty, uint8_t* smem, int stage_bytes, int tid) {
+    if ((ty >> 2) == NCT)
+      for (int s = 0; s < STAGES; ++s) fill_ones(smem + s * stage_bytes + 2 * KROWS * 128, KROWS * 128, tid);
+  }
+  SRL_DEVINL static void issue(const Params& p, int, int ty, int kb, uint8_t* sA, uint8_t* sB, uint64_t* bar) {
+    const int ct = ty >> 2, j0 = (ty & 3) * 128;
+    const int nb = ct < NCT ? (ct == NCT - 1 ? 1 : 4) : 0;                       // 64-column blocks of a3t this tile owns (3136 = 12 * 256 + 64)
+    mbar_arrive_expect_tx(bar, (2 + nb) * 64 * 128);
+    tma_load_2d(sA, &p.dhm, bar, j0, kb * 64);
+    tma_load_2d(sA + KROWS * 128, &p.dhm, bar, j0 + 64, kb * 64);
+    for (int q = 0; q < nb; ++q) tma_load_2d(sB + q * KROWS * 128, &p.a3tm, bar, ct * 256 + q * 64, kb * 64);
+  }
+  SRL_DEVINL static void epilogue16(const Params& p, int, int ty, int row, int c0, float (&v)[16]) {
+    const int j = (ty & 3) * 128 + row, ct = ty >> 2, col = ct * 256 + c0;
+    if (ct < NCT) {
+      if (col < 3136) {
+        float4* d = reinterpret_cast<float4*>(p.dw + (size_t)j * 3136 + col);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
     } else if (c0 == 0) {
       p.db[j] = v[0];
