@@ -636,6 +636,7 @@ def _main(real_stdout):
                 'launch': 'one CUDA graph per step (wgrad GEMMs on parallel branches, programmatic dependent launch)'
                           if (world == 1 or peer) else 'CUDA graphs begin|finish|apply; NCCL all-reduce of fc.weight overlaps the conv backward',
                 'numa': numa}
+        # gpu_launches: 18 kernels of this library per step (tests/diag/diag_timeline.py lists them; + 1 memset)
         out = {'metric': 'learner_frames_per_sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': W,
                'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
                'data': 'synthetic', 'config': cfg, 'impl_details': impl,
@@ -648,7 +649,7 @@ def _main(real_stdout):
                        'feeder_value': e2e_value, 'feeder_ms_per_step': e2e_s / K * 1e3, 'feeder_h2d_bytes_per_step': feeder.h2d_bytes,
                        'feeder_api': 'HostBatchFeeder.submit/learn/result (time-major pinned batches, no ring, no weight publish: round-1 e2e)',
                        'h2d_only_ms_per_step': h2d_only_ms, 'eager_launch_ms_per_step': e2e_eager_ms},
-               'gpu_launches': 17 * K, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'losses_finite': losses_finite,
+               'gpu_launches': 18 * K, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'losses_finite': losses_finite,
                'vtrace_standalone': vtrace, 'other_configs': extra_cfg, 'per_sampler': per}
         emit(real_stdout, out)
     trainer.close() if False else None
