@@ -9,17 +9,18 @@
 //   warp 16     producer: ONE cp.async.bulk (1-D TMA) per frame, 28,224 contiguous bytes of u8 -> shared memory, double-buffered
 //               (frame f+1 lands while frame f is being computed)
 //   warps 8-15  converters: u8 -> bf16 space-to-depth operand tile of conv1 (128 output positions + 22 halo rows of the 21x21
-//               grid, 64 channels (c,dy,dx), SWIZZLE_128B) written with generic stores + fence.proxy.async; two tiles in flight;
+//               grid, 64 channels (c,dy,dx), SWIZZLE_128B) written with generic stores + fence.proxy.async; three tile stages;
 //               the same values go to global `xs`
-//   warps 17/18 TWO tcgen05.mma issuers (one thread each): conv1 = 4 position tiles x (4 taps x 4 K-steps), N = 32, four TMEM
+//   warps 17/18 TWO tcgen05.mma issuers (converged warps, one elect.sync lane each): conv1 = 4 position tiles x (4 taps x 4 K-steps), N = 32, four TMEM
 //               accumulators; conv2 = 8 taps x 4 K-steps, N = 64, reading conv1's output from SHARED memory (the two row-parity
-//               planes of the layout in res_problems.cuh, so a stride-2 tap is a row shift).  Two issuers because one thread
-//               cannot keep the pipe busy with N <= 64 MMAs (56 clk each from one issuer, 40-48 in aggregate from two:
-//               profiles/r02_mma_issue_rate.md) and because conv2(f) must not queue behind conv1(f+1).
+//               planes of the layout in res_problems.cuh, so a stride-2 tap is a row shift).  Two issuers so that conv2(f) does not
+//               queue behind conv1(f+1) (issue cost: profiles/r02_mma_issue_rate.md).
 //   warps 0-3   conv1 epilogue: TMEM -> registers -> (x/255 + b1, ReLU) -> bf16 -> shared a1 planes + global a1
 //   warps 4-7   conv2 epilogue: (+ b2, ReLU) -> global a2
 // The conv weights are converted from the fp32 master parameters inside the prologue (80 KB of bf16 per CTA, from L2), so the
 // kernel does not depend on pack_weights_kernel -- that kernel (needed by conv3 / fc) runs beside it.
+// Opt-in (SRL_FUSED_FWD=1): bit-identical to the three kernels, 39.6 us against their 48 us stand-alone, but 1.7 us slower per step inside
+// the graph (profiles/r02_fused_front_timeline.md: one SM's shared-memory bandwidth is shared by the MMA operand reads, converters, epilogues).
 #pragma once
 #include "igemm_tma.cuh"
 #include "encoder_problems.cuh"

@@ -416,7 +416,7 @@ cudaError_t encoder_backward(const uint8_t* obs, int frames, const EncoderBuffer
         TFcWgradN::Params q{maps.dhm64, maps.a3tm64, g.wf, g.bf, frames};
         SRL_TRY((igemm_tma_launch<TFcWgradN, 0>(q, dim3(1, 4 * (TFcWgradN::NCT + 1)), s1)));
       } else {
-        TFcWgrad::Params q{maps.dhm64, maps.a3m64, L.dhm64, L.a3m64, g.wf, g.bf, frames, 0};
+        TFcWgrad::Params q{maps.dhm64, maps.a3m64, L.dhm64, L.a3m64, g.wf, g.bf, frames};
         if (sp) SRL_TRY((igemm_tma_launch<TFcWgrad, 1>(q, dim3(1, 4 * 50), s1))); else SRL_TRY((igemm_tma_launch<TFcWgrad, 0>(q, dim3(1, 4 * 50), s1)));
       }
       buf.a3t_ready = false;

@@ -94,12 +94,13 @@ SRL_DEVINL void fill_ones(uint8_t* dst, int bytes, int tid) {   // bf16 1.0 = 0x
   for (int i = tid; i < bytes / 16; i += IGT_THREADS) q[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
 }
 
+// (h,w,c)-ordered column tiles: used by the fp32-accurate split mode only (no low twin of a3t); the bf16 mode runs TFcWgradN below
 struct TFcWgrad {
   static constexpr int KID = 33;        // diagnostics timeline id
   static constexpr bool PREFETCH = false;   // grid = (1, 4*50): ty = hw*4 + jt, hw == 49 is the ones slice (B = ones -> dbfc); stage = 64 frames
   static constexpr int BN = 64, STAGES = 4, KROWS = 64;
   static constexpr bool A_MN = true, B_MN = true, ZERO_INIT = true;
-  struct Params { SRL_TMAP dhm; SRL_TMAP a3m; SRL_TMAP dhm_lo; SRL_TMAP a3m_lo; float* dw; float* db; int M; int native; };   // native: a3m maps a3t (columns in fc.weight order)
+  struct Params { SRL_TMAP dhm; SRL_TMAP a3m; SRL_TMAP dhm_lo; SRL_TMAP a3m_lo; float* dw; float* db; int M; };
   SRL_DEVINL static void prefetch(const Params& p) { tma_prefetch_desc(&p.dhm); tma_prefetch_desc(&p.a3m); }
   // split mode: the ones slice keeps B lo = 0 (zero-initialised once, never loaded), so only dh hi/lo . ones contribute
   SRL_DEVINL static void issue_split(const Params& p, int, int ty, int kb, uint8_t* st, int a_bytes, int half, uint64_t* bar) {
@@ -132,14 +133,8 @@ struct TFcWgrad {
   SRL_DEVINL static void epilogue16(const Params& p, int, int ty, int row, int c0, float (&v)[16]) {
     const int j = (ty & 3) * 128 + row, hw = ty >> 2;
     if (hw < 49) {
-      if (p.native) {          // column tile hw = 64 consecutive columns of fc.weight's own order
-        float4* d = reinterpret_cast<float4*>(p.dw + (size_t)j * 3136 + hw * 64 + c0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      } else {
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) p.dw[(size_t)j * 3136 + (c0 + jj) * 49 + hw] = v[jj];
-      }
+      for (int jj = 0; jj < 16; ++jj) p.dw[(size_t)j * 3136 + (c0 + jj) * 49 + hw] = v[jj];
     } else if (c0 == 0) {
       p.db[j] = v[0];
     }

@@ -104,6 +104,13 @@ def test_argument_errors_without_gpu(lib):
     assert b'A=99' in L.srl_last_error()
 
 
+def test_timeline_entry_is_inert_in_the_product_build(lib):
+    """srl_debug_kernel_timeline only works in a diagnostics build (SRL_DEFINES=SRL_KSTAMP): the shipped library refuses, without touching CUDA"""
+    L = _lib.lib()
+    assert L.srl_debug_kernel_timeline(None) != 0
+    assert b'SRL_KSTAMP' in L.srl_last_error()
+
+
 def test_product_path_has_no_oracle_import():
     """the shipped package must never import the oracle or fall back to CPU"""
     pkg = os.path.join(ROOT, 'scalerl_b200')
